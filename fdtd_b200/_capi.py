@@ -1,0 +1,107 @@
+"""ctypes binding of include/fdtd_b200.h (the C ABI of the CUDA engine).
+
+The product opens exactly one library, fdtd_b200/libfdtd_b200.so (nvcc, sm_100a), and fails
+loudly when it is missing: there is no CPU or PyTorch fallback for the hot path.
+"""
+import ctypes as C
+import os
+
+ABI_VERSION = 3
+MAX_SLABS, MAX_POST, MAX_SOURCES, MAX_DETECTORS = 6, 16, 64, 64
+F32, F64 = 0, 1
+CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT = 1, 2, 4, 8
+POST_PERIODIC, POST_PML_ADD = 0, 1
+SRC_POINTS, SRC_BOX = 0, 1
+
+_vp = C.c_void_p
+
+
+class Slab(C.Structure):
+    _fields_ = [("axis", C.c_int32), ("lo", C.c_int32), ("thickness", C.c_int32), ("fused", C.c_int32),
+                ("x0", C.c_int32), ("x1", C.c_int32), ("psi_count", C.c_int64),
+                ("psi_E", _vp), ("psi_H", _vp), ("bE", _vp), ("cE", _vp), ("bH", _vp), ("cH", _vp)]
+
+
+class Source(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("field", C.c_int32), ("comp", C.c_int32), ("n", C.c_int32),
+                ("idx", _vp), ("profile", _vp), ("amplitude", C.c_double), ("box", C.c_int32 * 6),
+                ("wave", _vp), ("wave_q0", C.c_int64), ("wave_len", C.c_int64)]
+
+
+class Detector(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pad_", C.c_int32), ("idx", _vp), ("ring_E", _vp), ("ring_H", _vp),
+                ("capacity", C.c_int64)]
+
+
+class Desc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("dtype", C.c_int32),
+                ("Nx", C.c_int32), ("Ny", C.c_int32), ("Nz", C.c_int32),
+                ("x_offset", C.c_int32), ("Nx_global", C.c_int32), ("pad0_", C.c_int32),
+                ("plane", C.c_int64),
+                ("E", _vp * 3), ("H", _vp * 3),
+                ("courant", C.c_double), ("bg_inv_eps", C.c_double * 3), ("bg_inv_mu", C.c_double * 3),
+                ("inv_eps", _vp * 3), ("inv_eps_grid", _vp * 3), ("absorb", _vp * 3), ("inv_mu", _vp * 3),
+                ("tile_class", _vp), ("tile_y", C.c_int32), ("tile_z", C.c_int32),
+                ("n_slabs", C.c_int32), ("n_post", C.c_int32),
+                ("slabs", Slab * MAX_SLABS),
+                ("post_kind", C.c_int32 * MAX_POST), ("post_arg", C.c_int32 * MAX_POST),
+                ("n_sources", C.c_int32), ("n_detectors", C.c_int32),
+                ("sources", Source * MAX_SOURCES), ("detectors", Detector * MAX_DETECTORS),
+                ("x_chunk", C.c_int32), ("pad1_", C.c_int32)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "fdtd_abi_version": (C.c_int32, []),
+    "fdtd_sizeof_desc": (C.c_int64, []),
+    "fdtd_last_error": (C.c_char_p, []),
+    "fdtd_launch_count": (C.c_int64, []),
+    "fdtd_tile_shape": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "fdtd_validate": (C.c_int, [C.POINTER(Desc)]),
+    "fdtd_e_halfstep": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_int32, _vp]),
+    "fdtd_h_halfstep": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_int32, _vp]),
+    "fdtd_post_E": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),
+    "fdtd_post_H": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),
+    "fdtd_update_E": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),
+    "fdtd_update_H": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),
+    "fdtd_run": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, C.c_int64, _vp]),
+}
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfdtd_b200.so")
+
+
+def bind(path):
+    """open a build of the C ABI and attach prototypes; checks ABI version and struct layout."""
+    lib = C.CDLL(path)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is missing
+        fn.restype, fn.argtypes = res, args
+    if lib.fdtd_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{path}: ABI {lib.fdtd_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+    if lib.fdtd_sizeof_desc() != C.sizeof(Desc):
+        raise RuntimeError(f"{path}: sizeof(fdtd_desc) {lib.fdtd_sizeof_desc()} != binding {C.sizeof(Desc)}")
+    return lib
+
+
+_lib = None
+
+
+def load():
+    """the CUDA library; RuntimeError (never a fallback) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is not built "
+                "(python -c 'import __graft_entry__ as g; g.build()'). fdtd_b200 has no CPU fallback.")
+        _lib = bind(LIB_PATH)
+    return _lib
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def check(lib, rc):
+    if rc != 0:
+        raise EngineError(f"fdtd_b200 C-ABI error {rc}: {lib.fdtd_last_error().decode()}")

@@ -1,0 +1,419 @@
+// fdtd_b200.cu -- C ABI (include/fdtd_b200.h) over the sm_100a Yee kernels.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//        -shared -Xcompiler -fPIC -Iinclude fdtd_b200/csrc/fdtd_b200.cu -o fdtd_b200/libfdtd_b200.so
+// (see __graft_entry__.build()).  The same file compiles as plain C++ with -DFDTD_EMU
+// against tests/emu/cuda_emu.h: a serial thread-by-thread interpreter of the kernels used
+// ONLY by the CPU test-suite to exercise the kernel logic where there is no GPU.  The
+// product library never contains that path.
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "fdtd_b200.h"
+
+#ifdef FDTD_EMU
+#include "cuda_emu.h"
+#define FDTD_DEV inline
+#define FDTD_LAUNCH(kern, grid, block, stream, ...) \
+  emu::launch(grid, block, [&]() { kern(__VA_ARGS__); })
+template <typename T>
+inline void fdtd_atomic_add(T* p, T v) { *p = *p + v; }
+#else
+#include <cuda_runtime.h>
+#define FDTD_DEV __device__ __forceinline__
+#define FDTD_LAUNCH(kern, grid, block, stream, ...) \
+  kern<<<grid, block, 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+template <typename T>
+__device__ __forceinline__ void fdtd_atomic_add(T* p, T v) { atomicAdd(p, v); }
+#endif
+
+#include "yee_kernels.cuh"
+
+namespace {
+
+using fdtd::i64;
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FDTD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return FDTD_OK;
+}
+
+struct Geometry {
+  int vec;          // cells per thread
+  int lanes_z;      // threads along z in a block (power of two)
+  int lanes_shift;
+  int rows;         // y rows per block (power of two)
+  int tile_y, tile_z;
+};
+
+int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+Geometry geometry(int dtype, int Ny, int Nz) {
+  Geometry g;
+  if (dtype == FDTD_F32)
+    g.vec = (Nz % 4 == 0) ? 4 : ((Nz % 2 == 0) ? 2 : 1);
+  else
+    g.vec = (Nz % 2 == 0) ? 2 : 1;
+  int nvz = (Nz + g.vec - 1) / g.vec;
+  g.lanes_z = pow2_ceil(nvz);
+  if (g.lanes_z > 32) g.lanes_z = 32;
+  g.lanes_shift = 0;
+  while ((1 << g.lanes_shift) < g.lanes_z) ++g.lanes_shift;
+  g.rows = 256 / g.lanes_z;
+  int ny2 = pow2_ceil(Ny);
+  if (g.rows > ny2) g.rows = ny2;
+  g.tile_y = g.rows;
+  g.tile_z = g.lanes_z * g.vec;
+  return g;
+}
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+int validate(const fdtd_desc* d) {
+  if (!d) return fail(FDTD_ERR_ARG, "null descriptor");
+  if (d->abi_version != FDTD_ABI_VERSION)
+    return fail(FDTD_ERR_ARG, "descriptor ABI %d != library ABI %d", d->abi_version, FDTD_ABI_VERSION);
+  if (d->dtype != FDTD_F32 && d->dtype != FDTD_F64) return fail(FDTD_ERR_ARG, "bad dtype %d", d->dtype);
+  if (d->Nx < 1 || d->Ny < 1 || d->Nz < 1) return fail(FDTD_ERR_ARG, "bad extents");
+  if (d->plane != (int64_t)d->Ny * d->Nz) return fail(FDTD_ERR_ARG, "plane != Ny*Nz");
+  if (d->x_offset < 0 || d->x_offset + d->Nx > d->Nx_global)
+    return fail(FDTD_ERR_ARG, "slab [%d,%d) outside global Nx=%d", d->x_offset, d->x_offset + d->Nx, d->Nx_global);
+  Geometry g = geometry(d->dtype, d->Ny, d->Nz);
+  size_t w = d->dtype == FDTD_F32 ? 4 : 8;
+  for (int c = 0; c < 3; ++c) {
+    if (!d->E[c] || !d->H[c]) return fail(FDTD_ERR_ARG, "null field pointer");
+    if (!aligned(d->E[c], w * g.vec) || !aligned(d->H[c], w * g.vec))
+      return fail(FDTD_ERR_ARG, "field pointer not aligned to %zu bytes", w * g.vec);
+    const void* opt[4] = {d->inv_eps[c], d->inv_eps_grid[c], d->absorb[c], d->inv_mu[c]};
+    for (int n = 0; n < 4; ++n)
+      if (opt[n] && !aligned(opt[n], w * g.vec)) return fail(FDTD_ERR_ARG, "material pointer misaligned");
+  }
+  bool any_e = d->inv_eps[0] || d->inv_eps[1] || d->inv_eps[2];
+  bool all_e = d->inv_eps[0] && d->inv_eps[1] && d->inv_eps[2];
+  bool any_m = d->inv_mu[0] || d->inv_mu[1] || d->inv_mu[2];
+  bool all_m = d->inv_mu[0] && d->inv_mu[1] && d->inv_mu[2];
+  if (any_e != all_e || any_m != all_m) return fail(FDTD_ERR_ARG, "material arrays must be given for all 3 components");
+  if (d->tile_class && (d->tile_y != g.tile_y || d->tile_z != g.tile_z))
+    return fail(FDTD_ERR_ARG, "tile_class laid out for %dx%d tiles, kernels use %dx%d", d->tile_y, d->tile_z,
+                g.tile_y, g.tile_z);
+  if (d->n_slabs < 0 || d->n_slabs > FDTD_MAX_SLABS) return fail(FDTD_ERR_ARG, "n_slabs");
+  for (int s = 0; s < d->n_slabs; ++s) {
+    const fdtd_slab& S = d->slabs[s];
+    int n_axis = S.axis == 0 ? d->Nx_global : (S.axis == 1 ? d->Ny : d->Nz);
+    if (S.axis < 0 || S.axis > 2 || S.thickness < 1 || S.lo < 0 || S.lo + S.thickness > n_axis)
+      return fail(FDTD_ERR_ARG, "slab %d geometry", s);
+    if (S.x0 < 0 || S.x1 > d->Nx || S.x0 > S.x1) return fail(FDTD_ERR_ARG, "slab %d x-range", s);
+    i64 want = S.axis == 0 ? (i64)(S.x1 - S.x0) * d->plane
+                           : (S.axis == 1 ? (i64)d->Nx * S.thickness * d->Nz : (i64)d->Nx * d->Ny * S.thickness);
+    if (S.psi_count != want) return fail(FDTD_ERR_ARG, "slab %d psi_count %lld != %lld", s, (long long)S.psi_count, want);
+    if (want > 0 && (!S.psi_E || !S.psi_H || !S.bE || !S.cE || !S.bH || !S.cH))
+      return fail(FDTD_ERR_ARG, "slab %d null pointer", s);
+    if (S.axis != 2 && want > 0 && (!aligned(S.psi_E, w * g.vec) || !aligned(S.psi_H, w * g.vec)))
+      return fail(FDTD_ERR_ARG, "slab %d psi misaligned", s);
+  }
+  if (d->n_post < 0 || d->n_post > FDTD_MAX_POST) return fail(FDTD_ERR_ARG, "n_post");
+  for (int n = 0; n < d->n_post; ++n) {
+    if (d->post_kind[n] == FDTD_POST_PERIODIC) {
+      if (d->post_arg[n] < 0 || d->post_arg[n] > 2) return fail(FDTD_ERR_ARG, "periodic axis");
+      if (d->post_arg[n] == 0 && d->Nx != d->Nx_global)
+        return fail(FDTD_ERR_UNSUPPORTED, "periodic x boundary on an x-sharded grid");
+    } else if (d->post_kind[n] == FDTD_POST_PML_ADD) {
+      if (d->post_arg[n] < 0 || d->post_arg[n] >= d->n_slabs) return fail(FDTD_ERR_ARG, "post slab index");
+    } else {
+      return fail(FDTD_ERR_ARG, "post kind");
+    }
+  }
+  if (d->n_sources < 0 || d->n_sources > FDTD_MAX_SOURCES) return fail(FDTD_ERR_ARG, "n_sources");
+  for (int n = 0; n < d->n_sources; ++n) {
+    const fdtd_source& S = d->sources[n];
+    if (S.field < 0 || S.field > 1 || S.comp < 0 || S.comp > 2) return fail(FDTD_ERR_ARG, "source %d field/comp", n);
+    if (S.kind == FDTD_SRC_POINTS) {
+      if (S.n < 0 || (S.n > 0 && (!S.idx || !S.profile))) return fail(FDTD_ERR_ARG, "source %d points", n);
+    } else if (S.kind == FDTD_SRC_BOX) {
+      if (S.box[0] < 0 || S.box[1] > d->Nx || S.box[2] < 0 || S.box[3] > d->Ny || S.box[4] < 0 || S.box[5] > d->Nz)
+        return fail(FDTD_ERR_ARG, "source %d box", n);
+    } else {
+      return fail(FDTD_ERR_ARG, "source %d kind", n);
+    }
+    if (!S.wave || S.wave_len < 1) return fail(FDTD_ERR_ARG, "source %d wave table", n);
+  }
+  if (d->n_detectors < 0 || d->n_detectors > FDTD_MAX_DETECTORS) return fail(FDTD_ERR_ARG, "n_detectors");
+  for (int n = 0; n < d->n_detectors; ++n) {
+    const fdtd_detector& D = d->detectors[n];
+    if (D.n < 0 || (D.n > 0 && (!D.idx || !D.ring_E || !D.ring_H || D.capacity < 1)))
+      return fail(FDTD_ERR_ARG, "detector %d", n);
+  }
+  return FDTD_OK;
+}
+
+template <typename T>
+T rounded_product(double a, double b) {
+  // sc * inverse material as the reference computes it: both operands in the grid dtype
+  return (T)((T)a * (T)b);
+}
+
+template <typename T, bool IS_E>
+fdtd::SlabK<T> slab_k(const fdtd_slab& S) {
+  fdtd::SlabK<T> k;
+  k.axis = S.axis;
+  k.lo = S.lo;
+  k.t = S.thickness;
+  k.fused = S.fused;
+  k.x0 = S.x0;
+  k.x1 = S.x1;
+  k.count = S.psi_count;
+  k.psi = (T*)(IS_E ? S.psi_E : S.psi_H);
+  k.b = (const T*)(IS_E ? S.bE : S.bH);
+  k.c = (const T*)(IS_E ? S.cE : S.cH);
+  return k;
+}
+
+template <typename T, bool IS_E>
+int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, void* stream) {
+  if (x_begin < 0 || x_end > d->Nx || x_begin > x_end) return fail(FDTD_ERR_ARG, "plane range [%d,%d)", x_begin, x_end);
+  if (x_begin == x_end) return FDTD_OK;
+  Geometry g = geometry(d->dtype, d->Ny, d->Nz);
+  fdtd::HalfStepParams<T> P;
+  memset(&P, 0, sizeof(P));
+  P.Nx = d->Nx;
+  P.Ny = d->Ny;
+  P.Nz = d->Nz;
+  P.x_offset = d->x_offset;
+  P.Nx_global = d->Nx_global;
+  P.x_begin = x_begin;
+  P.x_end = x_end;
+  P.x_chunk = d->x_chunk > 0 ? d->x_chunk : 32;
+  P.lanes_z = g.lanes_z;
+  P.lanes_shift = g.lanes_shift;
+  P.rows = g.rows;
+  P.plane = d->plane;
+  P.sc = (T)d->courant;
+  for (int c = 0; c < 3; ++c) {
+    P.F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
+    P.G[c] = (const T*)(IS_E ? d->H[c] : d->E[c]);
+    P.bg_c[c] = rounded_product<T>(d->courant, IS_E ? d->bg_inv_eps[c] : d->bg_inv_mu[c]);
+    P.inv[c] = (const T*)(IS_E ? d->inv_eps[c] : d->inv_mu[c]);
+    P.inv_grid[c] = IS_E ? (const T*)d->inv_eps_grid[c] : nullptr;
+    P.absorb[c] = IS_E ? (const T*)d->absorb[c] : nullptr;
+  }
+  // a class map is only meaningful with the arrays it refers to
+  P.cls = d->tile_class;
+  P.cls_vary = (P.inv[0] != nullptr) ? (IS_E ? FDTD_CLS_VARY_E : FDTD_CLS_VARY_H) : 0;
+  if (P.inv[0] != nullptr && P.cls == nullptr) return fail(FDTD_ERR_ARG, "material arrays need a tile_class map");
+  P.n_slabs = d->n_slabs;
+  for (int s = 0; s < d->n_slabs; ++s) P.slabs[s] = slab_k<T, IS_E>(d->slabs[s]);
+
+  int chunks = (x_end - x_begin + P.x_chunk - 1) / P.x_chunk;
+  dim3 grid((d->Nz + g.tile_z - 1) / g.tile_z, (d->Ny + g.tile_y - 1) / g.tile_y, chunks);
+  dim3 block(g.lanes_z * g.rows);
+  if (grid.y > 65535u || grid.z > 65535u) return fail(FDTD_ERR_UNSUPPORTED, "grid too large for one launch");
+  switch (g.vec) {
+    case 4:
+      if constexpr (sizeof(T) == 4) {
+        FDTD_LAUNCH((fdtd::halfstep_kernel<T, 4, IS_E>), grid, block, stream, P);
+      }
+      break;
+    case 2:
+      FDTD_LAUNCH((fdtd::halfstep_kernel<T, 2, IS_E>), grid, block, stream, P);
+      break;
+    default:
+      FDTD_LAUNCH((fdtd::halfstep_kernel<T, 1, IS_E>), grid, block, stream, P);
+  }
+  return check_launch(IS_E ? "e_halfstep" : "h_halfstep");
+}
+
+int blocks_for(i64 n, int threads = 256) {
+  i64 b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)b;
+}
+
+template <typename T, bool IS_E>
+int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
+  T* F[3];
+  for (int c = 0; c < 3; ++c) F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
+  // 1. periodic copies and late PML corrections, registration order (fdtd/grid.py:290-291, 316-317)
+  for (int n = 0; n < d->n_post; ++n) {
+    if (d->post_kind[n] == FDTD_POST_PERIODIC) {
+      int axis = d->post_arg[n];
+      int N = axis == 0 ? d->Nx : (axis == 1 ? d->Ny : d->Nz);
+      if (N < 2) continue;  // E[0] = E[-1] on a one-cell axis is the identity
+      int src = IS_E ? N - 1 : 0, dst = IS_E ? 0 : N - 1;
+      i64 cells = (axis == 0 ? (i64)d->Ny * d->Nz : (axis == 1 ? (i64)d->Nx * d->Nz : (i64)d->Nx * d->Ny));
+      FDTD_LAUNCH((fdtd::periodic_kernel<T>), dim3(blocks_for(cells * 3)), dim3(256), stream, F[0], F[1], F[2],
+                  axis, d->Nx, d->Ny, d->Nz, d->plane, src, dst);
+      int rc = check_launch("periodic");
+      if (rc) return rc;
+    } else {
+      const fdtd_slab& S = d->slabs[d->post_arg[n]];
+      if (S.psi_count == 0) continue;
+      const T* c[3];
+      T bg[3];
+      for (int k = 0; k < 3; ++k) {
+        if (IS_E)
+          c[k] = (const T*)(d->inv_eps_grid[k] ? d->inv_eps_grid[k] : d->inv_eps[k]);
+        else
+          c[k] = (const T*)d->inv_mu[k];
+        bg[k] = rounded_product<T>(d->courant, IS_E ? d->bg_inv_eps[k] : d->bg_inv_mu[k]);
+      }
+      FDTD_LAUNCH((fdtd::pml_add_kernel<T, IS_E>), dim3(blocks_for(S.psi_count)), dim3(256), stream,
+                  slab_k<T, IS_E>(S), F[0], F[1], F[2], c[0], c[1], c[2], bg[0], bg[1], bg[2], (T)d->courant,
+                  d->Nx, d->Ny, d->Nz, d->plane);
+      int rc = check_launch("pml_add");
+      if (rc) return rc;
+    }
+  }
+  // 2. sources, registration order (fdtd/grid.py:294-295, 320-321)
+  for (int n = 0; n < d->n_sources; ++n) {
+    const fdtd_source& S = d->sources[n];
+    if (S.field != (IS_E ? 0 : 1)) continue;
+    int64_t w = q - S.wave_q0;
+    if (w < 0 || w >= S.wave_len)
+      return fail(FDTD_ERR_ARG, "source %d: step %lld outside its waveform table [%lld,%lld)", n, (long long)q,
+                  (long long)S.wave_q0, (long long)(S.wave_q0 + S.wave_len));
+    if (S.kind == FDTD_SRC_POINTS) {
+      if (S.n == 0) continue;
+      FDTD_LAUNCH((fdtd::source_points_kernel<T>), dim3(blocks_for(S.n)), dim3(256), stream, F[S.comp],
+                  (const i64*)S.idx, (const T*)S.profile, S.n, (const T*)S.wave, (i64)w);
+    } else {
+      i64 cells = (i64)(S.box[1] - S.box[0]) * (S.box[3] - S.box[2]) * (S.box[5] - S.box[4]);
+      if (cells <= 0) continue;
+      FDTD_LAUNCH((fdtd::source_box_kernel<T>), dim3(blocks_for(cells)), dim3(256), stream, F[S.comp], S.box[0],
+                  S.box[1], S.box[2], S.box[3], S.box[4], S.box[5], d->Nz, d->plane, (T)S.amplitude,
+                  (const T*)S.wave, (i64)w);
+    }
+    int rc = check_launch("source");
+    if (rc) return rc;
+  }
+  // 3. detectors (fdtd/grid.py:298-299, 324-325)
+  for (int n = 0; n < d->n_detectors; ++n) {
+    const fdtd_detector& D = d->detectors[n];
+    if (D.n == 0) continue;
+    if (slot < 0 || slot >= D.capacity)
+      return fail(FDTD_ERR_ARG, "detector %d: ring slot %lld outside capacity %lld", n, (long long)slot,
+                  (long long)D.capacity);
+    FDTD_LAUNCH((fdtd::detector_kernel<T>), dim3(blocks_for((i64)D.n * 3)), dim3(256), stream, F[0], F[1], F[2],
+                (const i64*)D.idx, D.n, (T*)(IS_E ? D.ring_E : D.ring_H), (i64)slot);
+    int rc = check_launch("detector");
+    if (rc) return rc;
+  }
+  return FDTD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t fdtd_abi_version(void) { return FDTD_ABI_VERSION; }
+
+int64_t fdtd_sizeof_desc(void) { return (int64_t)sizeof(fdtd_desc); }
+
+const char* fdtd_last_error(void) { return g_err; }
+
+int64_t fdtd_launch_count(void) { return g_launches.load(); }
+
+int fdtd_tile_shape(int32_t dtype, int32_t Ny, int32_t Nz, int32_t* tile_y, int32_t* tile_z) {
+  if ((dtype != FDTD_F32 && dtype != FDTD_F64) || Ny < 1 || Nz < 1 || !tile_y || !tile_z)
+    return fail(FDTD_ERR_ARG, "fdtd_tile_shape: bad argument");
+  Geometry g = geometry(dtype, Ny, Nz);
+  *tile_y = g.tile_y;
+  *tile_z = g.tile_z;
+  return FDTD_OK;
+}
+
+int fdtd_validate(const fdtd_desc* d) { return validate(d); }
+
+int fdtd_e_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  return d->dtype == FDTD_F32 ? launch_halfstep<float, true>(d, x_begin, x_end, stream)
+                              : launch_halfstep<double, true>(d, x_begin, x_end, stream);
+}
+
+int fdtd_h_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  return d->dtype == FDTD_F32 ? launch_halfstep<float, false>(d, x_begin, x_end, stream)
+                              : launch_halfstep<double, false>(d, x_begin, x_end, stream);
+}
+
+int fdtd_post_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  return d->dtype == FDTD_F32 ? launch_post<float, true>(d, q, slot, stream)
+                              : launch_post<double, true>(d, q, slot, stream);
+}
+
+int fdtd_post_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  return d->dtype == FDTD_F32 ? launch_post<float, false>(d, q, slot, stream)
+                              : launch_post<double, false>(d, q, slot, stream);
+}
+
+static int update_E_nocheck(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
+  int rc = d->dtype == FDTD_F32 ? launch_halfstep<float, true>(d, 0, d->Nx, stream)
+                                : launch_halfstep<double, true>(d, 0, d->Nx, stream);
+  if (rc) return rc;
+  return d->dtype == FDTD_F32 ? launch_post<float, true>(d, q, slot, stream)
+                              : launch_post<double, true>(d, q, slot, stream);
+}
+
+static int update_H_nocheck(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
+  int rc = d->dtype == FDTD_F32 ? launch_halfstep<float, false>(d, 0, d->Nx, stream)
+                                : launch_halfstep<double, false>(d, 0, d->Nx, stream);
+  if (rc) return rc;
+  return d->dtype == FDTD_F32 ? launch_post<float, false>(d, q, slot, stream)
+                              : launch_post<double, false>(d, q, slot, stream);
+}
+
+int fdtd_update_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  return update_E_nocheck(d, q, slot, stream);
+}
+
+int fdtd_update_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  return update_H_nocheck(d, q, slot, stream);
+}
+
+int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (nsteps < 0) return fail(FDTD_ERR_ARG, "nsteps < 0");
+  if (d->Nx != d->Nx_global && nsteps > 0)
+    return fail(FDTD_ERR_UNSUPPORTED, "fdtd_run on an x-sharded slab: drive the half-steps and the halo exchange per step");
+  for (int64_t s = 0; s < nsteps; ++s) {
+    rc = update_E_nocheck(d, q0 + s, slot0 + s, stream);
+    if (rc) return rc;
+    rc = update_H_nocheck(d, q0 + s, slot0 + s, stream);
+    if (rc) return rc;
+  }
+  return FDTD_OK;
+}
+
+}  // extern "C"

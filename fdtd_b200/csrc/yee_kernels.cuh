@@ -1,0 +1,479 @@
+// yee_kernels.cuh -- sm_100a kernels of the fused Yee half-steps.
+//
+// One kernel per half-step (template IS_E selects E or H).  A thread owns VEC
+// consecutive z-cells of one (y) row and marches along x over a chunk of planes,
+// carrying the x-neighbour plane in registers, so that every field word crosses
+// HBM once per half-step: 128-bit coalesced loads of the own cells, the y-neighbour
+// row (an L1 hit inside the block's tile) and one scalar for the z-neighbour.
+// Material coefficients, CPML psi updates and field corrections are folded into
+// the same pass, selected by a per-(plane, tile) class byte, so homogeneous
+// interior tiles stream nothing but the 9 field words of the half-step.
+//
+// Arithmetic order follows the reference operation by operation (the file is
+// compiled with -fmad=false): in float64 the results are bit-identical to the
+// reference's numpy backend, in float32 to its true-float32 torch run.
+//
+// Reference semantics restated here (see oracle/yee_oracle.py for the CPU port):
+//   curl_H / curl_E            fdtd/grid.py:29-76
+//   E += sc*eps^-1*curl        fdtd/grid.py:283      H -= sc*mu^-1*curl   fdtd/grid.py:309
+//   Object.update_E            fdtd/objects.py:118-129
+//   AbsorbingObject.update_E   fdtd/objects.py:207-221
+//   PML.update_phi_E/H         fdtd/boundaries.py:433-487
+//   PML.update_E/H             fdtd/boundaries.py:409-431
+#pragma once
+
+namespace fdtd {
+
+typedef long long i64;
+
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) Pack {
+  T v[VEC];
+};
+
+template <typename T, int VEC>
+FDTD_DEV Pack<T, VEC> ldv(const T* p) {
+  return *reinterpret_cast<const Pack<T, VEC>*>(p);
+}
+template <typename T, int VEC>
+FDTD_DEV void stv(T* p, const Pack<T, VEC>& x) {
+  *reinterpret_cast<Pack<T, VEC>*>(p) = x;
+}
+
+template <typename T>
+struct SlabK {
+  int axis, lo, t, fused, x0, x1;
+  i64 count;
+  T* psi;      // psi_E in the E half-step, psi_H in the H half-step
+  const T* b;  // bE / bH
+  const T* c;  // cE / cH
+};
+
+template <typename T>
+struct HalfStepParams {
+  int Nx, Ny, Nz, x_offset, Nx_global;
+  int x_begin, x_end, x_chunk;
+  int lanes_z, lanes_shift, rows;  // block = lanes_z * rows threads, thread -> (row, lane)
+  i64 plane;
+  T* F[3];        // field being updated
+  const T* G[3];  // field being differentiated
+  T sc;
+  T bg_c[3];      // sc * background inverse material, rounded as the reference rounds it
+  const T* inv[3];       // effective inverse material of the curl term, or null
+  const T* inv_grid[3];  // grid's own eps^-1 for the PML correction, or null (= inv)
+  const T* absorb[3];    // absorption factor, or null
+  const unsigned char* cls;
+  unsigned char cls_vary;  // FDTD_CLS_VARY_E or FDTD_CLS_VARY_H
+  int n_slabs;
+  SlabK<T> slabs[6];
+};
+
+// CPML update of one slab for the VEC cells of a thread.  A = slab axis; (A, U, W) cyclic.
+// d0 = one-sided difference of G_W along A (drives psi[0], corrects F_U with sign -),
+// d1 = one-sided difference of G_U along A (drives psi[1], corrects F_W with sign +).
+template <typename T, int VEC, bool IS_E>
+FDTD_DEV void slab_cells(const SlabK<T>& S, bool contiguous, i64 idx0, int l0, int lstep,
+                         const T (&d0)[VEC], const T (&d1)[VEC], T (&fu)[VEC], T (&fw)[VEC],
+                         const T (&cu)[VEC], const T (&cw)[VEC]) {
+  // contiguous: the VEC cells share l (x / y slabs) and psi is contiguous in z -> vector access.
+  // otherwise (z slabs) l = l0 + e and psi index = idx0 + e (layout [x][y][l]).
+  T p0[VEC], p1[VEC];
+  bool in[VEC];
+  if (contiguous) {
+    Pack<T, VEC> a = ldv<T, VEC>(S.psi + idx0);
+    Pack<T, VEC> b = ldv<T, VEC>(S.psi + S.count + idx0);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      p0[e] = a.v[e];
+      p1[e] = b.v[e];
+      in[e] = true;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      int l = l0 + e * lstep;
+      in[e] = (l >= 0) && (l < S.t);
+      p0[e] = in[e] ? S.psi[idx0 + e] : T(0);
+      p1[e] = in[e] ? S.psi[S.count + idx0 + e] : T(0);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    int l = l0 + e * lstep;
+    if (in[e]) {
+      T b = S.b[l];
+      T c = S.c[l];
+      // psi *= b; psi[inner] += diff * c[inner]      fdtd/boundaries.py:439-454, 467-482
+      bool inner = IS_E ? (l >= 1) : (l < S.t - 1);
+      p0[e] = p0[e] * b;
+      p1[e] = p1[e] * b;
+      if (inner) {
+        p0[e] = p0[e] + d0[e] * c;
+        p1[e] = p1[e] + d1[e] * c;
+      }
+      if (S.fused) {
+        // phi_U = 0 - psi0, phi_W = psi1 - 0; F[loc] +-= sc*inv*phi   fdtd/boundaries.py:409-431, 456-459
+        T phi_u = T(0) - p0[e];
+        T phi_w = p1[e] - T(0);
+        if (IS_E) {
+          fu[e] = fu[e] + cu[e] * phi_u;
+          fw[e] = fw[e] + cw[e] * phi_w;
+        } else {
+          fu[e] = fu[e] - cu[e] * phi_u;
+          fw[e] = fw[e] - cw[e] * phi_w;
+        }
+      }
+    }
+  }
+  if (contiguous) {
+    Pack<T, VEC> a, b;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      a.v[e] = p0[e];
+      b.v[e] = p1[e];
+    }
+    stv<T, VEC>(S.psi + idx0, a);
+    stv<T, VEC>(S.psi + S.count + idx0, b);
+  } else {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      if (in[e]) {
+        S.psi[idx0 + e] = p0[e];
+        S.psi[S.count + idx0 + e] = p1[e];
+      }
+    }
+  }
+}
+
+template <typename T, int VEC, bool IS_E>
+__global__ void __launch_bounds__(256) halfstep_kernel(const HalfStepParams<T> P) {
+  const int tid = threadIdx.x;
+  const int lane = tid & (P.lanes_z - 1);
+  const int row = tid >> P.lanes_shift;
+  const int k0 = (blockIdx.x * P.lanes_z + lane) * VEC;
+  const int j = blockIdx.y * P.rows + row;
+  if (j >= P.Ny || k0 >= P.Nz) return;
+  const int Nz = P.Nz;
+  const i64 plane = P.plane;
+  const i64 p = (i64)j * Nz + k0;
+  const int i0 = P.x_begin + blockIdx.z * P.x_chunk;
+  const int i1 = (i0 + P.x_chunk < P.x_end) ? i0 + P.x_chunk : P.x_end;
+
+  const T* __restrict__ Gx = P.G[0];
+  const T* __restrict__ Gy = P.G[1];
+  const T* __restrict__ Gz = P.G[2];
+  T* Fx = P.F[0];
+  T* Fy = P.F[1];
+  T* Fz = P.F[2];
+
+  // neighbour offsets: backward differences for E (fdtd/grid.py:66-74), forward for H (:41-49)
+  const i64 off_y = IS_E ? -(i64)Nz : (i64)Nz;
+  const i64 off_zs = IS_E ? -1 : VEC;
+  const bool my = IS_E ? (j >= 1) : (j < P.Ny - 1);
+  bool mz[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) mz[e] = IS_E ? (k0 + e >= 1) : (k0 + e < Nz - 1);
+
+  // loop-invariant slab membership in y and z
+  bool pml_yz = false;
+  for (int s = 0; s < P.n_slabs; ++s) {
+    const SlabK<T>& S = P.slabs[s];
+    if (S.axis == 1) pml_yz |= (j >= S.lo) && (j < S.lo + S.t);
+    if (S.axis == 2) pml_yz |= (k0 + VEC > S.lo) && (k0 < S.lo + S.t);
+  }
+
+  // x-neighbour plane carried in registers: plane i-1 of (Gy, Gz) for E, plane i for H
+  Pack<T, VEC> carry_y, carry_z;
+  {
+    const i64 o = (IS_E ? (i64)(i0 - 1) : (i64)i0) * plane + p;
+    carry_y = ldv<T, VEC>(Gy + o);
+    carry_z = ldv<T, VEC>(Gz + o);
+  }
+  const i64 cls_stride = (i64)gridDim.y * gridDim.x;
+  const i64 cls_tile = (i64)blockIdx.y * gridDim.x + blockIdx.x;
+
+  for (int i = i0; i < i1; ++i) {
+    const i64 off = (i64)i * plane + p;
+    const unsigned cls = P.cls ? P.cls[(i64)i * cls_stride + cls_tile] : 0u;
+
+    // ---- loads -------------------------------------------------------------------------
+    Pack<T, VEC> gx = ldv<T, VEC>(Gx + off);
+    Pack<T, VEC> gy, gz, xnb_y, xnb_z;
+    if (IS_E) {
+      gy = ldv<T, VEC>(Gy + off);
+      gz = ldv<T, VEC>(Gz + off);
+      xnb_y = carry_y;
+      xnb_z = carry_z;
+    } else {
+      gy = carry_y;
+      gz = carry_z;
+      xnb_y = ldv<T, VEC>(Gy + off + plane);
+      xnb_z = ldv<T, VEC>(Gz + off + plane);
+    }
+    const Pack<T, VEC> ynb_x = ldv<T, VEC>(Gx + off + off_y);
+    const Pack<T, VEC> ynb_z = ldv<T, VEC>(Gz + off + off_y);
+    const T zs_x = Gx[off + off_zs];
+    const T zs_y = Gy[off + off_zs];
+    Pack<T, VEC> f0 = ldv<T, VEC>(Fx + off);
+    Pack<T, VEC> f1 = ldv<T, VEC>(Fy + off);
+    Pack<T, VEC> f2 = ldv<T, VEC>(Fz + off);
+
+    const int ig = i + P.x_offset;
+    const bool mx = IS_E ? (ig >= 1) : (ig < P.Nx_global - 1);
+
+    // ---- one-sided differences d_ca = d G_c / d a, each masked independently ------------
+    T d_zy[VEC], d_yz[VEC], d_xz[VEC], d_zx[VEC], d_yx[VEC], d_xy[VEC];
+    T fx[VEC], fy[VEC], fz[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const T znb_x = IS_E ? (e == 0 ? zs_x : gx.v[e > 0 ? e - 1 : 0])
+                           : (e == VEC - 1 ? zs_x : gx.v[e < VEC - 1 ? e + 1 : 0]);
+      const T znb_y = IS_E ? (e == 0 ? zs_y : gy.v[e > 0 ? e - 1 : 0])
+                           : (e == VEC - 1 ? zs_y : gy.v[e < VEC - 1 ? e + 1 : 0]);
+      if (IS_E) {
+        d_zy[e] = my ? gz.v[e] - ynb_z.v[e] : T(0);
+        d_xy[e] = my ? gx.v[e] - ynb_x.v[e] : T(0);
+        d_yz[e] = mz[e] ? gy.v[e] - znb_y : T(0);
+        d_xz[e] = mz[e] ? gx.v[e] - znb_x : T(0);
+        d_zx[e] = mx ? gz.v[e] - xnb_z.v[e] : T(0);
+        d_yx[e] = mx ? gy.v[e] - xnb_y.v[e] : T(0);
+      } else {
+        d_zy[e] = my ? ynb_z.v[e] - gz.v[e] : T(0);
+        d_xy[e] = my ? ynb_x.v[e] - gx.v[e] : T(0);
+        d_yz[e] = mz[e] ? znb_y - gy.v[e] : T(0);
+        d_xz[e] = mz[e] ? znb_x - gx.v[e] : T(0);
+        d_zx[e] = mx ? xnb_z.v[e] - gz.v[e] : T(0);
+        d_yx[e] = mx ? xnb_y.v[e] - gy.v[e] : T(0);
+      }
+      fx[e] = f0.v[e];
+      fy[e] = f1.v[e];
+      fz[e] = f2.v[e];
+    }
+
+    // ---- coefficients --------------------------------------------------------------------
+    T cx[VEC], cy[VEC], cz[VEC];
+    if (cls & P.cls_vary) {
+      // material arrays have no ghost planes: [x][y][z] index == off
+      Pack<T, VEC> a0 = ldv<T, VEC>(P.inv[0] + off);
+      Pack<T, VEC> a1 = ldv<T, VEC>(P.inv[1] + off);
+      Pack<T, VEC> a2 = ldv<T, VEC>(P.inv[2] + off);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        cx[e] = P.sc * a0.v[e];
+        cy[e] = P.sc * a1.v[e];
+        cz[e] = P.sc * a2.v[e];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        cx[e] = P.bg_c[0];
+        cy[e] = P.bg_c[1];
+        cz[e] = P.bg_c[2];
+      }
+    }
+
+    // ---- field update ----------------------------------------------------------------------
+    if (IS_E && (cls & FDTD_CLS_ABSORB)) {
+      // E *= (1-f)/(1+f); E += sc*eps^-1*curl/(1+f)        fdtd/objects.py:214-221
+      Pack<T, VEC> q0 = ldv<T, VEC>(P.absorb[0] + off);
+      Pack<T, VEC> q1 = ldv<T, VEC>(P.absorb[1] + off);
+      Pack<T, VEC> q2 = ldv<T, VEC>(P.absorb[2] + off);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T ux = d_zy[e] - d_yz[e];
+        const T uy = d_xz[e] - d_zx[e];
+        const T uz = d_yx[e] - d_xy[e];
+        fx[e] = fx[e] * ((T(1) - q0.v[e]) / (T(1) + q0.v[e]));
+        fy[e] = fy[e] * ((T(1) - q1.v[e]) / (T(1) + q1.v[e]));
+        fz[e] = fz[e] * ((T(1) - q2.v[e]) / (T(1) + q2.v[e]));
+        fx[e] = fx[e] + (cx[e] * ux) / (T(1) + q0.v[e]);
+        fy[e] = fy[e] + (cy[e] * uy) / (T(1) + q1.v[e]);
+        fz[e] = fz[e] + (cz[e] * uz) / (T(1) + q2.v[e]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T ux = d_zy[e] - d_yz[e];
+        const T uy = d_xz[e] - d_zx[e];
+        const T uz = d_yx[e] - d_xy[e];
+        if (IS_E) {
+          fx[e] = fx[e] + cx[e] * ux;
+          fy[e] = fy[e] + cy[e] * uy;
+          fz[e] = fz[e] + cz[e] * uz;
+        } else {
+          fx[e] = fx[e] - cx[e] * ux;
+          fy[e] = fy[e] - cy[e] * uy;
+          fz[e] = fz[e] - cz[e] * uz;
+        }
+      }
+    }
+
+    // ---- CPML slabs (registration order) -----------------------------------------------------
+    bool pml_x = false;
+    for (int s = 0; s < P.n_slabs; ++s) {
+      const SlabK<T>& S = P.slabs[s];
+      if (S.axis == 0) pml_x |= (i >= S.x0) && (i < S.x1);
+    }
+    if (pml_x || pml_yz) {
+      if (IS_E && (cls & FDTD_CLS_OBJECT) && P.inv_grid[0] != nullptr) {
+        // the correction uses the GRID's eps^-1, which is zero inside objects (fdtd/objects.py:92)
+        Pack<T, VEC> a0 = ldv<T, VEC>(P.inv_grid[0] + off);
+        Pack<T, VEC> a1 = ldv<T, VEC>(P.inv_grid[1] + off);
+        Pack<T, VEC> a2 = ldv<T, VEC>(P.inv_grid[2] + off);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          cx[e] = P.sc * a0.v[e];
+          cy[e] = P.sc * a1.v[e];
+          cz[e] = P.sc * a2.v[e];
+        }
+      }
+      for (int s = 0; s < P.n_slabs; ++s) {
+        const SlabK<T>& S = P.slabs[s];
+        if (S.axis == 0) {
+          if (i >= S.x0 && i < S.x1)
+            slab_cells<T, VEC, IS_E>(S, true, (i64)(i - S.x0) * plane + p, ig - S.lo, 0, d_zx, d_yx,
+                                     fy, fz, cy, cz);
+        } else if (S.axis == 1) {
+          const int l = j - S.lo;
+          if (l >= 0 && l < S.t)
+            slab_cells<T, VEC, IS_E>(S, true, ((i64)i * S.t + l) * Nz + k0, l, 0, d_xy, d_zy, fz, fx,
+                                     cz, cx);
+        } else {
+          const int l0 = k0 - S.lo;
+          if (l0 + VEC > 0 && l0 < S.t)
+            slab_cells<T, VEC, IS_E>(S, false, ((i64)i * P.Ny + j) * S.t + l0, l0, 1, d_yz, d_xz, fx,
+                                     fy, cx, cy);
+        }
+      }
+    }
+
+    // ---- stores --------------------------------------------------------------------------------
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      f0.v[e] = fx[e];
+      f1.v[e] = fy[e];
+      f2.v[e] = fz[e];
+    }
+    stv<T, VEC>(Fx + off, f0);
+    stv<T, VEC>(Fy + off, f1);
+    stv<T, VEC>(Fz + off, f2);
+
+    if (IS_E) {
+      carry_y = gy;
+      carry_z = gz;
+    } else {
+      carry_y = xnb_y;
+      carry_z = xnb_z;
+    }
+  }
+}
+
+// ---- post kernels ------------------------------------------------------------------------------
+
+// periodic copy of one plane of all three components (fdtd/boundaries.py:184-219)
+template <typename T>
+__global__ void periodic_kernel(T* F0, T* F1, T* F2, int axis, int Nx, int Ny, int Nz, i64 plane,
+                                int src, int dst) {
+  const i64 n_a = axis == 0 ? Ny : Nx;
+  const i64 n_b = axis == 2 ? Ny : Nz;
+  const i64 total = n_a * n_b * 3;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (i64)gridDim.x * blockDim.x) {
+    const int c = (int)(t / (n_a * n_b));
+    const i64 r = t % (n_a * n_b);
+    const i64 a = r / n_b, b = r % n_b;
+    i64 so, dofs;
+    if (axis == 0) {
+      so = (i64)src * plane + a * Nz + b;
+      dofs = (i64)dst * plane + a * Nz + b;
+    } else if (axis == 1) {
+      so = a * plane + (i64)src * Nz + b;
+      dofs = a * plane + (i64)dst * Nz + b;
+    } else {
+      so = a * plane + b * Nz + src;
+      dofs = a * plane + b * Nz + dst;
+    }
+    T* F = c == 0 ? F0 : (c == 1 ? F1 : F2);
+    F[dofs] = F[so];
+  }
+}
+
+// field correction of a PML registered after a periodic boundary (fdtd/boundaries.py:409-431)
+template <typename T, bool IS_E>
+__global__ void pml_add_kernel(SlabK<T> S, T* F0, T* F1, T* F2, const T* c0, const T* c1,
+                               const T* c2, T bg0, T bg1, T bg2, T sc, int Nx, int Ny, int Nz,
+                               i64 plane) {
+  for (i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x; n < S.count;
+       n += (i64)gridDim.x * blockDim.x) {
+    int i, j, k;
+    if (S.axis == 0) {
+      i = S.x0 + (int)(n / plane);
+      j = (int)((n % plane) / Nz);
+      k = (int)(n % Nz);
+    } else if (S.axis == 1) {
+      i = (int)(n / ((i64)S.t * Nz));
+      j = S.lo + (int)((n / Nz) % S.t);
+      k = (int)(n % Nz);
+    } else {
+      i = (int)(n / ((i64)Ny * S.t));
+      j = (int)((n / S.t) % Ny);
+      k = S.lo + (int)(n % S.t);
+    }
+    const i64 off = (i64)i * plane + (i64)j * Nz + k;
+    const int u = (S.axis + 1) % 3, w = (S.axis + 2) % 3;
+    T* Fu = u == 0 ? F0 : (u == 1 ? F1 : F2);
+    T* Fw = w == 0 ? F0 : (w == 1 ? F1 : F2);
+    const T* cu_p = u == 0 ? c0 : (u == 1 ? c1 : c2);
+    const T* cw_p = w == 0 ? c0 : (w == 1 ? c1 : c2);
+    const T cu = cu_p ? sc * cu_p[off] : (u == 0 ? bg0 : (u == 1 ? bg1 : bg2));
+    const T cw = cw_p ? sc * cw_p[off] : (w == 0 ? bg0 : (w == 1 ? bg1 : bg2));
+    const T phi_u = T(0) - S.psi[n];
+    const T phi_w = S.psi[S.count + n] - T(0);
+    if (IS_E) {
+      Fu[off] = Fu[off] + cu * phi_u;
+      Fw[off] = Fw[off] + cw * phi_w;
+    } else {
+      Fu[off] = Fu[off] - cu * phi_u;
+      Fw[off] = Fw[off] - cw * phi_w;
+    }
+  }
+}
+
+// soft source: F[idx[n]] += profile[n] * wave   (fdtd/sources.py:93-109, 278-297)
+template <typename T>
+__global__ void source_points_kernel(T* F, const i64* idx, const T* profile, int n, const T* wave,
+                                     i64 w) {
+  const T s = wave[w];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    fdtd_atomic_add(F + idx[t], profile[t] * s);
+  }
+}
+
+// hard source: F[box] = amplitude * wave   (fdtd/sources.py:476-486)
+template <typename T>
+__global__ void source_box_kernel(T* F, int x0, int x1, int y0, int y1, int z0, int z1, int Nz,
+                                  i64 plane, T amplitude, const T* wave, i64 w) {
+  const T v = amplitude * wave[w];
+  const i64 ny = y1 - y0, nz = z1 - z0;
+  const i64 total = (i64)(x1 - x0) * ny * nz;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (i64)gridDim.x * blockDim.x) {
+    const i64 x = x0 + t / (ny * nz);
+    const i64 y = y0 + (t / nz) % ny;
+    const i64 z = z0 + t % nz;
+    F[x * plane + y * Nz + z] = v;
+  }
+}
+
+// detector sampling into the device ring (fdtd/detectors.py:114-124, 241-263)
+template <typename T>
+__global__ void detector_kernel(const T* F0, const T* F1, const T* F2, const i64* idx, int n,
+                                T* ring, i64 slot) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 3 * n; t += gridDim.x * blockDim.x) {
+    const int pt = t / 3, c = t % 3;
+    const T* F = c == 0 ? F0 : (c == 1 ? F1 : F2);
+    ring[(slot * n + pt) * 3 + c] = F[idx[pt]];
+  }
+}
+
+}  // namespace fdtd

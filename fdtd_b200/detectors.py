@@ -1,0 +1,137 @@
+"""Detectors: LineDetector and BlockDetector (fdtd/detectors.py:20-280).
+
+The reference appends one array per half-step to Python lists (`detector.E`, `detector.H`).
+Here every half-step a small kernel gathers the detector's cells into a device ring buffer
+`[capacity][points][3]`; the ring is copied to the host in batches (when it fills up, or when
+the user reads the detector) and `detector.E` / `.H` materialise the reference's
+list-of-per-step-arrays lazily from those host chunks.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .backend import backend as bd
+from .sources import _diagonal_points, local_points
+
+
+class _Detector:
+    def __init__(self, name=None):
+        self.grid = None
+        self.name = name
+        self._chunks = {"E": [], "H": []}     # host arrays (T_chunk, *sample_shape, 3)
+        self._lists = {"E": None, "H": None}  # cached list view of the chunks
+        self._ring_E = self._ring_H = None
+        self._capacity = 0
+
+    def _attach(self, grid):
+        self.grid = grid
+        self.grid.detectors.append(self)
+        grid._register_name(self)
+
+    def _set_points(self, xs, ys, zs, sample_shape):
+        """global point list (sampling order) -> local subset on this rank."""
+        self._sample_shape = tuple(sample_shape)
+        self._n_points = int(np.prod(sample_shape))
+        mine, lin = local_points(self.grid, xs, ys, zs)
+        self._positions = mine
+        self._n_local = len(lin)
+        self._idx = torch.as_tensor(lin, dtype=torch.int64, device=bd.device)
+
+    def _ensure_ring(self, capacity):
+        if self._ring_E is None or self._capacity != capacity:
+            g = self.grid
+            if g._ring_fill["E"] or g._ring_fill["H"]:
+                raise RuntimeError("detector ring resized with samples pending")
+            self._capacity = capacity
+            self._ring_E = bd.zeros((capacity, max(1, self._n_local), 3))
+            self._ring_H = bd.zeros((capacity, max(1, self._n_local), 3))
+
+    def _drain(self, nE, nH):
+        """copy the filled part of the rings to the host (one batch) and assemble global samples."""
+        part = self.grid._part
+        for f, ring, n in (("E", self._ring_E, nE), ("H", self._ring_H, nH)):
+            if n == 0:
+                continue
+            local = ring[:n, :self._n_local].cpu().numpy()
+            if part.sharded:
+                gathered = [None] * part.world
+                dist.all_gather_object(gathered, (self._positions, local))
+                full = np.zeros((n, self._n_points, 3), dtype=local.dtype)
+                for pos, vals in gathered:
+                    full[:, pos] = vals
+            else:
+                full = local
+            self._chunks[f].append(full.reshape((n,) + self._sample_shape + (3,)))
+            self._lists[f] = None
+
+    def _history(self, f):
+        g = self.grid
+        if g is not None and g._engine is not None:
+            g._engine.flush_detectors()
+        if self._lists[f] is None:
+            self._lists[f] = [step for chunk in self._chunks[f] for step in chunk]
+        return self._lists[f]
+
+    @property
+    def E(self):
+        """list with one array per E half-step, as the reference's `detector.E`."""
+        return self._history("E")
+
+    @property
+    def H(self):
+        return self._history("H")
+
+    def detector_values(self):
+        """outputs what detector detects (fdtd/detectors.py:137-139)."""
+        return {"E": self.E, "H": self.H}
+
+    def detect_E(self):      # plug-in protocol of the reference; sampling happens on the device
+        pass
+
+    def detect_H(self):
+        pass
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(name={repr(self.name)})"
+
+    def __str__(self):
+        s = "    " + repr(self) + "\n"
+        return s + (f"        @ x=[{self.x[0]}, ... , {self.x[-1]}], y=[{self.y[0]}, ... , {self.y[-1]}], "
+                    f"z=[{self.z[0]}, ... , {self.z[-1]}]\n")
+
+
+class LineDetector(_Detector):
+    """samples E and H along the diagonal of a box: one (L, 3) array per half-step
+    (fdtd/detectors.py:20-139)."""
+
+    def _register_grid(self, grid, x, y, z):
+        self._attach(grid)
+        self.x, self.y, self.z = _diagonal_points(grid, x, y, z, False, 0, "LineDetector")
+        self._set_points(self.x, self.y, self.z, (len(self.x),))
+
+
+class BlockDetector(_Detector):
+    """samples a block with INCLUSIVE upper bounds (fdtd/detectors.py:236-238): one
+    (nx, ny, nz, 3) array per half-step, indexable like the reference's nested lists."""
+
+    def _register_grid(self, grid, x, y, z):
+        self._attach(grid)
+        if isinstance(x, list) and isinstance(y, list) and isinstance(z, list):
+            if len(x) != len(y) or len(y) != len(z) or len(z) != len(x):
+                raise IndexError("sources require grid to be indexed with slices or equal length list-indices")
+            self.x, self.y, self.z = x, y, z
+        else:
+            out = []
+            for s, n in ((x, grid.Nx), (y, grid.Ny), (z, grid.Nz)):
+                if isinstance(s, list):
+                    s = slice(s[0], s[-1], None)
+                a = s.start if s.start is not None else 0
+                b = s.stop if s.stop is not None else n
+                out.append(list(range(a, b + 1)))
+            self.x, self.y, self.z = out
+        for v, n in ((self.x, grid.Nx), (self.y, grid.Ny), (self.z, grid.Nz)):
+            if any(i >= n or i < -n for i in v):
+                # the reference fails with IndexError at the first step (SURVEY.md 8a trap 9)
+                raise IndexError("BlockDetector ranges are inclusive of `stop`: index out of range")
+        X, Y, Z = np.meshgrid(self.x, self.y, self.z, indexing="ij")
+        self._set_points(X.ravel(), Y.ravel(), Z.ravel(), X.shape)

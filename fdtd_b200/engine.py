@@ -1,0 +1,320 @@
+"""Host side of the fused Yee update: bakes a Grid's registrations into the C-ABI descriptor
+(include/fdtd_b200.h) and drives the CUDA kernels.
+
+What is baked (once, and again only when something registered or a material array changed):
+  * CPML slabs (registration order) with their psi storage and 1-D b/c tables; slabs registered
+    before the first periodic boundary are corrected inside the fused kernel, later ones by a
+    post-op so that the reference's registration-order semantics hold (fdtd/grid.py:290-291);
+  * materials: the grid's eps^-1 / mu^-1 arrays only if they exist (they are created lazily --
+    a homogeneous grid streams no coefficient array at all), the effective eps^-1 of the curl
+    term (grid + objects), the absorption factor, and the per-(plane, tile) class byte;
+  * sources (point lists / hard boxes) and their host-tabulated waveforms;
+  * detector point lists and device ring buffers, flushed to the host in batches.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _capi
+from .backend import backend as bd
+from ._hostmath import scalar_in_dtype
+from .sharding import HaloExchange
+
+RING_BYTES = 64 << 20          # detector ring budget per grid
+WAVE_TABLE_MIN = 1024          # look-ahead of the host waveform tables (steps)
+WAVE_TABLE_MAX = 1 << 16
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(None)
+
+
+class Engine:
+    def __init__(self, grid):
+        self.grid = grid
+        self.lib = bd.lib
+        self.desc = _capi.Desc()
+        self._keep = []            # tensors referenced by raw pointers in the descriptor
+        self._wave = None          # (q0, len)
+        self._halo = None
+        self._pending = {"E": None, "H": None}
+        self.bake()
+
+    # ------------------------------------------------------------------------------------ bake
+    def bake(self):
+        g, d = self.grid, self.desc
+        part = g._part
+        dt = g._dtype
+        C.memset(C.byref(d), 0, C.sizeof(d))
+        self._keep = []
+        d.abi_version = _capi.ABI_VERSION
+        d.dtype = _capi.F32 if dt is torch.float32 else _capi.F64
+        d.Nx, d.Ny, d.Nz = part.nx, g.Ny, g.Nz
+        d.x_offset, d.Nx_global = part.x0, g.Nx
+        d.plane = g.Ny * g.Nz
+        d.courant = g.courant_number
+        d.x_chunk = g._x_chunk
+        for c in range(3):
+            d.E[c] = g._E[c, 1].data_ptr()
+            d.H[c] = g._H[c, 1].data_ptr()
+            d.bg_inv_eps[c] = g._bg_inv_eps[c]
+            d.bg_inv_mu[c] = g._bg_inv_mu[c]
+
+        # --- boundaries -----------------------------------------------------------------------
+        from .boundaries import PML, PeriodicBoundary
+        slabs, post, seen_periodic = [], [], False
+        for b in g.boundaries:
+            if isinstance(b, PML):
+                if len(slabs) == _capi.MAX_SLABS:
+                    raise ValueError("at most six PMLs (one per face)")
+                idx = len(slabs)
+                slabs.append(b)
+                s = d.slabs[idx]
+                s.axis, s.lo, s.thickness = b.axis, b.lo, b.thickness
+                s.fused = 0 if seen_periodic else 1
+                s.x0, s.x1 = b._x0, b._x1
+                s.psi_count = b._psi_E.shape[1]
+                s.psi_E, s.psi_H = _ptr(b._psi_E), _ptr(b._psi_H)
+                s.bE, s.cE, s.bH, s.cH = (_ptr(b._tab[k]) for k in ("bE", "cE", "bH", "cH"))
+                if seen_periodic:
+                    post.append((_capi.POST_PML_ADD, idx))
+            elif isinstance(b, PeriodicBoundary):
+                seen_periodic = True
+                if b.axis == 0 and part.sharded:
+                    raise NotImplementedError("a periodic x boundary on an x-sharded grid")
+                post.append((_capi.POST_PERIODIC, b.axis))
+            else:
+                raise TypeError(f"unsupported boundary {b!r}")
+        if len(post) > _capi.MAX_POST:
+            raise ValueError("too many boundary post-ops")
+        d.n_slabs, d.n_post = len(slabs), len(post)
+        for n, (kind, arg) in enumerate(post):
+            d.post_kind[n], d.post_arg[n] = kind, arg
+
+        # --- materials ------------------------------------------------------------------------
+        ie_grid, imu = g._inv_eps, g._inv_mu
+        ie_eff, absorb = ie_grid, None
+        if g.objects:
+            ie_eff = ie_grid.clone()
+            for o in g.objects:
+                if o._nx_local == 0:
+                    continue
+                ie_eff[(slice(None),) + o._loc] += o._inv_eps_soa
+                if o._absorb_soa is not None:
+                    if absorb is None:
+                        absorb = torch.zeros_like(ie_grid)
+                    absorb[(slice(None),) + o._loc] = o._absorb_soa
+        self._mat_versions = (None if ie_grid is None else ie_grid._version,
+                              None if imu is None else imu._version)
+        ty, tz = C.c_int32(), C.c_int32()
+        _capi.check(self.lib, self.lib.fdtd_tile_shape(d.dtype, g.Ny, g.Nz, C.byref(ty), C.byref(tz)))
+        d.tile_y, d.tile_z = ty.value, tz.value
+        cls = None
+        if ie_eff is not None or imu is not None:
+            cls = self._classify(ie_eff, ie_grid if g.objects else None, absorb, imu, ty.value, tz.value)
+        for c in range(3):
+            d.inv_eps[c] = ie_eff[c].data_ptr() if ie_eff is not None else None
+            d.inv_eps_grid[c] = ie_grid[c].data_ptr() if (g.objects and ie_grid is not None) else None
+            d.absorb[c] = absorb[c].data_ptr() if absorb is not None else None
+            d.inv_mu[c] = imu[c].data_ptr() if imu is not None else None
+        d.tile_class = _ptr(cls)
+        self._keep += [ie_eff, absorb, cls]
+        self.tile_class = cls
+
+        # --- sources ----------------------------------------------------------------------------
+        self._src_entries = []       # (desc index, source object, kind tag)
+        n = 0
+        for s in g.sources:
+            for entry in s._entries():
+                if n == _capi.MAX_SOURCES:
+                    raise ValueError(f"at most {_capi.MAX_SOURCES} source entries")
+                e = d.sources[n]
+                e.kind, e.field, e.comp = entry["kind"], entry["field"], entry["comp"]
+                if entry["kind"] == _capi.SRC_POINTS:
+                    e.n = int(entry["idx"].numel())
+                    e.idx, e.profile = _ptr(entry["idx"]), _ptr(entry["profile"])
+                    self._keep += [entry["idx"], entry["profile"]]
+                else:
+                    e.amplitude = entry["amplitude"]
+                    for k in range(6):
+                        e.box[k] = entry["box"][k]
+                self._src_entries.append((n, s))
+                n += 1
+        d.n_sources = n
+        self._wave = None
+
+        # --- detectors --------------------------------------------------------------------------
+        if len(g.detectors) > _capi.MAX_DETECTORS:
+            raise ValueError(f"at most {_capi.MAX_DETECTORS} detectors")
+        w = 4 if dt is torch.float32 else 8
+        per_step = sum(2 * 3 * w * max(1, det._n_local) for det in g.detectors)
+        self.ring_capacity = int(min(8192, max(16, RING_BYTES // max(1, per_step)))) if g.detectors else 1 << 62
+        for n, det in enumerate(g.detectors):
+            det._ensure_ring(self.ring_capacity)
+            e = d.detectors[n]
+            e.n = det._n_local
+            e.idx = _ptr(det._idx)
+            e.ring_E, e.ring_H = _ptr(det._ring_E), _ptr(det._ring_H)
+            e.capacity = self.ring_capacity
+        d.n_detectors = len(g.detectors)
+
+        self._ensure_wave(g.time_steps_passed, 1)
+        _capi.check(self.lib, self.lib.fdtd_validate(C.byref(d)))
+
+        if part.sharded:
+            self._halo = HaloExchange(part, g._E, g._H)
+            self._halo.refresh()
+        g._baked_counts = g._registration_count
+
+    def _classify(self, ie_eff, ie_grid_if_objects, absorb, imu, ty, tz):
+        """per-(plane, y-tile, z-tile) class byte, FDTD_CLS_* (include/fdtd_b200.h)."""
+        g = self.grid
+        nx, Ny, Nz = g._part.nx, g.Ny, g.Nz
+        nty, ntz = -(-Ny // ty), -(-Nz // tz)
+        cls = torch.zeros((nx, nty, ntz), dtype=torch.uint8, device=g._E.device)
+        dt = g._dtype
+
+        def tiles(mask):        # (n, Ny, Nz) bool -> (n, nty, ntz) bool
+            m = torch.nn.functional.pad(mask, (0, ntz * tz - Nz, 0, nty * ty - Ny))
+            return m.view(m.shape[0], nty, ty, ntz, tz).any(dim=4).any(dim=2)
+
+        bg_e = torch.tensor(g._bg_inv_eps, dtype=dt, device=cls.device).view(3, 1, 1, 1)
+        bg_m = torch.tensor(g._bg_inv_mu, dtype=dt, device=cls.device).view(3, 1, 1, 1)
+        step = max(1, (64 << 20) // max(1, Ny * Nz))      # bound the temporaries
+        for a in range(0, nx, step):
+            b = min(nx, a + step)
+            bits = torch.zeros((b - a, nty, ntz), dtype=torch.uint8, device=cls.device)
+            if ie_eff is not None:
+                bits |= tiles((ie_eff[:, a:b] != bg_e).any(0)).to(torch.uint8) * _capi.CLS_VARY_E
+            if imu is not None:
+                bits |= tiles((imu[:, a:b] != bg_m).any(0)).to(torch.uint8) * _capi.CLS_VARY_H
+            if absorb is not None:
+                bits |= tiles((absorb[:, a:b] != 0).any(0)).to(torch.uint8) * _capi.CLS_ABSORB
+            if ie_grid_if_objects is not None:
+                bits |= tiles((ie_eff[:, a:b] != ie_grid_if_objects[:, a:b]).any(0)).to(torch.uint8) * _capi.CLS_OBJECT
+            cls[a:b] = bits
+        return cls.contiguous()
+
+    def stale(self):
+        g = self.grid
+        if g._baked_counts != g._registration_count:
+            return True
+        v = (None if g._inv_eps is None else g._inv_eps._version,
+             None if g._inv_mu is None else g._inv_mu._version)
+        return v != self._mat_versions
+
+    # ------------------------------------------------------------------------------ per-run state
+    def _ensure_wave(self, q0, n):
+        """host-tabulated per-step source scalars covering steps [q0, q0+n)."""
+        if not self._src_entries:
+            return
+        if self._wave is not None:
+            a, ln = self._wave
+            if a <= q0 and q0 + n <= a + ln:
+                return
+        ln = max(n, WAVE_TABLE_MIN)
+        g, d = self.grid, self.desc
+        tables = {}
+        for idx, src in self._src_entries:
+            if id(src) not in tables:
+                vals = torch.tensor([src._wave_value(q) for q in range(q0, q0 + ln)], dtype=torch.float64)
+                tables[id(src)] = vals.to(g._dtype).to(g._E.device)
+            t = tables[id(src)]
+            e = d.sources[idx]
+            e.wave, e.wave_q0, e.wave_len = _ptr(t), q0, ln
+        self._wave_keep = list(tables.values())
+        self._wave = (q0, ln)
+
+    def _stream(self):
+        dev = self.grid._E.device
+        return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream) if dev.type == "cuda" else C.c_void_p(None)
+
+    def _slot(self, field):
+        """next free ring slot for `field`, flushing the rings to the host when full."""
+        g = self.grid
+        if not g.detectors:
+            return 0
+        if g._ring_fill[field] >= self.ring_capacity:
+            self.flush_detectors()
+        return g._ring_fill[field]
+
+    def flush_detectors(self):
+        g = self.grid
+        nE, nH = g._ring_fill["E"], g._ring_fill["H"]
+        if nE == 0 and nH == 0:
+            return
+        for det in g.detectors:
+            det._drain(nE, nH)
+        g._ring_fill["E"] = g._ring_fill["H"] = 0
+
+    # ------------------------------------------------------------------------------------ stepping
+    def update_E(self, q):
+        g, lib, d = self.grid, self.lib, self.desc
+        self._ensure_wave(q, 1)
+        slot = self._slot("E")
+        st = self._stream()
+        if self._halo is None:
+            _capi.check(lib, lib.fdtd_update_E(C.byref(d), q, slot, st))
+        else:
+            n = d.Nx
+            _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 1, n, st))
+            self._halo.wait(self._pending["H"])
+            self._pending["H"] = None
+            _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 0, min(1, n), st))
+            _capi.check(lib, lib.fdtd_post_E(C.byref(d), q, slot, st))
+            self._pending["E"] = self._halo.start("E")
+        if g.detectors:
+            g._ring_fill["E"] += 1
+
+    def update_H(self, q):
+        g, lib, d = self.grid, self.lib, self.desc
+        self._ensure_wave(q, 1)
+        slot = self._slot("H")
+        st = self._stream()
+        if self._halo is None:
+            _capi.check(lib, lib.fdtd_update_H(C.byref(d), q, slot, st))
+        else:
+            n = d.Nx
+            _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), 0, n - 1, st))
+            self._halo.wait(self._pending["E"])
+            self._pending["E"] = None
+            _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), n - 1, n, st))
+            _capi.check(lib, lib.fdtd_post_H(C.byref(d), q, slot, st))
+            self._pending["H"] = self._halo.start("H")
+        if g.detectors:
+            g._ring_fill["H"] += 1
+
+    def run(self, q0, nsteps, progress=None):
+        """nsteps full steps from step index q0; one C call per chunk when not sharded."""
+        g, lib, d = self.grid, self.lib, self.desc
+        done = 0
+        while done < nsteps:
+            if g.detectors and (g._ring_fill["E"] != g._ring_fill["H"]
+                                or g._ring_fill["E"] >= self.ring_capacity):
+                self.flush_detectors()
+            room = self.ring_capacity - g._ring_fill["E"] if g.detectors else nsteps
+            n = min(nsteps - done, room, WAVE_TABLE_MAX)
+            q = q0 + done
+            self._ensure_wave(q, n)
+            if self._halo is None:
+                _capi.check(lib, lib.fdtd_run(C.byref(d), q, n, g._ring_fill["E"] if g.detectors else 0,
+                                              self._stream()))
+                if g.detectors:
+                    g._ring_fill["E"] += n
+                    g._ring_fill["H"] += n
+            else:
+                for s in range(n):
+                    self.update_E(q + s)
+                    self.update_H(q + s)
+            done += n
+            if progress is not None:
+                progress.update(n)
+
+    def quiesce(self):
+        """make every enqueued halo exchange visible to the current stream (before field reads)."""
+        if self._halo is not None:
+            for f in ("E", "H"):
+                self._halo.wait(self._pending[f])
+                self._pending[f] = None

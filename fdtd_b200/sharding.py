@@ -1,0 +1,126 @@
+"""x-slab partition of a Grid across the ranks of a torch.distributed job, and the one-plane
+halo exchange the Yee update needs each half-step.
+
+One process per GPU.  The stencil reaches one cell along x:
+  * the E half-step at local plane 0 needs (Hy, Hz) of the LEFT neighbour's last plane,
+  * the H half-step at the last local plane needs (Ey, Ez) of the RIGHT neighbour's first plane.
+Field storage carries one ghost x-plane at each end (include/fdtd_b200.h); an exchange is two
+contiguous Ny*Nz planes per neighbour, sent with NCCL send/recv on a side stream so that it
+overlaps with the bulk of the following half-step.  The `gloo` backend (CPU tensors) is
+supported for the host-logic tests only.
+"""
+import torch
+import torch.distributed as dist
+
+
+class Partition:
+    """contiguous, balanced x-slabs: rank r owns global planes [x0, x1)."""
+
+    def __init__(self, Nx, shard="auto"):
+        active = (shard not in (None, False) and dist.is_available() and dist.is_initialized()
+                  and dist.get_world_size() > 1)
+        if shard is True and not active:
+            raise RuntimeError("shard=True needs an initialised torch.distributed job with world_size > 1")
+        self.Nx = Nx
+        self.rank = dist.get_rank() if active else 0
+        self.world = dist.get_world_size() if active else 1
+        if self.world > Nx:
+            raise ValueError(f"cannot shard Nx={Nx} planes over {self.world} ranks")
+        self.x0, self.x1 = self.bounds(self.rank)
+
+    def bounds(self, r):
+        base, rem = divmod(self.Nx, self.world)
+        x0 = r * base + min(r, rem)
+        return x0, x0 + base + (1 if r < rem else 0)
+
+    @property
+    def nx(self):
+        return self.x1 - self.x0
+
+    @property
+    def sharded(self):
+        return self.world > 1
+
+    def local_range(self, g0, g1):
+        """global half-open x-range -> local half-open range clipped to this slab (may be empty)."""
+        a, b = max(g0, self.x0), min(g1, self.x1)
+        if a >= b:
+            return 0, 0
+        return a - self.x0, b - self.x0
+
+    def owner(self, gx):
+        for r in range(self.world):
+            a, b = self.bounds(r)
+            if a <= gx < b:
+                return r
+        raise IndexError(gx)
+
+
+class HaloExchange:
+    """asynchronous one-plane exchanges of (Ey,Ez) to the left and (Hy,Hz) to the right."""
+
+    def __init__(self, part, E, H):
+        self.part, self.E, self.H = part, E, H      # storage tensors (3, nx+2, Ny, Nz)
+        self.cuda = E.is_cuda
+        self.stream = torch.cuda.Stream(device=E.device) if self.cuda else None
+        self.pending = []                            # events / requests not yet waited
+
+    def _ops(self, F, to_left):
+        p, n = self.part, self.part.nx
+        ops = []
+        for c in (1, 2):                             # only the y and z components cross an x face
+            if to_left:
+                if p.rank > 0:
+                    ops.append(dist.P2POp(dist.isend, F[c, 1], p.rank - 1))
+                if p.rank < p.world - 1:
+                    ops.append(dist.P2POp(dist.irecv, F[c, n + 1], p.rank + 1))
+            else:
+                if p.rank < p.world - 1:
+                    ops.append(dist.P2POp(dist.isend, F[c, n], p.rank + 1))
+                if p.rank > 0:
+                    ops.append(dist.P2POp(dist.irecv, F[c, 0], p.rank - 1))
+        return ops
+
+    def start(self, field):
+        """begin the exchange that follows a half-step of `field` ('E' -> left, 'H' -> right).
+        Returns a handle for wait()."""
+        ops = self._ops(self.E if field == "E" else self.H, to_left=(field == "E"))
+        if not ops:
+            return None
+        if self.cuda:
+            main = torch.cuda.current_stream(self.E.device)
+            self.stream.wait_stream(main)
+            with torch.cuda.stream(self.stream):
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()                         # NCCL: orders the side stream, does not block the host
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            return ev
+        return [op.op(op.tensor, op.peer) for op in ops]   # gloo: plain isend / irecv requests
+
+    def wait(self, handle):
+        if handle is None:
+            return
+        if self.cuda:
+            torch.cuda.current_stream(self.E.device).wait_event(handle)
+        else:
+            for r in handle:
+                r.wait()
+
+    def refresh(self):
+        """synchronous exchange of both fields (after the user wrote E or H)."""
+        self.wait(self.start("E"))
+        self.wait(self.start("H"))
+
+
+def all_gather_slabs(part, local, dim):
+    """concatenate per-rank slabs of differing thickness along `dim` (convenience accessor)."""
+    sizes = [part.bounds(r)[1] - part.bounds(r)[0] for r in range(part.world)]
+    nmax = max(sizes)
+    pad_shape = list(local.shape)
+    pad_shape[dim] = nmax
+    buf = local.new_zeros(pad_shape)
+    buf.narrow(dim, 0, local.shape[dim]).copy_(local)
+    out = [torch.empty_like(buf) for _ in range(part.world)]
+    dist.all_gather(out, buf)
+    return torch.cat([o.narrow(dim, 0, s) for o, s in zip(out, sizes)], dim=dim)

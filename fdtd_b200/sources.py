@@ -1,0 +1,236 @@
+"""Sources: PointSource, LineSource (soft, on Ez) and PlaneSource (hard, on one E and one H
+component) with the reference's registration semantics (fdtd/sources.py:25-501).
+
+Per step the reference evaluates one Python scalar per source (`math.sin` / `hanning`) and
+writes it into the fields (fdtd/sources.py:93-109, 278-297, 476-486).  Here the scalars are
+tabulated on the host with the same expressions, uploaded once per run, and injected on the
+device; nothing per-step happens in Python.
+"""
+from math import pi, sin
+
+import numpy as np
+import torch
+
+from . import _capi
+from .backend import backend as bd
+from ._hostmath import HostLib, scalar_in_dtype
+from .waveforms import continuous, pulse
+
+
+def _diagonal_points(grid, x, y, z, convert, min_points, what):
+    """index lists of the diagonal through the box given by slices / lists
+    (fdtd/sources.py:209-276, fdtd/detectors.py:62-112).  numpy linspace semantics."""
+    conv = grid._handle_distance if convert else (lambda v: v)
+    if isinstance(x, list) and isinstance(y, list) and isinstance(z, list):
+        if len(x) != len(y) or len(y) != len(z) or len(z) != len(x):
+            raise IndexError("sources require grid to be indexed with slices or equal length list-indices")
+        return [conv(v) for v in x], [conv(v) for v in y], [conv(v) for v in z]
+    ends = []
+    for s, n in ((x, grid.Nx), (y, grid.Ny), (z, grid.Nz)):
+        if isinstance(s, list):
+            s = slice(conv(s[0]), conv(s[-1]), None)
+        a = conv(s.start if s.start is not None else 0)
+        b = conv(s.stop if s.stop is not None else n)
+        ends.append((a, b))
+    m = max(abs(b - a) for a, b in ends)
+    if m < min_points:
+        raise ValueError(f"a {what} should consist of at least two gridpoints")
+    out = [[int(v) for v in np.linspace(a, b, m, endpoint=False).astype(np.int64)] for a, b in ends]
+    return out[0], out[1], out[2]
+
+
+def local_points(grid, xs, ys, zs):
+    """-> (positions in the list, local linear cell indices) of the points this rank owns."""
+    part = grid._part
+    xs, ys, zs = (np.asarray(v, dtype=np.int64) for v in (xs, ys, zs))
+    # negative indices address from the end, as numpy / torch indexing does in the reference
+    xs = np.where(xs < 0, xs + grid.Nx, xs)
+    ys = np.where(ys < 0, ys + grid.Ny, ys)
+    zs = np.where(zs < 0, zs + grid.Nz, zs)
+    if ((xs < 0) | (xs >= grid.Nx) | (ys < 0) | (ys >= grid.Ny) | (zs < 0) | (zs >= grid.Nz)).any():
+        raise IndexError("index out of range for the grid")
+    mine = np.nonzero((xs >= part.x0) & (xs < part.x1))[0]
+    lin = (xs[mine] - part.x0) * (grid.Ny * grid.Nz) + ys[mine] * grid.Nz + zs[mine]
+    return mine, lin
+
+
+class _TimedSource:
+    """period / pulse bookkeeping shared by Point and Line sources."""
+
+    def __init__(self, period, amplitude, phase_shift, name, pulse, cycle, hanning_dt):
+        self.grid = None
+        self.period = period
+        self.amplitude = amplitude
+        self.phase_shift = phase_shift
+        self.name = name
+        self.pulse = pulse
+        self.cycle = cycle
+        self.frequency = 1.0 / period
+        self.hanning_dt = hanning_dt if hanning_dt is not None else 0.5 / self.frequency
+
+    def _attach(self, grid):
+        self.grid = grid
+        self.grid.sources.append(self)
+        grid._register_name(self)
+
+    def _scalar(self, q):
+        if self.pulse:
+            return pulse(q, self.frequency, self.hanning_dt, self.cycle)
+        return continuous(q, self.period, self.phase_shift)
+
+    def update_E(self):      # the reference's plug-in protocol; the engine does the work
+        pass
+
+    def update_H(self):
+        pass
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(period={self.period}, amplitude={self.amplitude}, "
+                f"phase_shift={self.phase_shift}, name={repr(self.name)})")
+
+
+class PointSource(_TimedSource):
+    """A source placed at a single grid cell: Ez += amplitude * waveform(q) (fdtd/sources.py:25-127)."""
+
+    def __init__(self, period=15, amplitude: float = 1.0, phase_shift: float = 0.0, name: str = None,
+                 pulse: bool = False, cycle: int = 5, hanning_dt: float = 10.0):
+        super().__init__(period, amplitude, phase_shift, name, pulse, cycle, hanning_dt)
+
+    def _register_grid(self, grid, x, y, z):
+        self._attach(grid)
+        try:
+            (x,), (y,), (z,) = x, y, z
+        except (TypeError, ValueError):
+            raise ValueError("a point source should be placed on a single grid cell.")
+        self.x, self.y, self.z = grid._handle_tuple((x, y, z))
+        self.period = grid._handle_time(self.period)
+        self.frequency = 1.0 / self.period
+        _, lin = local_points(grid, [self.x], [self.y], [self.z])
+        self._idx = torch.as_tensor(lin, dtype=torch.int64, device=bd.device)
+        self._profile = bd.ones((len(lin),))
+
+    def _wave_value(self, q):
+        # the reference adds the Python double amplitude*waveform to the array element
+        return self.amplitude * self._scalar(q)
+
+    def _entries(self):
+        return [dict(kind=_capi.SRC_POINTS, field=0, comp=2, idx=self._idx, profile=self._profile)]
+
+    def __str__(self):
+        return "    " + repr(self) + "\n" + f"        @ x={self.x}, y={self.y}, z={self.z}\n"
+
+
+class LineSource(_TimedSource):
+    """A source along the diagonal of a box, gaussian profile, on Ez (fdtd/sources.py:131-315)."""
+
+    def __init__(self, period=15, amplitude: float = 1.0, phase_shift: float = 0.0, name: str = None,
+                 pulse: bool = False, cycle: int = 5, hanning_dt: float = 10.0):
+        super().__init__(period, amplitude, phase_shift, name, pulse, cycle, hanning_dt)
+
+    def _register_grid(self, grid, x, y, z):
+        self._attach(grid)
+        self.x, self.y, self.z = _diagonal_points(grid, x, y, z, True, 2, "LineSource")
+        self.period = grid._handle_time(self.period)
+        self.frequency = 1.0 / self.period
+        # gaussian profile over the SQUARED distance to the middle point (fdtd/sources.py:197-207)
+        hl = HostLib(grid._dtype)
+        L = len(self.x)
+        ix, iy, iz = (np.array(v) for v in (self.x, self.y, self.z))
+        vect = hl.asarray((ix - self.x[L // 2]) ** 2 + (iy - self.y[L // 2]) ** 2 + (iz - self.z[L // 2]) ** 2)
+        profile = hl.exp(-(vect ** 2) / (2 * (0.5 * vect.max()) ** 2))
+        profile /= profile.sum()
+        profile *= self.amplitude
+        self.profile = hl.to_device(profile, bd.device)
+        mine, lin = local_points(grid, self.x, self.y, self.z)
+        self._idx = torch.as_tensor(lin, dtype=torch.int64, device=bd.device)
+        self._profile = self.profile[torch.as_tensor(mine, dtype=torch.int64, device=bd.device)].contiguous()
+
+    def _wave_value(self, q):
+        return self._scalar(q)
+
+    def _entries(self):
+        return [dict(kind=_capi.SRC_POINTS, field=0, comp=2, idx=self._idx, profile=self._profile)]
+
+    def __str__(self):
+        s = "    " + repr(self) + "\n"
+        return s + (f"        @ x=[{self.x[0]}, ... , {self.x[-1]}], y=[{self.y[0]}, ... , {self.y[-1]}], "
+                    f"z=[{self.z[0]}, ... , {self.z[-1]}]\n")
+
+
+class PlaneSource:
+    """A hard source on a one-cell-thick plane: E[pol] = H[hpol] = amplitude*sin(2 pi q/period + phase)
+    (fdtd/sources.py:319-501)."""
+
+    def __init__(self, period=15, amplitude: float = 1.0, phase_shift: float = 0.0, name: str = None,
+                 polarization: str = "z"):
+        self.grid = None
+        self.period = period
+        self.amplitude = amplitude
+        self.phase_shift = phase_shift
+        self.name = name
+        self.polarization = polarization
+
+    def _register_grid(self, grid, x, y, z):
+        self.grid = grid
+        self.grid.sources.append(self)
+        grid._register_name(self)
+        self.x, self.y, self.z = self._handle_slices(x, y, z)
+        self.period = grid._handle_time(self.period)
+        self.frequency = 1.0 / self.period
+        ext = [s.stop - s.start for s in (self.x, self.y, self.z)]
+        self.profile = self.amplitude * bd.ones(tuple(ext))      # reference attribute (uniform)
+
+    def _handle_slices(self, x, y, z):
+        g = self.grid
+        out = []
+        for s, n in ((x, g.Nx), (y, g.Ny), (z, g.Nz)):
+            if not isinstance(s, slice):
+                if isinstance(s, list):
+                    (s,) = s
+                s = slice(g._handle_distance(s), g._handle_distance(s) + 1, None)
+            a = g._handle_distance(s.start if s.start is not None else 0)
+            b = g._handle_distance(s.stop if s.stop is not None else n)
+            out.append(slice(a, b) if a < b else (slice(b, a) if a > b else slice(a, a + 1)))
+        x, y, z = out
+        ext = [x.stop - x.start, y.stop - y.start, z.stop - z.start]
+        if ext.count(0) > 0:
+            raise ValueError("Given location for PlaneSource results in slices of length 0!")
+        if ext.count(1) == 0:
+            raise ValueError("Given location for PlaneSource is not a 2D plane!")
+        if ext.count(1) > 1:
+            raise ValueError("Given location for PlaneSource should have no more than one dimension "
+                             "in which it's flat.\nUse a LineSource for lower dimensional sources.")
+        self._Epol = "xyz".index(self.polarization)
+        if ext[self._Epol] == 1:
+            raise ValueError("PlaneSource cannot be polarized perpendicular to the orientation of the plane.")
+        # H component: fdtd/sources.py:468-472 (pinned by the reference's tests/test_sources.py:25-43)
+        probe, first, second = [(2, 1, 2), (2, 0, 2), (1, 0, 1)][self._Epol]
+        self._Hpol = first if ext[probe] == 1 else second
+        return x, y, z
+
+    def _wave_value(self, q):
+        return sin(2 * pi * q / self.period + self.phase_shift)
+
+    def _entries(self):
+        g = self.grid
+        lx0, lx1 = g._part.local_range(self.x.start, self.x.stop)
+        box = [lx0, lx1, self.y.start, self.y.stop, self.z.start, self.z.stop]
+        amp = scalar_in_dtype(self.amplitude, g._dtype)
+        return [dict(kind=_capi.SRC_BOX, field=0, comp=self._Epol, box=box, amplitude=amp),
+                dict(kind=_capi.SRC_BOX, field=1, comp=self._Hpol, box=box, amplitude=amp)]
+
+    def update_E(self):
+        pass
+
+    def update_H(self):
+        pass
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(period={self.period}, amplitude={self.amplitude}, "
+                f"phase_shift={self.phase_shift}, name={repr(self.name)}, "
+                f"polarization={repr(self.polarization)})")
+
+    def __str__(self):
+        s = "    " + repr(self) + "\n"
+        return s + (f"        @ x=[{self.x.start}, ... , {self.x.stop}], y=[{self.y.start}, ... , {self.y.stop}], "
+                    f"z=[{self.z.start}, ... , {self.z.stop}]\n")

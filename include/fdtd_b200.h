@@ -1,0 +1,185 @@
+/* fdtd_b200.h -- C ABI of the B200-native Yee-update engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of flaport/fdtd: the
+ * per-timestep update Grid.step() = update_E + update_H (reference
+ * fdtd/grid.py:267-325) with everything the reference runs inside it: CPML
+ * psi/phi updates and field corrections (fdtd/boundaries.py:409-487), periodic
+ * copies (fdtd/boundaries.py:184-219), Object / AbsorbingObject /
+ * AnisotropicObject region updates (fdtd/objects.py:118-129, 207-221,
+ * 254-269), Point/Line/Plane source injection (fdtd/sources.py:93-109,
+ * 278-297, 476-486) and Line/Block detector sampling
+ * (fdtd/detectors.py:114-124, 241-263).
+ *
+ * The reference has no FFI: its seam is the Python backend singleton
+ * (fdtd/backend.py:363-439) plus the duck-typed plug-in protocol Grid calls
+ * every half-step (fdtd/grid.py:279-299, 305-325).  A maintainer binds this
+ * library with ctypes (INTEGRATION.md shows the stub); fdtd_b200/_capi.py is
+ * that binding.
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only, no torch / C++ types.
+ *  - every device pointer is owned by the caller (PyTorch tensors on the Python
+ *    side); the library never allocates or frees field memory.
+ *  - every entry point returns 0 on success or a negative FDTD_ERR_* code and
+ *    never throws; fdtd_last_error() gives the thread-local message.
+ *  - work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t
+ *    passed as void*); nothing synchronises implicitly.
+ *  - fields are SoA: one array per component, C-order [x][y][z], z contiguous,
+ *    `plane` = Ny*Nz elements between consecutive x-planes.  Each component
+ *    array has one ghost x-plane below local plane 0 and one above local plane
+ *    Nx-1 (pointers point at local plane 0); the ghosts carry the neighbour
+ *    slab's boundary plane when the grid is sharded in x and make every
+ *    stencil read in-bounds otherwise.
+ */
+#ifndef FDTD_B200_H
+#define FDTD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDTD_ABI_VERSION 3
+
+#define FDTD_F32 0
+#define FDTD_F64 1
+
+#define FDTD_MAX_SLABS 6
+#define FDTD_MAX_POST 16
+#define FDTD_MAX_SOURCES 64
+#define FDTD_MAX_DETECTORS 64
+
+#define FDTD_OK 0
+#define FDTD_ERR_ARG (-1)     /* invalid descriptor / argument */
+#define FDTD_ERR_CUDA (-2)    /* a CUDA runtime call or launch failed */
+#define FDTD_ERR_UNSUPPORTED (-3)
+
+/* tile_class bits (one byte per (x-plane, y-tile, z-tile)) */
+#define FDTD_CLS_VARY_E 1   /* eps^-1 differs from the background somewhere in the tile: stream inv_eps */
+#define FDTD_CLS_VARY_H 2   /* mu^-1 differs from the background: stream inv_mu */
+#define FDTD_CLS_ABSORB 4   /* an AbsorbingObject covers part of the tile: stream absorb */
+#define FDTD_CLS_OBJECT 8   /* an Object covers part of the tile: the PML add needs inv_eps_grid */
+
+/* post-op kinds, executed in registration order after the fused half-step kernel */
+#define FDTD_POST_PERIODIC 0  /* arg = axis: E[0]=E[-1] after E, H[-1]=H[0] after H  (fdtd/boundaries.py:184-219) */
+#define FDTD_POST_PML_ADD 1   /* arg = slab index: E[loc] += sc*eps^-1*phi_E for a PML registered after a periodic boundary */
+
+/* source kinds */
+#define FDTD_SRC_POINTS 0     /* soft: F[comp][idx[n]] += profile[n] * wave[q]   (Point/LineSource) */
+#define FDTD_SRC_BOX 1        /* hard: F[comp][box]     = amplitude  * wave[q]   (PlaneSource) */
+
+/* One CPML slab (replaces the 14 full-size arrays per PML of fdtd/boundaries.py:367-407).
+ * Local index l = global index along `axis` - lo.  Only two psi scalars per cell and per
+ * field can ever be non-zero:
+ *   psi[0] is driven by d F_w / d axis and corrects component u = axis+1 with sign -,
+ *   psi[1] is driven by d F_u / d axis and corrects component w = axis+2 with sign +.
+ * psi layout (psi[1] starts psi_count elements after psi[0]):
+ *   axis 0: [x - x0][y][z]   for local planes x0 <= x < x1
+ *   axis 1: [x][l][z]
+ *   axis 2: [x][y][l]                                                            */
+typedef struct fdtd_slab {
+  int32_t axis;
+  int32_t lo;          /* first GLOBAL index of the slab along axis */
+  int32_t thickness;
+  int32_t fused;       /* 1: field correction applied inside the half-step kernel */
+  int32_t x0, x1;      /* local x-plane range covered by this slab's psi storage */
+  int64_t psi_count;   /* elements per psi scalar */
+  void* psi_E;         /* device [2][psi_count] */
+  void* psi_H;         /* device [2][psi_count] */
+  const void* bE;      /* device [thickness]: exp(-(sigma_E/k + a) * sc)   fdtd/boundaries.py:396 */
+  const void* cE;      /* device [thickness]: (bE-1)*sigma_E/(sigma_E*k + a*k^2)   :397-401 */
+  const void* bH;
+  const void* cH;
+} fdtd_slab;
+
+typedef struct fdtd_source {
+  int32_t kind;        /* FDTD_SRC_* */
+  int32_t field;       /* 0 = E (applied after the E half-step), 1 = H */
+  int32_t comp;        /* component written */
+  int32_t n;           /* FDTD_SRC_POINTS: number of points on this slab */
+  const int64_t* idx;  /* device [n]: local linear cell index x*plane + y*Nz + z */
+  const void* profile; /* device [n] */
+  double amplitude;    /* FDTD_SRC_BOX */
+  int32_t box[6];      /* FDTD_SRC_BOX: local x0,x1,y0,y1,z0,z1 (half-open) */
+  const void* wave;    /* device [wave_len]: per-step scalar, entry q - wave_q0 */
+  int64_t wave_q0;
+  int64_t wave_len;
+} fdtd_source;
+
+typedef struct fdtd_detector {
+  int32_t n;           /* points on this slab */
+  int32_t pad_;
+  const int64_t* idx;  /* device [n]: local linear cell index */
+  void* ring_E;        /* device [capacity][n][3] */
+  void* ring_H;        /* device [capacity][n][3] */
+  int64_t capacity;
+} fdtd_detector;
+
+typedef struct fdtd_desc {
+  int32_t abi_version; /* FDTD_ABI_VERSION */
+  int32_t dtype;       /* FDTD_F32 / FDTD_F64: storage and arithmetic type */
+  int32_t Nx, Ny, Nz;  /* LOCAL slab extents */
+  int32_t x_offset;    /* global index of local plane 0 */
+  int32_t Nx_global;
+  int32_t pad0_;
+  int64_t plane;       /* Ny*Nz */
+  void* E[3];          /* device, local plane 0 of Ex, Ey, Ez */
+  void* H[3];
+  double courant;      /* sc = grid.courant_number (fdtd/grid.py:116-127) */
+  double bg_inv_eps[3];   /* background eps^-1 used by tiles without FDTD_CLS_VARY_E */
+  double bg_inv_mu[3];
+  const void* inv_eps[3];      /* effective eps^-1 of the curl term: grid value outside objects, object value inside; or NULL */
+  const void* inv_eps_grid[3]; /* the grid's own eps^-1 (zero inside objects, fdtd/objects.py:92) for the PML add; NULL = inv_eps */
+  const void* absorb[3];       /* AbsorbingObject absorption factor f (fdtd/objects.py:198-205), zero elsewhere; or NULL */
+  const void* inv_mu[3];       /* or NULL */
+  const uint8_t* tile_class;   /* device [Nx][tiles_y][tiles_z], or NULL = every tile homogeneous */
+  int32_t tile_y, tile_z;      /* tile extents in cells, as returned by fdtd_tile_shape */
+  int32_t n_slabs;
+  int32_t n_post;
+  fdtd_slab slabs[FDTD_MAX_SLABS];        /* registration order */
+  int32_t post_kind[FDTD_MAX_POST];
+  int32_t post_arg[FDTD_MAX_POST];
+  int32_t n_sources;
+  int32_t n_detectors;
+  fdtd_source sources[FDTD_MAX_SOURCES];       /* registration order */
+  fdtd_detector detectors[FDTD_MAX_DETECTORS]; /* registration order */
+  int32_t x_chunk;     /* planes marched per thread block; 0 = library default */
+  int32_t pad1_;
+} fdtd_desc;
+
+/* --- queries ------------------------------------------------------------------------- */
+int32_t fdtd_abi_version(void);
+/* sizeof(fdtd_desc) as the library was compiled: a binding checks its own struct layout against it */
+int64_t fdtd_sizeof_desc(void);
+const char* fdtd_last_error(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t fdtd_launch_count(void);
+/* tile extents the half-step kernels use for a (dtype, Ny, Nz) grid; tile_class must be laid out with them */
+int fdtd_tile_shape(int32_t dtype, int32_t Ny, int32_t Nz, int32_t* tile_y, int32_t* tile_z);
+/* validate a descriptor without launching anything */
+int fdtd_validate(const fdtd_desc* d);
+
+/* --- the hot path -------------------------------------------------------------------- */
+/* Fused E half-step on local planes [x_begin, x_end): psi_E update of every slab, curl_H,
+ * E += sc*eps^-1*curl with object / absorbing coefficients, fused PML field corrections.
+ * Replaces PML.update_phi_E + curl_H + grid.py:283 + Object.update_E + PML.update_E. */
+int fdtd_e_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, void* stream);
+/* Same for H: PML.update_phi_H + curl_E + grid.py:309 + PML.update_H. */
+int fdtd_h_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, void* stream);
+/* What follows the fused kernel inside Grid.update_E / update_H, in the reference's order:
+ * periodic copies and late PML corrections (registration order), sources (registration
+ * order, step index q), detector sampling into ring slot `slot`. */
+int fdtd_post_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
+int fdtd_post_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
+/* Grid.update_E / Grid.update_H (fdtd/grid.py:275-325) on the whole local slab */
+int fdtd_update_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
+int fdtd_update_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
+/* Grid.run (fdtd/grid.py:250-265): nsteps full steps starting at step index q0; detector
+ * samples of step q0+s go to ring slot slot0+s */
+int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDTD_B200_H */
