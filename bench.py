@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- Mcell-updates/s of the fused 3-D Yee step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size S] [--dtype float32]
+
+Workload (config.workload): BASELINE.json configs[3] -- 3-D S^3 (default 1024^3) float32 grid, 10-cell
+PML on all six faces, PointSource(period=20) at the centre, one LineDetector; strong scaling over x-slabs
+for N > 1 (one process per GPU, launched by torchrun; NCCL halo exchange).  A "step" is one full
+E+H update of the whole grid including PML, source and detector work.
+
+Printed JSON (one line, rank 0):
+  value        Mcell-updates/s over all GPUs, fields resident in HBM, device-timed (CUDA events),
+               max over ranks
+  e2e          the same through the public API with host buffers: grid.run(K) + the host->device upload
+               of the waveform tables and the device->host read-back of every detector sample, wall clock
+  roofline     the half-step kernel: algorithmic bytes per launch / its average duration (CUDA events,
+               live) against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline the oracle (CPU port of the reference algorithm, torch-CPU, all host threads) on a bounded
+               sample of the same workload
+--impl reference times that CPU port alone on the same config / metric / unit.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GRID_SPACING = 77.5e-9
+PML_CELLS = 10
+
+
+def build_c4(fd, n, pml=PML_CELLS):
+    """configs[3]: six PMLs, centre PointSource, LineDetector along z through the centre."""
+    g = fd.Grid(shape=(n, n, n), grid_spacing=GRID_SPACING)
+    g[0:pml, :, :] = fd.PML()
+    g[-pml:, :, :] = fd.PML()
+    g[:, 0:pml, :] = fd.PML()
+    g[:, -pml:, :] = fd.PML()
+    g[:, :, 0:pml] = fd.PML()
+    g[:, :, -pml:] = fd.PML()
+    g[n // 2, n // 2, n // 2] = fd.PointSource(period=20, name="src")
+    g[n // 2 + 4, n // 2, pml + 2:n - pml - 2] = fd.LineDetector(name="line")
+    return g
+
+
+def algorithmic_bytes_per_cell_step(n, w, pml=PML_CELLS):
+    """w*(18 + 8*M/N); M/N = PML slab memberships per cell = 6*pml/n for a cube."""
+    return w * (18.0 + 8.0 * 6 * pml / n)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_rate(n, steps, dtype, threads=None):
+    """Mcell-updates/s of the oracle (CPU port of the reference's algorithm) on an n^3 sample of the
+    workload, torch-CPU with all host threads."""
+    import torch
+    from oracle import yee_oracle as yo
+    if threads:
+        torch.set_num_threads(threads)
+    yo.set_backend("torch", dtype)
+    try:
+        g = build_c4(yo, n)
+        g.run(1)                                   # warm-up step (allocations, first-touch)
+        t0 = time.perf_counter()
+        g.run(steps)
+        dt = time.perf_counter() - t0
+    finally:
+        yo.set_backend("numpy", "float64")
+    return n ** 3 * steps / dt / 1e6, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU port on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_size
+    steps = max(1, args.steps)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_port_rate(n, 1, args.dtype)
+    rate, dt, threads = cpu_port_rate(n, steps, args.dtype)
+    sample = f"{n}^3 sample of the {args.size}^3 workload, {steps} steps, torch-CPU {args.dtype}"
+    line = {
+        "impl": "reference", "metric": "Mcell-updates/s (3D Yee E+H step)", "value": rate,
+        "unit": "Mcell-updates/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": rate, "unit": "Mcell-updates/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": rate, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE configs[3]: 3D {args.size}^3 {args.dtype} Yee grid, {PML_CELLS}-cell PML on all six "
+                        f"faces, PointSource(period=20) at centre, LineDetector; x-slab sharded, halo exchange per half-step",
+            "grid": [args.size] * 3, "pml_cells": PML_CELLS, "parallelism": f"x-slabs x{args.gpus}",
+            "l2_policy": "inputs larger than L2 (fields are 24 GiB at 1024^3; every step streams all of them)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--cpu-size", type=int, default=192, help="edge of the CPU-baseline sample grid")
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--x-chunk", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    import fdtd_b200 as fd
+    from fdtd_b200 import _capi
+    fd.set_backend("cuda." + args.dtype)
+    lib = _capi.load()
+    n, K, W = args.size, args.steps, args.warmup
+    w = 4 if args.dtype == "float32" else 8
+
+    grid = build_c4(fd, n)
+    grid._x_chunk = args.x_chunk
+    det = grid.detectors[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up --------------------------------------------------------------------------------
+    grid.run(W, progress_bar=False)
+    eng = grid._engine
+    eng.flush_detectors()
+    barrier()
+
+    # ---- value: K steps, fields resident, device-timed ---------------------------------------------
+    eng._ensure_wave(grid.time_steps_passed, K)
+    launches0 = lib.fdtd_launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        start.record()
+        grid.run(K, progress_bar=False)
+        stop.record()
+        barrier()
+    launches = lib.fdtd_launch_count() - launches0
+    ms = torch.tensor([start.elapsed_time(stop)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = n ** 3 * K / (ms * 1e-3) / 1e6
+    eng.flush_detectors()
+
+    # ---- e2e: public API, host buffers in the timed region -----------------------------------------
+    n_det_before = len(det.E)
+    eng._wave = None                       # the waveform table is rebuilt and uploaded inside the region
+    barrier()
+    t0 = time.perf_counter()
+    grid.run(K, progress_bar=False)
+    traces = (det.E, det.H)                # flushes the device ring to the host
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = n ** 3 * K / float(e2e_s.item()) / 1e6
+    assert len(traces[0]) == n_det_before + K
+    h2d = sum(1 for _ in grid.sources) * eng._wave[1] * w / K
+    d2h = 2 * det._n_points * 3 * w
+
+    # ---- roofline: the half-step kernel alone, live ------------------------------------------------
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    d = eng.desc
+    reps = max(4, min(K, 10))
+    barrier()
+    eng.quiesce()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(reps):
+        _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 0, d.Nx, st))
+        _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), 0, d.Nx, st))
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / (2 * reps)
+    cells_local = d.Nx * n * n
+    bytes_per_launch = algorithmic_bytes_per_cell_step(n, w) / 2 * cells_local
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            t = json.load(open(tpath))
+            if t.get("size") == n and t.get("dtype") == args.dtype and world == 1:
+                traffic = t.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "fdtd::halfstep_kernel (E and H half-steps)", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "kernel_ms_per_launch": kernel_ms,
+                "bytes_per_cell_step": algorithmic_bytes_per_cell_step(n, w)}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, dt, threads = cpu_port_rate(args.cpu_size, args.cpu_steps, args.dtype)
+        cpu = {"value": rate, "unit": "Mcell-updates/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_size}^3 sample of the workload, {args.cpu_steps} steps, oracle on torch-CPU "
+                         f"{args.dtype} ({dt:.1f} s)"}
+
+    if rank == 0:
+        line = {
+            "metric": "Mcell-updates/s (3D Yee E+H step)", "value": value, "unit": "Mcell-updates/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if w == 4 else "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "Mcell-updates/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+            "hbm_roofline_frac_whole_step": (algorithmic_bytes_per_cell_step(n, w) * n ** 3 * K
+                                             / (ms * 1e-3) / 1e9) / (peak * world),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,7 +52,7 @@ class _Detector:
         for f, ring, n in (("E", self._ring_E, nE), ("H", self._ring_H, nH)):
             if n == 0:
                 continue
-            local = ring[:n, :self._n_local].cpu().numpy()
+            local = ring[:n, :self._n_local].to("cpu", copy=True).numpy()
             if part.sharded:
                 gathered = [None] * part.world
                 dist.all_gather_object(gathered, (self._positions, local))

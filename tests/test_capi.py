@@ -1,0 +1,83 @@
+"""The C-ABI library: loads, exports every symbol include/fdtd_b200.h declares, and the ctypes
+mirror of fdtd_desc has the library's layout.  No compute calls (CPU-only container)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fdtd_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fdtd_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    import __graft_entry__ as entry
+    entry.build()
+    return entry.OUT
+
+
+def test_header_declares_the_hot_path():
+    names = declared_functions()
+    for must in ("fdtd_e_halfstep", "fdtd_h_halfstep", "fdtd_post_E", "fdtd_post_H", "fdtd_update_E",
+                 "fdtd_update_H", "fdtd_run", "fdtd_validate", "fdtd_tile_shape", "fdtd_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+
+
+def test_binding_matches_library(lib_path):
+    from fdtd_b200 import _capi
+    lib = _capi.bind(lib_path)          # checks ABI version and sizeof(fdtd_desc)
+    assert set(_capi.EXPORTS) == set(declared_functions())
+    ty, tz = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.fdtd_tile_shape(_capi.F32, 1024, 1024, ctypes.byref(ty), ctypes.byref(tz)) == 0
+    assert (ty.value, tz.value) == (8, 128)
+    assert lib.fdtd_tile_shape(_capi.F64, 97, 1, ctypes.byref(ty), ctypes.byref(tz)) == 0
+    assert (ty.value, tz.value) == (128, 1)
+    assert lib.fdtd_tile_shape(7, 4, 4, ctypes.byref(ty), ctypes.byref(tz)) < 0
+    assert b"bad argument" in lib.fdtd_last_error()
+
+
+def test_validate_rejects_bad_descriptors(lib_path):
+    from fdtd_b200 import _capi
+    lib = _capi.bind(lib_path)
+    d = _capi.Desc()
+    assert lib.fdtd_validate(ctypes.byref(d)) == -1          # ABI version 0
+    d.abi_version = _capi.ABI_VERSION
+    d.dtype = 5
+    assert lib.fdtd_validate(ctypes.byref(d)) == -1
+    assert b"dtype" in lib.fdtd_last_error()
+    d.dtype = _capi.F32
+    d.Nx = d.Ny = d.Nz = 4
+    d.Nx_global = 4
+    d.plane = 15
+    assert lib.fdtd_validate(ctypes.byref(d)) == -1
+    assert b"plane" in lib.fdtd_last_error()
+    d.plane = 16
+    assert lib.fdtd_validate(ctypes.byref(d)) == -1          # null field pointers
+    assert b"null field" in lib.fdtd_last_error()
+
+
+def test_no_cpu_fallback_without_cuda():
+    """the product refuses to run without a GPU instead of falling back (CPU container only)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import fdtd_b200 as fd
+    with pytest.raises(RuntimeError):
+        fd.set_backend("cuda.float32")
+    with pytest.raises(ValueError):
+        fd.set_backend("numpy")
+    with pytest.raises(ValueError):
+        fd.set_backend("torch.float64")

@@ -1,0 +1,181 @@
+"""Kernel logic + host layer on the CPU: the .cu file compiled as C++ against tests/emu/cuda_emu.h
+(a serial thread-by-thread interpreter, TEST INFRASTRUCTURE -- see that header) driven through the
+same C ABI and the same Python host code as on the GPU, compared with
+
+  * the committed golden outputs of the unmodified reference (tests/golden), and
+  * the oracle, on extra scenes that exercise every vector width, odd extents, registration
+    orders, overlapping objects, user pokes between half-steps, re-bakes and ring flushes.
+
+float64: rel-L2 <= 1e-12 is the stated bar; the arithmetic order is the reference's, so the
+assertion is the stronger bit-equality wherever the reference's own operation order is kept
+(everything except AnisotropicObject cells, whose bmm rounds sc*(eps^-1*curl) instead of
+(sc*eps^-1)*curl).  float32: bar 1e-5 against the reference's true-float32 run.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import scenes
+from emu.harness import use_emu
+from oracle import yee_oracle as yo
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NOT_BITWISE = {"objects3d"}        # contains an AnisotropicObject (see module docstring)
+
+
+def run_scene(fd, build, steps, **kw):
+    g = build(fd, **kw)
+    g.run(steps, progress_bar=False)
+    return scenes.dump(g)
+
+
+def run_oracle(build, steps, dtype="float64", **kw):
+    yo.set_backend("numpy" if dtype == "float64" else "torch", dtype)
+    try:
+        g = build(yo, **kw)
+        g.run(steps)
+        return scenes.dump(g)
+    finally:
+        yo.set_backend("numpy", "float64")
+
+
+def compare(got, want, tol, bitwise):
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        err = scenes.rel_l2(got[k], want[k])
+        assert err <= tol, f"{k}: rel-L2 {err:.3e} > {tol}"
+        if bitwise:
+            assert np.array_equal(got[k], want[k]), f"{k}: not bit-identical (rel-L2 {err:.3e})"
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*_f*.npz"))),
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_emu_vs_reference_golden(path):
+    scene, prec = os.path.basename(path)[:-4].rsplit("_", 1)
+    gold = dict(np.load(path))
+    steps = int(gold.pop("steps"))
+    dtype = "float64" if prec == "f64" else "float32"
+    fd = use_emu(dtype)
+    build, _ = scenes.SCENES[scene]
+    got = run_scene(fd, build, steps)
+    compare(got, gold, 1e-12 if prec == "f64" else 1e-5, bitwise=scene not in NOT_BITWISE)
+
+
+# extents chosen so that Nz hits vector widths 4, 2 and 1 in float32 and 2, 1 in float64,
+# partial tiles in y and z, and thickness > tile
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n,t", [((13, 11, 12), 4), ((12, 9, 10), 3), ((11, 12, 7), 3), ((9, 40, 36), 5),
+                                 ((10, 5, 132), 2)])
+def test_emu_vs_oracle_shapes(n, t, dtype):
+    fd = use_emu(dtype)
+    got = run_scene(fd, scenes.pml3d, 25, n=n, t=t)
+    want = run_oracle(scenes.pml3d, 25, dtype, n=n, t=t)
+    compare(got, want, 1e-12 if dtype == "float64" else 1e-5, bitwise=True)
+
+
+def _late_pml(fd):
+    """PMLs registered AFTER periodic boundaries: their correction must follow the copy."""
+    g = fd.Grid(shape=(14, 12, 10), grid_spacing=50e-9)
+    g[:, :, 0] = fd.PeriodicBoundary()
+    g[:, 0:4, :] = fd.PML()
+    g[0:3, :, :] = fd.PML()
+    g[-3:, :, :] = fd.PML()
+    g[:, -4:, :] = fd.PML()
+    g[7, 6, 0] = fd.PointSource(period=10)
+    g[6, 5, 9] = fd.PointSource(period=7, amplitude=0.5)
+    g[3:11, 6, 4] = fd.LineDetector()
+    return g
+
+
+def _overlap(fd):
+    """two overlapping plain objects (both add their term), one inheriting a zeroed border."""
+    g = fd.Grid(shape=(16, 14, 12), grid_spacing=50e-9, permittivity=1.5)
+    g[0:4, :, :] = fd.PML()
+    g[4:10, 3:9, 2:8] = fd.Object(permittivity=2.0, name="a")
+    g[8:16, 5:14, 4:12] = fd.Object(permittivity=3.0, name="b")      # reaches the grid's last planes
+    g[6:9, 10:13, 1:3] = fd.AbsorbingObject(permittivity=1.2, conductivity=3e4)
+    g[2, 7, 6] = fd.PointSource(period=12)
+    g[1:15, 7, 5] = fd.LineDetector()
+    return g
+
+
+@pytest.mark.parametrize("builder", [_late_pml, _overlap], ids=["late_pml", "overlap"])
+def test_emu_vs_oracle_orderings(builder):
+    fd = use_emu("float64")
+    got = run_scene(fd, builder, 40)
+    want = run_oracle(builder, 40)
+    # overlapping objects: (c1 + c2)*curl here vs c1*curl + c2*curl in the reference -> tolerance
+    compare(got, want, 1e-12, bitwise=builder is _late_pml)
+
+
+def test_pokes_between_half_steps_and_rebake():
+    """update_E(); poke E; update_H() as the reference's tests do (tests/test_detectors.py:62-70),
+    then register an object mid-run (re-bake) and continue."""
+    def drive(fd):
+        g = scenes.pml3d(fd, n=(12, 10, 8), t=3)
+        for n in range(20):
+            g.update_E()
+            g.E[6, 5, 4, 2] = 0.25 * n
+            g.update_H()
+            g.time_steps_passed += 1
+        g[3:6, 2:5, 2:6] = fd.Object(permittivity=2.2)
+        g.run(15, progress_bar=False)
+        return scenes.dump(g)
+    got = drive(use_emu("float64"))
+    yo.set_backend("numpy", "float64")
+    want = drive(yo)
+    compare(got, want, 1e-12, bitwise=True)
+
+
+def test_detector_ring_flush_and_step_granularity(monkeypatch):
+    """a tiny ring forces several device->host batches; run(n) == n * step()."""
+    import fdtd_b200.engine as engine
+    monkeypatch.setattr(engine, "RING_BYTES", 1)            # capacity clamps to its minimum (16)
+    fd = use_emu("float64")
+    a = scenes.c4small(fd, n=(10, 9, 8), t=2)
+    a.run(50, progress_bar=False)
+    assert a._engine.ring_capacity == 16
+    b = scenes.c4small(fd, n=(10, 9, 8), t=2)
+    for _ in range(50):
+        b.step()
+    da, db = scenes.dump(a), scenes.dump(b)
+    assert da["det0_E"].shape == (50, 6, 3)
+    compare(da, db, 0.0, bitwise=True)
+    want = run_oracle(scenes.c4small, 50, n=(10, 9, 8), t=2)
+    compare(da, want, 1e-12, bitwise=True)
+
+
+def test_x_chunk_invariance():
+    fd = use_emu("float32")
+    outs = []
+    for chunk in (1, 5, 64):
+        g = scenes.objects3d(fd)
+        g._x_chunk = chunk
+        g.run(12, progress_bar=False)
+        outs.append(scenes.dump(g))
+    compare(outs[0], outs[1], 0.0, bitwise=True)
+    compare(outs[0], outs[2], 0.0, bitwise=True)
+
+
+def test_homogeneous_grid_allocates_no_material_arrays():
+    fd = use_emu("float32")
+    g = scenes.c4small(fd, n=(12, 12, 12), t=3)
+    g.run(3, progress_bar=False)
+    assert g._inv_eps is None and g._inv_mu is None and g._engine.tile_class is None
+
+
+def test_user_write_to_materials_triggers_rebake():
+    fd = use_emu("float64")
+    g = scenes.c4small(fd, n=(12, 12, 12), t=3)
+    g.run(5, progress_bar=False)
+    g.inverse_permittivity[4:8, 4:8, 4:8, :] = 0.5
+    g.run(5, progress_bar=False)
+    yo.set_backend("numpy", "float64")
+    o = scenes.c4small(yo, n=(12, 12, 12), t=3)
+    o.run(5)
+    o.inverse_permittivity[4:8, 4:8, 4:8, :] = 0.5
+    o.run(5)
+    compare(scenes.dump(g), scenes.dump(o), 1e-12, bitwise=True)

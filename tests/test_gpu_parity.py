@@ -1,0 +1,194 @@
+"""Parity of the CUDA path (through the C ABI, on a real GPU) against
+
+  * tests/golden: outputs of the unmodified reference (float64 numpy and true-float32 torch),
+  * the oracle on seeded scenes at sizes it finishes in seconds,
+  * size-independent properties at BASELINE.json's full sizes (exact linearity under a power-of-two
+    amplitude, x-chunk invariance, run(n) == n*step(), a quiescent grid stays exactly zero).
+
+Tolerances are north_star's: rel-L2 <= 1e-12 (float64), <= 1e-5 (float32) on final E, H and on every
+detector trace; bit-equality is asserted in addition where the reference's operation order is kept.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from oracle import yee_oracle as yo
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {"float64": 1e-12, "float32": 1e-5}
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def cuda(dtype):
+    import fdtd_b200 as fd
+    fd.set_backend("cuda." + dtype)
+    from fdtd_b200 import _capi
+    assert fd.backend.lib is _capi.load()          # the nvcc-built library, nothing else
+    return fd
+
+
+def run_scene(fd, build, steps, **kw):
+    g = build(fd, **kw)
+    g.run(steps, progress_bar=False)
+    return scenes.dump(g)
+
+
+def run_oracle(build, steps, dtype="float64", **kw):
+    yo.set_backend("numpy" if dtype == "float64" else "torch", dtype)
+    try:
+        g = build(yo, **kw)
+        g.run(steps)
+        return scenes.dump(g)
+    finally:
+        yo.set_backend("numpy", "float64")
+
+
+def compare(got, want, tol, bitwise=False):
+    assert set(got) == set(want)
+    worst = 0.0
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        err = scenes.rel_l2(got[k], want[k])
+        worst = max(worst, err)
+        assert err <= tol, f"{k}: rel-L2 {err:.3e} > {tol}"
+        if bitwise:
+            assert np.array_equal(got[k], want[k]), f"{k}: not bit-identical (rel-L2 {err:.3e})"
+    return worst
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*_f*.npz"))),
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_cuda_vs_reference_golden(path):
+    scene, prec = os.path.basename(path)[:-4].rsplit("_", 1)
+    gold = dict(np.load(path))
+    steps = int(gold.pop("steps"))
+    dtype = "float64" if prec == "f64" else "float32"
+    got = run_scene(cuda(dtype), scenes.SCENES[scene][0], steps)
+    worst = compare(got, gold, TOL[dtype])
+    print(f"{scene}/{dtype}: worst rel-L2 vs reference {worst:.3e}")
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n,t", [((13, 11, 12), 4), ((12, 9, 10), 3), ((11, 12, 7), 3), ((9, 40, 36), 5),
+                                 ((10, 5, 132), 2), ((40, 72, 260), 6)])
+def test_cuda_vs_oracle_shapes(n, t, dtype):
+    got = run_scene(cuda(dtype), scenes.pml3d, 25, n=n, t=t)
+    want = run_oracle(scenes.pml3d, 25, dtype, n=n, t=t)
+    compare(got, want, TOL[dtype], bitwise=True)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_cuda_vs_oracle_objects_medium(dtype):
+    """config-2/3 structure at 64x56x48: heterogeneous eps/mu, all object kinds, all source kinds."""
+    n = (64, 56, 48)
+
+    def build(fd):
+        rs = np.random.RandomState(11)
+        eps = 1.0 + rs.rand(*n, 3)
+        g = fd.Grid(shape=n, grid_spacing=77.5e-9, permittivity=eps)
+        for key in ((slice(0, 8), slice(None), slice(None)), (slice(-8, None), slice(None), slice(None)),
+                    (slice(None), slice(0, 8), slice(None)), (slice(None), slice(-8, None), slice(None)),
+                    (slice(None), slice(None), slice(0, 8)), (slice(None), slice(None), slice(-8, None))):
+            g[key] = fd.PML()
+        g[12, :, :] = fd.PlaneSource(period=20, polarization="y")
+        g[20:30, 10:40, 12:40] = fd.AbsorbingObject(permittivity=2.5, conductivity=1.5e4)
+        g[34:50, 16:48, 8:40] = fd.Object(permittivity=1.0 + rs.rand(16, 32, 32))
+        g[52:60, 2:30, 30:46] = fd.Object(permittivity=4.0)       # overlaps three PMLs
+        g[16:40, 20:44, 24] = fd.LineSource(period=15, amplitude=2.0)
+        g[8:56, 28, 24] = fd.LineDetector()
+        g[40:42, 30:31, 20:22] = fd.BlockDetector()
+        return g
+
+    got = run_scene(cuda(dtype), build, 40)
+    want = run_oracle(build, 40, dtype)
+    compare(got, want, TOL[dtype], bitwise=True)
+
+
+def test_pokes_and_rebake_on_gpu():
+    def drive(fd):
+        g = scenes.pml3d(fd, n=(20, 18, 16), t=4)
+        for n in range(20):
+            g.update_E()
+            g.E[10, 9, 8, 2] = 0.25 * n
+            g.update_H()
+            g.time_steps_passed += 1
+        g[3:6, 2:5, 2:6] = fd.Object(permittivity=2.2)
+        g.run(15, progress_bar=False)
+        g.reset()
+        g.run(5, progress_bar=False)
+        return scenes.dump(g)
+    got = drive(cuda("float64"))
+    yo.set_backend("numpy", "float64")
+    want = drive(yo)
+    compare(got, want, 1e-12, bitwise=True)
+
+
+# ---- full-size properties (BASELINE.json configs 1-3 sizes) -------------------------------------
+
+def _c4(fd, n, amplitude=1.0, with_source=True):
+    g = fd.Grid(shape=(n, n, n), grid_spacing=77.5e-9)
+    g[0:10, :, :] = fd.PML()
+    g[-10:, :, :] = fd.PML()
+    g[:, 0:10, :] = fd.PML()
+    g[:, -10:, :] = fd.PML()
+    g[:, :, 0:10] = fd.PML()
+    g[:, :, -10:] = fd.PML()
+    if with_source:
+        g[n // 2, n // 2, n // 2] = fd.PointSource(period=20, amplitude=amplitude)
+    g[n // 2 + 4, n // 2, 12:n - 12] = fd.LineDetector()
+    return g
+
+
+@pytest.mark.parametrize("n,dtype,steps", [(256, "float64", 60), (512, "float32", 40)])
+def test_full_size_linearity_is_exact(n, dtype, steps):
+    """doubling the source amplitude doubles every field value and detector sample exactly
+    (scaling by a power of two commutes with every rounding of the update)."""
+    fd = cuda(dtype)
+    a = _c4(fd, n, 1.0)
+    a.run(steps, progress_bar=False)
+    Ea = a.E.clone()
+    da = np.stack(a.detectors[0].E)
+    del a
+    b = _c4(fd, n, 2.0)
+    b.run(steps, progress_bar=False)
+    assert float(Ea.abs().max()) > 0
+    assert torch.equal(b.E, 2 * Ea)
+    assert np.array_equal(np.stack(b.detectors[0].E), 2 * da)
+
+
+def test_full_size_chunk_invariance_and_stepping():
+    fd = cuda("float32")
+    ref = _c4(fd, 256)
+    ref.run(30, progress_bar=False)
+    other = _c4(fd, 256)
+    other._x_chunk = 7
+    for _ in range(30):
+        other.step()
+    assert torch.equal(ref.E, other.E) and torch.equal(ref.H, other.H)
+    assert np.array_equal(np.stack(ref.detectors[0].H), np.stack(other.detectors[0].H))
+
+
+def test_quiescent_grid_stays_zero():
+    fd = cuda("float32")
+    g = _c4(fd, 256, with_source=False)
+    g.run(10, progress_bar=False)
+    assert float(g.E.abs().max()) == 0.0 and float(g.H.abs().max()) == 0.0
+
+
+def test_c4_256_vs_oracle_prefix():
+    """the bench workload at 96^3 against the oracle (the oracle needs seconds per step beyond that)."""
+    def build(fd):
+        return _c4(fd, 96)
+    got = run_scene(cuda("float32"), build, 30)
+    want = run_oracle(build, 30, "float32")
+    compare(got, want, 1e-5, bitwise=True)
