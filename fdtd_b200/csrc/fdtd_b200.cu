@@ -69,10 +69,14 @@ int pow2_ceil(int v) {
   return p;
 }
 
+#ifndef FDTD_MAX_VEC_F32
+#define FDTD_MAX_VEC_F32 4
+#endif
+
 Geometry geometry(int dtype, int Ny, int Nz) {
   Geometry g;
   if (dtype == FDTD_F32)
-    g.vec = (Nz % 4 == 0) ? 4 : ((Nz % 2 == 0) ? 2 : 1);
+    g.vec = (Nz % 4 == 0 && FDTD_MAX_VEC_F32 >= 4) ? 4 : ((Nz % 2 == 0 && FDTD_MAX_VEC_F32 >= 2) ? 2 : 1);
   else
     g.vec = (Nz % 2 == 0) ? 2 : 1;
   int nvz = (Nz + g.vec - 1) / g.vec;
@@ -80,12 +84,22 @@ Geometry geometry(int dtype, int Ny, int Nz) {
   if (g.lanes_z > 32) g.lanes_z = 32;
   g.lanes_shift = 0;
   while ((1 << g.lanes_shift) < g.lanes_z) ++g.lanes_shift;
-  g.rows = 256 / g.lanes_z;
+  g.rows = FDTD_BLOCK_THREADS / g.lanes_z;
   int ny2 = pow2_ceil(Ny);
   if (g.rows > ny2) g.rows = ny2;
   g.tile_y = g.rows;
   g.tile_z = g.lanes_z * g.vec;
   return g;
+}
+
+// planes marched per block: enough blocks for ~32 waves of 3 blocks x 148 SMs (tail effect),
+// at most 32 planes (measured on B200: profiles/tune_r1.md)
+int default_x_chunk(const Geometry& g, int nx, int Ny, int Nz) {
+  long long tiles = (long long)((Ny + g.tile_y - 1) / g.tile_y) * ((Nz + g.tile_z - 1) / g.tile_z);
+  long long c = (long long)nx * tiles / (148LL * 3 * 32);
+  int chunk = 4;
+  while (chunk * 2 <= c && chunk < 32) chunk *= 2;
+  return chunk;
 }
 
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
@@ -203,7 +217,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, void* stream) {
   P.Nx_global = d->Nx_global;
   P.x_begin = x_begin;
   P.x_end = x_end;
-  P.x_chunk = d->x_chunk > 0 ? d->x_chunk : 32;
+  P.x_chunk = d->x_chunk > 0 ? d->x_chunk : default_x_chunk(g, x_end - x_begin, d->Ny, d->Nz);
   P.lanes_z = g.lanes_z;
   P.lanes_shift = g.lanes_shift;
   P.rows = g.rows;

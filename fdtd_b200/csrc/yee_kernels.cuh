@@ -22,6 +22,17 @@
 //   PML.update_E/H             fdtd/boundaries.py:409-431
 #pragma once
 
+// tuning knobs (defaults are the measured best on B200, see profiles/)
+#ifndef FDTD_MIN_BLOCKS
+#define FDTD_MIN_BLOCKS 3      // resident 256-thread blocks per SM the register budget is sized for
+#endif
+#ifndef FDTD_BLOCK_THREADS
+#define FDTD_BLOCK_THREADS 256 // threads per block of the half-step kernels
+#endif
+#ifndef FDTD_PREFETCH_PLANES
+#define FDTD_PREFETCH_PLANES 1 // software prefetch into L2 this many x-planes ahead (0 = off)
+#endif
+
 namespace fdtd {
 
 typedef long long i64;
@@ -38,6 +49,15 @@ FDTD_DEV Pack<T, VEC> ldv(const T* p) {
 template <typename T, int VEC>
 FDTD_DEV void stv(T* p, const Pack<T, VEC>& x) {
   *reinterpret_cast<Pack<T, VEC>*>(p) = x;
+}
+
+// fire-and-forget L2 prefetch of the line holding p (no registers, no scoreboard)
+FDTD_DEV void prefetch_l2(const void* p) {
+#if !defined(FDTD_EMU) && FDTD_PREFETCH_PLANES > 0
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
 }
 
 template <typename T>
@@ -146,7 +166,7 @@ FDTD_DEV void slab_cells(const SlabK<T>& S, bool contiguous, i64 idx0, int l0, i
 }
 
 template <typename T, int VEC, bool IS_E>
-__global__ void __launch_bounds__(256) halfstep_kernel(const HalfStepParams<T> P) {
+__global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_kernel(const HalfStepParams<T> P) {
   const int tid = threadIdx.x;
   const int lane = tid & (P.lanes_z - 1);
   const int row = tid >> P.lanes_shift;
@@ -196,6 +216,17 @@ __global__ void __launch_bounds__(256) halfstep_kernel(const HalfStepParams<T> P
     const i64 off = (i64)i * plane + p;
     const unsigned cls = P.cls ? P.cls[(i64)i * cls_stride + cls_tile] : 0u;
 
+#if FDTD_PREFETCH_PLANES > 0
+    if (i + FDTD_PREFETCH_PLANES < P.Nx) {
+      const i64 pf = off + (i64)FDTD_PREFETCH_PLANES * plane;
+      prefetch_l2(Gx + pf);
+      prefetch_l2(Gy + pf + (IS_E ? 0 : plane));
+      prefetch_l2(Gz + pf + (IS_E ? 0 : plane));
+      prefetch_l2(Fx + pf);
+      prefetch_l2(Fy + pf);
+      prefetch_l2(Fz + pf);
+    }
+#endif
     // ---- loads -------------------------------------------------------------------------
     Pack<T, VEC> gx = ldv<T, VEC>(Gx + off);
     Pack<T, VEC> gy, gz, xnb_y, xnb_z;

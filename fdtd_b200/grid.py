@@ -10,6 +10,8 @@ Differences a user can see, all deliberate:
   * under an initialised torch.distributed job the grid is split into x-slabs, one per rank
     (`shard="auto"`); `grid.E` then gathers (a copy), `grid.E_local` is the local view.
 """
+import gc
+
 import torch
 
 from . import constants as const
@@ -61,6 +63,7 @@ class Grid:
         self.time_step = self.courant_number * self.grid_spacing / const.c
 
         self._dtype = bd.float
+        gc.collect()      # grids hold reference cycles (plug-ins point back at them): free dead ones' HBM first
         self._part = Partition(self.Nx, shard)
         nx = self._part.nx
         self._E = bd.zeros((3, nx + 2, self.Ny, self.Nz))

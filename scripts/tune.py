@@ -1,0 +1,108 @@
+"""Kernel tuning harness (development tool).
+
+  python scripts/tune.py build      # here, no GPU: nvcc every variant into fdtd_b200/_variants/
+  python scripts/tune.py run        # on the B200: time the E+H half-step kernels of every variant
+
+Each variant is the same source compiled with different -D knobs (yee_kernels.cuh); timing is the
+bench's kernel-only loop (CUDA events around 2*reps half-step launches at size^3 float32, six PMLs).
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VDIR = os.path.join(ROOT, "fdtd_b200", "_variants")
+
+VARIANTS = {
+    "base": [],
+    "mb3": ["-DFDTD_MIN_BLOCKS=3"],
+    "mb4": ["-DFDTD_MIN_BLOCKS=4"],
+    "pf1": ["-DFDTD_PREFETCH_PLANES=1"],
+    "pf2": ["-DFDTD_PREFETCH_PLANES=2"],
+    "pf4": ["-DFDTD_PREFETCH_PLANES=4"],
+    "mb3_pf2": ["-DFDTD_MIN_BLOCKS=3", "-DFDTD_PREFETCH_PLANES=2"],
+    "mb3_pf1": ["-DFDTD_MIN_BLOCKS=3", "-DFDTD_PREFETCH_PLANES=1"],
+    "mb3_pf3": ["-DFDTD_MIN_BLOCKS=3", "-DFDTD_PREFETCH_PLANES=3"],
+    "mb4_pf2": ["-DFDTD_MIN_BLOCKS=4", "-DFDTD_PREFETCH_PLANES=2"],
+    "t128_mb6_pf2": ["-DFDTD_BLOCK_THREADS=128", "-DFDTD_MIN_BLOCKS=6", "-DFDTD_PREFETCH_PLANES=2"],
+    "t128_mb4_pf2": ["-DFDTD_BLOCK_THREADS=128", "-DFDTD_MIN_BLOCKS=4", "-DFDTD_PREFETCH_PLANES=2"],
+    "v2_mb4_pf2": ["-DFDTD_MAX_VEC_F32=2", "-DFDTD_MIN_BLOCKS=4", "-DFDTD_PREFETCH_PLANES=2"],
+    "v2_mb6_pf2": ["-DFDTD_MAX_VEC_F32=2", "-DFDTD_MIN_BLOCKS=6", "-DFDTD_PREFETCH_PLANES=2"],
+}
+
+
+def build():
+    import __graft_entry__ as entry
+    os.makedirs(VDIR, exist_ok=True)
+    only = sys.argv[2].split(",") if len(sys.argv) > 2 else list(VARIANTS)
+    for name, defs in VARIANTS.items():
+        if name not in only:
+            continue
+        out = os.path.join(VDIR, f"lib_{name}.so")
+        cmd = ["nvcc"] + entry.NVCC_FLAGS + defs + ["-Xptxas", "-v", "-I", os.path.join(ROOT, "include"),
+                                                  "-I", os.path.join(ROOT, "fdtd_b200", "csrc"), entry.SRC, "-o", out]
+        r = subprocess.run(cmd, check=True, capture_output=True, text=True)
+        lines = r.stderr.splitlines()
+        for n, l in enumerate(lines):
+            if "Compiling entry function" in l and ("halfstep_kernelIfLi4ELb" in l or ("MAX_VEC_F32=2" in " ".join(defs) and "halfstep_kernelIfLi2ELb" in l)):
+                print(name, "E" if "ELb1" in l else "H", " | ".join(x.strip() for x in lines[n + 1:n + 4]))
+
+
+def run(size=1024, dtype="float32", reps=10, chunks=(32,)):
+    import torch
+    import fdtd_b200 as fd
+    from fdtd_b200 import _capi
+    from fdtd_b200.backend import backend
+    sys.path.insert(0, ROOT)
+    from bench import build_c4, algorithmic_bytes_per_cell_step
+    fd.set_backend("cuda." + dtype)
+    w = 4 if dtype == "float32" else 8
+    results = []
+    names = sys.argv[2].split(",") if len(sys.argv) > 2 else list(VARIANTS)
+    for name in names:
+        path = os.path.join(VDIR, f"lib_{name}.so")
+        if not os.path.exists(path):
+            print("missing", path)
+            continue
+        lib = _capi.bind(path)
+        backend.lib = lib
+        for chunk in chunks:
+            grid = build_c4(fd, size)
+            grid._x_chunk = chunk
+            grid.run(2, progress_bar=False)
+            eng = grid._engine
+            d = eng.desc
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            out = {}
+            for label, fn in (("E", lib.fdtd_e_halfstep), ("H", lib.fdtd_h_halfstep)):
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    _capi.check(lib, fn(C.byref(d), 0, d.Nx, st))
+                b.record()
+                torch.cuda.synchronize()
+                out[label] = a.elapsed_time(b) / reps
+            bytes_launch = algorithmic_bytes_per_cell_step(size, w) / 2 * size ** 3
+            gbs = bytes_launch / ((out["E"] + out["H"]) / 2 * 1e-3) / 1e9
+            rec = {"variant": name, "x_chunk": chunk, "E_ms": round(out["E"], 3), "H_ms": round(out["H"], 3),
+                   "GBs": round(gbs, 1)}
+            print(json.dumps(rec), flush=True)
+            results.append(rec)
+            del grid, eng, d
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+    return results
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "build":
+        build()
+    else:
+        size = int(os.environ.get("TUNE_SIZE", "1024"))
+        chunks = tuple(int(c) for c in os.environ.get("TUNE_CHUNKS", "32").split(","))
+        run(size=size, chunks=chunks, dtype=os.environ.get("TUNE_DTYPE", "float32"))
