@@ -38,15 +38,16 @@ PML_CELLS = 10
 
 def build_c4(fd, n, pml=PML_CELLS):
     """configs[3]: six PMLs, centre PointSource, LineDetector along z through the centre."""
-    g = fd.Grid(shape=(n, n, n), grid_spacing=GRID_SPACING)
+    nx, ny, nz = (n, n, n) if isinstance(n, int) else n
+    g = fd.Grid(shape=(nx, ny, nz), grid_spacing=GRID_SPACING)
     g[0:pml, :, :] = fd.PML()
     g[-pml:, :, :] = fd.PML()
     g[:, 0:pml, :] = fd.PML()
     g[:, -pml:, :] = fd.PML()
     g[:, :, 0:pml] = fd.PML()
     g[:, :, -pml:] = fd.PML()
-    g[n // 2, n // 2, n // 2] = fd.PointSource(period=20, name="src")
-    g[n // 2 + 4, n // 2, pml + 2:n - pml - 2] = fd.LineDetector(name="line")
+    g[nx // 2, ny // 2, nz // 2] = fd.PointSource(period=20, name="src")
+    g[nx // 2 + 4, ny // 2, pml + 2:nz - pml - 2] = fd.LineDetector(name="line")
     return g
 
 
@@ -66,54 +67,61 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every 5 ms; the
+    recipe's nvidia-smi line polls too slowly for a 40 ms region)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop = index, [], False
+        self.thread = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates all GPUs of the box: map through CUDA_VISIBLE_DEVICES if set
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.replace(",", "").isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def poll():
+                while not self.stop:
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.rows.append((sm, reasons))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.pynvml = pynvml
+            self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop = True
+        if self.thread is not None:
+            self.thread.join(timeout=1)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
-                              ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+        nv = self.pynvml
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        names = []
+        for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            flag = getattr(nv, attr, None) or getattr(nv, attr.replace("Event", "Throttle"), 0)
+            if flag and (bits & flag):
+                names.append(name)
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.max_sm), "reasons": names,
                 "samples": len(sm)}
 
 
@@ -176,8 +184,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
-    ap.add_argument("--cpu-size", type=int, default=192, help="edge of the CPU-baseline sample grid")
-    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--cpu-size", type=int, default=320, help="edge of the CPU-baseline sample grid")
+    ap.add_argument("--cpu-steps", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--x-chunk", type=int, default=0)
     args = ap.parse_args()

@@ -86,7 +86,12 @@ def run(size=1024, dtype="float32", reps=10, chunks=(32,)):
                 b.record()
                 torch.cuda.synchronize()
                 out[label] = a.elapsed_time(b) / reps
-            bytes_launch = algorithmic_bytes_per_cell_step(size, w) / 2 * size ** 3
+            if isinstance(size, int):
+                bytes_launch = algorithmic_bytes_per_cell_step(size, w) / 2 * size ** 3
+            else:
+                nx, ny, nz = size
+                mem = 2 * 10 * (1.0 / nx + 1.0 / ny + 1.0 / nz)
+                bytes_launch = w * (9.0 + 4.0 * mem) * nx * ny * nz
             gbs = bytes_launch / ((out["E"] + out["H"]) / 2 * 1e-3) / 1e9
             rec = {"variant": name, "x_chunk": chunk, "E_ms": round(out["E"], 3), "H_ms": round(out["H"], 3),
                    "GBs": round(gbs, 1)}
@@ -103,6 +108,7 @@ if __name__ == "__main__":
     if sys.argv[1] == "build":
         build()
     else:
-        size = int(os.environ.get("TUNE_SIZE", "1024"))
+        size = os.environ.get("TUNE_SIZE", "1024")
+        size = int(size) if "x" not in size else tuple(int(v) for v in size.split("x"))
         chunks = tuple(int(c) for c in os.environ.get("TUNE_CHUNKS", "32").split(","))
         run(size=size, chunks=chunks, dtype=os.environ.get("TUNE_DTYPE", "float32"))

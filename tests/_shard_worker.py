@@ -1,0 +1,47 @@
+"""worker of tests/test_sharded_*.py: one rank of a torch.distributed job running a scene x-sharded.
+
+    RANK/WORLD_SIZE/MASTER_ADDR/MASTER_PORT in the env;  argv: backend(gloo|nccl) dtype scene steps out.npz
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+
+def main():
+    backend, dtype, scene, steps, out = sys.argv[1:6]
+    steps = int(steps)
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    import scenes
+    if backend == "gloo":
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from emu.harness import use_emu
+        fd = use_emu(dtype)
+    else:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", torch.cuda.current_device()))
+        import fdtd_b200 as fd
+        fd.set_backend("cuda." + dtype)
+    build = scenes.SCENES[scene][0] if scene in scenes.SCENES else getattr(scenes, scene)
+    g = build(fd)
+    assert g._part.world == world and g._part.sharded
+    half = steps // 2
+    g.run(half, progress_bar=False)
+    for _ in range(steps - half):          # exercise the step()-granular path too
+        g.step()
+    res = scenes.dump(g)                   # grid.E gathers the slabs, detectors gather their samples
+    if rank == 0:
+        np.savez(out, **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,29 @@
+"""x-slab sharding over NCCL on real GPUs: sharded == single-GPU result, bit for bit (needs >= 2 GPUs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from test_sharded_gloo import launch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("scene,dtype", [("pml3d", "float64"), ("objects3d", "float32"), ("c4small", "float32")])
+def test_nccl_sharded_equals_single(tmp_path, scene, dtype):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = min(4, torch.cuda.device_count())
+    steps = 30
+    out = str(tmp_path / "sharded.npz")
+    launch(world, "nccl", dtype, scene, steps, out)
+    got = dict(np.load(out))
+    import fdtd_b200 as fd
+    fd.set_backend("cuda." + dtype)
+    g = scenes.SCENES[scene][0](fd)
+    g.run(steps, progress_bar=False)
+    want = scenes.dump(g)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"

@@ -1,0 +1,56 @@
+"""x-slab sharding + halo exchange on 2 and 3 ranks (gloo, CPU): sharded == unsharded, bit for bit.
+
+The ranks run the same host code as on the GPUs (Partition, clipping of PML / objects / sources /
+detectors to the slab, ghost planes, the split half-step with the exchange in between) against the
+serial-interpreter build of the kernels (tests/emu, test infrastructure)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import scenes
+from emu.harness import use_emu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def launch(world, backend, dtype, scene, steps, out):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), WORLD_SIZE=str(world),
+               OMP_NUM_THREADS="1")
+    procs = []
+    for r in range(world):
+        e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_shard_worker.py"), backend, dtype,
+                                       scene, str(steps), out], env=e, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+
+
+@pytest.mark.parametrize("world,scene,dtype", [(2, "pml3d", "float64"), (2, "objects3d", "float64"),
+                                               (3, "periodic3d", "float64"), (2, "c4small", "float32"),
+                                               (3, "slab2d_xz", "float64")])
+def test_sharded_equals_single(tmp_path, world, scene, dtype):
+    steps = 24
+    out = str(tmp_path / "sharded.npz")
+    launch(world, "gloo", dtype, scene, steps, out)
+    got = dict(np.load(out))
+    fd = use_emu(dtype)
+    g = scenes.SCENES[scene][0](fd)
+    assert not g._part.sharded
+    g.run(steps, progress_bar=False)
+    want = scenes.dump(g)
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
