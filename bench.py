@@ -36,10 +36,14 @@ GRID_SPACING = 77.5e-9
 PML_CELLS = 10
 
 
-def build_c4(fd, n, pml=PML_CELLS):
+def build_c4(fd, n, pml=PML_CELLS, balance=False):
     """configs[3]: six PMLs, centre PointSource, LineDetector along z through the centre."""
     nx, ny, nz = (n, n, n) if isinstance(n, int) else n
-    g = fd.Grid(shape=(nx, ny, nz), grid_spacing=GRID_SPACING)
+    kw = {}
+    if balance:
+        # planes inside an x-PML move 13 instead of 9 words per cell and half-step: give their ranks fewer planes
+        kw["x_plane_cost"] = [13.0 / 9.0 if (i < pml or i >= nx - pml) else 1.0 for i in range(nx)]
+    g = fd.Grid(shape=(nx, ny, nz), grid_spacing=GRID_SPACING, **kw)
     g[0:pml, :, :] = fd.PML()
     g[-pml:, :, :] = fd.PML()
     g[:, 0:pml, :] = fd.PML()
@@ -52,8 +56,10 @@ def build_c4(fd, n, pml=PML_CELLS):
 
 
 def algorithmic_bytes_per_cell_step(n, w, pml=PML_CELLS):
-    """w*(18 + 8*M/N); M/N = PML slab memberships per cell = 6*pml/n for a cube."""
-    return w * (18.0 + 8.0 * 6 * pml / n)
+    """w*(18 + 8*M/N); M/N = PML slab memberships per cell = 2*pml*(1/Nx+1/Ny+1/Nz)
+    (= 6*pml/n for a cube)."""
+    nx, ny, nz = (n, n, n) if isinstance(n, int) else n
+    return w * (18.0 + 8.0 * 2 * pml * (1.0 / nx + 1.0 / ny + 1.0 / nz))
 
 
 def measured_peak():
@@ -169,10 +175,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def shape_of(args):
+    if getattr(args, "shape", None):
+        return tuple(int(v) for v in args.shape.split(","))
+    return (args.size, args.size, args.size)
+
+
 def workload_config(args):
-    return {"workload": f"BASELINE configs[3]: 3D {args.size}^3 {args.dtype} Yee grid, {PML_CELLS}-cell PML on all six "
-                        f"faces, PointSource(period=20) at centre, LineDetector; x-slab sharded, halo exchange per half-step",
-            "grid": [args.size] * 3, "pml_cells": PML_CELLS, "parallelism": f"x-slabs x{args.gpus}",
+    shape = shape_of(args)
+    return {"workload": f"BASELINE configs[3]: 3D {shape[0]}x{shape[1]}x{shape[2]} {args.dtype} Yee grid, {PML_CELLS}-cell PML "
+                        f"on all six faces, PointSource(period=20) at centre, LineDetector; x-slab sharded, halo exchange per half-step",
+            "grid": list(shape), "pml_cells": PML_CELLS, "parallelism": f"x-slabs x{args.gpus}",
             "l2_policy": "inputs larger than L2 (fields are 24 GiB at 1024^3; every step streams all of them)"}
 
 
@@ -188,6 +201,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--x-chunk", type=int, default=0)
+    ap.add_argument("--no-balance", action="store_true", help="equal plane counts per rank instead of equal cost")
+    ap.add_argument("--shape", default=None, help="nx,ny,nz instead of --size (experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -209,10 +224,11 @@ def main():
     from fdtd_b200 import _capi
     fd.set_backend("cuda." + args.dtype)
     lib = _capi.load()
-    n, K, W = args.size, args.steps, args.warmup
+    n, K, W = shape_of(args), args.steps, args.warmup
+    cells = n[0] * n[1] * n[2]
     w = 4 if args.dtype == "float32" else 8
 
-    grid = build_c4(fd, n)
+    grid = build_c4(fd, n, balance=not args.no_balance)
     grid._x_chunk = args.x_chunk
     det = grid.detectors[0]
 
@@ -239,10 +255,14 @@ def main():
         barrier()
     launches = lib.fdtd_launch_count() - launches0
     ms = torch.tensor([start.elapsed_time(stop)], device="cuda")
+    per_rank_ms = [float(ms.item())]
     if world > 1:
+        gathered = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(gathered, ms)
+        per_rank_ms = [float(t.item()) for t in gathered]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    value = n ** 3 * K / (ms * 1e-3) / 1e6
+    value = cells * K / (ms * 1e-3) / 1e6
     eng.flush_detectors()
 
     # ---- e2e: public API, host buffers in the timed region -----------------------------------------
@@ -256,7 +276,7 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = n ** 3 * K / float(e2e_s.item()) / 1e6
+    e2e_value = cells * K / float(e2e_s.item()) / 1e6
     assert len(traces[0]) == n_det_before + K
     h2d = sum(1 for _ in grid.sources) * eng._wave[1] * w / K
     d2h = 2 * det._n_points * 3 * w
@@ -265,18 +285,20 @@ def main():
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     d = eng.desc
     reps = max(4, min(K, 10))
+    q_now = grid.time_steps_passed
+    eng._ensure_wave(q_now, 1)
     barrier()
     eng.quiesce()
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for _ in range(reps):
-        _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 0, d.Nx, st))
-        _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), 0, d.Nx, st))
+        _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 0, d.Nx, q_now, 0, st))
+        _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), 0, d.Nx, q_now, 0, st))
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / (2 * reps)
-    cells_local = d.Nx * n * n
+    cells_local = d.Nx * n[1] * n[2]
     bytes_per_launch = algorithmic_bytes_per_cell_step(n, w) / 2 * cells_local
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
@@ -313,7 +335,8 @@ def main():
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
-            "hbm_roofline_frac_whole_step": (algorithmic_bytes_per_cell_step(n, w) * n ** 3 * K
+            "per_rank_ms_per_step": [round(t / K, 4) for t in per_rank_ms],
+            "hbm_roofline_frac_whole_step": (algorithmic_bytes_per_cell_step(n, w) * cells * K
                                              / (ms * 1e-3) / 1e9) / (peak * world),
         }
         print(json.dumps(line), flush=True)

@@ -6,8 +6,8 @@ loudly when it is missing: there is no CPU or PyTorch fallback for the hot path.
 import ctypes as C
 import os
 
-ABI_VERSION = 3
-MAX_SLABS, MAX_POST, MAX_SOURCES, MAX_DETECTORS = 6, 16, 64, 64
+ABI_VERSION = 4
+MAX_SLABS, MAX_POST, MAX_SOURCES, MAX_DETECTORS, FUSED_MAX = 6, 16, 64, 64, 6
 F32, F64 = 0, 1
 CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT = 1, 2, 4, 8
 POST_PERIODIC, POST_PML_ADD = 0, 1
@@ -25,12 +25,12 @@ class Slab(C.Structure):
 class Source(C.Structure):
     _fields_ = [("kind", C.c_int32), ("field", C.c_int32), ("comp", C.c_int32), ("n", C.c_int32),
                 ("idx", _vp), ("profile", _vp), ("amplitude", C.c_double), ("box", C.c_int32 * 6),
-                ("wave", _vp), ("wave_q0", C.c_int64), ("wave_len", C.c_int64)]
+                ("wave", _vp), ("wave_q0", C.c_int64), ("wave_len", C.c_int64), ("bbox", C.c_int32 * 6)]
 
 
 class Detector(C.Structure):
-    _fields_ = [("n", C.c_int32), ("pad_", C.c_int32), ("idx", _vp), ("ring_E", _vp), ("ring_H", _vp),
-                ("capacity", C.c_int64)]
+    _fields_ = [("n", C.c_int32), ("pad_", C.c_int32), ("idx", _vp), ("pos", _vp), ("ring_E", _vp),
+                ("ring_H", _vp), ("capacity", C.c_int64), ("bbox", C.c_int32 * 6)]
 
 
 class Desc(C.Structure):
@@ -47,7 +47,7 @@ class Desc(C.Structure):
                 ("post_kind", C.c_int32 * MAX_POST), ("post_arg", C.c_int32 * MAX_POST),
                 ("n_sources", C.c_int32), ("n_detectors", C.c_int32),
                 ("sources", Source * MAX_SOURCES), ("detectors", Detector * MAX_DETECTORS),
-                ("x_chunk", C.c_int32), ("pad1_", C.c_int32)]
+                ("x_chunk", C.c_int32), ("use_graphs", C.c_int32), ("dyn", _vp)]
 
 
 EXPORTS = {
@@ -58,8 +58,9 @@ EXPORTS = {
     "fdtd_launch_count": (C.c_int64, []),
     "fdtd_tile_shape": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "fdtd_validate": (C.c_int, [C.POINTER(Desc)]),
-    "fdtd_e_halfstep": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_int32, _vp]),
-    "fdtd_h_halfstep": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_int32, _vp]),
+    "fdtd_e_halfstep": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_int32, C.c_int64, C.c_int64, _vp]),
+    "fdtd_h_halfstep": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_int32, C.c_int64, C.c_int64, _vp]),
+    "fdtd_post_is_fused": (C.c_int, [C.POINTER(Desc)]),
     "fdtd_post_E": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),
     "fdtd_post_H": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),
     "fdtd_update_E": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),

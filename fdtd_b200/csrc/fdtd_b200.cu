@@ -175,10 +175,28 @@ int validate(const fdtd_desc* d) {
   if (d->n_detectors < 0 || d->n_detectors > FDTD_MAX_DETECTORS) return fail(FDTD_ERR_ARG, "n_detectors");
   for (int n = 0; n < d->n_detectors; ++n) {
     const fdtd_detector& D = d->detectors[n];
-    if (D.n < 0 || (D.n > 0 && (!D.idx || !D.ring_E || !D.ring_H || D.capacity < 1)))
+    if (D.n < 0 || (D.n > 0 && (!D.idx || !D.pos || !D.ring_E || !D.ring_H || D.capacity < 1)))
       return fail(FDTD_ERR_ARG, "detector %d", n);
   }
+  if (d->use_graphs && !d->dyn) return fail(FDTD_ERR_ARG, "use_graphs needs the dyn scratch");
   return FDTD_OK;
+}
+
+// periodic copies on a one-cell axis are the identity (E[0] = E[-1]); anything else between the field
+// update and the sources forbids folding sources / detectors into the half-step kernel
+bool post_is_fused(const fdtd_desc* d) {
+  for (int n = 0; n < d->n_post; ++n) {
+    if (d->post_kind[n] == FDTD_POST_PML_ADD) return false;
+    int axis = d->post_arg[n];
+    int N = axis == 0 ? d->Nx : (axis == 1 ? d->Ny : d->Nz);
+    if (N >= 2) return false;
+  }
+  int ns[2] = {0, 0};
+  for (int n = 0; n < d->n_sources; ++n) ns[d->sources[n].field]++;
+  if (ns[0] > FDTD_FUSED_MAX || ns[1] > FDTD_FUSED_MAX) return false;
+  int nd = 0;
+  for (int n = 0; n < d->n_detectors; ++n) nd += d->detectors[n].n > 0;
+  return nd <= FDTD_FUSED_MAX;
 }
 
 template <typename T>
@@ -203,8 +221,11 @@ fdtd::SlabK<T> slab_k(const fdtd_slab& S) {
   return k;
 }
 
+// graph_step >= 0: the launch is being captured as step `graph_step` of a replayable chunk; waveform
+// index and ring slot are then graph_step + the bases in d->dyn
 template <typename T, bool IS_E>
-int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, void* stream) {
+int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
+                    int64_t graph_step = -1) {
   if (x_begin < 0 || x_end > d->Nx || x_begin > x_end) return fail(FDTD_ERR_ARG, "plane range [%d,%d)", x_begin, x_end);
   if (x_begin == x_end) return FDTD_OK;
   Geometry g = geometry(d->dtype, d->Ny, d->Nz);
@@ -237,6 +258,42 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, void* stream) {
   if (P.inv[0] != nullptr && P.cls == nullptr) return fail(FDTD_ERR_ARG, "material arrays need a tile_class map");
   P.n_slabs = d->n_slabs;
   for (int s = 0; s < d->n_slabs; ++s) P.slabs[s] = slab_k<T, IS_E>(d->slabs[s]);
+  if (post_is_fused(d)) {
+    P.dyn = graph_step >= 0 ? (const i64*)d->dyn : nullptr;
+    for (int n = 0; n < d->n_sources; ++n) {
+      const fdtd_source& S = d->sources[n];
+      if (S.field != (IS_E ? 0 : 1)) continue;
+      if (S.kind == FDTD_SRC_POINTS && S.n == 0) continue;
+      int64_t w = q - S.wave_q0;
+      if (graph_step < 0 && (w < 0 || w >= S.wave_len))
+        return fail(FDTD_ERR_ARG, "source %d: step %lld outside its waveform table [%lld,%lld)", n, (long long)q,
+                    (long long)S.wave_q0, (long long)(S.wave_q0 + S.wave_len));
+      fdtd::SrcK<T>& K = P.src[P.n_src++];
+      K.kind = S.kind;
+      K.comp = S.comp;
+      K.n = S.n;
+      for (int k = 0; k < 6; ++k) K.bb[k] = S.kind == FDTD_SRC_BOX ? S.box[k] : S.bbox[k];
+      K.idx = (const i64*)S.idx;
+      K.profile = (const T*)S.profile;
+      K.amplitude = (T)S.amplitude;
+      K.wave = (const T*)S.wave;
+      K.w = graph_step >= 0 ? graph_step : w;
+    }
+    for (int n = 0; n < d->n_detectors; ++n) {
+      const fdtd_detector& D = d->detectors[n];
+      if (D.n == 0) continue;
+      if (graph_step < 0 && (slot < 0 || slot >= D.capacity))
+        return fail(FDTD_ERR_ARG, "detector %d: ring slot %lld outside capacity %lld", n, (long long)slot,
+                    (long long)D.capacity);
+      fdtd::DetK<T>& K = P.det[P.n_det++];
+      K.n = D.n;
+      for (int k = 0; k < 6; ++k) K.bb[k] = D.bbox[k];
+      K.idx = (const i64*)D.idx;
+      K.pos = (const int*)D.pos;
+      K.ring = (T*)(IS_E ? D.ring_E : D.ring_H);
+      K.slot = graph_step >= 0 ? graph_step : slot;
+    }
+  }
 
   int chunks = (x_end - x_begin + P.x_chunk - 1) / P.x_chunk;
   dim3 grid((d->Nz + g.tile_z - 1) / g.tile_z, (d->Ny + g.tile_y - 1) / g.tile_y, chunks);
@@ -266,6 +323,7 @@ int blocks_for(i64 n, int threads = 256) {
 
 template <typename T, bool IS_E>
 int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
+  if (post_is_fused(d)) return FDTD_OK;  // done inside the half-step kernel
   T* F[3];
   for (int c = 0; c < 3; ++c) F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
   // 1. periodic copies and late PML corrections, registration order (fdtd/grid.py:290-291, 316-317)
@@ -329,7 +387,7 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
       return fail(FDTD_ERR_ARG, "detector %d: ring slot %lld outside capacity %lld", n, (long long)slot,
                   (long long)D.capacity);
     FDTD_LAUNCH((fdtd::detector_kernel<T>), dim3(blocks_for((i64)D.n * 3)), dim3(256), stream, F[0], F[1], F[2],
-                (const i64*)D.idx, D.n, (T*)(IS_E ? D.ring_E : D.ring_H), (i64)slot);
+                (const i64*)D.idx, (const int*)D.pos, D.n, (T*)(IS_E ? D.ring_E : D.ring_H), (i64)slot);
     int rc = check_launch("detector");
     if (rc) return rc;
   }
@@ -359,18 +417,24 @@ int fdtd_tile_shape(int32_t dtype, int32_t Ny, int32_t Nz, int32_t* tile_y, int3
 
 int fdtd_validate(const fdtd_desc* d) { return validate(d); }
 
-int fdtd_e_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, void* stream) {
+int fdtd_post_is_fused(const fdtd_desc* d) {
   int rc = validate(d);
   if (rc) return rc;
-  return d->dtype == FDTD_F32 ? launch_halfstep<float, true>(d, x_begin, x_end, stream)
-                              : launch_halfstep<double, true>(d, x_begin, x_end, stream);
+  return post_is_fused(d) ? 1 : 0;
 }
 
-int fdtd_h_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, void* stream) {
+int fdtd_e_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, int64_t q, int64_t slot, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
-  return d->dtype == FDTD_F32 ? launch_halfstep<float, false>(d, x_begin, x_end, stream)
-                              : launch_halfstep<double, false>(d, x_begin, x_end, stream);
+  return d->dtype == FDTD_F32 ? launch_halfstep<float, true>(d, x_begin, x_end, q, slot, stream)
+                              : launch_halfstep<double, true>(d, x_begin, x_end, q, slot, stream);
+}
+
+int fdtd_h_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, int64_t q, int64_t slot, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  return d->dtype == FDTD_F32 ? launch_halfstep<float, false>(d, x_begin, x_end, q, slot, stream)
+                              : launch_halfstep<double, false>(d, x_begin, x_end, q, slot, stream);
 }
 
 int fdtd_post_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
@@ -387,17 +451,17 @@ int fdtd_post_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
                               : launch_post<double, false>(d, q, slot, stream);
 }
 
-static int update_E_nocheck(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
-  int rc = d->dtype == FDTD_F32 ? launch_halfstep<float, true>(d, 0, d->Nx, stream)
-                                : launch_halfstep<double, true>(d, 0, d->Nx, stream);
+static int update_E_nocheck(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int64_t graph_step = -1) {
+  int rc = d->dtype == FDTD_F32 ? launch_halfstep<float, true>(d, 0, d->Nx, q, slot, stream, graph_step)
+                                : launch_halfstep<double, true>(d, 0, d->Nx, q, slot, stream, graph_step);
   if (rc) return rc;
   return d->dtype == FDTD_F32 ? launch_post<float, true>(d, q, slot, stream)
                               : launch_post<double, true>(d, q, slot, stream);
 }
 
-static int update_H_nocheck(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
-  int rc = d->dtype == FDTD_F32 ? launch_halfstep<float, false>(d, 0, d->Nx, stream)
-                                : launch_halfstep<double, false>(d, 0, d->Nx, stream);
+static int update_H_nocheck(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int64_t graph_step = -1) {
+  int rc = d->dtype == FDTD_F32 ? launch_halfstep<float, false>(d, 0, d->Nx, q, slot, stream, graph_step)
+                                : launch_halfstep<double, false>(d, 0, d->Nx, q, slot, stream, graph_step);
   if (rc) return rc;
   return d->dtype == FDTD_F32 ? launch_post<float, false>(d, q, slot, stream)
                               : launch_post<double, false>(d, q, slot, stream);
@@ -415,13 +479,109 @@ int fdtd_update_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
   return update_H_nocheck(d, q, slot, stream);
 }
 
+#ifndef FDTD_EMU
+// ---- CUDA-graph replay of step chunks (small, launch-bound grids) ---------------------------------
+// One graph = FDTD_GRAPH_STEPS full steps with the fused kernels; the waveform index and ring slot of
+// node s are s + dyn[], and dyn[] is set by a one-thread kernel before each replay.  The executable
+// graph is cached per descriptor content (every pointer and size it bakes in).
+#define FDTD_GRAPH_STEPS 32
+namespace {
+struct GraphCache {
+  uint64_t key = 0;
+  cudaGraphExec_t exec = nullptr;
+  cudaStream_t capture_stream = nullptr;
+};
+thread_local GraphCache g_graph;
+
+uint64_t desc_key(const fdtd_desc* d) {
+  // FNV-1a over the descriptor bytes: any change of a pointer, size or table invalidates the graph
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(d);
+  uint64_t h = 1469598103934665603ull;
+  for (size_t n = 0; n < sizeof(fdtd_desc); ++n) h = (h ^ b[n]) * 1099511628211ull;
+  return h;
+}
+
+int graph_for(const fdtd_desc* d, cudaGraphExec_t* out) {
+  uint64_t key = desc_key(d);
+  if (g_graph.exec && g_graph.key == key) {
+    *out = g_graph.exec;
+    return FDTD_OK;
+  }
+  if (g_graph.exec) {
+    cudaGraphExecDestroy(g_graph.exec);
+    g_graph.exec = nullptr;
+  }
+  if (!g_graph.capture_stream &&
+      cudaStreamCreateWithFlags(&g_graph.capture_stream, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(FDTD_ERR_CUDA, "cudaStreamCreate for graph capture failed");
+  cudaStream_t cs = g_graph.capture_stream;
+  if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    return fail(FDTD_ERR_CUDA, "cudaStreamBeginCapture failed");
+  int rc = FDTD_OK;
+  for (int64_t s = 0; s < FDTD_GRAPH_STEPS && rc == FDTD_OK; ++s) {
+    rc = update_E_nocheck(d, 0, 0, cs, s);
+    if (rc == FDTD_OK) rc = update_H_nocheck(d, 0, 0, cs, s);
+  }
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(cs, &graph);
+  if (rc != FDTD_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess || !graph) return fail(FDTD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&g_graph.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    g_graph.exec = nullptr;
+    return fail(FDTD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  }
+  g_graph.key = key;
+  *out = g_graph.exec;
+  return FDTD_OK;
+}
+}  // namespace
+#endif
+
 int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
   if (nsteps < 0) return fail(FDTD_ERR_ARG, "nsteps < 0");
   if (d->Nx != d->Nx_global && nsteps > 0)
     return fail(FDTD_ERR_UNSUPPORTED, "fdtd_run on an x-sharded slab: drive the half-steps and the halo exchange per step");
-  for (int64_t s = 0; s < nsteps; ++s) {
+  int64_t s = 0;
+#ifndef FDTD_EMU
+  if (d->use_graphs && d->dyn && post_is_fused(d) && nsteps >= FDTD_GRAPH_STEPS) {
+    // the whole replay must stay inside every waveform table and detector ring
+    int64_t chunks = nsteps / FDTD_GRAPH_STEPS;
+    int64_t wave_base = 0;
+    bool ok = true, have_src = false;
+    for (int n = 0; n < d->n_sources; ++n) {
+      const fdtd_source& S = d->sources[n];
+      int64_t w = q0 - S.wave_q0;
+      if (w < 0 || w + chunks * FDTD_GRAPH_STEPS > S.wave_len) ok = false;
+      if (have_src && w != wave_base) ok = false;  // one base for all tables
+      wave_base = w;
+      have_src = true;
+    }
+    for (int n = 0; n < d->n_detectors; ++n)
+      if (d->detectors[n].n > 0 && (slot0 < 0 || slot0 + chunks * FDTD_GRAPH_STEPS > d->detectors[n].capacity)) ok = false;
+    if (ok) {
+      cudaGraphExec_t exec = nullptr;
+      rc = graph_for(d, &exec);
+      if (rc) return rc;
+      for (int64_t c = 0; c < chunks; ++c) {
+        FDTD_LAUNCH((fdtd::set_dyn_kernel), dim3(1), dim3(1), stream, (i64*)d->dyn, (i64)(wave_base + s), (i64)(slot0 + s));
+        rc = check_launch("set_dyn");
+        if (rc) return rc;
+        cudaError_t e = cudaGraphLaunch(exec, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(FDTD_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
+        g_launches.fetch_add(2 * FDTD_GRAPH_STEPS, std::memory_order_relaxed);
+        s += FDTD_GRAPH_STEPS;
+      }
+    }
+  }
+#endif
+  for (; s < nsteps; ++s) {
     rc = update_E_nocheck(d, q0 + s, slot0 + s, stream);
     if (rc) return rc;
     rc = update_H_nocheck(d, q0 + s, slot0 + s, stream);

@@ -33,6 +33,26 @@
 #define FDTD_PREFETCH_PLANES 1 // software prefetch into L2 this many x-planes ahead (0 = off)
 #endif
 
+#ifndef FDTD_PREFETCH_WHAT
+#define FDTD_PREFETCH_WHAT 3   // bit 0: the differentiated field G, bit 1: the updated field F
+#endif
+#ifndef FDTD_STREAM_HINTS
+#define FDTD_STREAM_HINTS 0    // 1: evict-first loads/stores (ld.global.cs / st.global.cs) for the updated field
+#endif
+#ifndef FDTD_NOINLINE_SLABS
+#define FDTD_NOINLINE_SLABS 0  // 1: the CPML pass is an out-of-line call, its registers do not count in the hot loop
+#endif
+#if defined(FDTD_EMU)
+#define FDTD_GRID_CONSTANT
+#define FDTD_SLAB_FN inline
+#elif FDTD_NOINLINE_SLABS
+#define FDTD_GRID_CONSTANT __grid_constant__
+#define FDTD_SLAB_FN __device__ __noinline__
+#else
+#define FDTD_GRID_CONSTANT __grid_constant__
+#define FDTD_SLAB_FN __device__ __forceinline__
+#endif
+
 namespace fdtd {
 
 typedef long long i64;
@@ -49,6 +69,28 @@ FDTD_DEV Pack<T, VEC> ldv(const T* p) {
 template <typename T, int VEC>
 FDTD_DEV void stv(T* p, const Pack<T, VEC>& x) {
   *reinterpret_cast<Pack<T, VEC>*>(p) = x;
+}
+
+// streaming (evict-first) access for data touched exactly once per half-step
+template <typename T, int VEC>
+FDTD_DEV Pack<T, VEC> ldv_stream(const T* p) {
+#if !defined(FDTD_EMU) && FDTD_STREAM_HINTS
+  if constexpr (sizeof(Pack<T, VEC>) == 16) {
+    float4 r = __ldcs(reinterpret_cast<const float4*>(p));
+    return *reinterpret_cast<Pack<T, VEC>*>(&r);
+  }
+#endif
+  return ldv<T, VEC>(p);
+}
+template <typename T, int VEC>
+FDTD_DEV void stv_stream(T* p, const Pack<T, VEC>& x) {
+#if !defined(FDTD_EMU) && FDTD_STREAM_HINTS
+  if constexpr (sizeof(Pack<T, VEC>) == 16) {
+    __stcs(reinterpret_cast<float4*>(p), *reinterpret_cast<const float4*>(&x));
+    return;
+  }
+#endif
+  stv<T, VEC>(p, x);
 }
 
 // fire-and-forget L2 prefetch of the line holding p (no registers, no scoreboard)
@@ -69,6 +111,29 @@ struct SlabK {
   const T* c;  // cE / cH
 };
 
+// a source folded into the half-step kernel: points (soft, +=) or box (hard, =)
+template <typename T>
+struct SrcK {
+  int kind, comp, n;
+  int bb[6];          // local bounding box x0,x1,y0,y1,z0,z1 (half-open); the box itself for FDTD_SRC_BOX
+  const i64* idx;     // ascending local linear cell indices
+  const T* profile;
+  T amplitude;
+  const T* wave;
+  i64 w;              // waveform table index (+ dyn[0])
+};
+
+// a detector folded into the half-step kernel
+template <typename T>
+struct DetK {
+  int n;
+  int bb[6];
+  const i64* idx;     // ascending
+  const int* pos;     // ring position of each sorted entry
+  T* ring;
+  i64 slot;           // (+ dyn[1])
+};
+
 template <typename T>
 struct HalfStepParams {
   int Nx, Ny, Nz, x_offset, Nx_global;
@@ -86,6 +151,12 @@ struct HalfStepParams {
   unsigned char cls_vary;  // FDTD_CLS_VARY_E or FDTD_CLS_VARY_H
   int n_slabs;
   SlabK<T> slabs[6];
+  // sources and detectors folded into this pass (only when nothing has to run between the field
+  // update and them, i.e. no periodic copy / late PML correction); registration order
+  int n_src, n_det;
+  const i64* dyn;  // optional device int64[2] {waveform index base, ring slot base} (CUDA-graph replays)
+  SrcK<T> src[FDTD_FUSED_MAX];
+  DetK<T> det[FDTD_FUSED_MAX];
 };
 
 // CPML update of one slab for the VEC cells of a thread.  A = slab axis; (A, U, W) cyclic.
@@ -165,8 +236,111 @@ FDTD_DEV void slab_cells(const SlabK<T>& S, bool contiguous, i64 idx0, int l0, i
   }
 }
 
+FDTD_DEV int lower_bound_i64(const i64* a, int n, i64 key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// sources (registration order) then detectors on the final values of a thread's cells
+// (fdtd/grid.py:294-299, 320-325; fdtd/sources.py:93-109, 278-297, 476-486; fdtd/detectors.py:114-124)
+template <typename T, int VEC>
+FDTD_DEV void fused_post(const HalfStepParams<T>& P, int i, int j, int k0, i64 lin0, T (&fx)[VEC], T (&fy)[VEC],
+                         T (&fz)[VEC]) {
+  for (int s = 0; s < P.n_src; ++s) {
+    const SrcK<T>& S = P.src[s];
+    if (i < S.bb[0] || i >= S.bb[1] || j < S.bb[2] || j >= S.bb[3] || k0 + VEC <= S.bb[4] || k0 >= S.bb[5]) continue;
+    const T wv = S.wave[S.w + (P.dyn ? P.dyn[0] : 0)];
+    if (S.kind == FDTD_SRC_BOX) {
+      const T v = S.amplitude * wv;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        if (k0 + e >= S.bb[4] && k0 + e < S.bb[5]) {
+          if (S.comp == 0) fx[e] = v; else if (S.comp == 1) fy[e] = v; else fz[e] = v;
+        }
+      }
+    } else {
+      for (int n = lower_bound_i64(S.idx, S.n, lin0); n < S.n && S.idx[n] < lin0 + VEC; ++n) {
+        const int de = (int)(S.idx[n] - lin0);
+        const T v = S.profile[n] * wv;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          if (e == de) {
+            if (S.comp == 0) fx[e] = fx[e] + v; else if (S.comp == 1) fy[e] = fy[e] + v; else fz[e] = fz[e] + v;
+          }
+        }
+      }
+    }
+  }
+  for (int s = 0; s < P.n_det; ++s) {
+    const DetK<T>& D = P.det[s];
+    if (i < D.bb[0] || i >= D.bb[1] || j < D.bb[2] || j >= D.bb[3] || k0 + VEC <= D.bb[4] || k0 >= D.bb[5]) continue;
+    const i64 slot = D.slot + (P.dyn ? P.dyn[1] : 0);
+    for (int n = lower_bound_i64(D.idx, D.n, lin0); n < D.n && D.idx[n] < lin0 + VEC; ++n) {
+      const int de = (int)(D.idx[n] - lin0);
+      T* out = D.ring + (slot * D.n + D.pos[n]) * 3;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        if (e == de) {
+          out[0] = fx[e];
+          out[1] = fy[e];
+          out[2] = fz[e];
+        }
+      }
+    }
+  }
+}
+
+// what the CPML pass needs about the VEC cells of a thread
+template <typename T, int VEC>
+struct CellState {
+  T d_zy[VEC], d_yz[VEC], d_xz[VEC], d_zx[VEC], d_yx[VEC], d_xy[VEC];
+  T fx[VEC], fy[VEC], fz[VEC];
+  T cx[VEC], cy[VEC], cz[VEC];
+};
+
+// all CPML slabs a thread's cells belong to, in registration order
 template <typename T, int VEC, bool IS_E>
-__global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_kernel(const HalfStepParams<T> P) {
+FDTD_SLAB_FN void slab_pass(const HalfStepParams<T>& P, CellState<T, VEC>& C, int i, int j, int k0, i64 p,
+                            i64 off, unsigned cls) {
+  const int ig = i + P.x_offset;
+  if (IS_E && (cls & FDTD_CLS_OBJECT) && P.inv_grid[0] != nullptr) {
+    // the correction uses the GRID's eps^-1, which is zero inside objects (fdtd/objects.py:92)
+    Pack<T, VEC> a0 = ldv<T, VEC>(P.inv_grid[0] + off);
+    Pack<T, VEC> a1 = ldv<T, VEC>(P.inv_grid[1] + off);
+    Pack<T, VEC> a2 = ldv<T, VEC>(P.inv_grid[2] + off);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      C.cx[e] = P.sc * a0.v[e];
+      C.cy[e] = P.sc * a1.v[e];
+      C.cz[e] = P.sc * a2.v[e];
+    }
+  }
+  for (int s = 0; s < P.n_slabs; ++s) {
+    const SlabK<T>& S = P.slabs[s];
+    if (S.axis == 0) {
+      if (i >= S.x0 && i < S.x1)
+        slab_cells<T, VEC, IS_E>(S, true, (i64)(i - S.x0) * P.plane + p, ig - S.lo, 0, C.d_zx, C.d_yx, C.fy,
+                                 C.fz, C.cy, C.cz);
+    } else if (S.axis == 1) {
+      const int l = j - S.lo;
+      if (l >= 0 && l < S.t)
+        slab_cells<T, VEC, IS_E>(S, true, ((i64)i * S.t + l) * P.Nz + k0, l, 0, C.d_xy, C.d_zy, C.fz, C.fx,
+                                 C.cz, C.cx);
+    } else {
+      const int l0 = k0 - S.lo;
+      if (l0 + VEC > 0 && l0 < S.t)
+        slab_cells<T, VEC, IS_E>(S, false, ((i64)i * P.Ny + j) * S.t + l0, l0, 1, C.d_yz, C.d_xz, C.fx, C.fy,
+                                 C.cx, C.cy);
+    }
+  }
+}
+
+template <typename T, int VEC, bool IS_E>
+__global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_kernel(const FDTD_GRID_CONSTANT HalfStepParams<T> P) {
   const int tid = threadIdx.x;
   const int lane = tid & (P.lanes_z - 1);
   const int row = tid >> P.lanes_shift;
@@ -219,12 +393,16 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
 #if FDTD_PREFETCH_PLANES > 0
     if (i + FDTD_PREFETCH_PLANES < P.Nx) {
       const i64 pf = off + (i64)FDTD_PREFETCH_PLANES * plane;
-      prefetch_l2(Gx + pf);
-      prefetch_l2(Gy + pf + (IS_E ? 0 : plane));
-      prefetch_l2(Gz + pf + (IS_E ? 0 : plane));
-      prefetch_l2(Fx + pf);
-      prefetch_l2(Fy + pf);
-      prefetch_l2(Fz + pf);
+      if (FDTD_PREFETCH_WHAT & 1) {
+        prefetch_l2(Gx + pf);
+        prefetch_l2(Gy + pf + (IS_E ? 0 : plane));
+        prefetch_l2(Gz + pf + (IS_E ? 0 : plane));
+      }
+      if (FDTD_PREFETCH_WHAT & 2) {
+        prefetch_l2(Fx + pf);
+        prefetch_l2(Fy + pf);
+        prefetch_l2(Fz + pf);
+      }
     }
 #endif
     // ---- loads -------------------------------------------------------------------------
@@ -245,9 +423,9 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     const Pack<T, VEC> ynb_z = ldv<T, VEC>(Gz + off + off_y);
     const T zs_x = Gx[off + off_zs];
     const T zs_y = Gy[off + off_zs];
-    Pack<T, VEC> f0 = ldv<T, VEC>(Fx + off);
-    Pack<T, VEC> f1 = ldv<T, VEC>(Fy + off);
-    Pack<T, VEC> f2 = ldv<T, VEC>(Fz + off);
+    Pack<T, VEC> f0 = ldv_stream<T, VEC>(Fx + off);
+    Pack<T, VEC> f1 = ldv_stream<T, VEC>(Fy + off);
+    Pack<T, VEC> f2 = ldv_stream<T, VEC>(Fz + off);
 
     const int ig = i + P.x_offset;
     const bool mx = IS_E ? (ig >= 1) : (ig < P.Nx_global - 1);
@@ -346,37 +524,23 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
       if (S.axis == 0) pml_x |= (i >= S.x0) && (i < S.x1);
     }
     if (pml_x || pml_yz) {
-      if (IS_E && (cls & FDTD_CLS_OBJECT) && P.inv_grid[0] != nullptr) {
-        // the correction uses the GRID's eps^-1, which is zero inside objects (fdtd/objects.py:92)
-        Pack<T, VEC> a0 = ldv<T, VEC>(P.inv_grid[0] + off);
-        Pack<T, VEC> a1 = ldv<T, VEC>(P.inv_grid[1] + off);
-        Pack<T, VEC> a2 = ldv<T, VEC>(P.inv_grid[2] + off);
+      CellState<T, VEC> C;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          cx[e] = P.sc * a0.v[e];
-          cy[e] = P.sc * a1.v[e];
-          cz[e] = P.sc * a2.v[e];
-        }
+      for (int e = 0; e < VEC; ++e) {
+        C.d_zy[e] = d_zy[e]; C.d_yz[e] = d_yz[e]; C.d_xz[e] = d_xz[e];
+        C.d_zx[e] = d_zx[e]; C.d_yx[e] = d_yx[e]; C.d_xy[e] = d_xy[e];
+        C.fx[e] = fx[e]; C.fy[e] = fy[e]; C.fz[e] = fz[e];
+        C.cx[e] = cx[e]; C.cy[e] = cy[e]; C.cz[e] = cz[e];
       }
-      for (int s = 0; s < P.n_slabs; ++s) {
-        const SlabK<T>& S = P.slabs[s];
-        if (S.axis == 0) {
-          if (i >= S.x0 && i < S.x1)
-            slab_cells<T, VEC, IS_E>(S, true, (i64)(i - S.x0) * plane + p, ig - S.lo, 0, d_zx, d_yx,
-                                     fy, fz, cy, cz);
-        } else if (S.axis == 1) {
-          const int l = j - S.lo;
-          if (l >= 0 && l < S.t)
-            slab_cells<T, VEC, IS_E>(S, true, ((i64)i * S.t + l) * Nz + k0, l, 0, d_xy, d_zy, fz, fx,
-                                     cz, cx);
-        } else {
-          const int l0 = k0 - S.lo;
-          if (l0 + VEC > 0 && l0 < S.t)
-            slab_cells<T, VEC, IS_E>(S, false, ((i64)i * P.Ny + j) * S.t + l0, l0, 1, d_yz, d_xz, fx,
-                                     fy, cx, cy);
-        }
+      slab_pass<T, VEC, IS_E>(P, C, i, j, k0, p, off, cls);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        fx[e] = C.fx[e]; fy[e] = C.fy[e]; fz[e] = C.fz[e];
       }
     }
+
+    // ---- folded sources and detectors ------------------------------------------------------------
+    if (P.n_src | P.n_det) fused_post<T, VEC>(P, i, j, k0, off, fx, fy, fz);
 
     // ---- stores --------------------------------------------------------------------------------
 #pragma unroll
@@ -385,9 +549,9 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
       f1.v[e] = fy[e];
       f2.v[e] = fz[e];
     }
-    stv<T, VEC>(Fx + off, f0);
-    stv<T, VEC>(Fy + off, f1);
-    stv<T, VEC>(Fz + off, f2);
+    stv_stream<T, VEC>(Fx + off, f0);
+    stv_stream<T, VEC>(Fy + off, f1);
+    stv_stream<T, VEC>(Fz + off, f2);
 
     if (IS_E) {
       carry_y = gy;
@@ -498,12 +662,20 @@ __global__ void source_box_kernel(T* F, int x0, int x1, int y0, int y1, int z0, 
 
 // detector sampling into the device ring (fdtd/detectors.py:114-124, 241-263)
 template <typename T>
-__global__ void detector_kernel(const T* F0, const T* F1, const T* F2, const i64* idx, int n,
+__global__ void detector_kernel(const T* F0, const T* F1, const T* F2, const i64* idx, const int* pos, int n,
                                 T* ring, i64 slot) {
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 3 * n; t += gridDim.x * blockDim.x) {
     const int pt = t / 3, c = t % 3;
     const T* F = c == 0 ? F0 : (c == 1 ? F1 : F2);
-    ring[(slot * n + pt) * 3 + c] = F[idx[pt]];
+    ring[(slot * n + pos[pt]) * 3 + c] = F[idx[pt]];
+  }
+}
+
+// graph replays: the per-launch bases of the waveform index and the ring slot
+__global__ void set_dyn_kernel(i64* dyn, i64 wave_base, i64 slot_base) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    dyn[0] = wave_base;
+    dyn[1] = slot_base;
   }
 }
 

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 from .backend import backend as bd
-from .sources import _diagonal_points, local_points
+from .sources import _diagonal_points, bounding_box, local_points
 
 
 class _Detector:
@@ -32,10 +32,16 @@ class _Detector:
         """global point list (sampling order) -> local subset on this rank."""
         self._sample_shape = tuple(sample_shape)
         self._n_points = int(np.prod(sample_shape))
-        mine, lin = local_points(self.grid, xs, ys, zs)
-        self._positions = mine
+        mine, lin = local_points(self.grid, xs, ys, zs)      # sorted by linear index
         self._n_local = len(lin)
         self._idx = torch.as_tensor(lin, dtype=torch.int64, device=bd.device)
+        # ring column of each sorted entry = its rank among this slab's points in sampling order
+        order = np.argsort(mine, kind="stable")
+        pos = np.empty(len(mine), dtype=np.int32)
+        pos[order] = np.arange(len(mine), dtype=np.int32)
+        self._pos = torch.as_tensor(pos, dtype=torch.int32, device=bd.device)
+        self._positions = mine[order]                         # global list positions, sampling order
+        self._bbox = bounding_box(self.grid, lin)
 
     def _ensure_ring(self, capacity):
         if self._ring_E is None or self._capacity != capacity:

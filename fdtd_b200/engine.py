@@ -25,6 +25,7 @@ from .sharding import HaloExchange
 RING_BYTES = 64 << 20          # detector ring budget per grid
 WAVE_TABLE_MIN = 1024          # look-ahead of the host waveform tables (steps)
 WAVE_TABLE_MAX = 1 << 16
+GRAPH_MAX_CELLS = 1 << 23      # grids up to this many cells replay CUDA graphs of 32-step chunks in run()
 
 
 def _ptr(t):
@@ -81,6 +82,8 @@ class Engine:
                 if seen_periodic:
                     post.append((_capi.POST_PML_ADD, idx))
             elif isinstance(b, PeriodicBoundary):
+                if (g.Nx, g.Ny, g.Nz)[b.axis] < 2:
+                    continue                      # E[0] = E[-1] on a one-cell axis is the identity
                 seen_periodic = True
                 if b.axis == 0 and part.sharded:
                     raise NotImplementedError("a periodic x boundary on an x-sharded grid")
@@ -135,6 +138,8 @@ class Engine:
                 if entry["kind"] == _capi.SRC_POINTS:
                     e.n = int(entry["idx"].numel())
                     e.idx, e.profile = _ptr(entry["idx"]), _ptr(entry["profile"])
+                    for k in range(6):
+                        e.bbox[k] = entry["bbox"][k]
                     self._keep += [entry["idx"], entry["profile"]]
                 else:
                     e.amplitude = entry["amplitude"]
@@ -155,10 +160,18 @@ class Engine:
             det._ensure_ring(self.ring_capacity)
             e = d.detectors[n]
             e.n = det._n_local
-            e.idx = _ptr(det._idx)
+            e.idx, e.pos = _ptr(det._idx), _ptr(det._pos)
             e.ring_E, e.ring_H = _ptr(det._ring_E), _ptr(det._ring_H)
             e.capacity = self.ring_capacity
+            for k in range(6):
+                e.bbox[k] = det._bbox[k]
         d.n_detectors = len(g.detectors)
+
+        # CUDA-graph replay of step chunks pays off where a step is launch-bound (small grids)
+        self._dyn = torch.zeros(2, dtype=torch.int64, device=g._E.device)
+        d.dyn = _ptr(self._dyn)
+        d.use_graphs = 1 if (g._E.is_cuda and not part.sharded and g._use_graphs is not False
+                             and (g._use_graphs or part.nx * g.Ny * g.Nz <= GRAPH_MAX_CELLS)) else 0
 
         self._ensure_wave(g.time_steps_passed, 1)
         _capi.check(self.lib, self.lib.fdtd_validate(C.byref(d)))
@@ -259,10 +272,10 @@ class Engine:
             _capi.check(lib, lib.fdtd_update_E(C.byref(d), q, slot, st))
         else:
             n = d.Nx
-            _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 1, n, st))
+            _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 1, n, q, slot, st))
             self._halo.wait(self._pending["H"])
             self._pending["H"] = None
-            _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 0, min(1, n), st))
+            _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 0, min(1, n), q, slot, st))
             _capi.check(lib, lib.fdtd_post_E(C.byref(d), q, slot, st))
             self._pending["E"] = self._halo.start("E")
         if g.detectors:
@@ -277,10 +290,10 @@ class Engine:
             _capi.check(lib, lib.fdtd_update_H(C.byref(d), q, slot, st))
         else:
             n = d.Nx
-            _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), 0, n - 1, st))
+            _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), 0, n - 1, q, slot, st))
             self._halo.wait(self._pending["E"])
             self._pending["E"] = None
-            _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), n - 1, n, st))
+            _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), n - 1, n, q, slot, st))
             _capi.check(lib, lib.fdtd_post_H(C.byref(d), q, slot, st))
             self._pending["H"] = self._halo.start("H")
         if g.detectors:

@@ -8,7 +8,8 @@ Differences a user can see, all deliberate:
     grid never allocates them (they are 12 GiB each at 1024^3 float32) and the kernels then
     stream no coefficient array at all;
   * under an initialised torch.distributed job the grid is split into x-slabs, one per rank
-    (`shard="auto"`); `grid.E` then gathers (a copy), `grid.E_local` is the local view.
+    (`shard="auto"`); `grid.E` then gathers (a copy), `grid.E_local` is the local view.  `x_plane_cost`
+    (one relative cost per x-plane) balances the slabs when some planes are dearer, e.g. inside x-PMLs.
 """
 import gc
 
@@ -48,7 +49,7 @@ class Grid:
     """The FDTD grid: owns E, H and the material arrays, and steps them (fdtd/grid.py:80-331)."""
 
     def __init__(self, shape, grid_spacing: float = 155e-9, permittivity=1.0, permeability=1.0,
-                 courant_number: float = None, shard="auto"):
+                 courant_number: float = None, shard="auto", x_plane_cost=None):
         bd.require()
         self.grid_spacing = float(grid_spacing)
         self.Nx, self.Ny, self.Nz = self._handle_tuple(shape)
@@ -64,7 +65,7 @@ class Grid:
 
         self._dtype = bd.float
         gc.collect()      # grids hold reference cycles (plug-ins point back at them): free dead ones' HBM first
-        self._part = Partition(self.Nx, shard)
+        self._part = Partition(self.Nx, shard, x_plane_cost)
         nx = self._part.nx
         self._E = bd.zeros((3, nx + 2, self.Ny, self.Nz))
         self._H = bd.zeros((3, nx + 2, self.Ny, self.Nz))
@@ -80,6 +81,7 @@ class Grid:
         self._engine = None
         self._ring_fill = {"E": 0, "H": 0}
         self._x_chunk = 0
+        self._use_graphs = None      # None: automatic (small grids), True / False: force
 
     # ----------------------------------------------------------------------------- materials
     def _material(self, value, what):

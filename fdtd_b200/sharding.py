@@ -9,6 +9,8 @@ contiguous Ny*Nz planes per neighbour, sent with NCCL send/recv on a side stream
 overlaps with the bulk of the following half-step.  The `gloo` backend (CPU tensors) is
 supported for the host-logic tests only.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -16,7 +18,7 @@ import torch.distributed as dist
 class Partition:
     """contiguous, balanced x-slabs: rank r owns global planes [x0, x1)."""
 
-    def __init__(self, Nx, shard="auto"):
+    def __init__(self, Nx, shard="auto", plane_cost=None):
         active = (shard not in (None, False) and dist.is_available() and dist.is_initialized()
                   and dist.get_world_size() > 1)
         if shard is True and not active:
@@ -26,12 +28,33 @@ class Partition:
         self.world = dist.get_world_size() if active else 1
         if self.world > Nx:
             raise ValueError(f"cannot shard Nx={Nx} planes over {self.world} ranks")
+        self._cuts = self._balanced_cuts(plane_cost)
         self.x0, self.x1 = self.bounds(self.rank)
 
+    def _balanced_cuts(self, plane_cost):
+        """slab boundaries: equal plane counts, or -- given a relative cost per x-plane (planes inside an
+        x-PML move 13 words per cell and half-step instead of 9) -- equal cumulative cost."""
+        n, p = self.Nx, self.world
+        if plane_cost is None or p == 1:
+            base, rem = divmod(n, p)
+            return [r * base + min(r, rem) for r in range(p)] + [n]
+        cost = [float(c) for c in plane_cost]
+        if len(cost) != n or min(cost) <= 0:
+            raise ValueError("plane_cost needs one positive entry per x-plane")
+        total, cuts, acc, i = sum(cost), [0], 0.0, 0
+        for r in range(1, p):
+            target = total * r / p
+            while i < n and acc + cost[i] / 2 < target:
+                acc += cost[i]
+                i += 1
+            i = max(i, cuts[-1] + 1)                 # at least one plane per rank
+            i = min(i, n - (p - r))
+            acc = sum(cost[:i])
+            cuts.append(i)
+        return cuts + [n]
+
     def bounds(self, r):
-        base, rem = divmod(self.Nx, self.world)
-        x0 = r * base + min(r, rem)
-        return x0, x0 + base + (1 if r < rem else 0)
+        return self._cuts[r], self._cuts[r + 1]
 
     @property
     def nx(self):
@@ -85,7 +108,7 @@ class HaloExchange:
         """begin the exchange that follows a half-step of `field` ('E' -> left, 'H' -> right).
         Returns a handle for wait()."""
         ops = self._ops(self.E if field == "E" else self.H, to_left=(field == "E"))
-        if not ops:
+        if not ops or os.environ.get("FDTD_B200_SKIP_HALO"):     # (timing experiments only: wrong results)
             return None
         if self.cuda:
             main = torch.cuda.current_stream(self.E.device)

@@ -39,8 +39,19 @@ def _diagonal_points(grid, x, y, z, convert, min_points, what):
     return out[0], out[1], out[2]
 
 
+def bounding_box(grid, lin):
+    """local half-open bounding box x0,x1,y0,y1,z0,z1 of local linear cell indices."""
+    if len(lin) == 0:
+        return [0, 0, 0, 0, 0, 0]
+    lin = np.asarray(lin, dtype=np.int64)
+    plane = grid.Ny * grid.Nz
+    x, y, z = lin // plane, (lin % plane) // grid.Nz, lin % grid.Nz
+    return [int(x.min()), int(x.max()) + 1, int(y.min()), int(y.max()) + 1, int(z.min()), int(z.max()) + 1]
+
+
 def local_points(grid, xs, ys, zs):
-    """-> (positions in the list, local linear cell indices) of the points this rank owns."""
+    """-> (positions in the list, local linear cell indices) of the points this rank owns,
+    sorted by ascending linear index (the C ABI wants ascending `idx`)."""
     part = grid._part
     xs, ys, zs = (np.asarray(v, dtype=np.int64) for v in (xs, ys, zs))
     # negative indices address from the end, as numpy / torch indexing does in the reference
@@ -51,7 +62,8 @@ def local_points(grid, xs, ys, zs):
         raise IndexError("index out of range for the grid")
     mine = np.nonzero((xs >= part.x0) & (xs < part.x1))[0]
     lin = (xs[mine] - part.x0) * (grid.Ny * grid.Nz) + ys[mine] * grid.Nz + zs[mine]
-    return mine, lin
+    order = np.argsort(lin, kind="stable")
+    return mine[order], lin[order]
 
 
 class _TimedSource:
@@ -107,6 +119,7 @@ class PointSource(_TimedSource):
         self.frequency = 1.0 / self.period
         _, lin = local_points(grid, [self.x], [self.y], [self.z])
         self._idx = torch.as_tensor(lin, dtype=torch.int64, device=bd.device)
+        self._bbox = bounding_box(grid, lin)
         self._profile = bd.ones((len(lin),))
 
     def _wave_value(self, q):
@@ -114,7 +127,7 @@ class PointSource(_TimedSource):
         return self.amplitude * self._scalar(q)
 
     def _entries(self):
-        return [dict(kind=_capi.SRC_POINTS, field=0, comp=2, idx=self._idx, profile=self._profile)]
+        return [dict(kind=_capi.SRC_POINTS, field=0, comp=2, idx=self._idx, profile=self._profile, bbox=self._bbox)]
 
     def __str__(self):
         return "    " + repr(self) + "\n" + f"        @ x={self.x}, y={self.y}, z={self.z}\n"
@@ -143,13 +156,14 @@ class LineSource(_TimedSource):
         self.profile = hl.to_device(profile, bd.device)
         mine, lin = local_points(grid, self.x, self.y, self.z)
         self._idx = torch.as_tensor(lin, dtype=torch.int64, device=bd.device)
+        self._bbox = bounding_box(grid, lin)
         self._profile = self.profile[torch.as_tensor(mine, dtype=torch.int64, device=bd.device)].contiguous()
 
     def _wave_value(self, q):
         return self._scalar(q)
 
     def _entries(self):
-        return [dict(kind=_capi.SRC_POINTS, field=0, comp=2, idx=self._idx, profile=self._profile)]
+        return [dict(kind=_capi.SRC_POINTS, field=0, comp=2, idx=self._idx, profile=self._profile, bbox=self._bbox)]
 
     def __str__(self):
         s = "    " + repr(self) + "\n"

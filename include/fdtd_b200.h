@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 3
+#define FDTD_ABI_VERSION 4
 
 #define FDTD_F32 0
 #define FDTD_F64 1
@@ -49,6 +49,7 @@ extern "C" {
 #define FDTD_MAX_POST 16
 #define FDTD_MAX_SOURCES 64
 #define FDTD_MAX_DETECTORS 64
+#define FDTD_FUSED_MAX 6       /* sources / detectors per field folded into the half-step kernel */
 
 #define FDTD_OK 0
 #define FDTD_ERR_ARG (-1)     /* invalid descriptor / argument */
@@ -98,22 +99,25 @@ typedef struct fdtd_source {
   int32_t field;       /* 0 = E (applied after the E half-step), 1 = H */
   int32_t comp;        /* component written */
   int32_t n;           /* FDTD_SRC_POINTS: number of points on this slab */
-  const int64_t* idx;  /* device [n]: local linear cell index x*plane + y*Nz + z */
-  const void* profile; /* device [n] */
+  const int64_t* idx;  /* device [n]: local linear cell index x*plane + y*Nz + z, ASCENDING */
+  const void* profile; /* device [n], same order as idx */
   double amplitude;    /* FDTD_SRC_BOX */
   int32_t box[6];      /* FDTD_SRC_BOX: local x0,x1,y0,y1,z0,z1 (half-open) */
   const void* wave;    /* device [wave_len]: per-step scalar, entry q - wave_q0 */
   int64_t wave_q0;
   int64_t wave_len;
+  int32_t bbox[6];     /* FDTD_SRC_POINTS: local bounding box x0,x1,y0,y1,z0,z1 (half-open) of the points */
 } fdtd_source;
 
 typedef struct fdtd_detector {
   int32_t n;           /* points on this slab */
   int32_t pad_;
-  const int64_t* idx;  /* device [n]: local linear cell index */
+  const int64_t* idx;  /* device [n]: local linear cell index, ASCENDING */
+  const int32_t* pos;  /* device [n]: position of each entry in the detector's sampling order (ring column) */
   void* ring_E;        /* device [capacity][n][3] */
   void* ring_H;        /* device [capacity][n][3] */
   int64_t capacity;
+  int32_t bbox[6];     /* local bounding box of the points */
 } fdtd_detector;
 
 typedef struct fdtd_desc {
@@ -145,7 +149,8 @@ typedef struct fdtd_desc {
   fdtd_source sources[FDTD_MAX_SOURCES];       /* registration order */
   fdtd_detector detectors[FDTD_MAX_DETECTORS]; /* registration order */
   int32_t x_chunk;     /* planes marched per thread block; 0 = library default */
-  int32_t pad1_;
+  int32_t use_graphs;  /* 1: fdtd_run may replay CUDA graphs of step chunks (launch-bound small grids) */
+  int64_t* dyn;        /* device int64[2] scratch owned by the caller, needed when use_graphs = 1 */
 } fdtd_desc;
 
 /* --- queries ------------------------------------------------------------------------- */
@@ -162,14 +167,21 @@ int fdtd_validate(const fdtd_desc* d);
 
 /* --- the hot path -------------------------------------------------------------------- */
 /* Fused E half-step on local planes [x_begin, x_end): psi_E update of every slab, curl_H,
- * E += sc*eps^-1*curl with object / absorbing coefficients, fused PML field corrections.
- * Replaces PML.update_phi_E + curl_H + grid.py:283 + Object.update_E + PML.update_E. */
-int fdtd_e_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, void* stream);
-/* Same for H: PML.update_phi_H + curl_E + grid.py:309 + PML.update_H. */
-int fdtd_h_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, void* stream);
-/* What follows the fused kernel inside Grid.update_E / update_H, in the reference's order:
- * periodic copies and late PML corrections (registration order), sources (registration
- * order, step index q), detector sampling into ring slot `slot`. */
+ * E += sc*eps^-1*curl with object / absorbing coefficients, fused PML field corrections and --
+ * when fdtd_post_is_fused(d) -- source injection (step index q) and detector sampling (ring slot
+ * `slot`) in the same pass.
+ * Replaces PML.update_phi_E + curl_H + grid.py:283 + Object.update_E + PML.update_E
+ * (+ Source.update_E + Detector.detect_E). */
+int fdtd_e_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, int64_t q, int64_t slot, void* stream);
+/* Same for H: PML.update_phi_H + curl_E + grid.py:309 + PML.update_H (+ sources, detectors). */
+int fdtd_h_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, int64_t q, int64_t slot, void* stream);
+/* 1 when sources and detectors are folded into the half-step kernels: nothing has to run between
+ * the field update and them (no periodic copy, no late PML correction) and there are at most
+ * FDTD_FUSED_MAX of each per field.  fdtd_post_E/H are then no-ops. */
+int fdtd_post_is_fused(const fdtd_desc* d);
+/* What follows the fused kernel inside Grid.update_E / update_H when it could not be folded, in
+ * the reference's order: periodic copies and late PML corrections (registration order), sources
+ * (registration order, step index q), detector sampling into ring slot `slot`. */
 int fdtd_post_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
 int fdtd_post_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
 /* Grid.update_E / Grid.update_H (fdtd/grid.py:275-325) on the whole local slab */

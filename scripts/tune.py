@@ -17,7 +17,14 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "fdtd_b200", "_variants")
 
 VARIANTS = {
-    "base": [],
+    "default": [],
+    "noinl": ["-DFDTD_NOINLINE_SLABS=1"],
+    "noinl_mb4": ["-DFDTD_NOINLINE_SLABS=1", "-DFDTD_MIN_BLOCKS=4"],
+    "pfG": ["-DFDTD_PREFETCH_WHAT=1"],
+    "pfF": ["-DFDTD_PREFETCH_WHAT=2"],
+    "cs": ["-DFDTD_STREAM_HINTS=1"],
+    "noinl_cs": ["-DFDTD_NOINLINE_SLABS=1", "-DFDTD_STREAM_HINTS=1"],
+    "base": ["-DFDTD_MIN_BLOCKS=2", "-DFDTD_PREFETCH_PLANES=0"],
     "mb3": ["-DFDTD_MIN_BLOCKS=3"],
     "mb4": ["-DFDTD_MIN_BLOCKS=4"],
     "pf1": ["-DFDTD_PREFETCH_PLANES=1"],
@@ -82,7 +89,7 @@ def run(size=1024, dtype="float32", reps=10, chunks=(32,)):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 for _ in range(reps):
-                    _capi.check(lib, fn(C.byref(d), 0, d.Nx, st))
+                    _capi.check(lib, fn(C.byref(d), 0, d.Nx, grid.time_steps_passed, 0, st))
                 b.record()
                 torch.cuda.synchronize()
                 out[label] = a.elapsed_time(b) / reps

@@ -179,3 +179,22 @@ def test_user_write_to_materials_triggers_rebake():
     o.inverse_permittivity[4:8, 4:8, 4:8, :] = 0.5
     o.run(5)
     compare(scenes.dump(g), scenes.dump(o), 1e-12, bitwise=True)
+
+
+def test_many_sources_fall_back_to_unfused_kernels():
+    """more than FDTD_FUSED_MAX sources: the separate source / detector kernels run instead."""
+    def build(fd):
+        g = scenes.pml3d(fd, n=(14, 12, 10), t=3)
+        for n in range(8):
+            g[3 + n, 6, 5] = fd.PointSource(period=9 + n, amplitude=0.5 + 0.1 * n)
+        return g
+    fd = use_emu("float64")
+    g = build(fd)
+    g.run(30, progress_bar=False)
+    import ctypes
+    assert g._engine.lib.fdtd_post_is_fused(ctypes.byref(g._engine.desc)) == 0
+    want = run_oracle(build, 30)
+    compare(scenes.dump(g), want, 1e-12, bitwise=True)
+    h = scenes.pml3d(fd, n=(14, 12, 10), t=3)
+    h.run(1, progress_bar=False)
+    assert h._engine.lib.fdtd_post_is_fused(ctypes.byref(h._engine.desc)) == 1

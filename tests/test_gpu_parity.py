@@ -192,3 +192,38 @@ def test_c4_256_vs_oracle_prefix():
     got = run_scene(cuda("float32"), build, 30)
     want = run_oracle(build, 30, "float32")
     compare(got, want, 1e-5, bitwise=True)
+
+
+def test_graph_replay_equals_plain_launches():
+    """run() on a small grid replays CUDA graphs of 32-step chunks (waveform index and ring slot come
+    from device scalars); results must equal plain per-step launches bit for bit."""
+    fd = cuda("float64")
+    outs = []
+    for graphs in (True, False):
+        g = scenes.objects3d(fd)
+        g._use_graphs = graphs
+        g.run(70, progress_bar=False)
+        g.run(45, progress_bar=False)
+        assert g._engine.desc.use_graphs == (1 if graphs else 0)
+        outs.append(scenes.dump(g))
+    compare(outs[0], outs[1], 0.0, bitwise=True)
+    want = run_oracle(scenes.objects3d, 115)
+    compare(outs[0], want, 1e-12)
+
+
+def test_many_sources_fall_back_to_unfused_kernels():
+    """more than FDTD_FUSED_MAX sources: the separate source / detector kernels run instead."""
+    def build(fd):
+        g = scenes.pml3d(fd, n=(20, 18, 16), t=4)
+        for n in range(8):
+            g[5 + n, 6, 7] = fd.PointSource(period=9 + n, amplitude=0.5 + 0.1 * n)
+        return g
+    fd = cuda("float64")
+    g = build(fd)
+    g.run(40, progress_bar=False)
+    import ctypes
+    assert g._engine.lib.fdtd_post_is_fused(ctypes.byref(g._engine.desc)) == 0
+    yo.set_backend("numpy", "float64")
+    o = build(yo)
+    o.run(40)
+    compare(scenes.dump(g), scenes.dump(o), 1e-12, bitwise=True)
