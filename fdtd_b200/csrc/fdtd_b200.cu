@@ -69,6 +69,9 @@ int pow2_ceil(int v) {
   return p;
 }
 
+#ifndef FDTD_FUSE_MAX_CELLS
+#define FDTD_FUSE_MAX_CELLS (1LL << 23)
+#endif
 #ifndef FDTD_MAX_VEC_F32
 #define FDTD_MAX_VEC_F32 4
 #endif
@@ -185,6 +188,10 @@ int validate(const fdtd_desc* d) {
 // periodic copies on a one-cell axis are the identity (E[0] = E[-1]); anything else between the field
 // update and the sources forbids folding sources / detectors into the half-step kernel
 bool post_is_fused(const fdtd_desc* d) {
+  // folding pays where a step is launch-bound; on large slabs the separate source / detector kernels
+  // cost < 0.1 % of a step while the folded code costs ~1 % of the streaming kernel (profiles/r1_tune6)
+  if (d->fuse_post == 0) return false;
+  if (d->fuse_post < 0 && (int64_t)d->Nx * d->Ny * d->Nz > FDTD_FUSE_MAX_CELLS) return false;
   for (int n = 0; n < d->n_post; ++n) {
     if (d->post_kind[n] == FDTD_POST_PML_ADD) return false;
     int axis = d->post_arg[n];
@@ -299,18 +306,26 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
   dim3 grid((d->Nz + g.tile_z - 1) / g.tile_z, (d->Ny + g.tile_y - 1) / g.tile_y, chunks);
   dim3 block(g.lanes_z * g.rows);
   if (grid.y > 65535u || grid.z > 65535u) return fail(FDTD_ERR_UNSUPPORTED, "grid too large for one launch");
+  const bool has_post = (P.n_src + P.n_det) > 0;
+#define FDTD_LAUNCH_HALFSTEP(V)                                                                    \
+  if (has_post) {                                                                                  \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true>), grid, block, stream, P);               \
+  } else {                                                                                         \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false>), grid, block, stream, P);              \
+  }
   switch (g.vec) {
     case 4:
       if constexpr (sizeof(T) == 4) {
-        FDTD_LAUNCH((fdtd::halfstep_kernel<T, 4, IS_E>), grid, block, stream, P);
+        FDTD_LAUNCH_HALFSTEP(4)
       }
       break;
     case 2:
-      FDTD_LAUNCH((fdtd::halfstep_kernel<T, 2, IS_E>), grid, block, stream, P);
+      FDTD_LAUNCH_HALFSTEP(2)
       break;
     default:
-      FDTD_LAUNCH((fdtd::halfstep_kernel<T, 1, IS_E>), grid, block, stream, P);
+      FDTD_LAUNCH_HALFSTEP(1)
   }
+#undef FDTD_LAUNCH_HALFSTEP
   return check_launch(IS_E ? "e_halfstep" : "h_halfstep");
 }
 

@@ -43,6 +43,13 @@
 #define FDTD_NOINLINE_SLABS 0  // 1: the CPML pass is an out-of-line call, its registers do not count in the hot loop
 #endif
 #if defined(FDTD_EMU)
+#define FDTD_RARE_FN inline
+#elif defined(FDTD_POST_INLINE)
+#define FDTD_RARE_FN __device__ __forceinline__
+#else
+#define FDTD_RARE_FN __device__ __noinline__   // rare paths out of line: their registers do not count in the hot loop
+#endif
+#if defined(FDTD_EMU)
 #define FDTD_GRID_CONSTANT
 #define FDTD_SLAB_FN inline
 #elif FDTD_NOINLINE_SLABS
@@ -248,8 +255,15 @@ FDTD_DEV int lower_bound_i64(const i64* a, int n, i64 key) {
 // sources (registration order) then detectors on the final values of a thread's cells
 // (fdtd/grid.py:294-299, 320-325; fdtd/sources.py:93-109, 278-297, 476-486; fdtd/detectors.py:114-124)
 template <typename T, int VEC>
-FDTD_DEV void fused_post(const HalfStepParams<T>& P, int i, int j, int k0, i64 lin0, T (&fx)[VEC], T (&fy)[VEC],
-                         T (&fz)[VEC]) {
+struct CellFields {
+  T fx[VEC], fy[VEC], fz[VEC];
+};
+
+template <typename T, int VEC>
+FDTD_RARE_FN void fused_post(const HalfStepParams<T>& P, int i, int j, int k0, i64 lin0, CellFields<T, VEC>& V) {
+  T (&fx)[VEC] = V.fx;
+  T (&fy)[VEC] = V.fy;
+  T (&fz)[VEC] = V.fz;
   for (int s = 0; s < P.n_src; ++s) {
     const SrcK<T>& S = P.src[s];
     if (i < S.bb[0] || i >= S.bb[1] || j < S.bb[2] || j >= S.bb[3] || k0 + VEC <= S.bb[4] || k0 >= S.bb[5]) continue;
@@ -339,7 +353,9 @@ FDTD_SLAB_FN void slab_pass(const HalfStepParams<T>& P, CellState<T, VEC>& C, in
   }
 }
 
-template <typename T, int VEC, bool IS_E>
+// HAS_POST: sources / detectors folded into this pass (small grids, where a separate launch per source
+// and detector would dominate the step); compiled out otherwise
+template <typename T, int VEC, bool IS_E, bool HAS_POST>
 __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_kernel(const FDTD_GRID_CONSTANT HalfStepParams<T> P) {
   const int tid = threadIdx.x;
   const int lane = tid & (P.lanes_z - 1);
@@ -375,6 +391,13 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     if (S.axis == 1) pml_yz |= (j >= S.lo) && (j < S.lo + S.t);
     if (S.axis == 2) pml_yz |= (k0 + VEC > S.lo) && (k0 < S.lo + S.t);
   }
+
+  // loop-invariant: does any folded source / detector touch this thread's row and z-range?
+  bool post_yz = false;
+  for (int s = 0; HAS_POST && s < P.n_src; ++s)
+    post_yz |= (j >= P.src[s].bb[2]) && (j < P.src[s].bb[3]) && (k0 + VEC > P.src[s].bb[4]) && (k0 < P.src[s].bb[5]);
+  for (int s = 0; HAS_POST && s < P.n_det; ++s)
+    post_yz |= (j >= P.det[s].bb[2]) && (j < P.det[s].bb[3]) && (k0 + VEC > P.det[s].bb[4]) && (k0 < P.det[s].bb[5]);
 
   // x-neighbour plane carried in registers: plane i-1 of (Gy, Gz) for E, plane i for H
   Pack<T, VEC> carry_y, carry_z;
@@ -539,8 +562,19 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
       }
     }
 
-    // ---- folded sources and detectors ------------------------------------------------------------
-    if (P.n_src | P.n_det) fused_post<T, VEC>(P, i, j, k0, off, fx, fy, fz);
+    // ---- folded sources and detectors (rare: only threads whose row / z-range a source or detector touches)
+    if (HAS_POST && post_yz) {
+      CellFields<T, VEC> V;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        V.fx[e] = fx[e]; V.fy[e] = fy[e]; V.fz[e] = fz[e];
+      }
+      fused_post<T, VEC>(P, i, j, k0, off, V);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        fx[e] = V.fx[e]; fy[e] = V.fy[e]; fz[e] = V.fz[e];
+      }
+    }
 
     // ---- stores --------------------------------------------------------------------------------
 #pragma unroll

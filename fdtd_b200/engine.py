@@ -170,6 +170,7 @@ class Engine:
         # CUDA-graph replay of step chunks pays off where a step is launch-bound (small grids)
         self._dyn = torch.zeros(2, dtype=torch.int64, device=g._E.device)
         d.dyn = _ptr(self._dyn)
+        d.fuse_post = -1 if g._fuse_post is None else int(bool(g._fuse_post))
         d.use_graphs = 1 if (g._E.is_cuda and not part.sharded and g._use_graphs is not False
                              and (g._use_graphs or part.nx * g.Ny * g.Nz <= GRAPH_MAX_CELLS)) else 0
 
@@ -263,21 +264,42 @@ class Engine:
         g._ring_fill["E"] = g._ring_fill["H"] = 0
 
     # ------------------------------------------------------------------------------------ stepping
+    def _sharded_halfstep(self, field, q, slot):
+        """one half-step of an x-sharded slab.  The plane that needs the neighbour's ghost plane (plane 0
+        for E, the last plane for H) runs on the halo stream right behind the exchange that delivers the
+        ghost, concurrently with the bulk on the main stream; the exchange of the freshly updated
+        boundary plane is then started and overlaps the bulk of the NEXT half-step."""
+        lib, d, halo = self.lib, self.desc, self._halo
+        n = d.Nx
+        step = lib.fdtd_e_halfstep if field == "E" else lib.fdtd_h_halfstep
+        post = lib.fdtd_post_E if field == "E" else lib.fdtd_post_H
+        bulk = (1, n) if field == "E" else (0, n - 1)
+        edge = (0, min(1, n)) if field == "E" else (max(n - 1, 0), n)
+        other = "H" if field == "E" else "E"
+        st = self._stream()
+        if halo.cuda:
+            dev = self.grid._E.device
+            main, side = torch.cuda.current_stream(dev), halo.stream
+            side.wait_stream(main)                       # everything enqueued so far (user writes included)
+            _capi.check(lib, step(C.byref(d), bulk[0], bulk[1], q, slot, st))
+            _capi.check(lib, step(C.byref(d), edge[0], edge[1], q, slot, C.c_void_p(side.cuda_stream)))
+            main.wait_stream(side)
+        else:
+            _capi.check(lib, step(C.byref(d), bulk[0], bulk[1], q, slot, st))
+            halo.wait(self._pending[other])
+            _capi.check(lib, step(C.byref(d), edge[0], edge[1], q, slot, st))
+        self._pending[other] = None
+        _capi.check(lib, post(C.byref(d), q, slot, st))
+        self._pending[field] = halo.start(field)
+
     def update_E(self, q):
         g, lib, d = self.grid, self.lib, self.desc
         self._ensure_wave(q, 1)
         slot = self._slot("E")
-        st = self._stream()
         if self._halo is None:
-            _capi.check(lib, lib.fdtd_update_E(C.byref(d), q, slot, st))
+            _capi.check(lib, lib.fdtd_update_E(C.byref(d), q, slot, self._stream()))
         else:
-            n = d.Nx
-            _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 1, n, q, slot, st))
-            self._halo.wait(self._pending["H"])
-            self._pending["H"] = None
-            _capi.check(lib, lib.fdtd_e_halfstep(C.byref(d), 0, min(1, n), q, slot, st))
-            _capi.check(lib, lib.fdtd_post_E(C.byref(d), q, slot, st))
-            self._pending["E"] = self._halo.start("E")
+            self._sharded_halfstep("E", q, slot)
         if g.detectors:
             g._ring_fill["E"] += 1
 
@@ -285,17 +307,10 @@ class Engine:
         g, lib, d = self.grid, self.lib, self.desc
         self._ensure_wave(q, 1)
         slot = self._slot("H")
-        st = self._stream()
         if self._halo is None:
-            _capi.check(lib, lib.fdtd_update_H(C.byref(d), q, slot, st))
+            _capi.check(lib, lib.fdtd_update_H(C.byref(d), q, slot, self._stream()))
         else:
-            n = d.Nx
-            _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), 0, n - 1, q, slot, st))
-            self._halo.wait(self._pending["E"])
-            self._pending["E"] = None
-            _capi.check(lib, lib.fdtd_h_halfstep(C.byref(d), n - 1, n, q, slot, st))
-            _capi.check(lib, lib.fdtd_post_H(C.byref(d), q, slot, st))
-            self._pending["H"] = self._halo.start("H")
+            self._sharded_halfstep("H", q, slot)
         if g.detectors:
             g._ring_fill["H"] += 1
 
@@ -331,3 +346,5 @@ class Engine:
             for f in ("E", "H"):
                 self._halo.wait(self._pending[f])
                 self._pending[f] = None
+            if self._halo.cuda:
+                torch.cuda.current_stream(self.grid._E.device).wait_stream(self._halo.stream)

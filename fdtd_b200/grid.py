@@ -82,6 +82,7 @@ class Grid:
         self._ring_fill = {"E": 0, "H": 0}
         self._x_chunk = 0
         self._use_graphs = None      # None: automatic (small grids), True / False: force
+        self._fuse_post = None       # None: automatic (small grids), True / False: force
 
     # ----------------------------------------------------------------------------- materials
     def _material(self, value, what):

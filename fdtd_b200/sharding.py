@@ -118,7 +118,8 @@ class HaloExchange:
                     r.wait()                         # NCCL: orders the side stream, does not block the host
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
-            return ev
+            return ev                                # (the boundary plane of the next half-step runs on
+                                                     #  this same stream, right behind the exchange)
         return [op.op(op.tensor, op.peer) for op in ops]   # gloo: plain isend / irecv requests
 
     def wait(self, handle):

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 4
+#define FDTD_ABI_VERSION 5
 
 #define FDTD_F32 0
 #define FDTD_F64 1
@@ -151,6 +151,9 @@ typedef struct fdtd_desc {
   int32_t x_chunk;     /* planes marched per thread block; 0 = library default */
   int32_t use_graphs;  /* 1: fdtd_run may replay CUDA graphs of step chunks (launch-bound small grids) */
   int64_t* dyn;        /* device int64[2] scratch owned by the caller, needed when use_graphs = 1 */
+  int32_t fuse_post;   /* sources/detectors folded into the half-step kernel: 1 always (when legal), 0 never,
+                          -1 automatic (local slabs up to 2^23 cells, where a step is launch-bound) */
+  int32_t pad1_;
 } fdtd_desc;
 
 /* --- queries ------------------------------------------------------------------------- */
@@ -175,9 +178,9 @@ int fdtd_validate(const fdtd_desc* d);
 int fdtd_e_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, int64_t q, int64_t slot, void* stream);
 /* Same for H: PML.update_phi_H + curl_E + grid.py:309 + PML.update_H (+ sources, detectors). */
 int fdtd_h_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, int64_t q, int64_t slot, void* stream);
-/* 1 when sources and detectors are folded into the half-step kernels: nothing has to run between
- * the field update and them (no periodic copy, no late PML correction) and there are at most
- * FDTD_FUSED_MAX of each per field.  fdtd_post_E/H are then no-ops. */
+/* 1 when sources and detectors are folded into the half-step kernels: d->fuse_post allows it, nothing
+ * has to run between the field update and them (no periodic copy, no late PML correction) and there
+ * are at most FDTD_FUSED_MAX of each per field.  fdtd_post_E/H are then no-ops. */
 int fdtd_post_is_fused(const fdtd_desc* d);
 /* What follows the fused kernel inside Grid.update_E / update_H when it could not be folded, in
  * the reference's order: periodic copies and late PML corrections (registration order), sources

@@ -18,6 +18,7 @@ VDIR = os.path.join(ROOT, "fdtd_b200", "_variants")
 
 VARIANTS = {
     "default": [],
+    "post_inline": ["-DFDTD_POST_INLINE=1"],
     "noinl": ["-DFDTD_NOINLINE_SLABS=1"],
     "noinl_mb4": ["-DFDTD_NOINLINE_SLABS=1", "-DFDTD_MIN_BLOCKS=4"],
     "pfG": ["-DFDTD_PREFETCH_WHAT=1"],
