@@ -147,9 +147,15 @@ class PML(Boundary):
         if self.axis == 0:
             self._x0, self._x1 = part.local_range(self.lo, self.lo + t)
             cells = (self._x1 - self._x0) * g.Ny * g.Nz
-        else:
+        elif self.axis == 1:
             self._x0, self._x1 = 0, part.nx
-            cells = part.nx * t * (g.Nz if self.axis == 1 else g.Ny)
+            cells = part.nx * t * g.Nz
+        else:
+            # z slabs: padded rows so that the kernels' 128-bit accesses stay aligned (fdtd_b200.h)
+            self._x0, self._x1 = 0, part.nx
+            self._row_lo = self.lo & ~3
+            self._row = ((self.lo + t - self._row_lo) + 3) & ~3
+            cells = part.nx * g.Ny * self._row
         self._psi_E = bd.zeros((2, cells))
         self._psi_H = bd.zeros((2, cells))
 
@@ -168,7 +174,8 @@ class PML(Boundary):
             return p.view(2, self._x1 - self._x0, g.Ny, g.Nz)
         if self.axis == 1:
             return p.view(2, g._part.nx, t, g.Nz)
-        return p.view(2, g._part.nx, g.Ny, t)
+        a = self.lo - self._row_lo
+        return p.view(2, g._part.nx, g.Ny, self._row)[..., a:a + t]
 
 
 def DomainBorderPML(grid, border_cells=5):

@@ -105,6 +105,11 @@ int default_x_chunk(const Geometry& g, int nx, int Ny, int Nz) {
   return chunk;
 }
 
+// z slabs: psi rows start at z = lo rounded down to a multiple of 4 and are padded to a multiple of 4,
+// so that a thread's VEC cells are one aligned vector of its psi row
+int z_slab_lo(const fdtd_slab& S) { return S.lo & ~3; }
+int z_slab_row(const fdtd_slab& S) { return ((S.lo + S.thickness - z_slab_lo(S)) + 3) & ~3; }
+
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 int validate(const fdtd_desc* d) {
@@ -142,11 +147,11 @@ int validate(const fdtd_desc* d) {
       return fail(FDTD_ERR_ARG, "slab %d geometry", s);
     if (S.x0 < 0 || S.x1 > d->Nx || S.x0 > S.x1) return fail(FDTD_ERR_ARG, "slab %d x-range", s);
     i64 want = S.axis == 0 ? (i64)(S.x1 - S.x0) * d->plane
-                           : (S.axis == 1 ? (i64)d->Nx * S.thickness * d->Nz : (i64)d->Nx * d->Ny * S.thickness);
+                           : (S.axis == 1 ? (i64)d->Nx * S.thickness * d->Nz : (i64)d->Nx * d->Ny * z_slab_row(S));
     if (S.psi_count != want) return fail(FDTD_ERR_ARG, "slab %d psi_count %lld != %lld", s, (long long)S.psi_count, want);
     if (want > 0 && (!S.psi_E || !S.psi_H || !S.bE || !S.cE || !S.bH || !S.cH))
       return fail(FDTD_ERR_ARG, "slab %d null pointer", s);
-    if (S.axis != 2 && want > 0 && (!aligned(S.psi_E, w * g.vec) || !aligned(S.psi_H, w * g.vec)))
+    if (want > 0 && (!aligned(S.psi_E, w * g.vec) || !aligned(S.psi_H, w * g.vec)))
       return fail(FDTD_ERR_ARG, "slab %d psi misaligned", s);
   }
   if (d->n_post < 0 || d->n_post > FDTD_MAX_POST) return fail(FDTD_ERR_ARG, "n_post");
@@ -222,6 +227,8 @@ fdtd::SlabK<T> slab_k(const fdtd_slab& S) {
   k.x0 = S.x0;
   k.x1 = S.x1;
   k.count = S.psi_count;
+  k.lo_al = z_slab_lo(S);
+  k.tp = z_slab_row(S);
   k.psi = (T*)(IS_E ? S.psi_E : S.psi_H);
   k.b = (const T*)(IS_E ? S.bE : S.bH);
   k.c = (const T*)(IS_E ? S.cE : S.cH);

@@ -112,6 +112,7 @@ FDTD_DEV void prefetch_l2(const void* p) {
 template <typename T>
 struct SlabK {
   int axis, lo, t, fused, x0, x1;
+  int lo_al, tp;  // z slabs: psi rows are [tp] long and start at z = lo_al (both multiples of 4) -> vector access
   i64 count;
   T* psi;      // psi_E in the E half-step, psi_H in the H half-step
   const T* b;  // bE / bH
@@ -170,49 +171,33 @@ struct HalfStepParams {
 // d0 = one-sided difference of G_W along A (drives psi[0], corrects F_U with sign -),
 // d1 = one-sided difference of G_U along A (drives psi[1], corrects F_W with sign +).
 template <typename T, int VEC, bool IS_E>
-FDTD_DEV void slab_cells(const SlabK<T>& S, bool contiguous, i64 idx0, int l0, int lstep,
-                         const T (&d0)[VEC], const T (&d1)[VEC], T (&fu)[VEC], T (&fw)[VEC],
-                         const T (&cu)[VEC], const T (&cw)[VEC]) {
-  // contiguous: the VEC cells share l (x / y slabs) and psi is contiguous in z -> vector access.
-  // otherwise (z slabs) l = l0 + e and psi index = idx0 + e (layout [x][y][l]).
-  T p0[VEC], p1[VEC];
-  bool in[VEC];
-  if (contiguous) {
-    Pack<T, VEC> a = ldv<T, VEC>(S.psi + idx0);
-    Pack<T, VEC> b = ldv<T, VEC>(S.psi + S.count + idx0);
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      p0[e] = a.v[e];
-      p1[e] = b.v[e];
-      in[e] = true;
-    }
-  } else {
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      int l = l0 + e * lstep;
-      in[e] = (l >= 0) && (l < S.t);
-      p0[e] = in[e] ? S.psi[idx0 + e] : T(0);
-      p1[e] = in[e] ? S.psi[S.count + idx0 + e] : T(0);
-    }
-  }
+FDTD_DEV void slab_cells(const SlabK<T>& S, i64 idx0, int l0, int lstep, const T (&d0)[VEC],
+                         const T (&d1)[VEC], T (&fu)[VEC], T (&fw)[VEC], const T (&cu)[VEC],
+                         const T (&cw)[VEC]) {
+  // x / y slabs: the VEC cells share l (lstep = 0).  z slabs: l = l0 + e; psi rows are padded so that
+  // idx0 is vector-aligned, cells outside [0, t) are padding (stay zero).  Always 128-bit psi access.
+  Pack<T, VEC> a = ldv<T, VEC>(S.psi + idx0);
+  Pack<T, VEC> b = ldv<T, VEC>(S.psi + S.count + idx0);
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
-    int l = l0 + e * lstep;
-    if (in[e]) {
-      T b = S.b[l];
-      T c = S.c[l];
+    const int l = l0 + e * lstep;
+    if (l >= 0 && l < S.t) {
+      const T bb = S.b[l];
+      const T cc = S.c[l];
       // psi *= b; psi[inner] += diff * c[inner]      fdtd/boundaries.py:439-454, 467-482
-      bool inner = IS_E ? (l >= 1) : (l < S.t - 1);
-      p0[e] = p0[e] * b;
-      p1[e] = p1[e] * b;
+      const bool inner = IS_E ? (l >= 1) : (l < S.t - 1);
+      T p0 = a.v[e] * bb;
+      T p1 = b.v[e] * bb;
       if (inner) {
-        p0[e] = p0[e] + d0[e] * c;
-        p1[e] = p1[e] + d1[e] * c;
+        p0 = p0 + d0[e] * cc;
+        p1 = p1 + d1[e] * cc;
       }
+      a.v[e] = p0;
+      b.v[e] = p1;
       if (S.fused) {
         // phi_U = 0 - psi0, phi_W = psi1 - 0; F[loc] +-= sc*inv*phi   fdtd/boundaries.py:409-431, 456-459
-        T phi_u = T(0) - p0[e];
-        T phi_w = p1[e] - T(0);
+        const T phi_u = T(0) - p0;
+        const T phi_w = p1 - T(0);
         if (IS_E) {
           fu[e] = fu[e] + cu[e] * phi_u;
           fw[e] = fw[e] + cw[e] * phi_w;
@@ -223,24 +208,8 @@ FDTD_DEV void slab_cells(const SlabK<T>& S, bool contiguous, i64 idx0, int l0, i
       }
     }
   }
-  if (contiguous) {
-    Pack<T, VEC> a, b;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      a.v[e] = p0[e];
-      b.v[e] = p1[e];
-    }
-    stv<T, VEC>(S.psi + idx0, a);
-    stv<T, VEC>(S.psi + S.count + idx0, b);
-  } else {
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      if (in[e]) {
-        S.psi[idx0 + e] = p0[e];
-        S.psi[S.count + idx0 + e] = p1[e];
-      }
-    }
-  }
+  stv<T, VEC>(S.psi + idx0, a);
+  stv<T, VEC>(S.psi + S.count + idx0, b);
 }
 
 FDTD_DEV int lower_bound_i64(const i64* a, int n, i64 key) {
@@ -337,18 +306,18 @@ FDTD_SLAB_FN void slab_pass(const HalfStepParams<T>& P, CellState<T, VEC>& C, in
     const SlabK<T>& S = P.slabs[s];
     if (S.axis == 0) {
       if (i >= S.x0 && i < S.x1)
-        slab_cells<T, VEC, IS_E>(S, true, (i64)(i - S.x0) * P.plane + p, ig - S.lo, 0, C.d_zx, C.d_yx, C.fy,
-                                 C.fz, C.cy, C.cz);
+        slab_cells<T, VEC, IS_E>(S, (i64)(i - S.x0) * P.plane + p, ig - S.lo, 0, C.d_zx, C.d_yx, C.fy, C.fz,
+                                 C.cy, C.cz);
     } else if (S.axis == 1) {
       const int l = j - S.lo;
       if (l >= 0 && l < S.t)
-        slab_cells<T, VEC, IS_E>(S, true, ((i64)i * S.t + l) * P.Nz + k0, l, 0, C.d_xy, C.d_zy, C.fz, C.fx,
-                                 C.cz, C.cx);
+        slab_cells<T, VEC, IS_E>(S, ((i64)i * S.t + l) * P.Nz + k0, l, 0, C.d_xy, C.d_zy, C.fz, C.fx, C.cz,
+                                 C.cx);
     } else {
       const int l0 = k0 - S.lo;
       if (l0 + VEC > 0 && l0 < S.t)
-        slab_cells<T, VEC, IS_E>(S, false, ((i64)i * P.Ny + j) * S.t + l0, l0, 1, C.d_yz, C.d_xz, C.fx, C.fy,
-                                 C.cx, C.cy);
+        slab_cells<T, VEC, IS_E>(S, ((i64)i * P.Ny + j) * S.tp + (k0 - S.lo_al), l0, 1, C.d_yz, C.d_xz, C.fx,
+                                 C.fy, C.cx, C.cy);
     }
   }
 }
@@ -644,9 +613,10 @@ __global__ void pml_add_kernel(SlabK<T> S, T* F0, T* F1, T* F2, const T* c0, con
       j = S.lo + (int)((n / Nz) % S.t);
       k = (int)(n % Nz);
     } else {
-      i = (int)(n / ((i64)Ny * S.t));
-      j = (int)((n / S.t) % Ny);
-      k = S.lo + (int)(n % S.t);
+      i = (int)(n / ((i64)Ny * S.tp));
+      j = (int)((n / S.tp) % Ny);
+      k = S.lo_al + (int)(n % S.tp);
+      if (k < S.lo || k >= S.lo + S.t) continue;  // row padding
     }
     const i64 off = (i64)i * plane + (i64)j * Nz + k;
     const int u = (S.axis + 1) % 3, w = (S.axis + 2) % 3;

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 5
+#define FDTD_ABI_VERSION 6
 
 #define FDTD_F32 0
 #define FDTD_F64 1
@@ -78,7 +78,8 @@ extern "C" {
  * psi layout (psi[1] starts psi_count elements after psi[0]):
  *   axis 0: [x - x0][y][z]   for local planes x0 <= x < x1
  *   axis 1: [x][l][z]
- *   axis 2: [x][y][l]                                                            */
+ *   axis 2: [x][y][r], rows of length R = roundup4(lo + thickness - (lo & ~3)) whose entry r is the cell
+ *           z = (lo & ~3) + r; entries outside the slab are padding (zero) -- keeps psi access 128-bit aligned */
 typedef struct fdtd_slab {
   int32_t axis;
   int32_t lo;          /* first GLOBAL index of the slab along axis */
