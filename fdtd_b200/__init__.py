@@ -19,8 +19,8 @@ __version__ = "0.1.0"
 
 from .backend import backend, set_backend
 from .grid import Grid
-from .sources import PointSource, LineSource, PlaneSource
-from .detectors import LineDetector, BlockDetector
+from .sources import PointSource, LineSource, PlaneSource, SoftArbitraryPointSource
+from .detectors import LineDetector, BlockDetector, CurrentDetector
 from .objects import Object, AbsorbingObject, AnisotropicObject
 from .boundaries import PeriodicBoundary, PML, DomainBorderPML
 from . import constants, waveforms

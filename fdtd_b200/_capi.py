@@ -6,12 +6,13 @@ loudly when it is missing: there is no CPU or PyTorch fallback for the hot path.
 import ctypes as C
 import os
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_SLABS, MAX_POST, MAX_SOURCES, MAX_DETECTORS, FUSED_MAX = 6, 16, 64, 64, 6
 F32, F64 = 0, 1
 CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT = 1, 2, 4, 8
 POST_PERIODIC, POST_PML_ADD = 0, 1
-SRC_POINTS, SRC_BOX = 0, 1
+SRC_POINTS, SRC_BOX, SRC_FEEDBACK = 0, 1, 2
+DET_FIELD, DET_CURRENT = 0, 1
 
 _vp = C.c_void_p
 
@@ -25,12 +26,15 @@ class Slab(C.Structure):
 class Source(C.Structure):
     _fields_ = [("kind", C.c_int32), ("field", C.c_int32), ("comp", C.c_int32), ("n", C.c_int32),
                 ("idx", _vp), ("profile", _vp), ("amplitude", C.c_double), ("box", C.c_int32 * 6),
-                ("wave", _vp), ("wave_q0", C.c_int64), ("wave_len", C.c_int64), ("bbox", C.c_int32 * 6)]
+                ("wave", _vp), ("wave_q0", C.c_int64), ("wave_len", C.c_int64), ("bbox", C.c_int32 * 6),
+                ("impedance", C.c_double), ("spacing", C.c_double), ("feedback", _vp), ("record", _vp),
+                ("record_capacity", C.c_int64)]
 
 
 class Detector(C.Structure):
-    _fields_ = [("n", C.c_int32), ("pad_", C.c_int32), ("idx", _vp), ("pos", _vp), ("ring_E", _vp),
-                ("ring_H", _vp), ("capacity", C.c_int64), ("bbox", C.c_int32 * 6)]
+    _fields_ = [("n", C.c_int32), ("kind", C.c_int32), ("idx", _vp), ("pos", _vp), ("ring_E", _vp),
+                ("ring_H", _vp), ("capacity", C.c_int64), ("bbox", C.c_int32 * 6), ("last", _vp),
+                ("spacing", C.c_double)]
 
 
 class Desc(C.Structure):

@@ -175,6 +175,10 @@ int validate(const fdtd_desc* d) {
     } else if (S.kind == FDTD_SRC_BOX) {
       if (S.box[0] < 0 || S.box[1] > d->Nx || S.box[2] < 0 || S.box[3] > d->Ny || S.box[4] < 0 || S.box[5] > d->Nz)
         return fail(FDTD_ERR_ARG, "source %d box", n);
+    } else if (S.kind == FDTD_SRC_FEEDBACK) {
+      if (S.n < 0 || S.n > 1 || (S.n == 1 && (!S.feedback || !S.profile || S.spacing <= 0 || S.field != 0)))
+        return fail(FDTD_ERR_ARG, "source %d feedback", n);
+      if (S.n == 1 && (S.box[0] < 0 || S.box[0] >= d->Nx)) return fail(FDTD_ERR_ARG, "source %d feedback cell", n);
     } else {
       return fail(FDTD_ERR_ARG, "source %d kind", n);
     }
@@ -183,8 +187,12 @@ int validate(const fdtd_desc* d) {
   if (d->n_detectors < 0 || d->n_detectors > FDTD_MAX_DETECTORS) return fail(FDTD_ERR_ARG, "n_detectors");
   for (int n = 0; n < d->n_detectors; ++n) {
     const fdtd_detector& D = d->detectors[n];
-    if (D.n < 0 || (D.n > 0 && (!D.idx || !D.pos || !D.ring_E || !D.ring_H || D.capacity < 1)))
+    if (D.kind != FDTD_DET_FIELD && D.kind != FDTD_DET_CURRENT) return fail(FDTD_ERR_ARG, "detector %d kind", n);
+    if (D.n < 0 || (D.n > 0 && (!D.idx || !D.pos || !D.ring_H || D.capacity < 1)))
       return fail(FDTD_ERR_ARG, "detector %d", n);
+    if (D.n > 0 && D.kind == FDTD_DET_FIELD && !D.ring_E) return fail(FDTD_ERR_ARG, "detector %d ring_E", n);
+    if (D.n > 0 && D.kind == FDTD_DET_CURRENT && (!D.last || D.spacing <= 0))
+      return fail(FDTD_ERR_ARG, "detector %d current", n);
   }
   if (d->use_graphs && !d->dyn) return fail(FDTD_ERR_ARG, "use_graphs needs the dyn scratch");
   return FDTD_OK;
@@ -204,7 +212,12 @@ bool post_is_fused(const fdtd_desc* d) {
     if (N >= 2) return false;
   }
   int ns[2] = {0, 0};
-  for (int n = 0; n < d->n_sources; ++n) ns[d->sources[n].field]++;
+  for (int n = 0; n < d->n_sources; ++n) {
+    if (d->sources[n].kind == FDTD_SRC_FEEDBACK) return false;
+    ns[d->sources[n].field]++;
+  }
+  for (int n = 0; n < d->n_detectors; ++n)
+    if (d->detectors[n].kind != FDTD_DET_FIELD) return false;
   if (ns[0] > FDTD_FUSED_MAX || ns[1] > FDTD_FUSED_MAX) return false;
   int nd = 0;
   for (int n = 0; n < d->n_detectors; ++n) nd += d->detectors[n].n > 0;
@@ -391,6 +404,14 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
       if (S.n == 0) continue;
       FDTD_LAUNCH((fdtd::source_points_kernel<T>), dim3(blocks_for(S.n)), dim3(256), stream, F[S.comp],
                   (const i64*)S.idx, (const T*)S.profile, S.n, (const T*)S.wave, (i64)w);
+    } else if (S.kind == FDTD_SRC_FEEDBACK) {
+      if (S.n == 0) continue;
+      if (S.record && (slot < 0 || slot >= S.record_capacity))
+        return fail(FDTD_ERR_ARG, "source %d: record slot %lld outside capacity", n, (long long)slot);
+      i64 cell = (i64)S.box[0] * d->plane + (i64)S.box[2] * d->Nz + S.box[4];
+      FDTD_LAUNCH((fdtd::source_feedback_kernel<T>), dim3(1), dim3(32), stream, F[2], cell, (const T*)S.wave,
+                  (const T*)S.profile, (i64)w, (T)S.impedance, (const T*)S.feedback, (int)(q > 0), (T)S.spacing,
+                  (T*)S.record, (i64)slot);
     } else {
       i64 cells = (i64)(S.box[1] - S.box[0]) * (S.box[3] - S.box[2]) * (S.box[5] - S.box[4]);
       if (cells <= 0) continue;
@@ -408,6 +429,15 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
     if (slot < 0 || slot >= D.capacity)
       return fail(FDTD_ERR_ARG, "detector %d: ring slot %lld outside capacity %lld", n, (long long)slot,
                   (long long)D.capacity);
+    if (D.kind == FDTD_DET_CURRENT) {
+      if (IS_E) continue;  // CurrentDetector.detect_E is empty (fdtd/detectors.py:414-415)
+      FDTD_LAUNCH((fdtd::current_kernel<T>), dim3(blocks_for(D.n)), dim3(256), stream, (const T*)d->H[0],
+                  (const T*)d->H[1], (const i64*)D.idx, (const int*)D.pos, D.n, d->Nx, d->Ny, d->Nz, d->plane,
+                  (T)D.spacing, (T*)D.ring_H, (T*)D.last, (i64)slot);
+      int rc2 = check_launch("current detector");
+      if (rc2) return rc2;
+      continue;
+    }
     FDTD_LAUNCH((fdtd::detector_kernel<T>), dim3(blocks_for((i64)D.n * 3)), dim3(256), stream, F[0], F[1], F[2],
                 (const i64*)D.idx, (const int*)D.pos, D.n, (T*)(IS_E ? D.ring_E : D.ring_H), (i64)slot);
     int rc = check_launch("detector");

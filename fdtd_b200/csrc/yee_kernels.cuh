@@ -675,6 +675,52 @@ __global__ void detector_kernel(const T* F0, const T* F1, const T* F2, const i64
   }
 }
 
+// CurrentDetector.single_point_current (fdtd/detectors.py:417-461): z-current through each cell from the
+// loop of H around it, averaged over the cell's z level and the one below; indices wrap like python's.
+// The second `current_vector_2` is ACCUMULATED onto the first (`+=`, fdtd/detectors.py:456) as in the reference.
+template <typename T>
+__global__ void current_kernel(const T* Hx, const T* Hy, const i64* idx, const int* pos, int n, int Nx, int Ny,
+                               int Nz, i64 plane, T dx, T* ring, T* last, i64 slot) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const i64 lin = idx[t];
+    const i64 px = lin / plane, py = (lin % plane) / Nz, pz = lin % Nz;
+    const i64 pxm = px > 0 ? px - 1 : Nx - 1;
+    const i64 pym = py > 0 ? py - 1 : Ny - 1;
+    const i64 pzm = pz > 0 ? pz - 1 : Nz - 1;
+    T cv1 = (Hx[px * plane + pym * Nz + pz] - Hx[px * plane + py * Nz + pz]) * dx;
+    T cv2 = (Hy[px * plane + py * Nz + pz] - Hy[pxm * plane + py * Nz + pz]) * dx;
+    const T c1 = cv1 + cv2;
+    cv1 = (Hx[px * plane + pym * Nz + pzm] - Hx[px * plane + py * Nz + pzm]) * dx;
+    cv2 = cv2 + (Hy[px * plane + py * Nz + pzm] - Hy[pxm * plane + py * Nz + pzm]) * dx;
+    const T c2 = cv1 + cv2;
+    const T I = (c1 + c2) / T(2);
+    ring[slot * n + pos[t]] = I;
+    last[pos[t]] = I;
+  }
+}
+
+// SoftArbitraryPointSource.update_E (fdtd/sources.py:596-626).
+//   wave[w]     = input voltage of the step, in the grid dtype
+//   wave_div[w] = input voltage / grid spacing evaluated in float64 on the host, then rounded: what the
+//                 reference adds when no current enters (Z <= 0, or the very first step) -- there the whole
+//                 expression is host float64 arithmetic
+//   otherwise   vout = vin + Z * I_prev and E += vout / dx, in the grid dtype
+template <typename T>
+__global__ void source_feedback_kernel(T* F, i64 cell, const T* wave, const T* wave_div, i64 w, T impedance,
+                                       const T* last_I, int use_current, T dx, T* record, i64 slot) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const T vin = wave[w];
+    T vout = vin;
+    if (impedance > T(0) && use_current) {
+      vout = vin + impedance * last_I[0];
+      F[cell] = F[cell] + vout / dx;
+    } else {
+      F[cell] = F[cell] + wave_div[w];
+    }
+    if (record) record[slot] = vout;
+  }
+}
+
 // graph replays: the per-launch bases of the waveform index and the ring slot
 __global__ void set_dyn_kernel(i64* dyn, i64 wave_base, i64 slot_base) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {

@@ -10,11 +10,16 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _capi
 from .backend import backend as bd
 from .sources import _diagonal_points, bounding_box, local_points
 
 
 class _Detector:
+    _kind = _capi.DET_FIELD
+    _fields = ("E", "H")         # histories kept, in ring order (ring_E, ring_H)
+    _width = 3                   # values per point and sample
+
     def __init__(self, name=None):
         self.grid = None
         self.name = name
@@ -49,25 +54,26 @@ class _Detector:
             if g._ring_fill["E"] or g._ring_fill["H"]:
                 raise RuntimeError("detector ring resized with samples pending")
             self._capacity = capacity
-            self._ring_E = bd.zeros((capacity, max(1, self._n_local), 3))
-            self._ring_H = bd.zeros((capacity, max(1, self._n_local), 3))
+            self._ring_E = bd.zeros((capacity, max(1, self._n_local), self._width))
+            self._ring_H = bd.zeros((capacity, max(1, self._n_local), self._width))
 
     def _drain(self, nE, nH):
         """copy the filled part of the rings to the host (one batch) and assemble global samples."""
         part = self.grid._part
         for f, ring, n in (("E", self._ring_E, nE), ("H", self._ring_H, nH)):
-            if n == 0:
+            if n == 0 or f not in self._chunks:
                 continue
             local = ring[:n, :self._n_local].to("cpu", copy=True).numpy()
             if part.sharded:
                 gathered = [None] * part.world
                 dist.all_gather_object(gathered, (self._positions, local))
-                full = np.zeros((n, self._n_points, 3), dtype=local.dtype)
+                full = np.zeros((n, self._n_points, self._width), dtype=local.dtype)
                 for pos, vals in gathered:
                     full[:, pos] = vals
             else:
                 full = local
-            self._chunks[f].append(full.reshape((n,) + self._sample_shape + (3,)))
+            tail = (self._width,) if self._width > 1 else ()
+            self._chunks[f].append(full.reshape((n,) + self._sample_shape + tail))
             self._lists[f] = None
 
     def _history(self, f):
@@ -141,3 +147,43 @@ class BlockDetector(_Detector):
                 raise IndexError("BlockDetector ranges are inclusive of `stop`: index out of range")
         X, Y, Z = np.meshgrid(self.x, self.y, self.z, indexing="ij")
         self._set_points(X.ravel(), Y.ravel(), Z.ravel(), X.shape)
+
+
+class CurrentDetector(BlockDetector):
+    """z-directed current through each cell of a block (inclusive ranges like BlockDetector), from the
+    loop of H around the cell averaged over two z levels (fdtd/detectors.py:284-496).  One (nx, ny, nz)
+    array per step in `detector.I`, sampled on the device after every H half-step; the most recent sample
+    also stays on the device, where a SoftArbitraryPointSource reads it back without a host round trip."""
+
+    _kind = _capi.DET_CURRENT
+    _width = 1
+
+    def __init__(self, name=None):
+        super().__init__(name)
+        self.orientation = None
+        self._chunks = {"H": []}          # the current is sampled with the H half-step
+        self._lists = {"H": None}
+
+    def _register_grid(self, grid, x, y, z):
+        super()._register_grid(grid, x, y, z)
+        part = grid._part
+        if part.sharded and self._n_local and self._bbox[0] == 0 and part.x0 > 0:
+            raise NotImplementedError("a CurrentDetector cell on the first plane of an x-slab (needs the "
+                                      "neighbour slab's H of the same half-step)")
+        self._last = bd.zeros((max(1, self._n_local),))
+
+    @property
+    def I(self):
+        return self._history("H")
+
+    @property
+    def E(self):
+        raise AttributeError("CurrentDetector records I, not E")
+
+    @property
+    def H(self):
+        raise AttributeError("CurrentDetector records I, not H")
+
+    def detector_values(self):
+        """outputs what detector detects (fdtd/detectors.py:494-496)."""
+        return {"I": self.I}

@@ -127,7 +127,8 @@ class Engine:
         self.tile_class = cls
 
         # --- sources ----------------------------------------------------------------------------
-        self._src_entries = []       # (desc index, source object, kind tag)
+        self._src_entries = []       # (desc index, source object)
+        self._feedback_sources = []  # those that record their voltages in a device ring
         n = 0
         for s in g.sources:
             for entry in s._entries():
@@ -135,7 +136,14 @@ class Engine:
                     raise ValueError(f"at most {_capi.MAX_SOURCES} source entries")
                 e = d.sources[n]
                 e.kind, e.field, e.comp = entry["kind"], entry["field"], entry["comp"]
-                if entry["kind"] == _capi.SRC_POINTS:
+                if entry["kind"] == _capi.SRC_FEEDBACK:
+                    e.n = entry["n"]
+                    for k in range(6):
+                        e.box[k] = entry["box"][k]
+                    e.impedance, e.spacing = entry["impedance"], g.grid_spacing
+                    e.feedback = _ptr(entry["feedback"])
+                    self._feedback_sources.append((n, s))
+                elif entry["kind"] == _capi.SRC_POINTS:
                     e.n = int(entry["idx"].numel())
                     e.idx, e.profile = _ptr(entry["idx"]), _ptr(entry["profile"])
                     for k in range(6):
@@ -154,18 +162,27 @@ class Engine:
         if len(g.detectors) > _capi.MAX_DETECTORS:
             raise ValueError(f"at most {_capi.MAX_DETECTORS} detectors")
         w = 4 if dt is torch.float32 else 8
-        per_step = sum(2 * 3 * w * max(1, det._n_local) for det in g.detectors)
+        per_step = sum(2 * det._width * w * max(1, det._n_local) for det in g.detectors)
         self.ring_capacity = int(min(8192, max(16, RING_BYTES // max(1, per_step)))) if g.detectors else 1 << 62
         for n, det in enumerate(g.detectors):
             det._ensure_ring(self.ring_capacity)
             e = d.detectors[n]
             e.n = det._n_local
+            e.kind = det._kind
+            if det._kind == _capi.DET_CURRENT:
+                e.last, e.spacing = _ptr(det._last), g.grid_spacing
             e.idx, e.pos = _ptr(det._idx), _ptr(det._pos)
             e.ring_E, e.ring_H = _ptr(det._ring_E), _ptr(det._ring_H)
             e.capacity = self.ring_capacity
             for k in range(6):
                 e.bbox[k] = det._bbox[k]
         d.n_detectors = len(g.detectors)
+        for idx, src in self._feedback_sources:
+            src._ensure_ring(self.ring_capacity if g.detectors else 4096)
+            d.sources[idx].record = _ptr(src._ring_V)
+            d.sources[idx].record_capacity = src._capacity
+        if self._feedback_sources and not g.detectors:
+            self.ring_capacity = 4096
 
         # CUDA-graph replay of step chunks pays off where a step is launch-bound (small grids)
         self._dyn = torch.zeros(2, dtype=torch.int64, device=g._E.device)
@@ -238,6 +255,13 @@ class Engine:
             t = tables[id(src)]
             e = d.sources[idx]
             e.wave, e.wave_q0, e.wave_len = _ptr(t), q0, ln
+            if e.kind == _capi.SRC_FEEDBACK:
+                key = ("div", id(src))
+                if key not in tables:
+                    vals = torch.tensor([src._wave_value(q) / g.grid_spacing for q in range(q0, q0 + ln)],
+                                        dtype=torch.float64)
+                    tables[key] = vals.to(g._dtype).to(g._E.device)
+                e.profile = _ptr(tables[key])
         self._wave_keep = list(tables.values())
         self._wave = (q0, ln)
 
@@ -248,7 +272,7 @@ class Engine:
     def _slot(self, field):
         """next free ring slot for `field`, flushing the rings to the host when full."""
         g = self.grid
-        if not g.detectors:
+        if not g.detectors and not self._feedback_sources:
             return 0
         if g._ring_fill[field] >= self.ring_capacity:
             self.flush_detectors()
@@ -261,6 +285,8 @@ class Engine:
             return
         for det in g.detectors:
             det._drain(nE, nH)
+        for _, src in self._feedback_sources:
+            src._drain(nE)
         g._ring_fill["E"] = g._ring_fill["H"] = 0
 
     # ------------------------------------------------------------------------------------ stepping
@@ -300,8 +326,10 @@ class Engine:
             _capi.check(lib, lib.fdtd_update_E(C.byref(d), q, slot, self._stream()))
         else:
             self._sharded_halfstep("E", q, slot)
-        if g.detectors:
+        if g.detectors or self._feedback_sources:
             g._ring_fill["E"] += 1
+        for _, src in self._feedback_sources:
+            src._steps_logged.append(q)
 
     def update_H(self, q):
         g, lib, d = self.grid, self.lib, self.desc
@@ -311,27 +339,29 @@ class Engine:
             _capi.check(lib, lib.fdtd_update_H(C.byref(d), q, slot, self._stream()))
         else:
             self._sharded_halfstep("H", q, slot)
-        if g.detectors:
+        if g.detectors or self._feedback_sources:
             g._ring_fill["H"] += 1
 
     def run(self, q0, nsteps, progress=None):
         """nsteps full steps from step index q0; one C call per chunk when not sharded."""
         g, lib, d = self.grid, self.lib, self.desc
         done = 0
+        rings = bool(g.detectors or self._feedback_sources)
         while done < nsteps:
-            if g.detectors and (g._ring_fill["E"] != g._ring_fill["H"]
-                                or g._ring_fill["E"] >= self.ring_capacity):
+            if rings and (g._ring_fill["E"] != g._ring_fill["H"] or g._ring_fill["E"] >= self.ring_capacity):
                 self.flush_detectors()
-            room = self.ring_capacity - g._ring_fill["E"] if g.detectors else nsteps
+            room = self.ring_capacity - g._ring_fill["E"] if rings else nsteps
             n = min(nsteps - done, room, WAVE_TABLE_MAX)
             q = q0 + done
             self._ensure_wave(q, n)
             if self._halo is None:
-                _capi.check(lib, lib.fdtd_run(C.byref(d), q, n, g._ring_fill["E"] if g.detectors else 0,
+                _capi.check(lib, lib.fdtd_run(C.byref(d), q, n, g._ring_fill["E"] if rings else 0,
                                               self._stream()))
-                if g.detectors:
+                if rings:
                     g._ring_fill["E"] += n
                     g._ring_fill["H"] += n
+                for _, src in self._feedback_sources:
+                    src._steps_logged.extend(range(q, q + n))
             else:
                 for s in range(n):
                     self.update_E(q + s)

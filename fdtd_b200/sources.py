@@ -248,3 +248,106 @@ class PlaneSource:
         s = "    " + repr(self) + "\n"
         return s + (f"        @ x=[{self.x.start}, ... , {self.x.stop}], y=[{self.y.start}, ... , {self.y.stop}], "
                     f"z=[{self.z.start}, ... , {self.z.stop}]\n")
+
+
+class SoftArbitraryPointSource:
+    """A voltage source with series impedance on one cell, paired with a CurrentDetector on the same cell
+    (fdtd/sources.py:504-643):  Ez += (waveform[q] + Z * I_prev) / grid_spacing, where I_prev is the
+    detector's sample of the previous step.  The reference reads that sample back on the host every step;
+    here it stays on the device (the detector kernel leaves its latest value in a device scalar the source
+    kernel reads), so a 50-ohm feed costs no host round trip.  `input_voltage` / `source_voltage` are
+    recorded in a device ring and materialised like detector histories."""
+
+    def __init__(self, waveform_array, name: str = None, impedance: float = 0.0):
+        self.grid = None
+        self.name = name
+        self.current_detector = None
+        self.waveform_array = waveform_array
+        self.impedance = impedance
+        self._chunks = []
+        self._lists = None
+        self._ring_V = None
+        self._capacity = 0
+        self._steps_logged = []      # step index of every E half-step this source took part in
+
+    def _register_grid(self, grid, x, y, z):
+        from .detectors import CurrentDetector
+        self.grid = grid
+        self.grid.sources.append(self)
+        grid._register_name(self)
+        try:
+            (x,), (y,), (z,) = x, y, z
+        except (TypeError, ValueError):
+            raise ValueError("a point source should be placed on a single grid cell.")
+        self.x, self.y, self.z = grid._handle_tuple((x, y, z))
+        # (the reference raises UnboundLocalError here when a name is given, fdtd/sources.py:592-593)
+        detector_name = self.name + "_I" if self.name is not None else None
+        self.current_detector = CurrentDetector(name=detector_name)
+        grid[x, y, z] = self.current_detector
+        lx0, lx1 = grid._part.local_range(self.x, self.x + 1)
+        self._n_local = lx1 - lx0
+        self._box = [lx0, lx1, self.y, self.y + 1, self.z, self.z + 1]
+        wf = self.waveform_array
+        wf = wf.detach().cpu().numpy() if torch.is_tensor(wf) else np.asarray(wf)
+        self._waveform_host = wf.reshape(-1)
+
+    def _wave_value(self, q):
+        # input voltage of step q; zero once the waveform is exhausted (fdtd/sources.py:601-605)
+        return float(self._waveform_host[q]) if q < self._waveform_host.shape[0] else 0.0
+
+    def _entries(self):
+        return [dict(kind=_capi.SRC_FEEDBACK, field=0, comp=2, n=self._n_local, box=self._box,
+                     impedance=float(self.impedance), feedback=self.current_detector._last)]
+
+    def _ensure_ring(self, capacity):
+        if self._ring_V is None or self._capacity != capacity:
+            self._capacity = capacity
+            self._ring_V = bd.zeros((capacity,))
+
+    def _drain(self, n):
+        if n == 0:
+            return
+        local = self._ring_V[:n].to("cpu", copy=True).numpy()
+        part = self.grid._part
+        if part.sharded:
+            import torch.distributed as dist
+            gathered = [None] * part.world
+            dist.all_gather_object(gathered, local if self._n_local else None)
+            local = next(v for v in gathered if v is not None)
+        self._chunks.append(local)
+        self._lists = None
+
+    def _history(self):
+        g = self.grid
+        if g is not None and g._engine is not None:
+            g._engine.flush_detectors()
+        if self._lists is None:
+            vout = [v for chunk in self._chunks for v in chunk]
+            # the input voltage is host data (the reference records the waveform element itself)
+            vin = [self._waveform_host[q] if q < self._waveform_host.shape[0] else 0.0
+                   for q in self._steps_logged[:len(vout)]]
+            if not self.impedance > 0:
+                vout = vin                       # no feedback: the output voltage is the waveform element
+            self._lists = ([[[[v]]] for v in vin], [[[[v]]] for v in vout])
+        return self._lists
+
+    @property
+    def input_voltage(self):
+        """voltage hard-imposed by the source, one [[[v]]] per step like the reference's list"""
+        return self._history()[0]
+
+    @property
+    def source_voltage(self):
+        return self._history()[1]
+
+    def update_E(self):
+        pass
+
+    def update_H(self):
+        pass
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}()"
+
+    def __str__(self):
+        return "    " + repr(self) + "\n" + f"        @ x={self.x}, y={self.y}, z={self.z}\n"

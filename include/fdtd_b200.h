@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 6
+#define FDTD_ABI_VERSION 7
 
 #define FDTD_F32 0
 #define FDTD_F64 1
@@ -69,6 +69,14 @@ extern "C" {
 /* source kinds */
 #define FDTD_SRC_POINTS 0     /* soft: F[comp][idx[n]] += profile[n] * wave[q]   (Point/LineSource) */
 #define FDTD_SRC_BOX 1        /* hard: F[comp][box]     = amplitude  * wave[q]   (PlaneSource) */
+#define FDTD_SRC_FEEDBACK 2   /* soft voltage source with series impedance (SoftArbitraryPointSource,
+                                 fdtd/sources.py:596-626): Ez[idx[0]] += (wave[q] + Z * I_prev) / spacing, where
+                                 I_prev is the last sample of a current detector, kept on the device */
+
+/* detector kinds */
+#define FDTD_DET_FIELD 0      /* E after the E half-step, H after the H half-step: [capacity][n][3] rings */
+#define FDTD_DET_CURRENT 1    /* CurrentDetector (fdtd/detectors.py:417-476): after the H half-step, the z-current
+                                 from the H loop around each cell (two z-levels averaged): ring_H is [capacity][n] */
 
 /* One CPML slab (replaces the 14 full-size arrays per PML of fdtd/boundaries.py:367-407).
  * Local index l = global index along `axis` - lo.  Only two psi scalars per cell and per
@@ -108,17 +116,26 @@ typedef struct fdtd_source {
   int64_t wave_q0;
   int64_t wave_len;
   int32_t bbox[6];     /* FDTD_SRC_POINTS: local bounding box x0,x1,y0,y1,z0,z1 (half-open) of the points */
+  /* FDTD_SRC_FEEDBACK only.  wave = input voltage per step; profile = device [wave_len] input voltage /
+   * spacing evaluated in float64 and rounded (added as is when no current enters the step: Z <= 0 or q = 0). */
+  double impedance;    /* Z (ohm); <= 0: plain voltage source */
+  double spacing;      /* grid spacing: volts -> field */
+  const void* feedback;/* device [1]: last current sample of the paired detector (fdtd_detector.last) */
+  void* record;        /* device [record_capacity]: output voltage per step, or NULL */
+  int64_t record_capacity;
 } fdtd_source;
 
 typedef struct fdtd_detector {
   int32_t n;           /* points on this slab */
-  int32_t pad_;
+  int32_t kind;        /* FDTD_DET_* */
   const int64_t* idx;  /* device [n]: local linear cell index, ASCENDING */
   const int32_t* pos;  /* device [n]: position of each entry in the detector's sampling order (ring column) */
   void* ring_E;        /* device [capacity][n][3] */
   void* ring_H;        /* device [capacity][n][3] */
   int64_t capacity;
   int32_t bbox[6];     /* local bounding box of the points */
+  void* last;          /* FDTD_DET_CURRENT: device [n], most recent sample (feeds FDTD_SRC_FEEDBACK) */
+  double spacing;      /* FDTD_DET_CURRENT: grid spacing */
 } fdtd_detector;
 
 typedef struct fdtd_desc {

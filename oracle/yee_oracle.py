@@ -23,6 +23,8 @@ What is restated (reference file:line):
   Point/Line/PlaneSource ..... fdtd/sources.py:25-127, 131-315, 319-501
   hanning .................... fdtd/waveforms.py:8-9
   Line/BlockDetector ......... fdtd/detectors.py:20-139, 146-280
+  CurrentDetector ............ fdtd/detectors.py:284-496
+  SoftArbitraryPointSource ... fdtd/sources.py:504-643
 
 It is NOT a copy: the reference keeps nine psi components, three phi components
 and six full-size coefficient arrays per PML and loops over plug-in objects; the
@@ -774,3 +776,73 @@ class BlockDetector(LineDetector):
 
     def detect_H(self):
         self.H.append(self._sample(self.grid.H))
+
+
+class CurrentDetector(BlockDetector):
+    """fdtd/detectors.py:284-496: z-current from the H loop around a cell, two z levels averaged.
+    One (nx,ny,nz) array per H half-step in `I`; nothing is recorded after the E half-step."""
+
+    def __init__(self, name=None):
+        super().__init__(name)
+        self.I = []
+
+    def detect_E(self):
+        pass
+
+    def _point(self, px, py, pz):
+        H, dx = self.grid.H, self.grid.grid_spacing
+        # fdtd/detectors.py:444-461 -- note the `+=` on the second current_vector_2
+        v1 = (H[px, py - 1, pz, 0] - H[px, py, pz, 0]) * dx
+        v2 = (H[px, py, pz, 1] - H[px - 1, py, pz, 1]) * dx
+        c1 = v1 + v2
+        v1 = (H[px, py - 1, pz - 1, 0] - H[px, py, pz - 1, 0]) * dx
+        v2 = v2 + (H[px, py, pz - 1, 1] - H[px - 1, py, pz - 1, 1]) * dx
+        c2 = v1 + v2
+        return (c1 + c2) / 2.0
+
+    def detect_H(self):
+        out = lib.zeros((len(self.x), len(self.y), len(self.z)))
+        for i, px in enumerate(self.x):
+            for j, py in enumerate(self.y):
+                for k, pz in enumerate(self.z):
+                    out[i, j, k] = self._point(px, py, pz)
+        self.I.append(out)
+
+    def detector_values(self):
+        return {"I": self.I}
+
+
+class SoftArbitraryPointSource:
+    """fdtd/sources.py:504-643: Ez += (waveform[q] + Z*I_prev)/dx with I_prev the paired
+    CurrentDetector's sample of the previous step."""
+
+    def __init__(self, waveform_array, name=None, impedance=0.0):
+        self.grid = None
+        self.name = name
+        self.waveform_array = waveform_array
+        self.impedance = impedance
+        self.input_voltage, self.source_voltage = [], []
+
+    def _register_grid(self, grid, x, y, z):
+        self.grid = grid
+        grid.sources.append(self)
+        grid._name(self)
+        try:
+            (x,), (y,), (z,) = x, y, z
+        except (TypeError, ValueError):
+            raise ValueError("a point source should be placed on a single grid cell.")
+        self.x, self.y, self.z = grid._cells(x), grid._cells(y), grid._cells(z)
+        self.current_detector = CurrentDetector(name=None if self.name is None else self.name + "_I")
+        grid[x, y, z] = self.current_detector
+
+    def update_E(self):
+        q = self.grid.time_steps_passed
+        vin = self.waveform_array[q] if q < self.waveform_array.shape[0] else 0.0
+        cur = self.current_detector.I[-1][0][0][0] if q > 0 else 0.0
+        vout = vin + self.impedance * cur if self.impedance > 0 else vin
+        self.grid.E[self.x, self.y, self.z, 2] += vout / self.grid.grid_spacing
+        self.input_voltage.append([[[vin]]])
+        self.source_voltage.append([[[vout]]])
+
+    def update_H(self):
+        pass

@@ -47,7 +47,7 @@ def load_reference():
     return mod
 
 
-F32_SCENES = ("pml3d", "objects3d", "periodic3d", "c4small")
+F32_SCENES = ("pml3d", "objects3d", "periodic3d", "c4small", "feed50")
 
 
 def main():
@@ -63,7 +63,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, "curls.npz"), E=E, H=H,
                         curl_E=curl_E(E), curl_H=curl_H(H))
 
+    only = sys.argv[1:]
     for name, (build, steps) in scenes.SCENES.items():
+        if only and name not in only:
+            continue
         torch.set_default_dtype(torch.float64)
         ref.set_backend("numpy")
         g = build(ref)

@@ -124,6 +124,28 @@ def c4small(fd, n=(32, 32, 32), t=6):
     return g
 
 
+def feed50(fd, n=(18, 16, 14), t=4):
+    """a SoftArbitraryPointSource with series impedance (gaussian-pulse voltage; Z = 0.5
+    in simulation units -- the explicit one-step feedback is unstable from Z ~ 1 on this grid) with its paired
+    CurrentDetector, a second CurrentDetector block away from it, an absorbing slab and a BlockDetector."""
+    g = fd.Grid(shape=n, grid_spacing=1e-3)
+    g[0:t, :, :] = fd.PML()
+    g[-t:, :, :] = fd.PML()
+    g[:, 0:t, :] = fd.PML()
+    g[:, -t:, :] = fd.PML()
+    g[:, :, 0:t] = fd.PML()
+    g[:, :, -t:] = fd.PML()
+    steps = np.arange(60)
+    wave = np.exp(-((steps - 20.0) ** 2) / (2 * 6.0 ** 2)) * 1e-3
+    # (the reference does not re-export this class at package level: fdtd/__init__.py:6-14)
+    saps = getattr(fd, "SoftArbitraryPointSource", None) or fd.sources.SoftArbitraryPointSource
+    g[9, 8, 7] = saps(wave, impedance=0.5)
+    g[6:7, 9:10, 5:6] = fd.CurrentDetector(name="probe")
+    g[11:13, 5:11, 5:9] = fd.AbsorbingObject(permittivity=2.0, conductivity=50.0)
+    g[9:10, 8:9, 8:9] = fd.BlockDetector(name="block")
+    return g
+
+
 # name -> (builder, steps)
 SCENES = {
     "quickstart2d": (quickstart2d, 300),
@@ -133,6 +155,7 @@ SCENES = {
     "vacuum_aniso": (vacuum_aniso, 40),
     "slab2d_xz": (slab2d_xz, 120),
     "c4small": (c4small, 50),
+    "feed50": (feed50, 80),
 }
 
 
@@ -151,8 +174,15 @@ def dump(grid):
     """final fields and every detector trace as numpy arrays."""
     out = {"E": _np(grid.E), "H": _np(grid.H)}
     for n, det in enumerate(grid.detectors):
-        out[f"det{n}_E"] = _np(det.E)
-        out[f"det{n}_H"] = _np(det.H)
+        if hasattr(det, "I"):
+            out[f"det{n}_I"] = _np(det.I)
+        else:
+            out[f"det{n}_E"] = _np(det.E)
+            out[f"det{n}_H"] = _np(det.H)
+    for n, src in enumerate(grid.sources):
+        if hasattr(src, "source_voltage"):
+            out[f"src{n}_Vin"] = np.asarray(_np(src.input_voltage), dtype=np.float64).reshape(-1)
+            out[f"src{n}_Vout"] = np.asarray(_np(src.source_voltage), dtype=np.float64).reshape(-1)
     return out
 
 

@@ -47,7 +47,7 @@ def compare(got, want, tol, bitwise):
         assert got[k].shape == want[k].shape, k
         err = scenes.rel_l2(got[k], want[k])
         assert err <= tol, f"{k}: rel-L2 {err:.3e} > {tol}"
-        if bitwise:
+        if bitwise and not k.startswith("src"):      # recorded source voltages: host float64 in the reference
             assert np.array_equal(got[k], want[k]), f"{k}: not bit-identical (rel-L2 {err:.3e})"
 
 
