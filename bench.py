@@ -307,7 +307,7 @@ def main():
     if os.path.exists(tpath):
         try:
             t = json.load(open(tpath))
-            if t.get("size") == n and t.get("dtype") == args.dtype and world == 1:
+            if list(t.get("size", [])) == list(n) and t.get("dtype") == args.dtype and world == 1:
                 traffic = t.get("dram_bytes_per_launch")
         except Exception:
             pass
