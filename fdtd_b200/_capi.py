@@ -6,7 +6,7 @@ loudly when it is missing: there is no CPU or PyTorch fallback for the hot path.
 import ctypes as C
 import os
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_SLABS, MAX_POST, MAX_SOURCES, MAX_DETECTORS, FUSED_MAX = 6, 16, 64, 64, 6
 F32, F64 = 0, 1
 CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT = 1, 2, 4, 8
@@ -71,6 +71,13 @@ EXPORTS = {
     "fdtd_update_E": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),
     "fdtd_update_H": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),
     "fdtd_run": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, C.c_int64, _vp]),
+    "fdtd_ipc_export": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64)]),
+    "fdtd_ipc_import": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
+    "fdtd_halfstep_push": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                     _vp, _vp, _vp]),
+    "fdtd_halo_push": (C.c_int, [C.POINTER(Desc), C.c_int32, _vp, _vp, _vp]),
+    "fdtd_halo_signal": (C.c_int, [_vp, C.c_int64, _vp]),
+    "fdtd_halo_wait": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfdtd_b200.so")

@@ -252,7 +252,7 @@ fdtd::SlabK<T> slab_k(const fdtd_slab& S) {
 // index and ring slot are then graph_step + the bases in d->dyn
 template <typename T, bool IS_E>
 int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
-                    int64_t graph_step = -1) {
+                    int64_t graph_step = -1, void* push_y = nullptr, void* push_z = nullptr) {
   if (x_begin < 0 || x_end > d->Nx || x_begin > x_end) return fail(FDTD_ERR_ARG, "plane range [%d,%d)", x_begin, x_end);
   if (x_begin == x_end) return FDTD_OK;
   Geometry g = geometry(d->dtype, d->Ny, d->Nz);
@@ -327,11 +327,23 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
   dim3 block(g.lanes_z * g.rows);
   if (grid.y > 65535u || grid.z > 65535u) return fail(FDTD_ERR_UNSUPPORTED, "grid too large for one launch");
   const bool has_post = (P.n_src + P.n_det) > 0;
+  const bool has_push = push_y != nullptr && push_z != nullptr;
+  if (has_push) {
+    P.push_plane = IS_E ? 0 : d->Nx - 1;
+    if (P.push_plane < x_begin || P.push_plane >= x_end)
+      return fail(FDTD_ERR_ARG, "halo push: the launch does not cover the boundary plane");
+    P.push_y = (T*)push_y;
+    P.push_z = (T*)push_z;
+  }
 #define FDTD_LAUNCH_HALFSTEP(V)                                                                    \
-  if (has_post) {                                                                                  \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true>), grid, block, stream, P);               \
+  if (has_push && has_post) {                                                                      \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, true>), grid, block, stream, P);         \
+  } else if (has_push) {                                                                           \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, true>), grid, block, stream, P);        \
+  } else if (has_post) {                                                                           \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, false>), grid, block, stream, P);        \
   } else {                                                                                         \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false>), grid, block, stream, P);              \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, false>), grid, block, stream, P);       \
   }
   switch (g.vec) {
     case 4:
@@ -530,6 +542,96 @@ int fdtd_update_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
   if (rc) return rc;
   return update_H_nocheck(d, q, slot, stream);
 }
+
+// ---- direct peer-to-peer halo exchange (x-sharded grids, one process per GPU) ----------------------------
+int fdtd_halfstep_push(const fdtd_desc* d, int32_t field, int32_t x_begin, int32_t x_end, int64_t q, int64_t slot,
+                       void* peer_ghost_y, void* peer_ghost_z, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!peer_ghost_y || !peer_ghost_z) return fail(FDTD_ERR_ARG, "null peer ghost pointer");
+  if (field == 0)
+    return d->dtype == FDTD_F32
+               ? launch_halfstep<float, true>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z)
+               : launch_halfstep<double, true>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z);
+  return d->dtype == FDTD_F32
+             ? launch_halfstep<float, false>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z)
+             : launch_halfstep<double, false>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z);
+}
+
+int fdtd_halo_push(const fdtd_desc* d, int32_t field, void* peer_ghost_y, void* peer_ghost_z, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!peer_ghost_y || !peer_ghost_z) return fail(FDTD_ERR_ARG, "null peer ghost pointer");
+  const int64_t plane_off = field == 0 ? 0 : (int64_t)(d->Nx - 1) * d->plane;
+  void* const* F = field == 0 ? d->E : d->H;
+  if (d->dtype == FDTD_F32) {
+    FDTD_LAUNCH((fdtd::halo_push_kernel<float>), dim3(blocks_for(d->plane)), dim3(256), stream,
+                (const float*)F[1] + plane_off, (const float*)F[2] + plane_off, (float*)peer_ghost_y,
+                (float*)peer_ghost_z, (i64)d->plane);
+  } else {
+    FDTD_LAUNCH((fdtd::halo_push_kernel<double>), dim3(blocks_for(d->plane)), dim3(256), stream,
+                (const double*)F[1] + plane_off, (const double*)F[2] + plane_off, (double*)peer_ghost_y,
+                (double*)peer_ghost_z, (i64)d->plane);
+  }
+  return check_launch("halo_push");
+}
+
+#ifdef FDTD_EMU
+int fdtd_halo_signal(int64_t*, int64_t, void*) { return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA"); }
+int fdtd_halo_wait(const int64_t*, int64_t, int32_t*, void*) { return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA"); }
+int fdtd_ipc_export(const void*, void*, int64_t*) { return fail(FDTD_ERR_UNSUPPORTED, "CUDA IPC needs CUDA"); }
+int fdtd_ipc_import(const void*, int64_t, void**) { return fail(FDTD_ERR_UNSUPPORTED, "CUDA IPC needs CUDA"); }
+#else
+int fdtd_halo_signal(int64_t* peer_flag, int64_t value, void* stream) {
+  if (!peer_flag) return fail(FDTD_ERR_ARG, "null flag");
+  FDTD_LAUNCH((fdtd::halo_signal_kernel), dim3(1), dim3(32), stream, (i64*)peer_flag, (i64)value);
+  return check_launch("halo_signal");
+}
+
+int fdtd_halo_wait(const int64_t* flag, int64_t value, int32_t* error, void* stream) {
+  if (!flag || !error) return fail(FDTD_ERR_ARG, "null flag");
+  FDTD_LAUNCH((fdtd::halo_wait_kernel), dim3(1), dim3(32), stream, (const i64*)flag, (i64)value, (int*)error);
+  return check_launch("halo_wait");
+}
+
+int fdtd_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset) {
+  if (!dev_ptr || !handle64 || !offset) return fail(FDTD_ERR_ARG, "fdtd_ipc_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  // the handle names the whole cudaMalloc allocation: find its base through the driver API (resolved at run
+  // time so that the library loads without libcuda in CPU-only containers)
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  static range_fn get_range = nullptr;
+  if (!get_range) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return fail(FDTD_ERR_CUDA, "cuMemGetAddressRange not available");
+    get_range = (range_fn)fn;
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (get_range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0)
+    return fail(FDTD_ERR_CUDA, "cuMemGetAddressRange failed");
+  cudaError_t e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, (void*)(uintptr_t)base);
+  if (e != cudaSuccess) return fail(FDTD_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  *offset = (int64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+  return FDTD_OK;
+}
+
+int fdtd_ipc_import(const void* handle64, int64_t offset, void** dev_ptr) {
+  if (!handle64 || !dev_ptr) return fail(FDTD_ERR_ARG, "fdtd_ipc_import: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* base = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(FDTD_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  }
+  *dev_ptr = (char*)base + offset;
+  return FDTD_OK;
+}
+#endif
 
 #ifndef FDTD_EMU
 // ---- CUDA-graph replay of step chunks (small, launch-bound grids) ---------------------------------

@@ -161,6 +161,11 @@ struct HalfStepParams {
   SlabK<T> slabs[6];
   // sources and detectors folded into this pass (only when nothing has to run between the field
   // update and them, i.e. no periodic copy / late PML correction); registration order
+  // boundary plane pushed straight into the neighbour slab's ghost plane over NVLink (peer pointers
+  // from CUDA IPC): components y and z of plane `push_plane`, written by the same threads that compute them
+  int push_plane;
+  T* push_y;
+  T* push_z;
   int n_src, n_det;
   const i64* dyn;  // optional device int64[2] {waveform index base, ring slot base} (CUDA-graph replays)
   SrcK<T> src[FDTD_FUSED_MAX];
@@ -324,7 +329,9 @@ FDTD_SLAB_FN void slab_pass(const HalfStepParams<T>& P, CellState<T, VEC>& C, in
 
 // HAS_POST: sources / detectors folded into this pass (small grids, where a separate launch per source
 // and detector would dominate the step); compiled out otherwise
-template <typename T, int VEC, bool IS_E, bool HAS_POST>
+// HAS_PUSH: the launch covers the slab's boundary plane and stores it into the neighbour's ghost plane as well
+// (compute + halo transfer in one kernel; fdtd_halo_signal publishes it afterwards)
+template <typename T, int VEC, bool IS_E, bool HAS_POST, bool HAS_PUSH>
 __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_kernel(const FDTD_GRID_CONSTANT HalfStepParams<T> P) {
   const int tid = threadIdx.x;
   const int lane = tid & (P.lanes_z - 1);
@@ -555,6 +562,10 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     stv_stream<T, VEC>(Fx + off, f0);
     stv_stream<T, VEC>(Fy + off, f1);
     stv_stream<T, VEC>(Fz + off, f2);
+    if (HAS_PUSH && i == P.push_plane) {
+      stv<T, VEC>(P.push_y + p, f1);
+      stv<T, VEC>(P.push_z + p, f2);
+    }
 
     if (IS_E) {
       carry_y = gy;
@@ -720,6 +731,46 @@ __global__ void source_feedback_kernel(T* F, i64 cell, const T* wave, const T* w
     if (record) record[slot] = vout;
   }
 }
+
+// ---- direct peer-to-peer halo (one process per GPU, peer pointers from CUDA IPC) --------------------------
+
+// unfused push: copy the boundary plane of the y and z components into the neighbour's ghost planes
+template <typename T>
+__global__ void halo_push_kernel(const T* src_y, const T* src_z, T* dst_y, T* dst_z, i64 n) {
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (i64)gridDim.x * blockDim.x) {
+    dst_y[t] = src_y[t];
+    dst_z[t] = src_z[t];
+  }
+}
+
+#ifndef FDTD_EMU
+// publish: everything this stream wrote before (kernel boundaries order it) is visible system-wide, then the
+// neighbour's flag takes the new half-step count
+__global__ void halo_signal_kernel(i64* peer_flag, i64 value) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(value) : "memory");
+  }
+}
+
+// consume: spin until the local flag (written by the neighbour) reaches `value`; gives up after ~2^32 cycles
+// and raises *error instead of hanging the GPU if the neighbour died
+__global__ void halo_wait_kernel(const i64* flag, i64 value, int* error) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long t0 = clock64();
+    i64 v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+      if (v >= value) break;
+      if (clock64() - t0 > (1LL << 32)) {
+        *error = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+}
+#endif
 
 // graph replays: the per-launch bases of the waveform index and the ring slot
 __global__ void set_dyn_kernel(i64* dyn, i64 wave_base, i64 slot_base) {

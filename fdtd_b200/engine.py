@@ -20,7 +20,7 @@ import torch
 from . import _capi
 from .backend import backend as bd
 from ._hostmath import scalar_in_dtype
-from .sharding import HaloExchange
+from .sharding import HaloExchange, P2PHalo
 
 RING_BYTES = 64 << 20          # detector ring budget per grid
 WAVE_TABLE_MIN = 1024          # look-ahead of the host waveform tables (steps)
@@ -40,6 +40,7 @@ class Engine:
         self._keep = []            # tensors referenced by raw pointers in the descriptor
         self._wave = None          # (q0, len)
         self._halo = None
+        self._p2p = None
         self._pending = {"E": None, "H": None}
         self.bake()
 
@@ -195,9 +196,97 @@ class Engine:
         _capi.check(self.lib, self.lib.fdtd_validate(C.byref(d)))
 
         if part.sharded:
-            self._halo = HaloExchange(part, g._E, g._H)
-            self._halo.refresh()
+            self._setup_halo()
         g._baked_counts = g._registration_count
+
+    def _setup_halo(self):
+        """x-sharded grids: direct peer-to-peer ghost-plane stores (default on CUDA), or NCCL / gloo send-recv
+        (FDTD_B200_HALO=nccl, CPU tests, or when CUDA IPC is not available between the ranks)."""
+        import os
+        g, d = self.grid, self.desc
+        want = os.environ.get("FDTD_B200_HALO", "p2p")
+        if self._p2p is None and g._E.is_cuda and want == "p2p":
+            try:
+                self._p2p = P2PHalo(g._part, g._E, g._H, self.lib)
+            except Exception as exc:                          # IPC refused (e.g. no peer access): NCCL path
+                import warnings
+                warnings.warn(f"fdtd_b200: peer-to-peer halo unavailable ({exc}); using NCCL send/recv")
+                self._p2p = False
+        self._halo = self._p2p if self._p2p else HaloExchange(g._part, g._E, g._H)
+        # may the boundary plane be pushed by the half-step kernel itself?  Only if nothing modifies that
+        # plane afterwards: no periodic copy / late PML correction, no unfused source on the plane
+        n = d.Nx
+        fused = bool(self.lib.fdtd_post_is_fused(C.byref(d)))
+        self._push_fused = {}
+        for field, plane in (("E", 0), ("H", n - 1)):
+            ok = fused or d.n_post == 0
+            if ok and not fused:
+                for k in range(d.n_sources):
+                    s = d.sources[k]
+                    if s.field != (0 if field == "E" else 1):
+                        continue
+                    box = s.bbox if s.kind == _capi.SRC_POINTS else s.box
+                    empty = (s.kind == _capi.SRC_POINTS and s.n == 0) or box[0] >= box[1]
+                    if not empty and box[0] <= plane < box[1]:
+                        ok = False
+            self._push_fused[field] = ok
+        if self._p2p:
+            self._p2p_refresh()
+        else:
+            self._halo.refresh()
+
+    def _p2p_refresh(self):
+        """push both boundary planes and wait for the neighbours' (collective; after the user wrote E / H)."""
+        lib, d, h = self.lib, self.desc, self._p2p
+        st = self._stream()
+        for field, idx in (("E", 0), ("H", 1)):
+            if field in h.dst:
+                gy, gz, flag = h.dst[field]
+                _capi.check(lib, lib.fdtd_halo_push(C.byref(d), idx, C.c_void_p(gy), C.c_void_p(gz), st))
+                _capi.check(lib, lib.fdtd_halo_signal(C.c_void_p(flag), h.count[field] + 1, st))
+            h.count[field] += 1
+        for field, idx, src_exists in (("E", 0, h.part.rank < h.part.world - 1), ("H", 1, h.part.rank > 0)):
+            if src_exists:
+                _capi.check(lib, lib.fdtd_halo_wait(C.c_void_p(h.flags.data_ptr() + 8 * idx), h.count[field],
+                                                    C.c_void_p(h.err.data_ptr()), st))
+
+    def _p2p_halfstep(self, field, q, slot):
+        """one half-step of an x-sharded slab with peer-to-peer ghost planes (see P2PHalo)."""
+        lib, d, h = self.lib, self.desc, self._p2p
+        n = d.Nx
+        fidx = 0 if field == "E" else 1
+        other = "H" if field == "E" else "E"
+        step = lib.fdtd_e_halfstep if field == "E" else lib.fdtd_h_halfstep
+        post = lib.fdtd_post_E if field == "E" else lib.fdtd_post_H
+        bulk = (1, n) if field == "E" else (0, n - 1)
+        edge = (0, min(1, n)) if field == "E" else (max(n - 1, 0), n)
+        st = self._stream()
+        dev = self.grid._E.device
+        main, side = torch.cuda.current_stream(dev), h.stream
+        sst = C.c_void_p(side.cuda_stream)
+        side.wait_stream(main)
+        _capi.check(lib, step(C.byref(d), bulk[0], bulk[1], q, slot, st))
+        has_nb = field in h.dst                # the neighbour this plane goes to, and the ghost comes from
+        if has_nb:
+            # the ghost this plane needs was pushed by the neighbour after its last `other` half-step
+            _capi.check(lib, lib.fdtd_halo_wait(C.c_void_p(h.flags.data_ptr() + 8 * (1 - fidx)), h.count[other],
+                                                C.c_void_p(h.err.data_ptr()), sst))
+        fused = has_nb and self._push_fused[field]
+        if fused:
+            gy, gz, flag = h.dst[field]
+            _capi.check(lib, lib.fdtd_halfstep_push(C.byref(d), fidx, edge[0], edge[1], q, slot,
+                                                    C.c_void_p(gy), C.c_void_p(gz), sst))
+            _capi.check(lib, lib.fdtd_halo_signal(C.c_void_p(flag), h.count[field] + 1, sst))
+        else:
+            _capi.check(lib, step(C.byref(d), edge[0], edge[1], q, slot, sst))
+        main.wait_stream(side)
+        _capi.check(lib, post(C.byref(d), q, slot, st))
+        if has_nb and not fused:
+            gy, gz, flag = h.dst[field]
+            side.wait_stream(main)
+            _capi.check(lib, lib.fdtd_halo_push(C.byref(d), fidx, C.c_void_p(gy), C.c_void_p(gz), sst))
+            _capi.check(lib, lib.fdtd_halo_signal(C.c_void_p(flag), h.count[field] + 1, sst))
+        h.count[field] += 1
 
     def _classify(self, ie_eff, ie_grid_if_objects, absorb, imu, ty, tz):
         """per-(plane, y-tile, z-tile) class byte, FDTD_CLS_* (include/fdtd_b200.h)."""
@@ -295,6 +384,8 @@ class Engine:
         for E, the last plane for H) runs on the halo stream right behind the exchange that delivers the
         ghost, concurrently with the bulk on the main stream; the exchange of the freshly updated
         boundary plane is then started and overlaps the bulk of the NEXT half-step."""
+        if self._p2p:
+            return self._p2p_halfstep(field, q, slot)
         lib, d, halo = self.lib, self.desc, self._halo
         n = d.Nx
         step = lib.fdtd_e_halfstep if field == "E" else lib.fdtd_h_halfstep
@@ -373,8 +464,11 @@ class Engine:
     def quiesce(self):
         """make every enqueued halo exchange visible to the current stream (before field reads)."""
         if self._halo is not None:
-            for f in ("E", "H"):
-                self._halo.wait(self._pending[f])
-                self._pending[f] = None
+            if not self._p2p:
+                for f in ("E", "H"):
+                    self._halo.wait(self._pending[f])
+                    self._pending[f] = None
             if self._halo.cuda:
                 torch.cuda.current_stream(self.grid._E.device).wait_stream(self._halo.stream)
+            if self._p2p:
+                self._p2p.check()

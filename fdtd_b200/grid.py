@@ -12,12 +12,18 @@ Differences a user can see, all deliberate:
     (one relative cost per x-plane) balances the slabs when some planes are dearer, e.g. inside x-PMLs.
 """
 import gc
+import os
 
 import torch
 
 from . import constants as const
 from .backend import backend as bd
 from .sharding import Partition, all_gather_slabs
+
+
+def _env_flag(name):
+    v = os.environ.get(name)
+    return None if v in (None, "") else v not in ("0", "false", "False")
 
 
 def curl_E(E):
@@ -81,8 +87,9 @@ class Grid:
         self._engine = None
         self._ring_fill = {"E": 0, "H": 0}
         self._x_chunk = 0
-        self._use_graphs = None      # None: automatic (small grids), True / False: force
-        self._fuse_post = None       # None: automatic (small grids), True / False: force
+        # None: automatic (launch-bound small grids), True / False: force.  FDTD_B200_GRAPHS / FDTD_B200_FUSE = 0|1
+        self._use_graphs = _env_flag("FDTD_B200_GRAPHS")
+        self._fuse_post = _env_flag("FDTD_B200_FUSE")
 
     # ----------------------------------------------------------------------------- materials
     def _material(self, value, what):
@@ -152,7 +159,10 @@ class Grid:
             value = value[self._part.x0:self._part.x1]
         view.copy_(value)
         if self._engine is not None and self._engine._halo is not None:
-            self._engine._halo.refresh()
+            if self._engine._p2p:
+                self._engine._p2p_refresh()
+            else:
+                self._engine._halo.refresh()
 
     @property
     def E(self):

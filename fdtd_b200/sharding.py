@@ -137,6 +137,70 @@ class HaloExchange:
         self.wait(self.start("H"))
 
 
+class P2PHalo:
+    """Halo exchange by direct stores into the neighbour slab's ghost planes over NVLink.
+
+    One process per GPU: every rank exports its E / H storage and a two-word flag array with CUDA IPC
+    (include/fdtd_b200.h, fdtd_ipc_export / fdtd_ipc_import) and maps its neighbours'.  The half-step kernel
+    that computes a slab's boundary plane stores it into the neighbour's ghost plane as well
+    (fdtd_halfstep_push: compute + transfer in one kernel); a one-thread kernel then publishes the new
+    half-step count in the neighbour's flag (release, system scope) and the neighbour's stream spins on its
+    local flag (acquire) before the kernel that consumes the ghost.  No NCCL call, no host synchronisation
+    between the processes; counts are monotonic, so ranks may run ahead of each other by at most one
+    half-step (the dependency chain of the flags is the back-pressure)."""
+
+    def __init__(self, part, E, H, lib):
+        import ctypes as C
+        from . import _capi
+        self.part, self.E, self.H, self.lib = part, E, H, lib
+        self.cuda = True
+        dev = E.device
+        self.stream = torch.cuda.Stream(device=dev)
+        self.flags = torch.zeros(2, dtype=torch.int64, device=dev)     # [0]: E pushes received, [1]: H pushes
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.count = {"E": 0, "H": 0}                                   # pushes sent == pushes expected
+        torch.cuda.synchronize(dev)
+
+        def export(t):
+            h = (C.c_char * 64)()
+            off = C.c_int64()
+            _capi.check(lib, lib.fdtd_ipc_export(C.c_void_p(t.data_ptr()), C.cast(h, C.c_void_p), C.byref(off)))
+            return bytes(h.raw), off.value
+
+        mine = {"E": export(E), "H": export(H), "flags": export(self.flags), "nx": part.nx}
+        everyone = [None] * part.world
+        dist.all_gather_object(everyone, mine)
+
+        def open_(rec):
+            h = (C.c_char * 64).from_buffer_copy(rec[0])
+            ptr = C.c_void_p()
+            _capi.check(lib, lib.fdtd_ipc_import(C.cast(h, C.c_void_p), rec[1], C.byref(ptr)))
+            return ptr.value
+
+        w = E.element_size()
+        plane = E.shape[2] * E.shape[3]
+        self.dst = {}      # field -> (peer ghost y, peer ghost z, peer flag address)
+        if part.rank > 0:                                   # E plane 0 -> left neighbour's high ghost
+            rec = everyone[part.rank - 1]
+            base, nxl = open_(rec["E"]), rec["nx"]
+            ghost = lambda c: base + ((c * (nxl + 2) + nxl + 1) * plane) * w
+            self.dst["E"] = (ghost(1), ghost(2), open_(rec["flags"]))
+        if part.rank < part.world - 1:                      # H last plane -> right neighbour's low ghost
+            rec = everyone[part.rank + 1]
+            base, nxl = open_(rec["H"]), rec["nx"]
+            ghost = lambda c: base + (c * (nxl + 2) * plane) * w
+            self.dst["H"] = (ghost(1), ghost(2), open_(rec["flags"]) + 8)
+        dist.barrier()
+
+    def neighbour(self, field):
+        """the rank this field's boundary plane goes to -- and the other field's ghost comes from."""
+        return field in self.dst
+
+    def check(self):
+        if int(self.err.item()) != 0:
+            raise RuntimeError("fdtd_b200: peer-to-peer halo wait timed out (a neighbour rank stopped stepping)")
+
+
 def all_gather_slabs(part, local, dim):
     """concatenate per-rank slabs of differing thickness along `dim` (convenience accessor)."""
     sizes = [part.bounds(r)[1] - part.bounds(r)[0] for r in range(part.world)]

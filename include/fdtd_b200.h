@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 7
+#define FDTD_ABI_VERSION 8
 
 #define FDTD_F32 0
 #define FDTD_F64 1
@@ -211,6 +211,29 @@ int fdtd_update_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
 /* Grid.run (fdtd/grid.py:250-265): nsteps full steps starting at step index q0; detector
  * samples of step q0+s go to ring slot slot0+s */
 int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void* stream);
+
+/* --- direct peer-to-peer halo exchange (x-sharded grids, one process per GPU) -------------------------
+ * No reference counterpart (the reference is single-device).  Each rank exports its field storage and a
+ * two-word flag array with CUDA IPC; neighbours import them and get peer pointers that the kernels below
+ * store through over NVLink.  Flags carry monotonically increasing half-step counts, so no host-side
+ * ordering between the processes is needed. */
+/* IPC handle (64 bytes) of the allocation holding dev_ptr and dev_ptr's offset inside it */
+int fdtd_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset);
+/* map a neighbour's allocation (lazy peer access) and return the pointer at `offset` */
+int fdtd_ipc_import(const void* handle64, int64_t offset, void** dev_ptr);
+/* fdtd_e_halfstep / fdtd_h_halfstep (field 0 / 1) on a plane range that contains the slab's boundary plane
+ * (local plane 0 for E, Nx-1 for H): the threads that compute that plane also store its y and z components
+ * into the neighbour's ghost planes -- compute and halo transfer in one kernel */
+int fdtd_halfstep_push(const fdtd_desc* d, int32_t field, int32_t x_begin, int32_t x_end, int64_t q, int64_t slot,
+                       void* peer_ghost_y, void* peer_ghost_z, void* stream);
+/* the same transfer as a separate copy kernel, for steps where something modifies the boundary plane after
+ * the half-step kernel (periodic copies, sources on that plane) */
+int fdtd_halo_push(const fdtd_desc* d, int32_t field, void* peer_ghost_y, void* peer_ghost_z, void* stream);
+/* publish `value` in the neighbour's flag after everything enqueued before on `stream` (release, system scope) */
+int fdtd_halo_signal(int64_t* peer_flag, int64_t value, void* stream);
+/* make `stream` wait until the local flag reaches `value` (acquire, system scope); after ~2 s of spinning it
+ * gives up and sets *error (device int) instead of hanging */
+int fdtd_halo_wait(const int64_t* flag, int64_t value, int32_t* error, void* stream);
 
 #ifdef __cplusplus
 }

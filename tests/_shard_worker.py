@@ -39,6 +39,10 @@ def main():
     res = scenes.dump(g)                   # grid.E gathers the slabs, detectors gather their samples
     if rank == 0:
         np.savez(out, **res)
+    if backend != "gloo":
+        if os.environ.get("FDTD_B200_HALO", "p2p") == "p2p":
+            assert g._engine._p2p, "peer-to-peer halo was requested but not set up"
+        torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
 

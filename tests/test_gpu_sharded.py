@@ -11,14 +11,18 @@ from test_sharded_gloo import launch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("scene,dtype", [("pml3d", "float64"), ("objects3d", "float32"), ("c4small", "float32")])
-def test_nccl_sharded_equals_single(tmp_path, scene, dtype):
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+@pytest.mark.parametrize("scene,dtype", [("pml3d", "float64"), ("objects3d", "float32"), ("c4small", "float32"),
+                                         ("periodic3d", "float64")])
+def test_sharded_equals_single(tmp_path, scene, dtype, halo):
+    """halo = p2p: ghost planes stored straight into the neighbour's memory (CUDA IPC peer pointers + flags);
+    halo = nccl: send/recv.  Both must reproduce the single-GPU run bit for bit."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world = min(4, torch.cuda.device_count())
     steps = 30
     out = str(tmp_path / "sharded.npz")
-    launch(world, "nccl", dtype, scene, steps, out)
+    launch(world, "nccl", dtype, scene, steps, out, FDTD_B200_HALO=halo)
     got = dict(np.load(out))
     import fdtd_b200 as fd
     fd.set_backend("cuda." + dtype)

@@ -23,9 +23,9 @@ def free_port():
         return s.getsockname()[1]
 
 
-def launch(world, backend, dtype, scene, steps, out):
+def launch(world, backend, dtype, scene, steps, out, **extra_env):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), WORLD_SIZE=str(world),
-               OMP_NUM_THREADS="1")
+               OMP_NUM_THREADS="1", **extra_env)
     procs = []
     for r in range(world):
         e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
