@@ -95,20 +95,24 @@ Geometry geometry(int dtype, int Ny, int Nz) {
   return g;
 }
 
-// planes marched per block: enough blocks for ~32 waves of 3 blocks x 148 SMs (tail effect),
-// at most 32 planes (measured on B200: profiles/tune_r1.md)
+// planes marched per block.  Two costs pull in opposite directions (fitted to profiles/r1_tune3.txt and
+// r1_tune4_slabs.txt on B200): every chunk re-reads two carried planes (~0.32/chunk of a launch) and the
+// last, partially filled wave of blocks runs the memory system below capacity (~1.2/waves, 444 resident
+// blocks).  Pick the power of two in [4, 32] that minimises their sum.
 int default_x_chunk(const Geometry& g, int nx, int Ny, int Nz) {
-  long long tiles = (long long)((Ny + g.tile_y - 1) / g.tile_y) * ((Nz + g.tile_z - 1) / g.tile_z);
-  long long c = (long long)nx * tiles / (148LL * 3 * 32);
-  int chunk = 4;
-  while (chunk * 2 <= c && chunk < 32) chunk *= 2;
-  return chunk;
+  const double tiles = (double)((Ny + g.tile_y - 1) / g.tile_y) * ((Nz + g.tile_z - 1) / g.tile_z);
+  int best = 4;
+  double best_cost = 1e30;
+  for (int chunk = 4; chunk <= 32; chunk *= 2) {
+    const double waves = ((nx + chunk - 1) / chunk) * tiles / (148.0 * 3);
+    const double cost = 0.32 / chunk + 1.2 / (waves > 0.25 ? waves : 0.25);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = chunk;
+    }
+  }
+  return best;
 }
-
-// z slabs: psi rows start at z = lo rounded down to a multiple of 4 and are padded to a multiple of 4,
-// so that a thread's VEC cells are one aligned vector of its psi row
-int z_slab_lo(const fdtd_slab& S) { return S.lo & ~3; }
-int z_slab_row(const fdtd_slab& S) { return ((S.lo + S.thickness - z_slab_lo(S)) + 3) & ~3; }
 
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 

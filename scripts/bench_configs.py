@@ -118,11 +118,41 @@ def c5slab():
     return g, 100, 4, words
 
 
-CONFIGS = {"c1": c1, "c2": c2, "c3": c3, "c3b": lambda: c3(True), "c4": c4, "c5slab": c5slab}
+def c5(nx=2048):
+    """configs[4]: 2048 x 1024 x 1024 float32 waveguide, PML on x, periodic y and z, GRIN medium over the middle
+    half, PlaneSource; x-sharded over the ranks of the job (torchrun).  `c5weak` gives every rank 256 planes."""
+    fd.set_backend("cuda.float32")
+    n = 1024
+    g = fd.Grid(shape=(nx, n, n), grid_spacing=SPACING)
+    g[0:10, :, :] = fd.PML()
+    g[-10:, :, :] = fd.PML()
+    g[:, 0, :] = fd.PeriodicBoundary()
+    g[:, :, 0] = fd.PeriodicBoundary()
+    ramp = (1.0 + 1.25 * np.arange(n) / (n - 1.0)).reshape(1, n, 1)
+    g[nx // 4:3 * nx // 4, :, :] = fd.Object(permittivity=ramp)
+    g[100, :, :] = fd.PlaneSource(period=20, polarization="z")
+    g[20:nx - 20, 512, 512] = fd.LineDetector()
+    words = 18 + 8 * 20 / nx + 3 * 0.5
+    return g, 100, 4, words
+
+
+def c5weak():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return c5(256 * world)
+
+
+CONFIGS = {"c1": c1, "c2": c2, "c3": c3, "c3b": lambda: c3(True), "c4": c4, "c5slab": c5slab, "c5": c5,
+           "c5weak": c5weak}
 
 
 def main():
-    names = sys.argv[1:] or list(CONFIGS)
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    names = sys.argv[1:] or ["c1", "c2", "c3", "c4", "c5slab"]
     peak, src = measured_peak()
     for name in names:
         t0 = time.perf_counter()
@@ -132,13 +162,19 @@ def main():
             _ = det.E
         torch.cuda.synchronize()
         setup_s = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         g.run(steps, progress_bar=False)
         traces = [(det.E, det.H) for det in g.detectors]
         b.record()
         torch.cuda.synchronize()
-        ms = a.elapsed_time(b)
+        ms = torch.tensor([a.elapsed_time(b)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
         cells = g.Nx * g.Ny * g.Nz
         w = 4 if g._dtype is torch.float32 else 8
         rec = {"config": name, "grid": [g.Nx, g.Ny, g.Nz], "dtype": str(g._dtype).split(".")[-1], "steps": steps,
@@ -146,15 +182,21 @@ def main():
                "steps_per_s": steps / (ms * 1e-3), "setup_s": round(setup_s, 2),
                "fused_post": bool(g._engine.lib.fdtd_post_is_fused(g._engine.desc)),
                "graphs": bool(g._engine.desc.use_graphs), "detector_samples": len(traces[0][0]) if traces else 0,
-               "E_absmax": float(g.E.abs().max())}
+               "E_absmax": float(g.E_local.abs().max()), "n_gpus": world,
+               "halo": ("p2p" if g._engine._p2p else "nccl") if world > 1 else None}
         if words:
             rec["bytes_per_cell_step"] = w * words
-            rec["hbm_frac_of_measured"] = (w * words * cells * steps / (ms * 1e-3) / 1e9) / peak
-        print(json.dumps(rec), flush=True)
+            rec["hbm_frac_of_measured"] = (w * words * cells * steps / (ms * 1e-3) / 1e9) / (peak * world)
+        if rank == 0:
+            print(json.dumps(rec), flush=True)
         del g, traces
         import gc
         gc.collect()
         torch.cuda.empty_cache()
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
