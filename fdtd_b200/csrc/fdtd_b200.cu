@@ -114,6 +114,11 @@ int default_x_chunk(const Geometry& g, int nx, int Ny, int Nz) {
   return best;
 }
 
+// z slabs: psi rows start at z = lo rounded down to a multiple of 4 and are padded to a multiple of 4,
+// so that a thread's VEC cells are one aligned vector of its psi row
+int z_slab_lo(const fdtd_slab& S) { return S.lo & ~3; }
+int z_slab_row(const fdtd_slab& S) { return ((S.lo + S.thickness - z_slab_lo(S)) + 3) & ~3; }
+
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 int validate(const fdtd_desc* d) {
