@@ -9,7 +9,7 @@ import os
 ABI_VERSION = 8
 MAX_SLABS, MAX_POST, MAX_SOURCES, MAX_DETECTORS, FUSED_MAX = 6, 16, 64, 64, 6
 F32, F64 = 0, 1
-CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT = 1, 2, 4, 8
+CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT, CLS_ANISO = 1, 2, 4, 8, 16
 POST_PERIODIC, POST_PML_ADD = 0, 1
 SRC_POINTS, SRC_BOX, SRC_FEEDBACK = 0, 1, 2
 DET_FIELD, DET_CURRENT = 0, 1

@@ -22,6 +22,9 @@
   emu::launch(grid, block, [&]() { kern(__VA_ARGS__); })
 template <typename T>
 inline void fdtd_atomic_add(T* p, T v) { *p = *p + v; }
+#include <cmath>
+template <typename T>
+inline bool fdtd_signbit(T v) { return std::signbit(v); }
 #else
 #include <cuda_runtime.h>
 #define FDTD_DEV __device__ __forceinline__
@@ -29,6 +32,8 @@ inline void fdtd_atomic_add(T* p, T v) { *p = *p + v; }
   kern<<<grid, block, 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
 template <typename T>
 __device__ __forceinline__ void fdtd_atomic_add(T* p, T v) { atomicAdd(p, v); }
+template <typename T>
+__device__ __forceinline__ bool fdtd_signbit(T v) { return signbit(v); }
 #endif
 
 #include "yee_kernels.cuh"
@@ -284,6 +289,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
     P.F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
     P.G[c] = (const T*)(IS_E ? d->H[c] : d->E[c]);
     P.bg_c[c] = rounded_product<T>(d->courant, IS_E ? d->bg_inv_eps[c] : d->bg_inv_mu[c]);
+    P.bg_inv[c] = (T)(IS_E ? d->bg_inv_eps[c] : d->bg_inv_mu[c]);
     P.inv[c] = (const T*)(IS_E ? d->inv_eps[c] : d->inv_mu[c]);
     P.inv_grid[c] = IS_E ? (const T*)d->inv_eps_grid[c] : nullptr;
     P.absorb[c] = IS_E ? (const T*)d->absorb[c] : nullptr;

@@ -152,6 +152,7 @@ struct HalfStepParams {
   const T* G[3];  // field being differentiated
   T sc;
   T bg_c[3];      // sc * background inverse material, rounded as the reference rounds it
+  T bg_inv[3];    // background inverse material itself (AnisotropicObject cells round sc*(inv*curl))
   const T* inv[3];       // effective inverse material of the curl term, or null
   const T* inv_grid[3];  // grid's own eps^-1 for the PML correction, or null (= inv)
   const T* absorb[3];    // absorption factor, or null
@@ -497,6 +498,33 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
         fx[e] = fx[e] + (cx[e] * ux) / (T(1) + q0.v[e]);
         fy[e] = fy[e] + (cy[e] * uy) / (T(1) + q1.v[e]);
         fz[e] = fz[e] + (cz[e] * uz) / (T(1) + q2.v[e]);
+      }
+    } else if (IS_E && (cls & FDTD_CLS_ANISO)) {
+      // AnisotropicObject cells: E += sc * (eps^-1 @ curl) -- the product with curl is rounded BEFORE the
+      // scaling by sc (fdtd/objects.py:262-269); they are marked by a NEGATIVE zero in the grid's eps^-1
+      const Pack<T, VEC> mark = ldv<T, VEC>(P.inv_grid[0] + off);
+      Pack<T, VEC> a0, a1, a2;
+      if (cls & P.cls_vary) {
+        a0 = ldv<T, VEC>(P.inv[0] + off);
+        a1 = ldv<T, VEC>(P.inv[1] + off);
+        a2 = ldv<T, VEC>(P.inv[2] + off);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          a0.v[e] = P.bg_inv[0];
+          a1.v[e] = P.bg_inv[1];
+          a2.v[e] = P.bg_inv[2];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T ux = d_zy[e] - d_yz[e];
+        const T uy = d_xz[e] - d_zx[e];
+        const T uz = d_yx[e] - d_xy[e];
+        const bool aniso = (mark.v[e] == T(0)) && fdtd_signbit(mark.v[e]);
+        fx[e] = fx[e] + (aniso ? P.sc * (a0.v[e] * ux) : cx[e] * ux);
+        fy[e] = fy[e] + (aniso ? P.sc * (a1.v[e] * uy) : cy[e] * uy);
+        fz[e] = fz[e] + (aniso ? P.sc * (a2.v[e] * uz) : cz[e] * uz);
       }
     } else {
 #pragma unroll

@@ -314,6 +314,8 @@ class Engine:
                 bits |= tiles((absorb[:, a:b] != 0).any(0)).to(torch.uint8) * _capi.CLS_ABSORB
             if ie_grid_if_objects is not None:
                 bits |= tiles((ie_eff[:, a:b] != ie_grid_if_objects[:, a:b]).any(0)).to(torch.uint8) * _capi.CLS_OBJECT
+                gx = ie_grid_if_objects[0, a:b]
+                bits |= tiles((gx == 0) & torch.signbit(gx)).to(torch.uint8) * _capi.CLS_ANISO
             cls[a:b] = bits
         return cls.contiguous()
 

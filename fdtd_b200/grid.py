@@ -317,6 +317,33 @@ class Grid:
             else:
                 raise ValueError(f"The grid already has an attribute with name {thing.name}")
 
+    # ------------------------------------------------ simulation I/O (fdtd/grid.py:407-439, 490-514)
+    def save_simulation(self, sim_name=None):
+        """create `fdtd_output/fdtd_output_<timestamp>[ (sim_name)]` and remember it (fdtd/grid.py:407-439)."""
+        from datetime import datetime
+        os.makedirs("fdtd_output", exist_ok=True)
+        now = datetime.now()
+        full_sim_name = f"{now.year}-{now.month}-{now.day}-{now.hour}-{now.minute}-{now.second}"
+        if sim_name is not None:
+            full_sim_name = full_sim_name + " (" + sim_name + ")"
+        self.folder = os.path.abspath(os.path.join("fdtd_output", "fdtd_output_" + full_sim_name))
+        self.full_sim_name = full_sim_name
+        os.makedirs(self.folder, exist_ok=True)
+        return self.folder
+
+    def save_data(self):
+        """detector readings -> `<folder>/detector_readings.npz`, keys "<name> (E)" / "<name> (H)" per detector
+        as in the reference (fdtd/grid.py:490-514); the device rings are drained first."""
+        import numpy as np
+        if self.folder is None:
+            raise Exception("Save location not initialized. Please read about 'fdtd.Grid.saveSimulation()' or "
+                            "try running 'grid.saveSimulation()'.")
+        dic = {}
+        for detector in self.detectors:
+            for key, values in detector.detector_values().items():
+                dic[f"{detector.name} ({key})"] = np.asarray(values)
+        np.savez(os.path.join(self.folder, "detector_readings"), **dic)
+
     def promote_dtypes_to_complex(self):
         raise NotImplementedError("complex fields are not supported by the CUDA engine")
 

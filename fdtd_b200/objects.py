@@ -65,7 +65,9 @@ class Object:
         self._inv_eps_soa = inv.permute(3, 0, 1, 2).contiguous() # (3, nx_local, Ny, Nz) for the bake
         self._absorb_soa = None
         if self._nx_local > 0:
-            gi[:, lx0:lx1, self.y, self.z] = 0
+            # zero inside the object (fdtd/objects.py:92); a NEGATIVE zero marks AnisotropicObject cells for the
+            # kernel (include/fdtd_b200.h, FDTD_CLS_ANISO) -- numerically it is the same zero everywhere
+            gi[:, lx0:lx1, self.y, self.z] = -0.0 if isinstance(self, AnisotropicObject) else 0.0
 
     def _grid_last_x_plane(self, gi):
         """grid.inverse_permittivity[-1, y, z, 0] -- lives on the last rank when sharded."""

@@ -61,6 +61,8 @@ extern "C" {
 #define FDTD_CLS_VARY_H 2   /* mu^-1 differs from the background: stream inv_mu */
 #define FDTD_CLS_ABSORB 4   /* an AbsorbingObject covers part of the tile: stream absorb */
 #define FDTD_CLS_OBJECT 8   /* an Object covers part of the tile: the PML add needs inv_eps_grid */
+#define FDTD_CLS_ANISO 16   /* an AnisotropicObject covers part of the tile: its cells (inv_eps_grid x-component
+                               == -0.0) round sc*(eps^-1*curl) like the reference's bmm, not (sc*eps^-1)*curl */
 
 /* post-op kinds, executed in registration order after the fused half-step kernel */
 #define FDTD_POST_PERIODIC 0  /* arg = axis: E[0]=E[-1] after E, H[-1]=H[0] after H  (fdtd/boundaries.py:184-219) */

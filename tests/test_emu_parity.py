@@ -6,10 +6,10 @@ same C ABI and the same Python host code as on the GPU, compared with
   * the oracle, on extra scenes that exercise every vector width, odd extents, registration
     orders, overlapping objects, user pokes between half-steps, re-bakes and ring flushes.
 
-float64: rel-L2 <= 1e-12 is the stated bar; the arithmetic order is the reference's, so the
-assertion is the stronger bit-equality wherever the reference's own operation order is kept
-(everything except AnisotropicObject cells, whose bmm rounds sc*(eps^-1*curl) instead of
-(sc*eps^-1)*curl).  float32: bar 1e-5 against the reference's true-float32 run.
+float64: rel-L2 <= 1e-12 is the stated bar; the arithmetic order is the reference's (including
+AnisotropicObject cells, whose bmm rounds sc*(eps^-1*curl) instead of (sc*eps^-1)*curl), so the
+assertion is the stronger bit-equality.  float32: bar 1e-5 against the reference's true-float32
+run, and bit-equality as well.
 """
 import glob
 import os
@@ -22,7 +22,7 @@ from emu.harness import use_emu
 from oracle import yee_oracle as yo
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-NOT_BITWISE = {"objects3d"}        # contains an AnisotropicObject (see module docstring)
+NOT_BITWISE = set()
 
 
 def run_scene(fd, build, steps, **kw):

@@ -195,3 +195,27 @@ def test_str_of_grid(fd, grid):
     for part in ("sources:", "detectors:", "boundaries:", "objects:", "PointSource(period=10", "@ x=0:3, y=:, z=:",
                  "Object(name='obj')", "@ x=4:6, y=4:6, z=4:6"):
         assert part in s, part
+
+
+def test_save_data_npz_layout(fd, grid, tmp_path, monkeypatch):
+    """reference fdtd/grid.py:490-514: one "<name> (E)" and "<name> (H)" array per detector."""
+    monkeypatch.chdir(tmp_path)
+    grid[2:8, 5, 5] = fd.LineDetector(name="det")
+    grid[5, 5, 5] = fd.PointSource(period=10)
+    with pytest.raises(Exception):
+        grid.save_data()
+    folder = grid.save_simulation("unit")
+    grid.run(6, progress_bar=False)
+    grid.save_data()
+    data = np.load(folder + "/detector_readings.npz")
+    assert set(data.files) == {"det (E)", "det (H)"}
+    assert data["det (E)"].shape == (6, 6, 3)
+
+
+def test_zero_step_run_and_empty_detector(fd, grid):
+    grid[3:3, 4, 4] = fd.LineDetector(name="empty")        # zero points
+    grid.run(0, progress_bar=False)
+    assert grid.time_steps_passed == 0 and grid.empty.E == []
+    grid.run(2.5 * grid.time_step, progress_bar=False)      # float seconds truncate to steps (fdtd/grid.py:259-261)
+    assert grid.time_steps_passed == 2
+    assert np.array(grid.empty.E).shape == (2, 0, 3)
