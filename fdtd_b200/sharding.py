@@ -167,30 +167,46 @@ class P2PHalo:
             _capi.check(lib, lib.fdtd_ipc_export(C.c_void_p(t.data_ptr()), C.cast(h, C.c_void_p), C.byref(off)))
             return bytes(h.raw), off.value
 
-        mine = {"E": export(E), "H": export(H), "flags": export(self.flags), "nx": part.nx}
-        everyone = [None] * part.world
-        dist.all_gather_object(everyone, mine)
+        mapped = {}        # IPC handle -> mapped base: tensors of one allocation are mapped once
 
         def open_(rec):
-            h = (C.c_char * 64).from_buffer_copy(rec[0])
-            ptr = C.c_void_p()
-            _capi.check(lib, lib.fdtd_ipc_import(C.cast(h, C.c_void_p), rec[1], C.byref(ptr)))
-            return ptr.value
+            if rec[0] not in mapped:
+                h = (C.c_char * 64).from_buffer_copy(rec[0])
+                ptr = C.c_void_p()
+                _capi.check(lib, lib.fdtd_ipc_import(C.cast(h, C.c_void_p), 0, C.byref(ptr)))
+                mapped[rec[0]] = ptr.value
+            return mapped[rec[0]] + rec[1]
 
+        # every step below is collective: a rank that cannot export or import must not leave the others
+        # waiting, and either ALL ranks use peer-to-peer ghosts or none does
+        try:
+            mine = {"E": export(E), "H": export(H), "flags": export(self.flags), "nx": part.nx}
+        except Exception as exc:
+            mine = {"error": str(exc)}
+        everyone = [None] * part.world
+        dist.all_gather_object(everyone, mine)
+        failure = next((r["error"] for r in everyone if "error" in r), None)
         w = E.element_size()
         plane = E.shape[2] * E.shape[3]
         self.dst = {}      # field -> (peer ghost y, peer ghost z, peer flag address)
-        if part.rank > 0:                                   # E plane 0 -> left neighbour's high ghost
-            rec = everyone[part.rank - 1]
-            base, nxl = open_(rec["E"]), rec["nx"]
-            ghost = lambda c: base + ((c * (nxl + 2) + nxl + 1) * plane) * w
-            self.dst["E"] = (ghost(1), ghost(2), open_(rec["flags"]))
-        if part.rank < part.world - 1:                      # H last plane -> right neighbour's low ghost
-            rec = everyone[part.rank + 1]
-            base, nxl = open_(rec["H"]), rec["nx"]
-            ghost = lambda c: base + (c * (nxl + 2) * plane) * w
-            self.dst["H"] = (ghost(1), ghost(2), open_(rec["flags"]) + 8)
-        dist.barrier()
+        if failure is None:
+            try:
+                if part.rank > 0:                                   # E plane 0 -> left neighbour's high ghost
+                    rec = everyone[part.rank - 1]
+                    base, nxl = open_(rec["E"]), rec["nx"]
+                    self.dst["E"] = (base + ((1 * (nxl + 2) + nxl + 1) * plane) * w,
+                                     base + ((2 * (nxl + 2) + nxl + 1) * plane) * w, open_(rec["flags"]))
+                if part.rank < part.world - 1:                      # H last plane -> right neighbour's low ghost
+                    rec = everyone[part.rank + 1]
+                    base, nxl = open_(rec["H"]), rec["nx"]
+                    self.dst["H"] = (base + (1 * (nxl + 2) * plane) * w, base + (2 * (nxl + 2) * plane) * w,
+                                     open_(rec["flags"]) + 8)
+            except Exception as exc:
+                failure = str(exc)
+        ok = torch.tensor([0 if failure else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            raise RuntimeError(failure or "a neighbour rank could not map this rank's memory")
 
     def neighbour(self, field):
         """the rank this field's boundary plane goes to -- and the other field's ghost comes from."""
