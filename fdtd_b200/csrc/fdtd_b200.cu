@@ -77,6 +77,9 @@ int pow2_ceil(int v) {
 #ifndef FDTD_FUSE_MAX_CELLS
 #define FDTD_FUSE_MAX_CELLS (1LL << 23)
 #endif
+#ifndef FDTD_MAX_LANES_Z
+#define FDTD_MAX_LANES_Z 32   // threads of a block along z (x VEC cells each); the rest of the 256 go to y rows
+#endif
 #ifndef FDTD_MAX_VEC_F32
 #define FDTD_MAX_VEC_F32 4
 #endif
@@ -89,7 +92,10 @@ Geometry geometry(int dtype, int Ny, int Nz) {
     g.vec = (Nz % 2 == 0) ? 2 : 1;
   int nvz = (Nz + g.vec - 1) / g.vec;
   g.lanes_z = pow2_ceil(nvz);
-  if (g.lanes_z > 32) g.lanes_z = 32;
+  // rows of up to 128 vectors: 16 lanes x 16 rows (fewer warps touch the z-PML ends of a row: +6 % at 512^3 f32
+  // and 256^3 f64); longer rows: 32 lanes x 8 rows (-1 % otherwise at 1024^3)            profiles/r1_tune8
+  const int max_lanes = nvz <= 128 ? (FDTD_MAX_LANES_Z < 16 ? FDTD_MAX_LANES_Z : 16) : FDTD_MAX_LANES_Z;
+  if (g.lanes_z > max_lanes) g.lanes_z = max_lanes;
   g.lanes_shift = 0;
   while ((1 << g.lanes_shift) < g.lanes_z) ++g.lanes_shift;
   g.rows = FDTD_BLOCK_THREADS / g.lanes_z;
@@ -102,7 +108,7 @@ Geometry geometry(int dtype, int Ny, int Nz) {
 
 // planes marched per block.  Two costs pull in opposite directions (fitted to profiles/r1_tune3.txt and
 // r1_tune4_slabs.txt on B200): every chunk re-reads two carried planes (~0.32/chunk of a launch) and the
-// last, partially filled wave of blocks runs the memory system below capacity (~1.2/waves, 444 resident
+// last, partially filled wave of blocks runs the memory system below capacity (~0.8/waves, 444 resident
 // blocks).  Pick the power of two in [4, 32] that minimises their sum.
 int default_x_chunk(const Geometry& g, int nx, int Ny, int Nz) {
   const double tiles = (double)((Ny + g.tile_y - 1) / g.tile_y) * ((Nz + g.tile_z - 1) / g.tile_z);
@@ -110,7 +116,7 @@ int default_x_chunk(const Geometry& g, int nx, int Ny, int Nz) {
   double best_cost = 1e30;
   for (int chunk = 4; chunk <= 32; chunk *= 2) {
     const double waves = ((nx + chunk - 1) / chunk) * tiles / (148.0 * 3);
-    const double cost = 0.32 / chunk + 1.2 / (waves > 0.25 ? waves : 0.25);
+    const double cost = 0.32 / chunk + 0.8 / (waves > 0.25 ? waves : 0.25);
     if (cost < best_cost) {
       best_cost = cost;
       best = chunk;

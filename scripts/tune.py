@@ -19,6 +19,9 @@ VDIR = os.path.join(ROOT, "fdtd_b200", "_variants")
 VARIANTS = {
     "default": [],
     "post_inline": ["-DFDTD_POST_INLINE=1"],
+    "lanes16": ["-DFDTD_MAX_LANES_Z=16"],
+    "lanes8": ["-DFDTD_MAX_LANES_Z=8"],
+    "lanes16_pf2": ["-DFDTD_MAX_LANES_Z=16", "-DFDTD_PREFETCH_PLANES=2"],
     "noinl": ["-DFDTD_NOINLINE_SLABS=1"],
     "noinl_mb4": ["-DFDTD_NOINLINE_SLABS=1", "-DFDTD_MIN_BLOCKS=4"],
     "pfG": ["-DFDTD_PREFETCH_WHAT=1"],

@@ -230,3 +230,27 @@ def test_many_sources_fall_back_to_unfused_kernels():
     o = build(yo)
     o.run(40)
     compare(scenes.dump(g), scenes.dump(o), 1e-12, bitwise=True)
+
+
+def test_float32_error_growth_against_float64_reference():
+    """north_star: <= 1e-5 in float32.  cuda.float32 is bit-identical to the reference's TRUE float32 run;
+    against the float64 run of the same scene the difference is float32's own (the reference's ".float32"
+    backends silently compute in float64).  40^3, six PMLs, continuous point source."""
+    def build(fd):
+        return scenes.pml3d(fd, n=(40, 40, 40), t=8)
+    yo.set_backend("numpy", "float64")
+    ref = build(yo)
+    got = build(cuda("float32"))
+    done, curve = 0, {}
+    for steps in (100, 200, 500):
+        ref.run(steps - done)
+        got.run(steps - done, progress_bar=False)
+        done = steps
+        e = scenes.rel_l2(got.E.cpu().numpy(), ref.E)
+        h = scenes.rel_l2(got.H.cpu().numpy(), ref.H)
+        curve[steps] = (e, h)
+        assert e <= 1e-5 and h <= 1e-5, (steps, e, h)
+    d = scenes.rel_l2(np.stack(got.detectors[0].E), np.stack([np.asarray(v) for v in ref.detectors[0].E]))
+    assert d <= 1e-5
+    print("float32 vs float64-reference rel-L2 (E, H):", {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in curve.items()},
+          "detector", f"{d:.2e}")
