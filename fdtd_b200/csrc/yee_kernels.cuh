@@ -39,6 +39,9 @@
 #ifndef FDTD_STREAM_HINTS
 #define FDTD_STREAM_HINTS 0    // 1: evict-first loads/stores (ld.global.cs / st.global.cs) for the updated field
 #endif
+#ifndef FDTD_H_DOWNWARD
+#define FDTD_H_DOWNWARD 0      // 1: the H half-step marches from high x to low x (mirror image of the E half-step)
+#endif
 #ifndef FDTD_NOINLINE_SLABS
 #define FDTD_NOINLINE_SLABS 0  // 1: the CPML pass is an out-of-line call, its registers do not count in the hot loop
 #endif
@@ -376,27 +379,33 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
   for (int s = 0; HAS_POST && s < P.n_det; ++s)
     post_yz |= (j >= P.det[s].bb[2]) && (j < P.det[s].bb[3]) && (k0 + VEC > P.det[s].bb[4]) && (k0 < P.det[s].bb[5]);
 
-  // x-neighbour plane carried in registers: plane i-1 of (Gy, Gz) for E, plane i for H
+  // x-neighbour plane carried in registers.  OWN_LOAD (E; H when marching downward): every plane's own
+  // (Gy, Gz) are loaded and the neighbour plane (i-1 for E, i+1 for H) is last iteration's own.  Otherwise
+  // (H marching upward): plane i comes from the carry and plane i+1 is loaded.
+  constexpr bool DOWN = !IS_E && (FDTD_H_DOWNWARD != 0);
+  constexpr bool OWN_LOAD = IS_E || DOWN;
+  constexpr int PF_DIR = DOWN ? -1 : 1;
   Pack<T, VEC> carry_y, carry_z;
   {
-    const i64 o = (IS_E ? (i64)(i0 - 1) : (i64)i0) * plane + p;
+    const i64 o = (IS_E ? (i64)(i0 - 1) : (DOWN ? (i64)i1 : (i64)i0)) * plane + p;
     carry_y = ldv<T, VEC>(Gy + o);
     carry_z = ldv<T, VEC>(Gz + o);
   }
   const i64 cls_stride = (i64)gridDim.y * gridDim.x;
   const i64 cls_tile = (i64)blockIdx.y * gridDim.x + blockIdx.x;
 
-  for (int i = i0; i < i1; ++i) {
+  for (int it = 0; it < i1 - i0; ++it) {
+    const int i = DOWN ? i1 - 1 - it : i0 + it;
     const i64 off = (i64)i * plane + p;
     const unsigned cls = P.cls ? P.cls[(i64)i * cls_stride + cls_tile] : 0u;
 
 #if FDTD_PREFETCH_PLANES > 0
-    if (i + FDTD_PREFETCH_PLANES < P.Nx) {
-      const i64 pf = off + (i64)FDTD_PREFETCH_PLANES * plane;
+    if (DOWN ? (i - FDTD_PREFETCH_PLANES >= 0) : (i + FDTD_PREFETCH_PLANES < P.Nx)) {
+      const i64 pf = off + (i64)(PF_DIR * FDTD_PREFETCH_PLANES) * plane;
       if (FDTD_PREFETCH_WHAT & 1) {
         prefetch_l2(Gx + pf);
-        prefetch_l2(Gy + pf + (IS_E ? 0 : plane));
-        prefetch_l2(Gz + pf + (IS_E ? 0 : plane));
+        prefetch_l2(Gy + pf + (OWN_LOAD ? 0 : plane));
+        prefetch_l2(Gz + pf + (OWN_LOAD ? 0 : plane));
       }
       if (FDTD_PREFETCH_WHAT & 2) {
         prefetch_l2(Fx + pf);
@@ -408,7 +417,7 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     // ---- loads -------------------------------------------------------------------------
     Pack<T, VEC> gx = ldv<T, VEC>(Gx + off);
     Pack<T, VEC> gy, gz, xnb_y, xnb_z;
-    if (IS_E) {
+    if (OWN_LOAD) {
       gy = ldv<T, VEC>(Gy + off);
       gz = ldv<T, VEC>(Gz + off);
       xnb_y = carry_y;
@@ -595,7 +604,7 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
       stv<T, VEC>(P.push_z + p, f2);
     }
 
-    if (IS_E) {
+    if (OWN_LOAD) {
       carry_y = gy;
       carry_z = gz;
     } else {

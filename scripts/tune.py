@@ -19,6 +19,7 @@ VDIR = os.path.join(ROOT, "fdtd_b200", "_variants")
 VARIANTS = {
     "default": [],
     "post_inline": ["-DFDTD_POST_INLINE=1"],
+    "hdown": ["-DFDTD_H_DOWNWARD=1"],
     "lanes16": ["-DFDTD_MAX_LANES_Z=16"],
     "lanes8": ["-DFDTD_MAX_LANES_Z=8"],
     "lanes16_pf2": ["-DFDTD_MAX_LANES_Z=16", "-DFDTD_PREFETCH_PLANES=2"],
@@ -121,5 +122,5 @@ if __name__ == "__main__":
     else:
         size = os.environ.get("TUNE_SIZE", "1024")
         size = int(size) if "x" not in size else tuple(int(v) for v in size.split("x"))
-        chunks = tuple(int(c) for c in os.environ.get("TUNE_CHUNKS", "32").split(","))
+        chunks = tuple(int(c) for c in os.environ.get("TUNE_CHUNKS", "0").split(","))
         run(size=size, chunks=chunks, dtype=os.environ.get("TUNE_DTYPE", "float32"))
