@@ -114,9 +114,17 @@ int default_x_chunk(const Geometry& g, int nx, int Ny, int Nz) {
   const double tiles = (double)((Ny + g.tile_y - 1) / g.tile_y) * ((Nz + g.tile_z - 1) / g.tile_z);
   int best = 4;
   double best_cost = 1e30;
+  // grids too small to fill the GPU even with 4-plane chunks are latency bound: the march is serial, so the
+  // shortest chunk (most blocks) wins
+  // (161x97x1 quick-start grid: 15.2 / 20.3 / 27.1 / 45.5 us per step with 1 / 2 / 4 / 8 planes per block)
+  if (((nx + 3) / 4) * tiles <= 2 * 148.0 * 3) {
+    for (int chunk = 1; chunk < 4; chunk *= 2)
+      if (((nx + chunk - 1) / chunk) * tiles <= 4 * 148.0 * 3) return chunk;
+    return 4;
+  }
   for (int chunk = 4; chunk <= 32; chunk *= 2) {
     const double waves = ((nx + chunk - 1) / chunk) * tiles / (148.0 * 3);
-    const double cost = 0.32 / chunk + 0.8 / (waves > 0.25 ? waves : 0.25);
+    const double cost = 0.32 / chunk + 0.8 / waves;
     if (cost < best_cost) {
       best_cost = cost;
       best = chunk;

@@ -86,7 +86,7 @@ def c3(as_grid_permittivity=False):
     # words/cell-step: 18 + PML 8*60/512 + absorber (3.6 % of cells) 6 words + lens (3.1 %) 3 words
     absorber = 50 * 312 * 312 / n ** 3
     lens = 64 * 256 * 256 / n ** 3
-    words = 18 + 8 * 60 / n + 6 * absorber + 3 * (lens if not as_grid_permittivity else 1.0)
+    words = 18 + 8 * 60 / n + 6 * absorber + 3 * lens     # (c3b: only tiles that differ from the background stream eps^-1)
     return g, 500, 4, words
 
 
@@ -157,6 +157,7 @@ def main():
     for name in names:
         t0 = time.perf_counter()
         g, steps, warm, words = CONFIGS[name]()
+        g._x_chunk = int(os.environ.get("X_CHUNK", "0"))
         g.run(warm, progress_bar=False)
         for det in g.detectors:
             _ = det.E
