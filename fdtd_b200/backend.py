@@ -113,13 +113,6 @@ class Backend:
             axes = tuple(range(arr.dim() - 1, -1, -1))
         return arr.permute(*axes)
 
-    # --- test hook ----------------------------------------------------------------------------
-    def _override_for_tests(self, lib, device, dtype):
-        """CPU test-suite only (tests/emu): run the host layer against the serial interpreter
-        build of the kernels.  Never called by the package."""
-        self.lib, self.device, self.float = lib, torch.device(device), dtype
-        self.name = f"emu.{str(dtype).split('.')[-1]}"
-
 
 backend = Backend()
 

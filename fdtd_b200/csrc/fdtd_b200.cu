@@ -155,8 +155,8 @@ int validate(const fdtd_desc* d) {
     if (!d->E[c] || !d->H[c]) return fail(FDTD_ERR_ARG, "null field pointer");
     if (!aligned(d->E[c], w * g.vec) || !aligned(d->H[c], w * g.vec))
       return fail(FDTD_ERR_ARG, "field pointer not aligned to %zu bytes", w * g.vec);
-    const void* opt[4] = {d->inv_eps[c], d->inv_eps_grid[c], d->absorb[c], d->inv_mu[c]};
-    for (int n = 0; n < 4; ++n)
+    const void* opt[5] = {d->inv_eps[c], d->inv_eps_grid[c], d->absorb[c], d->inv_mu[c], d->inv_eps2[c]};
+    for (int n = 0; n < 5; ++n)
       if (opt[n] && !aligned(opt[n], w * g.vec)) return fail(FDTD_ERR_ARG, "material pointer misaligned");
   }
   bool any_e = d->inv_eps[0] || d->inv_eps[1] || d->inv_eps[2];
@@ -306,6 +306,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
     P.bg_inv[c] = (T)(IS_E ? d->bg_inv_eps[c] : d->bg_inv_mu[c]);
     P.inv[c] = (const T*)(IS_E ? d->inv_eps[c] : d->inv_mu[c]);
     P.inv_grid[c] = IS_E ? (const T*)d->inv_eps_grid[c] : nullptr;
+    P.inv2[c] = IS_E ? (const T*)d->inv_eps2[c] : nullptr;
     P.absorb[c] = IS_E ? (const T*)d->absorb[c] : nullptr;
   }
   // a class map is only meaningful with the arrays it refers to

@@ -157,6 +157,7 @@ struct HalfStepParams {
   T bg_c[3];      // sc * background inverse material, rounded as the reference rounds it
   T bg_inv[3];    // background inverse material itself (AnisotropicObject cells round sc*(inv*curl))
   const T* inv[3];       // effective inverse material of the curl term, or null
+  const T* inv2[3];      // second object covering a cell (overlaps), or null
   const T* inv_grid[3];  // grid's own eps^-1 for the PML correction, or null (= inv)
   const T* absorb[3];    // absorption factor, or null
   const unsigned char* cls;
@@ -491,24 +492,12 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     }
 
     // ---- field update ----------------------------------------------------------------------
-    if (IS_E && (cls & FDTD_CLS_ABSORB)) {
-      // E *= (1-f)/(1+f); E += sc*eps^-1*curl/(1+f)        fdtd/objects.py:214-221
-      Pack<T, VEC> q0 = ldv<T, VEC>(P.absorb[0] + off);
-      Pack<T, VEC> q1 = ldv<T, VEC>(P.absorb[1] + off);
-      Pack<T, VEC> q2 = ldv<T, VEC>(P.absorb[2] + off);
+    // t = (sc * inverse material) * curl, the product the reference forms first (fdtd/grid.py:283, 309)
+    T tx[VEC], ty[VEC], tz[VEC];
+    bool aniso[VEC];
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const T ux = d_zy[e] - d_yz[e];
-        const T uy = d_xz[e] - d_zx[e];
-        const T uz = d_yx[e] - d_xy[e];
-        fx[e] = fx[e] * ((T(1) - q0.v[e]) / (T(1) + q0.v[e]));
-        fy[e] = fy[e] * ((T(1) - q1.v[e]) / (T(1) + q1.v[e]));
-        fz[e] = fz[e] * ((T(1) - q2.v[e]) / (T(1) + q2.v[e]));
-        fx[e] = fx[e] + (cx[e] * ux) / (T(1) + q0.v[e]);
-        fy[e] = fy[e] + (cy[e] * uy) / (T(1) + q1.v[e]);
-        fz[e] = fz[e] + (cz[e] * uz) / (T(1) + q2.v[e]);
-      }
-    } else if (IS_E && (cls & FDTD_CLS_ANISO)) {
+    for (int e = 0; e < VEC; ++e) aniso[e] = false;
+    if (IS_E && (cls & FDTD_CLS_ANISO)) {
       // AnisotropicObject cells: E += sc * (eps^-1 @ curl) -- the product with curl is rounded BEFORE the
       // scaling by sc (fdtd/objects.py:262-269); they are marked by a NEGATIVE zero in the grid's eps^-1
       const Pack<T, VEC> mark = ldv<T, VEC>(P.inv_grid[0] + off);
@@ -530,26 +519,57 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
         const T ux = d_zy[e] - d_yz[e];
         const T uy = d_xz[e] - d_zx[e];
         const T uz = d_yx[e] - d_xy[e];
-        const bool aniso = (mark.v[e] == T(0)) && fdtd_signbit(mark.v[e]);
-        fx[e] = fx[e] + (aniso ? P.sc * (a0.v[e] * ux) : cx[e] * ux);
-        fy[e] = fy[e] + (aniso ? P.sc * (a1.v[e] * uy) : cy[e] * uy);
-        fz[e] = fz[e] + (aniso ? P.sc * (a2.v[e] * uz) : cz[e] * uz);
+        aniso[e] = (mark.v[e] == T(0)) && fdtd_signbit(mark.v[e]);
+        tx[e] = aniso[e] ? P.sc * (a0.v[e] * ux) : cx[e] * ux;
+        ty[e] = aniso[e] ? P.sc * (a1.v[e] * uy) : cy[e] * uy;
+        tz[e] = aniso[e] ? P.sc * (a2.v[e] * uz) : cz[e] * uz;
       }
     } else {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        const T ux = d_zy[e] - d_yz[e];
-        const T uy = d_xz[e] - d_zx[e];
-        const T uz = d_yx[e] - d_xy[e];
+        tx[e] = cx[e] * (d_zy[e] - d_yz[e]);
+        ty[e] = cy[e] * (d_xz[e] - d_zx[e]);
+        tz[e] = cz[e] * (d_yx[e] - d_xy[e]);
+      }
+    }
+    if (IS_E && (cls & FDTD_CLS_ABSORB)) {
+      // E *= (1-f)/(1+f); E += sc*eps^-1*curl/(1+f)        fdtd/objects.py:214-221
+      Pack<T, VEC> q0 = ldv<T, VEC>(P.absorb[0] + off);
+      Pack<T, VEC> q1 = ldv<T, VEC>(P.absorb[1] + off);
+      Pack<T, VEC> q2 = ldv<T, VEC>(P.absorb[2] + off);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        fx[e] = fx[e] * ((T(1) - q0.v[e]) / (T(1) + q0.v[e]));
+        fy[e] = fy[e] * ((T(1) - q1.v[e]) / (T(1) + q1.v[e]));
+        fz[e] = fz[e] * ((T(1) - q2.v[e]) / (T(1) + q2.v[e]));
+        fx[e] = fx[e] + tx[e] / (T(1) + q0.v[e]);
+        fy[e] = fy[e] + ty[e] / (T(1) + q1.v[e]);
+        fz[e] = fz[e] + tz[e] / (T(1) + q2.v[e]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
         if (IS_E) {
-          fx[e] = fx[e] + cx[e] * ux;
-          fy[e] = fy[e] + cy[e] * uy;
-          fz[e] = fz[e] + cz[e] * uz;
+          fx[e] = fx[e] + tx[e];
+          fy[e] = fy[e] + ty[e];
+          fz[e] = fz[e] + tz[e];
         } else {
-          fx[e] = fx[e] - cx[e] * ux;
-          fy[e] = fy[e] - cy[e] * uy;
-          fz[e] = fz[e] - cz[e] * uz;
+          fx[e] = fx[e] - tx[e];
+          fy[e] = fy[e] - ty[e];
+          fz[e] = fz[e] - tz[e];
         }
+      }
+    }
+    if (IS_E && (cls & FDTD_CLS_OVERLAP)) {
+      // a second object on the same cell adds its own term afterwards (fdtd/objects.py:127-129); absorbers never
+      // overlap anything, so in their cells this adds zero
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T ux = d_zy[e] - d_yz[e], uy = d_xz[e] - d_zx[e], uz = d_yx[e] - d_xy[e];
+        const T b0 = P.inv2[0][off + e], b1 = P.inv2[1][off + e], b2 = P.inv2[2][off + e];
+        fx[e] = fx[e] + (aniso[e] ? P.sc * (b0 * ux) : (P.sc * b0) * ux);
+        fy[e] = fy[e] + (aniso[e] ? P.sc * (b1 * uy) : (P.sc * b1) * uy);
+        fz[e] = fz[e] + (aniso[e] ? P.sc * (b2 * uz) : (P.sc * b2) * uz);
       }
     }
 

@@ -99,13 +99,29 @@ class Engine:
 
         # --- materials ------------------------------------------------------------------------
         ie_grid, imu = g._inv_eps, g._inv_mu
-        ie_eff, absorb = ie_grid, None
+        ie_eff, absorb, ie2 = ie_grid, None, None
         if g.objects:
             ie_eff = ie_grid.clone()
+            # overlapping objects each add their own term in the reference (fdtd/objects.py:127-129): the first
+            # one covering a cell goes into ie_eff, the second into ie2 (further ones are summed into ie2)
+            boxes = [(o.x, o.y, o.z) for o in g.objects]
+            overlaps = any(all(max(p.start, q.start) < min(p.stop, q.stop) for p, q in zip(boxes[a], boxes[b]))
+                           for a in range(len(boxes)) for b in range(a + 1, len(boxes)))
+            cover = torch.zeros(ie_grid.shape[1:], dtype=torch.int8, device=ie_grid.device) if overlaps else None
             for o in g.objects:
                 if o._nx_local == 0:
                     continue
-                ie_eff[(slice(None),) + o._loc] += o._inv_eps_soa
+                loc = (slice(None),) + o._loc
+                if cover is None:
+                    ie_eff[loc] += o._inv_eps_soa
+                else:
+                    first = (cover[o._loc] == 0).unsqueeze(0)
+                    ie_eff[loc] += torch.where(first, o._inv_eps_soa, torch.zeros_like(o._inv_eps_soa))
+                    if not bool(first.all()):
+                        if ie2 is None:
+                            ie2 = torch.zeros_like(ie_grid)
+                        ie2[loc] += torch.where(first, torch.zeros_like(o._inv_eps_soa), o._inv_eps_soa)
+                    cover[o._loc] += 1
                 if o._absorb_soa is not None:
                     if absorb is None:
                         absorb = torch.zeros_like(ie_grid)
@@ -117,14 +133,15 @@ class Engine:
         d.tile_y, d.tile_z = ty.value, tz.value
         cls = None
         if ie_eff is not None or imu is not None:
-            cls = self._classify(ie_eff, ie_grid if g.objects else None, absorb, imu, ty.value, tz.value)
+            cls = self._classify(ie_eff, ie_grid if g.objects else None, absorb, imu, ty.value, tz.value, ie2)
         for c in range(3):
             d.inv_eps[c] = ie_eff[c].data_ptr() if ie_eff is not None else None
+            d.inv_eps2[c] = ie2[c].data_ptr() if ie2 is not None else None
             d.inv_eps_grid[c] = ie_grid[c].data_ptr() if (g.objects and ie_grid is not None) else None
             d.absorb[c] = absorb[c].data_ptr() if absorb is not None else None
             d.inv_mu[c] = imu[c].data_ptr() if imu is not None else None
         d.tile_class = _ptr(cls)
-        self._keep += [ie_eff, absorb, cls]
+        self._keep += [ie_eff, absorb, cls, ie2]
         self.tile_class = cls
 
         # --- sources ----------------------------------------------------------------------------
@@ -288,7 +305,7 @@ class Engine:
             _capi.check(lib, lib.fdtd_halo_signal(C.c_void_p(flag), h.count[field] + 1, sst))
         h.count[field] += 1
 
-    def _classify(self, ie_eff, ie_grid_if_objects, absorb, imu, ty, tz):
+    def _classify(self, ie_eff, ie_grid_if_objects, absorb, imu, ty, tz, ie2=None):
         """per-(plane, y-tile, z-tile) class byte, FDTD_CLS_* (include/fdtd_b200.h)."""
         g = self.grid
         nx, Ny, Nz = g._part.nx, g.Ny, g.Nz
@@ -312,8 +329,11 @@ class Engine:
                 bits |= tiles((imu[:, a:b] != bg_m).any(0)).to(torch.uint8) * _capi.CLS_VARY_H
             if absorb is not None:
                 bits |= tiles((absorb[:, a:b] != 0).any(0)).to(torch.uint8) * _capi.CLS_ABSORB
+            if ie2 is not None:
+                bits |= tiles((ie2[:, a:b] != 0).any(0)).to(torch.uint8) * _capi.CLS_OVERLAP
             if ie_grid_if_objects is not None:
-                bits |= tiles((ie_eff[:, a:b] != ie_grid_if_objects[:, a:b]).any(0)).to(torch.uint8) * _capi.CLS_OBJECT
+                bits |= tiles(((ie_eff[:, a:b] != ie_grid_if_objects[:, a:b])
+                               | (False if ie2 is None else ie2[:, a:b] != 0)).any(0)).to(torch.uint8) * _capi.CLS_OBJECT
                 gx = ie_grid_if_objects[0, a:b]
                 bits |= tiles((gx == 0) & torch.signbit(gx)).to(torch.uint8) * _capi.CLS_ANISO
             cls[a:b] = bits

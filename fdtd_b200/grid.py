@@ -14,6 +14,7 @@ Differences a user can see, all deliberate:
 import gc
 import os
 
+import numpy as np
 import torch
 
 from . import constants as const
@@ -100,8 +101,11 @@ class Grid:
             raise NotImplementedError(f"complex {what} is not supported by the CUDA engine")
         if bd.is_array(value) and len(value.shape) == 3:
             value = value[:, :, :, None]
-        v = torch.as_tensor(value).to(dtype=self._dtype, device="cpu") if not torch.is_tensor(value) \
-            else value.detach().to(dtype=self._dtype)
+        if torch.is_tensor(value):
+            v = value.detach().to(dtype=self._dtype)
+        else:
+            # via numpy: a python float must enter as float64 (torch.as_tensor would make it float32)
+            v = torch.from_numpy(np.asarray(value, dtype=np.float64)).to(dtype=self._dtype)
         ones = torch.ones(3, dtype=self._dtype, device=v.device)
         if v.numel() == 1 or (v.dim() >= 1 and v.numel() == 3 and v.shape[-1] == 3):
             inv = (ones / v.reshape(-1)).cpu()

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 8
+#define FDTD_ABI_VERSION 9
 
 #define FDTD_F32 0
 #define FDTD_F64 1
@@ -61,6 +61,8 @@ extern "C" {
 #define FDTD_CLS_VARY_H 2   /* mu^-1 differs from the background: stream inv_mu */
 #define FDTD_CLS_ABSORB 4   /* an AbsorbingObject covers part of the tile: stream absorb */
 #define FDTD_CLS_OBJECT 8   /* an Object covers part of the tile: the PML add needs inv_eps_grid */
+#define FDTD_CLS_OVERLAP 32 /* two objects overlap in the tile: the second one's term is added separately (inv_eps2),
+                               as the reference's per-object loop does (fdtd/objects.py:127-129) */
 #define FDTD_CLS_ANISO 16   /* an AnisotropicObject covers part of the tile: its cells (inv_eps_grid x-component
                                == -0.0) round sc*(eps^-1*curl) like the reference's bmm, not (sc*eps^-1)*curl */
 
@@ -154,6 +156,7 @@ typedef struct fdtd_desc {
   double bg_inv_eps[3];   /* background eps^-1 used by tiles without FDTD_CLS_VARY_E */
   double bg_inv_mu[3];
   const void* inv_eps[3];      /* effective eps^-1 of the curl term: grid value outside objects, object value inside; or NULL */
+  const void* inv_eps2[3];     /* eps^-1 of the SECOND object covering a cell (zero elsewhere), or NULL: no overlaps */
   const void* inv_eps_grid[3]; /* the grid's own eps^-1 (zero inside objects, fdtd/objects.py:92) for the PML add; NULL = inv_eps */
   const void* absorb[3];       /* AbsorbingObject absorption factor f (fdtd/objects.py:198-205), zero elsewhere; or NULL */
   const void* inv_mu[3];       /* or NULL */

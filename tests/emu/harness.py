@@ -1,4 +1,7 @@
-"""Switch fdtd_b200's host layer onto the serial-interpreter build of its kernels (CPU tests only)."""
+"""Point fdtd_b200's host layer at the serial-interpreter build of its kernels (CPU tests only).
+
+The product has no hook for this: the test pokes the backend singleton's attributes directly, the same
+ones `fdtd_b200.set_backend` fills in on a GPU box (library handle, device, dtype)."""
 import torch
 
 import fdtd_b200
@@ -14,5 +17,8 @@ def use_emu(dtype="float64"):
     global _lib
     if _lib is None:
         _lib = _capi.bind(build_emu.build())
-    backend._override_for_tests(_lib, "cpu", getattr(torch, dtype))
+    backend.lib = _lib
+    backend.device = torch.device("cpu")
+    backend.float = getattr(torch, dtype)
+    backend.name = f"emu.{dtype}"
     return fdtd_b200

@@ -254,3 +254,25 @@ def test_float32_error_growth_against_float64_reference():
     assert d <= 1e-5
     print("float32 vs float64-reference rel-L2 (E, H):", {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in curve.items()},
           "detector", f"{d:.2e}")
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("seed", range(100, 116))
+def test_random_scene_on_gpu(seed, dtype):
+    """seeded random registrations (tests/fuzz_scenes.py): CUDA vs oracle, bit for bit."""
+    from fuzz_scenes import random_scene
+    from test_fuzz_emu import inexact_overlaps
+    build, steps = random_scene(seed)
+    g = build(cuda(dtype))
+    g.run(steps // 2, progress_bar=False)
+    for _ in range(steps - steps // 2):
+        g.step()
+    got = scenes.dump(g)
+    yo.set_backend("numpy" if dtype == "float64" else "torch", dtype)
+    try:
+        o = build(yo)
+        o.run(steps)
+        want = scenes.dump(o)
+    finally:
+        yo.set_backend("numpy", "float64")
+    compare(got, want, TOL[dtype], bitwise=not inexact_overlaps(o))
