@@ -167,9 +167,11 @@ class CurrentDetector(BlockDetector):
     def _register_grid(self, grid, x, y, z):
         super()._register_grid(grid, x, y, z)
         part = grid._part
-        if part.sharded and self._n_local and self._bbox[0] == 0 and part.x0 > 0:
-            raise NotImplementedError("a CurrentDetector cell on the first plane of an x-slab (needs the "
-                                      "neighbour slab's H of the same half-step)")
+        if part.sharded:
+            firsts = {part.bounds(r)[0] for r in range(1, part.world)} | {0}
+            if any((v + grid.Nx) % grid.Nx in firsts for v in self.x):     # same verdict on every rank
+                raise NotImplementedError("a CurrentDetector cell on the first plane of an x-slab (needs the "
+                                          "neighbour slab's H of the same half-step)")
         self._last = bd.zeros((max(1, self._n_local),))
 
     @property

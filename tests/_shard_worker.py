@@ -29,8 +29,20 @@ def main():
                                 device_id=torch.device("cuda", torch.cuda.current_device()))
         import fdtd_b200 as fd
         fd.set_backend("cuda." + dtype)
-    build = scenes.SCENES[scene][0] if scene in scenes.SCENES else getattr(scenes, scene)
-    g = build(fd)
+    if scene.startswith("fuzz:"):
+        from fuzz_scenes import random_scene
+        build, _ = random_scene(int(scene[5:]))
+    else:
+        build = scenes.SCENES[scene][0] if scene in scenes.SCENES else getattr(scenes, scene)
+    try:
+        g = build(fd)
+        g.run(0, progress_bar=False)           # bake: sharding restrictions surface here, on every rank alike
+    except (NotImplementedError, ValueError) as exc:
+        if rank == 0:
+            np.savez(out, skipped=np.array(str(exc)))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     assert g._part.world == world and g._part.sharded
     half = steps // 2
     g.run(half, progress_bar=False)

@@ -54,3 +54,22 @@ def test_sharded_equals_single(tmp_path, world, scene, dtype):
     for k in want:
         assert got[k].shape == want[k].shape, k
         assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
+
+
+@pytest.mark.parametrize("seed", [3, 7, 11, 19, 23, 42])
+def test_sharded_random_scene(tmp_path, seed):
+    """seeded random registrations (tests/fuzz_scenes.py) on 2 ranks: sharded == unsharded, bit for bit."""
+    from fuzz_scenes import random_scene
+    build, steps = random_scene(seed)
+    out = str(tmp_path / "sharded.npz")
+    launch(2, "gloo", "float64", f"fuzz:{seed}", steps, out)
+    got = dict(np.load(out))
+    if "skipped" in got:
+        pytest.skip(f"not shardable: {got['skipped']}")
+    fd = use_emu("float64")
+    g = build(fd)
+    g.run(steps, progress_bar=False)
+    want = scenes.dump(g)
+    assert set(got) == set(want)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
