@@ -365,15 +365,21 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
     P.push_y = (T*)push_y;
     P.push_z = (T*)push_z;
   }
-#define FDTD_LAUNCH_HALFSTEP(V)                                                                    \
-  if (has_push && has_post) {                                                                      \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, true>), grid, block, stream, P);         \
-  } else if (has_push) {                                                                           \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, true>), grid, block, stream, P);        \
-  } else if (has_post) {                                                                           \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, false>), grid, block, stream, P);        \
-  } else {                                                                                         \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, false>), grid, block, stream, P);       \
+  // folded sources/detectors only occur on small slabs: they share the general (MAT) instantiation
+  const bool mat = P.cls != nullptr || has_post;
+#define FDTD_LAUNCH_HALFSTEP(V)                                                                         \
+  if (has_post && has_push) {                                                                           \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, true, true>), grid, block, stream, P);        \
+  } else if (has_post) {                                                                                \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, false, true>), grid, block, stream, P);       \
+  } else if (has_push && mat) {                                                                         \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, true, true>), grid, block, stream, P);       \
+  } else if (has_push) {                                                                                \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, true, false>), grid, block, stream, P);      \
+  } else if (mat) {                                                                                     \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, false, true>), grid, block, stream, P);      \
+  } else {                                                                                              \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, false, false>), grid, block, stream, P);     \
   }
   switch (g.vec) {
     case 4:

@@ -295,6 +295,70 @@ struct CellState {
   T cx[VEC], cy[VEC], cz[VEC];
 };
 
+// E update of the cells of a tile that an AbsorbingObject, an AnisotropicObject or overlapping objects touch
+// (fdtd/objects.py:118-129, 207-221, 254-269).  C.c* = sc * effective eps^-1 as computed by the caller.
+template <typename T, int VEC>
+FDTD_RARE_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC>& C, i64 off, unsigned cls) {
+  T tx[VEC], ty[VEC], tz[VEC], ux[VEC], uy[VEC], uz[VEC];
+  bool aniso[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    ux[e] = C.d_zy[e] - C.d_yz[e];
+    uy[e] = C.d_xz[e] - C.d_zx[e];
+    uz[e] = C.d_yx[e] - C.d_xy[e];
+    tx[e] = C.cx[e] * ux[e];
+    ty[e] = C.cy[e] * uy[e];
+    tz[e] = C.cz[e] * uz[e];
+    aniso[e] = false;
+  }
+  if (cls & FDTD_CLS_ANISO) {
+    // AnisotropicObject cells: E += sc * (eps^-1 @ curl) -- the product with curl is rounded BEFORE the
+    // scaling by sc (fdtd/objects.py:262-269); they are marked by a NEGATIVE zero in the grid's eps^-1
+    const Pack<T, VEC> mark = ldv<T, VEC>(P.inv_grid[0] + off);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      aniso[e] = (mark.v[e] == T(0)) && fdtd_signbit(mark.v[e]);
+      if (aniso[e]) {
+        const bool vary = (cls & P.cls_vary) != 0;
+        tx[e] = P.sc * ((vary ? P.inv[0][off + e] : P.bg_inv[0]) * ux[e]);
+        ty[e] = P.sc * ((vary ? P.inv[1][off + e] : P.bg_inv[1]) * uy[e]);
+        tz[e] = P.sc * ((vary ? P.inv[2][off + e] : P.bg_inv[2]) * uz[e]);
+      }
+    }
+  }
+  if (cls & FDTD_CLS_ABSORB) {
+    // E *= (1-f)/(1+f); E += sc*eps^-1*curl/(1+f)        fdtd/objects.py:214-221
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const T q0 = P.absorb[0][off + e], q1 = P.absorb[1][off + e], q2 = P.absorb[2][off + e];
+      C.fx[e] = C.fx[e] * ((T(1) - q0) / (T(1) + q0));
+      C.fy[e] = C.fy[e] * ((T(1) - q1) / (T(1) + q1));
+      C.fz[e] = C.fz[e] * ((T(1) - q2) / (T(1) + q2));
+      C.fx[e] = C.fx[e] + tx[e] / (T(1) + q0);
+      C.fy[e] = C.fy[e] + ty[e] / (T(1) + q1);
+      C.fz[e] = C.fz[e] + tz[e] / (T(1) + q2);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      C.fx[e] = C.fx[e] + tx[e];
+      C.fy[e] = C.fy[e] + ty[e];
+      C.fz[e] = C.fz[e] + tz[e];
+    }
+  }
+  if (cls & FDTD_CLS_OVERLAP) {
+    // a second object on the same cell adds its own term afterwards (fdtd/objects.py:127-129); absorbers never
+    // overlap anything, so in their cells this adds zero
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const T b0 = P.inv2[0][off + e], b1 = P.inv2[1][off + e], b2 = P.inv2[2][off + e];
+      C.fx[e] = C.fx[e] + (aniso[e] ? P.sc * (b0 * ux[e]) : (P.sc * b0) * ux[e]);
+      C.fy[e] = C.fy[e] + (aniso[e] ? P.sc * (b1 * uy[e]) : (P.sc * b1) * uy[e]);
+      C.fz[e] = C.fz[e] + (aniso[e] ? P.sc * (b2 * uz[e]) : (P.sc * b2) * uz[e]);
+    }
+  }
+}
+
 // all CPML slabs a thread's cells belong to, in registration order
 template <typename T, int VEC, bool IS_E>
 FDTD_SLAB_FN void slab_pass(const HalfStepParams<T>& P, CellState<T, VEC>& C, int i, int j, int k0, i64 p,
@@ -336,7 +400,9 @@ FDTD_SLAB_FN void slab_pass(const HalfStepParams<T>& P, CellState<T, VEC>& C, in
 // and detector would dominate the step); compiled out otherwise
 // HAS_PUSH: the launch covers the slab's boundary plane and stores it into the neighbour's ghost plane as well
 // (compute + halo transfer in one kernel; fdtd_halo_signal publishes it afterwards)
-template <typename T, int VEC, bool IS_E, bool HAS_POST, bool HAS_PUSH>
+// MAT: the grid has material arrays and a tile-class map; without them (homogeneous grids, e.g. the 1024^3
+// benchmark) all coefficient / object / absorber code is compiled out and costs no registers
+template <typename T, int VEC, bool IS_E, bool HAS_POST, bool HAS_PUSH, bool MAT>
 __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_kernel(const FDTD_GRID_CONSTANT HalfStepParams<T> P) {
   const int tid = threadIdx.x;
   const int lane = tid & (P.lanes_z - 1);
@@ -398,7 +464,7 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
   for (int it = 0; it < i1 - i0; ++it) {
     const int i = DOWN ? i1 - 1 - it : i0 + it;
     const i64 off = (i64)i * plane + p;
-    const unsigned cls = P.cls ? P.cls[(i64)i * cls_stride + cls_tile] : 0u;
+    const unsigned cls = (MAT && P.cls) ? P.cls[(i64)i * cls_stride + cls_tile] : 0u;
 
 #if FDTD_PREFETCH_PLANES > 0
     if (DOWN ? (i - FDTD_PREFETCH_PLANES >= 0) : (i + FDTD_PREFETCH_PLANES < P.Nx)) {
@@ -492,84 +558,38 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     }
 
     // ---- field update ----------------------------------------------------------------------
-    // t = (sc * inverse material) * curl, the product the reference forms first (fdtd/grid.py:283, 309)
-    T tx[VEC], ty[VEC], tz[VEC];
-    bool aniso[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) aniso[e] = false;
-    if (IS_E && (cls & FDTD_CLS_ANISO)) {
-      // AnisotropicObject cells: E += sc * (eps^-1 @ curl) -- the product with curl is rounded BEFORE the
-      // scaling by sc (fdtd/objects.py:262-269); they are marked by a NEGATIVE zero in the grid's eps^-1
-      const Pack<T, VEC> mark = ldv<T, VEC>(P.inv_grid[0] + off);
-      Pack<T, VEC> a0, a1, a2;
-      if (cls & P.cls_vary) {
-        a0 = ldv<T, VEC>(P.inv[0] + off);
-        a1 = ldv<T, VEC>(P.inv[1] + off);
-        a2 = ldv<T, VEC>(P.inv[2] + off);
-      } else {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          a0.v[e] = P.bg_inv[0];
-          a1.v[e] = P.bg_inv[1];
-          a2.v[e] = P.bg_inv[2];
-        }
-      }
+    if (IS_E && (cls & (FDTD_CLS_ABSORB | FDTD_CLS_ANISO | FDTD_CLS_OVERLAP))) {
+      // tiles an AbsorbingObject, an AnisotropicObject or two overlapping objects touch: out-of-line, so that
+      // their registers and divisions do not burden the streaming path
+      CellState<T, VEC> C;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        const T ux = d_zy[e] - d_yz[e];
-        const T uy = d_xz[e] - d_zx[e];
-        const T uz = d_yx[e] - d_xy[e];
-        aniso[e] = (mark.v[e] == T(0)) && fdtd_signbit(mark.v[e]);
-        tx[e] = aniso[e] ? P.sc * (a0.v[e] * ux) : cx[e] * ux;
-        ty[e] = aniso[e] ? P.sc * (a1.v[e] * uy) : cy[e] * uy;
-        tz[e] = aniso[e] ? P.sc * (a2.v[e] * uz) : cz[e] * uz;
+        C.d_zy[e] = d_zy[e]; C.d_yz[e] = d_yz[e]; C.d_xz[e] = d_xz[e];
+        C.d_zx[e] = d_zx[e]; C.d_yx[e] = d_yx[e]; C.d_xy[e] = d_xy[e];
+        C.fx[e] = fx[e]; C.fy[e] = fy[e]; C.fz[e] = fz[e];
+        C.cx[e] = cx[e]; C.cy[e] = cy[e]; C.cz[e] = cz[e];
+      }
+      special_update<T, VEC>(P, C, off, cls);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        fx[e] = C.fx[e]; fy[e] = C.fy[e]; fz[e] = C.fz[e];
       }
     } else {
+      // F +-= (sc * inverse material) * curl      fdtd/grid.py:283, 309; fdtd/objects.py:118-129
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        tx[e] = cx[e] * (d_zy[e] - d_yz[e]);
-        ty[e] = cy[e] * (d_xz[e] - d_zx[e]);
-        tz[e] = cz[e] * (d_yx[e] - d_xy[e]);
-      }
-    }
-    if (IS_E && (cls & FDTD_CLS_ABSORB)) {
-      // E *= (1-f)/(1+f); E += sc*eps^-1*curl/(1+f)        fdtd/objects.py:214-221
-      Pack<T, VEC> q0 = ldv<T, VEC>(P.absorb[0] + off);
-      Pack<T, VEC> q1 = ldv<T, VEC>(P.absorb[1] + off);
-      Pack<T, VEC> q2 = ldv<T, VEC>(P.absorb[2] + off);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        fx[e] = fx[e] * ((T(1) - q0.v[e]) / (T(1) + q0.v[e]));
-        fy[e] = fy[e] * ((T(1) - q1.v[e]) / (T(1) + q1.v[e]));
-        fz[e] = fz[e] * ((T(1) - q2.v[e]) / (T(1) + q2.v[e]));
-        fx[e] = fx[e] + tx[e] / (T(1) + q0.v[e]);
-        fy[e] = fy[e] + ty[e] / (T(1) + q1.v[e]);
-        fz[e] = fz[e] + tz[e] / (T(1) + q2.v[e]);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
+        const T tx = cx[e] * (d_zy[e] - d_yz[e]);
+        const T ty = cy[e] * (d_xz[e] - d_zx[e]);
+        const T tz = cz[e] * (d_yx[e] - d_xy[e]);
         if (IS_E) {
-          fx[e] = fx[e] + tx[e];
-          fy[e] = fy[e] + ty[e];
-          fz[e] = fz[e] + tz[e];
+          fx[e] = fx[e] + tx;
+          fy[e] = fy[e] + ty;
+          fz[e] = fz[e] + tz;
         } else {
-          fx[e] = fx[e] - tx[e];
-          fy[e] = fy[e] - ty[e];
-          fz[e] = fz[e] - tz[e];
+          fx[e] = fx[e] - tx;
+          fy[e] = fy[e] - ty;
+          fz[e] = fz[e] - tz;
         }
-      }
-    }
-    if (IS_E && (cls & FDTD_CLS_OVERLAP)) {
-      // a second object on the same cell adds its own term afterwards (fdtd/objects.py:127-129); absorbers never
-      // overlap anything, so in their cells this adds zero
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const T ux = d_zy[e] - d_yz[e], uy = d_xz[e] - d_zx[e], uz = d_yx[e] - d_xy[e];
-        const T b0 = P.inv2[0][off + e], b1 = P.inv2[1][off + e], b2 = P.inv2[2][off + e];
-        fx[e] = fx[e] + (aniso[e] ? P.sc * (b0 * ux) : (P.sc * b0) * ux);
-        fy[e] = fy[e] + (aniso[e] ? P.sc * (b1 * uy) : (P.sc * b1) * uy);
-        fz[e] = fz[e] + (aniso[e] ? P.sc * (b2 * uz) : (P.sc * b2) * uz);
       }
     }
 
