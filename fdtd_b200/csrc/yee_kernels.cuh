@@ -52,6 +52,15 @@
 #else
 #define FDTD_RARE_FN __device__ __noinline__   // rare paths out of line: their registers do not count in the hot loop
 #endif
+// absorbing / anisotropic / overlap tiles: inlined (measured +3 % on the 512^3 absorber + lens config over an
+// out-of-line call, profiles/r1_special_inline.txt); homogeneous grids never compile this code (MAT = false)
+#if defined(FDTD_EMU)
+#define FDTD_SPECIAL_FN inline
+#elif defined(FDTD_SPECIAL_NOINLINE)
+#define FDTD_SPECIAL_FN __device__ __noinline__
+#else
+#define FDTD_SPECIAL_FN __device__ __forceinline__
+#endif
 #if defined(FDTD_EMU)
 #define FDTD_GRID_CONSTANT
 #define FDTD_SLAB_FN inline
@@ -298,7 +307,7 @@ struct CellState {
 // E update of the cells of a tile that an AbsorbingObject, an AnisotropicObject or overlapping objects touch
 // (fdtd/objects.py:118-129, 207-221, 254-269).  C.c* = sc * effective eps^-1 as computed by the caller.
 template <typename T, int VEC>
-FDTD_RARE_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC>& C, i64 off, unsigned cls) {
+FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC>& C, i64 off, unsigned cls) {
   T tx[VEC], ty[VEC], tz[VEC], ux[VEC], uy[VEC], uz[VEC];
   bool aniso[VEC];
 #pragma unroll

@@ -158,6 +158,9 @@ def main():
         t0 = time.perf_counter()
         g, steps, warm, words = CONFIGS[name]()
         g._x_chunk = int(os.environ.get("X_CHUNK", "0"))
+        if os.environ.get("TUNE_LIB"):          # development: time a build variant from scripts/tune.py
+            from fdtd_b200 import _capi
+            fd.backend.lib = _capi.bind(os.environ["TUNE_LIB"])
         g.run(warm, progress_bar=False)
         for det in g.detectors:
             _ = det.E

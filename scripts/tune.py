@@ -20,6 +20,7 @@ VARIANTS = {
     "default": [],
     "post_inline": ["-DFDTD_POST_INLINE=1"],
     "hdown": ["-DFDTD_H_DOWNWARD=1"],
+    "special_noinline": ["-DFDTD_SPECIAL_NOINLINE=1"],
     "lanes16": ["-DFDTD_MAX_LANES_Z=16"],
     "lanes8": ["-DFDTD_MAX_LANES_Z=8"],
     "lanes16_pf2": ["-DFDTD_MAX_LANES_Z=16", "-DFDTD_PREFETCH_PLANES=2"],
