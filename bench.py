@@ -23,7 +23,6 @@ import argparse
 import ctypes as C
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

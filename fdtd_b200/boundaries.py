@@ -6,8 +6,6 @@ runs inside the fused CUDA kernels.  A PML keeps two psi scalars per slab cell a
 and four 1-D tables of length `thickness` instead of the reference's 14 slab-sized arrays
 (SURVEY.md section 8a rows P1-P5).
 """
-import torch
-
 from .backend import backend as bd
 from ._hostmath import HostLib
 

@@ -12,14 +12,11 @@ What is baked (once, and again only when something registered or a material arra
   * detector point lists and device ring buffers, flushed to the host in batches.
 """
 import ctypes as C
-import math
 
-import numpy as np
 import torch
 
 from . import _capi
 from .backend import backend as bd
-from ._hostmath import scalar_in_dtype
 from .sharding import HaloExchange, P2PHalo
 
 RING_BYTES = 64 << 20          # detector ring budget per grid

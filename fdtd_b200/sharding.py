@@ -86,7 +86,6 @@ class HaloExchange:
         self.part, self.E, self.H = part, E, H      # storage tensors (3, nx+2, Ny, Nz)
         self.cuda = E.is_cuda
         self.stream = torch.cuda.Stream(device=E.device) if self.cuda else None
-        self.pending = []                            # events / requests not yet waited
 
     def _ops(self, F, to_left):
         p, n = self.part, self.part.nx

@@ -1,6 +1,4 @@
 """x-slab sharding over NCCL on real GPUs: sharded == single-GPU result, bit for bit (needs >= 2 GPUs)."""
-import os
-
 import numpy as np
 import pytest
 import torch
