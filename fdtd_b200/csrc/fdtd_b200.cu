@@ -37,6 +37,9 @@ __device__ __forceinline__ bool fdtd_signbit(T v) { return signbit(v); }
 #endif
 
 #include "yee_kernels.cuh"
+#ifndef FDTD_EMU
+#include "yee_fused_eh.cuh"
+#endif
 
 namespace {
 
@@ -276,14 +279,38 @@ fdtd::SlabK<T> slab_k(const fdtd_slab& S) {
   return k;
 }
 
+// a shell launch of a temporally fused step: a cell box in y / z, explicit in / out / curl-source buffers, and no
+// folded sources or detectors (the fused step runs them itself)
+struct ShellOpts {
+  int y0, y1, z0, z1;
+  void* const* Fin;
+  void* const* Fout;
+  void* const* G;
+};
+
 // graph_step >= 0: the launch is being captured as step `graph_step` of a replayable chunk; waveform
 // index and ring slot are then graph_step + the bases in d->dyn
 template <typename T, bool IS_E>
 int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
-                    int64_t graph_step = -1, void* push_y = nullptr, void* push_z = nullptr) {
+                    int64_t graph_step = -1, void* push_y = nullptr, void* push_z = nullptr,
+                    const ShellOpts* shell = nullptr) {
   if (x_begin < 0 || x_end > d->Nx || x_begin > x_end) return fail(FDTD_ERR_ARG, "plane range [%d,%d)", x_begin, x_end);
   if (x_begin == x_end) return FDTD_OK;
   Geometry g = geometry(d->dtype, d->Ny, d->Nz);
+  if (shell) {
+    if (shell->y0 >= shell->y1 || shell->z0 >= shell->z1) return FDTD_OK;
+    // tile shape for the box: as few idle lanes as possible in a narrow z range
+    int nvz = (shell->z1 - shell->z0 + g.vec - 1) / g.vec;
+    g.lanes_z = pow2_ceil(nvz);
+    if (g.lanes_z > 32) g.lanes_z = 32;
+    g.lanes_shift = 0;
+    while ((1 << g.lanes_shift) < g.lanes_z) ++g.lanes_shift;
+    g.rows = FDTD_BLOCK_THREADS / g.lanes_z;
+    int ny2 = pow2_ceil(shell->y1 - shell->y0);
+    if (g.rows > ny2) g.rows = ny2;
+    g.tile_y = g.rows;
+    g.tile_z = g.lanes_z * g.vec;
+  }
   fdtd::HalfStepParams<T> P;
   memset(&P, 0, sizeof(P));
   P.Nx = d->Nx;
@@ -293,14 +320,21 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
   P.Nx_global = d->Nx_global;
   P.x_begin = x_begin;
   P.x_end = x_end;
-  P.x_chunk = d->x_chunk > 0 ? d->x_chunk : default_x_chunk(g, x_end - x_begin, d->Ny, d->Nz);
+  P.x_chunk = d->x_chunk > 0 ? d->x_chunk
+                             : default_x_chunk(g, x_end - x_begin, shell ? shell->y1 - shell->y0 : d->Ny,
+                                               shell ? shell->z1 - shell->z0 : d->Nz);
   P.lanes_z = g.lanes_z;
   P.lanes_shift = g.lanes_shift;
   P.rows = g.rows;
   P.plane = d->plane;
   P.sc = (T)d->courant;
+  P.y_begin = shell ? shell->y0 : 0;
+  P.y_end = shell ? shell->y1 : d->Ny;
+  P.z_begin = shell ? shell->z0 : 0;
+  P.z_end = shell ? shell->z1 : d->Nz;
   for (int c = 0; c < 3; ++c) {
     P.F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
+    P.Fo[c] = P.F[c];
     P.G[c] = (const T*)(IS_E ? d->H[c] : d->E[c]);
     P.bg_c[c] = rounded_product<T>(d->courant, IS_E ? d->bg_inv_eps[c] : d->bg_inv_mu[c]);
     P.bg_inv[c] = (T)(IS_E ? d->bg_inv_eps[c] : d->bg_inv_mu[c]);
@@ -308,6 +342,11 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
     P.inv_grid[c] = IS_E ? (const T*)d->inv_eps_grid[c] : nullptr;
     P.inv2[c] = IS_E ? (const T*)d->inv_eps2[c] : nullptr;
     P.absorb[c] = IS_E ? (const T*)d->absorb[c] : nullptr;
+    if (shell) {
+      P.F[c] = (T*)shell->Fin[c];
+      P.Fo[c] = (T*)shell->Fout[c];
+      P.G[c] = (const T*)shell->G[c];
+    }
   }
   // a class map is only meaningful with the arrays it refers to
   P.cls = d->tile_class;
@@ -315,7 +354,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
   if (P.inv[0] != nullptr && P.cls == nullptr) return fail(FDTD_ERR_ARG, "material arrays need a tile_class map");
   P.n_slabs = d->n_slabs;
   for (int s = 0; s < d->n_slabs; ++s) P.slabs[s] = slab_k<T, IS_E>(d->slabs[s]);
-  if (post_is_fused(d)) {
+  if (!shell && post_is_fused(d)) {
     P.dyn = graph_step >= 0 ? (const i64*)d->dyn : nullptr;
     for (int n = 0; n < d->n_sources; ++n) {
       const fdtd_source& S = d->sources[n];
@@ -353,7 +392,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
   }
 
   int chunks = (x_end - x_begin + P.x_chunk - 1) / P.x_chunk;
-  dim3 grid((d->Nz + g.tile_z - 1) / g.tile_z, (d->Ny + g.tile_y - 1) / g.tile_y, chunks);
+  dim3 grid((P.z_end - P.z_begin + g.tile_z - 1) / g.tile_z, (P.y_end - P.y_begin + g.tile_y - 1) / g.tile_y, chunks);
   dim3 block(g.lanes_z * g.rows);
   if (grid.y > 65535u || grid.z > 65535u) return fail(FDTD_ERR_UNSUPPORTED, "grid too large for one launch");
   const bool has_post = (P.n_src + P.n_det) > 0;
@@ -670,6 +709,142 @@ int fdtd_ipc_import(const void* handle64, int64_t offset, void** dev_ptr) {
 #endif
 
 #ifndef FDTD_EMU
+// ---- temporally fused E+H steps (yee_fused_eh.cuh) --------------------------------------------------------
+extern "C++" {
+namespace {
+struct InteriorBox {
+  int x0, x1, y0, y1, z0, z1;
+};
+
+// the largest box free of CPML cells and of the grid faces (where the curls are masked); z aligned to the vector
+bool interior_box(const fdtd_desc* d, int vec, InteriorBox* b) {
+  int lo[3] = {1, 1, 1}, hi[3] = {d->Nx - 1, d->Ny - 1, d->Nz - 1};
+  for (int s = 0; s < d->n_slabs; ++s) {
+    const fdtd_slab& S = d->slabs[s];
+    if (!S.fused) return false;
+    if (S.lo == 0) {
+      if (S.thickness > lo[S.axis]) lo[S.axis] = S.thickness;
+    } else if (S.lo < hi[S.axis]) {
+      hi[S.axis] = S.lo;
+    }
+  }
+  b->x0 = lo[0]; b->x1 = hi[0];
+  b->y0 = lo[1]; b->y1 = hi[1];
+  b->z0 = (lo[2] + vec - 1) / vec * vec;
+  b->z1 = hi[2] / vec * vec;
+  return b->x1 - b->x0 >= 8 && b->y1 - b->y0 >= fdtd::FUSED_R && b->z1 - b->z0 >= fdtd::FUSED_L * vec;
+}
+
+bool fuse_eh_eligible(const fdtd_desc* d, InteriorBox* box) {
+  if (!d->fuse_eh) return false;
+  for (int c = 0; c < 3; ++c)
+    if (!d->E2[c] || !d->H2[c] || d->inv_eps[c] || d->inv_mu[c] || d->absorb[c]) return false;
+  if (d->Nx != d->Nx_global || d->n_post != 0) return false;
+  const int vec = d->dtype == FDTD_F32 ? 4 : 2;
+  if (d->Nz % vec) return false;
+  int nsrc = 0;
+  for (int n = 0; n < d->n_sources; ++n) {
+    if (d->sources[n].kind != FDTD_SRC_POINTS || d->sources[n].field != 0) return false;
+    ++nsrc;
+  }
+  if (nsrc > FDTD_FUSED_MAX) return false;
+  for (int n = 0; n < d->n_detectors; ++n)
+    if (d->detectors[n].kind != FDTD_DET_FIELD) return false;
+  return interior_box(d, vec, box);
+}
+
+// one full step reading (Ein, Hin) and writing (Eout, Hout)
+template <typename T>
+int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, void* const* Eout, void* const* Hin,
+                  void* const* Hout, int64_t q, int64_t slot, void* stream) {
+  const int Nx = d->Nx, Ny = d->Ny, Nz = d->Nz;
+  // the shell: six boxes around the interior box
+  const int boxes[6][6] = {{0, B.x0, 0, Ny, 0, Nz},        {B.x1, Nx, 0, Ny, 0, Nz},
+                           {B.x0, B.x1, 0, B.y0, 0, Nz},   {B.x0, B.x1, B.y1, Ny, 0, Nz},
+                           {B.x0, B.x1, B.y0, B.y1, 0, B.z0}, {B.x0, B.x1, B.y0, B.y1, B.z1, Nz}};
+  int rc;
+  // 1. E half-step on the shell (CPML, boundary masks): A -> B
+  for (int n = 0; n < 6; ++n) {
+    ShellOpts o{boxes[n][2], boxes[n][3], boxes[n][4], boxes[n][5], Ein, Eout, Hin};
+    rc = launch_halfstep<T, true>(d, boxes[n][0], boxes[n][1], q, slot, stream, -1, nullptr, nullptr, &o);
+    if (rc) return rc;
+  }
+  // 2. sources: shell points here, interior points inside the fused kernel
+  fdtd::FusedParams<T> P;
+  memset(&P, 0, sizeof(P));
+  for (int n = 0; n < d->n_sources; ++n) {
+    const fdtd_source& S = d->sources[n];
+    int64_t w = q - S.wave_q0;
+    if (w < 0 || w >= S.wave_len)
+      return fail(FDTD_ERR_ARG, "source %d: step %lld outside its waveform table", n, (long long)q);
+    if (S.n == 0) continue;
+    FDTD_LAUNCH((fdtd::source_points_outside_kernel<T>), dim3(blocks_for(S.n)), dim3(256), stream, (T*)Eout[S.comp],
+                (const i64*)S.idx, (const T*)S.profile, S.n, (const T*)S.wave, (i64)w, (i64)d->plane, Nz, B.x0, B.x1,
+                B.y0, B.y1, B.z0, B.z1);
+    rc = check_launch("shell source");
+    if (rc) return rc;
+    fdtd::SrcK<T>& K = P.src[P.n_src++];
+    K.kind = S.kind;
+    K.comp = S.comp;
+    K.n = S.n;
+    for (int k = 0; k < 6; ++k) K.bb[k] = S.bbox[k];
+    K.idx = (const i64*)S.idx;
+    K.profile = (const T*)S.profile;
+    K.wave = (const T*)S.wave;
+    K.w = w;
+  }
+  // 3. the interior: E and H in one pass
+  constexpr int VEC = sizeof(T) == 4 ? 4 : 2;
+  P.Ny = Ny;
+  P.Nz = Nz;
+  P.plane = d->plane;
+  P.x0 = B.x0; P.x1 = B.x1; P.y0 = B.y0; P.y1 = B.y1; P.z0 = B.z0; P.z1 = B.z1;
+  P.x_chunk = d->x_chunk > 0 ? d->x_chunk : 32;
+  for (int c = 0; c < 3; ++c) {
+    P.Ein[c] = (const T*)Ein[c];
+    P.Eout[c] = (T*)Eout[c];
+    P.Hin[c] = (const T*)Hin[c];
+    P.Hout[c] = (T*)Hout[c];
+    P.ce[c] = rounded_product<T>(d->courant, d->bg_inv_eps[c]);
+    P.ch[c] = rounded_product<T>(d->courant, d->bg_inv_mu[c]);
+  }
+  {
+    dim3 grid((B.z1 - B.z0 + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC),
+              (B.y1 - B.y0 + fdtd::FUSED_R - 1) / fdtd::FUSED_R, (B.x1 - B.x0 + P.x_chunk - 1) / P.x_chunk);
+    dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
+    FDTD_LAUNCH((fdtd::fused_eh_kernel<T, VEC>), grid, block, stream, P);
+    rc = check_launch("fused_eh");
+    if (rc) return rc;
+  }
+  // 4. H half-step on the shell: A -> B, curls from the new E
+  for (int n = 0; n < 6; ++n) {
+    ShellOpts o{boxes[n][2], boxes[n][3], boxes[n][4], boxes[n][5], Hin, Hout, Eout};
+    rc = launch_halfstep<T, false>(d, boxes[n][0], boxes[n][1], q, slot, stream, -1, nullptr, nullptr, &o);
+    if (rc) return rc;
+  }
+  // 5. detectors on the new fields
+  for (int n = 0; n < d->n_detectors; ++n) {
+    const fdtd_detector& D = d->detectors[n];
+    if (D.n == 0) continue;
+    if (slot < 0 || slot >= D.capacity) return fail(FDTD_ERR_ARG, "detector %d: ring slot outside capacity", n);
+    FDTD_LAUNCH((fdtd::detector_kernel<T>), dim3(blocks_for((i64)D.n * 3)), dim3(256), stream, (const T*)Eout[0],
+                (const T*)Eout[1], (const T*)Eout[2], (const i64*)D.idx, (const int*)D.pos, D.n, (T*)D.ring_E,
+                (i64)slot);
+    rc = check_launch("detector");
+    if (rc) return rc;
+    FDTD_LAUNCH((fdtd::detector_kernel<T>), dim3(blocks_for((i64)D.n * 3)), dim3(256), stream, (const T*)Hout[0],
+                (const T*)Hout[1], (const T*)Hout[2], (const i64*)D.idx, (const int*)D.pos, D.n, (T*)D.ring_H,
+                (i64)slot);
+    rc = check_launch("detector");
+    if (rc) return rc;
+  }
+  return FDTD_OK;
+}
+}  // namespace
+}  // extern "C++"
+#endif
+
+#ifndef FDTD_EMU
 // ---- CUDA-graph replay of step chunks (small, launch-bound grids) ---------------------------------
 // One graph = FDTD_GRAPH_STEPS full steps with the fused kernels; the waveform index and ring slot of
 // node s are s + dyn[], and dyn[] is set by a one-thread kernel before each replay.  The executable
@@ -740,7 +915,23 @@ int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void
     return fail(FDTD_ERR_UNSUPPORTED, "fdtd_run on an x-sharded slab: drive the half-steps and the halo exchange per step");
   int64_t s = 0;
 #ifndef FDTD_EMU
-  if (d->use_graphs && d->dyn && post_is_fused(d) && nsteps >= FDTD_GRAPH_STEPS) {
+  {
+    // pairs of temporally fused steps: A -> B -> A, so the caller's buffers hold the result again
+    InteriorBox box;
+    if (nsteps >= 2 && fuse_eh_eligible(d, &box)) {
+      for (; s + 2 <= nsteps; s += 2) {
+        rc = d->dtype == FDTD_F32
+                 ? fused_eh_step<float>(d, box, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream)
+                 : fused_eh_step<double>(d, box, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream);
+        if (rc) return rc;
+        rc = d->dtype == FDTD_F32
+                 ? fused_eh_step<float>(d, box, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream)
+                 : fused_eh_step<double>(d, box, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream);
+        if (rc) return rc;
+      }
+    }
+  }
+  if (s == 0 && d->use_graphs && d->dyn && post_is_fused(d) && nsteps >= FDTD_GRAPH_STEPS) {
     // the whole replay must stay inside every waveform table and detector ring
     int64_t chunks = nsteps / FDTD_GRAPH_STEPS;
     int64_t wave_base = 0;

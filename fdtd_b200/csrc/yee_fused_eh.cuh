@@ -1,0 +1,196 @@
+// yee_fused_eh.cuh -- single-pass E+H update of the homogeneous interior (temporal fusion).
+//
+// The two-half-step algorithm moves 18 words per cell and step (E half-step: read H, read E, write E; H half-step:
+// read E, read H, write H).  Here a block marching along x updates E[i] and, one plane behind, H[i-1] in the same
+// pass, so that every field word is read once and written once per STEP: 12 words.  What makes this legal:
+//   * H[i-1]'s curl needs E_new of the y+1 / z+1 neighbours.  Inside the tile they come through shared memory;
+//     at the tile edge a one-cell halo of E_new is recomputed by extra threads (17x17 threads for a 16x16 core),
+//     or -- where the halo cell lies outside the interior box -- read back from memory, where the shell launches
+//     (the ordinary half-step kernel on the PML / boundary shell) have already put it;
+//   * blocks are not synchronised with each other, so nothing may be updated in place: E and H are ping-pong
+//     buffers (all kernels of a fused step read buffer A and write buffer B; an even number of fused steps ends
+//     in the caller's buffers, an odd remainder is run with the ordinary in-place kernels);
+//   * the box is free of CPML cells, material arrays and boundary masks, so a halo cell's E_new needs no state;
+//     E point sources inside the box are applied to every recomputed value (owner and halo alike).
+// Arithmetic per cell is the same as in halfstep_kernel, operation by operation: results are bit-identical.
+#pragma once
+
+namespace fdtd {
+
+template <typename T>
+struct FusedParams {
+  int Ny, Nz;
+  i64 plane;
+  int x0, x1, y0, y1, z0, z1;  // interior box (cells); z0, z1 multiples of the vector width
+  int x_chunk;
+  const T* Ein[3];
+  T* Eout[3];
+  const T* Hin[3];
+  T* Hout[3];
+  T ce[3], ch[3];  // sc * background eps^-1 / mu^-1, rounded as the reference rounds them
+  int n_src;
+  SrcK<T> src[FDTD_FUSED_MAX];  // soft point-list sources on E (ascending idx)
+};
+
+constexpr int FUSED_R = 16;  // core rows per block
+constexpr int FUSED_L = 16;  // core vector lanes per block
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), 2)
+    fused_eh_kernel(const __grid_constant__ FusedParams<T> P) {
+  constexpr int R = FUSED_R, L = FUSED_L, W = (L + 1) * VEC;
+  __shared__ T sm[2][3][R + 1][W];
+
+  const int tid = threadIdx.x;
+  const int r = tid / (L + 1), l = tid % (L + 1);
+  const int j = P.y0 + blockIdx.y * R + r;
+  const int k0 = P.z0 + (blockIdx.x * L + l) * VEC;
+  const bool core = (r < R) && (l < L) && (j < P.y1) && (k0 < P.z1);
+  const bool active = (j <= P.y1) && (k0 <= P.z1);  // own cells + the one-cell halo (always inside the grid)
+  const bool inside = (j < P.y1) && (k0 < P.z1);    // E_new recomputed here; otherwise the shell computed it
+  const int Nz = P.Nz;
+  const i64 plane = P.plane;
+  const i64 p = (i64)j * Nz + k0;
+  const int xa = P.x0 + blockIdx.z * P.x_chunk;
+  const int xb = (xa + P.x_chunk < P.x1) ? xa + P.x_chunk : P.x1;
+
+  // loop-invariant: can a source touch this thread's row / z-range at all?
+  bool src_yz = false;
+  for (int s = 0; s < P.n_src; ++s)
+    src_yz |= (j >= P.src[s].bb[2]) && (j < P.src[s].bb[3]) && (k0 + VEC > P.src[s].bb[4]) && (k0 < P.src[s].bb[5]);
+
+  // carried: H_old[i-1] and E_new[i-1] of the own cells
+  Pack<T, VEC> hp0, hp1, hp2, ep0, ep1, ep2;
+  if (active && inside) {
+    const i64 o = (i64)(xa - 1) * plane + p;
+    hp0 = ldv<T, VEC>(P.Hin[0] + o);
+    hp1 = ldv<T, VEC>(P.Hin[1] + o);
+    hp2 = ldv<T, VEC>(P.Hin[2] + o);
+  }
+
+  for (int i = xa; i <= xb; ++i) {
+    const i64 off = (i64)i * plane + p;
+    Pack<T, VEC> e0, e1, e2, h0, h1, h2;
+    if (active) {
+      if (inside && i < P.x1) {
+        // ---- E_new[i] = E_old + (sc eps^-1) * curl_H(H_old)      (fdtd/grid.py:54-76, 283)
+        h0 = ldv<T, VEC>(P.Hin[0] + off);
+        h1 = ldv<T, VEC>(P.Hin[1] + off);
+        h2 = ldv<T, VEC>(P.Hin[2] + off);
+        const Pack<T, VEC> y0v = ldv<T, VEC>(P.Hin[0] + off - Nz);
+        const Pack<T, VEC> y2v = ldv<T, VEC>(P.Hin[2] + off - Nz);
+        const T zs0 = P.Hin[0][off - 1];
+        const T zs1 = P.Hin[1][off - 1];
+        e0 = ldv<T, VEC>(P.Ein[0] + off);
+        e1 = ldv<T, VEC>(P.Ein[1] + off);
+        e2 = ldv<T, VEC>(P.Ein[2] + off);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const T zn0 = e == 0 ? zs0 : h0.v[e > 0 ? e - 1 : 0];
+          const T zn1 = e == 0 ? zs1 : h1.v[e > 0 ? e - 1 : 0];
+          const T d_zy = h2.v[e] - y2v.v[e];
+          const T d_xy = h0.v[e] - y0v.v[e];
+          const T d_yz = h1.v[e] - zn1;
+          const T d_xz = h0.v[e] - zn0;
+          const T d_zx = h2.v[e] - hp2.v[e];
+          const T d_yx = h1.v[e] - hp1.v[e];
+          e0.v[e] = e0.v[e] + P.ce[0] * (d_zy - d_yz);
+          e1.v[e] = e1.v[e] + P.ce[1] * (d_xz - d_zx);
+          e2.v[e] = e2.v[e] + P.ce[2] * (d_yx - d_xy);
+        }
+        if (src_yz) {
+          // soft sources, registration order (fdtd/sources.py:93-109, 278-297)
+          for (int s = 0; s < P.n_src; ++s) {
+            const SrcK<T>& S = P.src[s];
+            if (i < S.bb[0] || i >= S.bb[1] || j < S.bb[2] || j >= S.bb[3] || k0 + VEC <= S.bb[4] || k0 >= S.bb[5])
+              continue;
+            const T wv = S.wave[S.w];
+            for (int n = lower_bound_i64(S.idx, S.n, off); n < S.n && S.idx[n] < off + VEC; ++n) {
+              const int de = (int)(S.idx[n] - off);
+              const T v = S.profile[n] * wv;
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) {
+                if (e == de) {
+                  if (S.comp == 0) e0.v[e] = e0.v[e] + v;
+                  else if (S.comp == 1) e1.v[e] = e1.v[e] + v;
+                  else e2.v[e] = e2.v[e] + v;
+                }
+              }
+            }
+          }
+        }
+        if (core && i < xb) {
+          stv<T, VEC>(P.Eout[0] + off, e0);
+          stv<T, VEC>(P.Eout[1] + off, e1);
+          stv<T, VEC>(P.Eout[2] + off, e2);
+        }
+      } else {
+        // a shell cell (outside the box in y / z, or the plane x1): its E_new is already in memory
+        e0 = ldv<T, VEC>(P.Eout[0] + off);
+        e1 = ldv<T, VEC>(P.Eout[1] + off);
+        e2 = ldv<T, VEC>(P.Eout[2] + off);
+      }
+    }
+
+    // ---- H_new[i-1] = H_old - (sc mu^-1) * curl_E(E_new)      (fdtd/grid.py:29-51, 309)
+    if (core && i > xa) {
+      const int b = (i - 1) & 1;
+      Pack<T, VEC> hx = hp0, hy = hp1, hz = hp2;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T ex_y = sm[b][0][r + 1][l * VEC + e];
+        const T ez_y = sm[b][2][r + 1][l * VEC + e];
+        const T ex_z = e == VEC - 1 ? sm[b][0][r][(l + 1) * VEC] : ep0.v[e < VEC - 1 ? e + 1 : 0];
+        const T ey_z = e == VEC - 1 ? sm[b][1][r][(l + 1) * VEC] : ep1.v[e < VEC - 1 ? e + 1 : 0];
+        const T d_zy = ez_y - ep2.v[e];
+        const T d_xy = ex_y - ep0.v[e];
+        const T d_yz = ey_z - ep1.v[e];
+        const T d_xz = ex_z - ep0.v[e];
+        const T d_zx = e2.v[e] - ep2.v[e];
+        const T d_yx = e1.v[e] - ep1.v[e];
+        hx.v[e] = hx.v[e] - P.ch[0] * (d_zy - d_yz);
+        hy.v[e] = hy.v[e] - P.ch[1] * (d_xz - d_zx);
+        hz.v[e] = hz.v[e] - P.ch[2] * (d_yx - d_xy);
+      }
+      const i64 om = off - plane;
+      stv<T, VEC>(P.Hout[0] + om, hx);
+      stv<T, VEC>(P.Hout[1] + om, hy);
+      stv<T, VEC>(P.Hout[2] + om, hz);
+    }
+
+    // ---- publish E_new[i] to the block, carry the planes ---------------------------------------------
+    if (active) {
+      const int b = i & 1;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        sm[b][0][r][l * VEC + e] = e0.v[e];
+        sm[b][1][r][l * VEC + e] = e1.v[e];
+        sm[b][2][r][l * VEC + e] = e2.v[e];
+      }
+      ep0 = e0;
+      ep1 = e1;
+      ep2 = e2;
+      if (inside && i < P.x1) {
+        hp0 = h0;
+        hp1 = h1;
+        hp2 = h2;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// shell E sources of a fused step: the points OUTSIDE the interior box (those inside are applied by the fused kernel)
+template <typename T>
+__global__ void source_points_outside_kernel(T* F, const i64* idx, const T* profile, int n, const T* wave, i64 w,
+                                             i64 plane, int Nz, int x0, int x1, int y0, int y1, int z0, int z1) {
+  const T s = wave[w];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const i64 lin = idx[t];
+    const int x = (int)(lin / plane), y = (int)((lin % plane) / Nz), z = (int)(lin % Nz);
+    if (x >= x0 && x < x1 && y >= y0 && y < y1 && z >= z0 && z < z1) continue;
+    fdtd_atomic_add(F + lin, profile[t] * s);
+  }
+}
+
+}  // namespace fdtd

@@ -160,7 +160,9 @@ struct HalfStepParams {
   int x_begin, x_end, x_chunk;
   int lanes_z, lanes_shift, rows;  // block = lanes_z * rows threads, thread -> (row, lane)
   i64 plane;
-  T* F[3];        // field being updated
+  int y_begin, y_end, z_begin, z_end;  // cell box of this launch in y and z (full grid unless a shell launch)
+  T* F[3];        // field being updated (read)
+  T* Fo[3];       // where the updated field is written: F itself, or the other buffer of a ping-pong pair
   const T* G[3];  // field being differentiated
   T sc;
   T bg_c[3];      // sc * background inverse material, rounded as the reference rounds it
@@ -416,9 +418,9 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
   const int tid = threadIdx.x;
   const int lane = tid & (P.lanes_z - 1);
   const int row = tid >> P.lanes_shift;
-  const int k0 = (blockIdx.x * P.lanes_z + lane) * VEC;
-  const int j = blockIdx.y * P.rows + row;
-  if (j >= P.Ny || k0 >= P.Nz) return;
+  const int k0 = P.z_begin + (blockIdx.x * P.lanes_z + lane) * VEC;
+  const int j = P.y_begin + blockIdx.y * P.rows + row;
+  if (j >= P.y_end || k0 >= P.z_end) return;
   const int Nz = P.Nz;
   const i64 plane = P.plane;
   const i64 p = (i64)j * Nz + k0;
@@ -645,9 +647,9 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
       f1.v[e] = fy[e];
       f2.v[e] = fz[e];
     }
-    stv_stream<T, VEC>(Fx + off, f0);
-    stv_stream<T, VEC>(Fy + off, f1);
-    stv_stream<T, VEC>(Fz + off, f2);
+    stv_stream<T, VEC>(P.Fo[0] + off, f0);
+    stv_stream<T, VEC>(P.Fo[1] + off, f1);
+    stv_stream<T, VEC>(P.Fo[2] + off, f2);
     if (HAS_PUSH && i == P.push_plane) {
       stv<T, VEC>(P.push_y + p, f1);
       stv<T, VEC>(P.push_z + p, f2);

@@ -276,3 +276,38 @@ def test_random_scene_on_gpu(seed, dtype):
     finally:
         yo.set_backend("numpy", "float64")
     compare(got, want, TOL[dtype], bitwise=not inexact_overlaps(o))
+
+
+@pytest.mark.parametrize("dtype,n,t", [("float32", (72, 64, 96), 6), ("float64", (40, 52, 44), 5),
+                                       ("float32", (33, 41, 68), 3)])
+def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
+    """run() with FDTD_B200_FUSE_EH: pairs of single-pass E+H steps on the interior (ping-pong buffers, shared-
+    memory exchange of E_new, ordinary kernels on the PML shell) must reproduce the two-half-step path bit for
+    bit, for even and odd step counts, sources inside the interior and in the shell, detectors everywhere."""
+    fd = cuda(dtype)
+
+    def build():
+        g = fd.Grid(shape=n, grid_spacing=77.5e-9, permittivity=1.3, permeability=1.1)
+        g[0:t, :, :] = fd.PML()
+        g[-t:, :, :] = fd.PML()
+        g[:, 0:t, :] = fd.PML()
+        g[:, -t:, :] = fd.PML()
+        g[:, :, 0:t + 1] = fd.PML()
+        g[n[0] // 2, n[1] // 2, n[2] // 2] = fd.PointSource(period=17, name="centre")
+        g[2, n[1] // 2, 3] = fd.PointSource(period=11, amplitude=0.4, name="in_pml")
+        g[t + 2:n[0] - t - 2, t + 3:n[1] - t - 3, n[2] // 3] = fd.LineSource(period=23, name="line")
+        g[1:n[0] - 1, n[1] // 2 + 1, n[2] // 2 + 2] = fd.LineDetector(name="across")
+        g[n[0] // 2:n[0] // 2 + 1, 1:3, n[2] - 3:n[2] - 2] = fd.BlockDetector(name="corner")
+        return g
+
+    outs = []
+    for fuse in (False, True):
+        g = build()
+        g._fuse_eh = fuse
+        g.run(31, progress_bar=False)
+        g.step()
+        g.run(10, progress_bar=False)
+        assert bool(g._engine.desc.fuse_eh) == fuse
+        outs.append(scenes.dump(g))
+    assert float(np.abs(outs[0]["E"]).max()) > 0
+    compare(outs[1], outs[0], 0.0, bitwise=True)
