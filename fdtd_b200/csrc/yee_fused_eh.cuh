@@ -12,8 +12,23 @@
 //     in the caller's buffers, an odd remainder is run with the ordinary in-place kernels);
 //   * the box is free of CPML cells, material arrays and boundary masks, so a halo cell's E_new needs no state;
 //     E point sources inside the box are applied to every recomputed value (owner and halo alike).
-// Arithmetic per cell is the same as in halfstep_kernel, operation by operation: results are bit-identical.
+// Arithmetic per cell is the same as in halfstep_kernel, operation by operation: results are bit-identical
+// (tests/test_gpu_parity.py::test_temporally_fused_steps_equal_two_half_steps).
+//
+// STATUS (round 1): correct, opt-in (FDTD_B200_FUSE_EH=1), NOT yet faster.  1024^3 f32 on one B200
+// (profiles/r1_fused_eh_launches.csv): the fused kernel moves 51.8 GB in 10.8 ms (4.8 TB/s -- the barrier per
+// plane and 18 warps per SM hide latency worse than the barrier-free streaming kernel's 6.1 TB/s), the twelve
+// shell launches add 2.6 ms, 1.7 ms of which in the two 12-cell-wide z strips whose 48-byte rows waste DRAM
+// sectors 4x.  13.5 ms per step against 12.7 ms for the two half-steps.  To win it needs a deeper load pipeline
+// in the fused kernel (register or TMA prefetch across the barrier) and z strips handled inside it.
 #pragma once
+
+#ifndef FDTD_FUSED_MIN_BLOCKS
+#define FDTD_FUSED_MIN_BLOCKS 2
+#endif
+#ifndef FDTD_FUSED_PREFETCH
+#define FDTD_FUSED_PREFETCH 0   // L2 prefetch of the six input streams this many planes ahead (measured: hurts)
+#endif
 
 namespace fdtd {
 
@@ -36,7 +51,7 @@ constexpr int FUSED_R = 16;  // core rows per block
 constexpr int FUSED_L = 16;  // core vector lanes per block
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), 2)
+__global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_MIN_BLOCKS)
     fused_eh_kernel(const __grid_constant__ FusedParams<T> P) {
   constexpr int R = FUSED_R, L = FUSED_L, W = (L + 1) * VEC;
   __shared__ T sm[2][3][R + 1][W];
@@ -71,6 +86,17 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), 2)
   for (int i = xa; i <= xb; ++i) {
     const i64 off = (i64)i * plane + p;
     Pack<T, VEC> e0, e1, e2, h0, h1, h2;
+#if FDTD_FUSED_PREFETCH > 0
+    if (core && i + FDTD_FUSED_PREFETCH < P.x1) {
+      const i64 pf = off + (i64)FDTD_FUSED_PREFETCH * plane;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Hin[0] + pf));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Hin[1] + pf));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Hin[2] + pf));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Ein[0] + pf));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Ein[1] + pf));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Ein[2] + pf));
+    }
+#endif
     if (active) {
       if (inside && i < P.x1) {
         // ---- E_new[i] = E_old + (sc eps^-1) * curl_H(H_old)      (fdtd/grid.py:54-76, 283)

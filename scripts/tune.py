@@ -20,6 +20,10 @@ VARIANTS = {
     "default": [],
     "post_inline": ["-DFDTD_POST_INLINE=1"],
     "hdown": ["-DFDTD_H_DOWNWARD=1"],
+    "fz_pf0": ["-DFDTD_FUSED_PREFETCH=0"],
+    "fz_pf2": ["-DFDTD_FUSED_PREFETCH=2"],
+    "fz_mb3": ["-DFDTD_FUSED_MIN_BLOCKS=3"],
+    "fz_mb3_pf2": ["-DFDTD_FUSED_MIN_BLOCKS=3", "-DFDTD_FUSED_PREFETCH=2"],
     "special_noinline": ["-DFDTD_SPECIAL_NOINLINE=1"],
     "lanes16": ["-DFDTD_MAX_LANES_Z=16"],
     "lanes8": ["-DFDTD_MAX_LANES_Z=8"],
@@ -60,7 +64,9 @@ def build():
         r = subprocess.run(cmd, check=True, capture_output=True, text=True)
         lines = r.stderr.splitlines()
         for n, l in enumerate(lines):
-            if "Compiling entry function" in l and ("halfstep_kernelIfLi4ELb" in l or ("MAX_VEC_F32=2" in " ".join(defs) and "halfstep_kernelIfLi2ELb" in l)):
+            if "Compiling entry function" in l and ("fused_eh_kernelIfLi4" in l) and name.startswith("fz"):
+                print(name, "FUSED", " | ".join(x.strip() for x in lines[n + 1:n + 4]))
+            elif "Compiling entry function" in l and not name.startswith("fz") and ("halfstep_kernelIfLi4ELb" in l or ("MAX_VEC_F32=2" in " ".join(defs) and "halfstep_kernelIfLi2ELb" in l)):
                 print(name, "E" if "ELb1" in l else "H", " | ".join(x.strip() for x in lines[n + 1:n + 4]))
 
 
