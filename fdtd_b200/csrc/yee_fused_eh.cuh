@@ -16,15 +16,16 @@
 // (tests/test_gpu_parity.py::test_temporally_fused_steps_equal_two_half_steps).
 //
 // STATUS (round 1): correct, opt-in (FDTD_B200_FUSE_EH=1), NOT yet faster.  1024^3 f32 on one B200
-// (profiles/r1_fused_eh_launches.csv): the fused kernel moves 51.8 GB in 10.8 ms (4.8 TB/s -- the barrier per
-// plane and 18 warps per SM hide latency worse than the barrier-free streaming kernel's 6.1 TB/s), the twelve
-// shell launches add 2.6 ms, 1.7 ms of which in the two 12-cell-wide z strips whose 48-byte rows waste DRAM
-// sectors 4x.  13.5 ms per step against 12.7 ms for the two half-steps.  To win it needs a deeper load pipeline
-// in the fused kernel (register or TMA prefetch across the barrier) and z strips handled inside it.
+// (profiles/r1_fused_eh_launches.csv, 16x16 tile): the fused kernel moves 51.8 GB in 10.8 ms (4.8 TB/s -- the
+// barrier per plane hides latency worse than the barrier-free streaming kernel's 6.1 TB/s), the twelve shell
+// launches add 2.6 ms, 1.7 ms of which in the two 12-cell-wide z strips whose 48-byte rows waste DRAM sectors
+// 4x.  Best tile (4x32 lanes): 12.8 ms per step against 12.7 ms for the two half-steps.  Tried without gain:
+// L2 prefetch, 3 blocks/SM, register prefetch of the next plane across the barrier (spills).  To win it needs
+// the inputs staged by TMA / cp.async in shared memory and the z strips handled inside the fused kernel.
 #pragma once
 
 #ifndef FDTD_FUSED_MIN_BLOCKS
-#define FDTD_FUSED_MIN_BLOCKS 2
+#define FDTD_FUSED_MIN_BLOCKS 4
 #endif
 #ifndef FDTD_FUSED_PREFETCH
 #define FDTD_FUSED_PREFETCH 0   // L2 prefetch of the six input streams this many planes ahead (measured: hurts)
@@ -47,8 +48,16 @@ struct FusedParams {
   SrcK<T> src[FDTD_FUSED_MAX];  // soft point-list sources on E (ascending idx)
 };
 
-constexpr int FUSED_R = 16;  // core rows per block
-constexpr int FUSED_L = 16;  // core vector lanes per block
+// core tile of a block: measured on B200 at 1024^3 f32 (ms per fused step incl. shell): 16x16 lanes 13.5,
+// 8x16 13.2, 8x32 13.2, 4x32 12.8 -- small barrier domains matter more than the halo redundancy
+#ifndef FDTD_FUSED_ROWS
+#define FDTD_FUSED_ROWS 4
+#endif
+#ifndef FDTD_FUSED_LANES
+#define FDTD_FUSED_LANES 32
+#endif
+constexpr int FUSED_R = FDTD_FUSED_ROWS;   // core rows per block
+constexpr int FUSED_L = FDTD_FUSED_LANES;  // core vector lanes per block
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_MIN_BLOCKS)

@@ -21,6 +21,17 @@ VARIANTS = {
     "post_inline": ["-DFDTD_POST_INLINE=1"],
     "hdown": ["-DFDTD_H_DOWNWARD=1"],
     "fz_pf0": ["-DFDTD_FUSED_PREFETCH=0"],
+    "fzp_r16_mb2": [],
+    "fzp_r16_mb1": ["-DFDTD_FUSED_MIN_BLOCKS=1"],
+    "fzp_r4l32_mb3": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=3"],
+    "fzp_r4l32_mb4": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=4"],
+    "fzp_r8l16_mb3": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_MIN_BLOCKS=3"],
+    "fzp_r2l32_mb5": ["-DFDTD_FUSED_ROWS=2", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=5"],
+    "fznp_r4l32_mb4": ["-DFDTD_FUSED_PIPELINE=0", "-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=4"],
+    "fz_r8": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_MIN_BLOCKS=4"],
+    "fz_r8_l32": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=2"],
+    "fz_r4_l32": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=4"],
+    "fz_r8_mb3": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_MIN_BLOCKS=3"],
     "fz_pf2": ["-DFDTD_FUSED_PREFETCH=2"],
     "fz_mb3": ["-DFDTD_FUSED_MIN_BLOCKS=3"],
     "fz_mb3_pf2": ["-DFDTD_FUSED_MIN_BLOCKS=3", "-DFDTD_FUSED_PREFETCH=2"],
