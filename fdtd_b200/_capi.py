@@ -72,6 +72,7 @@ EXPORTS = {
     "fdtd_update_E": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),
     "fdtd_update_H": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, _vp]),
     "fdtd_run": (C.c_int, [C.POINTER(Desc), C.c_int64, C.c_int64, C.c_int64, _vp]),
+    "fdtd_fuse_eh_active": (C.c_int, [C.POINTER(Desc)]),
     "fdtd_ipc_export": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64)]),
     "fdtd_ipc_import": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "fdtd_halfstep_push": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,

@@ -907,6 +907,17 @@ int graph_for(const fdtd_desc* d, cudaGraphExec_t* out) {
 }  // namespace
 #endif
 
+int fdtd_fuse_eh_active(const fdtd_desc* d) {
+  int rc = validate(d);
+  if (rc) return rc;
+#ifndef FDTD_EMU
+  InteriorBox box;
+  return fuse_eh_eligible(d, &box) ? 1 : 0;
+#else
+  return 0;
+#endif
+}
+
 int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void* stream) {
   int rc = validate(d);
   if (rc) return rc;

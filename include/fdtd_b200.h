@@ -222,6 +222,10 @@ int fdtd_update_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
  * samples of step q0+s go to ring slot slot0+s */
 int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void* stream);
 
+/* 1 when fdtd_run will execute pairs of temporally fused E+H steps for this descriptor (fuse_eh set, second
+ * buffers given, homogeneous unsharded grid, point sources on E only, a large enough CPML-free interior) */
+int fdtd_fuse_eh_active(const fdtd_desc* d);
+
 /* --- direct peer-to-peer halo exchange (x-sharded grids, one process per GPU) -------------------------
  * No reference counterpart (the reference is single-device).  Each rank exports its field storage and a
  * two-word flag array with CUDA IPC; neighbours import them and get peer pointers that the kernels below

@@ -278,8 +278,8 @@ def test_random_scene_on_gpu(seed, dtype):
     compare(got, want, TOL[dtype], bitwise=not inexact_overlaps(o))
 
 
-@pytest.mark.parametrize("dtype,n,t", [("float32", (72, 64, 96), 6), ("float64", (40, 52, 44), 5),
-                                       ("float32", (33, 41, 68), 3)])
+@pytest.mark.parametrize("dtype,n,t", [("float32", (72, 64, 192), 6), ("float64", (40, 52, 100), 5),
+                                       ("float32", (33, 41, 148), 3)])
 def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
     """run() with FDTD_B200_FUSE_EH: pairs of single-pass E+H steps on the interior (ping-pong buffers, shared-
     memory exchange of E_new, ordinary kernels on the PML shell) must reproduce the two-half-step path bit for
@@ -307,7 +307,7 @@ def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
         g.run(31, progress_bar=False)
         g.step()
         g.run(10, progress_bar=False)
-        assert bool(g._engine.desc.fuse_eh) == fuse
+        assert bool(g._engine.lib.fdtd_fuse_eh_active(g._engine.desc)) == fuse
         outs.append(scenes.dump(g))
     assert float(np.abs(outs[0]["E"]).max()) > 0
     compare(outs[1], outs[0], 0.0, bitwise=True)
