@@ -47,6 +47,14 @@ class _Detector:
         self._pos = torch.as_tensor(pos, dtype=torch.int32, device=bd.device)
         self._positions = mine[order]                         # global list positions, sampling order
         self._bbox = bounding_box(self.grid, lin)
+        # which list positions every rank owns (the partition is known to all): lets a flush be ONE fixed-size
+        # all_gather of the ring chunks instead of pickled objects
+        part = self.grid._part
+        if part.sharded:
+            gx = np.asarray(xs, dtype=np.int64)
+            gx = np.where(gx < 0, gx + self.grid.Nx, gx)
+            self._rank_positions = [np.nonzero((gx >= part.bounds(r)[0]) & (gx < part.bounds(r)[1]))[0]
+                                    for r in range(part.world)]
 
     def _ensure_ring(self, capacity):
         if self._ring_E is None or self._capacity != capacity:
@@ -63,15 +71,18 @@ class _Detector:
         for f, ring, n in (("E", self._ring_E, nE), ("H", self._ring_H, nH)):
             if n == 0 or f not in self._chunks:
                 continue
-            local = ring[:n, :self._n_local].to("cpu", copy=True).numpy()
             if part.sharded:
-                gathered = [None] * part.world
-                dist.all_gather_object(gathered, (self._positions, local))
-                full = np.zeros((n, self._n_points, self._width), dtype=local.dtype)
-                for pos, vals in gathered:
-                    full[:, pos] = vals
+                n_max = max(1, max(len(p) for p in self._rank_positions))
+                send = ring.new_zeros((n, n_max, self._width))
+                send[:, :self._n_local] = ring[:n, :self._n_local]
+                recv = [torch.empty_like(send) for _ in range(part.world)]
+                dist.all_gather(recv, send)
+                recv = torch.stack(recv).to("cpu").numpy()
+                full = np.zeros((n, self._n_points, self._width), dtype=recv.dtype)
+                for r, pos in enumerate(self._rank_positions):
+                    full[:, pos] = recv[r, :, :len(pos)]
             else:
-                full = local
+                full = ring[:n, :self._n_local].to("cpu", copy=True).numpy()
             tail = (self._width,) if self._width > 1 else ()
             self._chunks[f].append(full.reshape((n,) + self._sample_shape + tail))
             self._lists[f] = None
