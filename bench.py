@@ -5,7 +5,7 @@
 
 Workload (config.workload): BASELINE.json configs[3] -- 3-D S^3 (default 1024^3) float32 grid, 10-cell
 PML on all six faces, PointSource(period=20) at the centre, one LineDetector; strong scaling over x-slabs
-for N > 1 (one process per GPU, launched by torchrun; NCCL halo exchange).  A "step" is one full
+for N > 1 (one process per GPU, launched by torchrun; peer-to-peer ghost-plane stores over NVLink, NCCL fallback).  A "step" is one full
 E+H update of the whole grid including PML, source and detector work.
 
 Printed JSON (one line, rank 0):

@@ -841,8 +841,8 @@ __global__ void halo_signal_kernel(i64* peer_flag, i64 value) {
   }
 }
 
-// consume: spin until the local flag (written by the neighbour) reaches `value`; gives up after ~2^32 cycles
-// and raises *error instead of hanging the GPU if the neighbour died
+// consume: spin until the local flag (written by the neighbour) reaches `value`; gives up after 2^34 cycles
+// (~9 s) and raises *error instead of hanging the GPU if the neighbour died
 __global__ void halo_wait_kernel(const i64* flag, i64 value, int* error) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const long long t0 = clock64();
@@ -850,7 +850,7 @@ __global__ void halo_wait_kernel(const i64* flag, i64 value, int* error) {
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
       if (v >= value) break;
-      if (clock64() - t0 > (1LL << 32)) {
+      if (clock64() - t0 > (1LL << 34)) {
         *error = 1;
         break;
       }

@@ -245,7 +245,7 @@ int fdtd_halfstep_push(const fdtd_desc* d, int32_t field, int32_t x_begin, int32
 int fdtd_halo_push(const fdtd_desc* d, int32_t field, void* peer_ghost_y, void* peer_ghost_z, void* stream);
 /* publish `value` in the neighbour's flag after everything enqueued before on `stream` (release, system scope) */
 int fdtd_halo_signal(int64_t* peer_flag, int64_t value, void* stream);
-/* make `stream` wait until the local flag reaches `value` (acquire, system scope); after ~2 s of spinning it
+/* make `stream` wait until the local flag reaches `value` (acquire, system scope); after ~9 s of spinning it
  * gives up and sets *error (device int) instead of hanging */
 int fdtd_halo_wait(const int64_t* flag, int64_t value, int32_t* error, void* stream);
 

@@ -219,3 +219,26 @@ def test_zero_step_run_and_empty_detector(fd, grid):
     grid.run(2.5 * grid.time_step, progress_bar=False)      # float seconds truncate to steps (fdtd/grid.py:259-261)
     assert grid.time_steps_passed == 2
     assert np.array(grid.empty.E).shape == (2, 0, 3)
+
+
+def test_partition_balances_plane_cost():
+    """x-slabs: equal plane counts by default, equal cumulative cost when planes are priced (x-PML planes move
+    13 instead of 9 words per cell and half-step)."""
+    from fdtd_b200.sharding import Partition
+
+    class P(Partition):
+        def __init__(self, Nx, world, cost=None):
+            self.Nx, self.world, self.rank = Nx, world, 0
+            self._cuts = self._balanced_cuts(cost)
+
+    assert P(1024, 8)._cuts == [0, 128, 256, 384, 512, 640, 768, 896, 1024]
+    assert P(10, 3)._cuts == [0, 4, 7, 10]
+    cost = [13 / 9 if (i < 10 or i >= 1014) else 1.0 for i in range(1024)]
+    cuts = P(1024, 8, cost)._cuts
+    sizes = [b - a for a, b in zip(cuts, cuts[1:])]
+    assert sizes[0] == sizes[-1] < sizes[3] and sum(sizes) == 1024
+    work = [sum(cost[a:b]) for a, b in zip(cuts, cuts[1:])]
+    assert max(work) - min(work) < 1.5                                   # within one plane of each other
+    assert P(5, 5, [1, 1, 10, 1, 1])._cuts == [0, 1, 2, 3, 4, 5]         # never an empty slab
+    with pytest.raises(ValueError):
+        P(4, 2, [1, 1, 1])
