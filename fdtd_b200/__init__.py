@@ -10,7 +10,8 @@ Drop-in for the reference's hot path and nothing else:
     grid.run(200)
 
 `Grid(...)`, `grid[...] = PML / PeriodicBoundary / Object / AbsorbingObject / AnisotropicObject /
-PointSource / LineSource / PlaneSource / LineDetector / BlockDetector`, `grid.run() / step() /
+PointSource / LineSource / PlaneSource / SoftArbitraryPointSource / LineDetector / BlockDetector /
+CurrentDetector`, `FrequencyRoutines`, `grid.run() / step() /
 update_E() / update_H() / reset()`, `grid.E / grid.H` and the detector outputs behave as in the
 reference (fdtd/__init__.py:6-14); each half-step is one fused sm_100a CUDA kernel reached
 through the C ABI of include/fdtd_b200.h.  There is no CPU fallback.
@@ -23,4 +24,5 @@ from .sources import PointSource, LineSource, PlaneSource, SoftArbitraryPointSou
 from .detectors import LineDetector, BlockDetector, CurrentDetector
 from .objects import Object, AbsorbingObject, AnisotropicObject
 from .boundaries import PeriodicBoundary, PML, DomainBorderPML
-from . import constants, waveforms
+from .fourier import FrequencyRoutines
+from . import constants, conversions, waveforms

@@ -6,10 +6,10 @@ loudly when it is missing: there is no CPU or PyTorch fallback for the hot path.
 import ctypes as C
 import os
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_SLABS, MAX_POST, MAX_SOURCES, MAX_DETECTORS, FUSED_MAX = 6, 16, 64, 64, 6
 F32, F64 = 0, 1
-CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT, CLS_ANISO, CLS_OVERLAP = 1, 2, 4, 8, 16, 32
+CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT, CLS_ANISO, CLS_OVERLAP, CLS_ABSORB2 = 1, 2, 4, 8, 16, 32, 64
 POST_PERIODIC, POST_PML_ADD = 0, 1
 SRC_POINTS, SRC_BOX, SRC_FEEDBACK = 0, 1, 2
 DET_FIELD, DET_CURRENT = 0, 1
@@ -44,7 +44,8 @@ class Desc(C.Structure):
                 ("plane", C.c_int64),
                 ("E", _vp * 3), ("H", _vp * 3),
                 ("courant", C.c_double), ("bg_inv_eps", C.c_double * 3), ("bg_inv_mu", C.c_double * 3),
-                ("inv_eps", _vp * 3), ("inv_eps2", _vp * 3), ("inv_eps_grid", _vp * 3), ("absorb", _vp * 3), ("inv_mu", _vp * 3),
+                ("inv_eps", _vp * 3), ("inv_eps2", _vp * 3), ("inv_eps_grid", _vp * 3), ("absorb", _vp * 3), ("absorb2", _vp * 3),
+                ("inv_mu", _vp * 3),
                 ("tile_class", _vp), ("tile_y", C.c_int32), ("tile_z", C.c_int32),
                 ("n_slabs", C.c_int32), ("n_post", C.c_int32),
                 ("slabs", Slab * MAX_SLABS),

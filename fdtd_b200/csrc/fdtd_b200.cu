@@ -158,8 +158,9 @@ int validate(const fdtd_desc* d) {
     if (!d->E[c] || !d->H[c]) return fail(FDTD_ERR_ARG, "null field pointer");
     if (!aligned(d->E[c], w * g.vec) || !aligned(d->H[c], w * g.vec))
       return fail(FDTD_ERR_ARG, "field pointer not aligned to %zu bytes", w * g.vec);
-    const void* opt[5] = {d->inv_eps[c], d->inv_eps_grid[c], d->absorb[c], d->inv_mu[c], d->inv_eps2[c]};
-    for (int n = 0; n < 5; ++n)
+    const void* opt[6] = {d->inv_eps[c], d->inv_eps_grid[c], d->absorb[c], d->inv_mu[c], d->inv_eps2[c],
+                          d->absorb2[c]};
+    for (int n = 0; n < 6; ++n)
       if (opt[n] && !aligned(opt[n], w * g.vec)) return fail(FDTD_ERR_ARG, "material pointer misaligned");
   }
   bool any_e = d->inv_eps[0] || d->inv_eps[1] || d->inv_eps[2];
@@ -342,6 +343,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
     P.inv_grid[c] = IS_E ? (const T*)d->inv_eps_grid[c] : nullptr;
     P.inv2[c] = IS_E ? (const T*)d->inv_eps2[c] : nullptr;
     P.absorb[c] = IS_E ? (const T*)d->absorb[c] : nullptr;
+    P.absorb2[c] = IS_E ? (const T*)d->absorb2[c] : nullptr;
     if (shell) {
       P.F[c] = (T*)shell->Fin[c];
       P.Fo[c] = (T*)shell->Fout[c];

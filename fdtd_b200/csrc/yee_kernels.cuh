@@ -171,6 +171,7 @@ struct HalfStepParams {
   const T* inv2[3];      // second object covering a cell (overlaps), or null
   const T* inv_grid[3];  // grid's own eps^-1 for the PML correction, or null (= inv)
   const T* absorb[3];    // absorption factor, or null
+  const T* absorb2[3];   // absorption factor of the second object covering a cell, or null
   const unsigned char* cls;
   unsigned char cls_vary;  // FDTD_CLS_VARY_E or FDTD_CLS_VARY_H
   int n_slabs;
@@ -308,10 +309,18 @@ struct CellState {
 
 // E update of the cells of a tile that an AbsorbingObject, an AnisotropicObject or overlapping objects touch
 // (fdtd/objects.py:118-129, 207-221, 254-269).  C.c* = sc * effective eps^-1 as computed by the caller.
+//
+// The reference updates every object in registration order; a cell covered by two objects gets two updates.
+// The host bakes the first object covering a cell into layer 1 (inv / absorb) and the second into layer 2
+// (inv2 / absorb2); each layer is applied exactly as its object kind does it:
+//   plain        E += (sc*eps^-1) * curl
+//   anisotropic  E += sc * (eps^-1 * curl)         the product with curl is rounded BEFORE the scaling by sc;
+//                                                   marked by a NEGATIVE zero in the grid's eps^-1: x-component
+//                                                   for layer 1, y-component for layer 2
+//   absorbing    E *= (1-f)/(1+f); E += (sc*eps^-1)*curl / (1+f)      (f = 0 gives the plain update bit for bit)
 template <typename T, int VEC>
 FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC>& C, i64 off, unsigned cls) {
   T tx[VEC], ty[VEC], tz[VEC], ux[VEC], uy[VEC], uz[VEC];
-  bool aniso[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
     ux[e] = C.d_zy[e] - C.d_yz[e];
@@ -320,16 +329,12 @@ FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC
     tx[e] = C.cx[e] * ux[e];
     ty[e] = C.cy[e] * uy[e];
     tz[e] = C.cz[e] * uz[e];
-    aniso[e] = false;
   }
   if (cls & FDTD_CLS_ANISO) {
-    // AnisotropicObject cells: E += sc * (eps^-1 @ curl) -- the product with curl is rounded BEFORE the
-    // scaling by sc (fdtd/objects.py:262-269); they are marked by a NEGATIVE zero in the grid's eps^-1
     const Pack<T, VEC> mark = ldv<T, VEC>(P.inv_grid[0] + off);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      aniso[e] = (mark.v[e] == T(0)) && fdtd_signbit(mark.v[e]);
-      if (aniso[e]) {
+      if ((mark.v[e] == T(0)) && fdtd_signbit(mark.v[e])) {
         const bool vary = (cls & P.cls_vary) != 0;
         tx[e] = P.sc * ((vary ? P.inv[0][off + e] : P.bg_inv[0]) * ux[e]);
         ty[e] = P.sc * ((vary ? P.inv[1][off + e] : P.bg_inv[1]) * uy[e]);
@@ -337,8 +342,8 @@ FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC
       }
     }
   }
+  // ---- layer 1
   if (cls & FDTD_CLS_ABSORB) {
-    // E *= (1-f)/(1+f); E += sc*eps^-1*curl/(1+f)        fdtd/objects.py:214-221
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const T q0 = P.absorb[0][off + e], q1 = P.absorb[1][off + e], q2 = P.absorb[2][off + e];
@@ -357,15 +362,41 @@ FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC
       C.fz[e] = C.fz[e] + tz[e];
     }
   }
+  // ---- layer 2
   if (cls & FDTD_CLS_OVERLAP) {
-    // a second object on the same cell adds its own term afterwards (fdtd/objects.py:127-129); absorbers never
-    // overlap anything, so in their cells this adds zero
+    bool aniso2[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) aniso2[e] = false;
+    if (cls & FDTD_CLS_ANISO) {
+      const Pack<T, VEC> mark2 = ldv<T, VEC>(P.inv_grid[1] + off);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) aniso2[e] = (mark2.v[e] == T(0)) && fdtd_signbit(mark2.v[e]);
+    }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const T b0 = P.inv2[0][off + e], b1 = P.inv2[1][off + e], b2 = P.inv2[2][off + e];
-      C.fx[e] = C.fx[e] + (aniso[e] ? P.sc * (b0 * ux[e]) : (P.sc * b0) * ux[e]);
-      C.fy[e] = C.fy[e] + (aniso[e] ? P.sc * (b1 * uy[e]) : (P.sc * b1) * uy[e]);
-      C.fz[e] = C.fz[e] + (aniso[e] ? P.sc * (b2 * uz[e]) : (P.sc * b2) * uz[e]);
+      tx[e] = aniso2[e] ? P.sc * (b0 * ux[e]) : (P.sc * b0) * ux[e];
+      ty[e] = aniso2[e] ? P.sc * (b1 * uy[e]) : (P.sc * b1) * uy[e];
+      tz[e] = aniso2[e] ? P.sc * (b2 * uz[e]) : (P.sc * b2) * uz[e];
+    }
+    if (cls & FDTD_CLS_ABSORB2) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T q0 = P.absorb2[0][off + e], q1 = P.absorb2[1][off + e], q2 = P.absorb2[2][off + e];
+        C.fx[e] = C.fx[e] * ((T(1) - q0) / (T(1) + q0));
+        C.fy[e] = C.fy[e] * ((T(1) - q1) / (T(1) + q1));
+        C.fz[e] = C.fz[e] * ((T(1) - q2) / (T(1) + q2));
+        C.fx[e] = C.fx[e] + tx[e] / (T(1) + q0);
+        C.fy[e] = C.fy[e] + ty[e] / (T(1) + q1);
+        C.fz[e] = C.fz[e] + tz[e] / (T(1) + q2);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        C.fx[e] = C.fx[e] + tx[e];
+        C.fy[e] = C.fy[e] + ty[e];
+        C.fz[e] = C.fz[e] + tz[e];
+      }
     }
   }
 }
@@ -569,7 +600,7 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     }
 
     // ---- field update ----------------------------------------------------------------------
-    if (IS_E && (cls & (FDTD_CLS_ABSORB | FDTD_CLS_ANISO | FDTD_CLS_OVERLAP))) {
+    if (IS_E && (cls & (FDTD_CLS_ABSORB | FDTD_CLS_ANISO | FDTD_CLS_OVERLAP | FDTD_CLS_ABSORB2))) {
       // tiles an AbsorbingObject, an AnisotropicObject or two overlapping objects touch: out-of-line, so that
       // their registers and divisions do not burden the streaming path
       CellState<T, VEC> C;

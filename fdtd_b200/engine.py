@@ -96,33 +96,58 @@ class Engine:
 
         # --- materials ------------------------------------------------------------------------
         ie_grid, imu = g._inv_eps, g._inv_mu
-        ie_eff, absorb, ie2 = ie_grid, None, None
+        ie_eff, absorb, ie2, absorb2 = ie_grid, None, None, None
         if g.objects:
+            # The reference updates every object in registration order (fdtd/grid.py:285-287), so a cell covered
+            # by two objects gets two updates.  The first object covering a cell becomes coefficient layer 1
+            # (ie_eff / absorb), the second one layer 2 (ie2 / absorb2); a third one is summed into layer 2
+            # (exact only to rounding; refused at registration when an absorber is involved).  Anisotropic
+            # layers are marked by a negative zero in the grid's eps^-1 (x-component: layer 1, y: layer 2).
+            from .objects import AnisotropicObject
             ie_eff = ie_grid.clone()
-            # overlapping objects each add their own term in the reference (fdtd/objects.py:127-129): the first
-            # one covering a cell goes into ie_eff, the second into ie2 (further ones are summed into ie2)
             boxes = [(o.x, o.y, o.z) for o in g.objects]
             overlaps = any(all(max(p.start, q.start) < min(p.stop, q.stop) for p, q in zip(boxes[a], boxes[b]))
                            for a in range(len(boxes)) for b in range(a + 1, len(boxes)))
             cover = torch.zeros(ie_grid.shape[1:], dtype=torch.int8, device=ie_grid.device) if overlaps else None
+
+            def mark(comp, loc, cells, aniso):
+                region = ie_grid[comp][loc]
+                sel = (region == 0) if cells is None else (cells & (region == 0))
+                ie_grid[comp][loc] = torch.where(sel, torch.full_like(region, -0.0 if aniso else 0.0), region)
+
             for o in g.objects:
                 if o._nx_local == 0:
                     continue
                 loc = (slice(None),) + o._loc
+                aniso = isinstance(o, AnisotropicObject)
                 if cover is None:
                     ie_eff[loc] += o._inv_eps_soa
-                else:
-                    first = (cover[o._loc] == 0).unsqueeze(0)
-                    ie_eff[loc] += torch.where(first, o._inv_eps_soa, torch.zeros_like(o._inv_eps_soa))
-                    if not bool(first.all()):
-                        if ie2 is None:
-                            ie2 = torch.zeros_like(ie_grid)
-                        ie2[loc] += torch.where(first, torch.zeros_like(o._inv_eps_soa), o._inv_eps_soa)
-                    cover[o._loc] += 1
+                    mark(0, o._loc, None, aniso)
+                    if o._absorb_soa is not None:
+                        if absorb is None:
+                            absorb = torch.zeros_like(ie_grid)
+                        absorb[loc] = o._absorb_soa
+                    continue
+                depth = cover[o._loc]
+                first, second = depth == 0, depth == 1
+                zero = torch.zeros_like(o._inv_eps_soa)
+                ie_eff[loc] += torch.where(first.unsqueeze(0), o._inv_eps_soa, zero)
+                mark(0, o._loc, first, aniso)
+                if not bool(first.all()):
+                    if ie2 is None:
+                        ie2 = torch.zeros_like(ie_grid)
+                    ie2[loc] += torch.where(first.unsqueeze(0), zero, o._inv_eps_soa)
+                    mark(1, o._loc, second, aniso)
                 if o._absorb_soa is not None:
-                    if absorb is None:
-                        absorb = torch.zeros_like(ie_grid)
-                    absorb[(slice(None),) + o._loc] = o._absorb_soa
+                    if bool(first.any()):
+                        if absorb is None:
+                            absorb = torch.zeros_like(ie_grid)
+                        absorb[loc] = torch.where(first.unsqueeze(0), o._absorb_soa, absorb[loc])
+                    if bool(second.any()):
+                        if absorb2 is None:
+                            absorb2 = torch.zeros_like(ie_grid)
+                        absorb2[loc] = torch.where(second.unsqueeze(0), o._absorb_soa, absorb2[loc])
+                cover[o._loc] += 1
         self._mat_versions = (None if ie_grid is None else ie_grid._version,
                               None if imu is None else imu._version)
         ty, tz = C.c_int32(), C.c_int32()
@@ -130,15 +155,16 @@ class Engine:
         d.tile_y, d.tile_z = ty.value, tz.value
         cls = None
         if ie_eff is not None or imu is not None:
-            cls = self._classify(ie_eff, ie_grid if g.objects else None, absorb, imu, ty.value, tz.value, ie2)
+            cls = self._classify(ie_eff, ie_grid if g.objects else None, absorb, imu, ty.value, tz.value, ie2, absorb2)
         for c in range(3):
             d.inv_eps[c] = ie_eff[c].data_ptr() if ie_eff is not None else None
             d.inv_eps2[c] = ie2[c].data_ptr() if ie2 is not None else None
             d.inv_eps_grid[c] = ie_grid[c].data_ptr() if (g.objects and ie_grid is not None) else None
             d.absorb[c] = absorb[c].data_ptr() if absorb is not None else None
+            d.absorb2[c] = absorb2[c].data_ptr() if absorb2 is not None else None
             d.inv_mu[c] = imu[c].data_ptr() if imu is not None else None
         d.tile_class = _ptr(cls)
-        self._keep += [ie_eff, absorb, cls, ie2]
+        self._keep += [ie_eff, absorb, cls, ie2, absorb2]
         self.tile_class = cls
 
         # --- sources ----------------------------------------------------------------------------
@@ -312,7 +338,7 @@ class Engine:
             _capi.check(lib, lib.fdtd_halo_signal(C.c_void_p(flag), h.count[field] + 1, sst))
         h.count[field] += 1
 
-    def _classify(self, ie_eff, ie_grid_if_objects, absorb, imu, ty, tz, ie2=None):
+    def _classify(self, ie_eff, ie_grid_if_objects, absorb, imu, ty, tz, ie2=None, absorb2=None):
         """per-(plane, y-tile, z-tile) class byte, FDTD_CLS_* (include/fdtd_b200.h)."""
         g = self.grid
         nx, Ny, Nz = g._part.nx, g.Ny, g.Nz
@@ -338,11 +364,13 @@ class Engine:
                 bits |= tiles((absorb[:, a:b] != 0).any(0)).to(torch.uint8) * _capi.CLS_ABSORB
             if ie2 is not None:
                 bits |= tiles((ie2[:, a:b] != 0).any(0)).to(torch.uint8) * _capi.CLS_OVERLAP
+            if absorb2 is not None:
+                bits |= tiles((absorb2[:, a:b] != 0).any(0)).to(torch.uint8) * _capi.CLS_ABSORB2
             if ie_grid_if_objects is not None:
                 bits |= tiles(((ie_eff[:, a:b] != ie_grid_if_objects[:, a:b])
                                | (False if ie2 is None else ie2[:, a:b] != 0)).any(0)).to(torch.uint8) * _capi.CLS_OBJECT
-                gx = ie_grid_if_objects[0, a:b]
-                bits |= tiles((gx == 0) & torch.signbit(gx)).to(torch.uint8) * _capi.CLS_ANISO
+                gx = ie_grid_if_objects[0:2, a:b]
+                bits |= tiles(((gx == 0) & torch.signbit(gx)).any(0)).to(torch.uint8) * _capi.CLS_ANISO
             cls[a:b] = bits
         return cls.contiguous()
 

@@ -26,16 +26,16 @@ class Object:
         self.permittivity = bd.require().array(permittivity)
 
     def _register_grid(self, grid, x, y, z):
-        self.grid = grid
-        self.grid.objects.append(self)
-        grid._register_name(self)
         self.x = self._handle_slice(x, max_index=grid.Nx)
         self.y = self._handle_slice(y, max_index=grid.Ny)
         self.z = self._handle_slice(z, max_index=grid.Nz)
         self.Nx = abs(self.x.stop - self.x.start)
         self.Ny = abs(self.y.stop - self.y.start)
         self.Nz = abs(self.z.stop - self.z.start)
-        self._check_overlap()
+        self._check_overlap(grid)                # before the grid learns about this object
+        self.grid = grid
+        self.grid.objects.append(self)
+        grid._register_name(self)
 
         part = grid._part
         lx0, lx1 = part.local_range(self.x.start, self.x.stop)
@@ -65,9 +65,9 @@ class Object:
         self._inv_eps_soa = inv.permute(3, 0, 1, 2).contiguous() # (3, nx_local, Ny, Nz) for the bake
         self._absorb_soa = None
         if self._nx_local > 0:
-            # zero inside the object (fdtd/objects.py:92); a NEGATIVE zero marks AnisotropicObject cells for the
-            # kernel (include/fdtd_b200.h, FDTD_CLS_ANISO) -- numerically it is the same zero everywhere
-            gi[:, lx0:lx1, self.y, self.z] = -0.0 if isinstance(self, AnisotropicObject) else 0.0
+            # zero inside the object (fdtd/objects.py:92); the bake later turns the zeros of AnisotropicObject
+            # cells into NEGATIVE zeros as a marker for the kernel (include/fdtd_b200.h, FDTD_CLS_ANISO)
+            gi[:, lx0:lx1, self.y, self.z] = 0.0
 
     def _grid_last_x_plane(self, gi):
         """grid.inverse_permittivity[-1, y, z, 0] -- lives on the last rank when sharded."""
@@ -78,15 +78,19 @@ class Object:
         dist.broadcast(buf, src=part.world - 1)
         return buf
 
-    def _check_overlap(self):
-        """Overlapping plain objects both add their term (fdtd/objects.py:127-129) and are summed
-        exactly; an AbsorbingObject overlapping anything is order-dependent in the reference and is
-        refused here."""
-        for other in self.grid.objects[:-1]:
-            inter = all(max(a.start, b.start) < min(a.stop, b.stop)
-                        for a, b in ((self.x, other.x), (self.y, other.y), (self.z, other.z)))
-            if inter and (isinstance(self, AbsorbingObject) or isinstance(other, AbsorbingObject)):
-                raise NotImplementedError("an AbsorbingObject overlapping another object")
+    def _check_overlap(self, grid):
+        """Each object covering a cell adds its own update, in registration order (fdtd/grid.py:285-287).  Two
+        objects on one cell are reproduced exactly, whatever their kinds; three plain / anisotropic ones to
+        rounding; three with an AbsorbingObject among them are order-dependent beyond that and refused."""
+        def meet(*objs):
+            return all(max(s.start for s in ax) < min(s.stop for s in ax)
+                       for ax in zip(*((o.x, o.y, o.z) for o in objs)))
+
+        earlier = list(grid.objects)
+        for n, a in enumerate(earlier):
+            for b in earlier[n + 1:]:
+                if meet(self, a, b) and any(isinstance(o, AbsorbingObject) for o in (self, a, b)):
+                    raise NotImplementedError("three objects, one of them an AbsorbingObject, on the same cells")
 
     def _handle_slice(self, s, max_index: int = None) -> slice:
         if isinstance(s, list):

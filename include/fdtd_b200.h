@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 10
+#define FDTD_ABI_VERSION 11
 
 #define FDTD_F32 0
 #define FDTD_F64 1
@@ -61,10 +61,13 @@ extern "C" {
 #define FDTD_CLS_VARY_H 2   /* mu^-1 differs from the background: stream inv_mu */
 #define FDTD_CLS_ABSORB 4   /* an AbsorbingObject covers part of the tile: stream absorb */
 #define FDTD_CLS_OBJECT 8   /* an Object covers part of the tile: the PML add needs inv_eps_grid */
-#define FDTD_CLS_OVERLAP 32 /* two objects overlap in the tile: the second one's term is added separately (inv_eps2),
-                               as the reference's per-object loop does (fdtd/objects.py:127-129) */
-#define FDTD_CLS_ANISO 16   /* an AnisotropicObject covers part of the tile: its cells (inv_eps_grid x-component
-                               == -0.0) round sc*(eps^-1*curl) like the reference's bmm, not (sc*eps^-1)*curl */
+#define FDTD_CLS_OVERLAP 32 /* two objects overlap in the tile: the second one's update is applied separately (inv_eps2,
+                               absorb2), as the reference's per-object loop does (fdtd/objects.py:127-129) */
+#define FDTD_CLS_ANISO 16   /* an AnisotropicObject covers part of the tile: its cells round sc*(eps^-1*curl) like the
+                               reference's bmm, not (sc*eps^-1)*curl.  They are marked by a NEGATIVE zero in inv_eps_grid:
+                               the x-component when it is the first object covering the cell, the y-component when it is
+                               the second */
+#define FDTD_CLS_ABSORB2 64 /* the second object covering some cell of the tile is an AbsorbingObject: stream absorb2 */
 
 /* post-op kinds, executed in registration order after the fused half-step kernel */
 #define FDTD_POST_PERIODIC 0  /* arg = axis: E[0]=E[-1] after E, H[-1]=H[0] after H  (fdtd/boundaries.py:184-219) */
@@ -159,6 +162,7 @@ typedef struct fdtd_desc {
   const void* inv_eps2[3];     /* eps^-1 of the SECOND object covering a cell (zero elsewhere), or NULL: no overlaps */
   const void* inv_eps_grid[3]; /* the grid's own eps^-1 (zero inside objects, fdtd/objects.py:92) for the PML add; NULL = inv_eps */
   const void* absorb[3];       /* AbsorbingObject absorption factor f (fdtd/objects.py:198-205), zero elsewhere; or NULL */
+  const void* absorb2[3];      /* the same for the SECOND object covering a cell; or NULL */
   const void* inv_mu[3];       /* or NULL */
   const uint8_t* tile_class;   /* device [Nx][tiles_y][tiles_z], or NULL = every tile homogeneous */
   int32_t tile_y, tile_z;      /* tile extents in cells, as returned by fdtd_tile_shape */

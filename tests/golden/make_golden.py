@@ -47,7 +47,8 @@ def load_reference():
     return mod
 
 
-F32_SCENES = ("pml3d", "objects3d", "periodic3d", "c4small", "feed50")
+F32_SCENES = ("pml3d", "objects3d", "periodic3d", "c4small", "feed50", "overlaps3d", "patch_antenna")
+SPECTRA_SCENES = ("patch_antenna",)
 
 
 def main():
@@ -75,6 +76,10 @@ def main():
         assert out["E"].dtype == np.float64
         np.savez_compressed(os.path.join(HERE, f"{name}_f64.npz"), steps=steps, **out)
         print(name, "f64", {k: v.shape for k, v in out.items()})
+        if name in SPECTRA_SCENES:          # FrequencyRoutines on the same run (fdtd/fourier.py)
+            spec = scenes.spectra(ref, g)
+            np.savez_compressed(os.path.join(HERE, f"spectra_{name}.npz"), steps=steps, **spec)
+            print(name, "spectra", {k: v.shape for k, v in spec.items()})
         if name in F32_SCENES:
             torch.set_default_dtype(torch.float32)
             ref.set_backend("torch.float32")

@@ -146,6 +146,77 @@ def feed50(fd, n=(18, 16, 14), t=4):
     return g
 
 
+def overlaps3d(fd, n=(22, 20, 20), t=4):
+    """every pair of object kinds on the same cells (the reference updates each object in registration
+    order, fdtd/grid.py:285-287): absorber+absorber, anisotropic+absorber, plain+anisotropic,
+    absorber+plain, anisotropic+anisotropic, some of them reaching into the PMLs; no cell has three."""
+    g = fd.Grid(shape=n, grid_spacing=77.5e-9)
+    g[0:t, :, :] = fd.PML()
+    g[-t:, :, :] = fd.PML()
+    g[:, 0:t, :] = fd.PML()
+    g[:, -t:, :] = fd.PML()
+    g[:, :, 0:t] = fd.PML()
+    g[:, :, -t:] = fd.PML()
+    rs = np.random.RandomState(11)
+    g[4:9, 4:10, 4:10] = fd.AbsorbingObject(permittivity=2.0, conductivity=2.0e4, name="P")
+    g[7:11, 7:13, 6:12] = fd.AbsorbingObject(permittivity=1.0 + rs.rand(4, 6, 6, 1), conductivity=6.0e3, name="Q")
+    g[11:15, 4:10, 4:10] = fd.AnisotropicObject(permittivity=1.0 + rs.rand(4, 6, 6, 3), name="R")
+    g[13:18, 7:12, 7:13] = fd.AbsorbingObject(permittivity=1.5, conductivity=1.0e4, name="S")
+    g[4:10, 13:18, 4:10] = fd.Object(permittivity=1.0 + rs.rand(6, 5, 6), name="T")
+    g[8:13, 14:19, 8:14] = fd.AnisotropicObject(permittivity=1.0 + rs.rand(5, 5, 6, 3), name="U")
+    g[11:16, 13:17, 12:16] = fd.AbsorbingObject(permittivity=2.2, conductivity=3.0e4, name="V")
+    g[14:18, 14:18, 13:17] = fd.Object(permittivity=3.0, name="W")
+    g[16:20, 3:7, 13:17] = fd.AnisotropicObject(permittivity=1.0 + rs.rand(4, 4, 4, 3), name="X")
+    g[17:21, 5:9, 15:19] = fd.AnisotropicObject(permittivity=1.0 + rs.rand(4, 4, 4, 3), name="Y")
+    g[5, :, :] = fd.PlaneSource(period=18, polarization="y", name="plane")
+    g[10, 10, 10] = fd.PointSource(period=12, amplitude=0.8, name="pt")
+    g[2:20, 8, 8] = fd.LineDetector(name="line")
+    g[11:12, 14:16, 12:13] = fd.BlockDetector(name="block")
+    g[17:18, 5:6, 15:16] = fd.BlockDetector(name="block2")
+    return g
+
+
+def patch_antenna(fd, patch=(20, 14), border=4, steps=240):
+    """the reference's probe-fed patch antenna (tests/test_antenna_impedance.py:18-99) at reduced size and with
+    one copper object per region (the original registers ONE AbsorbingObject instance three times, which
+    fails in the reference itself: the conductivity broadcast of the second shape, fdtd/objects.py:194).
+    Ground plane, substrate in four pieces around the feed column, top plane, a copper via that overlaps the
+    top plane, a SoftArbitraryPointSource with series impedance and a gaussian pulse, PML on all faces.  The
+    original's Z = 50 diverges in the reference itself (the explicit one-step feedback V_out = V_in + Z*I is
+    unstable from Z ~ 1 in simulation units: 1e110 after 240 steps); Z = 0.5 is used here."""
+    nsub = 3
+    spacing = 1.27e-3 / nsub
+    n = (patch[0] + 2 * border, patch[1] + 2 * border, nsub + 2 * border + 2)
+    g = fd.Grid(shape=n, grid_spacing=spacing, permittivity=1.0, permeability=1.0, courant_number=None)
+    pml = fd.PML
+    g[0:border, :, :] = pml(); g[-border:, :, :] = pml()
+    g[:, 0:border, :] = pml(); g[:, -border:, :] = pml()
+    g[:, :, 0:border] = pml(); g[:, :, -border:] = pml()
+    sl = slice(border, -border)
+    ground, top = border, border + 1 + nsub
+
+    def copper():
+        return fd.AbsorbingObject(permittivity=1.0, conductivity=1e8)
+
+    g[sl, sl, ground:ground + 1] = copper()
+    g[sl, sl, top:top + 1] = copper()
+    px, py = patch[0] // 2 + border, patch[1] // 4 + border
+    t = np.arange(steps) * g.time_step
+    fwhm = steps * g.time_step / 5.0
+    sigma = fwhm / 2.355
+    wave = np.exp(-0.5 * ((t - 2.0 * fwhm) / sigma) ** 2)
+    saps = getattr(fd, "SoftArbitraryPointSource", None) or fd.sources.SoftArbitraryPointSource
+    g[px, py, ground + 1] = saps(waveform_array=wave, impedance=0.5)
+    g[px:px + 1, py:py + 1, ground + 2:top + 1] = copper()          # feed via, one cell into the top plane
+    eps_r = 2.42
+    g[border:px, sl, ground + 1:top] = fd.Object(permittivity=eps_r)
+    g[px + 1:-border, sl, ground + 1:top] = fd.Object(permittivity=eps_r)
+    g[px:px + 1, border:py, ground + 1:top] = fd.Object(permittivity=eps_r)
+    g[px:px + 1, py + 1:-border, ground + 1:top] = fd.Object(permittivity=eps_r)
+    g[px + 3, py, ground + 2] = fd.BlockDetector(name="near")
+    return g
+
+
 # name -> (builder, steps)
 SCENES = {
     "quickstart2d": (quickstart2d, 300),
@@ -156,6 +227,8 @@ SCENES = {
     "slab2d_xz": (slab2d_xz, 120),
     "c4small": (c4small, 50),
     "feed50": (feed50, 80),
+    "overlaps3d": (overlaps3d, 60),
+    "patch_antenna": (patch_antenna, 240),
 }
 
 
@@ -186,9 +259,34 @@ def dump(grid):
     return out
 
 
+def spectra(fd, grid):
+    """what a user gets out of FrequencyRoutines (fdtd/fourier.py) for a scene with a SoftArbitraryPointSource
+    and a one-cell BlockDetector: the port impedance, the FFT of the port record, and the FFT of a detector's
+    Ez time trace with and without zero... edge padding."""
+    FR = fd.FrequencyRoutines
+    port = next(s for s in grid.sources if hasattr(s, "source_voltage"))
+    det = next(d for d in grid.detectors if not hasattr(d, "I"))
+    trace = np.array([_np(e)[0, 0, 0, 2] for e in det.E], dtype=np.float64)
+    out = {}
+    for key, (f, v) in {
+        "Z": FR(grid, port).impedance(),
+        "Zpad": FR(grid, port).impedance(fft_num_bins_in_window=3 * len(trace)),
+        "port": FR(grid, port).FFT(),
+        "current": FR(grid, port.current_detector).FFT(),
+        "trace": FR(grid, trace).FFT(),
+        "tracepad": FR(grid, trace).FFT(fft_num_bins_in_window=4 * len(trace)),
+    }.items():
+        out[key + "_f"], out[key] = np.asarray(_np(f), dtype=np.float64), np.asarray(_np(v))
+    return out
+
+
 def rel_l2(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
-    den = np.sqrt((b ** 2).sum())
-    num = np.sqrt(((a - b) ** 2).sum())
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if np.iscomplexobj(a) or np.iscomplexobj(b):
+        a, b = a.astype(np.complex128), b.astype(np.complex128)
+    else:
+        a, b = a.astype(np.float64), b.astype(np.float64)
+    den = np.sqrt((np.abs(b) ** 2).sum())
+    num = np.sqrt((np.abs(a - b) ** 2).sum())
     return num / den if den > 0 else num

@@ -198,3 +198,62 @@ def test_many_sources_fall_back_to_unfused_kernels():
     h = scenes.pml3d(fd, n=(14, 12, 10), t=3)
     h.run(1, progress_bar=False)
     assert h._engine.lib.fdtd_post_is_fused(ctypes.byref(h._engine.desc)) == 1
+
+
+def test_frequency_routines_vs_reference():
+    """FrequencyRoutines (fdtd/fourier.py) on the reduced patch-antenna run: port impedance, FFTs of the port
+    and detector records, with and without padding, against the reference's own outputs (tests/golden/
+    spectra_patch_antenna.npz).  The time-domain records are bit-identical; the transforms (cuFFT / torch here,
+    numpy pocketfft there) agree to rounding."""
+    gold = dict(np.load(os.path.join(GOLD, "spectra_patch_antenna.npz")))
+    steps = int(gold.pop("steps"))
+    fd = use_emu("float64")
+    g = scenes.patch_antenna(fd)
+    g.run(steps, progress_bar=False)
+    fd.FrequencyRoutines.verbose = False
+    got = scenes.spectra(fd, g)
+    assert set(got) == set(gold)
+    for k in gold:
+        assert got[k].shape == gold[k].shape, k
+        if k.endswith("_f"):
+            assert np.array_equal(got[k], gold[k]), k
+        else:
+            assert np.iscomplexobj(got[k])
+            assert scenes.rel_l2(got[k], gold[k]) <= 1e-10, f"{k}: {scenes.rel_l2(got[k], gold[k]):.3e}"
+    # nothing recorded yet: empty results, as the reference
+    g2 = scenes.patch_antenna(fd)
+    assert fd.FrequencyRoutines(g2, g2.detectors[0]).FFT() == ([], [])
+    assert fd.FrequencyRoutines(g2, g2.sources[0]).impedance() == ([], [])
+    with pytest.raises(ValueError):
+        fd.FrequencyRoutines(g, "nonsense").FFT()
+
+
+def test_rebake_with_new_overlapping_objects():
+    """objects registered mid-run on top of existing ones: the layer assignment and the anisotropy markers
+    are rebuilt at every bake."""
+    def drive(fd):
+        g = scenes.pml3d(fd, n=(14, 12, 12), t=3)
+        rs = np.random.RandomState(5)
+        g[4:9, 3:8, 3:9] = fd.AnisotropicObject(permittivity=1.0 + rs.rand(5, 5, 6, 3))
+        g.run(10, progress_bar=False)
+        g[7:11, 5:10, 2:7] = fd.Object(permittivity=2.5)                       # plain over anisotropic
+        g.run(10, progress_bar=False)
+        g[3:6, 6:11, 7:11] = fd.AbsorbingObject(permittivity=1.5, conductivity=2e4)   # absorber over anisotropic
+        g.run(10, progress_bar=False)
+        g[9:12, 8:11, 4:10] = fd.AnisotropicObject(permittivity=1.0 + rs.rand(3, 3, 6, 3))  # anisotropic over plain
+        g.run(10, progress_bar=False)
+        return scenes.dump(g)
+    got = drive(use_emu("float64"))
+    yo.set_backend("numpy", "float64")
+    want = drive(yo)
+    compare(got, want, 1e-12, bitwise=True)
+
+
+def test_three_objects_with_an_absorber_on_one_cell_are_refused():
+    fd = use_emu("float64")
+    g = fd.Grid(shape=(10, 10, 10), grid_spacing=50e-9)
+    g[2:6, 2:6, 2:6] = fd.Object(permittivity=2.0)
+    g[4:8, 4:8, 4:8] = fd.AbsorbingObject(permittivity=2.0, conductivity=1e3)
+    g[1:3, 1:3, 1:3] = fd.Object(permittivity=2.0)                # touches only the first
+    with pytest.raises(NotImplementedError):
+        g[5:9, 5:9, 5:9] = fd.Object(permittivity=3.0)            # third object on cell (5, 5, 5)

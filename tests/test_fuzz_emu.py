@@ -10,8 +10,8 @@ from oracle import yee_oracle as yo
 
 
 def inexact_overlaps(g):
-    """Two overlapping objects of the same kind are reproduced exactly (first and second coefficient layer);
-    three on one cell, or a plain and an anisotropic object on one cell, only to rounding."""
+    """Two objects on one cell are reproduced exactly whatever their kinds (first and second coefficient layer);
+    three on one cell only to rounding (the third is summed into the second layer)."""
     objs = g.objects
     boxes = [(o.x, o.y, o.z) for o in objs]
 
@@ -19,16 +19,8 @@ def inexact_overlaps(g):
         return all(max(s.start for s in axis) < min(s.stop for s in axis) for axis in zip(*bs))
 
     n = len(objs)
-    for a in range(n):
-        for b in range(a + 1, n):
-            if not meet(boxes[a], boxes[b]):
-                continue
-            if type(objs[a]) is not type(objs[b]):
-                return True
-            for c in range(b + 1, n):
-                if meet(boxes[a], boxes[b], boxes[c]):
-                    return True
-    return False
+    return any(meet(boxes[a], boxes[b], boxes[c])
+               for a in range(n) for b in range(a + 1, n) for c in range(b + 1, n))
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])

@@ -311,3 +311,23 @@ def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
         outs.append(scenes.dump(g))
     assert float(np.abs(outs[0]["E"]).max()) > 0
     compare(outs[1], outs[0], 0.0, bitwise=True)
+
+
+@pytest.mark.gpu
+def test_frequency_routines_vs_reference():
+    """FrequencyRoutines (fdtd/fourier.py) on the reduced patch-antenna run, transforms on the device (cuFFT),
+    against the reference's own outputs (tests/golden/spectra_patch_antenna.npz)."""
+    gold = dict(np.load(os.path.join(GOLD, "spectra_patch_antenna.npz")))
+    steps = int(gold.pop("steps"))
+    fd = cuda("float64")
+    g = scenes.patch_antenna(fd)
+    g.run(steps, progress_bar=False)
+    fd.FrequencyRoutines.verbose = False
+    got = scenes.spectra(fd, g)
+    assert set(got) == set(gold)
+    for k in gold:
+        assert got[k].shape == gold[k].shape, k
+        if k.endswith("_f"):
+            assert np.array_equal(got[k], gold[k]), k
+        else:
+            assert scenes.rel_l2(got[k], gold[k]) <= 1e-10, f"{k}: {scenes.rel_l2(got[k], gold[k]):.3e}"
