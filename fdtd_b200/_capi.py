@@ -6,7 +6,7 @@ loudly when it is missing: there is no CPU or PyTorch fallback for the hot path.
 import ctypes as C
 import os
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 MAX_SLABS, MAX_POST, MAX_SOURCES, MAX_DETECTORS, FUSED_MAX = 6, 16, 64, 64, 6
 F32, F64 = 0, 1
 CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT, CLS_ANISO, CLS_OVERLAP, CLS_ABSORB2 = 1, 2, 4, 8, 16, 32, 64
@@ -81,6 +81,7 @@ EXPORTS = {
     "fdtd_halo_push": (C.c_int, [C.POINTER(Desc), C.c_int32, _vp, _vp, _vp]),
     "fdtd_halo_signal": (C.c_int, [_vp, C.c_int64, _vp]),
     "fdtd_halo_wait": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
+    "fdtd_dft_accumulate": (C.c_int, [C.c_int32, _vp, C.c_int64, C.c_int64, _vp, C.c_int32, _vp, _vp]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfdtd_b200.so")

@@ -626,6 +626,7 @@ int fdtd_halfstep_push(const fdtd_desc* d, int32_t field, int32_t x_begin, int32
   int rc = validate(d);
   if (rc) return rc;
   if (!peer_ghost_y || !peer_ghost_z) return fail(FDTD_ERR_ARG, "null peer ghost pointer");
+  if (field != 0 && field != 1) return fail(FDTD_ERR_ARG, "field must be 0 (E) or 1 (H)");
   if (field == 0)
     return d->dtype == FDTD_F32
                ? launch_halfstep<float, true>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z)
@@ -639,6 +640,7 @@ int fdtd_halo_push(const fdtd_desc* d, int32_t field, void* peer_ghost_y, void* 
   int rc = validate(d);
   if (rc) return rc;
   if (!peer_ghost_y || !peer_ghost_z) return fail(FDTD_ERR_ARG, "null peer ghost pointer");
+  if (field != 0 && field != 1) return fail(FDTD_ERR_ARG, "field must be 0 (E) or 1 (H)");
   const int64_t plane_off = field == 0 ? 0 : (int64_t)(d->Nx - 1) * d->plane;
   void* const* F = field == 0 ? d->E : d->H;
   if (d->dtype == FDTD_F32) {
@@ -651,6 +653,23 @@ int fdtd_halo_push(const fdtd_desc* d, int32_t field, void* peer_ghost_y, void* 
                 (double*)peer_ghost_z, (i64)d->plane);
   }
   return check_launch("halo_push");
+}
+
+int fdtd_dft_accumulate(int32_t dtype, const void* ring, int64_t n_steps, int64_t n_values, const double* twiddle,
+                        int32_t n_freqs, double* acc, void* stream) {
+  if (dtype != FDTD_F32 && dtype != FDTD_F64) return fail(FDTD_ERR_ARG, "bad dtype %d", dtype);
+  if (n_steps < 0 || n_values < 0 || n_freqs < 0) return fail(FDTD_ERR_ARG, "fdtd_dft_accumulate: negative size");
+  if (n_steps == 0 || n_values == 0 || n_freqs == 0) return FDTD_OK;
+  if (!ring || !twiddle || !acc) return fail(FDTD_ERR_ARG, "fdtd_dft_accumulate: null pointer");
+  const dim3 grid(blocks_for(n_values * n_freqs)), block(256);
+  if (dtype == FDTD_F32) {
+    FDTD_LAUNCH((fdtd::dft_accumulate_kernel<float>), grid, block, stream, (const float*)ring, (i64)n_steps,
+                (i64)n_values, twiddle, (int)n_freqs, acc);
+  } else {
+    FDTD_LAUNCH((fdtd::dft_accumulate_kernel<double>), grid, block, stream, (const double*)ring, (i64)n_steps,
+                (i64)n_values, twiddle, (int)n_freqs, acc);
+  }
+  return check_launch("dft_accumulate");
 }
 
 #ifdef FDTD_EMU
@@ -849,34 +868,37 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
 #ifndef FDTD_EMU
 // ---- CUDA-graph replay of step chunks (small, launch-bound grids) ---------------------------------
 // One graph = FDTD_GRAPH_STEPS full steps with the fused kernels; the waveform index and ring slot of
-// node s are s + dyn[], and dyn[] is set by a one-thread kernel before each replay.  The executable
-// graph is cached per descriptor content (every pointer and size it bakes in).
+// node s are s + dyn[], and dyn[] is set by a one-thread kernel before each replay.  Executable graphs
+// are cached per descriptor content (every pointer and size they bake in), a few per host thread.
 #define FDTD_GRAPH_STEPS 32
+#define FDTD_GRAPH_CACHE 4     /* descriptors (grids) whose graphs are kept per host thread */
 namespace {
-struct GraphCache {
-  uint64_t key = 0;
+struct GraphEntry {
+  fdtd_desc desc;              // the exact descriptor the graph was captured from
   cudaGraphExec_t exec = nullptr;
+  uint64_t used = 0;           // LRU stamp
+};
+struct GraphCache {
+  GraphEntry entry[FDTD_GRAPH_CACHE];
+  uint64_t clock = 0;
   cudaStream_t capture_stream = nullptr;
 };
 thread_local GraphCache g_graph;
 
-uint64_t desc_key(const fdtd_desc* d) {
-  // FNV-1a over the descriptor bytes: any change of a pointer, size or table invalidates the graph
-  const unsigned char* b = reinterpret_cast<const unsigned char*>(d);
-  uint64_t h = 1469598103934665603ull;
-  for (size_t n = 0; n < sizeof(fdtd_desc); ++n) h = (h ^ b[n]) * 1099511628211ull;
-  return h;
-}
-
 int graph_for(const fdtd_desc* d, cudaGraphExec_t* out) {
-  uint64_t key = desc_key(d);
-  if (g_graph.exec && g_graph.key == key) {
-    *out = g_graph.exec;
-    return FDTD_OK;
+  // a graph bakes in every pointer, size and table of the descriptor: reuse it only for a byte-identical one
+  GraphEntry* slot = &g_graph.entry[0];
+  for (GraphEntry& e : g_graph.entry) {
+    if (e.exec && memcmp(&e.desc, d, sizeof(fdtd_desc)) == 0) {
+      e.used = ++g_graph.clock;
+      *out = e.exec;
+      return FDTD_OK;
+    }
+    if (e.used < slot->used) slot = &e;        // least recently used (or empty) entry
   }
-  if (g_graph.exec) {
-    cudaGraphExecDestroy(g_graph.exec);
-    g_graph.exec = nullptr;
+  if (slot->exec) {
+    cudaGraphExecDestroy(slot->exec);
+    slot->exec = nullptr;
   }
   if (!g_graph.capture_stream &&
       cudaStreamCreateWithFlags(&g_graph.capture_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -896,14 +918,15 @@ int graph_for(const fdtd_desc* d, cudaGraphExec_t* out) {
     return rc;
   }
   if (e != cudaSuccess || !graph) return fail(FDTD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-  e = cudaGraphInstantiate(&g_graph.exec, graph, 0);
+  e = cudaGraphInstantiate(&slot->exec, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) {
-    g_graph.exec = nullptr;
+    slot->exec = nullptr;
     return fail(FDTD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
   }
-  g_graph.key = key;
-  *out = g_graph.exec;
+  memcpy(&slot->desc, d, sizeof(fdtd_desc));
+  slot->used = ++g_graph.clock;
+  *out = slot->exec;
   return FDTD_OK;
 }
 }  // namespace

@@ -805,6 +805,25 @@ __global__ void detector_kernel(const T* F0, const T* F1, const T* F2, const i64
   }
 }
 
+// running DFT of a filled ring part: acc[f][v] += sum_s ring[s][v] * tw[s][f]  (complex, float64, rows in order)
+template <typename T>
+__global__ void dft_accumulate_kernel(const T* ring, i64 n_steps, i64 n_values, const double* tw, int n_freqs,
+                                      double* acc) {
+  const i64 total = n_values * n_freqs;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+    const i64 f = t / n_values, v = t % n_values;       // consecutive threads: consecutive ring columns
+    double re = acc[2 * t], im = acc[2 * t + 1];
+    const double* w = tw + 2 * f;
+    for (i64 s = 0; s < n_steps; ++s) {
+      const double x = (double)ring[s * n_values + v];
+      re = re + x * w[2 * s * n_freqs];
+      im = im + x * w[2 * s * n_freqs + 1];
+    }
+    acc[2 * t] = re;
+    acc[2 * t + 1] = im;
+  }
+}
+
 // CurrentDetector.single_point_current (fdtd/detectors.py:417-461): z-current through each cell from the
 // loop of H around it, averaged over the cell's z level and the one below; indices wrap like python's.
 // The second `current_vector_2` is ACCUMULATED onto the first (`+=`, fdtd/detectors.py:456) as in the reference.

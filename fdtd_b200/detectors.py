@@ -5,6 +5,11 @@ Here every half-step a small kernel gathers the detector's cells into a device r
 `[capacity][points][3]`; the ring is copied to the host in batches (when it fills up, or when
 the user reads the detector) and `detector.E` / `.H` materialise the reference's
 list-of-per-step-arrays lazily from those host chunks.
+
+Beyond the reference: `detector.track_frequencies(freqs)` keeps a running DFT of the record on
+the device (one small kernel per ring flush, include/fdtd_b200.h `fdtd_dft_accumulate`), so the
+spectrum of a long run on a large detector needs neither the host lists nor a device->host copy
+of the time trace.
 """
 import numpy as np
 import torch
@@ -27,6 +32,10 @@ class _Detector:
         self._lists = {"E": None, "H": None}  # cached list view of the chunks
         self._ring_E = self._ring_H = None
         self._capacity = 0
+        self._n_seen = {"E": 0, "H": 0}       # samples drained so far = record index of the next one
+        self._dft_freqs = None
+        self._dft_acc = {}
+        self._keep_trace = True
 
     def _attach(self, grid):
         self.grid = grid
@@ -65,11 +74,88 @@ class _Detector:
             self._ring_E = bd.zeros((capacity, max(1, self._n_local), self._width))
             self._ring_H = bd.zeros((capacity, max(1, self._n_local), self._width))
 
+    # ------------------------------------------------------------------ running DFT on the device
+    def track_frequencies(self, frequencies, keep_trace=True):
+        """From now on accumulate X(f) = sum_n x[n] exp(-2 pi i f n dt) of this detector's record on the device,
+        n being the index of the sample in the record (so that, tracked from the first step at f = k / (N dt),
+        it equals bin k of `numpy.fft.fft` over the N recorded samples).  `keep_trace=False` stops the time
+        trace from being copied to the host at all: `detector.E` then stays empty."""
+        if self.grid is None:
+            raise RuntimeError("register the detector on a grid first")
+        freqs = np.atleast_1d(np.asarray(frequencies, dtype=np.float64)).copy()
+        if freqs.ndim != 1 or freqs.size == 0:
+            raise ValueError("frequencies: a non-empty 1-D sequence in Hz")
+        self._dft_freqs = freqs
+        self._keep_trace = bool(keep_trace)
+        self._dft_acc = {f: bd.zeros((freqs.size, max(1, self._n_local) * self._width, 2), dtype=torch.float64)
+                         for f in self._chunks}
+
+    @property
+    def frequencies(self):
+        return None if self._dft_freqs is None else self._dft_freqs.copy()
+
+    def _accumulate(self, f, ring, n):
+        """add ring rows [0, n) to the running DFT of field `f` (record indices _n_seen[f] ...)."""
+        if self._n_local == 0:
+            return
+        import ctypes as C
+        g = self.grid
+        index = np.arange(self._n_seen[f], self._n_seen[f] + n, dtype=np.float64)
+        phase = (-2.0 * np.pi) * ((index * g.time_step)[:, None] * self._dft_freqs[None, :])
+        tw = torch.as_tensor(np.stack([np.cos(phase), np.sin(phase)], axis=-1), device=ring.device)
+        lib = bd.lib
+        rc = lib.fdtd_dft_accumulate(_capi.F32 if ring.dtype is torch.float32 else _capi.F64,
+                                     C.c_void_p(ring.data_ptr()), n, self._n_local * self._width,
+                                     C.c_void_p(tw.data_ptr()), self._dft_freqs.size,
+                                     C.c_void_p(self._dft_acc[f].data_ptr()), g._engine._stream())
+        _capi.check(lib, rc)
+
+    def spectrum(self, field="E"):
+        """complex array (n_frequencies, *sample_shape[, 3]) of the tracked DFT of `field`."""
+        if self._dft_freqs is None:
+            raise RuntimeError("call track_frequencies(...) before running")
+        if field not in self._dft_acc:
+            raise KeyError(field)
+        g = self.grid
+        if g._engine is not None:
+            g._engine.flush_detectors()
+        nf = self._dft_freqs.size
+        acc = self._dft_acc[field].view(nf, max(1, self._n_local), self._width, 2)
+        part = g._part
+        if part.sharded:
+            n_max = max(1, max(len(p) for p in self._rank_positions))
+            send = acc.new_zeros((nf, n_max, self._width, 2))
+            send[:, :self._n_local] = acc[:, :self._n_local]
+            recv = [torch.empty_like(send) for _ in range(part.world)]
+            dist.all_gather(recv, send)
+            recv = torch.stack(recv).to("cpu").numpy()
+            full = np.zeros((nf, self._n_points, self._width, 2))
+            for r, pos in enumerate(self._rank_positions):
+                full[:, pos] = recv[r, :, :len(pos)]
+        else:
+            full = acc[:, :self._n_local].to("cpu", copy=True).numpy()
+        out = full[..., 0] + 1j * full[..., 1]
+        tail = (self._width,) if self._width > 1 else ()
+        return out.reshape((nf,) + self._sample_shape + tail)
+
+    @property
+    def spectrum_E(self):
+        return self.spectrum("E")
+
+    @property
+    def spectrum_H(self):
+        return self.spectrum("H")
+
     def _drain(self, nE, nH):
         """copy the filled part of the rings to the host (one batch) and assemble global samples."""
         part = self.grid._part
         for f, ring, n in (("E", self._ring_E, nE), ("H", self._ring_H, nH)):
             if n == 0 or f not in self._chunks:
+                continue
+            if self._dft_freqs is not None:
+                self._accumulate(f, ring, n)
+            self._n_seen[f] += n
+            if not self._keep_trace:
                 continue
             if part.sharded:
                 n_max = max(1, max(len(p) for p in self._rank_positions))
@@ -190,12 +276,19 @@ class CurrentDetector(BlockDetector):
         return self._history("H")
 
     @property
+    def spectrum_I(self):
+        return self.spectrum("H")
+
+    @property
     def E(self):
         raise AttributeError("CurrentDetector records I, not E")
 
     @property
     def H(self):
         raise AttributeError("CurrentDetector records I, not H")
+
+    spectrum_E = E
+    spectrum_H = H
 
     def detector_values(self):
         """outputs what detector detects (fdtd/detectors.py:494-496)."""

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 11
+#define FDTD_ABI_VERSION 12
 
 #define FDTD_F32 0
 #define FDTD_F64 1
@@ -252,6 +252,16 @@ int fdtd_halo_signal(int64_t* peer_flag, int64_t value, void* stream);
 /* make `stream` wait until the local flag reaches `value` (acquire, system scope); after ~9 s of spinning it
  * gives up and sets *error (device int) instead of hanging */
 int fdtd_halo_wait(const int64_t* flag, int64_t value, int32_t* error, void* stream);
+
+/* ---- running DFT of detector records, on the device (spectra of long runs without
+ * moving the time traces to the host; the reference transforms the host lists, fdtd/fourier.py:172-213) -----
+ * ring     device [n_steps][n_values] samples of the library dtype (a filled part of a detector ring)
+ * twiddle  device double [n_steps][n_freqs][2]: (cos, sin) of -2 pi f n dt for the record index n of each row,
+ *          tabulated by the host like the source waveforms
+ * acc      device double [n_freqs][n_values][2], updated: acc[f][v] += sum_s ring[s][v] * twiddle[s][f]
+ *          (rows added in order, in float64, so the result does not depend on how a record is split into calls) */
+int fdtd_dft_accumulate(int32_t dtype, const void* ring, int64_t n_steps, int64_t n_values, const double* twiddle,
+                        int32_t n_freqs, double* acc, void* stream);
 
 #ifdef __cplusplus
 }

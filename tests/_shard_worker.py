@@ -36,6 +36,8 @@ def main():
         build = scenes.SCENES[scene][0] if scene in scenes.SCENES else getattr(scenes, scene)
     try:
         g = build(fd)
+        if os.environ.get("FDTD_TEST_TRACK"):
+            scenes.track_all(g, steps)
         g.run(0, progress_bar=False)           # bake: sharding restrictions surface here, on every rank alike
     except (NotImplementedError, ValueError) as exc:
         if rank == 0:
@@ -49,6 +51,8 @@ def main():
     for _ in range(steps - half):          # exercise the step()-granular path too
         g.step()
     res = scenes.dump(g)                   # grid.E gathers the slabs, detectors gather their samples
+    if os.environ.get("FDTD_TEST_TRACK"):
+        res.update(scenes.dump_tracked(g))
     if rank == 0:
         np.savez(out, **res)
     if backend != "gloo":

@@ -280,6 +280,25 @@ def spectra(fd, grid):
     return out
 
 
+def track_all(grid, steps, bins=(1, 3, 7)):
+    """fdtd_b200 only: running device DFT of every detector at FFT bins of a `steps`-long record."""
+    freqs = np.asarray(bins, dtype=np.float64) / (steps * grid.time_step)
+    for det in grid.detectors:
+        det.track_frequencies(freqs)
+    return freqs
+
+
+def dump_tracked(grid):
+    out = {}
+    for n, det in enumerate(grid.detectors):
+        if hasattr(det, "I"):
+            out[f"det{n}_SI"] = det.spectrum_I
+        else:
+            out[f"det{n}_SE"] = det.spectrum_E
+            out[f"det{n}_SH"] = det.spectrum_H
+    return out
+
+
 def rel_l2(a, b):
     a = np.asarray(a)
     b = np.asarray(b)

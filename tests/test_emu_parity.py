@@ -257,3 +257,62 @@ def test_three_objects_with_an_absorber_on_one_cell_are_refused():
     g[1:3, 1:3, 1:3] = fd.Object(permittivity=2.0)                # touches only the first
     with pytest.raises(NotImplementedError):
         g[5:9, 5:9, 5:9] = fd.Object(permittivity=3.0)            # third object on cell (5, 5, 5)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_running_dft_equals_fft_of_the_record(dtype, monkeypatch):
+    """detector.track_frequencies: the device-side running DFT at FFT-bin frequencies equals numpy's FFT of
+    the full record (ours, and the reference's golden trace), across several ring flushes."""
+    import fdtd_b200.engine as engine
+    monkeypatch.setattr(engine, "RING_BYTES", 1)            # ring capacity 16: several flushes
+    gold = np.load(os.path.join(GOLD, f"pml3d_{'f64' if dtype == 'float64' else 'f32'}.npz"))
+    steps = int(gold["steps"])
+    fd = use_emu(dtype)
+    g = scenes.pml3d(fd)
+    bins = (1, 3, 7)
+    freqs = scenes.track_all(g, steps, bins)
+    g.run(steps // 2, progress_bar=False)
+    for _ in range(steps - steps // 2):
+        g.step()
+    assert g._engine.ring_capacity == 16
+    got = scenes.dump_tracked(g)
+    tol = 1e-12 if dtype == "float64" else 1e-6
+    for n, det in enumerate(g.detectors):
+        assert np.array_equal(det.frequencies, freqs)
+        for f in "EH":
+            ours = np.fft.fft(np.asarray(getattr(det, f), dtype=np.float64), axis=0)[list(bins)]
+            ref = np.fft.fft(gold[f"det{n}_{f}"].astype(np.float64), axis=0)[list(bins)]
+            spec = got[f"det{n}_S{f}"]
+            assert spec.shape == ours.shape and np.iscomplexobj(spec)
+            assert scenes.rel_l2(spec, ours) <= 1e-12
+            assert scenes.rel_l2(spec, ref) <= tol
+
+
+def test_running_dft_without_time_trace():
+    fd = use_emu("float64")
+    a, b = scenes.c4small(fd, n=(10, 9, 8), t=2), scenes.c4small(fd, n=(10, 9, 8), t=2)
+    f = [0.02 / a.time_step, 0.05 / a.time_step]
+    a.detectors[0].track_frequencies(f)
+    b.detectors[0].track_frequencies(f, keep_trace=False)
+    a.run(40, progress_bar=False)
+    b.run(40, progress_bar=False)
+    assert len(a.detectors[0].E) == 40 and b.detectors[0].E == []
+    assert np.array_equal(a.detectors[0].spectrum_E, b.detectors[0].spectrum_E)
+    assert np.abs(a.detectors[0].spectrum_E).max() > 0
+    with pytest.raises(RuntimeError):
+        scenes.c4small(fd, n=(10, 9, 8), t=2).detectors[0].spectrum_E
+
+
+def test_running_dft_of_a_current_detector():
+    fd = use_emu("float64")
+    g = scenes.feed50(fd)
+    steps = 64
+    bins = (2, 5)
+    scenes.track_all(g, steps, bins)
+    g.run(steps, progress_bar=False)
+    for det in g.detectors:
+        if hasattr(det, "I"):
+            want = np.fft.fft(np.asarray(det.I, dtype=np.float64), axis=0)[list(bins)]
+            assert scenes.rel_l2(det.spectrum_I, want) <= 1e-12
+            with pytest.raises(AttributeError):
+                det.spectrum_E

@@ -331,3 +331,26 @@ def test_frequency_routines_vs_reference():
             assert np.array_equal(got[k], gold[k]), k
         else:
             assert scenes.rel_l2(got[k], gold[k]) <= 1e-10, f"{k}: {scenes.rel_l2(got[k], gold[k]):.3e}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_running_dft_equals_fft_of_the_record(dtype, monkeypatch):
+    """detector.track_frequencies (fdtd_dft_accumulate on the device, several ring flushes) against numpy's FFT
+    of the same record and of the reference's golden trace."""
+    import fdtd_b200.engine as engine
+    monkeypatch.setattr(engine, "RING_BYTES", 1)            # ring capacity 16
+    gold = np.load(os.path.join(GOLD, f"pml3d_{'f64' if dtype == 'float64' else 'f32'}.npz"))
+    steps = int(gold["steps"])
+    fd = cuda(dtype)
+    g = scenes.pml3d(fd)
+    bins = (1, 3, 7)
+    scenes.track_all(g, steps, bins)
+    g.run(steps, progress_bar=False)
+    got = scenes.dump_tracked(g)
+    for n, det in enumerate(g.detectors):
+        for f in "EH":
+            ours = np.fft.fft(np.asarray(getattr(det, f), dtype=np.float64), axis=0)[list(bins)]
+            ref = np.fft.fft(gold[f"det{n}_{f}"].astype(np.float64), axis=0)[list(bins)]
+            assert scenes.rel_l2(got[f"det{n}_S{f}"], ours) <= 1e-12
+            assert scenes.rel_l2(got[f"det{n}_S{f}"], ref) <= (1e-12 if dtype == "float64" else 1e-6)
