@@ -25,4 +25,5 @@ from .detectors import LineDetector, BlockDetector, CurrentDetector
 from .objects import Object, AbsorbingObject, AnisotropicObject
 from .boundaries import PeriodicBoundary, PML, DomainBorderPML
 from .fourier import FrequencyRoutines
+from .visualization import dB_map_2D, plot_detection
 from . import constants, conversions, waveforms

@@ -55,6 +55,8 @@ def curl_H(H):
 class Grid:
     """The FDTD grid: owns E, H and the material arrays, and steps them (fdtd/grid.py:80-331)."""
 
+    from .visualization import visualize       # Grid.visualize(x=|y=|z=, ...), fdtd/grid.py:88
+
     def __init__(self, shape, grid_spacing: float = 155e-9, permittivity=1.0, permeability=1.0,
                  courant_number: float = None, shard="auto", x_plane_cost=None):
         bd.require()

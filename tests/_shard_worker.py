@@ -53,6 +53,10 @@ def main():
     res = scenes.dump(g)                   # grid.E gathers the slabs, detectors gather their samples
     if os.environ.get("FDTD_TEST_TRACK"):
         res.update(scenes.dump_tracked(g))
+    if os.environ.get("FDTD_TEST_SLICES"):
+        from fdtd_b200.visualization import energy_slice
+        ix, iy, iz = (int(v) for v in os.environ["FDTD_TEST_SLICES"].split(","))
+        res.update(slice_x=energy_slice(g, x=ix), slice_y=energy_slice(g, y=iy), slice_z=energy_slice(g, z=iz))
     if rank == 0:
         np.savez(out, **res)
     if backend != "gloo":
