@@ -352,6 +352,25 @@ class Grid:
                 dic[f"{detector.name} ({key})"] = np.asarray(values)
         np.savez(os.path.join(self.folder, "detector_readings"), **dic)
 
+    def generate_video(self, delete_frames=False):
+        """frames written by `visualize(save=True, folder=grid.folder, index=n)` -> one mp4 in the simulation
+        folder, through the `ffmpeg` executable (fdtd/grid.py:441-488).  Returns the file name."""
+        import glob
+        import subprocess
+        if self.folder is None:
+            raise Exception("Save location not initialized. Please read about 'fdtd.Grid.saveSimulation()' or "
+                            "try running 'grid.saveSimulation()'.")
+        name = "fdtd_sim_video_" + self.full_sim_name + ".mp4"
+        cmd = ["ffmpeg", "-y", "-framerate", "8", "-i", "file%04d.png", "-r", "30", "-pix_fmt", "yuv420p", name]
+        try:
+            subprocess.check_call(cmd, cwd=self.folder)
+        except (FileNotFoundError, subprocess.CalledProcessError) as exc:
+            raise RuntimeError("Error when calling ffmpeg. Is ffmpeg installed and available in your path?") from exc
+        if delete_frames:
+            for frame in glob.glob(os.path.join(self.folder, "file*.png")):
+                os.remove(frame)
+        return name
+
     def promote_dtypes_to_complex(self):
         raise NotImplementedError("complex fields are not supported by the CUDA engine")
 

@@ -212,6 +212,29 @@ def test_save_data_npz_layout(fd, grid, tmp_path, monkeypatch):
     assert data["det (E)"].shape == (6, 6, 3)
 
 
+def test_generate_video_needs_a_folder_and_ffmpeg(fd, grid, tmp_path, monkeypatch):
+    """reference fdtd/grid.py:441-488: frames in the simulation folder -> ffmpeg; clear errors otherwise."""
+    with pytest.raises(Exception):
+        grid.generate_video()
+    monkeypatch.chdir(tmp_path)
+    folder = grid.save_simulation("video")
+    open(folder + "/file0000.png", "wb").close()
+    calls = []
+    import subprocess
+    monkeypatch.setattr(subprocess, "check_call", lambda cmd, cwd=None: calls.append((cmd, cwd)))
+    name = grid.generate_video(delete_frames=True)
+    assert name.startswith("fdtd_sim_video_") and name.endswith("(video).mp4")
+    assert calls[0][0][0] == "ffmpeg" and calls[0][1] == folder and "file%04d.png" in calls[0][0]
+    import os
+    assert not os.path.exists(folder + "/file0000.png")
+
+    def missing(cmd, cwd=None):
+        raise FileNotFoundError("ffmpeg")
+    monkeypatch.setattr(subprocess, "check_call", missing)
+    with pytest.raises(RuntimeError):
+        grid.generate_video()
+
+
 def test_zero_step_run_and_empty_detector(fd, grid):
     grid[3:3, 4, 4] = fd.LineDetector(name="empty")        # zero points
     grid.run(0, progress_bar=False)
