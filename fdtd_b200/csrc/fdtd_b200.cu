@@ -227,6 +227,9 @@ int validate(const fdtd_desc* d) {
       return fail(FDTD_ERR_ARG, "detector %d current", n);
   }
   if (d->use_graphs && !d->dyn) return fail(FDTD_ERR_ARG, "use_graphs needs the dyn scratch");
+  if (d->x_wrap < 0 || d->x_wrap > d->n_post + 1) return fail(FDTD_ERR_ARG, "x_wrap outside the post op list");
+  if (d->x_wrap && d->Nx == d->Nx_global)
+    return fail(FDTD_ERR_ARG, "x_wrap is for x-sharded slabs; an unsharded grid lists the periodic x boundary as a post op");
   return FDTD_OK;
 }
 
@@ -235,7 +238,7 @@ int validate(const fdtd_desc* d) {
 bool post_is_fused(const fdtd_desc* d) {
   // folding pays where a step is launch-bound; on large slabs the separate source / detector kernels
   // cost < 0.1 % of a step while the folded code costs ~1 % of the streaming kernel (profiles/r1_tune6)
-  if (d->fuse_post == 0) return false;
+  if (d->fuse_post == 0 || d->x_wrap) return false;
   if (d->fuse_post < 0 && (int64_t)d->Nx * d->Ny * d->Nz > FDTD_FUSE_MAX_CELLS) return false;
   for (int n = 0; n < d->n_post; ++n) {
     if (d->post_kind[n] == FDTD_POST_PML_ADD) return false;
@@ -445,13 +448,20 @@ int blocks_for(i64 n, int threads = 256) {
   return (int)b;
 }
 
+// part < 0: everything; 0 / 1: the post ops before / from the x-wrap of an x-sharded periodic grid on (sources
+// and detectors belong to part 1)
 template <typename T, bool IS_E>
-int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
+int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int part = -1) {
   if (post_is_fused(d)) return FDTD_OK;  // done inside the half-step kernel
+  if (part < 0 && d->x_wrap)
+    return fail(FDTD_ERR_ARG, "periodic x boundary across slabs: call fdtd_post_part around the plane transfer");
+  if (part >= 0 && !d->x_wrap) return fail(FDTD_ERR_ARG, "fdtd_post_part needs d->x_wrap");
+  const int first = part == 1 ? d->x_wrap - 1 : 0;
+  const int last = part == 0 ? d->x_wrap - 1 : d->n_post;
   T* F[3];
   for (int c = 0; c < 3; ++c) F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
   // 1. periodic copies and late PML corrections, registration order (fdtd/grid.py:290-291, 316-317)
-  for (int n = 0; n < d->n_post; ++n) {
+  for (int n = first; n < last; ++n) {
     if (d->post_kind[n] == FDTD_POST_PERIODIC) {
       int axis = d->post_arg[n];
       int N = axis == 0 ? d->Nx : (axis == 1 ? d->Ny : d->Nz);
@@ -481,6 +491,7 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
       if (rc) return rc;
     }
   }
+  if (part == 0) return FDTD_OK;
   // 2. sources, registration order (fdtd/grid.py:294-295, 320-321)
   for (int n = 0; n < d->n_sources; ++n) {
     const fdtd_source& S = d->sources[n];
@@ -590,6 +601,17 @@ int fdtd_post_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
   if (rc) return rc;
   return d->dtype == FDTD_F32 ? launch_post<float, false>(d, q, slot, stream)
                               : launch_post<double, false>(d, q, slot, stream);
+}
+
+int fdtd_post_part(const fdtd_desc* d, int32_t field, int32_t part, int64_t q, int64_t slot, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if ((field != 0 && field != 1) || (part != 0 && part != 1)) return fail(FDTD_ERR_ARG, "fdtd_post_part: field / part");
+  if (field == 0)
+    return d->dtype == FDTD_F32 ? launch_post<float, true>(d, q, slot, stream, part)
+                                : launch_post<double, true>(d, q, slot, stream, part);
+  return d->dtype == FDTD_F32 ? launch_post<float, false>(d, q, slot, stream, part)
+                              : launch_post<double, false>(d, q, slot, stream, part);
 }
 
 static int update_E_nocheck(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int64_t graph_step = -1) {

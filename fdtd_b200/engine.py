@@ -17,7 +17,7 @@ import torch
 
 from . import _capi
 from .backend import backend as bd
-from .sharding import HaloExchange, P2PHalo
+from .sharding import HaloExchange, P2PHalo, WrapExchange
 
 RING_BYTES = 64 << 20          # detector ring budget per grid
 WAVE_TABLE_MIN = 1024          # look-ahead of the host waveform tables (steps)
@@ -38,6 +38,7 @@ class Engine:
         self._wave = None          # (q0, len)
         self._halo = None
         self._p2p = None
+        self._wrap = None
         self._pending = {"E": None, "H": None}
         self.bake()
 
@@ -63,7 +64,7 @@ class Engine:
 
         # --- boundaries -----------------------------------------------------------------------
         from .boundaries import PML, PeriodicBoundary
-        slabs, post, seen_periodic = [], [], False
+        slabs, post, seen_periodic, x_wrap = [], [], False, 0
         for b in g.boundaries:
             if isinstance(b, PML):
                 if len(slabs) == _capi.MAX_SLABS:
@@ -84,13 +85,16 @@ class Engine:
                     continue                      # E[0] = E[-1] on a one-cell axis is the identity
                 seen_periodic = True
                 if b.axis == 0 and part.sharded:
-                    raise NotImplementedError("a periodic x boundary on an x-sharded grid")
+                    # the copy crosses the first and the last slab: the host moves the plane between the post ops
+                    # registered before and after this boundary (include/fdtd_b200.h, x_wrap)
+                    x_wrap = len(post) + 1
+                    continue
                 post.append((_capi.POST_PERIODIC, b.axis))
             else:
                 raise TypeError(f"unsupported boundary {b!r}")
         if len(post) > _capi.MAX_POST:
             raise ValueError("too many boundary post-ops")
-        d.n_slabs, d.n_post = len(slabs), len(post)
+        d.n_slabs, d.n_post, d.x_wrap = len(slabs), len(post), x_wrap
         for n, (kind, arg) in enumerate(post):
             d.post_kind[n], d.post_arg[n] = kind, arg
 
@@ -247,6 +251,7 @@ class Engine:
 
         if part.sharded:
             self._setup_halo()
+            self._wrap = WrapExchange(part, g._E, g._H) if x_wrap else None
         g._baked_counts = g._registration_count
 
     def _setup_halo(self):
@@ -285,6 +290,19 @@ class Engine:
         else:
             self._halo.refresh()
 
+    def _post(self, field, q, slot, st):
+        """what follows the half-step kernel on an x-sharded slab: post ops, sources, detectors -- around the
+        plane transfer of a periodic x boundary if there is one."""
+        lib, d = self.lib, self.desc
+        if self._wrap is None:
+            post = lib.fdtd_post_E if field == "E" else lib.fdtd_post_H
+            _capi.check(lib, post(C.byref(d), q, slot, st))
+            return
+        fidx = 0 if field == "E" else 1
+        _capi.check(lib, lib.fdtd_post_part(C.byref(d), fidx, 0, q, slot, st))
+        self._wrap.run(field)
+        _capi.check(lib, lib.fdtd_post_part(C.byref(d), fidx, 1, q, slot, st))
+
     def _p2p_refresh(self):
         """push both boundary planes and wait for the neighbours' (collective; after the user wrote E / H)."""
         lib, d, h = self.lib, self.desc, self._p2p
@@ -307,7 +325,6 @@ class Engine:
         fidx = 0 if field == "E" else 1
         other = "H" if field == "E" else "E"
         step = lib.fdtd_e_halfstep if field == "E" else lib.fdtd_h_halfstep
-        post = lib.fdtd_post_E if field == "E" else lib.fdtd_post_H
         bulk = (1, n) if field == "E" else (0, n - 1)
         edge = (0, min(1, n)) if field == "E" else (max(n - 1, 0), n)
         st = self._stream()
@@ -330,7 +347,7 @@ class Engine:
         else:
             _capi.check(lib, step(C.byref(d), edge[0], edge[1], q, slot, sst))
         main.wait_stream(side)
-        _capi.check(lib, post(C.byref(d), q, slot, st))
+        self._post(field, q, slot, st)
         if has_nb and not fused:
             gy, gz, flag = h.dst[field]
             side.wait_stream(main)
@@ -446,7 +463,6 @@ class Engine:
         lib, d, halo = self.lib, self.desc, self._halo
         n = d.Nx
         step = lib.fdtd_e_halfstep if field == "E" else lib.fdtd_h_halfstep
-        post = lib.fdtd_post_E if field == "E" else lib.fdtd_post_H
         bulk = (1, n) if field == "E" else (0, n - 1)
         edge = (0, min(1, n)) if field == "E" else (max(n - 1, 0), n)
         other = "H" if field == "E" else "E"
@@ -463,7 +479,7 @@ class Engine:
             halo.wait(self._pending[other])
             _capi.check(lib, step(C.byref(d), edge[0], edge[1], q, slot, st))
         self._pending[other] = None
-        _capi.check(lib, post(C.byref(d), q, slot, st))
+        self._post(field, q, slot, st)
         self._pending[field] = halo.start(field)
 
     def update_E(self, q):

@@ -136,6 +136,34 @@ class HaloExchange:
         self.wait(self.start("H"))
 
 
+class WrapExchange:
+    """The plane copy of a periodic x boundary on an x-sharded grid (fdtd/boundaries.py:184-195): after the E
+    update E[0] = E[-1] moves the last plane of the last slab into the first plane of the first slab, after the
+    H update H[-1] = H[0] goes the other way.  All three components travel, through one staging buffer, as a
+    send / recv pair of the process group (NCCL or gloo) ordered on the caller's stream; the other ranks do
+    nothing."""
+
+    def __init__(self, part, E, H):
+        self.part, self.E, self.H = part, E, H      # storage tensors (3, nx+2, Ny, Nz)
+        self.first, self.last = part.rank == 0, part.rank == part.world - 1
+        self.stage = E.new_empty((3,) + tuple(E.shape[2:])) if (self.first or self.last) else None
+
+    def run(self, field):
+        if not (self.first or self.last):
+            return
+        F = self.E if field == "E" else self.H
+        n = self.part.nx
+        sender = self.last if field == "E" else self.first
+        src_plane, dst_plane = (n, 1) if field == "E" else (1, n)        # storage index = local plane + 1
+        peer = 0 if self.last else self.part.world - 1
+        if sender:
+            self.stage.copy_(F[:, src_plane])
+            dist.send(self.stage, dst=peer)
+        else:
+            dist.recv(self.stage, src=peer)
+            F[:, dst_plane].copy_(self.stage)
+
+
 class P2PHalo:
     """Halo exchange by direct stores into the neighbour slab's ghost planes over NVLink.
 

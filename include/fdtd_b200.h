@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 12
+#define FDTD_ABI_VERSION 13
 
 #define FDTD_F32 0
 #define FDTD_F64 1
@@ -185,7 +185,10 @@ typedef struct fdtd_desc {
   void* H2[3];         /* or NULL; after fdtd_run the results are always in E / H */
   int32_t fuse_post;   /* sources/detectors folded into the half-step kernel: 1 always (when legal), 0 never,
                           -1 automatic (local slabs up to 2^23 cells, where a step is launch-bound) */
-  int32_t pad1_;
+  int32_t x_wrap;      /* x-sharded grid with a periodic x boundary (fdtd/boundaries.py:184-195): 0 = none, else
+                          1 + the number of post ops registered before it.  The copy E[0] = E[-1] / H[-1] = H[0] then
+                          crosses the first and last slab: the caller runs fdtd_post_part(.., 0, ..), moves the plane
+                          between the two ranks itself, then fdtd_post_part(.., 1, ..) */
 } fdtd_desc;
 
 /* --- queries ------------------------------------------------------------------------- */
@@ -219,6 +222,10 @@ int fdtd_post_is_fused(const fdtd_desc* d);
  * (registration order, step index q), detector sampling into ring slot `slot`. */
 int fdtd_post_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
 int fdtd_post_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
+/* The same in two parts around the plane transfer of an x-sharded periodic x boundary (d->x_wrap != 0):
+ * part 0 = the post ops registered before that boundary, part 1 = the remaining post ops, sources, detectors.
+ * field: 0 = E, 1 = H. */
+int fdtd_post_part(const fdtd_desc* d, int32_t field, int32_t part, int64_t q, int64_t slot, void* stream);
 /* Grid.update_E / Grid.update_H (fdtd/grid.py:275-325) on the whole local slab */
 int fdtd_update_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
 int fdtd_update_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);

@@ -88,6 +88,28 @@ def periodic3d(fd, n=(26, 14, 12), t=5):
     return g
 
 
+def ring3d(fd, n=(20, 12, 14), t=4):
+    """a ring along x: periodic x boundary registered BETWEEN a periodic y boundary and the z-PMLs (one PML
+    after it -> a late correction on both sides of the wrap), sources and detectors on both wrap planes, an
+    object reaching the last x plane.  On an x-sharded grid the copies E[0] = E[-1] / H[-1] = H[0] cross the
+    first and the last slab."""
+    g = fd.Grid(shape=n, grid_spacing=77.5e-9)
+    g[:, :, 0:t] = fd.PML(name="zl")
+    g[:, 0, :] = fd.PeriodicBoundary(name="ybounds")
+    g[0, :, :] = fd.PeriodicBoundary(name="xbounds")
+    g[:, :, -t:] = fd.PML(name="zh")
+    rs = np.random.RandomState(2)
+    g[14:20, 3:9, 5:10] = fd.Object(permittivity=1.0 + rs.rand(6, 6, 5), name="block_at_the_end")
+    g[2:5, 2:6, 5:9] = fd.AbsorbingObject(permittivity=1.5, conductivity=4e3, name="lossy")
+    g[n[0] - 1, 6, 7] = fd.PointSource(period=10, name="on_last_plane")
+    g[0, 3, 6] = fd.PointSource(period=13, amplitude=0.6, name="on_first_plane")
+    g[6:15, 4:10, 7] = fd.LineSource(period=16, name="line_src")
+    g[0:20, 7, 8] = fd.LineDetector(name="all_x")
+    g[0:1, 5:6, 6:7] = fd.BlockDetector(name="first")
+    g[n[0] - 2:n[0] - 1, 5:6, 6:7] = fd.BlockDetector(name="last")
+    return g
+
+
 def vacuum_aniso(fd, n=(12, 10, 9)):
     """no boundaries: random anisotropic eps/mu cavity, PointSource, LineDetector."""
     eps, mu = _rand_materials(n, seed=5)
@@ -229,6 +251,7 @@ SCENES = {
     "feed50": (feed50, 80),
     "overlaps3d": (overlaps3d, 60),
     "patch_antenna": (patch_antenna, 240),
+    "ring3d": (ring3d, 70),
 }
 
 

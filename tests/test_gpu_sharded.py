@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("halo", ["p2p", "nccl"])
 @pytest.mark.parametrize("scene,dtype", [("pml3d", "float64"), ("objects3d", "float32"), ("c4small", "float32"),
-                                         ("periodic3d", "float64")])
+                                         ("periodic3d", "float64"), ("ring3d", "float32"),
+                                         ("overlaps3d", "float64")])
 def test_sharded_equals_single(tmp_path, scene, dtype, halo):
     """halo = p2p: ghost planes stored straight into the neighbour's memory (CUDA IPC peer pointers + flags);
     halo = nccl: send/recv.  Both must reproduce the single-GPU run bit for bit."""

@@ -40,7 +40,8 @@ def launch(world, backend, dtype, scene, steps, out, **extra_env):
 @pytest.mark.parametrize("world,scene,dtype", [(2, "pml3d", "float64"), (2, "objects3d", "float64"),
                                                (3, "periodic3d", "float64"), (2, "c4small", "float32"),
                                                (3, "slab2d_xz", "float64"), (2, "overlaps3d", "float64"),
-                                               (3, "overlaps3d", "float32")])
+                                               (3, "overlaps3d", "float32"), (2, "ring3d", "float64"),
+                                               (3, "ring3d", "float32"), (4, "ring3d", "float64")])
 def test_sharded_equals_single(tmp_path, world, scene, dtype):
     steps = 24
     out = str(tmp_path / "sharded.npz")
