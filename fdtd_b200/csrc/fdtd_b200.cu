@@ -37,9 +37,7 @@ __device__ __forceinline__ bool fdtd_signbit(T v) { return signbit(v); }
 #endif
 
 #include "yee_kernels.cuh"
-#ifndef FDTD_EMU
 #include "yee_fused_eh.cuh"
-#endif
 
 namespace {
 
@@ -751,7 +749,6 @@ int fdtd_ipc_import(const void* handle64, int64_t offset, void** dev_ptr) {
 }
 #endif
 
-#ifndef FDTD_EMU
 // ---- temporally fused E+H steps (yee_fused_eh.cuh) --------------------------------------------------------
 extern "C++" {
 namespace {
@@ -775,7 +772,13 @@ bool interior_box(const fdtd_desc* d, int vec, InteriorBox* b) {
   b->y0 = lo[1]; b->y1 = hi[1];
   b->z0 = (lo[2] + vec - 1) / vec * vec;
   b->z1 = hi[2] / vec * vec;
-  return b->x1 - b->x0 >= 8 && b->y1 - b->y0 >= fdtd::FUSED_R && b->z1 - b->z0 >= fdtd::FUSED_L * vec;
+#ifdef FDTD_EMU
+  // (CPU tests: any non-empty box, so that small grids with partial tiles exercise every branch)
+  return b->x1 - b->x0 >= 2 && b->y1 - b->y0 >= 1 && b->z1 - b->z0 >= vec;
+#else
+  // below these extents the shell dominates and the ordinary half-steps are faster
+  return b->x1 - b->x0 >= 8 && b->y1 - b->y0 >= 8 && b->z1 - b->z0 >= 32 * vec;
+#endif
 }
 
 bool fuse_eh_eligible(const fdtd_desc* d, InteriorBox* box) {
@@ -851,14 +854,25 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
     P.ce[c] = rounded_product<T>(d->courant, d->bg_inv_eps[c]);
     P.ch[c] = rounded_product<T>(d->courant, d->bg_inv_mu[c]);
   }
-  {
+  const unsigned chunks = (B.x1 - B.x0 + P.x_chunk - 1) / P.x_chunk;
+#ifndef FDTD_EMU
+  if (d->fuse_eh != 2) {
+    // the shared-memory variant (one barrier per plane): the faster one so far (profiles/r1_fused_rt.log)
     dim3 grid((B.z1 - B.z0 + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC),
-              (B.y1 - B.y0 + fdtd::FUSED_R - 1) / fdtd::FUSED_R, (B.x1 - B.x0 + P.x_chunk - 1) / P.x_chunk);
+              (B.y1 - B.y0 + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);
     dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
     FDTD_LAUNCH((fdtd::fused_eh_kernel<T, VEC>), grid, block, stream, P);
-    rc = check_launch("fused_eh");
-    if (rc) return rc;
+  } else
+#endif
+  {
+    // the register-tiled variant: a thread owns R rows of VEC cells, no communication between threads
+    constexpr int R = fdtd::FUSED_RT_R, WARPS = fdtd::FUSED_RT_WARPS;
+    dim3 grid((B.z1 - B.z0 + 32 * VEC - 1) / (32 * VEC), (B.y1 - B.y0 + WARPS * R - 1) / (WARPS * R), chunks);
+    dim3 block(32 * WARPS);
+    FDTD_LAUNCH((fdtd::fused_eh_rt_kernel<T, VEC, R>), grid, block, stream, P);
   }
+  rc = check_launch("fused_eh");
+  if (rc) return rc;
   // 4. H half-step on the shell: A -> B, curls from the new E
   for (int n = 0; n < 6; ++n) {
     ShellOpts o{boxes[n][2], boxes[n][3], boxes[n][4], boxes[n][5], Hin, Hout, Eout};
@@ -885,7 +899,6 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
 }
 }  // namespace
 }  // extern "C++"
-#endif
 
 #ifndef FDTD_EMU
 // ---- CUDA-graph replay of step chunks (small, launch-bound grids) ---------------------------------
@@ -957,12 +970,8 @@ int graph_for(const fdtd_desc* d, cudaGraphExec_t* out) {
 int fdtd_fuse_eh_active(const fdtd_desc* d) {
   int rc = validate(d);
   if (rc) return rc;
-#ifndef FDTD_EMU
   InteriorBox box;
   return fuse_eh_eligible(d, &box) ? 1 : 0;
-#else
-  return 0;
-#endif
 }
 
 int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void* stream) {
@@ -972,7 +981,6 @@ int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void
   if (d->Nx != d->Nx_global && nsteps > 0)
     return fail(FDTD_ERR_UNSUPPORTED, "fdtd_run on an x-sharded slab: drive the half-steps and the halo exchange per step");
   int64_t s = 0;
-#ifndef FDTD_EMU
   {
     // pairs of temporally fused steps: A -> B -> A, so the caller's buffers hold the result again
     InteriorBox box;
@@ -989,6 +997,7 @@ int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void
       }
     }
   }
+#ifndef FDTD_EMU
   if (s == 0 && d->use_graphs && d->dyn && post_is_fused(d) && nsteps >= FDTD_GRAPH_STEPS) {
     // the whole replay must stay inside every waveform table and detector ring
     int64_t chunks = nsteps / FDTD_GRAPH_STEPS;

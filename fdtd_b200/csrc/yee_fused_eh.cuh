@@ -59,6 +59,7 @@ struct FusedParams {
 constexpr int FUSED_R = FDTD_FUSED_ROWS;   // core rows per block
 constexpr int FUSED_L = FDTD_FUSED_LANES;  // core vector lanes per block
 
+#ifndef FDTD_EMU      // shared memory + barriers: not for the serial interpreter of the CPU tests
 template <typename T, int VEC>
 __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_MIN_BLOCKS)
     fused_eh_kernel(const __grid_constant__ FusedParams<T> P) {
@@ -212,6 +213,304 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_MIN_
       }
     }
     __syncthreads();
+  }
+}
+
+#endif  // !FDTD_EMU
+
+// ---- register-tiled variant: no shared memory, no barrier, no shuffle ------------------------------------------
+// A thread owns R consecutive y rows of VEC z-cells and marches along x like the shared-memory kernel above, but
+// everything H_new[i-1] needs of E_new comes out of the thread's own registers:
+//   * the y+1 neighbour of row r is row r+1 of the same thread; above the last row one more row ("halo row") of
+//     Ex_new / Ez_new is recomputed (or, at the box edge, read back from the shell's result);
+//   * the z+1 neighbour of the last cell of a vector is recomputed too: Ex_new / Ey_new of the single cell at
+//     k0 + VEC (its inputs are the neighbouring lane's vectors: L1 hits).
+// Threads never communicate, so there is nothing to wait for except memory: the kernel keeps the latency-hiding
+// behaviour of the streaming half-step kernel (independent loads of R+1 rows in flight per thread) at 12 instead
+// of 18 words per cell and step, for (R+1)/R x (VEC+1)/VEC redundant flops, which are free here.  It also runs
+// under the serial interpreter of the CPU tests (tests/emu), which the shared-memory kernel cannot.
+// Arithmetic per value is the same as in halfstep_kernel, operation by operation.
+// STATUS (round 1, one measurement, profiles/r1_fused_rt.log): bit-identical on the GPU; with R = 4 (226 registers,
+// 8 warps per SM) a 1024^3 f32 step takes 15.0 ms against 12.8 ms for the shared-memory kernel and 12.9 ms for the
+// two half-steps -- the occupancy is too low to hide the latency.  Untried: R = 2 / 3 (151 / 188 registers), fewer
+// warps per block, loads of all rows issued ahead of the arithmetic.  Selected with fuse_eh = 2.
+#ifndef FDTD_FUSED_RT_ROWS
+#define FDTD_FUSED_RT_ROWS 4
+#endif
+#ifndef FDTD_FUSED_RT_WARPS
+#define FDTD_FUSED_RT_WARPS 4
+#endif
+#ifndef FDTD_FUSED_RT_MIN_BLOCKS
+#define FDTD_FUSED_RT_MIN_BLOCKS 2
+#endif
+constexpr int FUSED_RT_R = FDTD_FUSED_RT_ROWS;
+constexpr int FUSED_RT_WARPS = FDTD_FUSED_RT_WARPS;
+
+// inputs of a fused step are never written by it (ping-pong buffers): read-only path, free to be hoisted over stores
+template <typename T, int VEC>
+FDTD_DEV Pack<T, VEC> ldv_ro(const T* p) {
+#ifndef FDTD_EMU
+  if constexpr (sizeof(Pack<T, VEC>) == 16) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(p));
+    return *reinterpret_cast<const Pack<T, VEC>*>(&r);
+  } else if constexpr (sizeof(Pack<T, VEC>) == 8) {
+    const float2 r = __ldg(reinterpret_cast<const float2*>(p));
+    return *reinterpret_cast<const Pack<T, VEC>*>(&r);
+  }
+#endif
+  return ldv<T, VEC>(p);
+}
+template <typename T>
+FDTD_DEV T ld_ro(const T* p) {
+#ifndef FDTD_EMU
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// soft point sources of the box on ONE recomputed E value, registration order (fdtd/sources.py:93-109, 278-297)
+template <typename T>
+FDTD_DEV T fused_sources(const FusedParams<T>& P, int i, int j, int k, i64 lin, int comp, T v) {
+  for (int s = 0; s < P.n_src; ++s) {
+    const SrcK<T>& S = P.src[s];
+    if (S.comp != comp || i < S.bb[0] || i >= S.bb[1] || j < S.bb[2] || j >= S.bb[3] || k < S.bb[4] || k >= S.bb[5])
+      continue;
+    const T wv = S.wave[S.w];
+    for (int n = lower_bound_i64(S.idx, S.n, lin); n < S.n && S.idx[n] == lin; ++n) v = v + S.profile[n] * wv;
+  }
+  return v;
+}
+
+template <typename T, int VEC, int R>
+__global__ void __launch_bounds__(32 * FUSED_RT_WARPS, FDTD_FUSED_RT_MIN_BLOCKS)
+    fused_eh_rt_kernel(const FusedParams<T> P) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int jb = P.y0 + ((int)blockIdx.y * FUSED_RT_WARPS + warp) * R;  // first own row
+  const int k0 = P.z0 + ((int)blockIdx.x * 32 + lane) * VEC;
+  if (jb >= P.y1 || k0 >= P.z1) return;  // threads are independent: no barrier to miss
+  const int kz = k0 + VEC;               // the z+1 neighbour cell of the vector (<= z1 < Nz)
+  const bool kz_in = kz < P.z1;          // inside the box: recomputed here; at z1 the shell has computed it
+  const int Nz = P.Nz;
+  const i64 plane = P.plane;
+  const i64 pb = (i64)jb * Nz + k0;
+  const int xa = P.x0 + blockIdx.z * P.x_chunk;
+  const int xb = (xa + P.x_chunk < P.x1) ? xa + P.x_chunk : P.x1;
+
+  bool src_any = false;  // can a source touch this thread's rows / z-range (halo cells included) at all?
+  for (int s = 0; s < P.n_src; ++s)
+    src_any |= (jb + R >= P.src[s].bb[2]) && (jb < P.src[s].bb[3]) && (kz >= P.src[s].bb[4]) && (k0 < P.src[s].bb[5]);
+
+  // ---- carried from plane i-1 ----------------------------------------------------------------------------
+  T hp[R][3][VEC];   // H_old of the own rows
+  T hpy[VEC];        // Hy_old of the halo row (x-difference of its Ez)
+  T hpz[R];          // Hz_old at kz of the own rows (x-difference of the z-halo Ey)
+  T ep[R][3][VEC];   // E_new of the own rows
+  T eh0[VEC], eh2[VEC];  // Ex_new, Ez_new of the halo row
+  T ezx[R], ezy[R];      // Ex_new, Ey_new at kz of the own rows
+  {
+    const i64 o = (i64)(xa - 1) * plane + pb;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (jb + r < P.y1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const Pack<T, VEC> v = ldv_ro<T, VEC>(P.Hin[c] + o + (i64)r * Nz);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) hp[r][c][e] = v.v[e];
+        }
+        hpz[r] = kz_in ? ld_ro(P.Hin[2] + o + (i64)r * Nz + VEC) : T(0);
+      }
+    }
+    if (jb + R < P.y1) {
+      const Pack<T, VEC> v = ldv_ro<T, VEC>(P.Hin[1] + o + (i64)R * Nz);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) hpy[e] = v.v[e];
+    }
+  }
+
+  for (int i = xa; i <= xb; ++i) {
+    const i64 offb = (i64)i * plane + pb;
+    const bool in_x = i < P.x1;  // plane x1 belongs to the shell: its E_new is already in memory
+    // y-1 neighbours of the first row (H_old, plane i)
+    T hm0[VEC], hm2[VEC], hmz = T(0);
+    if (in_x) {
+      const Pack<T, VEC> a = ldv_ro<T, VEC>(P.Hin[0] + offb - Nz);
+      const Pack<T, VEC> b = ldv_ro<T, VEC>(P.Hin[2] + offb - Nz);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        hm0[e] = a.v[e];
+        hm2[e] = b.v[e];
+      }
+      if (kz_in) hmz = ld_ro(P.Hin[2] + offb - Nz + VEC);
+    }
+#pragma unroll
+    for (int r = 0; r <= R; ++r) {
+      const int j = jb + r;
+      if (j > P.y1) continue;            // beyond the y+1 neighbour of the box's last row: nothing needed
+      const bool own = r < R;            // false: the halo row (Ex, Ez only, no z-halo, no H)
+      const bool compute = in_x && j < P.y1;
+      const i64 off = offb + (i64)r * Nz;
+      T e0[VEC], e1[VEC], e2[VEC], ex = T(0), ey = T(0);
+      T h0[VEC], h1[VEC], h2[VEC], hzz = T(0);
+      if (compute) {
+        // ---- E_new[i] = E_old + (sc eps^-1) * curl_H(H_old)      (fdtd/grid.py:54-76, 283)
+        {
+          const Pack<T, VEC> a = ldv_ro<T, VEC>(P.Hin[0] + off);
+          const Pack<T, VEC> b = ldv_ro<T, VEC>(P.Hin[1] + off);
+          const Pack<T, VEC> c = ldv_ro<T, VEC>(P.Hin[2] + off);
+          const Pack<T, VEC> u = ldv_ro<T, VEC>(P.Ein[0] + off);
+          const Pack<T, VEC> w = ldv_ro<T, VEC>(P.Ein[2] + off);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            h0[e] = a.v[e]; h1[e] = b.v[e]; h2[e] = c.v[e];
+            e0[e] = u.v[e]; e2[e] = w.v[e];
+          }
+          if (own) {
+            const Pack<T, VEC> v = ldv_ro<T, VEC>(P.Ein[1] + off);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) e1[e] = v.v[e];
+          }
+        }
+        const T zs0 = ld_ro(P.Hin[0] + off - 1);
+        const T zs1 = ld_ro(P.Hin[1] + off - 1);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const T zn0 = e == 0 ? zs0 : h0[e > 0 ? e - 1 : 0];
+          const T zn1 = e == 0 ? zs1 : h1[e > 0 ? e - 1 : 0];
+          const T d_zy = h2[e] - hm2[e];
+          const T d_xy = h0[e] - hm0[e];
+          const T d_yz = h1[e] - zn1;
+          const T d_xz = h0[e] - zn0;
+          const T d_yx = h1[e] - (own ? hp[own ? r : 0][1][e] : hpy[e]);
+          e0[e] = e0[e] + P.ce[0] * (d_zy - d_yz);
+          e2[e] = e2[e] + P.ce[2] * (d_yx - d_xy);
+          if (own) {
+            const T d_zx = h2[e] - hp[own ? r : 0][2][e];
+            e1[e] = e1[e] + P.ce[1] * (d_xz - d_zx);
+          }
+        }
+        if (own) {
+          // the z+1 neighbour cell (j, kz): Ex_new and Ey_new only
+          if (kz_in) {
+            const T hxz = ld_ro(P.Hin[0] + off + VEC);
+            const T hyz = ld_ro(P.Hin[1] + off + VEC);
+            hzz = ld_ro(P.Hin[2] + off + VEC);
+            const T d_zy = hzz - hmz;
+            const T d_yz = hyz - h1[VEC - 1];
+            const T d_xz = hxz - h0[VEC - 1];
+            const T d_zx = hzz - hpz[own ? r : 0];
+            ex = ld_ro(P.Ein[0] + off + VEC) + P.ce[0] * (d_zy - d_yz);
+            ey = ld_ro(P.Ein[1] + off + VEC) + P.ce[1] * (d_xz - d_zx);
+          } else {
+            ex = P.Eout[0][off + VEC];
+            ey = P.Eout[1][off + VEC];
+          }
+        }
+        if (src_any) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            e0[e] = fused_sources(P, i, j, k0 + e, off + e, 0, e0[e]);
+            if (own) e1[e] = fused_sources(P, i, j, k0 + e, off + e, 1, e1[e]);
+            e2[e] = fused_sources(P, i, j, k0 + e, off + e, 2, e2[e]);
+          }
+          if (own && kz_in) {
+            ex = fused_sources(P, i, j, kz, off + VEC, 0, ex);
+            ey = fused_sources(P, i, j, kz, off + VEC, 1, ey);
+          }
+        }
+        if (own && i < xb) {
+          Pack<T, VEC> a, b, c;
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            a.v[e] = e0[e]; b.v[e] = e1[e]; c.v[e] = e2[e];
+          }
+          stv<T, VEC>(P.Eout[0] + off, a);
+          stv<T, VEC>(P.Eout[1] + off, b);
+          stv<T, VEC>(P.Eout[2] + off, c);
+        }
+      } else {
+        // a shell cell (row y1, or plane x1): its E_new is already in memory
+        const Pack<T, VEC> a = ldv<T, VEC>(P.Eout[0] + off);
+        const Pack<T, VEC> c = ldv<T, VEC>(P.Eout[2] + off);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          e0[e] = a.v[e]; e2[e] = c.v[e];
+        }
+        if (own) {
+          const Pack<T, VEC> b = ldv<T, VEC>(P.Eout[1] + off);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) e1[e] = b.v[e];
+          ex = P.Eout[0][off + VEC];
+          ey = P.Eout[1][off + VEC];
+        }
+      }
+
+      // ---- H_new[i-1] = H_old - (sc mu^-1) * curl_E(E_new)      (fdtd/grid.py:29-51, 309)
+      if (own && j < P.y1 && i > xa) {
+        Pack<T, VEC> hx, hy, hz;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const int rr = own ? r : 0;                       // (keeps the indices in range when r == R is unrolled)
+          const T ex_y = (rr + 1 < R) ? ep[rr + 1 < R ? rr + 1 : 0][0][e] : eh0[e];
+          const T ez_y = (rr + 1 < R) ? ep[rr + 1 < R ? rr + 1 : 0][2][e] : eh2[e];
+          const T ex_z = e == VEC - 1 ? ezx[rr] : ep[rr][0][e < VEC - 1 ? e + 1 : 0];
+          const T ey_z = e == VEC - 1 ? ezy[rr] : ep[rr][1][e < VEC - 1 ? e + 1 : 0];
+          const T d_zy = ez_y - ep[rr][2][e];
+          const T d_xy = ex_y - ep[rr][0][e];
+          const T d_yz = ey_z - ep[rr][1][e];
+          const T d_xz = ex_z - ep[rr][0][e];
+          const T d_zx = e2[e] - ep[rr][2][e];
+          const T d_yx = e1[e] - ep[rr][1][e];
+          hx.v[e] = hp[rr][0][e] - P.ch[0] * (d_zy - d_yz);
+          hy.v[e] = hp[rr][1][e] - P.ch[1] * (d_xz - d_zx);
+          hz.v[e] = hp[rr][2][e] - P.ch[2] * (d_yx - d_xy);
+        }
+        const i64 om = off - plane;
+        stv<T, VEC>(P.Hout[0] + om, hx);
+        stv<T, VEC>(P.Hout[1] + om, hy);
+        stv<T, VEC>(P.Hout[2] + om, hz);
+      }
+
+      // ---- carry to plane i+1, and down to row r+1 ---------------------------------------------------------
+      if (own) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          ep[own ? r : 0][0][e] = e0[e];
+          ep[own ? r : 0][1][e] = e1[e];
+          ep[own ? r : 0][2][e] = e2[e];
+        }
+        ezx[own ? r : 0] = ex;
+        ezy[own ? r : 0] = ey;
+        if (compute) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            hp[own ? r : 0][0][e] = h0[e];
+            hp[own ? r : 0][1][e] = h1[e];
+            hp[own ? r : 0][2][e] = h2[e];
+          }
+          hpz[own ? r : 0] = hzz;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          eh0[e] = e0[e];
+          eh2[e] = e2[e];
+        }
+        if (compute) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) hpy[e] = h1[e];
+        }
+      }
+      if (compute) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          hm0[e] = h0[e];
+          hm2[e] = h2[e];
+        }
+        hmz = hzz;
+      }
+    }
   }
 }
 

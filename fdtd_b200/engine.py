@@ -231,13 +231,13 @@ class Engine:
 
         # temporally fused E+H steps (12 instead of 18 words per cell and step) need a second pair of field
         # buffers; opt-in (FDTD_B200_FUSE_EH=1 / grid._fuse_eh): homogeneous, unsharded grids only
-        if (g._fuse_eh and g._E.is_cuda and not part.sharded and ie_eff is None and imu is None):
+        if (g._fuse_eh and not part.sharded and ie_eff is None and imu is None):
             if g._E2 is None:
                 g._E2, g._H2 = torch.zeros_like(g._E), torch.zeros_like(g._H)
             for c in range(3):
                 d.E2[c] = g._E2[c, 1].data_ptr()
                 d.H2[c] = g._H2[c, 1].data_ptr()
-            d.fuse_eh = 1
+            d.fuse_eh = 2 if int(g._fuse_eh) == 2 else 1
 
         # CUDA-graph replay of step chunks pays off where a step is launch-bound (small grids)
         self._dyn = torch.zeros(2, dtype=torch.int64, device=g._E.device)

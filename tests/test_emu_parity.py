@@ -316,3 +316,42 @@ def test_running_dft_of_a_current_detector():
             assert scenes.rel_l2(det.spectrum_I, want) <= 1e-12
             with pytest.raises(AttributeError):
                 det.spectrum_E
+
+
+@pytest.mark.parametrize("dtype,n,t", [("float32", (20, 23, 40), 3), ("float64", (14, 21, 22), 3),
+                                       ("float32", (13, 9, 16), 2), ("float32", (12, 40, 144), 2)])
+def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
+    """run() with the register-tiled single-pass E+H kernel on the interior (ping-pong buffers, halo values
+    recomputed in registers, ordinary kernels on the PML shell) reproduces the two-half-step path bit for bit:
+    even and odd step counts, partial tiles in y and z, several x chunks, sources inside the interior, on its
+    edges and in the shell, detectors everywhere."""
+    fd = use_emu(dtype)
+
+    def build():
+        g = fd.Grid(shape=n, grid_spacing=77.5e-9, permittivity=1.3, permeability=1.1)
+        g[0:t, :, :] = fd.PML()
+        g[-t:, :, :] = fd.PML()
+        g[:, 0:t, :] = fd.PML()
+        g[:, -t:, :] = fd.PML()
+        g[:, :, 0:t + 1] = fd.PML()
+        g[n[0] // 2, n[1] // 2, n[2] // 2] = fd.PointSource(period=17, name="centre")
+        g[2, n[1] // 2, 3] = fd.PointSource(period=11, amplitude=0.4, name="in_pml")
+        g[t + 1:n[0] - t - 1, t + 1:n[1] - t - 1, n[2] // 3] = fd.LineSource(period=23, name="line")
+        g[n[0] // 2 + 1, n[1] - t - 1, n[2] - 2] = fd.PointSource(period=9, amplitude=0.7, name="box_corner")
+        g[1:n[0] - 1, n[1] // 2 + 1, n[2] // 2 + 2] = fd.LineDetector(name="across")
+        g[n[0] // 2:n[0] // 2 + 1, 1:3, n[2] - 3:n[2] - 2] = fd.BlockDetector(name="corner")
+        return g
+
+    outs = []
+    for fuse, chunk in ((0, 0), (1, 0), (1, 3)):
+        g = build()
+        g._fuse_eh = fuse
+        g._x_chunk = chunk
+        g.run(9, progress_bar=False)
+        g.step()
+        g.run(4, progress_bar=False)
+        assert bool(g._engine.lib.fdtd_fuse_eh_active(g._engine.desc)) == bool(fuse)
+        outs.append(scenes.dump(g))
+    assert float(np.abs(outs[0]["E"]).max()) > 0
+    compare(outs[1], outs[0], 0.0, bitwise=True)
+    compare(outs[2], outs[0], 0.0, bitwise=True)

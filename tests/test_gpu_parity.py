@@ -301,16 +301,17 @@ def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
         return g
 
     outs = []
-    for fuse in (False, True):
+    for fuse in (0, 1, 2):                      # two half-steps / shared-memory kernel / register-tiled kernel
         g = build()
         g._fuse_eh = fuse
         g.run(31, progress_bar=False)
         g.step()
         g.run(10, progress_bar=False)
-        assert bool(g._engine.lib.fdtd_fuse_eh_active(g._engine.desc)) == fuse
+        assert bool(g._engine.lib.fdtd_fuse_eh_active(g._engine.desc)) == bool(fuse)
         outs.append(scenes.dump(g))
     assert float(np.abs(outs[0]["E"]).max()) > 0
     compare(outs[1], outs[0], 0.0, bitwise=True)
+    compare(outs[2], outs[0], 0.0, bitwise=True)
 
 
 @pytest.mark.gpu
