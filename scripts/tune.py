@@ -18,6 +18,15 @@ VDIR = os.path.join(ROOT, "fdtd_b200", "_variants")
 
 VARIANTS = {
     "default": [],
+    # register-tiled fused E+H kernel (yee_fused_eh.cuh, FDTD_B200_FUSE_EH=2): rows per thread / warps per block /
+    # blocks per SM -- time with scripts/gpu_fused_rt.sh
+    "rt_r2_w4_mb3": ["-DFDTD_FUSED_RT_ROWS=2", "-DFDTD_FUSED_RT_WARPS=4", "-DFDTD_FUSED_RT_MIN_BLOCKS=3"],
+    "rt_r2_w2_mb6": ["-DFDTD_FUSED_RT_ROWS=2", "-DFDTD_FUSED_RT_WARPS=2", "-DFDTD_FUSED_RT_MIN_BLOCKS=6"],
+    "rt_r2_w8_mb1": ["-DFDTD_FUSED_RT_ROWS=2", "-DFDTD_FUSED_RT_WARPS=8", "-DFDTD_FUSED_RT_MIN_BLOCKS=1"],
+    "rt_r3_w4_mb2": ["-DFDTD_FUSED_RT_ROWS=3", "-DFDTD_FUSED_RT_WARPS=4", "-DFDTD_FUSED_RT_MIN_BLOCKS=2"],
+    "rt_r4_w4_mb2": ["-DFDTD_FUSED_RT_ROWS=4", "-DFDTD_FUSED_RT_WARPS=4", "-DFDTD_FUSED_RT_MIN_BLOCKS=2"],
+    "rt_r4_w2_mb4": ["-DFDTD_FUSED_RT_ROWS=4", "-DFDTD_FUSED_RT_WARPS=2", "-DFDTD_FUSED_RT_MIN_BLOCKS=4"],
+    "rt_r1_w4_mb4": ["-DFDTD_FUSED_RT_ROWS=1", "-DFDTD_FUSED_RT_WARPS=4", "-DFDTD_FUSED_RT_MIN_BLOCKS=4"],
     "post_inline": ["-DFDTD_POST_INLINE=1"],
     "hdown": ["-DFDTD_H_DOWNWARD=1"],
     "fz_pf0": ["-DFDTD_FUSED_PREFETCH=0"],
@@ -75,7 +84,9 @@ def build():
         r = subprocess.run(cmd, check=True, capture_output=True, text=True)
         lines = r.stderr.splitlines()
         for n, l in enumerate(lines):
-            if "Compiling entry function" in l and ("fused_eh_kernelIfLi4" in l) and name.startswith("fz"):
+            if "Compiling entry function" in l and "fused_eh_rt_kernelIfLi4" in l and name.startswith("rt_"):
+                print(name, "FUSED-RT", " | ".join(x.strip() for x in lines[n + 1:n + 4]))
+            elif "Compiling entry function" in l and ("fused_eh_kernelIfLi4" in l) and name.startswith("fz"):
                 print(name, "FUSED", " | ".join(x.strip() for x in lines[n + 1:n + 4]))
             elif "Compiling entry function" in l and not name.startswith("fz") and ("halfstep_kernelIfLi4ELb" in l or ("MAX_VEC_F32=2" in " ".join(defs) and "halfstep_kernelIfLi2ELb" in l)):
                 print(name, "E" if "ELb1" in l else "H", " | ".join(x.strip() for x in lines[n + 1:n + 4]))

@@ -12,12 +12,15 @@ OUT = os.path.join(OUT_DIR, "libfdtd_b200_emu.so")
 def build(force=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     deps = [SRC, os.path.join(ROOT, "fdtd_b200", "csrc", "yee_kernels.cuh"),
+            os.path.join(ROOT, "fdtd_b200", "csrc", "yee_fused_eh.cuh"),
             os.path.join(ROOT, "include", "fdtd_b200.h"), os.path.join(HERE, "cuda_emu.h")]
+    extra = os.environ.get("FDTD_EMU_DEFS", "").split()      # e.g. "-DFDTD_FUSED_RT_ROWS=2" (kernel variants)
+    force = force or bool(extra)
     if (not force and os.path.exists(OUT)
             and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps)):
         return OUT
     cmd = ["g++", "-x", "c++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-DFDTD_EMU",
-           "-fPIC", "-shared", "-I", HERE, "-I", os.path.join(ROOT, "include"),
+           "-fPIC", "-shared", *extra, "-I", HERE, "-I", os.path.join(ROOT, "include"),
            "-I", os.path.join(ROOT, "fdtd_b200", "csrc"), SRC, "-o", OUT]
     subprocess.run(cmd, check=True)
     return OUT
