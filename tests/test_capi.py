@@ -81,3 +81,34 @@ def test_no_cpu_fallback_without_cuda():
         fd.set_backend("numpy")
     with pytest.raises(ValueError):
         fd.set_backend("torch.float64")
+
+
+def test_header_is_plain_c_and_layouts_agree(lib_path, tmp_path):
+    """include/fdtd_b200.h compiles as C99 (the boundary is a C ABI, not a C++ one), and a C program linked
+    against the library sees the same sizeof(fdtd_desc) and field offsets as the library and the ctypes mirror."""
+    import shutil
+    import subprocess
+    from fdtd_b200 import _capi
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "probe.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "fdtd_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("%d %zu %zu %zu %zu %zu %zu\\n", FDTD_ABI_VERSION, sizeof(fdtd_desc), offsetof(fdtd_desc, slabs),\n'
+        "         offsetof(fdtd_desc, sources), offsetof(fdtd_desc, detectors), offsetof(fdtd_desc, absorb2),\n"
+        "         offsetof(fdtd_desc, x_wrap));\n"
+        '  printf("%d %lld\\n", (int)fdtd_abi_version(), (long long)fdtd_sizeof_desc());\n'
+        "  return fdtd_validate(NULL) == FDTD_ERR_ARG ? 0 : 1;\n}\n")
+    exe = tmp_path / "probe"
+    libdir = os.path.dirname(lib_path)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(lib_path),
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    abi, size, o_slabs, o_src, o_det, o_abs2, o_wrap, lib_abi, lib_size = (int(v) for v in out)
+    assert abi == lib_abi == _capi.ABI_VERSION
+    assert size == lib_size == ctypes.sizeof(_capi.Desc)
+    D = _capi.Desc
+    assert (o_slabs, o_src, o_det, o_abs2, o_wrap) == (D.slabs.offset, D.sources.offset, D.detectors.offset,
+                                                       D.absorb2.offset, D.x_wrap.offset)
