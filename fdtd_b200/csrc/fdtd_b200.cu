@@ -3,7 +3,8 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
 //        -shared -Xcompiler -fPIC -Iinclude fdtd_b200/csrc/fdtd_b200.cu -o fdtd_b200/libfdtd_b200.so
 // (see __graft_entry__.build()).  The same file compiles as plain C++ with -DFDTD_EMU
-// against tests/emu/cuda_emu.h: a serial thread-by-thread interpreter of the kernels used
+// against tests/emu/cuda_emu.h: a serial thread-by-thread interpreter of the kernels (cooperative fibers for the
+// few kernels with barriers) used
 // ONLY by the CPU test-suite to exercise the kernel logic where there is no GPU.  The
 // product library never contains that path.
 #include <stdarg.h>
@@ -20,6 +21,9 @@
 #define FDTD_DEV inline
 #define FDTD_LAUNCH(kern, grid, block, stream, ...) \
   emu::launch(grid, block, [&]() { kern(__VA_ARGS__); })
+// kernels with shared memory and barriers: the threads of a block run as cooperative fibers
+#define FDTD_LAUNCH_SYNC(kern, grid, block, stream, ...) \
+  emu::launch_coop(grid, block, [&]() { kern(__VA_ARGS__); })
 template <typename T>
 inline void fdtd_atomic_add(T* p, T v) { *p = *p + v; }
 #include <cmath>
@@ -30,6 +34,7 @@ inline bool fdtd_signbit(T v) { return std::signbit(v); }
 #define FDTD_DEV __device__ __forceinline__
 #define FDTD_LAUNCH(kern, grid, block, stream, ...) \
   kern<<<grid, block, 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define FDTD_LAUNCH_SYNC FDTD_LAUNCH
 template <typename T>
 __device__ __forceinline__ void fdtd_atomic_add(T* p, T v) { atomicAdd(p, v); }
 template <typename T>
@@ -855,16 +860,13 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
     P.ch[c] = rounded_product<T>(d->courant, d->bg_inv_mu[c]);
   }
   const unsigned chunks = (B.x1 - B.x0 + P.x_chunk - 1) / P.x_chunk;
-#ifndef FDTD_EMU
   if (d->fuse_eh != 2) {
     // the shared-memory variant (one barrier per plane): the faster one so far (profiles/r1_fused_rt.log)
     dim3 grid((B.z1 - B.z0 + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC),
               (B.y1 - B.y0 + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);
     dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
-    FDTD_LAUNCH((fdtd::fused_eh_kernel<T, VEC>), grid, block, stream, P);
-  } else
-#endif
-  {
+    FDTD_LAUNCH_SYNC((fdtd::fused_eh_kernel<T, VEC>), grid, block, stream, P);
+  } else {
     // the register-tiled variant: a thread owns R rows of VEC cells, no communication between threads
     constexpr int R = fdtd::FUSED_RT_R, WARPS = fdtd::FUSED_RT_WARPS;
     dim3 grid((B.z1 - B.z0 + 32 * VEC - 1) / (32 * VEC), (B.y1 - B.y0 + WARPS * R - 1) / (WARPS * R), chunks);

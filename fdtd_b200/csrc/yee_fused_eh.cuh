@@ -59,7 +59,6 @@ struct FusedParams {
 constexpr int FUSED_R = FDTD_FUSED_ROWS;   // core rows per block
 constexpr int FUSED_L = FDTD_FUSED_LANES;  // core vector lanes per block
 
-#ifndef FDTD_EMU      // shared memory + barriers: not for the serial interpreter of the CPU tests
 template <typename T, int VEC>
 __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_MIN_BLOCKS)
     fused_eh_kernel(const __grid_constant__ FusedParams<T> P) {
@@ -216,8 +215,6 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_MIN_
   }
 }
 
-#endif  // !FDTD_EMU
-
 // ---- register-tiled variant: no shared memory, no barrier, no shuffle ------------------------------------------
 // A thread owns R consecutive y rows of VEC z-cells and marches along x like the shared-memory kernel above, but
 // everything H_new[i-1] needs of E_new comes out of the thread's own registers:
@@ -227,8 +224,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_MIN_
 //     k0 + VEC (its inputs are the neighbouring lane's vectors: L1 hits).
 // Threads never communicate, so there is nothing to wait for except memory: the kernel keeps the latency-hiding
 // behaviour of the streaming half-step kernel (independent loads of R+1 rows in flight per thread) at 12 instead
-// of 18 words per cell and step, for (R+1)/R x (VEC+1)/VEC redundant flops, which are free here.  It also runs
-// under the serial interpreter of the CPU tests (tests/emu), which the shared-memory kernel cannot.
+// of 18 words per cell and step, for (R+1)/R x (VEC+1)/VEC redundant flops, which are free here.
 // Arithmetic per value is the same as in halfstep_kernel, operation by operation.
 // STATUS (round 1, one measurement, profiles/r1_fused_rt.log): bit-identical on the GPU; with R = 4 (226 registers,
 // 8 warps per SM) a 1024^3 f32 step takes 15.0 ms against 12.8 ms for the shared-memory kernel and 12.9 ms for the

@@ -2,7 +2,10 @@
 // A serial interpreter for the CUDA kernels of fdtd_b200/csrc: the .cu file is compiled as
 // plain C++ with -DFDTD_EMU, every <<<grid, block>>> launch becomes a loop that runs the
 // kernel body once per (block, thread) with threadIdx / blockIdx set.  This works because
-// the kernels have no inter-thread communication (no shared memory, shuffles or barriers).
+// the streaming kernels have no inter-thread communication (no shared memory, shuffles or barriers).
+// Kernels that do use shared memory and __syncthreads() (the temporally fused E+H kernels) are run by
+// emu::launch_coop: the threads of a block become cooperative fibers (ucontext) on the one host thread,
+// __syncthreads() hands control to the next fiber, `__shared__` is a function-local static.
 // It lets the CPU test-suite (`pytest -m "not gpu"`) execute the kernel logic, the host
 // layer and the 2-rank halo exchange (gloo) in a container without a GPU.  The product
 // never loads this build: fdtd_b200 only opens libfdtd_b200.so (nvcc, sm_100a).
@@ -15,6 +18,8 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __grid_constant__
+#define __shared__ static
 
 struct dim3 {
   unsigned x, y, z;
@@ -40,6 +45,79 @@ inline void launch(dim3 grid, dim3 block, F&& body) {
             }
 }
 }  // namespace emu
+
+#include <ucontext.h>
+
+#include <type_traits>
+#include <vector>
+
+namespace emu {
+// ---- cooperative launch: one fiber per thread of a block, for kernels with barriers ---------------------
+struct Fiber {
+  ucontext_t ctx;
+  std::vector<char> stack;
+  bool done = false;
+  dim3 tid;
+};
+inline thread_local ucontext_t t_sched;
+inline thread_local Fiber* t_cur = nullptr;
+inline thread_local void (*t_entry)(void*) = nullptr;
+inline thread_local void* t_entry_arg = nullptr;
+
+inline void fiber_main() {
+  t_entry(t_entry_arg);
+  t_cur->done = true;
+  swapcontext(&t_cur->ctx, &t_sched);
+}
+
+// __syncthreads(): every live thread of the block runs up to its next barrier before any continues
+inline void sync_threads() { swapcontext(&t_cur->ctx, &t_sched); }
+
+template <typename F>
+inline void launch_coop(dim3 grid, dim3 block, F&& body) {
+  t_gridDim = grid;
+  t_blockDim = block;
+  const unsigned n = block.x * block.y * block.z;
+  static thread_local std::vector<Fiber> fibers;
+  if (fibers.size() < n) fibers.resize(n);
+  for (Fiber& f : fibers)
+    if (f.stack.empty()) f.stack.resize(256 << 10);
+  using Body = typename std::remove_reference<F>::type;
+  t_entry = [](void* p) { (*static_cast<Body*>(p))(); };
+  t_entry_arg = const_cast<void*>(static_cast<const void*>(&body));
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        unsigned t = 0;
+        for (unsigned tz = 0; tz < block.z; ++tz)
+          for (unsigned ty = 0; ty < block.y; ++ty)
+            for (unsigned tx = 0; tx < block.x; ++tx, ++t) {
+              Fiber& f = fibers[t];
+              f.done = false;
+              f.tid = dim3(tx, ty, tz);
+              getcontext(&f.ctx);
+              f.ctx.uc_stack.ss_sp = f.stack.data();
+              f.ctx.uc_stack.ss_size = f.stack.size();
+              f.ctx.uc_link = nullptr;
+              makecontext(&f.ctx, fiber_main, 0);
+            }
+        for (bool alive = true; alive;) {
+          alive = false;
+          for (unsigned k = 0; k < n; ++k) {
+            Fiber& f = fibers[k];
+            if (f.done) continue;
+            t_blockIdx = dim3(bx, by, bz);
+            t_threadIdx = f.tid;
+            t_cur = &f;
+            swapcontext(&t_sched, &f.ctx);
+            alive = alive || !f.done;
+          }
+        }
+      }
+}
+}  // namespace emu
+
+#define __syncthreads() emu::sync_threads()
 
 #define threadIdx (emu::t_threadIdx)
 #define blockIdx (emu::t_blockIdx)
