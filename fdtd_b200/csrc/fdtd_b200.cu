@@ -24,6 +24,8 @@
 // kernels with shared memory and barriers: the threads of a block run as cooperative fibers
 #define FDTD_LAUNCH_SYNC(kern, grid, block, stream, ...) \
   emu::launch_coop(grid, block, [&]() { kern(__VA_ARGS__); })
+#define FDTD_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) \
+  emu::launch_coop(grid, block, [&]() { kern(__VA_ARGS__); })
 template <typename T>
 inline void fdtd_atomic_add(T* p, T v) { *p = *p + v; }
 #include <cmath>
@@ -35,6 +37,8 @@ inline bool fdtd_signbit(T v) { return std::signbit(v); }
 #define FDTD_LAUNCH(kern, grid, block, stream, ...) \
   kern<<<grid, block, 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #define FDTD_LAUNCH_SYNC FDTD_LAUNCH
+#define FDTD_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) \
+  kern<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__)
 template <typename T>
 __device__ __forceinline__ void fdtd_atomic_add(T* p, T v) { atomicAdd(p, v); }
 template <typename T>
@@ -860,7 +864,23 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
     P.ch[c] = rounded_product<T>(d->courant, d->bg_inv_mu[c]);
   }
   const unsigned chunks = (B.x1 - B.x0 + P.x_chunk - 1) / P.x_chunk;
-  if (d->fuse_eh != 2) {
+  if (d->fuse_eh == 3) {
+    // the pipelined variant: inputs staged in shared memory by cp.async two planes ahead
+    using Lay = fdtd::FusedPipeLayout<T, VEC>;
+    dim3 grid((B.z1 - B.z0 + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC),
+              (B.y1 - B.y0 + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);
+    dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
+#ifndef FDTD_EMU
+    static bool configured = false;      // (per instantiation: one kernel function each)
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::BYTES);
+      if (e != cudaSuccess) return fail(FDTD_ERR_CUDA, "cudaFuncSetAttribute(smem %zu): %s", Lay::BYTES, cudaGetErrorString(e));
+      configured = true;
+    }
+#endif
+    FDTD_LAUNCH_SMEM((fdtd::fused_eh_pipe_kernel<T, VEC>), grid, block, Lay::BYTES, stream, P);
+  } else if (d->fuse_eh != 2) {
     // the shared-memory variant (one barrier per plane): the faster one so far (profiles/r1_fused_rt.log)
     dim3 grid((B.z1 - B.z0 + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC),
               (B.y1 - B.y0 + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);

@@ -48,6 +48,30 @@ struct FusedParams {
   SrcK<T> src[FDTD_FUSED_MAX];  // soft point-list sources on E (ascending idx)
 };
 
+// soft point sources of the box on the VEC recomputed E values of a thread, registration order
+// (fdtd/sources.py:93-109, 278-297); rare: kept out of line
+template <typename T, int VEC>
+FDTD_RARE_FN void fused_sources_vec(const FusedParams<T>& P, int i, int j, int k0, i64 off, Pack<T, VEC>& e0,
+                                    Pack<T, VEC>& e1, Pack<T, VEC>& e2) {
+  for (int s = 0; s < P.n_src; ++s) {
+    const SrcK<T>& S = P.src[s];
+    if (i < S.bb[0] || i >= S.bb[1] || j < S.bb[2] || j >= S.bb[3] || k0 + VEC <= S.bb[4] || k0 >= S.bb[5]) continue;
+    const T wv = S.wave[S.w];
+    for (int n = lower_bound_i64(S.idx, S.n, off); n < S.n && S.idx[n] < off + VEC; ++n) {
+      const int de = (int)(S.idx[n] - off);
+      const T v = S.profile[n] * wv;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        if (e == de) {
+          if (S.comp == 0) e0.v[e] = e0.v[e] + v;
+          else if (S.comp == 1) e1.v[e] = e1.v[e] + v;
+          else e2.v[e] = e2.v[e] + v;
+        }
+      }
+    }
+  }
+}
+
 // core tile of a block: measured on B200 at 1024^3 f32 (ms per fused step incl. shell): 16x16 lanes 13.5,
 // 8x16 13.2, 8x32 13.2, 4x32 12.8 -- small barrier domains matter more than the halo redundancy
 #ifndef FDTD_FUSED_ROWS
@@ -505,6 +529,246 @@ __global__ void __launch_bounds__(32 * FUSED_RT_WARPS, FDTD_FUSED_RT_MIN_BLOCKS)
           hm2[e] = h2[e];
         }
         hmz = hzz;
+      }
+    }
+  }
+}
+
+// ---- pipelined variant: the inputs of each plane are staged in shared memory by cp.async, two planes ahead -----
+// Same thread layout, halo scheme and arithmetic as fused_eh_kernel, but no thread ever waits for a global load it
+// has just issued: every plane's H_old tile (own cells + the y-1 row and the z-1 vector) and E_old tile arrive in
+// one of three shared-memory stages through asynchronous 16-byte copies (LDGSTS, L2 only) issued two iterations
+// before they are consumed, so the one barrier per plane no longer exposes the memory latency of the slowest warp.
+// Each global word is requested once per block (the y-1 / z-1 neighbours come out of the staged tile).
+// Iteration i:  wait for this thread's copies of plane i -> barrier (everyone's copies landed, everyone's
+// E_new[i-1] is published, stage (i-1)%3 is free) -> issue the copies of plane i+2 into stage (i-1)%3 ->
+// E_new[i] from stage i%3 -> H_new[i-1] from the published E_new[i-1] -> publish E_new[i].
+#ifdef FDTD_EMU
+#define FDTD_CP_ASYNC16(dst, src) emu::cp_async16((dst), (src))
+#define FDTD_CP_ASYNC_COMMIT() emu::cp_async_commit()
+#define FDTD_CP_ASYNC_WAIT_1() emu::cp_async_wait(1)
+#define FDTD_DYN_SMEM(name) alignas(16) static unsigned char name[128 << 10]
+#else
+#define FDTD_CP_ASYNC16(dst, src)                                                                      \
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), \
+               "l"(src)                                                                                \
+               : "memory")
+#define FDTD_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define FDTD_CP_ASYNC_WAIT_1() asm volatile("cp.async.wait_group 1;" ::: "memory")
+#define FDTD_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+#ifndef FDTD_FUSED_PIPE_MIN_BLOCKS
+#define FDTD_FUSED_PIPE_MIN_BLOCKS 3
+#endif
+
+template <typename T, int VEC>
+struct FusedPipeLayout {
+  static constexpr int R = FUSED_R, L = FUSED_L;
+  static constexpr int HV = L + 2, EV = L + 1;                 // vectors per staged row
+  static constexpr int H_WORDS = 3 * (R + 2) * HV * VEC;       // H_old tile: rows j0-1 .. j0+R, vectors -1 .. L
+  static constexpr int E_WORDS = 3 * (R + 1) * EV * VEC;       // E_old tile: rows j0 .. j0+R, vectors 0 .. L
+  static constexpr int STAGE_WORDS = H_WORDS + E_WORDS;
+  static constexpr int X_WORDS = 3 * (R + 1) * EV * VEC;       // one published E_new tile
+  static constexpr int STAGES = 3;
+  static constexpr size_t BYTES = sizeof(T) * (size_t)(STAGES * STAGE_WORDS + 2 * X_WORDS);
+};
+
+// The 16-byte copies a thread contributes to every stage: the tile's vectors are dealt round-robin to the threads
+// once, before the march (source pointer at plane 0 and word offset inside a stage; offset < 0 = nothing to copy),
+// so that a plane costs each thread one pointer add and one cp.async per slot.
+template <typename T, int VEC>
+struct FusedCopySlots {
+  using Lay = FusedPipeLayout<T, VEC>;
+  static constexpr int NTHREADS = (Lay::R + 1) * (Lay::L + 1);
+  static constexpr int NVEC = Lay::STAGE_WORDS / VEC;
+  static constexpr int N = (NVEC + NTHREADS - 1) / NTHREADS;
+  const T* src[N];
+  int off[N];
+};
+
+template <typename T, int VEC>
+FDTD_DEV void fused_copy_slots(const FusedParams<T>& P, FusedCopySlots<T, VEC>& S, int j0, int kz0, int tid) {
+  using Lay = FusedPipeLayout<T, VEC>;
+  constexpr int R = Lay::R, HV = Lay::HV, EV = Lay::EV;
+  constexpr int NH = 3 * (R + 2) * HV;
+#pragma unroll
+  for (int n = 0; n < FusedCopySlots<T, VEC>::N; ++n) {
+    const int v = tid + n * FusedCopySlots<T, VEC>::NTHREADS;
+    S.off[n] = -1;
+    S.src[n] = nullptr;
+    if (v >= FusedCopySlots<T, VEC>::NVEC) continue;
+    int c, j, k;
+    const T* const* F;
+    if (v < NH) {   // H_old tile: rows j0-1 .. j0+R, vectors -1 .. L
+      c = v / ((R + 2) * HV);
+      const int rem = v % ((R + 2) * HV);
+      j = j0 - 1 + rem / HV;
+      k = kz0 + (rem % HV - 1) * VEC;
+      F = P.Hin;
+    } else {        // E_old tile: rows j0 .. j0+R, vectors 0 .. L
+      const int w = v - NH;
+      c = w / ((R + 1) * EV);
+      const int rem = w % ((R + 1) * EV);
+      j = j0 + rem / EV;
+      k = kz0 + (rem % EV) * VEC;
+      F = P.Ein;
+    }
+    if (j < P.y1 && k < P.z1) {   // (beyond the box nothing is recomputed: those cells come from the shell's result)
+      S.off[n] = v * VEC;
+      S.src[n] = F[c] + (i64)j * P.Nz + k;
+    }
+  }
+}
+
+// asynchronous copies of plane i of the block's tile into one stage
+template <typename T, int VEC>
+FDTD_DEV void fused_stage_issue(const FusedCopySlots<T, VEC>& S, T* stage, i64 plane_offset) {
+#pragma unroll
+  for (int n = 0; n < FusedCopySlots<T, VEC>::N; ++n)
+    if (S.off[n] >= 0) FDTD_CP_ASYNC16(stage + S.off[n], S.src[n] + plane_offset);
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE_MIN_BLOCKS)
+    fused_eh_pipe_kernel(const __grid_constant__ FusedParams<T> P) {
+  using Lay = FusedPipeLayout<T, VEC>;
+  constexpr int R = Lay::R, L = Lay::L, HV = Lay::HV, EV = Lay::EV;
+  static_assert(sizeof(T) * VEC == 16, "the staged copies are 16 bytes wide");
+  FDTD_DYN_SMEM(smem_raw);
+  T* const stages = reinterpret_cast<T*>(smem_raw);
+  T* const xch = stages + Lay::STAGES * Lay::STAGE_WORDS;
+
+  const int tid = threadIdx.x;
+  const int r = tid / (L + 1), l = tid % (L + 1);
+  const int j0 = P.y0 + blockIdx.y * R, kz0 = P.z0 + blockIdx.x * L * VEC;
+  const int j = j0 + r, k0 = kz0 + l * VEC;
+  const bool core = (r < R) && (l < L) && (j < P.y1) && (k0 < P.z1);
+  const bool active = (j <= P.y1) && (k0 <= P.z1);
+  const bool inside = (j < P.y1) && (k0 < P.z1);
+  const int Nz = P.Nz;
+  const i64 plane = P.plane;
+  const i64 p = (i64)j * Nz + k0;
+  const int xa = P.x0 + blockIdx.z * P.x_chunk;
+  const int xb = (xa + P.x_chunk < P.x1) ? xa + P.x_chunk : P.x1;
+
+  bool src_yz = false;
+  for (int s = 0; s < P.n_src; ++s)
+    src_yz |= (j >= P.src[s].bb[2]) && (j < P.src[s].bb[3]) && (k0 + VEC > P.src[s].bb[4]) && (k0 < P.src[s].bb[5]);
+
+  FusedCopySlots<T, VEC> slots;
+  fused_copy_slots<T, VEC>(P, slots, j0, kz0, tid);
+  // two planes in flight before the first one is consumed (one commit group per plane, empty ones included)
+  for (int s = 0; s < 2; ++s) {
+    const int ip = xa + s;
+    if (ip <= xb && ip < P.x1) fused_stage_issue<T, VEC>(slots, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane);
+    FDTD_CP_ASYNC_COMMIT();
+  }
+
+  Pack<T, VEC> hp0, hp1, hp2, ep0, ep1, ep2;
+  if (active && inside) {
+    const i64 o = (i64)(xa - 1) * plane + p;
+    hp0 = ldv<T, VEC>(P.Hin[0] + o);
+    hp1 = ldv<T, VEC>(P.Hin[1] + o);
+    hp2 = ldv<T, VEC>(P.Hin[2] + o);
+  }
+
+  for (int i = xa; i <= xb; ++i) {
+    FDTD_CP_ASYNC_WAIT_1();
+    __syncthreads();
+    {
+      const int ip = i + 2;
+      if (ip <= xb && ip < P.x1) fused_stage_issue<T, VEC>(slots, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane);
+      FDTD_CP_ASYNC_COMMIT();
+    }
+    const T* sH = stages + (i % 3) * Lay::STAGE_WORDS;
+    const T* sE = sH + Lay::H_WORDS;
+    const i64 off = (i64)i * plane + p;
+    Pack<T, VEC> e0, e1, e2, h0, h1, h2;
+    if (active) {
+      if (inside && i < P.x1) {
+        // ---- E_new[i] = E_old + (sc eps^-1) * curl_H(H_old)      (fdtd/grid.py:54-76, 283)
+        const T* hrow = sH + ((r + 1) * HV + (l + 1)) * VEC;            // own vector of component 0
+        constexpr int HC = (R + 2) * HV * VEC;                          // words per staged H component
+        h0 = ldv<T, VEC>(hrow);
+        h1 = ldv<T, VEC>(hrow + HC);
+        h2 = ldv<T, VEC>(hrow + 2 * HC);
+        const Pack<T, VEC> y0v = ldv<T, VEC>(hrow - HV * VEC);
+        const Pack<T, VEC> y2v = ldv<T, VEC>(hrow + 2 * HC - HV * VEC);
+        const T zs0 = hrow[-1];
+        const T zs1 = hrow[HC - 1];
+        const T* erow = sE + (r * EV + l) * VEC;
+        constexpr int EC = (R + 1) * EV * VEC;
+        e0 = ldv<T, VEC>(erow);
+        e1 = ldv<T, VEC>(erow + EC);
+        e2 = ldv<T, VEC>(erow + 2 * EC);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const T zn0 = e == 0 ? zs0 : h0.v[e > 0 ? e - 1 : 0];
+          const T zn1 = e == 0 ? zs1 : h1.v[e > 0 ? e - 1 : 0];
+          const T d_zy = h2.v[e] - y2v.v[e];
+          const T d_xy = h0.v[e] - y0v.v[e];
+          const T d_yz = h1.v[e] - zn1;
+          const T d_xz = h0.v[e] - zn0;
+          const T d_zx = h2.v[e] - hp2.v[e];
+          const T d_yx = h1.v[e] - hp1.v[e];
+          e0.v[e] = e0.v[e] + P.ce[0] * (d_zy - d_yz);
+          e1.v[e] = e1.v[e] + P.ce[1] * (d_xz - d_zx);
+          e2.v[e] = e2.v[e] + P.ce[2] * (d_yx - d_xy);
+        }
+        if (src_yz) fused_sources_vec<T, VEC>(P, i, j, k0, off, e0, e1, e2);
+        if (core && i < xb) {
+          stv<T, VEC>(P.Eout[0] + off, e0);
+          stv<T, VEC>(P.Eout[1] + off, e1);
+          stv<T, VEC>(P.Eout[2] + off, e2);
+        }
+      } else {
+        // a shell cell (outside the box in y / z, or the plane x1): its E_new is already in memory
+        e0 = ldv<T, VEC>(P.Eout[0] + off);
+        e1 = ldv<T, VEC>(P.Eout[1] + off);
+        e2 = ldv<T, VEC>(P.Eout[2] + off);
+      }
+    }
+
+    // ---- H_new[i-1] = H_old - (sc mu^-1) * curl_E(E_new)      (fdtd/grid.py:29-51, 309)
+    constexpr int XC = (R + 1) * EV * VEC;                              // words per published component
+    if (core && i > xa) {
+      const T* x = xch + ((i - 1) & 1) * Lay::X_WORDS + (r * EV + l) * VEC;
+      Pack<T, VEC> hx = hp0, hy = hp1, hz = hp2;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T ex_y = x[EV * VEC + e];
+        const T ez_y = x[2 * XC + EV * VEC + e];
+        const T ex_z = e == VEC - 1 ? x[VEC] : ep0.v[e < VEC - 1 ? e + 1 : 0];
+        const T ey_z = e == VEC - 1 ? x[XC + VEC] : ep1.v[e < VEC - 1 ? e + 1 : 0];
+        const T d_zy = ez_y - ep2.v[e];
+        const T d_xy = ex_y - ep0.v[e];
+        const T d_yz = ey_z - ep1.v[e];
+        const T d_xz = ex_z - ep0.v[e];
+        const T d_zx = e2.v[e] - ep2.v[e];
+        const T d_yx = e1.v[e] - ep1.v[e];
+        hx.v[e] = hx.v[e] - P.ch[0] * (d_zy - d_yz);
+        hy.v[e] = hy.v[e] - P.ch[1] * (d_xz - d_zx);
+        hz.v[e] = hz.v[e] - P.ch[2] * (d_yx - d_xy);
+      }
+      const i64 om = off - plane;
+      stv<T, VEC>(P.Hout[0] + om, hx);
+      stv<T, VEC>(P.Hout[1] + om, hy);
+      stv<T, VEC>(P.Hout[2] + om, hz);
+    }
+
+    // ---- publish E_new[i] to the block, carry the planes ---------------------------------------------
+    if (active) {
+      T* x = xch + (i & 1) * Lay::X_WORDS + (r * EV + l) * VEC;
+      stv<T, VEC>(x, e0);
+      stv<T, VEC>(x + XC, e1);
+      stv<T, VEC>(x + 2 * XC, e2);
+      ep0 = e0;
+      ep1 = e1;
+      ep2 = e2;
+      if (inside && i < P.x1) {
+        hp0 = h0;
+        hp1 = h1;
+        hp2 = h2;
       }
     }
   }

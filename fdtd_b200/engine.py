@@ -237,7 +237,7 @@ class Engine:
             for c in range(3):
                 d.E2[c] = g._E2[c, 1].data_ptr()
                 d.H2[c] = g._H2[c, 1].data_ptr()
-            d.fuse_eh = 2 if int(g._fuse_eh) == 2 else 1
+            d.fuse_eh = int(g._fuse_eh) if int(g._fuse_eh) in (2, 3) else 1
 
         # CUDA-graph replay of step chunks pays off where a step is launch-bound (small grids)
         self._dyn = torch.zeros(2, dtype=torch.int64, device=g._E.device)

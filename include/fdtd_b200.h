@@ -181,7 +181,8 @@ typedef struct fdtd_desc {
   int32_t fuse_eh;     /* != 0: fdtd_run may run pairs of temporally fused E+H steps (12 instead of 18 words per cell
                           and step) on homogeneous unsharded grids; needs E2 / H2.  1 = shared-memory kernel (E_new exchanged through
                           shared memory, one barrier per plane), 2 = register-tiled kernel (no communication between
-                          threads) */
+                          threads), 3 = the shared-memory kernel with its inputs staged by cp.async two planes
+                          ahead */
   int32_t pad2_;
   void* E2[3];         /* second field buffers of the ping-pong pair, same layout as E / H (ghost planes included), */
   void* H2[3];         /* or NULL; after fdtd_run the results are always in E / H */

@@ -46,6 +46,7 @@ inline void launch(dim3 grid, dim3 block, F&& body) {
 }
 }  // namespace emu
 
+#include <string.h>
 #include <ucontext.h>
 
 #include <type_traits>
@@ -53,11 +54,19 @@ inline void launch(dim3 grid, dim3 block, F&& body) {
 
 namespace emu {
 // ---- cooperative launch: one fiber per thread of a block, for kernels with barriers ---------------------
+struct AsyncCopy {
+  void* dst;
+  const void* src;
+};
 struct Fiber {
   ucontext_t ctx;
   std::vector<char> stack;
   bool done = false;
   dim3 tid;
+  // cp.async emulation: copies are DEFERRED to the wait that covers their group (the latest moment the hardware
+  // may complete them), so a kernel that reads a staged value before waiting for it reads stale data here too
+  std::vector<AsyncCopy> open;
+  std::vector<std::vector<AsyncCopy>> groups;
 };
 inline thread_local ucontext_t t_sched;
 inline thread_local Fiber* t_cur = nullptr;
@@ -72,6 +81,19 @@ inline void fiber_main() {
 
 // __syncthreads(): every live thread of the block runs up to its next barrier before any continues
 inline void sync_threads() { swapcontext(&t_cur->ctx, &t_sched); }
+
+inline void cp_async16(void* dst, const void* src) { t_cur->open.push_back({dst, src}); }
+inline void cp_async_commit() {
+  t_cur->groups.push_back(std::move(t_cur->open));
+  t_cur->open.clear();
+}
+inline void cp_async_wait(size_t pending) {   // cp.async.wait_group N: at most N most recent groups stay pending
+  std::vector<std::vector<AsyncCopy>>& g = t_cur->groups;
+  while (g.size() > pending) {
+    for (const AsyncCopy& c : g.front()) memcpy(c.dst, c.src, 16);
+    g.erase(g.begin());
+  }
+}
 
 template <typename F>
 inline void launch_coop(dim3 grid, dim3 block, F&& body) {
@@ -94,6 +116,8 @@ inline void launch_coop(dim3 grid, dim3 block, F&& body) {
             for (unsigned tx = 0; tx < block.x; ++tx, ++t) {
               Fiber& f = fibers[t];
               f.done = false;
+              f.open.clear();
+              f.groups.clear();
               f.tid = dim3(tx, ty, tz);
               getcontext(&f.ctx);
               f.ctx.uc_stack.ss_sp = f.stack.data();

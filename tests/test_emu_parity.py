@@ -345,7 +345,7 @@ def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
         return g
 
     outs = []
-    for fuse, chunk in ((0, 0), (2, 0), (2, 3), (1, 0), (1, 5)):
+    for fuse, chunk in ((0, 0), (2, 0), (2, 3), (1, 0), (1, 5), (3, 0), (3, 4), (3, 1)):
         g = build()
         g._fuse_eh = fuse
         g._x_chunk = chunk
