@@ -6,7 +6,7 @@ loudly when it is missing: there is no CPU or PyTorch fallback for the hot path.
 import ctypes as C
 import os
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 MAX_SLABS, MAX_POST, MAX_SOURCES, MAX_DETECTORS, FUSED_MAX = 6, 16, 64, 64, 6
 F32, F64 = 0, 1
 CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT, CLS_ANISO, CLS_OVERLAP, CLS_ABSORB2 = 1, 2, 4, 8, 16, 32, 64
@@ -54,7 +54,8 @@ class Desc(C.Structure):
                 ("sources", Source * MAX_SOURCES), ("detectors", Detector * MAX_DETECTORS),
                 ("x_chunk", C.c_int32), ("use_graphs", C.c_int32), ("dyn", _vp),
                 ("fuse_eh", C.c_int32), ("pad2_", C.c_int32), ("E2", _vp * 3), ("H2", _vp * 3),
-                ("fuse_post", C.c_int32), ("x_wrap", C.c_int32)]
+                ("fuse_post", C.c_int32), ("pad3_", C.c_int32),
+                ("psi_E2", _vp * MAX_SLABS), ("x_wrap", C.c_int32), ("pad4_", C.c_int32)]
 
 
 EXPORTS = {

@@ -768,9 +768,14 @@ struct InteriorBox {
 // the largest box free of CPML cells and of the grid faces (where the curls are masked); z aligned to the vector
 bool interior_box(const fdtd_desc* d, int vec, InteriorBox* b) {
   int lo[3] = {1, 1, 1}, hi[3] = {d->Nx - 1, d->Ny - 1, d->Nz - 1};
+  const bool whole_rows = d->fuse_eh == 3;   // the pipelined kernel handles the z slabs and z faces itself
   for (int s = 0; s < d->n_slabs; ++s) {
     const fdtd_slab& S = d->slabs[s];
     if (!S.fused) return false;
+    if (whole_rows && S.axis == 2) {
+      if (!d->psi_E2[s] && S.psi_count > 0) return false;
+      continue;
+    }
     if (S.lo == 0) {
       if (S.thickness > lo[S.axis]) lo[S.axis] = S.thickness;
     } else if (S.lo < hi[S.axis]) {
@@ -779,8 +784,8 @@ bool interior_box(const fdtd_desc* d, int vec, InteriorBox* b) {
   }
   b->x0 = lo[0]; b->x1 = hi[0];
   b->y0 = lo[1]; b->y1 = hi[1];
-  b->z0 = (lo[2] + vec - 1) / vec * vec;
-  b->z1 = hi[2] / vec * vec;
+  b->z0 = whole_rows ? 0 : (lo[2] + vec - 1) / vec * vec;
+  b->z1 = whole_rows ? d->Nz : hi[2] / vec * vec;
 #ifdef FDTD_EMU
   // (CPU tests: any non-empty box, so that small grids with partial tiles exercise every branch)
   return b->x1 - b->x0 >= 2 && b->y1 - b->y0 >= 1 && b->z1 - b->z0 >= vec;
@@ -811,7 +816,7 @@ bool fuse_eh_eligible(const fdtd_desc* d, InteriorBox* box) {
 // one full step reading (Ein, Hin) and writing (Eout, Hout)
 template <typename T>
 int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, void* const* Eout, void* const* Hin,
-                  void* const* Hout, int64_t q, int64_t slot, void* stream) {
+                  void* const* Hout, int64_t q, int64_t slot, void* stream, int parity) {
   const int Nx = d->Nx, Ny = d->Ny, Nz = d->Nz;
   // the shell: six boxes around the interior box
   const int boxes[6][6] = {{0, B.x0, 0, Ny, 0, Nz},        {B.x1, Nx, 0, Ny, 0, Nz},
@@ -865,6 +870,25 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
   }
   const unsigned chunks = (B.x1 - B.x0 + P.x_chunk - 1) / P.x_chunk;
   if (d->fuse_eh == 3) {
+    // z slabs inside the kernel: psi_E read from one buffer and written to the other (parity 0: psi_E -> psi_E2)
+    for (int s = 0; s < d->n_slabs; ++s) {
+      const fdtd_slab& S = d->slabs[s];
+      if (S.axis != 2 || S.psi_count == 0) continue;
+      if (P.n_zs == 2) return fail(FDTD_ERR_UNSUPPORTED, "more than two z slabs");
+      const int n = P.n_zs++;
+      P.zs_lo[n] = S.lo;
+      P.zs_t[n] = S.thickness;
+      P.zs_lo_al[n] = z_slab_lo(S);
+      P.zs_tp[n] = z_slab_row(S);
+      P.zs_count[n] = S.psi_count;
+      P.zs_psiE_in[n] = (const T*)(parity == 0 ? S.psi_E : d->psi_E2[s]);
+      P.zs_psiE_out[n] = (T*)(parity == 0 ? d->psi_E2[s] : S.psi_E);
+      P.zs_psiH[n] = (T*)S.psi_H;
+      P.zs_bE[n] = (const T*)S.bE;
+      P.zs_cE[n] = (const T*)S.cE;
+      P.zs_bH[n] = (const T*)S.bH;
+      P.zs_cH[n] = (const T*)S.cH;
+    }
     // the pipelined variant: inputs staged in shared memory by cp.async two planes ahead
     using Lay = fdtd::FusedPipeLayout<T, VEC>;
     dim3 grid((B.z1 - B.z0 + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC),
@@ -1009,12 +1033,12 @@ int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void
     if (nsteps >= 2 && fuse_eh_eligible(d, &box)) {
       for (; s + 2 <= nsteps; s += 2) {
         rc = d->dtype == FDTD_F32
-                 ? fused_eh_step<float>(d, box, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream)
-                 : fused_eh_step<double>(d, box, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream);
+                 ? fused_eh_step<float>(d, box, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream, 0)
+                 : fused_eh_step<double>(d, box, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream, 0);
         if (rc) return rc;
         rc = d->dtype == FDTD_F32
-                 ? fused_eh_step<float>(d, box, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream)
-                 : fused_eh_step<double>(d, box, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream);
+                 ? fused_eh_step<float>(d, box, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream, 1)
+                 : fused_eh_step<double>(d, box, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream, 1);
         if (rc) return rc;
       }
     }

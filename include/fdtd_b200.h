@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 13
+#define FDTD_ABI_VERSION 14
 
 #define FDTD_F32 0
 #define FDTD_F64 1
@@ -188,10 +188,16 @@ typedef struct fdtd_desc {
   void* H2[3];         /* or NULL; after fdtd_run the results are always in E / H */
   int32_t fuse_post;   /* sources/detectors folded into the half-step kernel: 1 always (when legal), 0 never,
                           -1 automatic (local slabs up to 2^23 cells, where a step is launch-bound) */
+  int32_t pad3_;
+  void* psi_E2[FDTD_MAX_SLABS];  /* fuse_eh = 3: a second psi_E buffer [2][psi_count] for every z slab (axis 2), NULL for
+                          the others.  That kernel also updates the z-CPML cells of the interior rows in its single
+                          pass; cells whose E_new is recomputed by a neighbouring thread need the OLD psi_E, so psi_E
+                          alternates between the two buffers like the fields (results always end in psi_E) */
   int32_t x_wrap;      /* x-sharded grid with a periodic x boundary (fdtd/boundaries.py:184-195): 0 = none, else
                           1 + the number of post ops registered before it.  The copy E[0] = E[-1] / H[-1] = H[0] then
                           crosses the first and last slab: the caller runs fdtd_post_part(.., 0, ..), moves the plane
                           between the two ranks itself, then fdtd_post_part(.., 1, ..) */
+  int32_t pad4_;
 } fdtd_desc;
 
 /* --- queries ------------------------------------------------------------------------- */

@@ -7,7 +7,13 @@ for lib in fdtd_b200/_variants/lib_rt_*.so; do
   echo "# $lib"
   TUNE_LIB=$lib FDTD_B200_FUSE_EH=2 timeout 60 python scripts/bench_configs.py c4 2>&1 | tail -1
 done
+for lib in fdtd_b200/_variants/lib_pipe_*.so; do
+  echo "# $lib"
+  TUNE_LIB=$lib FDTD_B200_FUSE_EH=3 timeout 60 python scripts/bench_configs.py c4 2>&1 | tail -1
+done
 echo "# two half-steps"
 FDTD_B200_FUSE_EH=0 timeout 60 python scripts/bench_configs.py c4 2>&1 | tail -1
 echo "# shared-memory fused kernel"
 FDTD_B200_FUSE_EH=1 timeout 60 python scripts/bench_configs.py c4 2>&1 | tail -1
+echo "# pipelined fused kernel (default build)"
+FDTD_B200_FUSE_EH=3 timeout 60 python scripts/bench_configs.py c4 2>&1 | tail -1

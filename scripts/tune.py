@@ -27,6 +27,13 @@ VARIANTS = {
     "rt_r4_w4_mb2": ["-DFDTD_FUSED_RT_ROWS=4", "-DFDTD_FUSED_RT_WARPS=4", "-DFDTD_FUSED_RT_MIN_BLOCKS=2"],
     "rt_r4_w2_mb4": ["-DFDTD_FUSED_RT_ROWS=4", "-DFDTD_FUSED_RT_WARPS=2", "-DFDTD_FUSED_RT_MIN_BLOCKS=4"],
     "rt_r1_w4_mb4": ["-DFDTD_FUSED_RT_ROWS=1", "-DFDTD_FUSED_RT_WARPS=4", "-DFDTD_FUSED_RT_MIN_BLOCKS=4"],
+    # cp.async-pipelined fused kernel (FDTD_B200_FUSE_EH=3): tile and blocks per SM (shared memory: 3 stages + 2 tiles)
+    "pipe_r4l32_mb3": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=3"],
+    "pipe_r4l32_mb2": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
+    "pipe_r8l32_mb1": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=1"],
+    "pipe_r8l16_mb2": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_LANES=16", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
+    "pipe_r2l32_mb4": ["-DFDTD_FUSED_ROWS=2", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4"],
+    "pipe_r4l16_mb4": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=16", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4"],
     "post_inline": ["-DFDTD_POST_INLINE=1"],
     "hdown": ["-DFDTD_H_DOWNWARD=1"],
     "fz_pf0": ["-DFDTD_FUSED_PREFETCH=0"],

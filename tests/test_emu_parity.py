@@ -318,9 +318,10 @@ def test_running_dft_of_a_current_detector():
                 det.spectrum_E
 
 
-@pytest.mark.parametrize("dtype,n,t", [("float32", (20, 23, 40), 3), ("float64", (14, 21, 22), 3),
-                                       ("float32", (13, 9, 16), 2), ("float32", (12, 40, 144), 2)])
-def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
+@pytest.mark.parametrize("dtype,n,t,zp", [("float32", (20, 23, 40), 3, "lo"), ("float64", (14, 21, 22), 3, "both"),
+                                          ("float32", (13, 9, 16), 2, "none"), ("float32", (12, 40, 144), 2, "both"),
+                                          ("float64", (12, 11, 136), 2, "hi")])
+def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t, zp):
     """run() with the single-pass E+H kernels on the interior (ping-pong buffers, ordinary kernels on the PML
     shell) reproduces the two-half-step path bit for bit -- the shared-memory kernel (variant 1: E_new exchanged
     through shared memory, one barrier per plane; its block runs as cooperative fibers here) and the
@@ -335,9 +336,14 @@ def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
         g[-t:, :, :] = fd.PML()
         g[:, 0:t, :] = fd.PML()
         g[:, -t:, :] = fd.PML()
-        g[:, :, 0:t + 1] = fd.PML()
+        if zp in ("lo", "both"):
+            g[:, :, 0:t + 1] = fd.PML()
+        if zp in ("hi", "both"):
+            g[:, :, -(t + 2):] = fd.PML()
         g[n[0] // 2, n[1] // 2, n[2] // 2] = fd.PointSource(period=17, name="centre")
         g[2, n[1] // 2, 3] = fd.PointSource(period=11, amplitude=0.4, name="in_pml")
+        g[n[0] // 2, n[1] // 2 - 1, 0] = fd.PointSource(period=13, amplitude=0.3, name="on_z_face")
+        g[n[0] // 2 - 1, n[1] // 2, n[2] - 1] = fd.PointSource(period=15, amplitude=0.5, name="on_far_z_face")
         g[t + 1:n[0] - t - 1, t + 1:n[1] - t - 1, n[2] // 3] = fd.LineSource(period=23, name="line")
         g[n[0] // 2 + 1, n[1] - t - 1, n[2] - 2] = fd.PointSource(period=9, amplitude=0.7, name="box_corner")
         g[1:n[0] - 1, n[1] // 2 + 1, n[2] // 2 + 2] = fd.LineDetector(name="across")
