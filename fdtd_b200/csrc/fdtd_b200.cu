@@ -768,11 +768,11 @@ struct InteriorBox {
 // the largest box free of CPML cells and of the grid faces (where the curls are masked); z aligned to the vector
 bool interior_box(const fdtd_desc* d, int vec, InteriorBox* b) {
   int lo[3] = {1, 1, 1}, hi[3] = {d->Nx - 1, d->Ny - 1, d->Nz - 1};
-  const bool whole_rows = d->fuse_eh == 3;   // the pipelined kernel handles the z slabs and z faces itself
+  const bool whole_rows = d->fuse_eh == 3;   // the pipelined kernel handles every slab and face itself: no shell
   for (int s = 0; s < d->n_slabs; ++s) {
     const fdtd_slab& S = d->slabs[s];
     if (!S.fused) return false;
-    if (whole_rows && S.axis == 2) {
+    if (whole_rows) {
       if (!d->psi_E2[s] && S.psi_count > 0) return false;
       continue;
     }
@@ -782,8 +782,10 @@ bool interior_box(const fdtd_desc* d, int vec, InteriorBox* b) {
       hi[S.axis] = S.lo;
     }
   }
-  b->x0 = lo[0]; b->x1 = hi[0];
-  b->y0 = lo[1]; b->y1 = hi[1];
+  b->x0 = whole_rows ? 0 : lo[0];
+  b->x1 = whole_rows ? d->Nx : hi[0];
+  b->y0 = whole_rows ? 0 : lo[1];
+  b->y1 = whole_rows ? d->Ny : hi[1];
   b->z0 = whole_rows ? 0 : (lo[2] + vec - 1) / vec * vec;
   b->z1 = whole_rows ? d->Nz : hi[2] / vec * vec;
 #ifdef FDTD_EMU
@@ -838,11 +840,14 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
     if (w < 0 || w >= S.wave_len)
       return fail(FDTD_ERR_ARG, "source %d: step %lld outside its waveform table", n, (long long)q);
     if (S.n == 0) continue;
-    FDTD_LAUNCH((fdtd::source_points_outside_kernel<T>), dim3(blocks_for(S.n)), dim3(256), stream, (T*)Eout[S.comp],
-                (const i64*)S.idx, (const T*)S.profile, S.n, (const T*)S.wave, (i64)w, (i64)d->plane, Nz, B.x0, B.x1,
-                B.y0, B.y1, B.z0, B.z1);
-    rc = check_launch("shell source");
-    if (rc) return rc;
+    const bool whole_grid = B.x0 == 0 && B.x1 == Nx && B.y0 == 0 && B.y1 == Ny && B.z0 == 0 && B.z1 == Nz;
+    if (!whole_grid) {
+      FDTD_LAUNCH((fdtd::source_points_outside_kernel<T>), dim3(blocks_for(S.n)), dim3(256), stream, (T*)Eout[S.comp],
+                  (const i64*)S.idx, (const T*)S.profile, S.n, (const T*)S.wave, (i64)w, (i64)d->plane, Nz, B.x0, B.x1,
+                  B.y0, B.y1, B.z0, B.z1);
+      rc = check_launch("shell source");
+      if (rc) return rc;
+    }
     fdtd::SrcK<T>& K = P.src[P.n_src++];
     K.kind = S.kind;
     K.comp = S.comp;
@@ -870,24 +875,26 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
   }
   const unsigned chunks = (B.x1 - B.x0 + P.x_chunk - 1) / P.x_chunk;
   if (d->fuse_eh == 3) {
-    // z slabs inside the kernel: psi_E read from one buffer and written to the other (parity 0: psi_E -> psi_E2)
+    // every slab inside the kernel, registration order: psi_E read from one buffer and written to the other
+    // (parity 0: psi_E -> psi_E2)
+    P.Nx = Nx;
     for (int s = 0; s < d->n_slabs; ++s) {
       const fdtd_slab& S = d->slabs[s];
-      if (S.axis != 2 || S.psi_count == 0) continue;
-      if (P.n_zs == 2) return fail(FDTD_ERR_UNSUPPORTED, "more than two z slabs");
-      const int n = P.n_zs++;
-      P.zs_lo[n] = S.lo;
-      P.zs_t[n] = S.thickness;
-      P.zs_lo_al[n] = z_slab_lo(S);
-      P.zs_tp[n] = z_slab_row(S);
-      P.zs_count[n] = S.psi_count;
-      P.zs_psiE_in[n] = (const T*)(parity == 0 ? S.psi_E : d->psi_E2[s]);
-      P.zs_psiE_out[n] = (T*)(parity == 0 ? d->psi_E2[s] : S.psi_E);
-      P.zs_psiH[n] = (T*)S.psi_H;
-      P.zs_bE[n] = (const T*)S.bE;
-      P.zs_cE[n] = (const T*)S.cE;
-      P.zs_bH[n] = (const T*)S.bH;
-      P.zs_cH[n] = (const T*)S.cH;
+      if (S.psi_count == 0) continue;
+      typename fdtd::FusedParams<T>::Slab& K = P.sl[P.n_sl++];
+      K.axis = S.axis;
+      K.lo = S.lo;
+      K.t = S.thickness;
+      K.lo_al = z_slab_lo(S);
+      K.tp = z_slab_row(S);
+      K.count = S.psi_count;
+      K.psiE_in = (const T*)(parity == 0 ? S.psi_E : d->psi_E2[s]);
+      K.psiE_out = (T*)(parity == 0 ? d->psi_E2[s] : S.psi_E);
+      K.psiH = (T*)S.psi_H;
+      K.bE = (const T*)S.bE;
+      K.cE = (const T*)S.cE;
+      K.bH = (const T*)S.bH;
+      K.cH = (const T*)S.cH;
     }
     // the pipelined variant: inputs staged in shared memory by cp.async two planes ahead
     using Lay = fdtd::FusedPipeLayout<T, VEC>;

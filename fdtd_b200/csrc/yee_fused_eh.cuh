@@ -46,19 +46,23 @@ struct FusedParams {
   T ce[3], ch[3];  // sc * background eps^-1 / mu^-1, rounded as the reference rounds them
   int n_src;
   SrcK<T> src[FDTD_FUSED_MAX];  // soft point-list sources on E (ascending idx)
-  // fused_eh_pipe_kernel only: the box spans whole z rows (z0 = 0, z1 = Nz), so the z-CPML slabs and the masked
-  // one-sided differences at the two z faces are handled inside the kernel.  psi_E is ping-pong like the fields
-  // (halo cells recompute E_new from the OLD psi while the owner writes the new one); psi_H is owner-only, in place.
-  int n_zs;
-  int zs_lo[2], zs_t[2], zs_lo_al[2], zs_tp[2];
-  i64 zs_count[2];
-  const T* zs_psiE_in[2];
-  T* zs_psiE_out[2];
-  T* zs_psiH[2];
-  const T* zs_bE[2];
-  const T* zs_cE[2];
-  const T* zs_bH[2];
-  const T* zs_cH[2];
+  // fused_eh_pipe_kernel only: the box is the WHOLE grid, so every CPML slab and the masked one-sided differences
+  // at the six faces are handled inside the kernel, in registration order -- one kernel per step, no shell.
+  // psi_E is ping-pong like the fields (halo cells and the last plane of an x-chunk recompute E_new from the OLD
+  // psi while the owner writes the new one); psi_H is owner-only, in place.
+  int Nx;
+  int n_sl;
+  struct Slab {
+    int axis, lo, t, lo_al, tp;   // lo_al / tp: padded psi rows of z slabs (include/fdtd_b200.h)
+    i64 count;
+    const T* psiE_in;
+    T* psiE_out;
+    T* psiH;
+    const T* bE;
+    const T* cE;
+    const T* bH;
+    const T* cH;
+  } sl[6];
 };
 
 // soft point sources of the box on the VEC recomputed E values of a thread, registration order
@@ -626,7 +630,7 @@ FDTD_DEV void fused_copy_slots(const FusedParams<T>& P, FusedCopySlots<T, VEC>& 
       k = kz0 + (rem % EV) * VEC;
       F = P.Ein;
     }
-    if (j < P.y1 && k < P.z1 && k >= 0) {   // (beyond the box nothing is recomputed: the shell's result is used)
+    if (j < P.y1 && k < P.z1 && j >= 0 && k >= 0) {   // (beyond the box nothing is recomputed: the shell's result is used)
       S.off[n] = v * VEC;
       S.src[n] = F[c] + (i64)j * P.Nz + k;
     }
@@ -657,7 +661,8 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   const int j = j0 + r, k0 = kz0 + l * VEC;
   const int Nz = P.Nz;
   const bool core = (r < R) && (l < L) && (j < P.y1) && (k0 < P.z1);
-  const bool active = (j <= P.y1) && (k0 <= P.z1) && (k0 < Nz);   // (z1 == Nz: there is no z+1 neighbour column)
+  // (y1 == Ny / z1 == Nz: there is no y+1 neighbour row / z+1 neighbour column)
+  const bool active = (j <= P.y1) && (k0 <= P.z1) && (j < P.Ny) && (k0 < Nz);
   const bool inside = (j < P.y1) && (k0 < P.z1);
   const i64 plane = P.plane;
   const i64 p = (i64)j * Nz + k0;
@@ -667,9 +672,11 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   bool src_yz = false;
   for (int s = 0; s < P.n_src; ++s)
     src_yz |= (j >= P.src[s].bb[2]) && (j < P.src[s].bb[3]) && (k0 + VEC > P.src[s].bb[4]) && (k0 < P.src[s].bb[5]);
-  // z-CPML slabs this thread's cells lie in (loop-invariant)
-  bool zs_hit[2] = {false, false};
-  for (int s = 0; s < P.n_zs; ++s) zs_hit[s] = (k0 - P.zs_lo[s] + VEC > 0) && (k0 - P.zs_lo[s] < P.zs_t[s]);
+  // CPML slabs this thread's cells lie in (loop-invariant)
+  bool sl_hit[6] = {false, false, false, false, false, false};   // (x slabs: decided per plane)
+  for (int s = 0; s < P.n_sl; ++s)
+    sl_hit[s] = P.sl[s].axis == 1 ? (j >= P.sl[s].lo && j < P.sl[s].lo + P.sl[s].t)
+                                  : (k0 - P.sl[s].lo + VEC > 0) && (k0 - P.sl[s].lo < P.sl[s].t);
 
   FusedCopySlots<T, VEC> slots;
   fused_copy_slots<T, VEC>(P, slots, j0, kz0, tid);
@@ -681,7 +688,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   }
 
   Pack<T, VEC> hp0, hp1, hp2, ep0, ep1, ep2;
-  if (active && inside) {
+  if (active && inside && xa > 0) {
     const i64 o = (i64)(xa - 1) * plane + p;
     hp0 = ldv<T, VEC>(P.Hin[0] + o);
     hp1 = ldv<T, VEC>(P.Hin[1] + o);
@@ -717,56 +724,75 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
         e0 = ldv<T, VEC>(erow);
         e1 = ldv<T, VEC>(erow + EC);
         e2 = ldv<T, VEC>(erow + 2 * EC);
-        T dyz[VEC], dxz[VEC];
+        T dyz[VEC], dxz[VEC], dzy[VEC], dxy[VEC], dzx[VEC], dyx[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           const T zn0 = e == 0 ? zs0 : h0.v[e > 0 ? e - 1 : 0];
           const T zn1 = e == 0 ? zs1 : h1.v[e > 0 ? e - 1 : 0];
-          const T d_zy = h2.v[e] - y2v.v[e];
-          const T d_xy = h0.v[e] - y0v.v[e];
-          // backward z-differences are masked on the face k = 0 (fdtd/grid.py:66-74)
-          const bool face = (e == 0) && (k0 == 0);
-          const T d_yz = face ? T(0) : h1.v[e] - zn1;
-          const T d_xz = face ? T(0) : h0.v[e] - zn0;
-          const T d_zx = h2.v[e] - hp2.v[e];
-          const T d_yx = h1.v[e] - hp1.v[e];
+          // backward differences are masked on the faces i = 0, j = 0 and k = 0 (fdtd/grid.py:66-74)
+          const bool face_x = i == 0;
+          const bool face_y = j == 0;
+          const bool face_z = (e == 0) && (k0 == 0);
+          const T d_zy = face_y ? T(0) : h2.v[e] - y2v.v[e];
+          const T d_xy = face_y ? T(0) : h0.v[e] - y0v.v[e];
+          const T d_yz = face_z ? T(0) : h1.v[e] - zn1;
+          const T d_xz = face_z ? T(0) : h0.v[e] - zn0;
+          const T d_zx = face_x ? T(0) : h2.v[e] - hp2.v[e];
+          const T d_yx = face_x ? T(0) : h1.v[e] - hp1.v[e];
           dyz[e] = d_yz;
           dxz[e] = d_xz;
+          dzy[e] = d_zy;
+          dxy[e] = d_xy;
+          dzx[e] = d_zx;
+          dyx[e] = d_yx;
           e0.v[e] = e0.v[e] + P.ce[0] * (d_zy - d_yz);
           e1.v[e] = e1.v[e] + P.ce[1] * (d_xz - d_zx);
           e2.v[e] = e2.v[e] + P.ce[2] * (d_yx - d_xy);
         }
-        // z-CPML slabs, registration order: psi_E from the OLD buffer, corrections of Ex (-) and Ey (+)
+        // CPML slabs, registration order: psi_E from the OLD buffer; an x slab corrects Ey (-) and Ez (+), a y slab
+        // Ez (-) and Ex (+), a z slab Ex (-) and Ey (+)
         // (fdtd/boundaries.py:433-459, 409-419; same operations as slab_cells)
-        for (int s = 0; s < P.n_zs; ++s) {
-          if (!zs_hit[s]) continue;
-          const int l0 = k0 - P.zs_lo[s];
-          const i64 idx = ((i64)i * P.Ny + j) * P.zs_tp[s] + (k0 - P.zs_lo_al[s]);
-          Pack<T, VEC> a = ldv<T, VEC>(P.zs_psiE_in[s] + idx);
-          Pack<T, VEC> b = ldv<T, VEC>(P.zs_psiE_in[s] + P.zs_count[s] + idx);
+        for (int s = 0; s < P.n_sl; ++s) {
+          const typename FusedParams<T>::Slab& S = P.sl[s];
+          const int ax = S.axis;
+          if (ax == 0 ? (i < S.lo || i >= S.lo + S.t) : !sl_hit[s]) continue;
+          const int l0 = ax == 0 ? i - S.lo : (ax == 1 ? j - S.lo : k0 - S.lo);
+          const i64 idx = ax == 0 ? (i64)l0 * plane + p
+                                  : (ax == 1 ? ((i64)i * S.t + l0) * Nz + k0
+                                             : ((i64)i * P.Ny + j) * S.tp + (k0 - S.lo_al));
+          Pack<T, VEC> a = ldv<T, VEC>(S.psiE_in + idx);
+          Pack<T, VEC> b = ldv<T, VEC>(S.psiE_in + S.count + idx);
 #pragma unroll
           for (int e = 0; e < VEC; ++e) {
-            const int ll = l0 + e;
-            if (ll >= 0 && ll < P.zs_t[s]) {
-              const T bb = P.zs_bE[s][ll];
-              const T cc = P.zs_cE[s][ll];
+            const int ll = ax == 2 ? l0 + e : l0;
+            if (ll >= 0 && ll < S.t) {
+              const T bb = S.bE[ll];
+              const T cc = S.cE[ll];
               T p0 = a.v[e] * bb;
               T p1 = b.v[e] * bb;
               if (ll >= 1) {
-                p0 = p0 + dyz[e] * cc;
-                p1 = p1 + dxz[e] * cc;
+                p0 = p0 + (ax == 0 ? dzx[e] : (ax == 1 ? dxy[e] : dyz[e])) * cc;
+                p1 = p1 + (ax == 0 ? dyx[e] : (ax == 1 ? dzy[e] : dxz[e])) * cc;
               }
               a.v[e] = p0;
               b.v[e] = p1;
               const T phi_u = T(0) - p0;
               const T phi_w = p1 - T(0);
-              e0.v[e] = e0.v[e] + P.ce[0] * phi_u;
-              e1.v[e] = e1.v[e] + P.ce[1] * phi_w;
+              if (ax == 0) {
+                e1.v[e] = e1.v[e] + P.ce[1] * phi_u;
+                e2.v[e] = e2.v[e] + P.ce[2] * phi_w;
+              } else if (ax == 1) {
+                e2.v[e] = e2.v[e] + P.ce[2] * phi_u;
+                e0.v[e] = e0.v[e] + P.ce[0] * phi_w;
+              } else {
+                e0.v[e] = e0.v[e] + P.ce[0] * phi_u;
+                e1.v[e] = e1.v[e] + P.ce[1] * phi_w;
+              }
             }
           }
           if (core && i < xb) {
-            stv<T, VEC>(P.zs_psiE_out[s] + idx, a);
-            stv<T, VEC>(P.zs_psiE_out[s] + P.zs_count[s] + idx, b);
+            stv<T, VEC>(S.psiE_out + idx, a);
+            stv<T, VEC>(S.psiE_out + S.count + idx, b);
           }
         }
         if (src_yz) fused_sources_vec<T, VEC>(P, i, j, k0, off, e0, e1, e2);
@@ -775,7 +801,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
           stv<T, VEC>(P.Eout[1] + off, e1);
           stv<T, VEC>(P.Eout[2] + off, e2);
         }
-      } else {
+      } else if (i < P.Nx) {
         // a shell cell (outside the box in y / z, or the plane x1): its E_new is already in memory
         e0 = ldv<T, VEC>(P.Eout[0] + off);
         e1 = ldv<T, VEC>(P.Eout[1] + off);
@@ -788,57 +814,76 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     if (core && i > xa) {
       const T* x = xch + ((i - 1) & 1) * Lay::X_WORDS + (r * EV + l) * VEC;
       Pack<T, VEC> hx = hp0, hy = hp1, hz = hp2;
-      T dyz[VEC], dxz[VEC];
+      T dyz[VEC], dxz[VEC], dzy[VEC], dxy[VEC], dzx[VEC], dyx[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const T ex_y = x[EV * VEC + e];
         const T ez_y = x[2 * XC + EV * VEC + e];
         const T ex_z = e == VEC - 1 ? x[VEC] : ep0.v[e < VEC - 1 ? e + 1 : 0];
         const T ey_z = e == VEC - 1 ? x[XC + VEC] : ep1.v[e < VEC - 1 ? e + 1 : 0];
-        const T d_zy = ez_y - ep2.v[e];
-        const T d_xy = ex_y - ep0.v[e];
-        // forward z-differences are masked on the face k = Nz-1 (fdtd/grid.py:41-49)
-        const bool face = (e == VEC - 1) && (k0 + VEC == Nz);
-        const T d_yz = face ? T(0) : ey_z - ep1.v[e];
-        const T d_xz = face ? T(0) : ex_z - ep0.v[e];
-        const T d_zx = e2.v[e] - ep2.v[e];
-        const T d_yx = e1.v[e] - ep1.v[e];
+        // forward differences are masked on the faces i = Nx-1, j = Ny-1 and k = Nz-1 (fdtd/grid.py:41-49)
+        const bool face_x = i == P.Nx;
+        const bool face_y = j == P.Ny - 1;
+        const bool face_z = (e == VEC - 1) && (k0 + VEC == Nz);
+        const T d_zy = face_y ? T(0) : ez_y - ep2.v[e];
+        const T d_xy = face_y ? T(0) : ex_y - ep0.v[e];
+        const T d_yz = face_z ? T(0) : ey_z - ep1.v[e];
+        const T d_xz = face_z ? T(0) : ex_z - ep0.v[e];
+        const T d_zx = face_x ? T(0) : e2.v[e] - ep2.v[e];
+        const T d_yx = face_x ? T(0) : e1.v[e] - ep1.v[e];
         dyz[e] = d_yz;
         dxz[e] = d_xz;
+        dzy[e] = d_zy;
+        dxy[e] = d_xy;
+        dzx[e] = d_zx;
+        dyx[e] = d_yx;
         hx.v[e] = hx.v[e] - P.ch[0] * (d_zy - d_yz);
         hy.v[e] = hy.v[e] - P.ch[1] * (d_xz - d_zx);
         hz.v[e] = hz.v[e] - P.ch[2] * (d_yx - d_xy);
       }
-      // z-CPML slabs: psi_H in place (only the owner touches it), corrections of Hx and Hy
-      // (fdtd/boundaries.py:461-487, 421-431)
-      for (int s = 0; s < P.n_zs; ++s) {
-        if (!zs_hit[s]) continue;
-        const int l0 = k0 - P.zs_lo[s];
-        const i64 idx = ((i64)(i - 1) * P.Ny + j) * P.zs_tp[s] + (k0 - P.zs_lo_al[s]);
-        Pack<T, VEC> a = ldv<T, VEC>(P.zs_psiH[s] + idx);
-        Pack<T, VEC> b = ldv<T, VEC>(P.zs_psiH[s] + P.zs_count[s] + idx);
+      // CPML slabs, registration order: psi_H in place (only the owner touches it); an x slab corrects Hy and Hz,
+      // a y slab Hz and Hx, a z slab Hx and Hy      (fdtd/boundaries.py:461-487, 421-431)
+      const int ih = i - 1;
+      for (int s = 0; s < P.n_sl; ++s) {
+        const typename FusedParams<T>::Slab& S = P.sl[s];
+        const int ax = S.axis;
+        if (ax == 0 ? (ih < S.lo || ih >= S.lo + S.t) : !sl_hit[s]) continue;
+        const int l0 = ax == 0 ? ih - S.lo : (ax == 1 ? j - S.lo : k0 - S.lo);
+        const i64 idx = ax == 0 ? (i64)l0 * plane + p
+                                : (ax == 1 ? ((i64)ih * S.t + l0) * Nz + k0
+                                           : ((i64)ih * P.Ny + j) * S.tp + (k0 - S.lo_al));
+        Pack<T, VEC> a = ldv<T, VEC>(S.psiH + idx);
+        Pack<T, VEC> b = ldv<T, VEC>(S.psiH + S.count + idx);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-          const int ll = l0 + e;
-          if (ll >= 0 && ll < P.zs_t[s]) {
-            const T bb = P.zs_bH[s][ll];
-            const T cc = P.zs_cH[s][ll];
+          const int ll = ax == 2 ? l0 + e : l0;
+          if (ll >= 0 && ll < S.t) {
+            const T bb = S.bH[ll];
+            const T cc = S.cH[ll];
             T p0 = a.v[e] * bb;
             T p1 = b.v[e] * bb;
-            if (ll < P.zs_t[s] - 1) {
-              p0 = p0 + dyz[e] * cc;
-              p1 = p1 + dxz[e] * cc;
+            if (ll < S.t - 1) {
+              p0 = p0 + (ax == 0 ? dzx[e] : (ax == 1 ? dxy[e] : dyz[e])) * cc;
+              p1 = p1 + (ax == 0 ? dyx[e] : (ax == 1 ? dzy[e] : dxz[e])) * cc;
             }
             a.v[e] = p0;
             b.v[e] = p1;
             const T phi_u = T(0) - p0;
             const T phi_w = p1 - T(0);
-            hx.v[e] = hx.v[e] - P.ch[0] * phi_u;
-            hy.v[e] = hy.v[e] - P.ch[1] * phi_w;
+            if (ax == 0) {
+              hy.v[e] = hy.v[e] - P.ch[1] * phi_u;
+              hz.v[e] = hz.v[e] - P.ch[2] * phi_w;
+            } else if (ax == 1) {
+              hz.v[e] = hz.v[e] - P.ch[2] * phi_u;
+              hx.v[e] = hx.v[e] - P.ch[0] * phi_w;
+            } else {
+              hx.v[e] = hx.v[e] - P.ch[0] * phi_u;
+              hy.v[e] = hy.v[e] - P.ch[1] * phi_w;
+            }
           }
         }
-        stv<T, VEC>(P.zs_psiH[s] + idx, a);
-        stv<T, VEC>(P.zs_psiH[s] + P.zs_count[s] + idx, b);
+        stv<T, VEC>(S.psiH + idx, a);
+        stv<T, VEC>(S.psiH + S.count + idx, b);
       }
       const i64 om = off - plane;
       stv<T, VEC>(P.Hout[0] + om, hx);

@@ -239,11 +239,10 @@ class Engine:
                 d.H2[c] = g._H2[c, 1].data_ptr()
             d.fuse_eh = int(g._fuse_eh) if int(g._fuse_eh) in (2, 3) else 1
             if d.fuse_eh == 3:
-                for idx, b in enumerate(slabs):          # z slabs: psi_E ping-pong (include/fdtd_b200.h, psi_E2)
-                    if b.axis == 2:
-                        if getattr(b, "_psi_E2", None) is None:
-                            b._psi_E2 = torch.zeros_like(b._psi_E)
-                        d.psi_E2[idx] = _ptr(b._psi_E2)
+                for idx, b in enumerate(slabs):          # psi_E ping-pong (include/fdtd_b200.h, psi_E2)
+                    if getattr(b, "_psi_E2", None) is None:
+                        b._psi_E2 = torch.zeros_like(b._psi_E)
+                    d.psi_E2[idx] = _ptr(b._psi_E2)
 
         # CUDA-graph replay of step chunks pays off where a step is launch-bound (small grids)
         self._dyn = torch.zeros(2, dtype=torch.int64, device=g._E.device)

@@ -189,9 +189,8 @@ typedef struct fdtd_desc {
   int32_t fuse_post;   /* sources/detectors folded into the half-step kernel: 1 always (when legal), 0 never,
                           -1 automatic (local slabs up to 2^23 cells, where a step is launch-bound) */
   int32_t pad3_;
-  void* psi_E2[FDTD_MAX_SLABS];  /* fuse_eh = 3: a second psi_E buffer [2][psi_count] for every z slab (axis 2), NULL for
-                          the others.  That kernel also updates the z-CPML cells of the interior rows in its single
-                          pass; cells whose E_new is recomputed by a neighbouring thread need the OLD psi_E, so psi_E
+  void* psi_E2[FDTD_MAX_SLABS];  /* fuse_eh = 3: a second psi_E buffer [2][psi_count] for every slab.  That kernel
+                          updates the whole grid, CPML cells and faces included, in its single pass; cells whose E_new is recomputed by a neighbouring thread need the OLD psi_E, so psi_E
                           alternates between the two buffers like the fields (results always end in psi_E) */
   int32_t x_wrap;      /* x-sharded grid with a periodic x boundary (fdtd/boundaries.py:184-195): 0 = none, else
                           1 + the number of post ops registered before it.  The copy E[0] = E[-1] / H[-1] = H[0] then

@@ -17,6 +17,8 @@ def build(n, t):
     g[0:t, :, :] = fd.PML(); g[-t:, :, :] = fd.PML()
     g[:, 0:t, :] = fd.PML(); g[:, -t:, :] = fd.PML()
     g[:, :, 0:t + 1] = fd.PML()
+    g[:, :, -t:] = fd.PML()
+    g[0, 3, 5] = fd.PointSource(period=9, amplitude=0.3)          # on a face, inside a PML
     g[n[0] // 2, n[1] // 2, n[2] // 2] = fd.PointSource(period=17)
     g[t + 2:n[0] - t - 2, t + 3:n[1] - t - 3, n[2] // 3] = fd.LineSource(period=23)
     g[1:n[0] - 1, n[1] // 2 + 1, n[2] // 2 + 2] = fd.LineDetector()
