@@ -557,6 +557,9 @@ __global__ void __launch_bounds__(32 * FUSED_RT_WARPS, FDTD_FUSED_RT_MIN_BLOCKS)
 // one of three shared-memory stages through asynchronous 16-byte copies (LDGSTS, L2 only) issued two iterations
 // before they are consumed, so the one barrier per plane no longer exposes the memory latency of the slowest warp.
 // Each global word is requested once per block (the y-1 / z-1 neighbours come out of the staged tile).
+// STATUS (round 1): bit-identical on the B200, but as built 2.8x SLOWER than the two half-steps at 512^3 f32
+// (profiles/r1_fused_pipe_check.log) -- never profiled; 96 registers with 168 bytes of spills per thread at 3 blocks
+// per SM are the first suspect.  Opt-in only (fuse_eh = 3).
 // Iteration i:  wait for this thread's copies of plane i -> barrier (everyone's copies landed, everyone's
 // E_new[i-1] is published, stage (i-1)%3 is free) -> issue the copies of plane i+2 into stage (i-1)%3 ->
 // E_new[i] from stage i%3 -> H_new[i-1] from the published E_new[i-1] -> publish E_new[i].
