@@ -66,9 +66,9 @@ struct FusedParams {
 };
 
 // soft point sources of the box on the VEC recomputed E values of a thread, registration order
-// (fdtd/sources.py:93-109, 278-297); rare: kept out of line
+// (fdtd/sources.py:93-109, 278-297); inlined: an out-of-line call would force the field vectors into local memory
 template <typename T, int VEC>
-FDTD_RARE_FN void fused_sources_vec(const FusedParams<T>& P, int i, int j, int k0, i64 off, Pack<T, VEC>& e0,
+FDTD_DEV void fused_sources_vec(const FusedParams<T>& P, int i, int j, int k0, i64 off, Pack<T, VEC>& e0,
                                     Pack<T, VEC>& e1, Pack<T, VEC>& e2) {
   for (int s = 0; s < P.n_src; ++s) {
     const SrcK<T>& S = P.src[s];
@@ -557,9 +557,13 @@ __global__ void __launch_bounds__(32 * FUSED_RT_WARPS, FDTD_FUSED_RT_MIN_BLOCKS)
 // one of three shared-memory stages through asynchronous 16-byte copies (LDGSTS, L2 only) issued two iterations
 // before they are consumed, so the one barrier per plane no longer exposes the memory latency of the slowest warp.
 // Each global word is requested once per block (the y-1 / z-1 neighbours come out of the staged tile).
-// STATUS (round 1): bit-identical on the B200, but as built 2.8x SLOWER than the two half-steps at 512^3 f32
-// (profiles/r1_fused_pipe_check.log) -- never profiled; 96 registers with 168 bytes of spills per thread at 3 blocks
-// per SM are the first suspect.  Opt-in only (fuse_eh = 3).
+// STATUS (round 1): bit-identical on the B200, but the first build was 2.8x SLOWER than the two half-steps at 512^3
+// f32 (profiles/r1_fused_pipe_check.log).  Never profiled.  What its SASS showed, and what has been changed since
+// (CPU-verified only, not re-measured): a per-thread copy table and the field vectors lived in local memory (the
+// table is gone: copy addresses derive from the thread's own cell; the slab helper selects its operands at compile
+// time; the source helper is inlined) and the shared-memory carve-out was left to the driver (3 blocks of 69 KB only
+// fit at the maximum carve-out, which is now requested).  64 bytes of spills remain at 96 registers (3 blocks per
+// SM); 132 registers and none at 2 blocks per SM.  Opt-in only (fuse_eh = 3).
 // Iteration i:  wait for this thread's copies of plane i -> barrier (everyone's copies landed, everyone's
 // E_new[i-1] is published, stage (i-1)%3 is free) -> issue the copies of plane i+2 into stage (i-1)%3 ->
 // E_new[i] from stage i%3 -> H_new[i-1] from the published E_new[i-1] -> publish E_new[i].
@@ -593,59 +597,87 @@ struct FusedPipeLayout {
   static constexpr size_t BYTES = sizeof(T) * (size_t)(STAGES * STAGE_WORDS + 2 * X_WORDS);
 };
 
-// The 16-byte copies a thread contributes to every stage: the tile's vectors are dealt round-robin to the threads
-// once, before the march (source pointer at plane 0 and word offset inside a stage; offset < 0 = nothing to copy),
-// so that a plane costs each thread one pointer add and one cp.async per slot.
+// CPML update of one slab (axis AX) for the VEC cells of a thread, psi read from `psi_in` and (if `store`) written
+// to `psi_out` -- the same operations as slab_cells (yee_kernels.cuh).  With (AX, U, W) cyclic: psi[0] is driven by
+// the one-sided difference of G_W along AX and corrects F_U with sign -, psi[1] by that of G_U and corrects F_W with
+// sign +.  Everything is selected at compile time, so the field vectors stay in registers.
 template <typename T, int VEC>
-struct FusedCopySlots {
-  using Lay = FusedPipeLayout<T, VEC>;
-  static constexpr int NTHREADS = (Lay::R + 1) * (Lay::L + 1);
-  static constexpr int NVEC = Lay::STAGE_WORDS / VEC;
-  static constexpr int N = (NVEC + NTHREADS - 1) / NTHREADS;
-  const T* src[N];
-  int off[N];
+struct FusedDiffs {
+  T zy[VEC], yz[VEC], xz[VEC], zx[VEC], yx[VEC], xy[VEC];   // d G_c / d a, named "ca"
 };
 
-template <typename T, int VEC>
-FDTD_DEV void fused_copy_slots(const FusedParams<T>& P, FusedCopySlots<T, VEC>& S, int j0, int kz0, int tid) {
-  using Lay = FusedPipeLayout<T, VEC>;
-  constexpr int R = Lay::R, HV = Lay::HV, EV = Lay::EV;
-  constexpr int NH = 3 * (R + 2) * HV;
+template <typename T, int VEC, bool IS_E, int AX>
+FDTD_DEV void fused_slab_cells(const typename FusedParams<T>::Slab& S, const T* psi_in, T* psi_out, bool store,
+                               i64 idx, int l0, const FusedDiffs<T, VEC>& D, Pack<T, VEC>& f0, Pack<T, VEC>& f1,
+                               Pack<T, VEC>& f2, const T (&coef)[3]) {
+  Pack<T, VEC> a = ldv<T, VEC>(psi_in + idx);
+  Pack<T, VEC> b = ldv<T, VEC>(psi_in + S.count + idx);
+  const T* bt = IS_E ? S.bE : S.bH;
+  const T* ct = IS_E ? S.cE : S.cH;
+  constexpr int U = (AX + 1) % 3, W = (AX + 2) % 3;
+  Pack<T, VEC>& fu = U == 0 ? f0 : (U == 1 ? f1 : f2);
+  Pack<T, VEC>& fw = W == 0 ? f0 : (W == 1 ? f1 : f2);
+  const T (&d0)[VEC] = AX == 0 ? D.zx : (AX == 1 ? D.xy : D.yz);
+  const T (&d1)[VEC] = AX == 0 ? D.yx : (AX == 1 ? D.zy : D.xz);
+  const T cu = coef[U], cw = coef[W];
 #pragma unroll
-  for (int n = 0; n < FusedCopySlots<T, VEC>::N; ++n) {
-    const int v = tid + n * FusedCopySlots<T, VEC>::NTHREADS;
-    S.off[n] = -1;
-    S.src[n] = nullptr;
-    if (v >= FusedCopySlots<T, VEC>::NVEC) continue;
-    int c, j, k;
-    const T* const* F;
-    if (v < NH) {   // H_old tile: rows j0-1 .. j0+R, vectors -1 .. L
-      c = v / ((R + 2) * HV);
-      const int rem = v % ((R + 2) * HV);
-      j = j0 - 1 + rem / HV;
-      k = kz0 + (rem % HV - 1) * VEC;
-      F = P.Hin;
-    } else {        // E_old tile: rows j0 .. j0+R, vectors 0 .. L
-      const int w = v - NH;
-      c = w / ((R + 1) * EV);
-      const int rem = w % ((R + 1) * EV);
-      j = j0 + rem / EV;
-      k = kz0 + (rem % EV) * VEC;
-      F = P.Ein;
+  for (int e = 0; e < VEC; ++e) {
+    const int ll = AX == 2 ? l0 + e : l0;
+    if (ll >= 0 && ll < S.t) {
+      const T bb = bt[ll];
+      const T cc = ct[ll];
+      T p0 = a.v[e] * bb;
+      T p1 = b.v[e] * bb;
+      if (IS_E ? (ll >= 1) : (ll < S.t - 1)) {   // fdtd/boundaries.py:439-454, 467-482
+        p0 = p0 + d0[e] * cc;
+        p1 = p1 + d1[e] * cc;
+      }
+      a.v[e] = p0;
+      b.v[e] = p1;
+      const T phi_u = T(0) - p0;
+      const T phi_w = p1 - T(0);
+      if (IS_E) {
+        fu.v[e] = fu.v[e] + cu * phi_u;
+        fw.v[e] = fw.v[e] + cw * phi_w;
+      } else {
+        fu.v[e] = fu.v[e] - cu * phi_u;
+        fw.v[e] = fw.v[e] - cw * phi_w;
+      }
     }
-    if (j < P.y1 && k < P.z1 && j >= 0 && k >= 0) {   // (beyond the box nothing is recomputed: the shell's result is used)
-      S.off[n] = v * VEC;
-      S.src[n] = F[c] + (i64)j * P.Nz + k;
-    }
+  }
+  if (store) {
+    stv<T, VEC>(psi_out + idx, a);
+    stv<T, VEC>(psi_out + S.count + idx, b);
   }
 }
 
-// asynchronous copies of plane i of the block's tile into one stage
+// The asynchronous 16-byte copies of one plane of the block's tile into a stage.  Every thread whose cells lie in
+// the box copies the six input vectors of its own cells (they land where its neighbours will look for their y-1 /
+// z-1 values too); the threads of the first row add the y-1 row (Hx, Hz: the only components differenced along y)
+// and those of the first lane the z-1 vector (Hx, Hy).  Addresses derive from the thread's own cell offset: no
+// per-thread copy table, no registers held across the march.
 template <typename T, int VEC>
-FDTD_DEV void fused_stage_issue(const FusedCopySlots<T, VEC>& S, T* stage, i64 plane_offset) {
+FDTD_DEV void fused_stage_issue(const FusedParams<T>& P, T* stage, i64 off, int r, int l, bool inside, bool row_m1,
+                                bool vec_m1) {
+  using Lay = FusedPipeLayout<T, VEC>;
+  constexpr int R = Lay::R, HV = Lay::HV, EV = Lay::EV;
+  constexpr int HC = (R + 2) * HV * VEC, EC = (R + 1) * EV * VEC;
+  if (!inside) return;
+  T* h = stage + ((r + 1) * HV + (l + 1)) * VEC;
+  T* e = stage + Lay::H_WORDS + (r * EV + l) * VEC;
 #pragma unroll
-  for (int n = 0; n < FusedCopySlots<T, VEC>::N; ++n)
-    if (S.off[n] >= 0) FDTD_CP_ASYNC16(stage + S.off[n], S.src[n] + plane_offset);
+  for (int c = 0; c < 3; ++c) {
+    FDTD_CP_ASYNC16(h + c * HC, P.Hin[c] + off);
+    FDTD_CP_ASYNC16(e + c * EC, P.Ein[c] + off);
+  }
+  if (row_m1) {
+    FDTD_CP_ASYNC16(h - HV * VEC, P.Hin[0] + off - P.Nz);
+    FDTD_CP_ASYNC16(h + 2 * HC - HV * VEC, P.Hin[2] + off - P.Nz);
+  }
+  if (vec_m1) {
+    FDTD_CP_ASYNC16(h - VEC, P.Hin[0] + off - VEC);
+    FDTD_CP_ASYNC16(h + HC - VEC, P.Hin[1] + off - VEC);
+  }
 }
 
 template <typename T, int VEC>
@@ -676,17 +708,19 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   for (int s = 0; s < P.n_src; ++s)
     src_yz |= (j >= P.src[s].bb[2]) && (j < P.src[s].bb[3]) && (k0 + VEC > P.src[s].bb[4]) && (k0 < P.src[s].bb[5]);
   // CPML slabs this thread's cells lie in (loop-invariant)
-  bool sl_hit[6] = {false, false, false, false, false, false};   // (x slabs: decided per plane)
-  for (int s = 0; s < P.n_sl; ++s)
-    sl_hit[s] = P.sl[s].axis == 1 ? (j >= P.sl[s].lo && j < P.sl[s].lo + P.sl[s].t)
-                                  : (k0 - P.sl[s].lo + VEC > 0) && (k0 - P.sl[s].lo < P.sl[s].t);
+  unsigned sl_hit = 0;   // bit s: this thread's cells lie in y / z slab s (x slabs are decided per plane)
+  for (int s = 0; s < P.n_sl; ++s) {
+    const bool hit = P.sl[s].axis == 1 ? (j >= P.sl[s].lo && j < P.sl[s].lo + P.sl[s].t)
+                                       : (k0 - P.sl[s].lo + VEC > 0) && (k0 - P.sl[s].lo < P.sl[s].t);
+    sl_hit |= (hit && P.sl[s].axis != 0) ? (1u << s) : 0u;
+  }
 
-  FusedCopySlots<T, VEC> slots;
-  fused_copy_slots<T, VEC>(P, slots, j0, kz0, tid);
+  const bool row_m1 = (r == 0) && (j >= 1), vec_m1 = (l == 0) && (k0 >= VEC);   // who copies the y-1 row / z-1 vector
   // two planes in flight before the first one is consumed (one commit group per plane, empty ones included)
   for (int s = 0; s < 2; ++s) {
     const int ip = xa + s;
-    if (ip <= xb && ip < P.x1) fused_stage_issue<T, VEC>(slots, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane);
+    if (ip <= xb && ip < P.x1)
+        fused_stage_issue<T, VEC>(P, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane + p, r, l, inside, row_m1, vec_m1);
     FDTD_CP_ASYNC_COMMIT();
   }
 
@@ -703,7 +737,8 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     __syncthreads();
     {
       const int ip = i + 2;
-      if (ip <= xb && ip < P.x1) fused_stage_issue<T, VEC>(slots, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane);
+      if (ip <= xb && ip < P.x1)
+        fused_stage_issue<T, VEC>(P, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane + p, r, l, inside, row_m1, vec_m1);
       FDTD_CP_ASYNC_COMMIT();
     }
     const T* sH = stages + (i % 3) * Lay::STAGE_WORDS;
@@ -727,7 +762,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
         e0 = ldv<T, VEC>(erow);
         e1 = ldv<T, VEC>(erow + EC);
         e2 = ldv<T, VEC>(erow + 2 * EC);
-        T dyz[VEC], dxz[VEC], dzy[VEC], dxy[VEC], dzx[VEC], dyx[VEC];
+        FusedDiffs<T, VEC> D;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           const T zn0 = e == 0 ? zs0 : h0.v[e > 0 ? e - 1 : 0];
@@ -742,60 +777,33 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
           const T d_xz = face_z ? T(0) : h0.v[e] - zn0;
           const T d_zx = face_x ? T(0) : h2.v[e] - hp2.v[e];
           const T d_yx = face_x ? T(0) : h1.v[e] - hp1.v[e];
-          dyz[e] = d_yz;
-          dxz[e] = d_xz;
-          dzy[e] = d_zy;
-          dxy[e] = d_xy;
-          dzx[e] = d_zx;
-          dyx[e] = d_yx;
+          D.yz[e] = d_yz;
+          D.xz[e] = d_xz;
+          D.zy[e] = d_zy;
+          D.xy[e] = d_xy;
+          D.zx[e] = d_zx;
+          D.yx[e] = d_yx;
           e0.v[e] = e0.v[e] + P.ce[0] * (d_zy - d_yz);
           e1.v[e] = e1.v[e] + P.ce[1] * (d_xz - d_zx);
           e2.v[e] = e2.v[e] + P.ce[2] * (d_yx - d_xy);
         }
         // CPML slabs, registration order: psi_E from the OLD buffer; an x slab corrects Ey (-) and Ez (+), a y slab
-        // Ez (-) and Ex (+), a z slab Ex (-) and Ey (+)
-        // (fdtd/boundaries.py:433-459, 409-419; same operations as slab_cells)
+        // Ez (-) and Ex (+), a z slab Ex (-) and Ey (+)      (fdtd/boundaries.py:433-459, 409-419)
         for (int s = 0; s < P.n_sl; ++s) {
           const typename FusedParams<T>::Slab& S = P.sl[s];
-          const int ax = S.axis;
-          if (ax == 0 ? (i < S.lo || i >= S.lo + S.t) : !sl_hit[s]) continue;
-          const int l0 = ax == 0 ? i - S.lo : (ax == 1 ? j - S.lo : k0 - S.lo);
-          const i64 idx = ax == 0 ? (i64)l0 * plane + p
-                                  : (ax == 1 ? ((i64)i * S.t + l0) * Nz + k0
-                                             : ((i64)i * P.Ny + j) * S.tp + (k0 - S.lo_al));
-          Pack<T, VEC> a = ldv<T, VEC>(S.psiE_in + idx);
-          Pack<T, VEC> b = ldv<T, VEC>(S.psiE_in + S.count + idx);
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            const int ll = ax == 2 ? l0 + e : l0;
-            if (ll >= 0 && ll < S.t) {
-              const T bb = S.bE[ll];
-              const T cc = S.cE[ll];
-              T p0 = a.v[e] * bb;
-              T p1 = b.v[e] * bb;
-              if (ll >= 1) {
-                p0 = p0 + (ax == 0 ? dzx[e] : (ax == 1 ? dxy[e] : dyz[e])) * cc;
-                p1 = p1 + (ax == 0 ? dyx[e] : (ax == 1 ? dzy[e] : dxz[e])) * cc;
-              }
-              a.v[e] = p0;
-              b.v[e] = p1;
-              const T phi_u = T(0) - p0;
-              const T phi_w = p1 - T(0);
-              if (ax == 0) {
-                e1.v[e] = e1.v[e] + P.ce[1] * phi_u;
-                e2.v[e] = e2.v[e] + P.ce[2] * phi_w;
-              } else if (ax == 1) {
-                e2.v[e] = e2.v[e] + P.ce[2] * phi_u;
-                e0.v[e] = e0.v[e] + P.ce[0] * phi_w;
-              } else {
-                e0.v[e] = e0.v[e] + P.ce[0] * phi_u;
-                e1.v[e] = e1.v[e] + P.ce[1] * phi_w;
-              }
-            }
-          }
-          if (core && i < xb) {
-            stv<T, VEC>(S.psiE_out + idx, a);
-            stv<T, VEC>(S.psiE_out + S.count + idx, b);
+          const bool store = core && i < xb;
+          if (S.axis == 0) {
+            if (i >= S.lo && i < S.lo + S.t)
+              fused_slab_cells<T, VEC, true, 0>(S, S.psiE_in, S.psiE_out, store, (i64)(i - S.lo) * plane + p, i - S.lo,
+                                                D, e0, e1, e2, P.ce);
+          } else if ((sl_hit >> s) & 1u) {
+            if (S.axis == 1)
+              fused_slab_cells<T, VEC, true, 1>(S, S.psiE_in, S.psiE_out, store, ((i64)i * S.t + (j - S.lo)) * Nz + k0,
+                                                j - S.lo, D, e0, e1, e2, P.ce);
+            else
+              fused_slab_cells<T, VEC, true, 2>(S, S.psiE_in, S.psiE_out, store,
+                                                ((i64)i * P.Ny + j) * S.tp + (k0 - S.lo_al), k0 - S.lo, D, e0, e1, e2,
+                                                P.ce);
           }
         }
         if (src_yz) fused_sources_vec<T, VEC>(P, i, j, k0, off, e0, e1, e2);
@@ -817,7 +825,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     if (core && i > xa) {
       const T* x = xch + ((i - 1) & 1) * Lay::X_WORDS + (r * EV + l) * VEC;
       Pack<T, VEC> hx = hp0, hy = hp1, hz = hp2;
-      T dyz[VEC], dxz[VEC], dzy[VEC], dxy[VEC], dzx[VEC], dyx[VEC];
+      FusedDiffs<T, VEC> D;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const T ex_y = x[EV * VEC + e];
@@ -834,12 +842,12 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
         const T d_xz = face_z ? T(0) : ex_z - ep0.v[e];
         const T d_zx = face_x ? T(0) : e2.v[e] - ep2.v[e];
         const T d_yx = face_x ? T(0) : e1.v[e] - ep1.v[e];
-        dyz[e] = d_yz;
-        dxz[e] = d_xz;
-        dzy[e] = d_zy;
-        dxy[e] = d_xy;
-        dzx[e] = d_zx;
-        dyx[e] = d_yx;
+        D.yz[e] = d_yz;
+        D.xz[e] = d_xz;
+        D.zy[e] = d_zy;
+        D.xy[e] = d_xy;
+        D.zx[e] = d_zx;
+        D.yx[e] = d_yx;
         hx.v[e] = hx.v[e] - P.ch[0] * (d_zy - d_yz);
         hy.v[e] = hy.v[e] - P.ch[1] * (d_xz - d_zx);
         hz.v[e] = hz.v[e] - P.ch[2] * (d_yx - d_xy);
@@ -849,44 +857,18 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
       const int ih = i - 1;
       for (int s = 0; s < P.n_sl; ++s) {
         const typename FusedParams<T>::Slab& S = P.sl[s];
-        const int ax = S.axis;
-        if (ax == 0 ? (ih < S.lo || ih >= S.lo + S.t) : !sl_hit[s]) continue;
-        const int l0 = ax == 0 ? ih - S.lo : (ax == 1 ? j - S.lo : k0 - S.lo);
-        const i64 idx = ax == 0 ? (i64)l0 * plane + p
-                                : (ax == 1 ? ((i64)ih * S.t + l0) * Nz + k0
-                                           : ((i64)ih * P.Ny + j) * S.tp + (k0 - S.lo_al));
-        Pack<T, VEC> a = ldv<T, VEC>(S.psiH + idx);
-        Pack<T, VEC> b = ldv<T, VEC>(S.psiH + S.count + idx);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const int ll = ax == 2 ? l0 + e : l0;
-          if (ll >= 0 && ll < S.t) {
-            const T bb = S.bH[ll];
-            const T cc = S.cH[ll];
-            T p0 = a.v[e] * bb;
-            T p1 = b.v[e] * bb;
-            if (ll < S.t - 1) {
-              p0 = p0 + (ax == 0 ? dzx[e] : (ax == 1 ? dxy[e] : dyz[e])) * cc;
-              p1 = p1 + (ax == 0 ? dyx[e] : (ax == 1 ? dzy[e] : dxz[e])) * cc;
-            }
-            a.v[e] = p0;
-            b.v[e] = p1;
-            const T phi_u = T(0) - p0;
-            const T phi_w = p1 - T(0);
-            if (ax == 0) {
-              hy.v[e] = hy.v[e] - P.ch[1] * phi_u;
-              hz.v[e] = hz.v[e] - P.ch[2] * phi_w;
-            } else if (ax == 1) {
-              hz.v[e] = hz.v[e] - P.ch[2] * phi_u;
-              hx.v[e] = hx.v[e] - P.ch[0] * phi_w;
-            } else {
-              hx.v[e] = hx.v[e] - P.ch[0] * phi_u;
-              hy.v[e] = hy.v[e] - P.ch[1] * phi_w;
-            }
-          }
+        if (S.axis == 0) {
+          if (ih >= S.lo && ih < S.lo + S.t)
+            fused_slab_cells<T, VEC, false, 0>(S, S.psiH, S.psiH, true, (i64)(ih - S.lo) * plane + p, ih - S.lo, D, hx,
+                                               hy, hz, P.ch);
+        } else if ((sl_hit >> s) & 1u) {
+          if (S.axis == 1)
+            fused_slab_cells<T, VEC, false, 1>(S, S.psiH, S.psiH, true, ((i64)ih * S.t + (j - S.lo)) * Nz + k0,
+                                               j - S.lo, D, hx, hy, hz, P.ch);
+          else
+            fused_slab_cells<T, VEC, false, 2>(S, S.psiH, S.psiH, true, ((i64)ih * P.Ny + j) * S.tp + (k0 - S.lo_al),
+                                               k0 - S.lo, D, hx, hy, hz, P.ch);
         }
-        stv<T, VEC>(S.psiH + idx, a);
-        stv<T, VEC>(S.psiH + S.count + idx, b);
       }
       const i64 om = off - plane;
       stv<T, VEC>(P.Hout[0] + om, hx);
