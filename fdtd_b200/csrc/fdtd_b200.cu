@@ -540,7 +540,7 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int p
       if (IS_E) continue;  // CurrentDetector.detect_E is empty (fdtd/detectors.py:414-415)
       FDTD_LAUNCH((fdtd::current_kernel<T>), dim3(blocks_for(D.n)), dim3(256), stream, (const T*)d->H[0],
                   (const T*)d->H[1], (const i64*)D.idx, (const int*)D.pos, D.n, d->Nx, d->Ny, d->Nz, d->plane,
-                  (T)D.spacing, (T*)D.ring_H, (T*)D.last, (i64)slot);
+                  (T)D.spacing, (T*)D.ring_H, (T*)D.last, (i64)slot, (int)(d->x_offset > 0));
       int rc2 = check_launch("current detector");
       if (rc2) return rc2;
       continue;

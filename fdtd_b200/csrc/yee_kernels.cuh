@@ -827,13 +827,15 @@ __global__ void dft_accumulate_kernel(const T* ring, i64 n_steps, i64 n_values, 
 // CurrentDetector.single_point_current (fdtd/detectors.py:417-461): z-current through each cell from the
 // loop of H around it, averaged over the cell's z level and the one below; indices wrap like python's.
 // The second `current_vector_2` is ACCUMULATED onto the first (`+=`, fdtd/detectors.py:456) as in the reference.
+// `ghost`: the slab has a left neighbour, whose last H plane lies in the ghost plane just below local plane 0
+// (x-sharded grids; the caller samples after that plane has arrived) -- no wrap-around along x then.
 template <typename T>
 __global__ void current_kernel(const T* Hx, const T* Hy, const i64* idx, const int* pos, int n, int Nx, int Ny,
-                               int Nz, i64 plane, T dx, T* ring, T* last, i64 slot) {
+                               int Nz, i64 plane, T dx, T* ring, T* last, i64 slot, int ghost) {
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const i64 lin = idx[t];
     const i64 px = lin / plane, py = (lin % plane) / Nz, pz = lin % Nz;
-    const i64 pxm = px > 0 ? px - 1 : Nx - 1;
+    const i64 pxm = (px > 0 || ghost) ? px - 1 : Nx - 1;
     const i64 pym = py > 0 ? py - 1 : Ny - 1;
     const i64 pzm = pz > 0 ? pz - 1 : Nz - 1;
     T cv1 = (Hx[px * plane + pym * Nz + pz] - Hx[px * plane + py * Nz + pz]) * dx;

@@ -264,11 +264,14 @@ class CurrentDetector(BlockDetector):
     def _register_grid(self, grid, x, y, z):
         super()._register_grid(grid, x, y, z)
         part = grid._part
+        self._needs_ghost = False
         if part.sharded:
-            firsts = {part.bounds(r)[0] for r in range(1, part.world)} | {0}
-            if any((v + grid.Nx) % grid.Nx in firsts for v in self.x):     # same verdict on every rank
-                raise NotImplementedError("a CurrentDetector cell on the first plane of an x-slab (needs the "
-                                          "neighbour slab's H of the same half-step)")
+            xs = {(v + grid.Nx) % grid.Nx for v in self.x}
+            if 0 in xs:                                   # H[x-1] wraps to the LAST slab (fdtd/detectors.py:432-447)
+                raise NotImplementedError("a CurrentDetector cell on plane x = 0 of an x-sharded grid")
+            # a cell on the first plane of a slab reads the left neighbour's H of the same half-step: the engine then
+            # samples after the ghost plane has arrived (same verdict on every rank)
+            self._needs_ghost = bool(xs & {part.bounds(r)[0] for r in range(1, part.world)})
         self._last = bd.zeros((max(1, self._n_local),))
 
     @property

@@ -39,6 +39,7 @@ class Engine:
         self._halo = None
         self._p2p = None
         self._wrap = None
+        self._late = False
         self._pending = {"E": None, "H": None}
         self.bake()
 
@@ -265,6 +266,11 @@ class Engine:
         import os
         g, d = self.grid, self.desc
         want = os.environ.get("FDTD_B200_HALO", "p2p")
+        # detectors that read the ghost plane of the half-step being sampled: exchange first, then sample -- done on
+        # the send / recv path only
+        self._late = any(getattr(det, "_needs_ghost", False) for det in g.detectors)
+        if self._late:
+            want, self._p2p = "nccl", False
         if self._p2p is None and g._E.is_cuda and want == "p2p":
             try:
                 self._p2p = P2PHalo(g._part, g._E, g._H, self.lib)
@@ -290,6 +296,9 @@ class Engine:
                     if not empty and box[0] <= plane < box[1]:
                         ok = False
             self._push_fused[field] = ok
+        if self._late and not self._push_fused["H"]:
+            raise NotImplementedError("a CurrentDetector cell on the first plane of an x-slab together with something "
+                                      "that modifies the slab's last H plane after the update (periodic copy, source)")
         if self._p2p:
             self._p2p_refresh()
         else:
@@ -484,6 +493,12 @@ class Engine:
             halo.wait(self._pending[other])
             _capi.check(lib, step(C.byref(d), edge[0], edge[1], q, slot, st))
         self._pending[other] = None
+        if field == "H" and self._late:
+            # a CurrentDetector on the first plane of a slab reads the neighbour's H of THIS half-step
+            halo.wait(halo.start(field))
+            self._post(field, q, slot, st)
+            self._pending[field] = None
+            return
         self._post(field, q, slot, st)
         self._pending[field] = halo.start(field)
 

@@ -46,6 +46,8 @@ def main():
         dist.destroy_process_group()
         return
     assert g._part.world == world and g._part.sharded
+    if os.environ.get("FDTD_TEST_EXPECT_LATE"):      # a CurrentDetector on a slab's first plane: exchange-then-sample path
+        assert g._engine._late and not g._engine._p2p
     half = steps // 2
     g.run(half, progress_bar=False)
     for _ in range(steps - half):          # exercise the step()-granular path too

@@ -41,7 +41,8 @@ def launch(world, backend, dtype, scene, steps, out, **extra_env):
                                                (3, "periodic3d", "float64"), (2, "c4small", "float32"),
                                                (3, "slab2d_xz", "float64"), (2, "overlaps3d", "float64"),
                                                (3, "overlaps3d", "float32"), (2, "ring3d", "float64"),
-                                               (3, "ring3d", "float32"), (4, "ring3d", "float64")])
+                                               (3, "ring3d", "float32"), (4, "ring3d", "float64"),
+                                               (2, "feed50", "float64"), (3, "feed50", "float32")])
 def test_sharded_equals_single(tmp_path, world, scene, dtype):
     steps = 24
     out = str(tmp_path / "sharded.npz")
@@ -73,6 +74,23 @@ def test_sharded_random_scene(tmp_path, seed):
     g.run(steps, progress_bar=False)
     want = scenes.dump(g)
     assert set(got) == set(want)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
+
+
+def test_current_detector_on_a_slab_boundary(tmp_path):
+    """feed50 on 2 ranks cuts the grid at x = 9, exactly where the impedance port and its CurrentDetector sit: the
+    loop of H around that cell reaches into the left neighbour's last plane of the SAME half-step, so the ranks
+    exchange the H ghost plane before sampling.  Bit-identical to the unsharded run."""
+    steps = 40
+    out = str(tmp_path / "sharded.npz")
+    launch(2, "gloo", "float64", "feed50", steps, out, FDTD_TEST_EXPECT_LATE="1")
+    got = dict(np.load(out))
+    fd = use_emu("float64")
+    g = scenes.feed50(fd)
+    g.run(steps, progress_bar=False)
+    want = scenes.dump(g)
+    assert float(np.abs(want["det0_I"]).max()) > 0
     for k in want:
         assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
 
