@@ -104,7 +104,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_MIN_BLOCKS)
     fused_eh_kernel(const __grid_constant__ FusedParams<T> P) {
   constexpr int R = FUSED_R, L = FUSED_L, W = (L + 1) * VEC;
-  __shared__ T sm[2][3][R + 1][W];
+  __shared__ __align__(16) T sm[2][3][R + 1][W];   // rows are multiples of 16 bytes: vector stores / loads
 
   const int tid = threadIdx.x;
   const int r = tid / (L + 1), l = tid % (L + 1);
@@ -237,12 +237,10 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_MIN_
     // ---- publish E_new[i] to the block, carry the planes ---------------------------------------------
     if (active) {
       const int b = i & 1;
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        sm[b][0][r][l * VEC + e] = e0.v[e];
-        sm[b][1][r][l * VEC + e] = e1.v[e];
-        sm[b][2][r][l * VEC + e] = e2.v[e];
-      }
+      // (one 128-bit store per component: scalar stores at a stride of VEC words conflict 4-way on the banks)
+      stv<T, VEC>(&sm[b][0][r][l * VEC], e0);
+      stv<T, VEC>(&sm[b][1][r][l * VEC], e1);
+      stv<T, VEC>(&sm[b][2][r][l * VEC], e2);
       ep0 = e0;
       ep1 = e1;
       ep2 = e2;

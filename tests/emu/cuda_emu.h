@@ -20,6 +20,7 @@
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 {
   unsigned x, y, z;
