@@ -11,6 +11,11 @@ for lib in fdtd_b200/_variants/lib_pipe_*.so; do
   echo "# $lib"
   TUNE_LIB=$lib FDTD_B200_FUSE_EH=3 timeout 60 python scripts/bench_configs.py c4 2>&1 | tail -1
 done
+for lib in fdtd_b200/_variants/lib_fz*.so; do
+  [ -e "$lib" ] || continue
+  echo "# $lib"
+  TUNE_LIB=$lib FDTD_B200_FUSE_EH=1 timeout 60 python scripts/bench_configs.py c4 2>&1 | tail -1
+done
 echo "# two half-steps"
 FDTD_B200_FUSE_EH=0 timeout 60 python scripts/bench_configs.py c4 2>&1 | tail -1
 echo "# shared-memory fused kernel"

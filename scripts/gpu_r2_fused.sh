@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 first GPU session for the temporally fused E+H kernels (development tool; one B200).
-#   here (no GPU):  python scripts/tune.py build rt_r2_w4_mb3,rt_r2_w2_mb6,rt_r3_w4_mb2,rt_r4_w2_mb4,pipe_r4l32_mb3,pipe_r4l32_mb2,pipe_r8l32_mb1,pipe_r8l16_mb2,pipe_r2l32_mb4,pipe_r4l16_mb4
+#   here (no GPU):  python scripts/tune.py build rt_r2_w4_mb3,rt_r2_w2_mb6,rt_r3_w4_mb2,rt_r4_w2_mb4,pipe_r4l32_mb3,pipe_r4l32_mb2,pipe_r8l32_mb1,pipe_r8l16_mb2,pipe_r2l32_mb4,pipe_r4l16_mb4,pipe_r4l31_mb3,pipe_r4l31_mb2,pipe_r7l31_mb2,fz_r4l31_mb4
 #   on the box:     gpurun --timeout 900 -- 'bash scripts/gpu_r2_fused.sh'
 # Writes everything under gpurun_out/r2_fused/.
 set -u

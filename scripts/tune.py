@@ -34,6 +34,11 @@ VARIANTS = {
     "pipe_r8l16_mb2": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_LANES=16", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
     "pipe_r2l32_mb4": ["-DFDTD_FUSED_ROWS=2", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4"],
     "pipe_r4l16_mb4": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=16", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4"],
+    # 31 core lanes + 1 halo lane = one full warp per tile row (5 or 8 warps per block, none partially filled)
+    "pipe_r4l31_mb3": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=3"],
+    "pipe_r4l31_mb2": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
+    "pipe_r7l31_mb2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
+    "fz_r4l31_mb4": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_MIN_BLOCKS=4"],
     "post_inline": ["-DFDTD_POST_INLINE=1"],
     "hdown": ["-DFDTD_H_DOWNWARD=1"],
     "fz_pf0": ["-DFDTD_FUSED_PREFETCH=0"],
