@@ -566,11 +566,13 @@ __global__ void __launch_bounds__(32 * FUSED_RT_WARPS, FDTD_FUSED_RT_MIN_BLOCKS)
 // E_new[i-1] is published, stage (i-1)%3 is free) -> issue the copies of plane i+2 into stage (i-1)%3 ->
 // E_new[i] from stage i%3 -> H_new[i-1] from the published E_new[i-1] -> publish E_new[i].
 #ifdef FDTD_EMU
+#define FDTD_FFS(x) __builtin_ffs((int)(x))
 #define FDTD_CP_ASYNC16(dst, src) emu::cp_async16((dst), (src))
 #define FDTD_CP_ASYNC_COMMIT() emu::cp_async_commit()
 #define FDTD_CP_ASYNC_WAIT_1() emu::cp_async_wait(1)
 #define FDTD_DYN_SMEM(name) alignas(16) static unsigned char name[128 << 10]
 #else
+#define FDTD_FFS(x) __ffs((int)(x))
 #define FDTD_CP_ASYNC16(dst, src)                                                                      \
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), \
                "l"(src)                                                                                \
@@ -707,11 +709,14 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     src_yz |= (j >= P.src[s].bb[2]) && (j < P.src[s].bb[3]) && (k0 + VEC > P.src[s].bb[4]) && (k0 < P.src[s].bb[5]);
   // CPML slabs this thread's cells lie in (loop-invariant)
   unsigned sl_hit = 0;   // bit s: this thread's cells lie in y / z slab s (x slabs are decided per plane)
+  unsigned xs_bits = 0;  // bit s: slab s is an x slab
   for (int s = 0; s < P.n_sl; ++s) {
     const bool hit = P.sl[s].axis == 1 ? (j >= P.sl[s].lo && j < P.sl[s].lo + P.sl[s].t)
                                        : (k0 - P.sl[s].lo + VEC > 0) && (k0 - P.sl[s].lo < P.sl[s].t);
     sl_hit |= (hit && P.sl[s].axis != 0) ? (1u << s) : 0u;
+    xs_bits |= P.sl[s].axis == 0 ? (1u << s) : 0u;
   }
+  unsigned hit_prev = 0;   // slabs (x slabs included) the cells of plane i-1 lie in: what the H update of i-1 needs
 
   const bool row_m1 = (r == 0) && (j >= 1), vec_m1 = (l == 0) && (k0 >= VEC);   // who copies the y-1 row / z-1 vector
   // two planes in flight before the first one is consumed (one commit group per plane, empty ones included)
@@ -741,6 +746,11 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     }
     const T* sH = stages + (i % 3) * Lay::STAGE_WORDS;
     const T* sE = sH + Lay::H_WORDS;
+    unsigned hit_now = sl_hit;   // + the x slabs plane i lies in (the same for the whole block)
+    for (unsigned m = xs_bits; m != 0; m &= m - 1) {
+      const int s = FDTD_FFS(m) - 1;
+      hit_now |= (i >= P.sl[s].lo && i < P.sl[s].lo + P.sl[s].t) ? (1u << s) : 0u;
+    }
     const i64 off = (i64)i * plane + p;
     Pack<T, VEC> e0, e1, e2, h0, h1, h2;
     if (active) {
@@ -787,14 +797,15 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
         }
         // CPML slabs, registration order: psi_E from the OLD buffer; an x slab corrects Ey (-) and Ez (+), a y slab
         // Ez (-) and Ex (+), a z slab Ex (-) and Ey (+)      (fdtd/boundaries.py:433-459, 409-419)
-        for (int s = 0; s < P.n_sl; ++s) {
+        // (the interior -- no slab at all -- skips the loop with one test)
+        for (int s = 0; hit_now != 0 && s < P.n_sl; ++s) {
+          if (!((hit_now >> s) & 1u)) continue;
           const typename FusedParams<T>::Slab& S = P.sl[s];
           const bool store = core && i < xb;
           if (S.axis == 0) {
-            if (i >= S.lo && i < S.lo + S.t)
-              fused_slab_cells<T, VEC, true, 0>(S, S.psiE_in, S.psiE_out, store, (i64)(i - S.lo) * plane + p, i - S.lo,
-                                                D, e0, e1, e2, P.ce);
-          } else if ((sl_hit >> s) & 1u) {
+            fused_slab_cells<T, VEC, true, 0>(S, S.psiE_in, S.psiE_out, store, (i64)(i - S.lo) * plane + p, i - S.lo,
+                                              D, e0, e1, e2, P.ce);
+          } else {
             if (S.axis == 1)
               fused_slab_cells<T, VEC, true, 1>(S, S.psiE_in, S.psiE_out, store, ((i64)i * S.t + (j - S.lo)) * Nz + k0,
                                                 j - S.lo, D, e0, e1, e2, P.ce);
@@ -853,13 +864,13 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
       // CPML slabs, registration order: psi_H in place (only the owner touches it); an x slab corrects Hy and Hz,
       // a y slab Hz and Hx, a z slab Hx and Hy      (fdtd/boundaries.py:461-487, 421-431)
       const int ih = i - 1;
-      for (int s = 0; s < P.n_sl; ++s) {
+      for (int s = 0; hit_prev != 0 && s < P.n_sl; ++s) {
+        if (!((hit_prev >> s) & 1u)) continue;
         const typename FusedParams<T>::Slab& S = P.sl[s];
         if (S.axis == 0) {
-          if (ih >= S.lo && ih < S.lo + S.t)
-            fused_slab_cells<T, VEC, false, 0>(S, S.psiH, S.psiH, true, (i64)(ih - S.lo) * plane + p, ih - S.lo, D, hx,
-                                               hy, hz, P.ch);
-        } else if ((sl_hit >> s) & 1u) {
+          fused_slab_cells<T, VEC, false, 0>(S, S.psiH, S.psiH, true, (i64)(ih - S.lo) * plane + p, ih - S.lo, D, hx,
+                                             hy, hz, P.ch);
+        } else {
           if (S.axis == 1)
             fused_slab_cells<T, VEC, false, 1>(S, S.psiH, S.psiH, true, ((i64)ih * S.t + (j - S.lo)) * Nz + k0,
                                                j - S.lo, D, hx, hy, hz, P.ch);
@@ -889,6 +900,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
         hp2 = h2;
       }
     }
+    hit_prev = hit_now;
   }
 }
 
