@@ -561,7 +561,10 @@ __global__ void __launch_bounds__(32 * FUSED_RT_WARPS, FDTD_FUSED_RT_MIN_BLOCKS)
 // table is gone: copy addresses derive from the thread's own cell; the slab helper selects its operands at compile
 // time; the source helper is inlined) and the shared-memory carve-out was left to the driver (3 blocks of 69 KB only
 // fit at the maximum carve-out, which is now requested).  64 bytes of spills remain at 96 registers (3 blocks per
-// SM); 132 registers and none at 2 blocks per SM.  Opt-in only (fuse_eh = 3).
+// SM); 132 registers and none at 2 blocks per SM; without any slab / source code the march needs 89 registers and
+// ~300 instructions per thread and plane.  Moving the slab code out of line was tried and dropped: the difference
+// arrays and field vectors it takes by reference are then stored to local memory on EVERY plane (36 STL), not only
+// on the planes that call it.  Opt-in only (fuse_eh = 3).
 // Iteration i:  wait for this thread's copies of plane i -> barrier (everyone's copies landed, everyone's
 // E_new[i-1] is published, stage (i-1)%3 is free) -> issue the copies of plane i+2 into stage (i-1)%3 ->
 // E_new[i] from stage i%3 -> H_new[i-1] from the published E_new[i-1] -> publish E_new[i].
