@@ -112,3 +112,20 @@ def test_header_is_plain_c_and_layouts_agree(lib_path, tmp_path):
     D = _capi.Desc
     assert (o_slabs, o_src, o_det, o_abs2, o_wrap) == (D.slabs.offset, D.sources.offset, D.detectors.offset,
                                                        D.absorb2.offset, D.x_wrap.offset)
+
+
+def test_argument_checks_of_the_auxiliary_entry_points(lib_path):
+    """entry points that validate before they launch can be exercised without a GPU."""
+    from fdtd_b200 import _capi
+    lib = _capi.bind(lib_path)
+    null = ctypes.c_void_p(None)
+    assert lib.fdtd_dft_accumulate(_capi.F32, null, 0, 16, null, 4, null, null) == 0          # nothing to do
+    assert lib.fdtd_dft_accumulate(_capi.F32, null, 8, 16, null, 4, null, null) == -1         # null pointers
+    assert b"null pointer" in lib.fdtd_last_error()
+    assert lib.fdtd_dft_accumulate(9, null, 8, 16, null, 4, null, null) == -1
+    assert lib.fdtd_dft_accumulate(_capi.F64, null, -1, 16, null, 4, null, null) == -1
+    assert lib.fdtd_halo_signal(null, 1, null) == -1 and b"null flag" in lib.fdtd_last_error()
+    assert lib.fdtd_ipc_export(null, null, None) == -1
+    d = _capi.Desc()
+    assert lib.fdtd_post_part(ctypes.byref(d), 0, 0, 0, 0, null) == -1                         # invalid descriptor
+    assert lib.fdtd_fuse_eh_active(ctypes.byref(d)) == -1
