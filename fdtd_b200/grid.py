@@ -27,6 +27,17 @@ def _env_flag(name):
     return None if v in (None, "") else v not in ("0", "false", "False")
 
 
+def _array_in_array_out(fn):
+    """numpy in -> numpy out (the reference's users call the curls on numpy arrays), tensors stay tensors."""
+    def wrapped(F):
+        if torch.is_tensor(F):
+            return fn(F)
+        return fn(torch.as_tensor(np.asarray(F))).numpy()
+    wrapped.__doc__, wrapped.__name__ = fn.__doc__, fn.__name__
+    return wrapped
+
+
+@_array_in_array_out
 def curl_E(E):
     """H-type curl of an (Nx,Ny,Nz,3) array, forward differences (fdtd/grid.py:29-51).
     Convenience for user code and tests; the stepping kernels fuse this and never call it."""
@@ -40,6 +51,7 @@ def curl_E(E):
     return curl
 
 
+@_array_in_array_out
 def curl_H(H):
     """E-type curl, backward differences (fdtd/grid.py:54-76)."""
     curl = torch.zeros_like(H)
