@@ -2,7 +2,7 @@
 
     python tests/run_notebook.py /root/reference/examples/00-quick-start.ipynb [...]
 
-`fdtd` is aliased to fdtd_b200 by tests/refshim.py; matplotlib / IPython are forgiving stand-ins (every attribute is
+`fdtd` is aliased to fdtd_b200 by tests/refshim.py; matplotlib / IPython / line_profiler are forgiving stand-ins (every attribute is
 a callable that returns itself), notebook magics are dropped.  Prints "OK <notebook>" per notebook, or the failing
 cell, and exits non-zero on the first failure."""
 import json
@@ -28,7 +28,8 @@ class _Anything:
         return iter([self, self])
 
 
-for _m in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors", "IPython", "IPython.display"):
+for _m in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors", "IPython", "IPython.display",
+           "line_profiler"):
     _mod = types.ModuleType(_m)
     _mod.__getattr__ = lambda name, _a=_Anything(): _a
     sys.modules[_m] = _mod

@@ -26,13 +26,14 @@ def test_the_reference_suite_passes_against_this_package(tmp_path):
 
 EXAMPLES = os.path.join(os.environ.get("FDTD_REFERENCE", "/root/reference"), "examples")
 NOTEBOOKS = ["00-quick-start", "01-basic-example", "02-absorbing-object", "03-objects-of-arbitrary-shape",
-             "05-lenses-and-analysing-lensing-actions", "06-GRIN-medium-and-analysing-refraction"]
+             "04-performance-profiling", "05-lenses-and-analysing-lensing-actions",
+             "06-GRIN-medium-and-analysing-refraction"]
 
 
 @pytest.mark.skipif(not os.path.isdir(EXAMPLES), reason="the reference is not mounted here")
 def test_the_reference_example_notebooks_run_unchanged(tmp_path):
-    """every example notebook of the reference (except 04, which needs the line_profiler package) executes cell by
-    cell against this package: grids, PMLs, periodic boundaries, objects of arbitrary shape built from hundreds of
+    """every example notebook of the reference executes cell by cell against this package (04's line_profiler, like
+    matplotlib, is a stand-in): grids, PMLs, periodic boundaries, objects of arbitrary shape built from hundreds of
     registrations, lenses, GRIN media, detectors, visualize / save_simulation / save_data / dB_map_2D /
     plot_detection calls (plotting goes to a stand-in)."""
     paths = [os.path.join(EXAMPLES, n + ".ipynb") for n in NOTEBOOKS]
