@@ -42,3 +42,66 @@ def test_the_reference_example_notebooks_run_unchanged(tmp_path):
                        env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert r.stdout.count("\nOK ") + r.stdout.startswith("OK ") == len(NOTEBOOKS), r.stdout[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference is not mounted here")
+def test_grid_indexing_matches_the_reference():
+    """differential fuzz of `grid[key] = thing` (ints, floats in metres, slices of both, index lists, negative
+    values) for every plug-in type: the registered x / y / z and the exception types equal the reference's.
+    Known, deliberate differences are excluded: a BlockDetector whose inclusive ranges leave the grid is refused at
+    registration here (the reference fails with IndexError at the first step), and Objects with reversed / empty
+    ranges (the reference's behaviour there depends on incidental numpy broadcasting)."""
+    import random
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden
+    from emu.harness import use_emu
+    import numpy as np
+    ref = make_golden.load_reference()
+    ref.set_backend("numpy")
+    fd = use_emu("float64")
+    rnd = random.Random(7)
+    N, sp = (12, 9, 7), 50e-9
+
+    def rand_index(n):
+        kind = rnd.choice(["int", "float", "slice", "list"])
+        if kind == "int":
+            return rnd.randrange(-n, n)
+        if kind == "float":
+            return rnd.uniform(0, (n - 1) * sp)
+        if kind == "slice":
+            return slice(rnd.choice([None, rnd.randrange(-n, n), rnd.uniform(0, (n - 1) * sp)]),
+                         rnd.choice([None, rnd.randrange(-n, n + 1), rnd.uniform(0, n * sp)]))
+        return [rnd.randrange(0, n) for _ in range(rnd.randrange(1, 4))]
+
+    def describe(obj):
+        out = []
+        for a in "xyz":
+            v = getattr(obj, a)
+            out.append(("slice", v.start, v.stop) if isinstance(v, slice) else
+                       ("list", [int(t) for t in v]) if isinstance(v, (list, tuple, np.ndarray)) else ("val", int(v)))
+        return out
+
+    makers = {"LineDetector": lambda m: m.LineDetector(), "BlockDetector": lambda m: m.BlockDetector(),
+              "PointSource": lambda m: m.PointSource(period=10), "LineSource": lambda m: m.LineSource(period=10),
+              "PlaneSource": lambda m: m.PlaneSource(period=10), "Object": lambda m: m.Object(permittivity=2.0),
+              "PML": lambda m: m.PML(), "PeriodicBoundary": lambda m: m.PeriodicBoundary()}
+    compared = 0
+    for _ in range(160):
+        name = rnd.choice(list(makers))
+        key = tuple(rand_index(n) for n in N)
+        res = []
+        for m in (ref, fd):
+            g = m.Grid(shape=N, grid_spacing=sp)
+            try:
+                thing = makers[name](m)
+                g[key] = thing
+                res.append(("ok", describe(thing)))
+            except Exception as exc:     # noqa: BLE001
+                res.append(("err", type(exc).__name__))
+        if name == "BlockDetector" and res[0][0] == "ok" and res[1] == ("err", "IndexError"):
+            continue
+        if name == "Object" and (res[0][0] == "err" or any(d[0] == "slice" and d[2] <= d[1] for d in res[0][1])):
+            continue
+        compared += 1
+        assert res[0] == res[1], f"{name} {key}: reference {res[0]}, here {res[1]}"
+    assert compared > 110
