@@ -105,3 +105,30 @@ def test_grid_indexing_matches_the_reference():
         compared += 1
         assert res[0] == res[1], f"{name} {key}: reference {res[0]}, here {res[1]}"
     assert compared > 110
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference is not mounted here")
+def test_oracle_equals_the_reference_on_random_scenes():
+    """beyond the committed golden scenes: the oracle against the live reference (numpy float64) on seeded random
+    registrations (tests/fuzz_scenes.py) -- final E, H and every detector trace bit for bit.  (150 seeds were run
+    during development; a dozen stay in the suite.)"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden
+    import scenes
+    from fuzz_scenes import random_scene
+    from oracle import yee_oracle as yo
+    ref = make_golden.load_reference()
+    ref.set_backend("numpy")
+    yo.set_backend("numpy", "float64")
+    for seed in range(300, 312):
+        build, steps = random_scene(seed)
+        g = build(ref)
+        g.run(steps, progress_bar=False)
+        want = scenes.dump(g)
+        o = build(yo)
+        o.run(steps)
+        got = scenes.dump(o)
+        assert set(got) == set(want)
+        for k in want:
+            assert np.array_equal(got[k], want[k], equal_nan=True), f"seed {seed} {k}: {scenes.rel_l2(got[k], want[k]):.3e}"
