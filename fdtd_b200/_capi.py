@@ -6,8 +6,8 @@ loudly when it is missing: there is no CPU or PyTorch fallback for the hot path.
 import ctypes as C
 import os
 
-ABI_VERSION = 14
-MAX_SLABS, MAX_POST, MAX_SOURCES, MAX_DETECTORS, FUSED_MAX = 6, 16, 64, 64, 6
+ABI_VERSION = 15
+MAX_SLABS, MAX_POST, FUSED_MAX = 6, 16, 6
 F32, F64 = 0, 1
 CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT, CLS_ANISO, CLS_OVERLAP, CLS_ABSORB2 = 1, 2, 4, 8, 16, 32, 64
 POST_PERIODIC, POST_PML_ADD = 0, 1
@@ -51,11 +51,20 @@ class Desc(C.Structure):
                 ("slabs", Slab * MAX_SLABS),
                 ("post_kind", C.c_int32 * MAX_POST), ("post_arg", C.c_int32 * MAX_POST),
                 ("n_sources", C.c_int32), ("n_detectors", C.c_int32),
-                ("sources", Source * MAX_SOURCES), ("detectors", Detector * MAX_DETECTORS),
+                ("sources", C.POINTER(Source)), ("detectors", C.POINTER(Detector)),
                 ("x_chunk", C.c_int32), ("use_graphs", C.c_int32), ("dyn", _vp),
                 ("fuse_eh", C.c_int32), ("pad2_", C.c_int32), ("E2", _vp * 3), ("H2", _vp * 3),
                 ("fuse_post", C.c_int32), ("pad3_", C.c_int32),
                 ("psi_E2", _vp * MAX_SLABS), ("x_wrap", C.c_int32), ("pad4_", C.c_int32)]
+
+
+class Halo(C.Structure):
+    """mirror of fdtd_halo: one rank's peer pointers, flags and push counts of the peer-to-peer halo exchange"""
+    _fields_ = [("has_left", C.c_int32), ("has_right", C.c_int32),
+                ("left_ghost_y", _vp), ("left_ghost_z", _vp), ("right_ghost_y", _vp), ("right_ghost_z", _vp),
+                ("left_flag", _vp), ("right_flag", _vp), ("flags", _vp), ("error", _vp),
+                ("count", C.c_int64 * 2), ("push_fused", C.c_int32 * 2), ("side_stream", _vp),
+                ("timeout_ns", C.c_int64)]
 
 
 EXPORTS = {
@@ -81,7 +90,11 @@ EXPORTS = {
                                      _vp, _vp, _vp]),
     "fdtd_halo_push": (C.c_int, [C.POINTER(Desc), C.c_int32, _vp, _vp, _vp]),
     "fdtd_halo_signal": (C.c_int, [_vp, C.c_int64, _vp]),
-    "fdtd_halo_wait": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
+    "fdtd_halo_wait": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp]),
+    "fdtd_sharded_halfstep": (C.c_int, [C.POINTER(Desc), C.POINTER(Halo), C.c_int32, C.c_int64, C.c_int64, _vp]),
+    "fdtd_run_sharded": (C.c_int, [C.POINTER(Desc), C.POINTER(Halo), C.c_int64, C.c_int64, C.c_int64, _vp]),
+    "fdtd_halo_refresh": (C.c_int, [C.POINTER(Desc), C.POINTER(Halo), _vp]),
+    "fdtd_sizeof_halo": (C.c_int64, []),
     "fdtd_post_part": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_int32, C.c_int64, C.c_int64, _vp]),
     "fdtd_dft_accumulate": (C.c_int, [C.c_int32, _vp, C.c_int64, C.c_int64, _vp, C.c_int32, _vp, _vp]),
 }
@@ -99,6 +112,8 @@ def bind(path):
         raise RuntimeError(f"{path}: ABI {lib.fdtd_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
     if lib.fdtd_sizeof_desc() != C.sizeof(Desc):
         raise RuntimeError(f"{path}: sizeof(fdtd_desc) {lib.fdtd_sizeof_desc()} != binding {C.sizeof(Desc)}")
+    if lib.fdtd_sizeof_halo() != C.sizeof(Halo):
+        raise RuntimeError(f"{path}: sizeof(fdtd_halo) {lib.fdtd_sizeof_halo()} != binding {C.sizeof(Halo)}")
     return lib
 
 

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <vector>
 
 #include "fdtd_b200.h"
 
@@ -205,7 +206,7 @@ int validate(const fdtd_desc* d) {
       return fail(FDTD_ERR_ARG, "post kind");
     }
   }
-  if (d->n_sources < 0 || d->n_sources > FDTD_MAX_SOURCES) return fail(FDTD_ERR_ARG, "n_sources");
+  if (d->n_sources < 0 || (d->n_sources > 0 && !d->sources)) return fail(FDTD_ERR_ARG, "n_sources");
   for (int n = 0; n < d->n_sources; ++n) {
     const fdtd_source& S = d->sources[n];
     if (S.field < 0 || S.field > 1 || S.comp < 0 || S.comp > 2) return fail(FDTD_ERR_ARG, "source %d field/comp", n);
@@ -223,7 +224,7 @@ int validate(const fdtd_desc* d) {
     }
     if (!S.wave || S.wave_len < 1) return fail(FDTD_ERR_ARG, "source %d wave table", n);
   }
-  if (d->n_detectors < 0 || d->n_detectors > FDTD_MAX_DETECTORS) return fail(FDTD_ERR_ARG, "n_detectors");
+  if (d->n_detectors < 0 || (d->n_detectors > 0 && !d->detectors)) return fail(FDTD_ERR_ARG, "n_detectors");
   for (int n = 0; n < d->n_detectors; ++n) {
     const fdtd_detector& D = d->detectors[n];
     if (D.kind != FDTD_DET_FIELD && D.kind != FDTD_DET_CURRENT) return fail(FDTD_ERR_ARG, "detector %d kind", n);
@@ -561,6 +562,8 @@ int32_t fdtd_abi_version(void) { return FDTD_ABI_VERSION; }
 
 int64_t fdtd_sizeof_desc(void) { return (int64_t)sizeof(fdtd_desc); }
 
+int64_t fdtd_sizeof_halo(void) { return (int64_t)sizeof(fdtd_halo); }
+
 const char* fdtd_last_error(void) { return g_err; }
 
 int64_t fdtd_launch_count(void) { return g_launches.load(); }
@@ -703,7 +706,7 @@ int fdtd_dft_accumulate(int32_t dtype, const void* ring, int64_t n_steps, int64_
 
 #ifdef FDTD_EMU
 int fdtd_halo_signal(int64_t*, int64_t, void*) { return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA"); }
-int fdtd_halo_wait(const int64_t*, int64_t, int32_t*, void*) { return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA"); }
+int fdtd_halo_wait(const int64_t*, int64_t, int32_t*, int64_t, void*) { return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA"); }
 int fdtd_ipc_export(const void*, void*, int64_t*) { return fail(FDTD_ERR_UNSUPPORTED, "CUDA IPC needs CUDA"); }
 int fdtd_ipc_import(const void*, int64_t, void**) { return fail(FDTD_ERR_UNSUPPORTED, "CUDA IPC needs CUDA"); }
 #else
@@ -713,9 +716,10 @@ int fdtd_halo_signal(int64_t* peer_flag, int64_t value, void* stream) {
   return check_launch("halo_signal");
 }
 
-int fdtd_halo_wait(const int64_t* flag, int64_t value, int32_t* error, void* stream) {
+int fdtd_halo_wait(const int64_t* flag, int64_t value, int32_t* error, int64_t timeout_ns, void* stream) {
   if (!flag || !error) return fail(FDTD_ERR_ARG, "null flag");
-  FDTD_LAUNCH((fdtd::halo_wait_kernel), dim3(1), dim3(32), stream, (const i64*)flag, (i64)value, (int*)error);
+  FDTD_LAUNCH((fdtd::halo_wait_kernel), dim3(1), dim3(32), stream, (const i64*)flag, (i64)value, (int*)error,
+              (i64)timeout_ns);
   return check_launch("halo_wait");
 }
 
@@ -754,6 +758,161 @@ int fdtd_ipc_import(const void* handle64, int64_t offset, void** dev_ptr) {
     return fail(FDTD_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
   }
   *dev_ptr = (char*)base + offset;
+  return FDTD_OK;
+}
+#endif
+
+// ---- a whole half-step / run of an x-sharded slab on the C side (no host work between the steps) -----------
+#ifdef FDTD_EMU
+int fdtd_sharded_halfstep(const fdtd_desc*, fdtd_halo*, int32_t, int64_t, int64_t, void*) {
+  return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA");
+}
+int fdtd_run_sharded(const fdtd_desc*, fdtd_halo*, int64_t, int64_t, int64_t, void*) {
+  return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA");
+}
+int fdtd_halo_refresh(const fdtd_desc*, fdtd_halo*, void*) { return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA"); }
+#else
+extern "C++" {
+namespace {
+// two events order the caller's stream and the side stream; re-recorded every half-step (a wait refers to the
+// most recent record at the time it is enqueued)
+struct StreamJoin {
+  cudaEvent_t to_side = nullptr, to_main = nullptr;
+  int ensure() {
+    if (!to_side && cudaEventCreateWithFlags(&to_side, cudaEventDisableTiming) != cudaSuccess)
+      return fail(FDTD_ERR_CUDA, "cudaEventCreate failed");
+    if (!to_main && cudaEventCreateWithFlags(&to_main, cudaEventDisableTiming) != cudaSuccess)
+      return fail(FDTD_ERR_CUDA, "cudaEventCreate failed");
+    return FDTD_OK;
+  }
+};
+thread_local StreamJoin g_join;
+
+int stream_after(cudaStream_t waiter, cudaStream_t signaller, cudaEvent_t ev) {
+  if (cudaEventRecord(ev, signaller) != cudaSuccess || cudaStreamWaitEvent(waiter, ev, 0) != cudaSuccess)
+    return fail(FDTD_ERR_CUDA, "stream join: %s", cudaGetErrorString(cudaGetLastError()));
+  return FDTD_OK;
+}
+
+int check_halo(const fdtd_desc* d, const fdtd_halo* h) {
+  if (!h) return fail(FDTD_ERR_ARG, "null halo");
+  if (d->Nx == d->Nx_global) return fail(FDTD_ERR_ARG, "not an x-sharded slab");
+  if (!h->flags || !h->error || !h->side_stream) return fail(FDTD_ERR_ARG, "halo: null flags / error / side stream");
+  if (h->has_left && (!h->left_ghost_y || !h->left_ghost_z || !h->left_flag))
+    return fail(FDTD_ERR_ARG, "halo: left neighbour pointers");
+  if (h->has_right && (!h->right_ghost_y || !h->right_ghost_z || !h->right_flag))
+    return fail(FDTD_ERR_ARG, "halo: right neighbour pointers");
+  return FDTD_OK;
+}
+
+template <typename T>
+int sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int field, int64_t q, int64_t slot, void* stream) {
+  const int n = d->Nx;
+  const bool is_e = field == 0;
+  cudaStream_t main = (cudaStream_t)stream, side = (cudaStream_t)h->side_stream;
+  // E: plane 0 needs the left neighbour's H ghost and goes to the left neighbour; H: the last plane needs the
+  // right neighbour's E ghost and goes to the right neighbour
+  const bool has_nb = is_e ? h->has_left != 0 : h->has_right != 0;
+  const int b0 = is_e ? 1 : 0, b1 = is_e ? n : n - 1;
+  const int e0 = is_e ? 0 : (n - 1 > 0 ? n - 1 : 0), e1 = is_e ? (n < 1 ? n : 1) : n;
+  void* gy = is_e ? h->left_ghost_y : h->right_ghost_y;
+  void* gz = is_e ? h->left_ghost_z : h->right_ghost_z;
+  int64_t* peer_flag = is_e ? h->left_flag : h->right_flag;
+  int rc = stream_after(side, main, g_join.to_side);      // everything enqueued so far (user writes included)
+  if (rc) return rc;
+  rc = is_e ? launch_halfstep<T, true>(d, b0, b1, q, slot, main) : launch_halfstep<T, false>(d, b0, b1, q, slot, main);
+  if (rc) return rc;
+  if (has_nb) {
+    // the ghost this plane needs was pushed by the neighbour after its last half-step of the OTHER field
+    FDTD_LAUNCH((fdtd::halo_wait_kernel), dim3(1), dim3(32), side, (const i64*)h->flags + (1 - field),
+                (i64)h->count[1 - field], (int*)h->error, (i64)h->timeout_ns);
+    rc = check_launch("halo_wait");
+    if (rc) return rc;
+  }
+  const bool fused = has_nb && h->push_fused[field];
+  rc = is_e ? launch_halfstep<T, true>(d, e0, e1, q, slot, side, -1, fused ? gy : nullptr, fused ? gz : nullptr)
+            : launch_halfstep<T, false>(d, e0, e1, q, slot, side, -1, fused ? gy : nullptr, fused ? gz : nullptr);
+  if (rc) return rc;
+  if (fused) {
+    FDTD_LAUNCH((fdtd::halo_signal_kernel), dim3(1), dim3(32), side, (i64*)peer_flag, (i64)(h->count[field] + 1));
+    rc = check_launch("halo_signal");
+    if (rc) return rc;
+  }
+  rc = stream_after(main, side, g_join.to_main);
+  if (rc) return rc;
+  rc = is_e ? launch_post<T, true>(d, q, slot, main) : launch_post<T, false>(d, q, slot, main);
+  if (rc) return rc;
+  if (has_nb && !fused) {
+    rc = stream_after(side, main, g_join.to_side);
+    if (rc) return rc;
+    const int64_t plane_off = is_e ? 0 : (int64_t)(n - 1) * d->plane;
+    void* const* F = is_e ? d->E : d->H;
+    FDTD_LAUNCH((fdtd::halo_push_kernel<T>), dim3(blocks_for(d->plane)), dim3(256), side, (const T*)F[1] + plane_off,
+                (const T*)F[2] + plane_off, (T*)gy, (T*)gz, (i64)d->plane);
+    rc = check_launch("halo_push");
+    if (rc) return rc;
+    FDTD_LAUNCH((fdtd::halo_signal_kernel), dim3(1), dim3(32), side, (i64*)peer_flag, (i64)(h->count[field] + 1));
+    rc = check_launch("halo_signal");
+    if (rc) return rc;
+  }
+  h->count[field] += 1;
+  return FDTD_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int fdtd_sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int32_t field, int64_t q, int64_t slot, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if ((rc = check_halo(d, h)) != 0) return rc;
+  if (field != 0 && field != 1) return fail(FDTD_ERR_ARG, "field must be 0 (E) or 1 (H)");
+  if (d->x_wrap) return fail(FDTD_ERR_UNSUPPORTED, "periodic x boundary across slabs: drive the parts yourself");
+  if ((rc = g_join.ensure()) != 0) return rc;
+  return d->dtype == FDTD_F32 ? sharded_halfstep<float>(d, h, field, q, slot, stream)
+                              : sharded_halfstep<double>(d, h, field, q, slot, stream);
+}
+
+int fdtd_run_sharded(const fdtd_desc* d, fdtd_halo* h, int64_t q0, int64_t nsteps, int64_t slot0, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if ((rc = check_halo(d, h)) != 0) return rc;
+  if (nsteps < 0) return fail(FDTD_ERR_ARG, "nsteps < 0");
+  if (d->x_wrap) return fail(FDTD_ERR_UNSUPPORTED, "periodic x boundary across slabs: drive the parts yourself");
+  if ((rc = g_join.ensure()) != 0) return rc;
+  for (int64_t s = 0; s < nsteps; ++s) {
+    for (int field = 0; field < 2; ++field) {
+      rc = d->dtype == FDTD_F32 ? sharded_halfstep<float>(d, h, field, q0 + s, slot0 + s, stream)
+                                : sharded_halfstep<double>(d, h, field, q0 + s, slot0 + s, stream);
+      if (rc) return rc;
+    }
+  }
+  return FDTD_OK;
+}
+
+int fdtd_halo_refresh(const fdtd_desc* d, fdtd_halo* h, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if ((rc = check_halo(d, h)) != 0) return rc;
+  for (int field = 0; field < 2; ++field) {
+    const bool is_e = field == 0;
+    if (is_e ? h->has_left : h->has_right) {
+      rc = fdtd_halo_push(d, field, is_e ? h->left_ghost_y : h->right_ghost_y, is_e ? h->left_ghost_z : h->right_ghost_z,
+                          stream);
+      if (rc) return rc;
+      rc = fdtd_halo_signal(is_e ? h->left_flag : h->right_flag, h->count[field] + 1, stream);
+      if (rc) return rc;
+    }
+    h->count[field] += 1;
+  }
+  // E ghosts come from the right neighbour, H ghosts from the left one
+  if (h->has_right) {
+    rc = fdtd_halo_wait(h->flags, h->count[0], h->error, h->timeout_ns, stream);
+    if (rc) return rc;
+  }
+  if (h->has_left) {
+    rc = fdtd_halo_wait(h->flags + 1, h->count[1], h->error, h->timeout_ns, stream);
+    if (rc) return rc;
+  }
   return FDTD_OK;
 }
 #endif
@@ -965,9 +1124,20 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
 #define FDTD_GRAPH_CACHE 4     /* descriptors (grids) whose graphs are kept per host thread */
 namespace {
 struct GraphEntry {
-  fdtd_desc desc;              // the exact descriptor the graph was captured from
+  fdtd_desc desc;              // the exact descriptor the graph was captured from ...
+  std::vector<fdtd_source> sources;       // ... and the source / detector tables it points to
+  std::vector<fdtd_detector> detectors;
   cudaGraphExec_t exec = nullptr;
   uint64_t used = 0;           // LRU stamp
+  bool same(const fdtd_desc* d) const {
+    fdtd_desc a = desc, b = *d;
+    a.sources = b.sources = nullptr;      // compared by content
+    a.detectors = b.detectors = nullptr;
+    if (memcmp(&a, &b, sizeof(fdtd_desc)) != 0) return false;
+    if ((size_t)d->n_sources != sources.size() || (size_t)d->n_detectors != detectors.size()) return false;
+    if (d->n_sources && memcmp(sources.data(), d->sources, sizeof(fdtd_source) * sources.size()) != 0) return false;
+    return !d->n_detectors || memcmp(detectors.data(), d->detectors, sizeof(fdtd_detector) * detectors.size()) == 0;
+  }
 };
 struct GraphCache {
   GraphEntry entry[FDTD_GRAPH_CACHE];
@@ -980,7 +1150,7 @@ int graph_for(const fdtd_desc* d, cudaGraphExec_t* out) {
   // a graph bakes in every pointer, size and table of the descriptor: reuse it only for a byte-identical one
   GraphEntry* slot = &g_graph.entry[0];
   for (GraphEntry& e : g_graph.entry) {
-    if (e.exec && memcmp(&e.desc, d, sizeof(fdtd_desc)) == 0) {
+    if (e.exec && e.same(d)) {
       e.used = ++g_graph.clock;
       *out = e.exec;
       return FDTD_OK;
@@ -1016,6 +1186,8 @@ int graph_for(const fdtd_desc* d, cudaGraphExec_t* out) {
     return fail(FDTD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
   }
   memcpy(&slot->desc, d, sizeof(fdtd_desc));
+  slot->sources.assign(d->sources, d->sources + d->n_sources);
+  slot->detectors.assign(d->detectors, d->detectors + d->n_detectors);
   slot->used = ++g_graph.clock;
   *out = slot->exec;
   return FDTD_OK;

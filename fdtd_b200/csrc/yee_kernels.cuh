@@ -893,18 +893,23 @@ __global__ void halo_signal_kernel(i64* peer_flag, i64 value) {
   }
 }
 
-// consume: spin until the local flag (written by the neighbour) reaches `value`; gives up after 2^34 cycles
-// (~9 s) and raises *error instead of hanging the GPU if the neighbour died
-__global__ void halo_wait_kernel(const i64* flag, i64 value, int* error) {
+// consume: spin until the local flag (written by the neighbour) reaches `value`.  A neighbour that stopped
+// stepping must not turn into a silent wrong result: after `timeout_ns` of wall-clock time (%globaltimer) the
+// kernel raises *error and TRAPS, so nothing enqueued behind it ever consumes a stale ghost plane -- the next
+// synchronising call of the host reports the failure.
+__global__ void halo_wait_kernel(const i64* flag, i64 value, int* error, i64 timeout_ns) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const long long t0 = clock64();
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     i64 v;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
       if (v >= value) break;
-      if (clock64() - t0 > (1LL << 34)) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (timeout_ns > 0 && (i64)(t1 - t0) > timeout_ns) {
         *error = 1;
-        break;
+        __threadfence_system();
+        __trap();
       }
       __nanosleep(200);
     }

@@ -64,6 +64,8 @@ class _Detector:
             gx = np.where(gx < 0, gx + self.grid.Nx, gx)
             self._rank_positions = [np.nonzero((gx >= part.bounds(r)[0]) & (gx < part.bounds(r)[1]))[0]
                                     for r in range(part.world)]
+        # points of the rank that holds most of them: what every rank sizes the ring capacity with
+        self._n_ring = max(len(p) for p in self._rank_positions) if part.sharded else self._n_local
 
     def _ensure_ring(self, capacity):
         if self._ring_E is None or self._capacity != capacity:

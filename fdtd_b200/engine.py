@@ -175,40 +175,44 @@ class Engine:
         # --- sources ----------------------------------------------------------------------------
         self._src_entries = []       # (desc index, source object)
         self._feedback_sources = []  # those that record their voltages in a device ring
+        entries = [(s, entry) for s in g.sources for entry in s._entries()]
+        # host tables of any length (the reference keeps plain lists, fdtd/grid.py:155-163); the descriptor points at them
+        self._src_table = (_capi.Source * max(1, len(entries)))()
+        d.sources = C.cast(self._src_table, C.POINTER(_capi.Source))
         n = 0
-        for s in g.sources:
-            for entry in s._entries():
-                if n == _capi.MAX_SOURCES:
-                    raise ValueError(f"at most {_capi.MAX_SOURCES} source entries")
-                e = d.sources[n]
-                e.kind, e.field, e.comp = entry["kind"], entry["field"], entry["comp"]
-                if entry["kind"] == _capi.SRC_FEEDBACK:
-                    e.n = entry["n"]
-                    for k in range(6):
-                        e.box[k] = entry["box"][k]
-                    e.impedance, e.spacing = entry["impedance"], g.grid_spacing
-                    e.feedback = _ptr(entry["feedback"])
-                    self._feedback_sources.append((n, s))
-                elif entry["kind"] == _capi.SRC_POINTS:
-                    e.n = int(entry["idx"].numel())
-                    e.idx, e.profile = _ptr(entry["idx"]), _ptr(entry["profile"])
-                    for k in range(6):
-                        e.bbox[k] = entry["bbox"][k]
-                    self._keep += [entry["idx"], entry["profile"]]
-                else:
-                    e.amplitude = entry["amplitude"]
-                    for k in range(6):
-                        e.box[k] = entry["box"][k]
-                self._src_entries.append((n, s))
-                n += 1
+        for s, entry in entries:
+            e = d.sources[n]
+            e.kind, e.field, e.comp = entry["kind"], entry["field"], entry["comp"]
+            if entry["kind"] == _capi.SRC_FEEDBACK:
+                e.n = entry["n"]
+                for k in range(6):
+                    e.box[k] = entry["box"][k]
+                e.impedance, e.spacing = entry["impedance"], g.grid_spacing
+                e.feedback = _ptr(entry["feedback"])
+                self._feedback_sources.append((n, s))
+            elif entry["kind"] == _capi.SRC_POINTS:
+                e.n = int(entry["idx"].numel())
+                e.idx, e.profile = _ptr(entry["idx"]), _ptr(entry["profile"])
+                for k in range(6):
+                    e.bbox[k] = entry["bbox"][k]
+                self._keep += [entry["idx"], entry["profile"]]
+            else:
+                e.amplitude = entry["amplitude"]
+                for k in range(6):
+                    e.box[k] = entry["box"][k]
+            self._src_entries.append((n, s))
+            n += 1
         d.n_sources = n
         self._wave = None
+        self._src_sig = self._source_signature()
 
         # --- detectors --------------------------------------------------------------------------
-        if len(g.detectors) > _capi.MAX_DETECTORS:
-            raise ValueError(f"at most {_capi.MAX_DETECTORS} detectors")
+        self._det_table = (_capi.Detector * max(1, len(g.detectors)))()
+        d.detectors = C.cast(self._det_table, C.POINTER(_capi.Detector))
         w = 4 if dt is torch.float32 else 8
-        per_step = sum(2 * det._width * w * max(1, det._n_local) for det in g.detectors)
+        # the capacity must be the SAME on every rank of an x-sharded grid (a ring flush is collective): size it
+        # from the largest per-rank share of every detector, which every rank can compute from the partition
+        per_step = sum(2 * det._width * w * max(1, det._n_ring) for det in g.detectors)
         self.ring_capacity = int(min(8192, max(16, RING_BYTES // max(1, per_step)))) if g.detectors else 1 << 62
         for n, det in enumerate(g.detectors):
             det._ensure_ring(self.ring_capacity)
@@ -300,6 +304,8 @@ class Engine:
             raise NotImplementedError("a CurrentDetector cell on the first plane of an x-slab together with something "
                                       "that modifies the slab's last H plane after the update (periodic copy, source)")
         if self._p2p:
+            self._p2p.h.push_fused[0] = int(self._push_fused["E"])
+            self._p2p.h.push_fused[1] = int(self._push_fused["H"])
             self._p2p_refresh()
         else:
             self._halo.refresh()
@@ -319,55 +325,40 @@ class Engine:
 
     def _p2p_refresh(self):
         """push both boundary planes and wait for the neighbours' (collective; after the user wrote E / H)."""
-        lib, d, h = self.lib, self.desc, self._p2p
-        st = self._stream()
-        for field, idx in (("E", 0), ("H", 1)):
-            if field in h.dst:
-                gy, gz, flag = h.dst[field]
-                _capi.check(lib, lib.fdtd_halo_push(C.byref(d), idx, C.c_void_p(gy), C.c_void_p(gz), st))
-                _capi.check(lib, lib.fdtd_halo_signal(C.c_void_p(flag), h.count[field] + 1, st))
-            h.count[field] += 1
-        for field, idx, src_exists in (("E", 0, h.part.rank < h.part.world - 1), ("H", 1, h.part.rank > 0)):
-            if src_exists:
-                _capi.check(lib, lib.fdtd_halo_wait(C.c_void_p(h.flags.data_ptr() + 8 * idx), h.count[field],
-                                                    C.c_void_p(h.err.data_ptr()), st))
+        _capi.check(self.lib, self.lib.fdtd_halo_refresh(C.byref(self.desc), C.byref(self._p2p.h), self._stream()))
 
     def _p2p_halfstep(self, field, q, slot):
-        """one half-step of an x-sharded slab with peer-to-peer ghost planes (see P2PHalo)."""
-        lib, d, h = self.lib, self.desc, self._p2p
-        n = d.Nx
+        """one half-step of an x-sharded slab with peer-to-peer ghost planes: one C call (fdtd_sharded_halfstep)."""
+        lib, d, h = self.lib, self.desc, self._p2p.h
         fidx = 0 if field == "E" else 1
-        other = "H" if field == "E" else "E"
+        if self._wrap is None:
+            _capi.check(lib, lib.fdtd_sharded_halfstep(C.byref(d), C.byref(h), fidx, q, slot, self._stream()))
+            return
+        # a periodic x boundary crosses the slabs: the wrap plane travels between the post ops registered before and
+        # after it (send / recv of the process group), so the parts are driven from here
+        n = d.Nx
         step = lib.fdtd_e_halfstep if field == "E" else lib.fdtd_h_halfstep
         bulk = (1, n) if field == "E" else (0, n - 1)
         edge = (0, min(1, n)) if field == "E" else (max(n - 1, 0), n)
         st = self._stream()
-        dev = self.grid._E.device
-        main, side = torch.cuda.current_stream(dev), h.stream
+        main, side = torch.cuda.current_stream(self.grid._E.device), self._p2p.stream
         sst = C.c_void_p(side.cuda_stream)
         side.wait_stream(main)
         _capi.check(lib, step(C.byref(d), bulk[0], bulk[1], q, slot, st))
-        has_nb = field in h.dst                # the neighbour this plane goes to, and the ghost comes from
+        has_nb = bool(h.has_left if field == "E" else h.has_right)
         if has_nb:
-            # the ghost this plane needs was pushed by the neighbour after its last `other` half-step
-            _capi.check(lib, lib.fdtd_halo_wait(C.c_void_p(h.flags.data_ptr() + 8 * (1 - fidx)), h.count[other],
-                                                C.c_void_p(h.err.data_ptr()), sst))
-        fused = has_nb and self._push_fused[field]
-        if fused:
-            gy, gz, flag = h.dst[field]
-            _capi.check(lib, lib.fdtd_halfstep_push(C.byref(d), fidx, edge[0], edge[1], q, slot,
-                                                    C.c_void_p(gy), C.c_void_p(gz), sst))
-            _capi.check(lib, lib.fdtd_halo_signal(C.c_void_p(flag), h.count[field] + 1, sst))
-        else:
-            _capi.check(lib, step(C.byref(d), edge[0], edge[1], q, slot, sst))
+            _capi.check(lib, lib.fdtd_halo_wait(C.c_void_p(h.flags + 8 * (1 - fidx)), h.count[1 - fidx],
+                                                C.c_void_p(h.error), h.timeout_ns, sst))
+        _capi.check(lib, step(C.byref(d), edge[0], edge[1], q, slot, sst))
         main.wait_stream(side)
         self._post(field, q, slot, st)
-        if has_nb and not fused:
-            gy, gz, flag = h.dst[field]
+        if has_nb:
+            gy, gz, flag = ((h.left_ghost_y, h.left_ghost_z, h.left_flag) if field == "E"
+                            else (h.right_ghost_y, h.right_ghost_z, h.right_flag))
             side.wait_stream(main)
             _capi.check(lib, lib.fdtd_halo_push(C.byref(d), fidx, C.c_void_p(gy), C.c_void_p(gz), sst))
-            _capi.check(lib, lib.fdtd_halo_signal(C.c_void_p(flag), h.count[field] + 1, sst))
-        h.count[field] += 1
+            _capi.check(lib, lib.fdtd_halo_signal(C.c_void_p(flag), h.count[fidx] + 1, sst))
+        h.count[fidx] += 1
 
     def _classify(self, ie_eff, ie_grid_if_objects, absorb, imu, ty, tz, ie2=None, absorb2=None):
         """per-(plane, y-tile, z-tile) class byte, FDTD_CLS_* (include/fdtd_b200.h)."""
@@ -405,9 +396,16 @@ class Engine:
             cls[a:b] = bits
         return cls.contiguous()
 
+    def _source_signature(self):
+        """the per-step parameters the reference re-reads from every source on every step (fdtd/sources.py:95-108,
+        280-295, 478-486, 601-626): changing one between steps must take effect on the next step."""
+        return tuple(s._signature() for s in self.grid.sources)
+
     def stale(self):
         g = self.grid
         if g._baked_counts != g._registration_count:
+            return True
+        if self._src_sig != self._source_signature():
             return True
         v = (None if g._inv_eps is None else g._inv_eps._version,
              None if g._inv_mu is None else g._inv_mu._version)
@@ -465,6 +463,8 @@ class Engine:
         for _, src in self._feedback_sources:
             src._drain(nE)
         g._ring_fill["E"] = g._ring_fill["H"] = 0
+        if self._p2p:
+            self._p2p.check()        # the drain synchronised anyway: a timed-out halo wait surfaces here at the latest
 
     # ------------------------------------------------------------------------------------ stepping
     def _sharded_halfstep(self, field, q, slot):
@@ -546,11 +546,21 @@ class Engine:
                     g._ring_fill["H"] += n
                 for _, src in self._feedback_sources:
                     src._steps_logged.extend(range(q, q + n))
+            elif self._p2p and self._wrap is None:
+                # the whole chunk in one C call: the ranks only meet through the flag words
+                _capi.check(lib, lib.fdtd_run_sharded(C.byref(d), C.byref(self._p2p.h), q, n,
+                                                      g._ring_fill["E"] if rings else 0, self._stream()))
+                if rings:
+                    g._ring_fill["E"] += n
+                    g._ring_fill["H"] += n
+                for _, src in self._feedback_sources:
+                    src._steps_logged.extend(range(q, q + n))
             else:
                 for s in range(n):
                     self.update_E(q + s)
                     self.update_H(q + s)
             done += n
+            g.time_steps_passed = q0 + done      # per chunk: an interrupted run leaves counter and fields in step
             if progress is not None:
                 progress.update(n)
 
@@ -563,5 +573,3 @@ class Engine:
                     self._pending[f] = None
             if self._halo.cuda:
                 torch.cuda.current_stream(self.grid._E.device).wait_stream(self._halo.stream)
-            if self._p2p:
-                self._p2p.check()

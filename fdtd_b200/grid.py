@@ -282,10 +282,11 @@ class Grid:
         if progress_bar:
             from tqdm import tqdm
             bar = tqdm(total=n)
-        eng.run(self.time_steps_passed, n, bar)
-        self.time_steps_passed += n
-        if bar is not None:
-            bar.close()
+        try:
+            eng.run(self.time_steps_passed, n, bar)       # advances time_steps_passed chunk by chunk
+        finally:
+            if bar is not None:
+                bar.close()
 
     def step(self):
         """one full step: update_E, update_H, count (fdtd/grid.py:267-273)."""

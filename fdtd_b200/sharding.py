@@ -168,13 +168,15 @@ class P2PHalo:
     """Halo exchange by direct stores into the neighbour slab's ghost planes over NVLink.
 
     One process per GPU: every rank exports its E / H storage and a two-word flag array with CUDA IPC
-    (include/fdtd_b200.h, fdtd_ipc_export / fdtd_ipc_import) and maps its neighbours'.  The half-step kernel
-    that computes a slab's boundary plane stores it into the neighbour's ghost plane as well
-    (fdtd_halfstep_push: compute + transfer in one kernel); a one-thread kernel then publishes the new
-    half-step count in the neighbour's flag (release, system scope) and the neighbour's stream spins on its
-    local flag (acquire) before the kernel that consumes the ghost.  No NCCL call, no host synchronisation
-    between the processes; counts are monotonic, so ranks may run ahead of each other by at most one
-    half-step (the dependency chain of the flags is the back-pressure)."""
+    (include/fdtd_b200.h, fdtd_ipc_export / fdtd_ipc_import) and maps its neighbours'.  The result is one
+    `fdtd_halo` struct (`self.h`): peer pointers, flag addresses, running push counts.  The library does the rest
+    (fdtd_sharded_halfstep / fdtd_run_sharded): the half-step kernel that computes a slab's boundary plane stores it
+    into the neighbour's ghost plane as well (compute + transfer in one kernel); a one-thread kernel then publishes
+    the new half-step count in the neighbour's flag (release, system scope) and the neighbour's stream spins on its
+    local flag (acquire) before the kernel that consumes the ghost.  No NCCL call, no host synchronisation between
+    the processes; counts are monotonic, so ranks may run ahead of each other by at most one half-step (the
+    dependency chain of the flags is the back-pressure).  A wait that exceeds FDTD_B200_HALO_TIMEOUT_S (default
+    120 s) raises the error word and traps, so a dead neighbour can never turn into a silently wrong result."""
 
     def __init__(self, part, E, H, lib):
         import ctypes as C
@@ -185,7 +187,6 @@ class P2PHalo:
         self.stream = torch.cuda.Stream(device=dev)
         self.flags = torch.zeros(2, dtype=torch.int64, device=dev)     # [0]: E pushes received, [1]: H pushes
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.count = {"E": 0, "H": 0}                                   # pushes sent == pushes expected
         torch.cuda.synchronize(dev)
 
         def export(t):
@@ -215,19 +216,25 @@ class P2PHalo:
         failure = next((r["error"] for r in everyone if "error" in r), None)
         w = E.element_size()
         plane = E.shape[2] * E.shape[3]
-        self.dst = {}      # field -> (peer ghost y, peer ghost z, peer flag address)
+        h = self.h = _capi.Halo()
+        h.has_left, h.has_right = int(part.rank > 0), int(part.rank < part.world - 1)
+        h.flags, h.error = self.flags.data_ptr(), self.err.data_ptr()
+        h.side_stream = self.stream.cuda_stream
+        h.timeout_ns = int(float(os.environ.get("FDTD_B200_HALO_TIMEOUT_S", "120")) * 1e9)
         if failure is None:
             try:
-                if part.rank > 0:                                   # E plane 0 -> left neighbour's high ghost
+                if h.has_left:                                      # E plane 0 -> left neighbour's high ghost
                     rec = everyone[part.rank - 1]
                     base, nxl = open_(rec["E"]), rec["nx"]
-                    self.dst["E"] = (base + ((1 * (nxl + 2) + nxl + 1) * plane) * w,
-                                     base + ((2 * (nxl + 2) + nxl + 1) * plane) * w, open_(rec["flags"]))
-                if part.rank < part.world - 1:                      # H last plane -> right neighbour's low ghost
+                    h.left_ghost_y = base + ((1 * (nxl + 2) + nxl + 1) * plane) * w
+                    h.left_ghost_z = base + ((2 * (nxl + 2) + nxl + 1) * plane) * w
+                    h.left_flag = open_(rec["flags"])
+                if h.has_right:                                     # H last plane -> right neighbour's low ghost
                     rec = everyone[part.rank + 1]
                     base, nxl = open_(rec["H"]), rec["nx"]
-                    self.dst["H"] = (base + (1 * (nxl + 2) * plane) * w, base + (2 * (nxl + 2) * plane) * w,
-                                     open_(rec["flags"]) + 8)
+                    h.right_ghost_y = base + (1 * (nxl + 2) * plane) * w
+                    h.right_ghost_z = base + (2 * (nxl + 2) * plane) * w
+                    h.right_flag = open_(rec["flags"]) + 8
             except Exception as exc:
                 failure = str(exc)
         ok = torch.tensor([0 if failure else 1], device=dev)
@@ -235,11 +242,8 @@ class P2PHalo:
         if int(ok.item()) == 0:
             raise RuntimeError(failure or "a neighbour rank could not map this rank's memory")
 
-    def neighbour(self, field):
-        """the rank this field's boundary plane goes to -- and the other field's ghost comes from."""
-        return field in self.dst
-
     def check(self):
+        """raise if a halo wait timed out (call where the host synchronises anyway: ring flushes)"""
         if int(self.err.item()) != 0:
             raise RuntimeError("fdtd_b200: peer-to-peer halo wait timed out (a neighbour rank stopped stepping)")
 

@@ -90,6 +90,9 @@ class _TimedSource:
             return pulse(q, self.frequency, self.hanning_dt, self.cycle)
         return continuous(q, self.period, self.phase_shift)
 
+    def _signature(self):
+        return (self.period, self.amplitude, self.phase_shift, self.pulse, self.cycle, self.frequency, self.hanning_dt)
+
     def update_E(self):      # the reference's plug-in protocol; the engine does the work
         pass
 
@@ -186,13 +189,15 @@ class PlaneSource:
 
     def _register_grid(self, grid, x, y, z):
         self.grid = grid
+        self.x, self.y, self.z = self._handle_slices(x, y, z)
+        self._resolved()                   # out-of-range regions fail here, not at the first step, and register nothing
         self.grid.sources.append(self)
         grid._register_name(self)
-        self.x, self.y, self.z = self._handle_slices(x, y, z)
         self.period = grid._handle_time(self.period)
         self.frequency = 1.0 / self.period
         ext = [s.stop - s.start for s in (self.x, self.y, self.z)]
         self.profile = self.amplitude * bd.ones(tuple(ext))      # reference attribute (uniform)
+        self._amplitude0 = self.amplitude     # the reference bakes the amplitude into `profile` here, once
 
     def _handle_slices(self, x, y, z):
         g = self.grid
@@ -225,11 +230,30 @@ class PlaneSource:
     def _wave_value(self, q):
         return sin(2 * pi * q / self.period + self.phase_shift)
 
+    def _signature(self):
+        return (self.period, self.phase_shift)
+
+    def _resolved(self):
+        """the cells `E[self.x, self.y, self.z]` addresses in the reference: slice bounds resolved the way numpy
+        resolves them (negative bounds count from the end).  A region the `profile` (shaped by the nominal extents)
+        could not be assigned to raises, as the reference's assignment would at the first step."""
+        g = self.grid
+        out = []
+        for s, n in ((self.x, g.Nx), (self.y, g.Ny), (self.z, g.Nz)):
+            a, b, _ = slice(s.start, s.stop).indices(n)
+            b = max(a, b)
+            nominal = s.stop - s.start
+            if b - a != nominal and not (nominal == 1 and b == a):     # (1 -> 0 broadcasts: a silent no-op there)
+                raise IndexError(f"PlaneSource region {s.start}:{s.stop} reaches outside the grid (extent {n})")
+            out.append((a, b))
+        return out
+
     def _entries(self):
         g = self.grid
-        lx0, lx1 = g._part.local_range(self.x.start, self.x.stop)
-        box = [lx0, lx1, self.y.start, self.y.stop, self.z.start, self.z.stop]
-        amp = scalar_in_dtype(self.amplitude, g._dtype)
+        (x0, x1), (y0, y1), (z0, z1) = self._resolved()
+        lx0, lx1 = g._part.local_range(x0, x1)
+        box = [lx0, lx1, y0, y1, z0, z1]
+        amp = scalar_in_dtype(self._amplitude0, g._dtype)
         return [dict(kind=_capi.SRC_BOX, field=0, comp=self._Epol, box=box, amplitude=amp),
                 dict(kind=_capi.SRC_BOX, field=1, comp=self._Hpol, box=box, amplitude=amp)]
 
@@ -269,6 +293,7 @@ class SoftArbitraryPointSource:
         self._ring_V = None
         self._capacity = 0
         self._steps_logged = []      # step index of every E half-step this source took part in
+        self._wf_cache = None
 
     def _register_grid(self, grid, x, y, z):
         from .detectors import CurrentDetector
@@ -284,12 +309,25 @@ class SoftArbitraryPointSource:
         detector_name = self.name + "_I" if self.name is not None else None
         self.current_detector = CurrentDetector(name=detector_name)
         grid[x, y, z] = self.current_detector
-        lx0, lx1 = grid._part.local_range(self.x, self.x + 1)
+        # negative indices address from the end, as the reference's `grid.E[x, y, z, 2] += ...` does
+        cell = []
+        for v, n in ((self.x, grid.Nx), (self.y, grid.Ny), (self.z, grid.Nz)):
+            c = v + n if v < 0 else v
+            if not 0 <= c < n:
+                raise IndexError(f"index {v} is out of bounds for a grid axis of size {n}")
+            cell.append(c)
+        lx0, lx1 = grid._part.local_range(cell[0], cell[0] + 1)
         self._n_local = lx1 - lx0
-        self._box = [lx0, lx1, self.y, self.y + 1, self.z, self.z + 1]
+        self._box = [lx0, lx1, cell[1], cell[1] + 1, cell[2], cell[2] + 1]
+
+    @property
+    def _waveform_host(self):
+        """the waveform as a flat host array (re-read when the user assigns a new `waveform_array`)"""
         wf = self.waveform_array
-        wf = wf.detach().cpu().numpy() if torch.is_tensor(wf) else np.asarray(wf)
-        self._waveform_host = wf.reshape(-1)
+        if self._wf_cache is None or self._wf_cache[0] is not wf:
+            arr = wf.detach().cpu().numpy() if torch.is_tensor(wf) else np.asarray(wf)
+            self._wf_cache = (wf, arr.reshape(-1))
+        return self._wf_cache[1]
 
     def _wave_value(self, q):
         # input voltage of step q; zero once the waveform is exhausted (fdtd/sources.py:601-605)
@@ -298,6 +336,9 @@ class SoftArbitraryPointSource:
     def _entries(self):
         return [dict(kind=_capi.SRC_FEEDBACK, field=0, comp=2, n=self._n_local, box=self._box,
                      impedance=float(self.impedance), feedback=self.current_detector._last)]
+
+    def _signature(self):
+        return (id(self.waveform_array), float(self.impedance))
 
     def _ensure_ring(self, capacity):
         if self._ring_V is None or self._capacity != capacity:

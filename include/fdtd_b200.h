@@ -40,15 +40,13 @@
 extern "C" {
 #endif
 
-#define FDTD_ABI_VERSION 14
+#define FDTD_ABI_VERSION 15
 
 #define FDTD_F32 0
 #define FDTD_F64 1
 
 #define FDTD_MAX_SLABS 6
 #define FDTD_MAX_POST 16
-#define FDTD_MAX_SOURCES 64
-#define FDTD_MAX_DETECTORS 64
 #define FDTD_FUSED_MAX 6       /* sources / detectors per field folded into the half-step kernel */
 
 #define FDTD_OK 0
@@ -173,8 +171,9 @@ typedef struct fdtd_desc {
   int32_t post_arg[FDTD_MAX_POST];
   int32_t n_sources;
   int32_t n_detectors;
-  fdtd_source sources[FDTD_MAX_SOURCES];       /* registration order */
-  fdtd_detector detectors[FDTD_MAX_DETECTORS]; /* registration order */
+  const fdtd_source* sources;      /* HOST array [n_sources], registration order; any length (the reference keeps plain
+                                      Python lists, fdtd/grid.py:155-163); caller-owned, read during the call only */
+  const fdtd_detector* detectors;  /* HOST array [n_detectors], registration order */
   int32_t x_chunk;     /* planes marched per thread block; 0 = library default */
   int32_t use_graphs;  /* 1: fdtd_run may replay CUDA graphs of step chunks (launch-bound small grids) */
   int64_t* dyn;        /* device int64[2] scratch owned by the caller, needed when use_graphs = 1 */
@@ -203,6 +202,7 @@ typedef struct fdtd_desc {
 int32_t fdtd_abi_version(void);
 /* sizeof(fdtd_desc) as the library was compiled: a binding checks its own struct layout against it */
 int64_t fdtd_sizeof_desc(void);
+int64_t fdtd_sizeof_halo(void);
 const char* fdtd_last_error(void);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t fdtd_launch_count(void);
@@ -264,9 +264,45 @@ int fdtd_halfstep_push(const fdtd_desc* d, int32_t field, int32_t x_begin, int32
 int fdtd_halo_push(const fdtd_desc* d, int32_t field, void* peer_ghost_y, void* peer_ghost_z, void* stream);
 /* publish `value` in the neighbour's flag after everything enqueued before on `stream` (release, system scope) */
 int fdtd_halo_signal(int64_t* peer_flag, int64_t value, void* stream);
-/* make `stream` wait until the local flag reaches `value` (acquire, system scope); after ~9 s of spinning it
- * gives up and sets *error (device int) instead of hanging */
-int fdtd_halo_wait(const int64_t* flag, int64_t value, int32_t* error, void* stream);
+/* make `stream` wait until the local flag reaches `value` (acquire, system scope).  After `timeout_ns` of wall-clock
+ * time (0 = wait for ever) the waiting kernel sets *error (device int) and TRAPS: nothing enqueued behind it runs on
+ * a stale ghost plane, and the caller's next synchronising CUDA call fails */
+int fdtd_halo_wait(const int64_t* flag, int64_t value, int32_t* error, int64_t timeout_ns, void* stream);
+
+/* One rank's view of the peer-to-peer halo exchange: peer pointers into the two neighbour slabs (from
+ * fdtd_ipc_import), this rank's flag words, and the running push counts.  Caller-owned host struct; `count` is
+ * updated by the calls below. */
+typedef struct fdtd_halo {
+  int32_t has_left, has_right;   /* this slab has a left / right neighbour */
+  void* left_ghost_y;            /* LEFT neighbour's HIGH ghost plane of Ey (peer pointer) */
+  void* left_ghost_z;            /*   ... of Ez: where this slab's E plane 0 goes after every E half-step */
+  void* right_ghost_y;           /* RIGHT neighbour's LOW ghost plane of Hy */
+  void* right_ghost_z;           /*   ... of Hz: where this slab's last H plane goes after every H half-step */
+  int64_t* left_flag;            /* left neighbour's flag word [0]: number of E pushes it has received */
+  int64_t* right_flag;           /* right neighbour's flag word [1]: number of H pushes it has received */
+  const int64_t* flags;          /* this rank's device int64[2], written by the neighbours */
+  int32_t* error;                /* device int32, raised by a wait that timed out */
+  int64_t count[2];              /* E / H pushes done so far == pushes expected from the neighbours (in / out) */
+  int32_t push_fused[2];         /* E / H: nothing modifies the boundary plane after the half-step kernel (no periodic
+                                    copy, late PML correction or unfused source on it): the kernel that computes the
+                                    plane stores it into the neighbour's ghost as well; otherwise a copy kernel
+                                    pushes it after the post ops */
+  void* side_stream;             /* cudaStream_t the boundary plane runs on, concurrently with the bulk */
+  int64_t timeout_ns;            /* fdtd_halo_wait limit; 0 = none */
+} fdtd_halo;
+
+/* One half-step (field 0 = E, 1 = H) of an x-sharded slab, everything a rank does for it: the bulk planes on
+ * `stream`; on h->side_stream the wait for the neighbour's ghost plane, the boundary plane (pushed into the
+ * neighbour's ghost by the same kernel when h->push_fused allows) and the flag that publishes it; then the post
+ * ops, sources and detectors (fdtd_post_E/H) on `stream`; the streams are joined with events.  Not for slabs with
+ * d->x_wrap (the caller moves the wrap plane between fdtd_post_part calls itself). */
+int fdtd_sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int32_t field, int64_t q, int64_t slot, void* stream);
+/* Grid.run on an x-sharded slab: nsteps x { E half-step, H half-step } as above, no host work in between --
+ * the ranks only meet through the flag words */
+int fdtd_run_sharded(const fdtd_desc* d, fdtd_halo* h, int64_t q0, int64_t nsteps, int64_t slot0, void* stream);
+/* push both boundary planes and wait for the neighbours' (collective: every rank calls it; after the user wrote
+ * E / H, and once after set-up) */
+int fdtd_halo_refresh(const fdtd_desc* d, fdtd_halo* h, void* stream);
 
 /* ---- running DFT of detector records, on the device (spectra of long runs without
  * moving the time traces to the host; the reference transforms the host lists, fdtd/fourier.py:172-213) -----

@@ -34,6 +34,9 @@ def main():
         build, _ = random_scene(int(scene[5:]))
     else:
         build = scenes.SCENES[scene][0] if scene in scenes.SCENES else getattr(scenes, scene)
+    if os.environ.get("FDTD_TEST_RING_BYTES"):           # tiny detector rings: several collective flushes per run
+        import fdtd_b200.engine as engine
+        engine.RING_BYTES = int(os.environ["FDTD_TEST_RING_BYTES"])
     try:
         g = build(fd)
         if os.environ.get("FDTD_TEST_TRACK"):

@@ -132,6 +132,20 @@ def slab2d_xz(fd, n=(40, 1, 36), t=6):
     return g
 
 
+def slabdet(fd, n=(24, 40, 10), t=4):
+    """a 40-point LineDetector that lives on ONE x-plane (one rank of a sharded grid holds all of it, the others
+    none) next to a one-point BlockDetector elsewhere: the ring capacity, and with it the collective flushes,
+    must not depend on a rank's share of the points."""
+    g = fd.Grid(shape=n, grid_spacing=77.5e-9)
+    g[0:t, :, :] = fd.PML()
+    g[-t:, :, :] = fd.PML()
+    g[:, :, 0:t] = fd.PML()
+    g[n[0] // 2, n[1] // 2, n[2] // 2] = fd.PointSource(period=12)
+    g[n[0] - 6, :, n[2] // 2] = fd.LineDetector(name="plane_line")
+    g[3:3, 5:5, 2:2] = fd.BlockDetector(name="one_point")
+    return g
+
+
 def c4small(fd, n=(32, 32, 32), t=6):
     """configs[3] shape (the bench workload) reduced: six PMLs, centre PointSource, LineDetector."""
     g = fd.Grid(shape=n, grid_spacing=77.5e-9)

@@ -368,3 +368,84 @@ def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t, zp):
     assert float(np.abs(outs[0]["E"]).max()) > 0
     for other in outs[1:]:
         compare(other, outs[0], 0.0, bitwise=True)
+
+
+# ---- ADVICE r1 ------------------------------------------------------------------------------------------------
+
+def test_negative_indices_of_plane_and_feed_sources():
+    """grid[-5, :, :] = PlaneSource() and a SoftArbitraryPointSource at negative indices address from the end, as
+    numpy indexing does in the reference (fdtd/sources.py:476-486, 611-626); they used to inject nothing."""
+    def build(fd):
+        g = fd.Grid(shape=(20, 14, 12), grid_spacing=77.5e-9)
+        g[0:4, :, :] = fd.PML()
+        g[-6, :, :] = fd.PlaneSource(period=11, polarization="y", name="plane")
+        g[:, -3, :] = fd.PlaneSource(period=7, amplitude=0.5, polarization="x", name="plane_y")
+        wf = np.sin(np.arange(40) * 0.3)
+        g[-4, -5, -2] = fd.SoftArbitraryPointSource(wf, impedance=0.5)
+        g[2:18, 7, 6] = fd.LineDetector(name="line")
+        return g
+    got = run_scene(use_emu("float64"), build, 30)
+    want = run_oracle(build, 30)
+    assert float(np.abs(want["E"]).max()) > 0
+    compare(got, want, 1e-12, bitwise=True)
+
+
+def test_plane_source_regions_outside_the_grid():
+    fd = use_emu("float64")
+    g = fd.Grid(shape=(10, 10, 10), grid_spacing=77.5e-9)
+    with pytest.raises(IndexError):
+        g[3, 0:14, :] = fd.PlaneSource()                      # profile (1, 14, 10) cannot be assigned to (1, 10, 10)
+    g[-1, :, :] = fd.PlaneSource(name="empty")                # slice(-1, 0): an empty region, a silent no-op there too
+    g.run(3, progress_bar=False)
+    assert float(g.E.abs().max()) == 0.0
+    with pytest.raises(IndexError):
+        g[12, 3, 3] = fd.SoftArbitraryPointSource(np.ones(4))
+
+
+def test_source_parameters_changed_between_steps_take_effect_at_once():
+    """the reference reads amplitude / period / phase_shift of a source on every step (fdtd/sources.py:95-108);
+    the host-tabulated waveforms must not lag behind a change (e.g. switching a source off with amplitude = 0)."""
+    def drive(fd):
+        g = fd.Grid(shape=(14, 12, 10), grid_spacing=77.5e-9)
+        g[7, 6, 5] = fd.PointSource(period=9, amplitude=1.0, name="p")
+        g[3:11, 6, 4] = fd.LineSource(period=13, name="l")
+        g[4, 4, 4:8] = fd.LineDetector(name="d")
+        g.run(10, **({} if fd is yo else {"progress_bar": False}))
+        g.p.amplitude = 0.0
+        g.l.phase_shift = 0.7
+        for _ in range(6):
+            g.step()
+        g.p.amplitude = 2.5
+        g.p.period = 5
+        g.run(9, **({} if fd is yo else {"progress_bar": False}))
+        return scenes.dump(g)
+    got = drive(use_emu("float64"))
+    yo.set_backend("numpy", "float64")
+    want = drive(yo)
+    compare(got, want, 1e-12, bitwise=True)
+
+
+def test_step_counter_follows_the_chunks_of_an_interrupted_run(monkeypatch):
+    """Grid.run advances time_steps_passed chunk by chunk: an exception in the middle of a run leaves the counter
+    (and with it the source phase) where the fields are, as the reference's per-step increment does."""
+    import fdtd_b200.engine as engine
+    monkeypatch.setattr(engine, "RING_BYTES", 1)            # ring capacity 16 -> chunks of 16 steps
+    fd = use_emu("float64")
+    g = scenes.pml3d(fd, n=(12, 10, 9), t=3)
+    eng = g._ready()
+    calls = {"n": 0}
+    real = eng.flush_detectors
+
+    def flaky():
+        calls["n"] += 1
+        if calls["n"] == 3:
+            raise KeyboardInterrupt
+        real()
+    monkeypatch.setattr(eng, "flush_detectors", flaky)
+    with pytest.raises(KeyboardInterrupt):
+        g.run(100, progress_bar=False)
+    assert g.time_steps_passed == 48                          # three complete chunks ran before the third flush
+    monkeypatch.setattr(eng, "flush_detectors", real)
+    g.run(100 - g.time_steps_passed, progress_bar=False)
+    want = run_oracle(scenes.pml3d, 100, n=(12, 10, 9), t=3)
+    compare(scenes.dump(g), want, 1e-12, bitwise=True)

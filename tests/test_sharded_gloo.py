@@ -112,3 +112,23 @@ def test_sharded_running_dft(tmp_path):
         assert got[k].shape == want[k].shape, k
         assert np.abs(want[k]).max() > 0, k
         assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ring_capacity_is_the_same_on_every_rank(tmp_path, world):
+    """a detector whose points all live on one slab, with detector rings so small that a run flushes them several
+    times: every flush is collective, so every rank must reach it at the same step (the capacity was
+    derived from the rank-local point count and the ranks deadlocked)."""
+    steps = 70
+    out = str(tmp_path / "sharded.npz")
+    # 40 points x 2 fields x 3 components x 8 bytes = 1920 bytes per step on the owning rank
+    launch(world, "gloo", "float64", "slabdet", steps, out, FDTD_TEST_RING_BYTES=str(1920 * 20))
+    got = dict(np.load(out))
+    fd = use_emu("float64")
+    g = scenes.slabdet(fd)
+    g.run(steps, progress_bar=False)
+    want = scenes.dump(g)
+    assert float(np.abs(want["det0_E"]).max()) > 0
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
