@@ -8,7 +8,7 @@ import os
 
 ABI_VERSION = 15
 MAX_SLABS, MAX_POST, FUSED_MAX = 6, 16, 6
-F32, F64 = 0, 1
+F32, F64, F32X = 0, 1, 2
 CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT, CLS_ANISO, CLS_OVERLAP, CLS_ABSORB2 = 1, 2, 4, 8, 16, 32, 64
 POST_PERIODIC, POST_PML_ADD = 0, 1
 SRC_POINTS, SRC_BOX, SRC_FEEDBACK = 0, 1, 2

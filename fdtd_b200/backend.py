@@ -5,6 +5,10 @@ of include/fdtd_b200.h.  Accepted names:
     "cuda"            float64 storage and arithmetic (the reference's default precision)
     "cuda.float64"
     "cuda.float32"    true float32 storage and arithmetic
+    "cuda.float32x"   float32 storage of the state (E, H, CPML psi, detector rings) with float64 arithmetic and
+                      coefficients: every value is widened where it is used and rounded once where it is stored.
+                      Same memory footprint and HBM traffic as "cuda.float32"; stays within 1e-5 of the reference
+                      (which computes in float64 whatever its backend name says) over thousands of steps
     "torch.cuda[.float32|.float64]"   accepted as aliases of the above for drop-in scripts
 
 Every other reference name ("numpy", "torch", ...) raises: this package has no CPU path.
@@ -29,7 +33,8 @@ class Backend:
     def __init__(self):
         self.name = None
         self.device = None
-        self.float = torch.float64
+        self.float = torch.float64        # arithmetic / coefficient dtype (what `bd.zeros`, `bd.array` ... create)
+        self.storage = torch.float64      # dtype of the state: fields, CPML psi, detector rings
         self.lib = None
 
     # --- state ------------------------------------------------------------------------------
@@ -116,9 +121,12 @@ class Backend:
 
 backend = Backend()
 
+# name -> (arithmetic / coefficient dtype, storage dtype of the state)
 _NAMES = {
-    "cuda": torch.float64, "cuda.float64": torch.float64, "cuda.float32": torch.float32,
-    "torch.cuda": torch.float64, "torch.cuda.float64": torch.float64, "torch.cuda.float32": torch.float32,
+    "cuda": (torch.float64, torch.float64), "cuda.float64": (torch.float64, torch.float64),
+    "cuda.float32": (torch.float32, torch.float32), "cuda.float32x": (torch.float64, torch.float32),
+    "torch.cuda": (torch.float64, torch.float64), "torch.cuda.float64": (torch.float64, torch.float64),
+    "torch.cuda.float32": (torch.float32, torch.float32),
 }
 
 
@@ -136,6 +144,6 @@ def set_backend(name: str):
     lib = _capi.load()  # RuntimeError if the extension is not built
     backend.lib = lib
     backend.device = torch.device("cuda", torch.cuda.current_device())
-    backend.float = _NAMES[name]
+    backend.float, backend.storage = _NAMES[name]
     backend.name = name
     return backend

@@ -154,8 +154,8 @@ class PML(Boundary):
             self._row_lo = self.lo & ~3
             self._row = ((self.lo + t - self._row_lo) + 3) & ~3
             cells = part.nx * g.Ny * self._row
-        self._psi_E = bd.zeros((2, cells))
-        self._psi_H = bd.zeros((2, cells))
+        self._psi_E = bd.zeros((2, cells), dtype=g._sdtype)
+        self._psi_H = bd.zeros((2, cells), dtype=g._sdtype)
 
     # user-visible location, as the reference's `loc` (fdtd/boundaries.py:493-497 etc.)
     @property

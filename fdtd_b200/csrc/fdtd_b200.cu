@@ -97,7 +97,7 @@ int pow2_ceil(int v) {
 
 Geometry geometry(int dtype, int Ny, int Nz) {
   Geometry g;
-  if (dtype == FDTD_F32)
+  if (dtype == FDTD_F32 || dtype == FDTD_F32X)
     g.vec = (Nz % 4 == 0 && FDTD_MAX_VEC_F32 >= 4) ? 4 : ((Nz % 2 == 0 && FDTD_MAX_VEC_F32 >= 2) ? 2 : 1);
   else
     g.vec = (Nz % 2 == 0) ? 2 : 1;
@@ -155,13 +155,15 @@ int validate(const fdtd_desc* d) {
   if (!d) return fail(FDTD_ERR_ARG, "null descriptor");
   if (d->abi_version != FDTD_ABI_VERSION)
     return fail(FDTD_ERR_ARG, "descriptor ABI %d != library ABI %d", d->abi_version, FDTD_ABI_VERSION);
-  if (d->dtype != FDTD_F32 && d->dtype != FDTD_F64) return fail(FDTD_ERR_ARG, "bad dtype %d", d->dtype);
+  if (d->dtype != FDTD_F32 && d->dtype != FDTD_F64 && d->dtype != FDTD_F32X)
+    return fail(FDTD_ERR_ARG, "bad dtype %d", d->dtype);
   if (d->Nx < 1 || d->Ny < 1 || d->Nz < 1) return fail(FDTD_ERR_ARG, "bad extents");
   if (d->plane != (int64_t)d->Ny * d->Nz) return fail(FDTD_ERR_ARG, "plane != Ny*Nz");
   if (d->x_offset < 0 || d->x_offset + d->Nx > d->Nx_global)
     return fail(FDTD_ERR_ARG, "slab [%d,%d) outside global Nx=%d", d->x_offset, d->x_offset + d->Nx, d->Nx_global);
   Geometry g = geometry(d->dtype, d->Ny, d->Nz);
-  size_t w = d->dtype == FDTD_F32 ? 4 : 8;
+  const size_t w = d->dtype == FDTD_F64 ? 8 : 4;     // state: fields, psi, rings
+  const size_t wa = d->dtype == FDTD_F32 ? 4 : 8;    // coefficients: material arrays, tables, profiles, waveforms
   for (int c = 0; c < 3; ++c) {
     if (!d->E[c] || !d->H[c]) return fail(FDTD_ERR_ARG, "null field pointer");
     if (!aligned(d->E[c], w * g.vec) || !aligned(d->H[c], w * g.vec))
@@ -169,7 +171,7 @@ int validate(const fdtd_desc* d) {
     const void* opt[6] = {d->inv_eps[c], d->inv_eps_grid[c], d->absorb[c], d->inv_mu[c], d->inv_eps2[c],
                           d->absorb2[c]};
     for (int n = 0; n < 6; ++n)
-      if (opt[n] && !aligned(opt[n], w * g.vec)) return fail(FDTD_ERR_ARG, "material pointer misaligned");
+      if (opt[n] && !aligned(opt[n], wa * g.vec)) return fail(FDTD_ERR_ARG, "material pointer misaligned");
   }
   bool any_e = d->inv_eps[0] || d->inv_eps[1] || d->inv_eps[2];
   bool all_e = d->inv_eps[0] && d->inv_eps[1] && d->inv_eps[2];
@@ -273,9 +275,9 @@ T rounded_product(double a, double b) {
   return (T)((T)a * (T)b);
 }
 
-template <typename T, bool IS_E>
-fdtd::SlabK<T> slab_k(const fdtd_slab& S) {
-  fdtd::SlabK<T> k;
+template <typename T, bool IS_E, typename A = T>
+fdtd::SlabK<T, A> slab_k(const fdtd_slab& S) {
+  fdtd::SlabK<T, A> k;
   k.axis = S.axis;
   k.lo = S.lo;
   k.t = S.thickness;
@@ -286,8 +288,8 @@ fdtd::SlabK<T> slab_k(const fdtd_slab& S) {
   k.lo_al = z_slab_lo(S);
   k.tp = z_slab_row(S);
   k.psi = (T*)(IS_E ? S.psi_E : S.psi_H);
-  k.b = (const T*)(IS_E ? S.bE : S.bH);
-  k.c = (const T*)(IS_E ? S.cE : S.cH);
+  k.b = (const A*)(IS_E ? S.bE : S.bH);
+  k.c = (const A*)(IS_E ? S.cE : S.cH);
   return k;
 }
 
@@ -302,7 +304,7 @@ struct ShellOpts {
 
 // graph_step >= 0: the launch is being captured as step `graph_step` of a replayable chunk; waveform
 // index and ring slot are then graph_step + the bases in d->dyn
-template <typename T, bool IS_E>
+template <typename T, bool IS_E, typename A = T>
 int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
                     int64_t graph_step = -1, void* push_y = nullptr, void* push_z = nullptr,
                     const ShellOpts* shell = nullptr) {
@@ -323,7 +325,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
     g.tile_y = g.rows;
     g.tile_z = g.lanes_z * g.vec;
   }
-  fdtd::HalfStepParams<T> P;
+  fdtd::HalfStepParams<T, A> P;
   memset(&P, 0, sizeof(P));
   P.Nx = d->Nx;
   P.Ny = d->Ny;
@@ -339,7 +341,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
   P.lanes_shift = g.lanes_shift;
   P.rows = g.rows;
   P.plane = d->plane;
-  P.sc = (T)d->courant;
+  P.sc = (A)d->courant;
   P.y_begin = shell ? shell->y0 : 0;
   P.y_end = shell ? shell->y1 : d->Ny;
   P.z_begin = shell ? shell->z0 : 0;
@@ -348,13 +350,13 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
     P.F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
     P.Fo[c] = P.F[c];
     P.G[c] = (const T*)(IS_E ? d->H[c] : d->E[c]);
-    P.bg_c[c] = rounded_product<T>(d->courant, IS_E ? d->bg_inv_eps[c] : d->bg_inv_mu[c]);
-    P.bg_inv[c] = (T)(IS_E ? d->bg_inv_eps[c] : d->bg_inv_mu[c]);
-    P.inv[c] = (const T*)(IS_E ? d->inv_eps[c] : d->inv_mu[c]);
-    P.inv_grid[c] = IS_E ? (const T*)d->inv_eps_grid[c] : nullptr;
-    P.inv2[c] = IS_E ? (const T*)d->inv_eps2[c] : nullptr;
-    P.absorb[c] = IS_E ? (const T*)d->absorb[c] : nullptr;
-    P.absorb2[c] = IS_E ? (const T*)d->absorb2[c] : nullptr;
+    P.bg_c[c] = rounded_product<A>(d->courant, IS_E ? d->bg_inv_eps[c] : d->bg_inv_mu[c]);
+    P.bg_inv[c] = (A)(IS_E ? d->bg_inv_eps[c] : d->bg_inv_mu[c]);
+    P.inv[c] = (const A*)(IS_E ? d->inv_eps[c] : d->inv_mu[c]);
+    P.inv_grid[c] = IS_E ? (const A*)d->inv_eps_grid[c] : nullptr;
+    P.inv2[c] = IS_E ? (const A*)d->inv_eps2[c] : nullptr;
+    P.absorb[c] = IS_E ? (const A*)d->absorb[c] : nullptr;
+    P.absorb2[c] = IS_E ? (const A*)d->absorb2[c] : nullptr;
     if (shell) {
       P.F[c] = (T*)shell->Fin[c];
       P.Fo[c] = (T*)shell->Fout[c];
@@ -366,7 +368,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
   P.cls_vary = (P.inv[0] != nullptr) ? (IS_E ? FDTD_CLS_VARY_E : FDTD_CLS_VARY_H) : 0;
   if (P.inv[0] != nullptr && P.cls == nullptr) return fail(FDTD_ERR_ARG, "material arrays need a tile_class map");
   P.n_slabs = d->n_slabs;
-  for (int s = 0; s < d->n_slabs; ++s) P.slabs[s] = slab_k<T, IS_E>(d->slabs[s]);
+  for (int s = 0; s < d->n_slabs; ++s) P.slabs[s] = slab_k<T, IS_E, A>(d->slabs[s]);
   if (!shell && post_is_fused(d)) {
     P.dyn = graph_step >= 0 ? (const i64*)d->dyn : nullptr;
     for (int n = 0; n < d->n_sources; ++n) {
@@ -377,15 +379,15 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
       if (graph_step < 0 && (w < 0 || w >= S.wave_len))
         return fail(FDTD_ERR_ARG, "source %d: step %lld outside its waveform table [%lld,%lld)", n, (long long)q,
                     (long long)S.wave_q0, (long long)(S.wave_q0 + S.wave_len));
-      fdtd::SrcK<T>& K = P.src[P.n_src++];
+      fdtd::SrcK<A>& K = P.src[P.n_src++];
       K.kind = S.kind;
       K.comp = S.comp;
       K.n = S.n;
       for (int k = 0; k < 6; ++k) K.bb[k] = S.kind == FDTD_SRC_BOX ? S.box[k] : S.bbox[k];
       K.idx = (const i64*)S.idx;
-      K.profile = (const T*)S.profile;
-      K.amplitude = (T)S.amplitude;
-      K.wave = (const T*)S.wave;
+      K.profile = (const A*)S.profile;
+      K.amplitude = (A)S.amplitude;
+      K.wave = (const A*)S.wave;
       K.w = graph_step >= 0 ? graph_step : w;
     }
     for (int n = 0; n < d->n_detectors; ++n) {
@@ -421,17 +423,17 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
   const bool mat = P.cls != nullptr || has_post;
 #define FDTD_LAUNCH_HALFSTEP(V)                                                                         \
   if (has_post && has_push) {                                                                           \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, true, true>), grid, block, stream, P);        \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, true, true, A>), grid, block, stream, P);     \
   } else if (has_post) {                                                                                \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, false, true>), grid, block, stream, P);       \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, false, true, A>), grid, block, stream, P);    \
   } else if (has_push && mat) {                                                                         \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, true, true>), grid, block, stream, P);       \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, true, true, A>), grid, block, stream, P);    \
   } else if (has_push) {                                                                                \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, true, false>), grid, block, stream, P);      \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, true, false, A>), grid, block, stream, P);   \
   } else if (mat) {                                                                                     \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, false, true>), grid, block, stream, P);      \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, false, true, A>), grid, block, stream, P);   \
   } else {                                                                                              \
-    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, false, false>), grid, block, stream, P);     \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, false, false, false, A>), grid, block, stream, P);  \
   }
   switch (g.vec) {
     case 4:
@@ -458,7 +460,7 @@ int blocks_for(i64 n, int threads = 256) {
 
 // part < 0: everything; 0 / 1: the post ops before / from the x-wrap of an x-sharded periodic grid on (sources
 // and detectors belong to part 1)
-template <typename T, bool IS_E>
+template <typename T, bool IS_E, typename A = T>
 int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int part = -1) {
   if (post_is_fused(d)) return FDTD_OK;  // done inside the half-step kernel
   if (part < 0 && d->x_wrap)
@@ -483,17 +485,17 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int p
     } else {
       const fdtd_slab& S = d->slabs[d->post_arg[n]];
       if (S.psi_count == 0) continue;
-      const T* c[3];
-      T bg[3];
+      const A* c[3];
+      A bg[3];
       for (int k = 0; k < 3; ++k) {
         if (IS_E)
-          c[k] = (const T*)(d->inv_eps_grid[k] ? d->inv_eps_grid[k] : d->inv_eps[k]);
+          c[k] = (const A*)(d->inv_eps_grid[k] ? d->inv_eps_grid[k] : d->inv_eps[k]);
         else
-          c[k] = (const T*)d->inv_mu[k];
-        bg[k] = rounded_product<T>(d->courant, IS_E ? d->bg_inv_eps[k] : d->bg_inv_mu[k]);
+          c[k] = (const A*)d->inv_mu[k];
+        bg[k] = rounded_product<A>(d->courant, IS_E ? d->bg_inv_eps[k] : d->bg_inv_mu[k]);
       }
-      FDTD_LAUNCH((fdtd::pml_add_kernel<T, IS_E>), dim3(blocks_for(S.psi_count)), dim3(256), stream,
-                  slab_k<T, IS_E>(S), F[0], F[1], F[2], c[0], c[1], c[2], bg[0], bg[1], bg[2], (T)d->courant,
+      FDTD_LAUNCH((fdtd::pml_add_kernel<T, IS_E, A>), dim3(blocks_for(S.psi_count)), dim3(256), stream,
+                  slab_k<T, IS_E, A>(S), F[0], F[1], F[2], c[0], c[1], c[2], bg[0], bg[1], bg[2], (A)d->courant,
                   d->Nx, d->Ny, d->Nz, d->plane);
       int rc = check_launch("pml_add");
       if (rc) return rc;
@@ -510,22 +512,22 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int p
                   (long long)S.wave_q0, (long long)(S.wave_q0 + S.wave_len));
     if (S.kind == FDTD_SRC_POINTS) {
       if (S.n == 0) continue;
-      FDTD_LAUNCH((fdtd::source_points_kernel<T>), dim3(blocks_for(S.n)), dim3(256), stream, F[S.comp],
-                  (const i64*)S.idx, (const T*)S.profile, S.n, (const T*)S.wave, (i64)w);
+      FDTD_LAUNCH((fdtd::source_points_kernel<T, A>), dim3(blocks_for(S.n)), dim3(256), stream, F[S.comp],
+                  (const i64*)S.idx, (const A*)S.profile, S.n, (const A*)S.wave, (i64)w);
     } else if (S.kind == FDTD_SRC_FEEDBACK) {
       if (S.n == 0) continue;
       if (S.record && (slot < 0 || slot >= S.record_capacity))
         return fail(FDTD_ERR_ARG, "source %d: record slot %lld outside capacity", n, (long long)slot);
       i64 cell = (i64)S.box[0] * d->plane + (i64)S.box[2] * d->Nz + S.box[4];
-      FDTD_LAUNCH((fdtd::source_feedback_kernel<T>), dim3(1), dim3(32), stream, F[2], cell, (const T*)S.wave,
-                  (const T*)S.profile, (i64)w, (T)S.impedance, (const T*)S.feedback, (int)(q > 0), (T)S.spacing,
+      FDTD_LAUNCH((fdtd::source_feedback_kernel<T, A>), dim3(1), dim3(32), stream, F[2], cell, (const A*)S.wave,
+                  (const A*)S.profile, (i64)w, (A)S.impedance, (const T*)S.feedback, (int)(q > 0), (A)S.spacing,
                   (T*)S.record, (i64)slot);
     } else {
       i64 cells = (i64)(S.box[1] - S.box[0]) * (S.box[3] - S.box[2]) * (S.box[5] - S.box[4]);
       if (cells <= 0) continue;
-      FDTD_LAUNCH((fdtd::source_box_kernel<T>), dim3(blocks_for(cells)), dim3(256), stream, F[S.comp], S.box[0],
-                  S.box[1], S.box[2], S.box[3], S.box[4], S.box[5], d->Nz, d->plane, (T)S.amplitude,
-                  (const T*)S.wave, (i64)w);
+      FDTD_LAUNCH((fdtd::source_box_kernel<T, A>), dim3(blocks_for(cells)), dim3(256), stream, F[S.comp], S.box[0],
+                  S.box[1], S.box[2], S.box[3], S.box[4], S.box[5], d->Nz, d->plane, (A)S.amplitude,
+                  (const A*)S.wave, (i64)w);
     }
     int rc = check_launch("source");
     if (rc) return rc;
@@ -539,9 +541,9 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int p
                   (long long)D.capacity);
     if (D.kind == FDTD_DET_CURRENT) {
       if (IS_E) continue;  // CurrentDetector.detect_E is empty (fdtd/detectors.py:414-415)
-      FDTD_LAUNCH((fdtd::current_kernel<T>), dim3(blocks_for(D.n)), dim3(256), stream, (const T*)d->H[0],
+      FDTD_LAUNCH((fdtd::current_kernel<T, A>), dim3(blocks_for(D.n)), dim3(256), stream, (const T*)d->H[0],
                   (const T*)d->H[1], (const i64*)D.idx, (const int*)D.pos, D.n, d->Nx, d->Ny, d->Nz, d->plane,
-                  (T)D.spacing, (T*)D.ring_H, (T*)D.last, (i64)slot, (int)(d->x_offset > 0));
+                  (A)D.spacing, (T*)D.ring_H, (T*)D.last, (i64)slot, (int)(d->x_offset > 0));
       int rc2 = check_launch("current detector");
       if (rc2) return rc2;
       continue;
@@ -569,7 +571,7 @@ const char* fdtd_last_error(void) { return g_err; }
 int64_t fdtd_launch_count(void) { return g_launches.load(); }
 
 int fdtd_tile_shape(int32_t dtype, int32_t Ny, int32_t Nz, int32_t* tile_y, int32_t* tile_z) {
-  if ((dtype != FDTD_F32 && dtype != FDTD_F64) || Ny < 1 || Nz < 1 || !tile_y || !tile_z)
+  if ((dtype != FDTD_F32 && dtype != FDTD_F64 && dtype != FDTD_F32X) || Ny < 1 || Nz < 1 || !tile_y || !tile_z)
     return fail(FDTD_ERR_ARG, "fdtd_tile_shape: bad argument");
   Geometry g = geometry(dtype, Ny, Nz);
   *tile_y = g.tile_y;
@@ -588,29 +590,25 @@ int fdtd_post_is_fused(const fdtd_desc* d) {
 int fdtd_e_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, int64_t q, int64_t slot, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
-  return d->dtype == FDTD_F32 ? launch_halfstep<float, true>(d, x_begin, x_end, q, slot, stream)
-                              : launch_halfstep<double, true>(d, x_begin, x_end, q, slot, stream);
+  return (d->dtype == FDTD_F32 ? launch_halfstep<float, true, float>(d, x_begin, x_end, q, slot, stream) : d->dtype == FDTD_F64 ? launch_halfstep<double, true, double>(d, x_begin, x_end, q, slot, stream) : launch_halfstep<float, true, double>(d, x_begin, x_end, q, slot, stream));
 }
 
 int fdtd_h_halfstep(const fdtd_desc* d, int32_t x_begin, int32_t x_end, int64_t q, int64_t slot, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
-  return d->dtype == FDTD_F32 ? launch_halfstep<float, false>(d, x_begin, x_end, q, slot, stream)
-                              : launch_halfstep<double, false>(d, x_begin, x_end, q, slot, stream);
+  return (d->dtype == FDTD_F32 ? launch_halfstep<float, false, float>(d, x_begin, x_end, q, slot, stream) : d->dtype == FDTD_F64 ? launch_halfstep<double, false, double>(d, x_begin, x_end, q, slot, stream) : launch_halfstep<float, false, double>(d, x_begin, x_end, q, slot, stream));
 }
 
 int fdtd_post_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
-  return d->dtype == FDTD_F32 ? launch_post<float, true>(d, q, slot, stream)
-                              : launch_post<double, true>(d, q, slot, stream);
+  return (d->dtype == FDTD_F32 ? launch_post<float, true, float>(d, q, slot, stream) : d->dtype == FDTD_F64 ? launch_post<double, true, double>(d, q, slot, stream) : launch_post<float, true, double>(d, q, slot, stream));
 }
 
 int fdtd_post_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
-  return d->dtype == FDTD_F32 ? launch_post<float, false>(d, q, slot, stream)
-                              : launch_post<double, false>(d, q, slot, stream);
+  return (d->dtype == FDTD_F32 ? launch_post<float, false, float>(d, q, slot, stream) : d->dtype == FDTD_F64 ? launch_post<double, false, double>(d, q, slot, stream) : launch_post<float, false, double>(d, q, slot, stream));
 }
 
 int fdtd_post_part(const fdtd_desc* d, int32_t field, int32_t part, int64_t q, int64_t slot, void* stream) {
@@ -618,26 +616,20 @@ int fdtd_post_part(const fdtd_desc* d, int32_t field, int32_t part, int64_t q, i
   if (rc) return rc;
   if ((field != 0 && field != 1) || (part != 0 && part != 1)) return fail(FDTD_ERR_ARG, "fdtd_post_part: field / part");
   if (field == 0)
-    return d->dtype == FDTD_F32 ? launch_post<float, true>(d, q, slot, stream, part)
-                                : launch_post<double, true>(d, q, slot, stream, part);
-  return d->dtype == FDTD_F32 ? launch_post<float, false>(d, q, slot, stream, part)
-                              : launch_post<double, false>(d, q, slot, stream, part);
+    return (d->dtype == FDTD_F32 ? launch_post<float, true, float>(d, q, slot, stream, part) : d->dtype == FDTD_F64 ? launch_post<double, true, double>(d, q, slot, stream, part) : launch_post<float, true, double>(d, q, slot, stream, part));
+  return (d->dtype == FDTD_F32 ? launch_post<float, false, float>(d, q, slot, stream, part) : d->dtype == FDTD_F64 ? launch_post<double, false, double>(d, q, slot, stream, part) : launch_post<float, false, double>(d, q, slot, stream, part));
 }
 
 static int update_E_nocheck(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int64_t graph_step = -1) {
-  int rc = d->dtype == FDTD_F32 ? launch_halfstep<float, true>(d, 0, d->Nx, q, slot, stream, graph_step)
-                                : launch_halfstep<double, true>(d, 0, d->Nx, q, slot, stream, graph_step);
+  int rc = (d->dtype == FDTD_F32 ? launch_halfstep<float, true, float>(d, 0, d->Nx, q, slot, stream, graph_step) : d->dtype == FDTD_F64 ? launch_halfstep<double, true, double>(d, 0, d->Nx, q, slot, stream, graph_step) : launch_halfstep<float, true, double>(d, 0, d->Nx, q, slot, stream, graph_step));
   if (rc) return rc;
-  return d->dtype == FDTD_F32 ? launch_post<float, true>(d, q, slot, stream)
-                              : launch_post<double, true>(d, q, slot, stream);
+  return (d->dtype == FDTD_F32 ? launch_post<float, true, float>(d, q, slot, stream) : d->dtype == FDTD_F64 ? launch_post<double, true, double>(d, q, slot, stream) : launch_post<float, true, double>(d, q, slot, stream));
 }
 
 static int update_H_nocheck(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int64_t graph_step = -1) {
-  int rc = d->dtype == FDTD_F32 ? launch_halfstep<float, false>(d, 0, d->Nx, q, slot, stream, graph_step)
-                                : launch_halfstep<double, false>(d, 0, d->Nx, q, slot, stream, graph_step);
+  int rc = (d->dtype == FDTD_F32 ? launch_halfstep<float, false, float>(d, 0, d->Nx, q, slot, stream, graph_step) : d->dtype == FDTD_F64 ? launch_halfstep<double, false, double>(d, 0, d->Nx, q, slot, stream, graph_step) : launch_halfstep<float, false, double>(d, 0, d->Nx, q, slot, stream, graph_step));
   if (rc) return rc;
-  return d->dtype == FDTD_F32 ? launch_post<float, false>(d, q, slot, stream)
-                              : launch_post<double, false>(d, q, slot, stream);
+  return (d->dtype == FDTD_F32 ? launch_post<float, false, float>(d, q, slot, stream) : d->dtype == FDTD_F64 ? launch_post<double, false, double>(d, q, slot, stream) : launch_post<float, false, double>(d, q, slot, stream));
 }
 
 int fdtd_update_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
@@ -660,12 +652,8 @@ int fdtd_halfstep_push(const fdtd_desc* d, int32_t field, int32_t x_begin, int32
   if (!peer_ghost_y || !peer_ghost_z) return fail(FDTD_ERR_ARG, "null peer ghost pointer");
   if (field != 0 && field != 1) return fail(FDTD_ERR_ARG, "field must be 0 (E) or 1 (H)");
   if (field == 0)
-    return d->dtype == FDTD_F32
-               ? launch_halfstep<float, true>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z)
-               : launch_halfstep<double, true>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z);
-  return d->dtype == FDTD_F32
-             ? launch_halfstep<float, false>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z)
-             : launch_halfstep<double, false>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z);
+    return (d->dtype == FDTD_F32 ? launch_halfstep<float, true, float>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z) : d->dtype == FDTD_F64 ? launch_halfstep<double, true, double>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z) : launch_halfstep<float, true, double>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z));
+  return (d->dtype == FDTD_F32 ? launch_halfstep<float, false, float>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z) : d->dtype == FDTD_F64 ? launch_halfstep<double, false, double>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z) : launch_halfstep<float, false, double>(d, x_begin, x_end, q, slot, stream, -1, peer_ghost_y, peer_ghost_z));
 }
 
 int fdtd_halo_push(const fdtd_desc* d, int32_t field, void* peer_ghost_y, void* peer_ghost_z, void* stream) {
@@ -675,7 +663,7 @@ int fdtd_halo_push(const fdtd_desc* d, int32_t field, void* peer_ghost_y, void* 
   if (field != 0 && field != 1) return fail(FDTD_ERR_ARG, "field must be 0 (E) or 1 (H)");
   const int64_t plane_off = field == 0 ? 0 : (int64_t)(d->Nx - 1) * d->plane;
   void* const* F = field == 0 ? d->E : d->H;
-  if (d->dtype == FDTD_F32) {
+  if (d->dtype != FDTD_F64) {
     FDTD_LAUNCH((fdtd::halo_push_kernel<float>), dim3(blocks_for(d->plane)), dim3(256), stream,
                 (const float*)F[1] + plane_off, (const float*)F[2] + plane_off, (float*)peer_ghost_y,
                 (float*)peer_ghost_z, (i64)d->plane);
@@ -689,12 +677,12 @@ int fdtd_halo_push(const fdtd_desc* d, int32_t field, void* peer_ghost_y, void* 
 
 int fdtd_dft_accumulate(int32_t dtype, const void* ring, int64_t n_steps, int64_t n_values, const double* twiddle,
                         int32_t n_freqs, double* acc, void* stream) {
-  if (dtype != FDTD_F32 && dtype != FDTD_F64) return fail(FDTD_ERR_ARG, "bad dtype %d", dtype);
+  if (dtype != FDTD_F32 && dtype != FDTD_F64 && dtype != FDTD_F32X) return fail(FDTD_ERR_ARG, "bad dtype %d", dtype);
   if (n_steps < 0 || n_values < 0 || n_freqs < 0) return fail(FDTD_ERR_ARG, "fdtd_dft_accumulate: negative size");
   if (n_steps == 0 || n_values == 0 || n_freqs == 0) return FDTD_OK;
   if (!ring || !twiddle || !acc) return fail(FDTD_ERR_ARG, "fdtd_dft_accumulate: null pointer");
   const dim3 grid(blocks_for(n_values * n_freqs)), block(256);
-  if (dtype == FDTD_F32) {
+  if (dtype != FDTD_F64) {
     FDTD_LAUNCH((fdtd::dft_accumulate_kernel<float>), grid, block, stream, (const float*)ring, (i64)n_steps,
                 (i64)n_values, twiddle, (int)n_freqs, acc);
   } else {
@@ -805,7 +793,7 @@ int check_halo(const fdtd_desc* d, const fdtd_halo* h) {
   return FDTD_OK;
 }
 
-template <typename T>
+template <typename T, typename A>
 int sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int field, int64_t q, int64_t slot, void* stream) {
   const int n = d->Nx;
   const bool is_e = field == 0;
@@ -820,7 +808,8 @@ int sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int field, int64_t q, int
   int64_t* peer_flag = is_e ? h->left_flag : h->right_flag;
   int rc = stream_after(side, main, g_join.to_side);      // everything enqueued so far (user writes included)
   if (rc) return rc;
-  rc = is_e ? launch_halfstep<T, true>(d, b0, b1, q, slot, main) : launch_halfstep<T, false>(d, b0, b1, q, slot, main);
+  rc = is_e ? launch_halfstep<T, true, A>(d, b0, b1, q, slot, main)
+            : launch_halfstep<T, false, A>(d, b0, b1, q, slot, main);
   if (rc) return rc;
   if (has_nb) {
     // the ghost this plane needs was pushed by the neighbour after its last half-step of the OTHER field
@@ -830,8 +819,8 @@ int sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int field, int64_t q, int
     if (rc) return rc;
   }
   const bool fused = has_nb && h->push_fused[field];
-  rc = is_e ? launch_halfstep<T, true>(d, e0, e1, q, slot, side, -1, fused ? gy : nullptr, fused ? gz : nullptr)
-            : launch_halfstep<T, false>(d, e0, e1, q, slot, side, -1, fused ? gy : nullptr, fused ? gz : nullptr);
+  rc = is_e ? launch_halfstep<T, true, A>(d, e0, e1, q, slot, side, -1, fused ? gy : nullptr, fused ? gz : nullptr)
+            : launch_halfstep<T, false, A>(d, e0, e1, q, slot, side, -1, fused ? gy : nullptr, fused ? gz : nullptr);
   if (rc) return rc;
   if (fused) {
     FDTD_LAUNCH((fdtd::halo_signal_kernel), dim3(1), dim3(32), side, (i64*)peer_flag, (i64)(h->count[field] + 1));
@@ -840,7 +829,7 @@ int sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int field, int64_t q, int
   }
   rc = stream_after(main, side, g_join.to_main);
   if (rc) return rc;
-  rc = is_e ? launch_post<T, true>(d, q, slot, main) : launch_post<T, false>(d, q, slot, main);
+  rc = is_e ? launch_post<T, true, A>(d, q, slot, main) : launch_post<T, false, A>(d, q, slot, main);
   if (rc) return rc;
   if (has_nb && !fused) {
     rc = stream_after(side, main, g_join.to_side);
@@ -868,8 +857,7 @@ int fdtd_sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int32_t field, int64
   if (field != 0 && field != 1) return fail(FDTD_ERR_ARG, "field must be 0 (E) or 1 (H)");
   if (d->x_wrap) return fail(FDTD_ERR_UNSUPPORTED, "periodic x boundary across slabs: drive the parts yourself");
   if ((rc = g_join.ensure()) != 0) return rc;
-  return d->dtype == FDTD_F32 ? sharded_halfstep<float>(d, h, field, q, slot, stream)
-                              : sharded_halfstep<double>(d, h, field, q, slot, stream);
+  return (d->dtype == FDTD_F32 ? sharded_halfstep<float, float>(d, h, field, q, slot, stream) : d->dtype == FDTD_F64 ? sharded_halfstep<double, double>(d, h, field, q, slot, stream) : sharded_halfstep<float, double>(d, h, field, q, slot, stream));
 }
 
 int fdtd_run_sharded(const fdtd_desc* d, fdtd_halo* h, int64_t q0, int64_t nsteps, int64_t slot0, void* stream) {
@@ -881,8 +869,7 @@ int fdtd_run_sharded(const fdtd_desc* d, fdtd_halo* h, int64_t q0, int64_t nstep
   if ((rc = g_join.ensure()) != 0) return rc;
   for (int64_t s = 0; s < nsteps; ++s) {
     for (int field = 0; field < 2; ++field) {
-      rc = d->dtype == FDTD_F32 ? sharded_halfstep<float>(d, h, field, q0 + s, slot0 + s, stream)
-                                : sharded_halfstep<double>(d, h, field, q0 + s, slot0 + s, stream);
+      rc = (d->dtype == FDTD_F32 ? sharded_halfstep<float, float>(d, h, field, q0 + s, slot0 + s, stream) : d->dtype == FDTD_F64 ? sharded_halfstep<double, double>(d, h, field, q0 + s, slot0 + s, stream) : sharded_halfstep<float, double>(d, h, field, q0 + s, slot0 + s, stream));
       if (rc) return rc;
     }
   }
@@ -957,7 +944,7 @@ bool interior_box(const fdtd_desc* d, int vec, InteriorBox* b) {
 }
 
 bool fuse_eh_eligible(const fdtd_desc* d, InteriorBox* box) {
-  if (!d->fuse_eh) return false;
+  if (!d->fuse_eh || d->dtype == FDTD_F32X) return false;
   for (int c = 0; c < 3; ++c)
     if (!d->E2[c] || !d->H2[c] || d->inv_eps[c] || d->inv_mu[c] || d->absorb[c]) return false;
   if (d->Nx != d->Nx_global || d->n_post != 0) return false;

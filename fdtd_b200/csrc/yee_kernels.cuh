@@ -121,25 +121,28 @@ FDTD_DEV void prefetch_l2(const void* p) {
 #endif
 }
 
-template <typename T>
+// T = storage type of the state (fields, psi, detector rings); A = arithmetic type, which is also the type of
+// every coefficient (tables, material arrays, source profiles and waveforms).  A = T except in the float32x
+// mode (FDTD_F32X): float storage, double arithmetic, one rounding at each store.
+template <typename T, typename A = T>
 struct SlabK {
   int axis, lo, t, fused, x0, x1;
   int lo_al, tp;  // z slabs: psi rows are [tp] long and start at z = lo_al (both multiples of 4) -> vector access
   i64 count;
   T* psi;      // psi_E in the E half-step, psi_H in the H half-step
-  const T* b;  // bE / bH
-  const T* c;  // cE / cH
+  const A* b;  // bE / bH
+  const A* c;  // cE / cH
 };
 
 // a source folded into the half-step kernel: points (soft, +=) or box (hard, =)
-template <typename T>
+template <typename A>
 struct SrcK {
   int kind, comp, n;
   int bb[6];          // local bounding box x0,x1,y0,y1,z0,z1 (half-open); the box itself for FDTD_SRC_BOX
   const i64* idx;     // ascending local linear cell indices
-  const T* profile;
-  T amplitude;
-  const T* wave;
+  const A* profile;
+  A amplitude;
+  const A* wave;
   i64 w;              // waveform table index (+ dyn[0])
 };
 
@@ -154,7 +157,7 @@ struct DetK {
   i64 slot;           // (+ dyn[1])
 };
 
-template <typename T>
+template <typename T, typename A = T>
 struct HalfStepParams {
   int Nx, Ny, Nz, x_offset, Nx_global;
   int x_begin, x_end, x_chunk;
@@ -164,18 +167,18 @@ struct HalfStepParams {
   T* F[3];        // field being updated (read)
   T* Fo[3];       // where the updated field is written: F itself, or the other buffer of a ping-pong pair
   const T* G[3];  // field being differentiated
-  T sc;
-  T bg_c[3];      // sc * background inverse material, rounded as the reference rounds it
-  T bg_inv[3];    // background inverse material itself (AnisotropicObject cells round sc*(inv*curl))
-  const T* inv[3];       // effective inverse material of the curl term, or null
-  const T* inv2[3];      // second object covering a cell (overlaps), or null
-  const T* inv_grid[3];  // grid's own eps^-1 for the PML correction, or null (= inv)
-  const T* absorb[3];    // absorption factor, or null
-  const T* absorb2[3];   // absorption factor of the second object covering a cell, or null
+  A sc;
+  A bg_c[3];      // sc * background inverse material, rounded as the reference rounds it
+  A bg_inv[3];    // background inverse material itself (AnisotropicObject cells round sc*(inv*curl))
+  const A* inv[3];       // effective inverse material of the curl term, or null
+  const A* inv2[3];      // second object covering a cell (overlaps), or null
+  const A* inv_grid[3];  // grid's own eps^-1 for the PML correction, or null (= inv)
+  const A* absorb[3];    // absorption factor, or null
+  const A* absorb2[3];   // absorption factor of the second object covering a cell, or null
   const unsigned char* cls;
   unsigned char cls_vary;  // FDTD_CLS_VARY_E or FDTD_CLS_VARY_H
   int n_slabs;
-  SlabK<T> slabs[6];
+  SlabK<T, A> slabs[6];
   // sources and detectors folded into this pass (only when nothing has to run between the field
   // update and them, i.e. no periodic copy / late PML correction); registration order
   // boundary plane pushed straight into the neighbour slab's ghost plane over NVLink (peer pointers
@@ -185,17 +188,32 @@ struct HalfStepParams {
   T* push_z;
   int n_src, n_det;
   const i64* dyn;  // optional device int64[2] {waveform index base, ring slot base} (CUDA-graph replays)
-  SrcK<T> src[FDTD_FUSED_MAX];
+  SrcK<A> src[FDTD_FUSED_MAX];
   DetK<T> det[FDTD_FUSED_MAX];
 };
+
+// load VEC stored values and widen them to the arithmetic type / narrow and store (the one rounding per store)
+template <typename T, typename A, int VEC>
+FDTD_DEV void ld_wide(const T* p, A (&out)[VEC]) {
+  const Pack<T, VEC> v = ldv<T, VEC>(p);
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) out[e] = (A)v.v[e];
+}
+template <typename T, typename A, int VEC>
+FDTD_DEV void st_narrow(T* p, const A (&in)[VEC]) {
+  Pack<T, VEC> v;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) v.v[e] = (T)in[e];
+  stv<T, VEC>(p, v);
+}
 
 // CPML update of one slab for the VEC cells of a thread.  A = slab axis; (A, U, W) cyclic.
 // d0 = one-sided difference of G_W along A (drives psi[0], corrects F_U with sign -),
 // d1 = one-sided difference of G_U along A (drives psi[1], corrects F_W with sign +).
-template <typename T, int VEC, bool IS_E>
-FDTD_DEV void slab_cells(const SlabK<T>& S, i64 idx0, int l0, int lstep, const T (&d0)[VEC],
-                         const T (&d1)[VEC], T (&fu)[VEC], T (&fw)[VEC], const T (&cu)[VEC],
-                         const T (&cw)[VEC]) {
+template <typename T, typename A, int VEC, bool IS_E>
+FDTD_DEV void slab_cells(const SlabK<T, A>& S, i64 idx0, int l0, int lstep, const A (&d0)[VEC],
+                         const A (&d1)[VEC], A (&fu)[VEC], A (&fw)[VEC], const A (&cu)[VEC],
+                         const A (&cw)[VEC]) {
   // x / y slabs: the VEC cells share l (lstep = 0).  z slabs: l = l0 + e; psi rows are padded so that
   // idx0 is vector-aligned, cells outside [0, t) are padding (stay zero).  Always 128-bit psi access.
   Pack<T, VEC> a = ldv<T, VEC>(S.psi + idx0);
@@ -204,22 +222,23 @@ FDTD_DEV void slab_cells(const SlabK<T>& S, i64 idx0, int l0, int lstep, const T
   for (int e = 0; e < VEC; ++e) {
     const int l = l0 + e * lstep;
     if (l >= 0 && l < S.t) {
-      const T bb = S.b[l];
-      const T cc = S.c[l];
+      const A bb = S.b[l];
+      const A cc = S.c[l];
       // psi *= b; psi[inner] += diff * c[inner]      fdtd/boundaries.py:439-454, 467-482
       const bool inner = IS_E ? (l >= 1) : (l < S.t - 1);
-      T p0 = a.v[e] * bb;
-      T p1 = b.v[e] * bb;
+      A p0 = (A)a.v[e] * bb;
+      A p1 = (A)b.v[e] * bb;
       if (inner) {
         p0 = p0 + d0[e] * cc;
         p1 = p1 + d1[e] * cc;
       }
-      a.v[e] = p0;
-      b.v[e] = p1;
+      a.v[e] = (T)p0;
+      b.v[e] = (T)p1;
       if (S.fused) {
         // phi_U = 0 - psi0, phi_W = psi1 - 0; F[loc] +-= sc*inv*phi   fdtd/boundaries.py:409-431, 456-459
-        const T phi_u = T(0) - p0;
-        const T phi_w = p1 - T(0);
+        // (float32x: the correction uses the psi just computed, before it is rounded for storage)
+        const A phi_u = A(0) - p0;
+        const A phi_w = p1 - A(0);
         if (IS_E) {
           fu[e] = fu[e] + cu[e] * phi_u;
           fw[e] = fw[e] + cw[e] * phi_w;
@@ -245,22 +264,23 @@ FDTD_DEV int lower_bound_i64(const i64* a, int n, i64 key) {
 
 // sources (registration order) then detectors on the final values of a thread's cells
 // (fdtd/grid.py:294-299, 320-325; fdtd/sources.py:93-109, 278-297, 476-486; fdtd/detectors.py:114-124)
-template <typename T, int VEC>
+template <typename A, int VEC>
 struct CellFields {
-  T fx[VEC], fy[VEC], fz[VEC];
+  A fx[VEC], fy[VEC], fz[VEC];
 };
 
-template <typename T, int VEC>
-FDTD_RARE_FN void fused_post(const HalfStepParams<T>& P, int i, int j, int k0, i64 lin0, CellFields<T, VEC>& V) {
-  T (&fx)[VEC] = V.fx;
-  T (&fy)[VEC] = V.fy;
-  T (&fz)[VEC] = V.fz;
+template <typename T, typename A, int VEC>
+FDTD_RARE_FN void fused_post(const HalfStepParams<T, A>& P, int i, int j, int k0, i64 lin0, CellFields<A, VEC>& V) {
+  A (&fx)[VEC] = V.fx;
+  A (&fy)[VEC] = V.fy;
+  A (&fz)[VEC] = V.fz;
   for (int s = 0; s < P.n_src; ++s) {
-    const SrcK<T>& S = P.src[s];
+    const SrcK<A>& S = P.src[s];
     if (i < S.bb[0] || i >= S.bb[1] || j < S.bb[2] || j >= S.bb[3] || k0 + VEC <= S.bb[4] || k0 >= S.bb[5]) continue;
-    const T wv = S.wave[S.w + (P.dyn ? P.dyn[0] : 0)];
+    const A wv = S.wave[S.w + (P.dyn ? P.dyn[0] : 0)];
     if (S.kind == FDTD_SRC_BOX) {
-      const T v = S.amplitude * wv;
+      // (a hard source writes a STORED value: rounded to the storage type like the field it replaces)
+      const A v = (A)(T)(S.amplitude * wv);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         if (k0 + e >= S.bb[4] && k0 + e < S.bb[5]) {
@@ -270,7 +290,7 @@ FDTD_RARE_FN void fused_post(const HalfStepParams<T>& P, int i, int j, int k0, i
     } else {
       for (int n = lower_bound_i64(S.idx, S.n, lin0); n < S.n && S.idx[n] < lin0 + VEC; ++n) {
         const int de = (int)(S.idx[n] - lin0);
-        const T v = S.profile[n] * wv;
+        const A v = S.profile[n] * wv;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           if (e == de) {
@@ -300,11 +320,11 @@ FDTD_RARE_FN void fused_post(const HalfStepParams<T>& P, int i, int j, int k0, i
 }
 
 // what the CPML pass needs about the VEC cells of a thread
-template <typename T, int VEC>
+template <typename A, int VEC>
 struct CellState {
-  T d_zy[VEC], d_yz[VEC], d_xz[VEC], d_zx[VEC], d_yx[VEC], d_xy[VEC];
-  T fx[VEC], fy[VEC], fz[VEC];
-  T cx[VEC], cy[VEC], cz[VEC];
+  A d_zy[VEC], d_yz[VEC], d_xz[VEC], d_zx[VEC], d_yx[VEC], d_xy[VEC];
+  A fx[VEC], fy[VEC], fz[VEC];
+  A cx[VEC], cy[VEC], cz[VEC];
 };
 
 // E update of the cells of a tile that an AbsorbingObject, an AnisotropicObject or overlapping objects touch
@@ -318,9 +338,9 @@ struct CellState {
 //                                                   marked by a NEGATIVE zero in the grid's eps^-1: x-component
 //                                                   for layer 1, y-component for layer 2
 //   absorbing    E *= (1-f)/(1+f); E += (sc*eps^-1)*curl / (1+f)      (f = 0 gives the plain update bit for bit)
-template <typename T, int VEC>
-FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC>& C, i64 off, unsigned cls) {
-  T tx[VEC], ty[VEC], tz[VEC], ux[VEC], uy[VEC], uz[VEC];
+template <typename T, typename A, int VEC>
+FDTD_SPECIAL_FN void special_update(const HalfStepParams<T, A>& P, CellState<A, VEC>& C, i64 off, unsigned cls) {
+  A tx[VEC], ty[VEC], tz[VEC], ux[VEC], uy[VEC], uz[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
     ux[e] = C.d_zy[e] - C.d_yz[e];
@@ -331,10 +351,10 @@ FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC
     tz[e] = C.cz[e] * uz[e];
   }
   if (cls & FDTD_CLS_ANISO) {
-    const Pack<T, VEC> mark = ldv<T, VEC>(P.inv_grid[0] + off);
+    const Pack<A, VEC> mark = ldv<A, VEC>(P.inv_grid[0] + off);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      if ((mark.v[e] == T(0)) && fdtd_signbit(mark.v[e])) {
+      if ((mark.v[e] == A(0)) && fdtd_signbit(mark.v[e])) {
         const bool vary = (cls & P.cls_vary) != 0;
         tx[e] = P.sc * ((vary ? P.inv[0][off + e] : P.bg_inv[0]) * ux[e]);
         ty[e] = P.sc * ((vary ? P.inv[1][off + e] : P.bg_inv[1]) * uy[e]);
@@ -346,13 +366,13 @@ FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC
   if (cls & FDTD_CLS_ABSORB) {
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      const T q0 = P.absorb[0][off + e], q1 = P.absorb[1][off + e], q2 = P.absorb[2][off + e];
-      C.fx[e] = C.fx[e] * ((T(1) - q0) / (T(1) + q0));
-      C.fy[e] = C.fy[e] * ((T(1) - q1) / (T(1) + q1));
-      C.fz[e] = C.fz[e] * ((T(1) - q2) / (T(1) + q2));
-      C.fx[e] = C.fx[e] + tx[e] / (T(1) + q0);
-      C.fy[e] = C.fy[e] + ty[e] / (T(1) + q1);
-      C.fz[e] = C.fz[e] + tz[e] / (T(1) + q2);
+      const A q0 = P.absorb[0][off + e], q1 = P.absorb[1][off + e], q2 = P.absorb[2][off + e];
+      C.fx[e] = C.fx[e] * ((A(1) - q0) / (A(1) + q0));
+      C.fy[e] = C.fy[e] * ((A(1) - q1) / (A(1) + q1));
+      C.fz[e] = C.fz[e] * ((A(1) - q2) / (A(1) + q2));
+      C.fx[e] = C.fx[e] + tx[e] / (A(1) + q0);
+      C.fy[e] = C.fy[e] + ty[e] / (A(1) + q1);
+      C.fz[e] = C.fz[e] + tz[e] / (A(1) + q2);
     }
   } else {
 #pragma unroll
@@ -368,13 +388,13 @@ FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC
 #pragma unroll
     for (int e = 0; e < VEC; ++e) aniso2[e] = false;
     if (cls & FDTD_CLS_ANISO) {
-      const Pack<T, VEC> mark2 = ldv<T, VEC>(P.inv_grid[1] + off);
+      const Pack<A, VEC> mark2 = ldv<A, VEC>(P.inv_grid[1] + off);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) aniso2[e] = (mark2.v[e] == T(0)) && fdtd_signbit(mark2.v[e]);
+      for (int e = 0; e < VEC; ++e) aniso2[e] = (mark2.v[e] == A(0)) && fdtd_signbit(mark2.v[e]);
     }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      const T b0 = P.inv2[0][off + e], b1 = P.inv2[1][off + e], b2 = P.inv2[2][off + e];
+      const A b0 = P.inv2[0][off + e], b1 = P.inv2[1][off + e], b2 = P.inv2[2][off + e];
       tx[e] = aniso2[e] ? P.sc * (b0 * ux[e]) : (P.sc * b0) * ux[e];
       ty[e] = aniso2[e] ? P.sc * (b1 * uy[e]) : (P.sc * b1) * uy[e];
       tz[e] = aniso2[e] ? P.sc * (b2 * uz[e]) : (P.sc * b2) * uz[e];
@@ -382,13 +402,13 @@ FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC
     if (cls & FDTD_CLS_ABSORB2) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        const T q0 = P.absorb2[0][off + e], q1 = P.absorb2[1][off + e], q2 = P.absorb2[2][off + e];
-        C.fx[e] = C.fx[e] * ((T(1) - q0) / (T(1) + q0));
-        C.fy[e] = C.fy[e] * ((T(1) - q1) / (T(1) + q1));
-        C.fz[e] = C.fz[e] * ((T(1) - q2) / (T(1) + q2));
-        C.fx[e] = C.fx[e] + tx[e] / (T(1) + q0);
-        C.fy[e] = C.fy[e] + ty[e] / (T(1) + q1);
-        C.fz[e] = C.fz[e] + tz[e] / (T(1) + q2);
+        const A q0 = P.absorb2[0][off + e], q1 = P.absorb2[1][off + e], q2 = P.absorb2[2][off + e];
+        C.fx[e] = C.fx[e] * ((A(1) - q0) / (A(1) + q0));
+        C.fy[e] = C.fy[e] * ((A(1) - q1) / (A(1) + q1));
+        C.fz[e] = C.fz[e] * ((A(1) - q2) / (A(1) + q2));
+        C.fx[e] = C.fx[e] + tx[e] / (A(1) + q0);
+        C.fy[e] = C.fy[e] + ty[e] / (A(1) + q1);
+        C.fz[e] = C.fz[e] + tz[e] / (A(1) + q2);
       }
     } else {
 #pragma unroll
@@ -402,15 +422,15 @@ FDTD_SPECIAL_FN void special_update(const HalfStepParams<T>& P, CellState<T, VEC
 }
 
 // all CPML slabs a thread's cells belong to, in registration order
-template <typename T, int VEC, bool IS_E>
-FDTD_SLAB_FN void slab_pass(const HalfStepParams<T>& P, CellState<T, VEC>& C, int i, int j, int k0, i64 p,
+template <typename T, typename A, int VEC, bool IS_E>
+FDTD_SLAB_FN void slab_pass(const HalfStepParams<T, A>& P, CellState<A, VEC>& C, int i, int j, int k0, i64 p,
                             i64 off, unsigned cls) {
   const int ig = i + P.x_offset;
   if (IS_E && (cls & FDTD_CLS_OBJECT) && P.inv_grid[0] != nullptr) {
     // the correction uses the GRID's eps^-1, which is zero inside objects (fdtd/objects.py:92)
-    Pack<T, VEC> a0 = ldv<T, VEC>(P.inv_grid[0] + off);
-    Pack<T, VEC> a1 = ldv<T, VEC>(P.inv_grid[1] + off);
-    Pack<T, VEC> a2 = ldv<T, VEC>(P.inv_grid[2] + off);
+    Pack<A, VEC> a0 = ldv<A, VEC>(P.inv_grid[0] + off);
+    Pack<A, VEC> a1 = ldv<A, VEC>(P.inv_grid[1] + off);
+    Pack<A, VEC> a2 = ldv<A, VEC>(P.inv_grid[2] + off);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       C.cx[e] = P.sc * a0.v[e];
@@ -419,20 +439,20 @@ FDTD_SLAB_FN void slab_pass(const HalfStepParams<T>& P, CellState<T, VEC>& C, in
     }
   }
   for (int s = 0; s < P.n_slabs; ++s) {
-    const SlabK<T>& S = P.slabs[s];
+    const SlabK<T, A>& S = P.slabs[s];
     if (S.axis == 0) {
       if (i >= S.x0 && i < S.x1)
-        slab_cells<T, VEC, IS_E>(S, (i64)(i - S.x0) * P.plane + p, ig - S.lo, 0, C.d_zx, C.d_yx, C.fy, C.fz,
+        slab_cells<T, A, VEC, IS_E>(S, (i64)(i - S.x0) * P.plane + p, ig - S.lo, 0, C.d_zx, C.d_yx, C.fy, C.fz,
                                  C.cy, C.cz);
     } else if (S.axis == 1) {
       const int l = j - S.lo;
       if (l >= 0 && l < S.t)
-        slab_cells<T, VEC, IS_E>(S, ((i64)i * S.t + l) * P.Nz + k0, l, 0, C.d_xy, C.d_zy, C.fz, C.fx, C.cz,
+        slab_cells<T, A, VEC, IS_E>(S, ((i64)i * S.t + l) * P.Nz + k0, l, 0, C.d_xy, C.d_zy, C.fz, C.fx, C.cz,
                                  C.cx);
     } else {
       const int l0 = k0 - S.lo;
       if (l0 + VEC > 0 && l0 < S.t)
-        slab_cells<T, VEC, IS_E>(S, ((i64)i * P.Ny + j) * S.tp + (k0 - S.lo_al), l0, 1, C.d_yz, C.d_xz, C.fx,
+        slab_cells<T, A, VEC, IS_E>(S, ((i64)i * P.Ny + j) * S.tp + (k0 - S.lo_al), l0, 1, C.d_yz, C.d_xz, C.fx,
                                  C.fy, C.cx, C.cy);
     }
   }
@@ -444,8 +464,8 @@ FDTD_SLAB_FN void slab_pass(const HalfStepParams<T>& P, CellState<T, VEC>& C, in
 // (compute + halo transfer in one kernel; fdtd_halo_signal publishes it afterwards)
 // MAT: the grid has material arrays and a tile-class map; without them (homogeneous grids, e.g. the 1024^3
 // benchmark) all coefficient / object / absorber code is compiled out and costs no registers
-template <typename T, int VEC, bool IS_E, bool HAS_POST, bool HAS_PUSH, bool MAT>
-__global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_kernel(const FDTD_GRID_CONSTANT HalfStepParams<T> P) {
+template <typename T, int VEC, bool IS_E, bool HAS_POST, bool HAS_PUSH, bool MAT, typename A = T>
+__global__ void __launch_bounds__(FDTD_BLOCK_THREADS, (sizeof(A) > sizeof(T) ? 2 : FDTD_MIN_BLOCKS)) halfstep_kernel(const FDTD_GRID_CONSTANT HalfStepParams<T, A> P) {
   const int tid = threadIdx.x;
   const int lane = tid & (P.lanes_z - 1);
   const int row = tid >> P.lanes_shift;
@@ -476,7 +496,7 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
   // loop-invariant slab membership in y and z
   bool pml_yz = false;
   for (int s = 0; s < P.n_slabs; ++s) {
-    const SlabK<T>& S = P.slabs[s];
+    const SlabK<T, A>& S = P.slabs[s];
     if (S.axis == 1) pml_yz |= (j >= S.lo) && (j < S.lo + S.t);
     if (S.axis == 2) pml_yz |= (k0 + VEC > S.lo) && (k0 < S.lo + S.t);
   }
@@ -549,41 +569,43 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     const bool mx = IS_E ? (ig >= 1) : (ig < P.Nx_global - 1);
 
     // ---- one-sided differences d_ca = d G_c / d a, each masked independently ------------
-    T d_zy[VEC], d_yz[VEC], d_xz[VEC], d_zx[VEC], d_yx[VEC], d_xy[VEC];
-    T fx[VEC], fy[VEC], fz[VEC];
+    // (float32x: the stored values are widened here, where they are used; the loaded vectors stay narrow)
+    A d_zy[VEC], d_yz[VEC], d_xz[VEC], d_zx[VEC], d_yx[VEC], d_xy[VEC];
+    A fx[VEC], fy[VEC], fz[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      const T znb_x = IS_E ? (e == 0 ? zs_x : gx.v[e > 0 ? e - 1 : 0])
-                           : (e == VEC - 1 ? zs_x : gx.v[e < VEC - 1 ? e + 1 : 0]);
-      const T znb_y = IS_E ? (e == 0 ? zs_y : gy.v[e > 0 ? e - 1 : 0])
-                           : (e == VEC - 1 ? zs_y : gy.v[e < VEC - 1 ? e + 1 : 0]);
+      const A znb_x = (A)(IS_E ? (e == 0 ? zs_x : gx.v[e > 0 ? e - 1 : 0])
+                               : (e == VEC - 1 ? zs_x : gx.v[e < VEC - 1 ? e + 1 : 0]));
+      const A znb_y = (A)(IS_E ? (e == 0 ? zs_y : gy.v[e > 0 ? e - 1 : 0])
+                               : (e == VEC - 1 ? zs_y : gy.v[e < VEC - 1 ? e + 1 : 0]));
+      const A ax = (A)gx.v[e], ay = (A)gy.v[e], az = (A)gz.v[e];
       if (IS_E) {
-        d_zy[e] = my ? gz.v[e] - ynb_z.v[e] : T(0);
-        d_xy[e] = my ? gx.v[e] - ynb_x.v[e] : T(0);
-        d_yz[e] = mz[e] ? gy.v[e] - znb_y : T(0);
-        d_xz[e] = mz[e] ? gx.v[e] - znb_x : T(0);
-        d_zx[e] = mx ? gz.v[e] - xnb_z.v[e] : T(0);
-        d_yx[e] = mx ? gy.v[e] - xnb_y.v[e] : T(0);
+        d_zy[e] = my ? az - (A)ynb_z.v[e] : A(0);
+        d_xy[e] = my ? ax - (A)ynb_x.v[e] : A(0);
+        d_yz[e] = mz[e] ? ay - znb_y : A(0);
+        d_xz[e] = mz[e] ? ax - znb_x : A(0);
+        d_zx[e] = mx ? az - (A)xnb_z.v[e] : A(0);
+        d_yx[e] = mx ? ay - (A)xnb_y.v[e] : A(0);
       } else {
-        d_zy[e] = my ? ynb_z.v[e] - gz.v[e] : T(0);
-        d_xy[e] = my ? ynb_x.v[e] - gx.v[e] : T(0);
-        d_yz[e] = mz[e] ? znb_y - gy.v[e] : T(0);
-        d_xz[e] = mz[e] ? znb_x - gx.v[e] : T(0);
-        d_zx[e] = mx ? xnb_z.v[e] - gz.v[e] : T(0);
-        d_yx[e] = mx ? xnb_y.v[e] - gy.v[e] : T(0);
+        d_zy[e] = my ? (A)ynb_z.v[e] - az : A(0);
+        d_xy[e] = my ? (A)ynb_x.v[e] - ax : A(0);
+        d_yz[e] = mz[e] ? znb_y - ay : A(0);
+        d_xz[e] = mz[e] ? znb_x - ax : A(0);
+        d_zx[e] = mx ? (A)xnb_z.v[e] - az : A(0);
+        d_yx[e] = mx ? (A)xnb_y.v[e] - ay : A(0);
       }
-      fx[e] = f0.v[e];
-      fy[e] = f1.v[e];
-      fz[e] = f2.v[e];
+      fx[e] = (A)f0.v[e];
+      fy[e] = (A)f1.v[e];
+      fz[e] = (A)f2.v[e];
     }
 
     // ---- coefficients --------------------------------------------------------------------
-    T cx[VEC], cy[VEC], cz[VEC];
+    A cx[VEC], cy[VEC], cz[VEC];
     if (cls & P.cls_vary) {
       // material arrays have no ghost planes: [x][y][z] index == off
-      Pack<T, VEC> a0 = ldv<T, VEC>(P.inv[0] + off);
-      Pack<T, VEC> a1 = ldv<T, VEC>(P.inv[1] + off);
-      Pack<T, VEC> a2 = ldv<T, VEC>(P.inv[2] + off);
+      Pack<A, VEC> a0 = ldv<A, VEC>(P.inv[0] + off);
+      Pack<A, VEC> a1 = ldv<A, VEC>(P.inv[1] + off);
+      Pack<A, VEC> a2 = ldv<A, VEC>(P.inv[2] + off);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         cx[e] = P.sc * a0.v[e];
@@ -603,7 +625,7 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     if (IS_E && (cls & (FDTD_CLS_ABSORB | FDTD_CLS_ANISO | FDTD_CLS_OVERLAP | FDTD_CLS_ABSORB2))) {
       // tiles an AbsorbingObject, an AnisotropicObject or two overlapping objects touch: out-of-line, so that
       // their registers and divisions do not burden the streaming path
-      CellState<T, VEC> C;
+      CellState<A, VEC> C;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         C.d_zy[e] = d_zy[e]; C.d_yz[e] = d_yz[e]; C.d_xz[e] = d_xz[e];
@@ -611,7 +633,7 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
         C.fx[e] = fx[e]; C.fy[e] = fy[e]; C.fz[e] = fz[e];
         C.cx[e] = cx[e]; C.cy[e] = cy[e]; C.cz[e] = cz[e];
       }
-      special_update<T, VEC>(P, C, off, cls);
+      special_update<T, A, VEC>(P, C, off, cls);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         fx[e] = C.fx[e]; fy[e] = C.fy[e]; fz[e] = C.fz[e];
@@ -620,9 +642,9 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
       // F +-= (sc * inverse material) * curl      fdtd/grid.py:283, 309; fdtd/objects.py:118-129
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        const T tx = cx[e] * (d_zy[e] - d_yz[e]);
-        const T ty = cy[e] * (d_xz[e] - d_zx[e]);
-        const T tz = cz[e] * (d_yx[e] - d_xy[e]);
+        const A tx = cx[e] * (d_zy[e] - d_yz[e]);
+        const A ty = cy[e] * (d_xz[e] - d_zx[e]);
+        const A tz = cz[e] * (d_yx[e] - d_xy[e]);
         if (IS_E) {
           fx[e] = fx[e] + tx;
           fy[e] = fy[e] + ty;
@@ -638,11 +660,11 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     // ---- CPML slabs (registration order) -----------------------------------------------------
     bool pml_x = false;
     for (int s = 0; s < P.n_slabs; ++s) {
-      const SlabK<T>& S = P.slabs[s];
+      const SlabK<T, A>& S = P.slabs[s];
       if (S.axis == 0) pml_x |= (i >= S.x0) && (i < S.x1);
     }
     if (pml_x || pml_yz) {
-      CellState<T, VEC> C;
+      CellState<A, VEC> C;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         C.d_zy[e] = d_zy[e]; C.d_yz[e] = d_yz[e]; C.d_xz[e] = d_xz[e];
@@ -650,7 +672,7 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
         C.fx[e] = fx[e]; C.fy[e] = fy[e]; C.fz[e] = fz[e];
         C.cx[e] = cx[e]; C.cy[e] = cy[e]; C.cz[e] = cz[e];
       }
-      slab_pass<T, VEC, IS_E>(P, C, i, j, k0, p, off, cls);
+      slab_pass<T, A, VEC, IS_E>(P, C, i, j, k0, p, off, cls);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         fx[e] = C.fx[e]; fy[e] = C.fy[e]; fz[e] = C.fz[e];
@@ -659,12 +681,12 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
 
     // ---- folded sources and detectors (rare: only threads whose row / z-range a source or detector touches)
     if (HAS_POST && post_yz) {
-      CellFields<T, VEC> V;
+      CellFields<A, VEC> V;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         V.fx[e] = fx[e]; V.fy[e] = fy[e]; V.fz[e] = fz[e];
       }
-      fused_post<T, VEC>(P, i, j, k0, off, V);
+      fused_post<T, A, VEC>(P, i, j, k0, off, V);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         fx[e] = V.fx[e]; fy[e] = V.fy[e]; fz[e] = V.fz[e];
@@ -674,9 +696,9 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, FDTD_MIN_BLOCKS) halfstep_
     // ---- stores --------------------------------------------------------------------------------
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      f0.v[e] = fx[e];
-      f1.v[e] = fy[e];
-      f2.v[e] = fz[e];
+      f0.v[e] = (T)fx[e];
+      f1.v[e] = (T)fy[e];
+      f2.v[e] = (T)fz[e];
     }
     stv_stream<T, VEC>(P.Fo[0] + off, f0);
     stv_stream<T, VEC>(P.Fo[1] + off, f1);
@@ -727,9 +749,9 @@ __global__ void periodic_kernel(T* F0, T* F1, T* F2, int axis, int Nx, int Ny, i
 }
 
 // field correction of a PML registered after a periodic boundary (fdtd/boundaries.py:409-431)
-template <typename T, bool IS_E>
-__global__ void pml_add_kernel(SlabK<T> S, T* F0, T* F1, T* F2, const T* c0, const T* c1,
-                               const T* c2, T bg0, T bg1, T bg2, T sc, int Nx, int Ny, int Nz,
+template <typename T, bool IS_E, typename A = T>
+__global__ void pml_add_kernel(SlabK<T, A> S, T* F0, T* F1, T* F2, const A* c0, const A* c1,
+                               const A* c2, A bg0, A bg1, A bg2, A sc, int Nx, int Ny, int Nz,
                                i64 plane) {
   for (i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x; n < S.count;
        n += (i64)gridDim.x * blockDim.x) {
@@ -752,37 +774,39 @@ __global__ void pml_add_kernel(SlabK<T> S, T* F0, T* F1, T* F2, const T* c0, con
     const int u = (S.axis + 1) % 3, w = (S.axis + 2) % 3;
     T* Fu = u == 0 ? F0 : (u == 1 ? F1 : F2);
     T* Fw = w == 0 ? F0 : (w == 1 ? F1 : F2);
-    const T* cu_p = u == 0 ? c0 : (u == 1 ? c1 : c2);
-    const T* cw_p = w == 0 ? c0 : (w == 1 ? c1 : c2);
-    const T cu = cu_p ? sc * cu_p[off] : (u == 0 ? bg0 : (u == 1 ? bg1 : bg2));
-    const T cw = cw_p ? sc * cw_p[off] : (w == 0 ? bg0 : (w == 1 ? bg1 : bg2));
-    const T phi_u = T(0) - S.psi[n];
-    const T phi_w = S.psi[S.count + n] - T(0);
+    const A* cu_p = u == 0 ? c0 : (u == 1 ? c1 : c2);
+    const A* cw_p = w == 0 ? c0 : (w == 1 ? c1 : c2);
+    const A cu = cu_p ? sc * cu_p[off] : (u == 0 ? bg0 : (u == 1 ? bg1 : bg2));
+    const A cw = cw_p ? sc * cw_p[off] : (w == 0 ? bg0 : (w == 1 ? bg1 : bg2));
+    const A phi_u = A(0) - (A)S.psi[n];
+    const A phi_w = (A)S.psi[S.count + n] - A(0);
     if (IS_E) {
-      Fu[off] = Fu[off] + cu * phi_u;
-      Fw[off] = Fw[off] + cw * phi_w;
+      Fu[off] = (T)((A)Fu[off] + cu * phi_u);
+      Fw[off] = (T)((A)Fw[off] + cw * phi_w);
     } else {
-      Fu[off] = Fu[off] - cu * phi_u;
-      Fw[off] = Fw[off] - cw * phi_w;
+      Fu[off] = (T)((A)Fu[off] - cu * phi_u);
+      Fw[off] = (T)((A)Fw[off] - cw * phi_w);
     }
   }
 }
 
 // soft source: F[idx[n]] += profile[n] * wave   (fdtd/sources.py:93-109, 278-297)
-template <typename T>
-__global__ void source_points_kernel(T* F, const i64* idx, const T* profile, int n, const T* wave,
+// (a point list never names a cell twice: the points of a LineSource differ along its longest axis, so the
+// read-modify-write needs no atomic)
+template <typename T, typename A = T>
+__global__ void source_points_kernel(T* F, const i64* idx, const A* profile, int n, const A* wave,
                                      i64 w) {
-  const T s = wave[w];
+  const A s = wave[w];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    fdtd_atomic_add(F + idx[t], profile[t] * s);
+    F[idx[t]] = (T)((A)F[idx[t]] + profile[t] * s);
   }
 }
 
 // hard source: F[box] = amplitude * wave   (fdtd/sources.py:476-486)
-template <typename T>
+template <typename T, typename A = T>
 __global__ void source_box_kernel(T* F, int x0, int x1, int y0, int y1, int z0, int z1, int Nz,
-                                  i64 plane, T amplitude, const T* wave, i64 w) {
-  const T v = amplitude * wave[w];
+                                  i64 plane, A amplitude, const A* wave, i64 w) {
+  const T v = (T)(amplitude * wave[w]);
   const i64 ny = y1 - y0, nz = z1 - z0;
   const i64 total = (i64)(x1 - x0) * ny * nz;
   for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -829,22 +853,22 @@ __global__ void dft_accumulate_kernel(const T* ring, i64 n_steps, i64 n_values, 
 // The second `current_vector_2` is ACCUMULATED onto the first (`+=`, fdtd/detectors.py:456) as in the reference.
 // `ghost`: the slab has a left neighbour, whose last H plane lies in the ghost plane just below local plane 0
 // (x-sharded grids; the caller samples after that plane has arrived) -- no wrap-around along x then.
-template <typename T>
+template <typename T, typename A = T>
 __global__ void current_kernel(const T* Hx, const T* Hy, const i64* idx, const int* pos, int n, int Nx, int Ny,
-                               int Nz, i64 plane, T dx, T* ring, T* last, i64 slot, int ghost) {
+                               int Nz, i64 plane, A dx, T* ring, T* last, i64 slot, int ghost) {
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const i64 lin = idx[t];
     const i64 px = lin / plane, py = (lin % plane) / Nz, pz = lin % Nz;
     const i64 pxm = (px > 0 || ghost) ? px - 1 : Nx - 1;
     const i64 pym = py > 0 ? py - 1 : Ny - 1;
     const i64 pzm = pz > 0 ? pz - 1 : Nz - 1;
-    T cv1 = (Hx[px * plane + pym * Nz + pz] - Hx[px * plane + py * Nz + pz]) * dx;
-    T cv2 = (Hy[px * plane + py * Nz + pz] - Hy[pxm * plane + py * Nz + pz]) * dx;
-    const T c1 = cv1 + cv2;
-    cv1 = (Hx[px * plane + pym * Nz + pzm] - Hx[px * plane + py * Nz + pzm]) * dx;
-    cv2 = cv2 + (Hy[px * plane + py * Nz + pzm] - Hy[pxm * plane + py * Nz + pzm]) * dx;
-    const T c2 = cv1 + cv2;
-    const T I = (c1 + c2) / T(2);
+    A cv1 = ((A)Hx[px * plane + pym * Nz + pz] - (A)Hx[px * plane + py * Nz + pz]) * dx;
+    A cv2 = ((A)Hy[px * plane + py * Nz + pz] - (A)Hy[pxm * plane + py * Nz + pz]) * dx;
+    const A c1 = cv1 + cv2;
+    cv1 = ((A)Hx[px * plane + pym * Nz + pzm] - (A)Hx[px * plane + py * Nz + pzm]) * dx;
+    cv2 = cv2 + ((A)Hy[px * plane + py * Nz + pzm] - (A)Hy[pxm * plane + py * Nz + pzm]) * dx;
+    const A c2 = cv1 + cv2;
+    const T I = (T)((c1 + c2) / A(2));
     ring[slot * n + pos[t]] = I;
     last[pos[t]] = I;
   }
@@ -856,19 +880,19 @@ __global__ void current_kernel(const T* Hx, const T* Hy, const i64* idx, const i
 //                 reference adds when no current enters (Z <= 0, or the very first step) -- there the whole
 //                 expression is host float64 arithmetic
 //   otherwise   vout = vin + Z * I_prev and E += vout / dx, in the grid dtype
-template <typename T>
-__global__ void source_feedback_kernel(T* F, i64 cell, const T* wave, const T* wave_div, i64 w, T impedance,
-                                       const T* last_I, int use_current, T dx, T* record, i64 slot) {
+template <typename T, typename A = T>
+__global__ void source_feedback_kernel(T* F, i64 cell, const A* wave, const A* wave_div, i64 w, A impedance,
+                                       const T* last_I, int use_current, A dx, T* record, i64 slot) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const T vin = wave[w];
-    T vout = vin;
-    if (impedance > T(0) && use_current) {
-      vout = vin + impedance * last_I[0];
-      F[cell] = F[cell] + vout / dx;
+    const A vin = wave[w];
+    A vout = vin;
+    if (impedance > A(0) && use_current) {
+      vout = vin + impedance * (A)last_I[0];
+      F[cell] = (T)((A)F[cell] + vout / dx);
     } else {
-      F[cell] = F[cell] + wave_div[w];
+      F[cell] = (T)((A)F[cell] + wave_div[w]);
     }
-    if (record) record[slot] = vout;
+    if (record) record[slot] = (T)vout;
   }
 }
 

@@ -73,8 +73,8 @@ class _Detector:
             if g._ring_fill["E"] or g._ring_fill["H"]:
                 raise RuntimeError("detector ring resized with samples pending")
             self._capacity = capacity
-            self._ring_E = bd.zeros((capacity, max(1, self._n_local), self._width))
-            self._ring_H = bd.zeros((capacity, max(1, self._n_local), self._width))
+            self._ring_E = bd.zeros((capacity, max(1, self._n_local), self._width), dtype=g._sdtype)
+            self._ring_H = bd.zeros((capacity, max(1, self._n_local), self._width), dtype=g._sdtype)
 
     # ------------------------------------------------------------------ running DFT on the device
     def track_frequencies(self, frequencies, keep_trace=True):
@@ -106,7 +106,7 @@ class _Detector:
         phase = (-2.0 * np.pi) * ((index * g.time_step)[:, None] * self._dft_freqs[None, :])
         tw = torch.as_tensor(np.stack([np.cos(phase), np.sin(phase)], axis=-1), device=ring.device)
         lib = bd.lib
-        rc = lib.fdtd_dft_accumulate(_capi.F32 if ring.dtype is torch.float32 else _capi.F64,
+        rc = lib.fdtd_dft_accumulate(_capi.F32 if ring.dtype is torch.float32 else _capi.F64,   # (storage type)
                                      C.c_void_p(ring.data_ptr()), n, self._n_local * self._width,
                                      C.c_void_p(tw.data_ptr()), self._dft_freqs.size,
                                      C.c_void_p(self._dft_acc[f].data_ptr()), g._engine._stream())
@@ -274,7 +274,7 @@ class CurrentDetector(BlockDetector):
             # a cell on the first plane of a slab reads the left neighbour's H of the same half-step: the engine then
             # samples after the ghost plane has arrived (same verdict on every rank)
             self._needs_ghost = bool(xs & {part.bounds(r)[0] for r in range(1, part.world)})
-        self._last = bd.zeros((max(1, self._n_local),))
+        self._last = bd.zeros((max(1, self._n_local),), dtype=grid._sdtype)
 
     @property
     def I(self):

@@ -51,7 +51,8 @@ class Engine:
         C.memset(C.byref(d), 0, C.sizeof(d))
         self._keep = []
         d.abi_version = _capi.ABI_VERSION
-        d.dtype = _capi.F32 if dt is torch.float32 else _capi.F64
+        d.dtype = (_capi.F32 if dt is torch.float32 else
+                   _capi.F32X if g._sdtype is torch.float32 else _capi.F64)
         d.Nx, d.Ny, d.Nz = part.nx, g.Ny, g.Nz
         d.x_offset, d.Nx_global = part.x0, g.Nx
         d.plane = g.Ny * g.Nz
@@ -209,7 +210,7 @@ class Engine:
         # --- detectors --------------------------------------------------------------------------
         self._det_table = (_capi.Detector * max(1, len(g.detectors)))()
         d.detectors = C.cast(self._det_table, C.POINTER(_capi.Detector))
-        w = 4 if dt is torch.float32 else 8
+        w = 4 if g._sdtype is torch.float32 else 8
         # the capacity must be the SAME on every rank of an x-sharded grid (a ring flush is collective): size it
         # from the largest per-rank share of every detector, which every rank can compute from the partition
         per_step = sum(2 * det._width * w * max(1, det._n_ring) for det in g.detectors)

@@ -84,12 +84,13 @@ class Grid:
             self.courant_number = float(courant_number)
         self.time_step = self.courant_number * self.grid_spacing / const.c
 
-        self._dtype = bd.float
+        self._dtype = bd.float            # arithmetic and coefficients
+        self._sdtype = bd.storage         # the state: E, H, psi, rings ("cuda.float32x": float32 under float64)
         gc.collect()      # grids hold reference cycles (plug-ins point back at them): free dead ones' HBM first
         self._part = Partition(self.Nx, shard, x_plane_cost)
         nx = self._part.nx
-        self._E = bd.zeros((3, nx + 2, self.Ny, self.Nz))
-        self._H = bd.zeros((3, nx + 2, self.Ny, self.Nz))
+        self._E = bd.zeros((3, nx + 2, self.Ny, self.Nz), dtype=self._sdtype)
+        self._H = bd.zeros((3, nx + 2, self.Ny, self.Nz), dtype=self._sdtype)
         self._bg_inv_eps, self._inv_eps = self._material(permittivity, "permittivity")
         self._bg_inv_mu, self._inv_mu = self._material(permeability, "permeability")
 

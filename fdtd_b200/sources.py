@@ -343,7 +343,7 @@ class SoftArbitraryPointSource:
     def _ensure_ring(self, capacity):
         if self._ring_V is None or self._capacity != capacity:
             self._capacity = capacity
-            self._ring_V = bd.zeros((capacity,))
+            self._ring_V = bd.zeros((capacity,), dtype=self.grid._sdtype)
 
     def _drain(self, n):
         if n == 0:

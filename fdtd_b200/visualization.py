@@ -76,7 +76,7 @@ def energy_slice(grid, x=None, y=None, z=None):
             i = index - part.x0
             plane = (E[:, i] ** 2 + H[:, i] ** 2).sum(0)                     # (Ny, Nz)
         else:
-            plane = torch.empty((grid.Ny, grid.Nz), dtype=grid._dtype, device=E.device)
+            plane = torch.empty((grid.Ny, grid.Nz), dtype=grid._sdtype, device=E.device)
         if part.sharded:
             plane = plane.contiguous()
             dist.broadcast(plane, src=owner)

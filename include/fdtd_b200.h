@@ -44,6 +44,12 @@ extern "C" {
 
 #define FDTD_F32 0
 #define FDTD_F64 1
+#define FDTD_F32X 2   /* float storage of the STATE (fields, psi, detector rings), double arithmetic: every value is
+                         widened where it is used and rounded once where it is stored; every COEFFICIENT (material
+                         arrays, CPML tables, source profiles and waveform tables) is double.  The reference's
+                         ".float32" backends compute in float64 (fdtd/backend.py:43-49, 281-284): this mode keeps
+                         the float32 footprint and traffic but stays within 1e-5 of that reference over thousands
+                         of steps, where float32 arithmetic drifts (1.6e-5 at 2000 steps) */
 
 #define FDTD_MAX_SLABS 6
 #define FDTD_MAX_POST 16
@@ -145,7 +151,8 @@ typedef struct fdtd_detector {
 
 typedef struct fdtd_desc {
   int32_t abi_version; /* FDTD_ABI_VERSION */
-  int32_t dtype;       /* FDTD_F32 / FDTD_F64: storage and arithmetic type */
+  int32_t dtype;       /* FDTD_F32 / FDTD_F64: storage and arithmetic type; FDTD_F32X: float state, double arithmetic
+                          and coefficients -- below, "device [n]" arrays of coefficients are double in that mode */
   int32_t Nx, Ny, Nz;  /* LOCAL slab extents */
   int32_t x_offset;    /* global index of local plane 0 */
   int32_t Nx_global;

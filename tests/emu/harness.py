@@ -19,6 +19,8 @@ def use_emu(dtype="float64"):
         _lib = _capi.bind(build_emu.build())
     backend.lib = _lib
     backend.device = torch.device("cpu")
-    backend.float = getattr(torch, dtype)
+    # "float32x": float32 state, float64 arithmetic and coefficients (fdtd_b200/backend.py)
+    backend.float = torch.float64 if dtype == "float32x" else getattr(torch, dtype)
+    backend.storage = torch.float32 if dtype == "float32x" else backend.float
     backend.name = f"emu.{dtype}"
     return fdtd_b200

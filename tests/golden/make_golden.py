@@ -47,7 +47,8 @@ def load_reference():
     return mod
 
 
-F32_SCENES = ("pml3d", "objects3d", "periodic3d", "c4small", "feed50", "overlaps3d", "patch_antenna", "ring3d")
+F32_SCENES = ("pml3d", "objects3d", "periodic3d", "c4small", "feed50", "overlaps3d", "patch_antenna", "ring3d",
+              "overlaps3d_stable")
 SPECTRA_SCENES = ("patch_antenna",)
 
 

@@ -449,3 +449,54 @@ def test_step_counter_follows_the_chunks_of_an_interrupted_run(monkeypatch):
     g.run(100 - g.time_steps_passed, progress_bar=False)
     want = run_oracle(scenes.pml3d, 100, n=(12, 10, 9), t=3)
     compare(scenes.dump(g), want, 1e-12, bitwise=True)
+
+
+# ---- float32x: float32 state, float64 arithmetic and coefficients ------------------------------------------------
+
+@pytest.mark.parametrize("scene", ["pml3d", "objects3d", "periodic3d", "feed50", "overlaps3d_stable", "ring3d",
+                                   "quickstart2d", "patch_antenna"])
+def test_float32x_vs_float64_reference(scene):
+    """north_star's float32 bar is against the reference's own backends, which compute in float64 whatever their
+    name says: rel-L2 <= 1e-5 on final E, H and every detector trace."""
+    gold = dict(np.load(os.path.join(GOLD, f"{scene}_f64.npz")))
+    steps = int(gold.pop("steps"))
+    fd = use_emu("float32x")
+    g = scenes.SCENES[scene][0](fd)
+    assert g._E.dtype == np_torch("float32") and g._dtype == np_torch("float64")
+    g.run(steps, progress_bar=False)
+    got = scenes.dump(g)
+    assert set(got) == set(gold)
+    # feed50 is quasi-static: |H| is 1.7e-4 of |E|, so the float32 STORAGE rounding of E alone (6e-8 relative) shows up
+    # as 3e-4 in H and in the currents derived from it -- in the reference's own true-float32 run just the same
+    # (tests/golden/feed50_f32.npz).  There the bar is that run's own error, which float32x must not exceed.
+    own_f32 = dict(np.load(os.path.join(GOLD, "feed50_f32.npz"))) if scene == "feed50" else None
+    for k in gold:
+        if k.startswith("src"):
+            continue
+        assert got[k].dtype == np.float32 and got[k].shape == gold[k].shape, k
+        err = scenes.rel_l2(got[k].astype(np.float64), gold[k])
+        tol = 1e-5 if own_f32 is None else max(1e-5, scenes.rel_l2(own_f32[k].astype(np.float64), gold[k]))
+        assert err <= tol, f"{scene} {k}: rel-L2 {err:.3e} > {tol:.1e}"
+
+
+def np_torch(name):
+    import torch
+    return getattr(torch, name)
+
+
+def test_float32x_error_growth_stays_flat():
+    """float32 arithmetic drifts from the float64 reference roughly linearly in the step count (the rounded
+    coefficients shift the phase velocity); float32x only accumulates the storage roundings."""
+    def build(fd):
+        return scenes.pml3d(fd, n=(16, 16, 16), t=4)
+    yo.set_backend("numpy", "float64")
+    ref = build(yo)
+    grids = {m: build(use_emu(m)) for m in ("float32", "float32x")}
+    ref.run(600)
+    err = {}
+    for m, g in grids.items():
+        use_emu(m)
+        g.run(600, progress_bar=False)
+        err[m] = max(scenes.rel_l2(g.E.numpy().astype(np.float64), ref.E),
+                     scenes.rel_l2(g.H.numpy().astype(np.float64), ref.H))
+    assert err["float32x"] <= 5e-6 and err["float32x"] < 0.5 * err["float32"], err
