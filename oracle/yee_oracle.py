@@ -48,8 +48,9 @@ ETA0 = MU0 * C0             # fdtd/constants.py:23
 class _Lib:
     """Minimal array interface shared by the numpy and torch flavours."""
 
-    def __init__(self, kind="numpy", dtype="float64"):
+    def __init__(self, kind="numpy", dtype="float64", device=None):
         self.kind = kind
+        self.kw = {}
         if kind == "numpy":
             self.mod = _np
             self.dtype = getattr(_np, dtype)
@@ -57,22 +58,26 @@ class _Lib:
             import torch
             self.mod = torch
             self.dtype = getattr(torch, dtype)
+            # device="cuda": the same slicing code as eager ATen kernels on a GPU, which is how the reference's
+            # `torch.cuda` backends run (fdtd/backend.py:322-355) -- bench.py's `gpu_eager_baseline`, nothing else
+            if device is not None:
+                self.kw = {"device": device}
         else:
             raise ValueError(kind)
 
     def zeros(self, shape):
-        return self.mod.zeros(tuple(shape), dtype=self.dtype)
+        return self.mod.zeros(tuple(shape), dtype=self.dtype, **self.kw)
 
     def ones(self, shape):
-        return self.mod.ones(tuple(shape), dtype=self.dtype)
+        return self.mod.ones(tuple(shape), dtype=self.dtype, **self.kw)
 
     def asarray(self, a):
         if self.kind == "numpy":
             return _np.array(a, dtype=self.dtype)
         import torch
         if torch.is_tensor(a):
-            return a.clone().to(self.dtype)
-        return torch.tensor(_np.asarray(a), dtype=self.dtype)
+            return a.clone().to(dtype=self.dtype, **self.kw)
+        return torch.tensor(_np.asarray(a), dtype=self.dtype, **self.kw)
 
     def is_array(self, a):
         if isinstance(a, _np.ndarray):
@@ -85,7 +90,7 @@ class _Lib:
     def arange(self, a, b, s):
         if self.kind == "numpy":
             return _np.asarray(_np.arange(a, b, s), dtype=self.dtype)
-        return self.mod.arange(a, b, s, dtype=self.dtype)
+        return self.mod.arange(a, b, s, dtype=self.dtype, **self.kw)
 
     def exp(self, a):
         return self.mod.exp(a)
@@ -94,16 +99,16 @@ class _Lib:
         return a.copy() if self.kind == "numpy" else a.clone()
 
     def to_numpy(self, a):
-        return a if isinstance(a, _np.ndarray) else a.numpy()
+        return a if isinstance(a, _np.ndarray) else a.cpu().numpy()
 
 
 lib = _Lib()
 
 
-def set_backend(kind="numpy", dtype="float64"):
+def set_backend(kind="numpy", dtype="float64", device=None):
     """Choose the oracle's array library and precision (before building a grid)."""
     global lib
-    lib = _Lib(kind, dtype)
+    lib = _Lib(kind, dtype, device)
     return lib
 
 
