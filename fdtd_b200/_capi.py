@@ -37,6 +37,13 @@ class Detector(C.Structure):
                 ("spacing", C.c_double)]
 
 
+class DeepObject(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("box", C.c_int32 * 6), ("inv", _vp * 3), ("absorb", _vp * 3), ("mask", _vp)]
+
+
+OBJ_PLAIN, OBJ_ANISO, OBJ_ABSORB = 0, 1, 2
+
+
 class Desc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("dtype", C.c_int32),
                 ("Nx", C.c_int32), ("Ny", C.c_int32), ("Nz", C.c_int32),
@@ -55,7 +62,8 @@ class Desc(C.Structure):
                 ("x_chunk", C.c_int32), ("use_graphs", C.c_int32), ("dyn", _vp),
                 ("fuse_eh", C.c_int32), ("pad2_", C.c_int32), ("E2", _vp * 3), ("H2", _vp * 3),
                 ("fuse_post", C.c_int32), ("pad3_", C.c_int32),
-                ("psi_E2", _vp * MAX_SLABS), ("x_wrap", C.c_int32), ("pad4_", C.c_int32)]
+                ("psi_E2", _vp * MAX_SLABS), ("n_deep", C.c_int32), ("h_wrap_ghost", C.c_int32),
+                ("deep", C.POINTER(DeepObject)), ("x_wrap", C.c_int32), ("pad4_", C.c_int32)]
 
 
 class Halo(C.Structure):

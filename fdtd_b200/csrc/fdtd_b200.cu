@@ -236,6 +236,17 @@ int validate(const fdtd_desc* d) {
     if (D.n > 0 && D.kind == FDTD_DET_CURRENT && (!D.last || D.spacing <= 0))
       return fail(FDTD_ERR_ARG, "detector %d current", n);
   }
+  if (d->n_deep < 0 || (d->n_deep > 0 && !d->deep)) return fail(FDTD_ERR_ARG, "n_deep");
+  for (int n = 0; n < d->n_deep; ++n) {
+    const fdtd_deep_object& O = d->deep[n];
+    if (O.kind < FDTD_OBJ_PLAIN || O.kind > FDTD_OBJ_ABSORB) return fail(FDTD_ERR_ARG, "deep object %d kind", n);
+    if (O.box[0] < 0 || O.box[1] > d->Nx || O.box[2] < 0 || O.box[3] > d->Ny || O.box[4] < 0 || O.box[5] > d->Nz)
+      return fail(FDTD_ERR_ARG, "deep object %d box", n);
+    const bool empty = O.box[0] >= O.box[1] || O.box[2] >= O.box[3] || O.box[4] >= O.box[5];
+    if (!empty && (!O.mask || !O.inv[0] || !O.inv[1] || !O.inv[2] ||
+                   (O.kind == FDTD_OBJ_ABSORB && (!O.absorb[0] || !O.absorb[1] || !O.absorb[2]))))
+      return fail(FDTD_ERR_ARG, "deep object %d null pointer", n);
+  }
   if (d->use_graphs && !d->dyn) return fail(FDTD_ERR_ARG, "use_graphs needs the dyn scratch");
   if (d->x_wrap < 0 || d->x_wrap > d->n_post + 1) return fail(FDTD_ERR_ARG, "x_wrap outside the post op list");
   if (d->x_wrap && d->Nx == d->Nx_global)
@@ -248,7 +259,8 @@ int validate(const fdtd_desc* d) {
 bool post_is_fused(const fdtd_desc* d) {
   // folding pays where a step is launch-bound; on large slabs the separate source / detector kernels
   // cost < 0.1 % of a step while the folded code costs ~1 % of the streaming kernel (profiles/r1_tune6)
-  if (d->fuse_post == 0 || d->x_wrap) return false;
+  // (objects applied by their own kernels after the fused one come BEFORE the sources, fdtd/grid.py:285-295)
+  if (d->fuse_post == 0 || d->x_wrap || d->n_deep > 0) return false;
   if (d->fuse_post < 0 && (int64_t)d->Nx * d->Ny * d->Nz > FDTD_FUSE_MAX_CELLS) return false;
   for (int n = 0; n < d->n_post; ++n) {
     if (d->post_kind[n] == FDTD_POST_PML_ADD) return false;
@@ -470,6 +482,20 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int p
   const int last = part == 0 ? d->x_wrap - 1 : d->n_post;
   T* F[3];
   for (int c = 0; c < 3; ++c) F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
+  // 0. objects beyond the second one on a cell, registration order (fdtd/grid.py:285-287); update_H of every
+  //    object kind is empty (fdtd/objects.py:131-137, 223-229, 271-277)
+  for (int n = 0; IS_E && part != 1 && n < d->n_deep; ++n) {
+    const fdtd_deep_object& O = d->deep[n];
+    const i64 cells = (i64)(O.box[1] - O.box[0]) * (O.box[3] - O.box[2]) * (O.box[5] - O.box[4]);
+    if (O.box[0] >= O.box[1] || O.box[2] >= O.box[3] || O.box[4] >= O.box[5]) continue;
+    FDTD_LAUNCH((fdtd::object_layer_kernel<T, A>), dim3(blocks_for(cells)), dim3(256), stream, F[0], F[1], F[2],
+                (const T*)d->H[0], (const T*)d->H[1], (const T*)d->H[2], (const A*)O.inv[0], (const A*)O.inv[1],
+                (const A*)O.inv[2], (const A*)O.absorb[0], (const A*)O.absorb[1], (const A*)O.absorb[2], O.mask, O.kind,
+                O.box[0], O.box[1], O.box[2], O.box[3], O.box[4], O.box[5], d->Nz, d->plane, d->x_offset,
+                (A)d->courant);
+    int rc = check_launch("object layer");
+    if (rc) return rc;
+  }
   // 1. periodic copies and late PML corrections, registration order (fdtd/grid.py:290-291, 316-317)
   for (int n = first; n < last; ++n) {
     if (d->post_kind[n] == FDTD_POST_PERIODIC) {
@@ -543,7 +569,7 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int p
       if (IS_E) continue;  // CurrentDetector.detect_E is empty (fdtd/detectors.py:414-415)
       FDTD_LAUNCH((fdtd::current_kernel<T, A>), dim3(blocks_for(D.n)), dim3(256), stream, (const T*)d->H[0],
                   (const T*)d->H[1], (const i64*)D.idx, (const int*)D.pos, D.n, d->Nx, d->Ny, d->Nz, d->plane,
-                  (A)D.spacing, (T*)D.ring_H, (T*)D.last, (i64)slot, (int)(d->x_offset > 0));
+                  (A)D.spacing, (T*)D.ring_H, (T*)D.last, (i64)slot, (int)(d->x_offset > 0 || d->h_wrap_ghost));
       int rc2 = check_launch("current detector");
       if (rc2) return rc2;
       continue;

@@ -790,6 +790,54 @@ __global__ void pml_add_kernel(SlabK<T, A> S, T* F0, T* F1, T* F2, const A* c0, 
   }
 }
 
+// An object that is the third or later one covering a cell: its update_E on the cells of its box named by `mask`
+// (fdtd/objects.py:118-129 plain, 254-269 anisotropic, 207-221 absorbing), with curl_H recomputed from H
+// (fdtd/grid.py:54-76: backward differences, each masked on its own face).  H pointers are at local plane 0 of
+// arrays with ghost planes, so plane -1 is readable on slabs with a left neighbour.
+template <typename T, typename A = T>
+__global__ void object_layer_kernel(T* E0, T* E1, T* E2, const T* H0, const T* H1, const T* H2, const A* i0,
+                                    const A* i1, const A* i2, const A* a0, const A* a1, const A* a2,
+                                    const unsigned char* mask, int kind, int x0, int x1, int y0, int y1, int z0, int z1,
+                                    int Nz, i64 plane, int x_offset, A sc) {
+  const i64 ny = y1 - y0, nz = z1 - z0;
+  const i64 total = (i64)(x1 - x0) * ny * nz;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+    if (!mask[t]) continue;
+    const int i = x0 + (int)(t / (ny * nz)), j = y0 + (int)((t / nz) % ny), k = z0 + (int)(t % nz);
+    const i64 o = (i64)i * plane + (i64)j * Nz + k;
+    const bool mx = i + x_offset >= 1, my = j >= 1, mz = k >= 1;
+    const A hx = (A)H0[o], hy = (A)H1[o], hz = (A)H2[o];
+    const A d_zy = my ? hz - (A)H2[o - Nz] : A(0);
+    const A d_xy = my ? hx - (A)H0[o - Nz] : A(0);
+    const A d_yz = mz ? hy - (A)H1[o - 1] : A(0);
+    const A d_xz = mz ? hx - (A)H0[o - 1] : A(0);
+    const A d_zx = mx ? hz - (A)H2[o - plane] : A(0);
+    const A d_yx = mx ? hy - (A)H1[o - plane] : A(0);
+    const A c0 = d_zy - d_yz, c1 = d_xz - d_zx, c2 = d_yx - d_xy;
+    A e0 = (A)E0[o], e1 = (A)E1[o], e2 = (A)E2[o];
+    if (kind == FDTD_OBJ_ANISO) {
+      e0 = e0 + sc * (i0[t] * c0);
+      e1 = e1 + sc * (i1[t] * c1);
+      e2 = e2 + sc * (i2[t] * c2);
+    } else if (kind == FDTD_OBJ_ABSORB) {
+      const A q0 = a0[t], q1 = a1[t], q2 = a2[t];
+      e0 = e0 * ((A(1) - q0) / (A(1) + q0));
+      e1 = e1 * ((A(1) - q1) / (A(1) + q1));
+      e2 = e2 * ((A(1) - q2) / (A(1) + q2));
+      e0 = e0 + ((sc * i0[t]) * c0) / (A(1) + q0);
+      e1 = e1 + ((sc * i1[t]) * c1) / (A(1) + q1);
+      e2 = e2 + ((sc * i2[t]) * c2) / (A(1) + q2);
+    } else {
+      e0 = e0 + (sc * i0[t]) * c0;
+      e1 = e1 + (sc * i1[t]) * c1;
+      e2 = e2 + (sc * i2[t]) * c2;
+    }
+    E0[o] = (T)e0;
+    E1[o] = (T)e1;
+    E2[o] = (T)e2;
+  }
+}
+
 // soft source: F[idx[n]] += profile[n] * wave   (fdtd/sources.py:93-109, 278-297)
 // (a point list never names a cell twice: the points of a LineSource differ along its longest axis, so the
 // read-modify-write needs no atomic)

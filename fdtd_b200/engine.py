@@ -103,13 +103,14 @@ class Engine:
         # --- materials ------------------------------------------------------------------------
         ie_grid, imu = g._inv_eps, g._inv_mu
         ie_eff, absorb, ie2, absorb2 = ie_grid, None, None, None
+        deep = []                    # (object, mask): objects that are the third or later one on some cells
         if g.objects:
             # The reference updates every object in registration order (fdtd/grid.py:285-287), so a cell covered
-            # by two objects gets two updates.  The first object covering a cell becomes coefficient layer 1
-            # (ie_eff / absorb), the second one layer 2 (ie2 / absorb2); a third one is summed into layer 2
-            # (exact only to rounding; refused at registration when an absorber is involved).  Anisotropic
+            # by several objects gets several updates.  The first object covering a cell becomes coefficient layer 1
+            # (ie_eff / absorb), the second one layer 2 (ie2 / absorb2), both applied inside the fused kernel; every
+            # further one is applied on those cells by its own kernel right after it (fdtd_deep_object).  Anisotropic
             # layers are marked by a negative zero in the grid's eps^-1 (x-component: layer 1, y: layer 2).
-            from .objects import AnisotropicObject
+            from .objects import AbsorbingObject, AnisotropicObject
             ie_eff = ie_grid.clone()
             boxes = [(o.x, o.y, o.z) for o in g.objects]
             overlaps = any(all(max(p.start, q.start) < min(p.stop, q.stop) for p, q in zip(boxes[a], boxes[b]))
@@ -135,14 +136,14 @@ class Engine:
                         absorb[loc] = o._absorb_soa
                     continue
                 depth = cover[o._loc]
-                first, second = depth == 0, depth == 1
+                first, second, later = depth == 0, depth == 1, depth >= 2
                 zero = torch.zeros_like(o._inv_eps_soa)
                 ie_eff[loc] += torch.where(first.unsqueeze(0), o._inv_eps_soa, zero)
                 mark(0, o._loc, first, aniso)
-                if not bool(first.all()):
+                if bool(second.any()):
                     if ie2 is None:
                         ie2 = torch.zeros_like(ie_grid)
-                    ie2[loc] += torch.where(first.unsqueeze(0), zero, o._inv_eps_soa)
+                    ie2[loc] += torch.where(second.unsqueeze(0), o._inv_eps_soa, zero)
                     mark(1, o._loc, second, aniso)
                 if o._absorb_soa is not None:
                     if bool(first.any()):
@@ -153,7 +154,24 @@ class Engine:
                         if absorb2 is None:
                             absorb2 = torch.zeros_like(ie_grid)
                         absorb2[loc] = torch.where(second.unsqueeze(0), o._absorb_soa, absorb2[loc])
-                cover[o._loc] += 1
+                if bool(later.any()):
+                    deep.append((o, later.to(torch.uint8).contiguous()))
+                cover[o._loc] = torch.clamp(depth + 1, max=3)
+            self._deep_table = (_capi.DeepObject * max(1, len(deep)))()
+            d.deep = C.cast(self._deep_table, C.POINTER(_capi.DeepObject))
+            for n, (o, mask) in enumerate(deep):
+                e = d.deep[n]
+                e.kind = (_capi.OBJ_ANISO if isinstance(o, AnisotropicObject) else
+                          _capi.OBJ_ABSORB if isinstance(o, AbsorbingObject) else _capi.OBJ_PLAIN)
+                box = (o._loc[0].start, o._loc[0].stop, o.y.start, o.y.stop, o.z.start, o.z.stop)
+                for k in range(6):
+                    e.box[k] = box[k]
+                for c in range(3):
+                    e.inv[c] = o._inv_eps_soa[c].data_ptr()
+                    e.absorb[c] = o._absorb_soa[c].data_ptr() if o._absorb_soa is not None else None
+                e.mask = mask.data_ptr()
+                self._keep.append(mask)
+        d.n_deep = len(deep)
         self._mat_versions = (None if ie_grid is None else ie_grid._version,
                               None if imu is None else imu._version)
         ty, tz = C.c_int32(), C.c_int32()
@@ -290,7 +308,7 @@ class Engine:
         fused = bool(self.lib.fdtd_post_is_fused(C.byref(d)))
         self._push_fused = {}
         for field, plane in (("E", 0), ("H", n - 1)):
-            ok = fused or d.n_post == 0
+            ok = fused or (d.n_post == 0 and not (field == "E" and d.n_deep))
             if ok and not fused:
                 for k in range(d.n_sources):
                     s = d.sources[k]

@@ -6,7 +6,8 @@ plane (:79-90), zeroing the grid's eps^-1 inside the region (:92), the absorptio
 (:198-205).  The per-step `update_E` of every object (:118-129, :207-221, :254-269) is not a
 Python call here: the engine folds all objects into per-cell coefficient arrays that the fused
 E half-step kernel streams only in the tiles an object touches (hundreds of objects, as in the
-reference's lens examples, cost nothing per step).
+reference's lens examples, cost nothing per step).  Objects may overlap to any depth: the first two
+covering a cell are the kernel's two coefficient layers, further ones run as small kernels of their own.
 """
 import torch
 import torch.distributed as dist
@@ -32,7 +33,6 @@ class Object:
         self.Nx = abs(self.x.stop - self.x.start)
         self.Ny = abs(self.y.stop - self.y.start)
         self.Nz = abs(self.z.stop - self.z.start)
-        self._check_overlap(grid)                # before the grid learns about this object
         self.grid = grid
         self.grid.objects.append(self)
         grid._register_name(self)
@@ -77,20 +77,6 @@ class Object:
         buf = gi[0, -1, self.y, self.z].clone().contiguous()
         dist.broadcast(buf, src=part.world - 1)
         return buf
-
-    def _check_overlap(self, grid):
-        """Each object covering a cell adds its own update, in registration order (fdtd/grid.py:285-287).  Two
-        objects on one cell are reproduced exactly, whatever their kinds; three plain / anisotropic ones to
-        rounding; three with an AbsorbingObject among them are order-dependent beyond that and refused."""
-        def meet(*objs):
-            return all(max(s.start for s in ax) < min(s.stop for s in ax)
-                       for ax in zip(*((o.x, o.y, o.z) for o in objs)))
-
-        earlier = list(grid.objects)
-        for n, a in enumerate(earlier):
-            for b in earlier[n + 1:]:
-                if meet(self, a, b) and any(isinstance(o, AbsorbingObject) for o in (self, a, b)):
-                    raise NotImplementedError("three objects, one of them an AbsorbingObject, on the same cells")
 
     def _handle_slice(self, s, max_index: int = None) -> slice:
         if isinstance(s, list):

@@ -149,6 +149,22 @@ typedef struct fdtd_detector {
   double spacing;      /* FDTD_DET_CURRENT: grid spacing */
 } fdtd_detector;
 
+/* An object that is the THIRD (or later) one covering some cells.  The reference updates every object in registration
+ * order (fdtd/grid.py:285-287), whatever the depth; the fused kernel applies the first two objects covering a cell
+ * (coefficient layers 1 and 2), every further one is applied by its own small kernel over its box, in registration
+ * order, right after the fused kernel -- exactly its update_E on the cells named by `mask`
+ * (fdtd/objects.py:118-129, 207-221, 254-269). */
+#define FDTD_OBJ_PLAIN 0
+#define FDTD_OBJ_ANISO 1
+#define FDTD_OBJ_ABSORB 2
+typedef struct fdtd_deep_object {
+  int32_t kind;           /* FDTD_OBJ_* */
+  int32_t box[6];         /* local x0,x1,y0,y1,z0,z1 (half-open) */
+  const void* inv[3];     /* device [x1-x0][y1-y0][z1-z0] per component: the object's eps^-1 over its box (coefficient type) */
+  const void* absorb[3];  /* FDTD_OBJ_ABSORB: absorption factor over the box */
+  const uint8_t* mask;    /* device [x1-x0][y1-y0][z1-z0]: 1 where two earlier objects already cover the cell */
+} fdtd_deep_object;
+
 typedef struct fdtd_desc {
   int32_t abi_version; /* FDTD_ABI_VERSION */
   int32_t dtype;       /* FDTD_F32 / FDTD_F64: storage and arithmetic type; FDTD_F32X: float state, double arithmetic
@@ -198,6 +214,11 @@ typedef struct fdtd_desc {
   void* psi_E2[FDTD_MAX_SLABS];  /* fuse_eh = 3: a second psi_E buffer [2][psi_count] for every slab.  That kernel
                           updates the whole grid, CPML cells and faces included, in its single pass; cells whose E_new is recomputed by a neighbouring thread need the OLD psi_E, so psi_E
                           alternates between the two buffers like the fields (results always end in psi_E) */
+  int32_t n_deep;      /* objects beyond the second one on a cell */
+  int32_t h_wrap_ghost;/* x-sharded grids: 1 = the caller keeps the LOW ghost plane of Hy on the first slab equal to the last
+                          slab's last plane, so that a CurrentDetector cell on global plane x = 0 finds H[x-1] = H[-1]
+                          there (fdtd/detectors.py:432-447 wraps like python indexing) */
+  const fdtd_deep_object* deep;  /* HOST array [n_deep], registration order */
   int32_t x_wrap;      /* x-sharded grid with a periodic x boundary (fdtd/boundaries.py:184-195): 0 = none, else
                           1 + the number of post ops registered before it.  The copy E[0] = E[-1] / H[-1] = H[0] then
                           crosses the first and last slab: the caller runs fdtd_post_part(.., 0, ..), moves the plane

@@ -48,7 +48,7 @@ def load_reference():
 
 
 F32_SCENES = ("pml3d", "objects3d", "periodic3d", "c4small", "feed50", "overlaps3d", "patch_antenna", "ring3d",
-              "overlaps3d_stable")
+              "overlaps3d_stable", "stacked3d")
 SPECTRA_SCENES = ("patch_antenna",)
 
 

@@ -244,6 +244,30 @@ def overlaps3d_stable(fd, n=(22, 20, 20), t=4):
     return g
 
 
+def stacked3d(fd, n=(20, 18, 16), t=3):
+    """objects stacked three, four and five deep on the same cells, absorbers among them at every depth, one stack
+    reaching into the PMLs and across the middle of the grid (an x-slab boundary when sharded)."""
+    g = fd.Grid(shape=n, grid_spacing=77.5e-9, courant_number=0.25)
+    g[0:t, :, :] = fd.PML()
+    g[-t:, :, :] = fd.PML()
+    g[:, 0:t, :] = fd.PML()
+    g[:, :, -t:] = fd.PML()
+    rs = np.random.RandomState(21)
+    g[3:12, 3:12, 3:12] = fd.Object(permittivity=3.0, name="objA")
+    g[5:14, 5:14, 4:11] = fd.AbsorbingObject(permittivity=2.5 + rs.rand(9, 9, 7, 1), conductivity=8.0e3, name="objB")
+    g[7:13, 2:10, 5:12] = fd.AnisotropicObject(permittivity=3.0 + rs.rand(6, 8, 7, 3), name="objC")      # third
+    g[8:16, 6:12, 6:10] = fd.AbsorbingObject(permittivity=4.0, conductivity=2.0e4, name="objD")          # fourth
+    g[9:11, 7:16, 2:14] = fd.Object(permittivity=3.0 + rs.rand(2, 9, 12), name="objE")                   # fifth
+    g[0:6, 0:6, 8:16] = fd.Object(permittivity=3.5, name="objF")                                         # in three PMLs
+    g[1:5, 1:7, 9:15] = fd.AbsorbingObject(permittivity=3.0, conductivity=1.0e4, name="objG")
+    g[2:8, 2:5, 10:16] = fd.AnisotropicObject(permittivity=3.0 + rs.rand(6, 3, 6, 3), name="objH")       # third, in PMLs
+    g[4, :, :] = fd.PlaneSource(period=16, polarization="y", name="plane")
+    g[10, 8, 8] = fd.PointSource(period=11, amplitude=0.7, name="pt")                                 # on a 5-deep cell
+    g[2:18, 8, 7] = fd.LineDetector(name="line")
+    g[9:10, 7:9, 7:8] = fd.BlockDetector(name="block")
+    return g
+
+
 def patch_antenna(fd, patch=(20, 14), border=4, steps=240):
     """the reference's probe-fed patch antenna (tests/test_antenna_impedance.py:18-99) at reduced size and with
     one copper object per region (the original registers ONE AbsorbingObject instance three times, which
@@ -298,6 +322,7 @@ SCENES = {
     "feed50": (feed50, 80),
     "overlaps3d": (overlaps3d, 60),
     "overlaps3d_stable": (overlaps3d_stable, 300),
+    "stacked3d": (stacked3d, 120),
     "patch_antenna": (patch_antenna, 240),
     "ring3d": (ring3d, 70),
 }

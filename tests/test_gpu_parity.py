@@ -323,7 +323,6 @@ def test_config2_shape_at_its_full_step_count():
 def test_random_scene_on_gpu(seed, dtype):
     """seeded random registrations (tests/fuzz_scenes.py): CUDA vs oracle, bit for bit."""
     from fuzz_scenes import random_scene
-    from test_fuzz_emu import inexact_overlaps
     build, steps = random_scene(seed)
     g = build(cuda(dtype))
     g.run(steps // 2, progress_bar=False)
@@ -337,7 +336,7 @@ def test_random_scene_on_gpu(seed, dtype):
         want = scenes.dump(o)
     finally:
         yo.set_backend("numpy", "float64")
-    compare(got, want, TOL[dtype], bitwise=not inexact_overlaps(o))
+    compare(got, want, TOL[dtype], bitwise=True)
 
 
 @pytest.mark.parametrize("dtype,n,t", [("float32", (72, 64, 192), 6), ("float64", (40, 52, 100), 5),

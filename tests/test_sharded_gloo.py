@@ -43,7 +43,8 @@ def launch(world, backend, dtype, scene, steps, out, **extra_env):
                                                (3, "overlaps3d", "float32"), (2, "ring3d", "float64"),
                                                (3, "ring3d", "float32"), (4, "ring3d", "float64"),
                                                (2, "feed50", "float64"), (3, "feed50", "float32"),
-                                               (2, "objects3d", "float32x"), (3, "periodic3d", "float32x")])
+                                               (2, "objects3d", "float32x"), (3, "periodic3d", "float32x"),
+                                               (2, "stacked3d", "float64"), (3, "stacked3d", "float32")])
 def test_sharded_equals_single(tmp_path, world, scene, dtype):
     steps = 24
     out = str(tmp_path / "sharded.npz")
