@@ -72,7 +72,7 @@ def build_c4(fd, n, pml=PML_CELLS, balance=False, **kw):
     return g
 
 
-def build_c1(fd, scale=1, **kw):
+def build_c1(fd, balance=False, **kw):
     """configs[0]: the README quick-start (fdtd README.md:137-297)."""
     g = fd.Grid(shape=(25e-6, 15e-6, 1), grid_spacing=155e-9, **kw)
     g[11:32, 30:84, 0] = fd.Object(permittivity=1.7 ** 2, name="object")

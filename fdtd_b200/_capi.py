@@ -13,6 +13,7 @@ CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT, CLS_ANISO, CLS_OVERLAP, CLS_ABSO
 POST_PERIODIC, POST_PML_ADD = 0, 1
 SRC_POINTS, SRC_BOX, SRC_FEEDBACK = 0, 1, 2
 DET_FIELD, DET_CURRENT = 0, 1
+PHASE_BEFORE, PHASE_AFTER, PHASE_SOURCES, PHASE_DETECTORS, PHASE_ALL = 1, 2, 4, 8, 15
 
 _vp = C.c_void_p
 
@@ -103,6 +104,7 @@ EXPORTS = {
     "fdtd_run_sharded": (C.c_int, [C.POINTER(Desc), C.POINTER(Halo), C.c_int64, C.c_int64, C.c_int64, _vp]),
     "fdtd_halo_refresh": (C.c_int, [C.POINTER(Desc), C.POINTER(Halo), _vp]),
     "fdtd_sizeof_halo": (C.c_int64, []),
+    "fdtd_post_phases": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_uint32, C.c_int64, C.c_int64, _vp]),
     "fdtd_post_part": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_int32, C.c_int64, C.c_int64, _vp]),
     "fdtd_dft_accumulate": (C.c_int, [C.c_int32, _vp, C.c_int64, C.c_int64, _vp, C.c_int32, _vp, _vp]),
 }

@@ -470,21 +470,22 @@ int blocks_for(i64 n, int threads = 256) {
   return (int)b;
 }
 
-// part < 0: everything; 0 / 1: the post ops before / from the x-wrap of an x-sharded periodic grid on (sources
-// and detectors belong to part 1)
+// `phases` (FDTD_PHASE_*): which parts of what follows the half-step kernel to run.  With a periodic x boundary
+// across slabs (d->x_wrap) the boundary post ops are split at it: BEFORE = those registered before it, AFTER = the
+// rest; without one, BEFORE covers them all.
 template <typename T, bool IS_E, typename A = T>
-int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int part = -1) {
+int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, unsigned phases = FDTD_PHASE_ALL) {
   if (post_is_fused(d)) return FDTD_OK;  // done inside the half-step kernel
-  if (part < 0 && d->x_wrap)
-    return fail(FDTD_ERR_ARG, "periodic x boundary across slabs: call fdtd_post_part around the plane transfer");
-  if (part >= 0 && !d->x_wrap) return fail(FDTD_ERR_ARG, "fdtd_post_part needs d->x_wrap");
-  const int first = part == 1 ? d->x_wrap - 1 : 0;
-  const int last = part == 0 ? d->x_wrap - 1 : d->n_post;
+  if (d->x_wrap && (phases & FDTD_PHASE_BEFORE) && (phases & FDTD_PHASE_AFTER))
+    return fail(FDTD_ERR_ARG, "periodic x boundary across slabs: run the phases around the plane transfer");
+  const int split = d->x_wrap ? d->x_wrap - 1 : d->n_post;
+  const int first = (phases & FDTD_PHASE_BEFORE) ? 0 : split;
+  const int last = (phases & FDTD_PHASE_AFTER) ? d->n_post : ((phases & FDTD_PHASE_BEFORE) ? split : first);
   T* F[3];
   for (int c = 0; c < 3; ++c) F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
   // 0. objects beyond the second one on a cell, registration order (fdtd/grid.py:285-287); update_H of every
   //    object kind is empty (fdtd/objects.py:131-137, 223-229, 271-277)
-  for (int n = 0; IS_E && part != 1 && n < d->n_deep; ++n) {
+  for (int n = 0; IS_E && (phases & FDTD_PHASE_BEFORE) && n < d->n_deep; ++n) {
     const fdtd_deep_object& O = d->deep[n];
     const i64 cells = (i64)(O.box[1] - O.box[0]) * (O.box[3] - O.box[2]) * (O.box[5] - O.box[4]);
     if (O.box[0] >= O.box[1] || O.box[2] >= O.box[3] || O.box[4] >= O.box[5]) continue;
@@ -527,9 +528,8 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int p
       if (rc) return rc;
     }
   }
-  if (part == 0) return FDTD_OK;
   // 2. sources, registration order (fdtd/grid.py:294-295, 320-321)
-  for (int n = 0; n < d->n_sources; ++n) {
+  for (int n = 0; (phases & FDTD_PHASE_SOURCES) && n < d->n_sources; ++n) {
     const fdtd_source& S = d->sources[n];
     if (S.field != (IS_E ? 0 : 1)) continue;
     int64_t w = q - S.wave_q0;
@@ -559,7 +559,7 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int p
     if (rc) return rc;
   }
   // 3. detectors (fdtd/grid.py:298-299, 324-325)
-  for (int n = 0; n < d->n_detectors; ++n) {
+  for (int n = 0; (phases & FDTD_PHASE_DETECTORS) && n < d->n_detectors; ++n) {
     const fdtd_detector& D = d->detectors[n];
     if (D.n == 0) continue;
     if (slot < 0 || slot >= D.capacity)
@@ -637,13 +637,21 @@ int fdtd_post_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream) {
   return (d->dtype == FDTD_F32 ? launch_post<float, false, float>(d, q, slot, stream) : d->dtype == FDTD_F64 ? launch_post<double, false, double>(d, q, slot, stream) : launch_post<float, false, double>(d, q, slot, stream));
 }
 
-int fdtd_post_part(const fdtd_desc* d, int32_t field, int32_t part, int64_t q, int64_t slot, void* stream) {
+int fdtd_post_phases(const fdtd_desc* d, int32_t field, uint32_t phases, int64_t q, int64_t slot, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
-  if ((field != 0 && field != 1) || (part != 0 && part != 1)) return fail(FDTD_ERR_ARG, "fdtd_post_part: field / part");
+  if ((field != 0 && field != 1) || (phases & ~(uint32_t)FDTD_PHASE_ALL)) return fail(FDTD_ERR_ARG, "fdtd_post_phases: field / phases");
   if (field == 0)
-    return (d->dtype == FDTD_F32 ? launch_post<float, true, float>(d, q, slot, stream, part) : d->dtype == FDTD_F64 ? launch_post<double, true, double>(d, q, slot, stream, part) : launch_post<float, true, double>(d, q, slot, stream, part));
-  return (d->dtype == FDTD_F32 ? launch_post<float, false, float>(d, q, slot, stream, part) : d->dtype == FDTD_F64 ? launch_post<double, false, double>(d, q, slot, stream, part) : launch_post<float, false, double>(d, q, slot, stream, part));
+    return (d->dtype == FDTD_F32 ? launch_post<float, true, float>(d, q, slot, stream, phases) : d->dtype == FDTD_F64 ? launch_post<double, true, double>(d, q, slot, stream, phases) : launch_post<float, true, double>(d, q, slot, stream, phases));
+  return (d->dtype == FDTD_F32 ? launch_post<float, false, float>(d, q, slot, stream, phases) : d->dtype == FDTD_F64 ? launch_post<double, false, double>(d, q, slot, stream, phases) : launch_post<float, false, double>(d, q, slot, stream, phases));
+}
+
+int fdtd_post_part(const fdtd_desc* d, int32_t field, int32_t part, int64_t q, int64_t slot, void* stream) {
+  if (part != 0 && part != 1) return fail(FDTD_ERR_ARG, "fdtd_post_part: part");
+  if (d && !d->x_wrap) return fail(FDTD_ERR_ARG, "fdtd_post_part needs d->x_wrap");
+  return fdtd_post_phases(d, field, part == 0 ? FDTD_PHASE_BEFORE
+                                              : (FDTD_PHASE_AFTER | FDTD_PHASE_SOURCES | FDTD_PHASE_DETECTORS),
+                          q, slot, stream);
 }
 
 static int update_E_nocheck(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, int64_t graph_step = -1) {

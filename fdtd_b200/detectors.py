@@ -266,14 +266,15 @@ class CurrentDetector(BlockDetector):
     def _register_grid(self, grid, x, y, z):
         super()._register_grid(grid, x, y, z)
         part = grid._part
-        self._needs_ghost = False
+        self._needs_ghost = self._needs_wrap = False
         if part.sharded:
             xs = {(v + grid.Nx) % grid.Nx for v in self.x}
-            if 0 in xs:                                   # H[x-1] wraps to the LAST slab (fdtd/detectors.py:432-447)
-                raise NotImplementedError("a CurrentDetector cell on plane x = 0 of an x-sharded grid")
             # a cell on the first plane of a slab reads the left neighbour's H of the same half-step: the engine then
-            # samples after the ghost plane has arrived (same verdict on every rank)
-            self._needs_ghost = bool(xs & {part.bounds(r)[0] for r in range(1, part.world)})
+            # samples after the ghost plane has arrived (same verdict on every rank).  On global plane x = 0 that
+            # neighbour is the LAST slab: H[x-1] = H[-1] wraps like python indexing (fdtd/detectors.py:432-447), and
+            # the last slab's last plane travels into the first slab's low ghost plane before sampling.
+            self._needs_wrap = 0 in xs
+            self._needs_ghost = self._needs_wrap or bool(xs & {part.bounds(r)[0] for r in range(1, part.world)})
         self._last = bd.zeros((max(1, self._n_local),), dtype=grid._sdtype)
 
     @property

@@ -292,6 +292,8 @@ class Engine:
         # detectors that read the ghost plane of the half-step being sampled: exchange first, then sample -- done on
         # the send / recv path only
         self._late = any(getattr(det, "_needs_ghost", False) for det in g.detectors)
+        wrap_H = any(getattr(det, "_needs_wrap", False) for det in g.detectors)
+        d.h_wrap_ghost = int(wrap_H and g._part.rank == 0)
         if self._late:
             want, self._p2p = "nccl", False
         if self._p2p is None and g._E.is_cuda and want == "p2p":
@@ -301,7 +303,7 @@ class Engine:
                 import warnings
                 warnings.warn(f"fdtd_b200: peer-to-peer halo unavailable ({exc}); using NCCL send/recv")
                 self._p2p = False
-        self._halo = self._p2p if self._p2p else HaloExchange(g._part, g._E, g._H)
+        self._halo = self._p2p if self._p2p else HaloExchange(g._part, g._E, g._H, wrap_H=wrap_H)
         # may the boundary plane be pushed by the half-step kernel itself?  Only if nothing modifies that
         # plane afterwards: no periodic copy / late PML correction, no unfused source on the plane
         n = d.Nx
@@ -319,9 +321,6 @@ class Engine:
                     if not empty and box[0] <= plane < box[1]:
                         ok = False
             self._push_fused[field] = ok
-        if self._late and not self._push_fused["H"]:
-            raise NotImplementedError("a CurrentDetector cell on the first plane of an x-slab together with something "
-                                      "that modifies the slab's last H plane after the update (periodic copy, source)")
         if self._p2p:
             self._p2p.h.push_fused[0] = int(self._push_fused["E"])
             self._p2p.h.push_fused[1] = int(self._push_fused["H"])
@@ -329,18 +328,21 @@ class Engine:
         else:
             self._halo.refresh()
 
-    def _post(self, field, q, slot, st):
-        """what follows the half-step kernel on an x-sharded slab: post ops, sources, detectors -- around the
-        plane transfer of a periodic x boundary if there is one."""
+    def _post(self, field, q, slot, st, phases=_capi.PHASE_ALL):
+        """what follows the half-step kernel on an x-sharded slab: deep objects and post ops, sources, detectors
+        (`phases`: a subset, include/fdtd_b200.h FDTD_PHASE_*) -- around the plane transfer of a periodic x boundary
+        if there is one."""
         lib, d = self.lib, self.desc
-        if self._wrap is None:
-            post = lib.fdtd_post_E if field == "E" else lib.fdtd_post_H
-            _capi.check(lib, post(C.byref(d), q, slot, st))
-            return
         fidx = 0 if field == "E" else 1
-        _capi.check(lib, lib.fdtd_post_part(C.byref(d), fidx, 0, q, slot, st))
-        self._wrap.run(field)
-        _capi.check(lib, lib.fdtd_post_part(C.byref(d), fidx, 1, q, slot, st))
+        if self._wrap is None:
+            _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, phases, q, slot, st))
+            return
+        if phases & _capi.PHASE_BEFORE:
+            _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, _capi.PHASE_BEFORE, q, slot, st))
+            self._wrap.run(field)
+        rest = phases & ~_capi.PHASE_BEFORE
+        if rest:
+            _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, rest, q, slot, st))
 
     def _p2p_refresh(self):
         """push both boundary planes and wait for the neighbours' (collective; after the user wrote E / H)."""
@@ -513,9 +515,11 @@ class Engine:
             _capi.check(lib, step(C.byref(d), edge[0], edge[1], q, slot, st))
         self._pending[other] = None
         if field == "H" and self._late:
-            # a CurrentDetector on the first plane of a slab reads the neighbour's H of THIS half-step
+            # a CurrentDetector on the first plane of a slab reads the neighbour's H of THIS half-step, in its final
+            # state: post ops and sources first, then the exchange, then the detectors
+            self._post(field, q, slot, st, _capi.PHASE_ALL & ~_capi.PHASE_DETECTORS)
             halo.wait(halo.start(field))
-            self._post(field, q, slot, st)
+            self._post(field, q, slot, st, _capi.PHASE_DETECTORS)
             self._pending[field] = None
             return
         self._post(field, q, slot, st)

@@ -82,10 +82,13 @@ class Partition:
 class HaloExchange:
     """asynchronous one-plane exchanges of (Ey,Ez) to the left and (Hy,Hz) to the right."""
 
-    def __init__(self, part, E, H):
+    def __init__(self, part, E, H, wrap_H=False):
         self.part, self.E, self.H = part, E, H      # storage tensors (3, nx+2, Ny, Nz)
         self.cuda = E.is_cuda
         self.stream = torch.cuda.Stream(device=E.device) if self.cuda else None
+        # wrap_H: the last slab's last H plane also goes into the FIRST slab's low ghost plane (a CurrentDetector on
+        # global plane x = 0 reads H[-1], fdtd/detectors.py:432-447)
+        self.wrap_H = wrap_H
 
     def _ops(self, F, to_left):
         p, n = self.part, self.part.nx
@@ -101,6 +104,11 @@ class HaloExchange:
                     ops.append(dist.P2POp(dist.isend, F[c, n], p.rank + 1))
                 if p.rank > 0:
                     ops.append(dist.P2POp(dist.irecv, F[c, 0], p.rank - 1))
+                if self.wrap_H and F is self.H:
+                    if p.rank == p.world - 1:
+                        ops.append(dist.P2POp(dist.isend, F[c, n], 0))
+                    if p.rank == 0:
+                        ops.append(dist.P2POp(dist.irecv, F[c, 0], p.world - 1))
         return ops
 
     def start(self, field):

@@ -146,6 +146,21 @@ def slabdet(fd, n=(24, 40, 10), t=4):
     return g
 
 
+def current_x0(fd, n=(18, 12, 10), t=3):
+    """CurrentDetectors on global plane x = 0 (H[x-1] wraps to the LAST plane, fdtd/detectors.py:432-447 -- another
+    slab when sharded) and on the first plane of an inner slab, next to a source that makes H differ there."""
+    g = fd.Grid(shape=n, grid_spacing=77.5e-9)
+    g[:, 0:t, :] = fd.PML()
+    g[:, :, -t:] = fd.PML()
+    g[n[0] - 2, 6, 5] = fd.PointSource(period=9, name="near_the_end")
+    g[1, 5, 4] = fd.PointSource(period=7, amplitude=0.6, name="near_the_start")
+    g[0, 5, 5] = fd.CurrentDetector(name="on_plane_0")
+    g[0:1, 4:6, 3:4] = fd.CurrentDetector(name="block_on_plane_0")
+    g[n[0] // 2, 6, 5] = fd.CurrentDetector(name="on_a_cut")
+    g[0:n[0], 6, 5] = fd.LineDetector(name="line")
+    return g
+
+
 def c4small(fd, n=(32, 32, 32), t=6):
     """configs[3] shape (the bench workload) reduced: six PMLs, centre PointSource, LineDetector."""
     g = fd.Grid(shape=n, grid_spacing=77.5e-9)

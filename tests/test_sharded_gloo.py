@@ -134,3 +134,29 @@ def test_ring_capacity_is_the_same_on_every_rank(tmp_path, world):
     for k in want:
         assert got[k].shape == want[k].shape, k
         assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_current_detector_on_global_plane_zero(tmp_path, world):
+    """a CurrentDetector cell at x = 0 reads H[x-1] = H[-1] (python wrap-around, fdtd/detectors.py:432-447): on an
+    x-sharded grid that plane lives on the LAST slab and travels into the first slab's low ghost before sampling."""
+    steps = 30
+    out = str(tmp_path / "sharded.npz")
+    launch(world, "gloo", "float64", "current_x0", steps, out, FDTD_TEST_EXPECT_LATE="1")
+    got = dict(np.load(out))
+    assert "skipped" not in got, got
+    fd = use_emu("float64")
+    g = scenes.current_x0(fd)
+    g.run(steps, progress_bar=False)
+    want = scenes.dump(g)
+    assert float(np.abs(want["det0_I"]).max()) > 0
+    for k in want:
+        assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
+    # ... and the unsharded run is the reference's (oracle, bit for bit)
+    from oracle import yee_oracle as yo
+    yo.set_backend("numpy", "float64")
+    o = scenes.current_x0(yo)
+    o.run(steps)
+    ref = scenes.dump(o)
+    for k in ref:
+        assert np.array_equal(want[k], ref[k]), k
