@@ -13,7 +13,7 @@ CLS_VARY_E, CLS_VARY_H, CLS_ABSORB, CLS_OBJECT, CLS_ANISO, CLS_OVERLAP, CLS_ABSO
 POST_PERIODIC, POST_PML_ADD = 0, 1
 SRC_POINTS, SRC_BOX, SRC_FEEDBACK = 0, 1, 2
 DET_FIELD, DET_CURRENT = 0, 1
-PHASE_BEFORE, PHASE_AFTER, PHASE_SOURCES, PHASE_DETECTORS, PHASE_ALL = 1, 2, 4, 8, 15
+PHASE_BEFORE, PHASE_AFTER, PHASE_SOURCES, PHASE_DETECTORS, PHASE_OBJECTS, PHASE_ALL = 1, 2, 4, 8, 16, 31
 
 _vp = C.c_void_p
 

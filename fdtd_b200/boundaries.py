@@ -25,6 +25,24 @@ class Boundary:
         self.z = self._handle_slice(z)
         grid._register_name(self)
 
+    # the reference's plug-in protocol (fdtd/grid.py:279-281, 290-291, 305-307, 316-317): done inside the kernels for
+    # the built-in boundaries; overridden in a subclass, they are called per step (fdtd_b200/engine.py, `_hooks`)
+    def update_phi_E(self):
+        pass
+
+    def update_phi_H(self):
+        pass
+
+    def update_E(self):
+        pass
+
+    def update_H(self):
+        pass
+
+    for _m in (update_phi_E, update_phi_H, update_E, update_H):
+        _m._fdtd_b200_builtin = True
+    del _m
+
     def _handle_slice(self, s):
         if isinstance(s, list):
             if len(s) > 1:

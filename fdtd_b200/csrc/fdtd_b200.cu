@@ -485,7 +485,7 @@ int launch_post(const fdtd_desc* d, int64_t q, int64_t slot, void* stream, unsig
   for (int c = 0; c < 3; ++c) F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
   // 0. objects beyond the second one on a cell, registration order (fdtd/grid.py:285-287); update_H of every
   //    object kind is empty (fdtd/objects.py:131-137, 223-229, 271-277)
-  for (int n = 0; IS_E && (phases & FDTD_PHASE_BEFORE) && n < d->n_deep; ++n) {
+  for (int n = 0; IS_E && (phases & FDTD_PHASE_OBJECTS) && n < d->n_deep; ++n) {
     const fdtd_deep_object& O = d->deep[n];
     const i64 cells = (i64)(O.box[1] - O.box[0]) * (O.box[3] - O.box[2]) * (O.box[5] - O.box[4]);
     if (O.box[0] >= O.box[1] || O.box[2] >= O.box[3] || O.box[4] >= O.box[5]) continue;
@@ -649,7 +649,7 @@ int fdtd_post_phases(const fdtd_desc* d, int32_t field, uint32_t phases, int64_t
 int fdtd_post_part(const fdtd_desc* d, int32_t field, int32_t part, int64_t q, int64_t slot, void* stream) {
   if (part != 0 && part != 1) return fail(FDTD_ERR_ARG, "fdtd_post_part: part");
   if (d && !d->x_wrap) return fail(FDTD_ERR_ARG, "fdtd_post_part needs d->x_wrap");
-  return fdtd_post_phases(d, field, part == 0 ? FDTD_PHASE_BEFORE
+  return fdtd_post_phases(d, field, part == 0 ? (FDTD_PHASE_OBJECTS | FDTD_PHASE_BEFORE)
                                               : (FDTD_PHASE_AFTER | FDTD_PHASE_SOURCES | FDTD_PHASE_DETECTORS),
                           q, slot, stream);
 }

@@ -202,6 +202,8 @@ class _Detector:
     def detect_H(self):
         pass
 
+    detect_E._fdtd_b200_builtin = detect_H._fdtd_b200_builtin = True
+
     def __repr__(self):
         return f"{self.__class__.__name__}(name={repr(self.name)})"
 

@@ -64,9 +64,39 @@ class Engine:
             d.bg_inv_eps[c] = g._bg_inv_eps[c]
             d.bg_inv_mu[c] = g._bg_inv_mu[c]
 
-        # --- boundaries -----------------------------------------------------------------------
+        # --- plug-ins -------------------------------------------------------------------------
+        # Built-in plug-ins are folded into the kernels.  Anything else registered on the grid -- a class of the user's
+        # that follows the reference's duck-typed protocol (fdtd/grid.py:279-299, 305-325), or a subclass of a built-in
+        # that overrides a protocol method -- is called from Python on every half-step, at the reference's place in
+        # the order (`_hooked_halfstep`): a documented slow path, never a silent skip.
         from .boundaries import PML, PeriodicBoundary
+        from .detectors import _Detector
+        from .objects import Object
+
+        def custom(thing, *methods):
+            return [m for m in methods
+                    if callable(getattr(thing, m, None))
+                    and not getattr(getattr(type(thing), m, None), "_fdtd_b200_builtin", False)]
+
+        self._hooks = {
+            "boundaries": [(b, custom(b, "update_phi_E", "update_phi_H", "update_E", "update_H")) for b in g.boundaries],
+            "objects": [(o, custom(o, "update_E", "update_H")) for o in g.objects],
+            "sources": [(x, custom(x, "update_E", "update_H")) for x in g.sources],
+            "detectors": [(x, custom(x, "detect_E", "detect_H")) for x in g.detectors],
+        }
+        self._hooks = {k: [(t, m) for t, m in v if m] for k, v in self._hooks.items()}
+        self._hooked = any(self._hooks.values())
+        if self._hooked and part.sharded:
+            raise NotImplementedError("user-defined plug-ins (objects / sources / detectors / boundaries with their own "
+                                      "update or detect methods) on an x-sharded grid: they see one slab only")
+        objects = [o for o in g.objects if isinstance(o, Object)]
+        sources = [x for x in g.sources if hasattr(x, "_entries")]
+        self._dets = [x for x in g.detectors if isinstance(x, _Detector)]
+
+        # --- boundaries -----------------------------------------------------------------------
         slabs, post, seen_periodic, x_wrap = [], [], False, 0
+        # a user object's update_E runs between the field update and the PML corrections: keep those out of the kernel
+        unfuse = bool(self._hooks["objects"])
         for b in g.boundaries:
             if isinstance(b, PML):
                 if len(slabs) == _capi.MAX_SLABS:
@@ -75,12 +105,12 @@ class Engine:
                 slabs.append(b)
                 s = d.slabs[idx]
                 s.axis, s.lo, s.thickness = b.axis, b.lo, b.thickness
-                s.fused = 0 if seen_periodic else 1
+                s.fused = 0 if (seen_periodic or unfuse) else 1
                 s.x0, s.x1 = b._x0, b._x1
                 s.psi_count = b._psi_E.shape[1]
                 s.psi_E, s.psi_H = _ptr(b._psi_E), _ptr(b._psi_H)
                 s.bE, s.cE, s.bH, s.cH = (_ptr(b._tab[k]) for k in ("bE", "cE", "bH", "cH"))
-                if seen_periodic:
+                if seen_periodic or unfuse:
                     post.append((_capi.POST_PML_ADD, idx))
             elif isinstance(b, PeriodicBoundary):
                 if (g.Nx, g.Ny, g.Nz)[b.axis] < 2:
@@ -92,8 +122,8 @@ class Engine:
                     x_wrap = len(post) + 1
                     continue
                 post.append((_capi.POST_PERIODIC, b.axis))
-            else:
-                raise TypeError(f"unsupported boundary {b!r}")
+            elif not any(t is b for t, _ in self._hooks["boundaries"]):
+                raise TypeError(f"unsupported boundary {b!r}: neither a built-in one nor a plug-in with update methods")
         if len(post) > _capi.MAX_POST:
             raise ValueError("too many boundary post-ops")
         d.n_slabs, d.n_post, d.x_wrap = len(slabs), len(post), x_wrap
@@ -104,7 +134,7 @@ class Engine:
         ie_grid, imu = g._inv_eps, g._inv_mu
         ie_eff, absorb, ie2, absorb2 = ie_grid, None, None, None
         deep = []                    # (object, mask): objects that are the third or later one on some cells
-        if g.objects:
+        if objects:
             # The reference updates every object in registration order (fdtd/grid.py:285-287), so a cell covered
             # by several objects gets several updates.  The first object covering a cell becomes coefficient layer 1
             # (ie_eff / absorb), the second one layer 2 (ie2 / absorb2), both applied inside the fused kernel; every
@@ -112,7 +142,7 @@ class Engine:
             # layers are marked by a negative zero in the grid's eps^-1 (x-component: layer 1, y: layer 2).
             from .objects import AbsorbingObject, AnisotropicObject
             ie_eff = ie_grid.clone()
-            boxes = [(o.x, o.y, o.z) for o in g.objects]
+            boxes = [(o.x, o.y, o.z) for o in objects]
             overlaps = any(all(max(p.start, q.start) < min(p.stop, q.stop) for p, q in zip(boxes[a], boxes[b]))
                            for a in range(len(boxes)) for b in range(a + 1, len(boxes)))
             cover = torch.zeros(ie_grid.shape[1:], dtype=torch.int8, device=ie_grid.device) if overlaps else None
@@ -122,7 +152,7 @@ class Engine:
                 sel = (region == 0) if cells is None else (cells & (region == 0))
                 ie_grid[comp][loc] = torch.where(sel, torch.full_like(region, -0.0 if aniso else 0.0), region)
 
-            for o in g.objects:
+            for o in objects:
                 if o._nx_local == 0:
                     continue
                 loc = (slice(None),) + o._loc
@@ -179,11 +209,11 @@ class Engine:
         d.tile_y, d.tile_z = ty.value, tz.value
         cls = None
         if ie_eff is not None or imu is not None:
-            cls = self._classify(ie_eff, ie_grid if g.objects else None, absorb, imu, ty.value, tz.value, ie2, absorb2)
+            cls = self._classify(ie_eff, ie_grid if objects else None, absorb, imu, ty.value, tz.value, ie2, absorb2)
         for c in range(3):
             d.inv_eps[c] = ie_eff[c].data_ptr() if ie_eff is not None else None
             d.inv_eps2[c] = ie2[c].data_ptr() if ie2 is not None else None
-            d.inv_eps_grid[c] = ie_grid[c].data_ptr() if (g.objects and ie_grid is not None) else None
+            d.inv_eps_grid[c] = ie_grid[c].data_ptr() if (objects and ie_grid is not None) else None
             d.absorb[c] = absorb[c].data_ptr() if absorb is not None else None
             d.absorb2[c] = absorb2[c].data_ptr() if absorb2 is not None else None
             d.inv_mu[c] = imu[c].data_ptr() if imu is not None else None
@@ -194,7 +224,7 @@ class Engine:
         # --- sources ----------------------------------------------------------------------------
         self._src_entries = []       # (desc index, source object)
         self._feedback_sources = []  # those that record their voltages in a device ring
-        entries = [(s, entry) for s in g.sources for entry in s._entries()]
+        entries = [(s, entry) for s in sources for entry in s._entries()]
         # host tables of any length (the reference keeps plain lists, fdtd/grid.py:155-163); the descriptor points at them
         self._src_table = (_capi.Source * max(1, len(entries)))()
         d.sources = C.cast(self._src_table, C.POINTER(_capi.Source))
@@ -226,14 +256,14 @@ class Engine:
         self._src_sig = self._source_signature()
 
         # --- detectors --------------------------------------------------------------------------
-        self._det_table = (_capi.Detector * max(1, len(g.detectors)))()
+        self._det_table = (_capi.Detector * max(1, len(self._dets)))()
         d.detectors = C.cast(self._det_table, C.POINTER(_capi.Detector))
         w = 4 if g._sdtype is torch.float32 else 8
         # the capacity must be the SAME on every rank of an x-sharded grid (a ring flush is collective): size it
         # from the largest per-rank share of every detector, which every rank can compute from the partition
-        per_step = sum(2 * det._width * w * max(1, det._n_ring) for det in g.detectors)
-        self.ring_capacity = int(min(8192, max(16, RING_BYTES // max(1, per_step)))) if g.detectors else 1 << 62
-        for n, det in enumerate(g.detectors):
+        per_step = sum(2 * det._width * w * max(1, det._n_ring) for det in self._dets)
+        self.ring_capacity = int(min(8192, max(16, RING_BYTES // max(1, per_step)))) if self._dets else 1 << 62
+        for n, det in enumerate(self._dets):
             det._ensure_ring(self.ring_capacity)
             e = d.detectors[n]
             e.n = det._n_local
@@ -245,12 +275,12 @@ class Engine:
             e.capacity = self.ring_capacity
             for k in range(6):
                 e.bbox[k] = det._bbox[k]
-        d.n_detectors = len(g.detectors)
+        d.n_detectors = len(self._dets)
         for idx, src in self._feedback_sources:
-            src._ensure_ring(self.ring_capacity if g.detectors else 4096)
+            src._ensure_ring(self.ring_capacity if self._dets else 4096)
             d.sources[idx].record = _ptr(src._ring_V)
             d.sources[idx].record_capacity = src._capacity
-        if self._feedback_sources and not g.detectors:
+        if self._feedback_sources and not self._dets:
             self.ring_capacity = 4096
 
         # temporally fused E+H steps (12 instead of 18 words per cell and step) need a second pair of field
@@ -271,8 +301,8 @@ class Engine:
         # CUDA-graph replay of step chunks pays off where a step is launch-bound (small grids)
         self._dyn = torch.zeros(2, dtype=torch.int64, device=g._E.device)
         d.dyn = _ptr(self._dyn)
-        d.fuse_post = -1 if g._fuse_post is None else int(bool(g._fuse_post))
-        d.use_graphs = 1 if (g._E.is_cuda and not part.sharded and g._use_graphs is not False
+        d.fuse_post = 0 if self._hooked else (-1 if g._fuse_post is None else int(bool(g._fuse_post)))
+        d.use_graphs = 1 if (g._E.is_cuda and not part.sharded and not self._hooked and g._use_graphs is not False
                              and (g._use_graphs or part.nx * g.Ny * g.Nz <= GRAPH_MAX_CELLS)) else 0
 
         self._ensure_wave(g.time_steps_passed, 1)
@@ -291,8 +321,8 @@ class Engine:
         want = os.environ.get("FDTD_B200_HALO", "p2p")
         # detectors that read the ghost plane of the half-step being sampled: exchange first, then sample -- done on
         # the send / recv path only
-        self._late = any(getattr(det, "_needs_ghost", False) for det in g.detectors)
-        wrap_H = any(getattr(det, "_needs_wrap", False) for det in g.detectors)
+        self._late = any(getattr(det, "_needs_ghost", False) for det in self._dets)
+        wrap_H = any(getattr(det, "_needs_wrap", False) for det in self._dets)
         d.h_wrap_ghost = int(wrap_H and g._part.rank == 0)
         if self._late:
             want, self._p2p = "nccl", False
@@ -337,10 +367,12 @@ class Engine:
         if self._wrap is None:
             _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, phases, q, slot, st))
             return
-        if phases & _capi.PHASE_BEFORE:
-            _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, _capi.PHASE_BEFORE, q, slot, st))
-            self._wrap.run(field)
-        rest = phases & ~_capi.PHASE_BEFORE
+        first = _capi.PHASE_OBJECTS | _capi.PHASE_BEFORE
+        if phases & first:
+            _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, phases & first, q, slot, st))
+            if phases & _capi.PHASE_BEFORE:
+                self._wrap.run(field)
+        rest = phases & ~first
         if rest:
             _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, rest, q, slot, st))
 
@@ -420,7 +452,7 @@ class Engine:
     def _source_signature(self):
         """the per-step parameters the reference re-reads from every source on every step (fdtd/sources.py:95-108,
         280-295, 478-486, 601-626): changing one between steps must take effect on the next step."""
-        return tuple(s._signature() for s in self.grid.sources)
+        return tuple(s._signature() for s in self.grid.sources if hasattr(s, "_signature"))
 
     def stale(self):
         g = self.grid
@@ -468,7 +500,7 @@ class Engine:
     def _slot(self, field):
         """next free ring slot for `field`, flushing the rings to the host when full."""
         g = self.grid
-        if not g.detectors and not self._feedback_sources:
+        if not self._dets and not self._feedback_sources:
             return 0
         if g._ring_fill[field] >= self.ring_capacity:
             self.flush_detectors()
@@ -479,7 +511,7 @@ class Engine:
         nE, nH = g._ring_fill["E"], g._ring_fill["H"]
         if nE == 0 and nH == 0:
             return
-        for det in g.detectors:
+        for det in self._dets:
             det._drain(nE, nH)
         for _, src in self._feedback_sources:
             src._drain(nE)
@@ -525,15 +557,47 @@ class Engine:
         self._post(field, q, slot, st)
         self._pending[field] = halo.start(field)
 
+    def _hooked_halfstep(self, field, q, slot):
+        """one half-step with user plug-ins in the loop (unsharded), in the reference's order (fdtd/grid.py:275-325):
+        boundaries' update_phi -> field update + built-in objects (kernel) -> deeper built-in objects -> user objects'
+        update(curl) -> boundaries' update (built-in post ops, then the user's) -> sources (built-in, then the user's) ->
+        detectors (built-in, then the user's).  Within a phase the built-in plug-ins run before the user's."""
+        g, lib, d, hk = self.grid, self.lib, self.desc, self._hooks
+        fidx = 0 if field == "E" else 1
+        st = self._stream()
+
+        def call(kind, method, *args):
+            for thing, methods in hk[kind]:
+                if method in methods:
+                    getattr(thing, method)(*args)
+
+        call("boundaries", "update_phi_" + field)
+        step = lib.fdtd_e_halfstep if field == "E" else lib.fdtd_h_halfstep
+        curl = None
+        if any("update_" + field in m for _, m in hk["objects"]):
+            from .grid import curl_E, curl_H        # the curl the update is about to use, for the user's objects
+            curl = curl_H(g.H) if field == "E" else curl_E(g.E)
+        _capi.check(lib, step(C.byref(d), 0, d.Nx, q, slot, st))
+        _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, _capi.PHASE_OBJECTS, q, slot, st))
+        call("objects", "update_" + field, curl)
+        _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, _capi.PHASE_BEFORE | _capi.PHASE_AFTER, q, slot, st))
+        call("boundaries", "update_" + field)
+        _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, _capi.PHASE_SOURCES, q, slot, st))
+        call("sources", "update_" + field)
+        _capi.check(lib, lib.fdtd_post_phases(C.byref(d), fidx, _capi.PHASE_DETECTORS, q, slot, st))
+        call("detectors", "detect_" + field)
+
     def update_E(self, q):
         g, lib, d = self.grid, self.lib, self.desc
         self._ensure_wave(q, 1)
         slot = self._slot("E")
-        if self._halo is None:
+        if self._hooked:
+            self._hooked_halfstep("E", q, slot)
+        elif self._halo is None:
             _capi.check(lib, lib.fdtd_update_E(C.byref(d), q, slot, self._stream()))
         else:
             self._sharded_halfstep("E", q, slot)
-        if g.detectors or self._feedback_sources:
+        if self._dets or self._feedback_sources:
             g._ring_fill["E"] += 1
         for _, src in self._feedback_sources:
             src._steps_logged.append(q)
@@ -542,18 +606,20 @@ class Engine:
         g, lib, d = self.grid, self.lib, self.desc
         self._ensure_wave(q, 1)
         slot = self._slot("H")
-        if self._halo is None:
+        if self._hooked:
+            self._hooked_halfstep("H", q, slot)
+        elif self._halo is None:
             _capi.check(lib, lib.fdtd_update_H(C.byref(d), q, slot, self._stream()))
         else:
             self._sharded_halfstep("H", q, slot)
-        if g.detectors or self._feedback_sources:
+        if self._dets or self._feedback_sources:
             g._ring_fill["H"] += 1
 
     def run(self, q0, nsteps, progress=None):
         """nsteps full steps from step index q0; one C call per chunk when not sharded."""
         g, lib, d = self.grid, self.lib, self.desc
         done = 0
-        rings = bool(g.detectors or self._feedback_sources)
+        rings = bool(self._dets or self._feedback_sources)
         while done < nsteps:
             if rings and (g._ring_fill["E"] != g._ring_fill["H"] or g._ring_fill["E"] >= self.ring_capacity):
                 self.flush_detectors()
@@ -561,7 +627,13 @@ class Engine:
             n = min(nsteps - done, room, WAVE_TABLE_MAX)
             q = q0 + done
             self._ensure_wave(q, n)
-            if self._halo is None:
+            if self._hooked:
+                # user plug-ins read grid.time_steps_passed like the reference's sources do: keep it current per step
+                for s in range(n):
+                    g.time_steps_passed = q + s
+                    self.update_E(q + s)
+                    self.update_H(q + s)
+            elif self._halo is None:
                 _capi.check(lib, lib.fdtd_run(C.byref(d), q, n, g._ring_fill["E"] if rings else 0,
                                               self._stream()))
                 if rings:

@@ -37,31 +37,34 @@ def _array_in_array_out(fn):
     return wrapped
 
 
+def _one_sided(F, comp, axis, forward):
+    """difference of component `comp` along `axis` towards the next (forward) or from the previous (backward) cell,
+    zero on the face where that neighbour does not exist"""
+    out = torch.zeros_like(F[..., comp])
+    if F.shape[axis] > 1:
+        keep = [slice(None)] * 3
+        keep[axis] = slice(None, -1) if forward else slice(1, None)
+        out[tuple(keep)] = torch.diff(F[..., comp], dim=axis)
+    return out
+
+
+def _curl(F, forward):
+    # component a of the curl is dF_w/du - dF_u/dw with (a, u, w) cyclic
+    return torch.stack([_one_sided(F, (a + 2) % 3, (a + 1) % 3, forward) - _one_sided(F, (a + 1) % 3, (a + 2) % 3, forward)
+                        for a in range(3)], dim=-1)
+
+
 @_array_in_array_out
 def curl_E(E):
-    """H-type curl of an (Nx,Ny,Nz,3) array, forward differences (fdtd/grid.py:29-51).
-    Convenience for user code and tests; the stepping kernels fuse this and never call it."""
-    curl = torch.zeros_like(E)
-    curl[:, :-1, :, 0] += E[:, 1:, :, 2] - E[:, :-1, :, 2]
-    curl[:, :, :-1, 0] -= E[:, :, 1:, 1] - E[:, :, :-1, 1]
-    curl[:, :, :-1, 1] += E[:, :, 1:, 0] - E[:, :, :-1, 0]
-    curl[:-1, :, :, 1] -= E[1:, :, :, 2] - E[:-1, :, :, 2]
-    curl[:-1, :, :, 2] += E[1:, :, :, 1] - E[:-1, :, :, 1]
-    curl[:, :-1, :, 2] -= E[:, 1:, :, 0] - E[:, :-1, :, 0]
-    return curl
+    """H-type curl of an (Nx,Ny,Nz,3) array: forward differences, masked on the high faces (fdtd/grid.py:29-51).
+    Convenience for user code, the plug-in path and tests; the stepping kernels fuse this and never call it."""
+    return _curl(E, forward=True)
 
 
 @_array_in_array_out
 def curl_H(H):
-    """E-type curl, backward differences (fdtd/grid.py:54-76)."""
-    curl = torch.zeros_like(H)
-    curl[:, 1:, :, 0] += H[:, 1:, :, 2] - H[:, :-1, :, 2]
-    curl[:, :, 1:, 0] -= H[:, :, 1:, 1] - H[:, :, :-1, 1]
-    curl[:, :, 1:, 1] += H[:, :, 1:, 0] - H[:, :, :-1, 0]
-    curl[1:, :, :, 1] -= H[1:, :, :, 2] - H[:-1, :, :, 2]
-    curl[1:, :, :, 2] += H[1:, :, :, 1] - H[:-1, :, :, 1]
-    curl[:, 1:, :, 2] -= H[:, 1:, :, 0] - H[:, :-1, :, 0]
-    return curl
+    """E-type curl: backward differences, masked on the low faces (fdtd/grid.py:54-76)."""
+    return _curl(H, forward=False)
 
 
 class Grid:

@@ -78,6 +78,17 @@ class Object:
         dist.broadcast(buf, src=part.world - 1)
         return buf
 
+    # the reference's plug-in protocol (fdtd/grid.py:285-287, 311-313).  The engine folds the built-in object kinds
+    # into the fused kernel and never calls these; a subclass that OVERRIDES them is driven through the per-step
+    # plug-in path instead (fdtd_b200/engine.py, `_hooks`)
+    def update_E(self, curl_H):
+        pass
+
+    def update_H(self, curl_E):
+        pass
+
+    update_E._fdtd_b200_builtin = update_H._fdtd_b200_builtin = True
+
     def _handle_slice(self, s, max_index: int = None) -> slice:
         if isinstance(s, list):
             if len(s) == 1:

@@ -99,6 +99,8 @@ class _TimedSource:
     def update_H(self):
         pass
 
+    update_E._fdtd_b200_builtin = update_H._fdtd_b200_builtin = True
+
     def __repr__(self):
         return (f"{self.__class__.__name__}(period={self.period}, amplitude={self.amplitude}, "
                 f"phase_shift={self.phase_shift}, name={repr(self.name)})")
@@ -263,6 +265,8 @@ class PlaneSource:
     def update_H(self):
         pass
 
+    update_E._fdtd_b200_builtin = update_H._fdtd_b200_builtin = True
+
     def __repr__(self):
         return (f"{self.__class__.__name__}(period={self.period}, amplitude={self.amplitude}, "
                 f"phase_shift={self.phase_shift}, name={repr(self.name)}, "
@@ -386,6 +390,8 @@ class SoftArbitraryPointSource:
 
     def update_H(self):
         pass
+
+    update_E._fdtd_b200_builtin = update_H._fdtd_b200_builtin = True
 
     def __repr__(self):
         return f"{self.__class__.__name__}()"

@@ -265,12 +265,13 @@ int fdtd_post_part(const fdtd_desc* d, int32_t field, int32_t part, int64_t q, i
 /* The general form: any subset of the phases that follow the half-step kernel, in their fixed order.  A caller that
  * has to do something in between (move the wrap plane of a periodic x boundary; exchange the ghost planes BEFORE the
  * detectors sample, for a CurrentDetector whose H loop reaches into the neighbour slab) calls it more than once. */
-#define FDTD_PHASE_BEFORE 1u     /* objects beyond the second on a cell, then the boundary post ops registered before
-                                    the x-wrap boundary (all of them when d->x_wrap == 0) */
+#define FDTD_PHASE_OBJECTS 16u   /* objects beyond the second one on a cell (fdtd_deep_object), registration order */
+#define FDTD_PHASE_BEFORE 1u     /* the boundary post ops registered before the x-wrap boundary (all of them when
+                                    d->x_wrap == 0) */
 #define FDTD_PHASE_AFTER 2u      /* the boundary post ops registered after the x-wrap boundary */
 #define FDTD_PHASE_SOURCES 4u
 #define FDTD_PHASE_DETECTORS 8u
-#define FDTD_PHASE_ALL 15u
+#define FDTD_PHASE_ALL 31u
 int fdtd_post_phases(const fdtd_desc* d, int32_t field, uint32_t phases, int64_t q, int64_t slot, void* stream);
 /* Grid.update_E / Grid.update_H (fdtd/grid.py:275-325) on the whole local slab */
 int fdtd_update_E(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);

@@ -420,3 +420,121 @@ def rel_l2(a, b):
     den = np.sqrt((np.abs(b) ** 2).sum())
     num = np.sqrt((np.abs(a - b) ** 2).sum())
     return num / den if den > 0 else num
+
+
+# ---- user-defined plug-ins (the reference's duck-typed protocol, fdtd/grid.py:279-299, 305-325) -------------------
+# Written against that protocol only -- _register_grid + update_phi_E/H, update_E/H, detect_E/H on `grid.E` / `grid.H`
+# -- so the same classes run on the unmodified reference, on the oracle and on fdtd_b200.
+
+class UserGainObject:
+    """a user object: scales E in its box and feeds a little of the curl back"""
+
+    def __init__(self, factor=0.995, feed=0.01, name=None):
+        self.factor, self.feed, self.name = factor, feed, name
+
+    def _register_grid(self, grid, x, y, z):
+        self.grid, self.loc = grid, (x, y, z)
+        grid.objects.append(self)
+
+    def update_E(self, curl_H):
+        E = self.grid.E
+        E[self.loc] = E[self.loc] * self.factor + self.feed * curl_H[self.loc]
+
+    def update_H(self, curl_E):
+        pass
+
+
+class UserSquareSource:
+    """a user source: a square wave on Ey of one cell, and a kick on Hx every seventh step"""
+
+    def __init__(self, half_period=5, name=None):
+        self.half_period, self.name = half_period, name
+
+    def _register_grid(self, grid, x, y, z):
+        self.grid, self.cell = grid, (x[0], y[0], z[0])
+        grid.sources.append(self)
+
+    def update_E(self):
+        q = self.grid.time_steps_passed
+        x, y, z = self.cell
+        self.grid.E[x, y, z, 1] += 1.0 if (q // self.half_period) % 2 == 0 else -1.0
+
+    def update_H(self):
+        if self.grid.time_steps_passed % 7 == 0:
+            x, y, z = self.cell
+            self.grid.H[x, y, z, 0] += 0.25
+
+
+class UserProbe:
+    """a user detector: one component of one cell per half-step, as python floats"""
+
+    def __init__(self, name=None):
+        self.name, self.E, self.H = name, [], []
+
+    def _register_grid(self, grid, x, y, z):
+        self.grid, self.cell = grid, (x[0], y[0], z[0])
+        grid.detectors.append(self)
+
+    def detect_E(self):
+        x, y, z = self.cell
+        self.E.append(float(self.grid.E[x, y, z, 1]))
+
+    def detect_H(self):
+        x, y, z = self.cell
+        self.H.append(float(self.grid.H[x, y, z, 2]))
+
+    def detector_values(self):
+        return {"E": self.E, "H": self.H}
+
+
+class UserWall:
+    """a user boundary: a perfect-conductor wall on one x-plane (tangential E forced to zero after every E update)"""
+
+    def __init__(self, name=None):
+        self.name = name
+
+    def _register_grid(self, grid, x, y, z):
+        self.grid, self.ix = grid, x[0]
+        grid.boundaries.append(self)
+
+    def update_phi_E(self):
+        pass
+
+    def update_phi_H(self):
+        pass
+
+    def update_E(self):
+        self.grid.E[self.ix, :, :, 1:] = 0.0
+
+    def update_H(self):
+        pass
+
+    # the oracle names the same four hooks differently (oracle/yee_oracle.py, _Boundary)
+    def advance_psi_E(self, d):
+        pass
+
+    def advance_psi_H(self, d):
+        pass
+
+    def apply_E(self):
+        self.update_E()
+
+    def apply_H(self):
+        pass
+
+
+def user_plugins(fd, n=(20, 16, 14), t=3):
+    """built-in and user-defined plug-ins side by side: PMLs, a built-in object and sources, and a user object (inside
+    a PML too), a user source, a user detector and a user boundary."""
+    g = fd.Grid(shape=n, grid_spacing=77.5e-9)
+    g[0:t, :, :] = fd.PML()
+    g[:, 0:t, :] = fd.PML()
+    g[:, :, -t:] = fd.PML()
+    g[5:9, 5:9, 4:8] = fd.Object(permittivity=2.2, name="glass")
+    g[1:12, 1:7, 8:13] = UserGainObject(name="gain")
+    g[n[0] - 3, :, :] = UserWall(name="wall")
+    g[10, 8, 7] = fd.PointSource(period=13, name="pt")
+    g[12, 9, 6] = UserSquareSource(name="square")
+    g[3:17, 8, 7] = fd.LineDetector(name="line")
+    g[11, 9, 6] = UserProbe(name="probe")
+    return g

@@ -502,3 +502,41 @@ def test_float32x_error_growth_stays_flat():
         err[m] = max(scenes.rel_l2(g.E.numpy().astype(np.float64), ref.E),
                      scenes.rel_l2(g.H.numpy().astype(np.float64), ref.H))
     assert err["float32x"] <= 5e-6 and err["float32x"] < 0.5 * err["float32"], err
+
+
+def test_user_defined_plugins_are_called_like_the_reference_calls_them():
+    """objects / sources / detectors / boundaries of the user's own that follow the reference's duck-typed protocol
+    (fdtd/grid.py:279-299, 305-325) are driven per step at their place in the order -- a slow path, not a silent
+    skip -- next to the built-in plug-ins, which stay in the kernels.  Bit-identical to the oracle."""
+    def drive(fd):
+        g = scenes.user_plugins(fd)
+        kw = {} if fd is yo else {"progress_bar": False}
+        g.run(25, **kw)
+        for _ in range(10):
+            g.step()
+        out = scenes.dump(g)
+        out["probe_E"], out["probe_H"] = np.array(g.detectors[1].E), np.array(g.detectors[1].H)
+        return g, out
+    g, got = drive(use_emu("float64"))
+    assert g._engine._hooked and g._engine.desc.use_graphs == 0
+    yo.set_backend("numpy", "float64")
+    _, want = drive(yo)
+    assert len(want["probe_E"]) == 35 and float(np.abs(want["probe_E"]).max()) > 0
+    compare(got, want, 1e-12, bitwise=True)
+
+
+def test_subclass_overrides_of_builtin_plugins_are_called_too():
+    fd = use_emu("float64")
+    calls = []
+
+    class CountingDetector(fd.LineDetector):
+        def detect_E(self):
+            calls.append(self.grid.time_steps_passed)
+
+    g = scenes.pml3d(fd, n=(12, 10, 9), t=3)
+    g[2:8, 4, 4] = CountingDetector(name="counting")
+    g.run(7, progress_bar=False)
+    assert calls == list(range(7))
+    assert len(g.counting.E) == 7                       # ... and the built-in sampling still happened on the device
+    want = run_oracle(scenes.pml3d, 7, n=(12, 10, 9), t=3)
+    assert np.array_equal(g.E.numpy(), want["E"])

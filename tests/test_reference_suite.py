@@ -132,3 +132,29 @@ def test_oracle_equals_the_reference_on_random_scenes():
         assert set(got) == set(want)
         for k in want:
             assert np.array_equal(got[k], want[k], equal_nan=True), f"seed {seed} {k}: {scenes.rel_l2(got[k], want[k]):.3e}"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference is not mounted here")
+def test_user_plugins_against_the_live_reference():
+    """the user-defined plug-ins of tests/scenes.py (written against the reference's duck-typed protocol only) on the
+    unmodified reference and on this package: final fields, the built-in detector and the user's probe agree bit for
+    bit -- the drop-in holds for plug-ins the package has never seen."""
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden
+    import numpy as np
+    import scenes
+    from emu.harness import use_emu
+    ref = make_golden.load_reference()
+    ref.set_backend("numpy")
+    r = scenes.user_plugins(ref)
+    r.run(30, progress_bar=False)
+    want = scenes.dump(r)
+    g = scenes.user_plugins(use_emu("float64"))
+    g.run(30, progress_bar=False)
+    got = scenes.dump(g)
+    assert g._engine._hooked
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(np.array(g.detectors[1].E), np.array(r.detectors[1].E))
+    assert np.array_equal(np.array(g.detectors[1].H), np.array(r.detectors[1].H))
+    assert float(np.abs(np.array(r.detectors[1].E)).max()) > 0
