@@ -126,9 +126,11 @@ def build_c5(fd, nx, n=1024, balance=False, **kw):
     """configs[4]: waveguide, PML on x, periodic y and z, GRIN medium (linear ramp along y) over the middle half,
     PlaneSource, LineDetector along x."""
     import numpy as np
-    if balance:
-        kw["x_plane_cost"] = pml_plane_cost(nx)
     t = PML_CELLS if nx >= 64 else 3
+    if balance:
+        # words per cell-step of each x-plane: 18, + 8 inside an x-PML (psi), + 3 where the GRIN eps^-1 is streamed
+        kw["x_plane_cost"] = [(18.0 + 8.0 * (i < t or i >= nx - t) + 3.0 * (nx // 4 <= i < 3 * nx // 4)) / 18.0
+                              for i in range(nx)]
     g = fd.Grid(shape=(nx, n, n), grid_spacing=GRID_SPACING, **kw)
     g[0:t, :, :] = fd.PML()
     g[-t:, :, :] = fd.PML()

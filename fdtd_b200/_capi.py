@@ -54,7 +54,7 @@ class Desc(C.Structure):
                 ("courant", C.c_double), ("bg_inv_eps", C.c_double * 3), ("bg_inv_mu", C.c_double * 3),
                 ("inv_eps", _vp * 3), ("inv_eps2", _vp * 3), ("inv_eps_grid", _vp * 3), ("absorb", _vp * 3), ("absorb2", _vp * 3),
                 ("inv_mu", _vp * 3),
-                ("tile_class", _vp), ("tile_y", C.c_int32), ("tile_z", C.c_int32),
+                ("tile_class", _vp), ("plane_class", _vp), ("tile_y", C.c_int32), ("tile_z", C.c_int32),
                 ("n_slabs", C.c_int32), ("n_post", C.c_int32),
                 ("slabs", Slab * MAX_SLABS),
                 ("post_kind", C.c_int32 * MAX_POST), ("post_arg", C.c_int32 * MAX_POST),

@@ -317,11 +317,61 @@ struct ShellOpts {
 // graph_step >= 0: the launch is being captured as step `graph_step` of a replayable chunk; waveform
 // index and ring slot are then graph_step + the bases in d->dyn
 template <typename T, bool IS_E, typename A = T>
+int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
+                        int64_t graph_step, void* push_y, void* push_z, const ShellOpts* shell, bool plain);
+
+#ifndef FDTD_PLAIN_RUN_MIN
+#ifdef FDTD_EMU
+#define FDTD_PLAIN_RUN_MIN 2   // (CPU tests: small scenes must take the split path too)
+#else
+#define FDTD_PLAIN_RUN_MIN 8   // shorter runs of object-free planes are not worth a launch of their own
+#endif
+#endif
+
+// the planes [x_begin, x_end) of a half-step: one launch, or -- when the descriptor says which x-planes carry
+// material classes at all -- one launch per run of planes with / without them, the latter with the material-free
+// instantiation of the kernel
+template <typename T, bool IS_E, typename A = T>
 int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
                     int64_t graph_step = -1, void* push_y = nullptr, void* push_z = nullptr,
                     const ShellOpts* shell = nullptr) {
   if (x_begin < 0 || x_end > d->Nx || x_begin > x_end) return fail(FDTD_ERR_ARG, "plane range [%d,%d)", x_begin, x_end);
   if (x_begin == x_end) return FDTD_OK;
+  if (!d->plane_class || !d->tile_class || shell || post_is_fused(d))
+    return launch_halfstep_run<T, IS_E, A>(d, x_begin, x_end, q, slot, stream, graph_step, push_y, push_z, shell, false);
+  // the class bits this half-step reads: everything but the mu^-1 bit for E, only that bit for H
+  const unsigned char bits = IS_E ? (unsigned char)~FDTD_CLS_VARY_H : (unsigned char)FDTD_CLS_VARY_H;
+  auto is_plain = [&](int x) { return (d->plane_class[x] & bits) == 0; };
+  const int push_plane = IS_E ? 0 : d->Nx - 1;
+  int i = x_begin;
+  while (i < x_end) {
+    // the next run: planes of one kind; a short plain run is absorbed by the material run around it
+    bool plain = is_plain(i);
+    int j = i + 1;
+    while (j < x_end && is_plain(j) == plain) ++j;
+    if (plain && j - i < FDTD_PLAIN_RUN_MIN && !(i == x_begin && j == x_end)) plain = false;
+    if (!plain) {
+      for (;;) {     // extend over material planes and short plain runs
+        while (j < x_end && !is_plain(j)) ++j;
+        int k = j;
+        while (k < x_end && is_plain(k)) ++k;
+        if (k == j || k - j >= FDTD_PLAIN_RUN_MIN) break;
+        j = k;
+      }
+    }
+    const bool has = push_y && push_plane >= i && push_plane < j;
+    int rc = launch_halfstep_run<T, IS_E, A>(d, i, j, q, slot, stream, graph_step, has ? push_y : nullptr,
+                                             has ? push_z : nullptr, nullptr, plain);
+    if (rc) return rc;
+    i = j;
+  }
+  return FDTD_OK;
+}
+
+// plain: every tile of these planes is homogeneous -> no class map, no material arrays
+template <typename T, bool IS_E, typename A>
+int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
+                        int64_t graph_step, void* push_y, void* push_z, const ShellOpts* shell, bool plain) {
   Geometry g = geometry(d->dtype, d->Ny, d->Nz);
   if (shell) {
     if (shell->y0 >= shell->y1 || shell->z0 >= shell->z1) return FDTD_OK;
@@ -376,9 +426,9 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
     }
   }
   // a class map is only meaningful with the arrays it refers to
-  P.cls = d->tile_class;
-  P.cls_vary = (P.inv[0] != nullptr) ? (IS_E ? FDTD_CLS_VARY_E : FDTD_CLS_VARY_H) : 0;
-  if (P.inv[0] != nullptr && P.cls == nullptr) return fail(FDTD_ERR_ARG, "material arrays need a tile_class map");
+  P.cls = plain ? nullptr : d->tile_class;
+  P.cls_vary = (P.inv[0] != nullptr && !plain) ? (IS_E ? FDTD_CLS_VARY_E : FDTD_CLS_VARY_H) : 0;
+  if (P.inv[0] != nullptr && d->tile_class == nullptr) return fail(FDTD_ERR_ARG, "material arrays need a tile_class map");
   P.n_slabs = d->n_slabs;
   for (int s = 0; s < d->n_slabs; ++s) P.slabs[s] = slab_k<T, IS_E, A>(d->slabs[s]);
   if (!shell && post_is_fused(d)) {

@@ -33,6 +33,11 @@
 #define FDTD_PREFETCH_PLANES 1 // software prefetch into L2 this many x-planes ahead (0 = off)
 #endif
 
+#ifndef FDTD_PREFETCH_CAP
+#define FDTD_PREFETCH_CAP 0    // 1: never prefetch past the block's own x-chunk (the next chunk belongs to a block that
+                               // runs much later: by then the lines are evicted again and were fetched for nothing)
+#endif
+
 #ifndef FDTD_PREFETCH_WHAT
 #define FDTD_PREFETCH_WHAT 3   // bit 0: the differentiated field G, bit 1: the updated field F
 #endif
@@ -529,7 +534,8 @@ __global__ void __launch_bounds__(FDTD_BLOCK_THREADS, (sizeof(A) > sizeof(T) ? 2
     const unsigned cls = (MAT && P.cls) ? P.cls[(i64)i * cls_stride + cls_tile] : 0u;
 
 #if FDTD_PREFETCH_PLANES > 0
-    if (DOWN ? (i - FDTD_PREFETCH_PLANES >= 0) : (i + FDTD_PREFETCH_PLANES < P.Nx)) {
+    if (FDTD_PREFETCH_CAP ? (DOWN ? (i - FDTD_PREFETCH_PLANES >= i0) : (i + FDTD_PREFETCH_PLANES < i1))
+                          : (DOWN ? (i - FDTD_PREFETCH_PLANES >= 0) : (i + FDTD_PREFETCH_PLANES < P.Nx))) {
       const i64 pf = off + (i64)(PF_DIR * FDTD_PREFETCH_PLANES) * plane;
       if (FDTD_PREFETCH_WHAT & 1) {
         prefetch_l2(Gx + pf);

@@ -218,6 +218,11 @@ class Engine:
             d.absorb2[c] = absorb2[c].data_ptr() if absorb2 is not None else None
             d.inv_mu[c] = imu[c].data_ptr() if imu is not None else None
         d.tile_class = _ptr(cls)
+        self._plane_class = None
+        if cls is not None and cls.numel() > 0:
+            # which x-planes carry any material class at all (host): the others run the material-free kernel
+            self._plane_class = cls.view(cls.shape[0], -1).amax(dim=1).to("cpu").numpy().copy()
+            d.plane_class = self._plane_class.ctypes.data
         self._keep += [ie_eff, absorb, cls, ie2, absorb2]
         self.tile_class = cls
 

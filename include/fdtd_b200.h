@@ -186,6 +186,10 @@ typedef struct fdtd_desc {
   const void* absorb2[3];      /* the same for the SECOND object covering a cell; or NULL */
   const void* inv_mu[3];       /* or NULL */
   const uint8_t* tile_class;   /* device [Nx][tiles_y][tiles_z], or NULL = every tile homogeneous */
+  const uint8_t* plane_class;  /* HOST [Nx], optional: the OR of tile_class over each x-plane.  Runs of planes without any
+                                  class bit are then launched with the material-free instantiation of the kernel
+                                  (no coefficient / object code, fewer registers): objects confined to a part of
+                                  the x-range cost nothing outside it */
   int32_t tile_y, tile_z;      /* tile extents in cells, as returned by fdtd_tile_shape */
   int32_t n_slabs;
   int32_t n_post;

@@ -39,6 +39,9 @@ VARIANTS = {
     "pipe_r4l31_mb2": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
     "pipe_r7l31_mb2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
     "fz_r4l31_mb4": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_MIN_BLOCKS=4"],
+    "pfcap": ["-DFDTD_PREFETCH_CAP=1"],
+    "pfcap_pf2": ["-DFDTD_PREFETCH_CAP=1", "-DFDTD_PREFETCH_PLANES=2"],
+    "nopf": ["-DFDTD_PREFETCH_PLANES=0"],
     "post_inline": ["-DFDTD_POST_INLINE=1"],
     "hdown": ["-DFDTD_H_DOWNWARD=1"],
     "fz_pf0": ["-DFDTD_FUSED_PREFETCH=0"],

@@ -540,3 +540,32 @@ def test_subclass_overrides_of_builtin_plugins_are_called_too():
     assert len(g.counting.E) == 7                       # ... and the built-in sampling still happened on the device
     want = run_oracle(scenes.pml3d, 7, n=(12, 10, 9), t=3)
     assert np.array_equal(g.E.numpy(), want["E"])
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_launches_split_into_runs_of_planes_with_and_without_objects(dtype):
+    """with unfolded sources the half-step is launched per run of x-planes: the material-free instantiation where no
+    tile of a plane carries a class bit (objects confined to part of the x-range), the general one elsewhere.
+    Same results as the single launch, bit for bit, and as the oracle."""
+    import bench
+
+    def build(fd):
+        rs = np.random.RandomState(3)
+        g = bench.build_c3(fd, 40)                       # config 3's structure: absorber slab, anisotropic lens
+        g[2:4, 10:20, 10:30] = fd.Object(permittivity=1.0 + rs.rand(2, 10, 20))       # a short run near the x-PML
+        g[36:40, 5:9, 5:9] = fd.Object(permittivity=3.0)                              # reaching the last plane
+        return g
+
+    outs = []
+    for fold in (False, True):
+        g = build(use_emu(dtype))
+        g._fuse_post = fold
+        g.run(18, progress_bar=False)
+        for _ in range(4):
+            g.step()
+        pc = g._engine._plane_class
+        assert pc is not None and (pc == 0).any() and (pc != 0).any()
+        outs.append(scenes.dump(g))
+    compare(outs[0], outs[1], 0.0, bitwise=True)
+    want = run_oracle(build, 22, dtype)
+    compare(outs[0], want, 1e-12 if dtype == "float64" else 1e-5, bitwise=True)
