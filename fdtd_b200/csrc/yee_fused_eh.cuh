@@ -587,6 +587,21 @@ __global__ void __launch_bounds__(32 * FUSED_RT_WARPS, FDTD_FUSED_RT_MIN_BLOCKS)
 #ifndef FDTD_FUSED_PIPE_MIN_BLOCKS
 #define FDTD_FUSED_PIPE_MIN_BLOCKS 3
 #endif
+#ifndef FDTD_FUSED_PIPE_PSI_PREFETCH
+#define FDTD_FUSED_PIPE_PSI_PREFETCH 2   // CPML psi of the thread's cells is prefetched (L1) this many planes ahead: the psi
+                                         // loads are the only global loads left on the per-plane critical path, and one
+                                         // thread waiting for them holds its whole block at the barrier -- a quarter of all
+                                         // blocks touch a z slab (profiles/r2_pipe_stalls.txt: 13 % of all stall samples on
+                                         // the first use of psi / the b table).  0 = off
+#endif
+#ifndef FDTD_FUSED_PIPE_PSI_LEVEL
+#define FDTD_FUSED_PIPE_PSI_LEVEL 1      // 1: prefetch.global.L1, 2: prefetch.global.L2
+#endif
+#ifndef FDTD_FUSED_PIPE_PREFETCH
+#define FDTD_FUSED_PIPE_PREFETCH 0   // L2 prefetch of the six input streams this many planes ahead of the march (0 = off):
+                                     // the two planes the cp.async stages hold in flight are ~100 KB per SM, about half
+                                     // of what saturates HBM; prefetches cost neither registers nor shared memory
+#endif
 
 template <typename T, int VEC>
 struct FusedPipeLayout {
@@ -683,6 +698,27 @@ FDTD_DEV void fused_stage_issue(const FusedParams<T>& P, T* stage, i64 off, int 
   }
 }
 
+// psi index of the VEC cells of a thread at plane i in slab S (the layouts of include/fdtd_b200.h, fdtd_slab)
+template <typename T, int VEC>
+FDTD_DEV i64 fused_psi_index(const typename FusedParams<T>::Slab& S, int i, int j, int k0, i64 plane, i64 p, int Ny,
+                             int Nz) {
+  if (S.axis == 0) return (i64)(i - S.lo) * plane + p;
+  if (S.axis == 1) return ((i64)i * S.t + (j - S.lo)) * Nz + k0;
+  return ((i64)i * Ny + j) * S.tp + (k0 - S.lo_al);
+}
+
+FDTD_DEV void fused_prefetch(const void* a) {
+#if !defined(FDTD_EMU)
+#if FDTD_FUSED_PIPE_PSI_LEVEL == 1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+#else
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+#endif
+#else
+  (void)a;
+#endif
+}
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE_MIN_BLOCKS)
     fused_eh_pipe_kernel(const __grid_constant__ FusedParams<T> P) {
@@ -747,6 +783,43 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
         fused_stage_issue<T, VEC>(P, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane + p, r, l, inside, row_m1, vec_m1);
       FDTD_CP_ASYNC_COMMIT();
     }
+#if FDTD_FUSED_PIPE_PSI_PREFETCH > 0
+    if (inside && active && (sl_hit | xs_bits) != 0) {
+      // psi_E of plane i + PP and psi_H of plane i + PP - 1 (the H update lags one plane) of the slabs this thread's
+      // cells lie in
+      const int ip = i + FDTD_FUSED_PIPE_PSI_PREFETCH;
+      for (int s = 0; s < P.n_sl; ++s) {
+        const typename FusedParams<T>::Slab& S = P.sl[s];
+        const bool yz = ((sl_hit >> s) & 1u) != 0;
+        if (!yz && S.axis != 0) continue;
+        if (ip < xb && ip < P.x1 && (yz || (ip >= S.lo && ip < S.lo + S.t))) {
+          const i64 idx = fused_psi_index<T, VEC>(S, ip, j, k0, plane, p, P.Ny, Nz);
+          fused_prefetch(S.psiE_in + idx);
+          fused_prefetch(S.psiE_in + S.count + idx);
+        }
+        const int ih = ip - 1;      // (psi_H belongs to the owner of the cell only: the halo threads never touch it)
+        if (core && ih >= xa && ih < xb && (yz || (ih >= S.lo && ih < S.lo + S.t))) {
+          const i64 idx = fused_psi_index<T, VEC>(S, ih, j, k0, plane, p, P.Ny, Nz);
+          fused_prefetch(S.psiH + idx);
+          fused_prefetch(S.psiH + S.count + idx);
+        }
+      }
+    }
+#endif
+#if FDTD_FUSED_PIPE_PREFETCH > 0 && !defined(FDTD_EMU)
+    {
+      // one prefetch per 128-byte line of the tile row (every eighth lane, and the last one: rows start unaligned)
+      const int ip = i + FDTD_FUSED_PIPE_PREFETCH;
+      if (inside && ip <= xb && ip < P.x1 && ((l & 7) == 0 || l == L)) {
+        const i64 po = (i64)ip * plane + p;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Hin[c] + po));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Ein[c] + po));
+        }
+      }
+    }
+#endif
     const T* sH = stages + (i % 3) * Lay::STAGE_WORDS;
     const T* sE = sH + Lay::H_WORDS;
     unsigned hit_now = sl_hit;   // + the x slabs plane i lies in (the same for the whole block)

@@ -39,6 +39,19 @@ VARIANTS = {
     "pipe_r4l31_mb2": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
     "pipe_r7l31_mb2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
     "fz_r4l31_mb4": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_MIN_BLOCKS=4"],
+    "pipe_r7l31_mb2_pf3": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=3"],
+    "pipe_r7l31_mb2_pf4": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=4"],
+    "pipe_r7l31_mb2_pf6": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=6"],
+    "pipe_r7l31_mb2_psi0": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PSI_PREFETCH=0"],
+    "pipe_r7l31_mb2_psi2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PSI_PREFETCH=2"],
+    "pipe_r7l31_mb2_psi3": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PSI_PREFETCH=3"],
+    "pipe_r7l31_mb2_psi2L2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PSI_PREFETCH=2", "-DFDTD_FUSED_PIPE_PSI_LEVEL=2"],
+    "pipe_r15l31_mb1": ["-DFDTD_FUSED_ROWS=15", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=1"],
+    "pipe_r15l31_mb1_pf4": ["-DFDTD_FUSED_ROWS=15", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=1", "-DFDTD_FUSED_PIPE_PREFETCH=4"],
+    "pipe_r3l31_mb4": ["-DFDTD_FUSED_ROWS=3", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4"],
+    "pipe_r3l31_mb4_pf4": ["-DFDTD_FUSED_ROWS=3", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4", "-DFDTD_FUSED_PIPE_PREFETCH=4"],
+    "fz_r7l31_mb2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_MIN_BLOCKS=2"],
+    "fz_r7l31_mb3": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_MIN_BLOCKS=3"],
     "pfcap": ["-DFDTD_PREFETCH_CAP=1"],
     "pfcap_pf2": ["-DFDTD_PREFETCH_CAP=1", "-DFDTD_PREFETCH_PLANES=2"],
     "nopf": ["-DFDTD_PREFETCH_PLANES=0"],
@@ -101,6 +114,8 @@ def build():
         for n, l in enumerate(lines):
             if "Compiling entry function" in l and "fused_eh_rt_kernelIfLi4" in l and name.startswith("rt_"):
                 print(name, "FUSED-RT", " | ".join(x.strip() for x in lines[n + 1:n + 4]))
+            elif "Compiling entry function" in l and "fused_eh_pipe_kernelIfLi4" in l and name.startswith("pipe"):
+                print(name, "PIPE", " | ".join(x.strip() for x in lines[n + 1:n + 4]))
             elif "Compiling entry function" in l and ("fused_eh_kernelIfLi4" in l) and name.startswith("fz"):
                 print(name, "FUSED", " | ".join(x.strip() for x in lines[n + 1:n + 4]))
             elif "Compiling entry function" in l and not name.startswith("fz") and ("halfstep_kernelIfLi4ELb" in l or ("MAX_VEC_F32=2" in " ".join(defs) and "halfstep_kernelIfLi2ELb" in l)):
