@@ -305,20 +305,11 @@ fdtd::SlabK<T, A> slab_k(const fdtd_slab& S) {
   return k;
 }
 
-// a shell launch of a temporally fused step: a cell box in y / z, explicit in / out / curl-source buffers, and no
-// folded sources or detectors (the fused step runs them itself)
-struct ShellOpts {
-  int y0, y1, z0, z1;
-  void* const* Fin;
-  void* const* Fout;
-  void* const* G;
-};
-
 // graph_step >= 0: the launch is being captured as step `graph_step` of a replayable chunk; waveform
 // index and ring slot are then graph_step + the bases in d->dyn
 template <typename T, bool IS_E, typename A = T>
 int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
-                        int64_t graph_step, void* push_y, void* push_z, const ShellOpts* shell, bool plain);
+                        int64_t graph_step, void* push_y, void* push_z, bool plain);
 
 #ifndef FDTD_PLAIN_RUN_MIN
 #ifdef FDTD_EMU
@@ -333,12 +324,11 @@ int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, i
 // instantiation of the kernel
 template <typename T, bool IS_E, typename A = T>
 int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
-                    int64_t graph_step = -1, void* push_y = nullptr, void* push_z = nullptr,
-                    const ShellOpts* shell = nullptr) {
+                    int64_t graph_step = -1, void* push_y = nullptr, void* push_z = nullptr) {
   if (x_begin < 0 || x_end > d->Nx || x_begin > x_end) return fail(FDTD_ERR_ARG, "plane range [%d,%d)", x_begin, x_end);
   if (x_begin == x_end) return FDTD_OK;
-  if (!d->plane_class || !d->tile_class || shell || post_is_fused(d))
-    return launch_halfstep_run<T, IS_E, A>(d, x_begin, x_end, q, slot, stream, graph_step, push_y, push_z, shell, false);
+  if (!d->plane_class || !d->tile_class || post_is_fused(d))
+    return launch_halfstep_run<T, IS_E, A>(d, x_begin, x_end, q, slot, stream, graph_step, push_y, push_z, false);
   // the class bits this half-step reads: everything but the mu^-1 bit for E, only that bit for H
   const unsigned char bits = IS_E ? (unsigned char)~FDTD_CLS_VARY_H : (unsigned char)FDTD_CLS_VARY_H;
   auto is_plain = [&](int x) { return (d->plane_class[x] & bits) == 0; };
@@ -361,7 +351,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
     }
     const bool has = push_y && push_plane >= i && push_plane < j;
     int rc = launch_halfstep_run<T, IS_E, A>(d, i, j, q, slot, stream, graph_step, has ? push_y : nullptr,
-                                             has ? push_z : nullptr, nullptr, plain);
+                                             has ? push_z : nullptr, plain);
     if (rc) return rc;
     i = j;
   }
@@ -371,22 +361,8 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
 // plain: every tile of these planes is homogeneous -> no class map, no material arrays
 template <typename T, bool IS_E, typename A>
 int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
-                        int64_t graph_step, void* push_y, void* push_z, const ShellOpts* shell, bool plain) {
+                        int64_t graph_step, void* push_y, void* push_z, bool plain) {
   Geometry g = geometry(d->dtype, d->Ny, d->Nz);
-  if (shell) {
-    if (shell->y0 >= shell->y1 || shell->z0 >= shell->z1) return FDTD_OK;
-    // tile shape for the box: as few idle lanes as possible in a narrow z range
-    int nvz = (shell->z1 - shell->z0 + g.vec - 1) / g.vec;
-    g.lanes_z = pow2_ceil(nvz);
-    if (g.lanes_z > 32) g.lanes_z = 32;
-    g.lanes_shift = 0;
-    while ((1 << g.lanes_shift) < g.lanes_z) ++g.lanes_shift;
-    g.rows = FDTD_BLOCK_THREADS / g.lanes_z;
-    int ny2 = pow2_ceil(shell->y1 - shell->y0);
-    if (g.rows > ny2) g.rows = ny2;
-    g.tile_y = g.rows;
-    g.tile_z = g.lanes_z * g.vec;
-  }
   fdtd::HalfStepParams<T, A> P;
   memset(&P, 0, sizeof(P));
   P.Nx = d->Nx;
@@ -397,17 +373,16 @@ int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, i
   P.x_begin = x_begin;
   P.x_end = x_end;
   P.x_chunk = d->x_chunk > 0 ? d->x_chunk
-                             : default_x_chunk(g, x_end - x_begin, shell ? shell->y1 - shell->y0 : d->Ny,
-                                               shell ? shell->z1 - shell->z0 : d->Nz);
+                             : default_x_chunk(g, x_end - x_begin, d->Ny, d->Nz);
   P.lanes_z = g.lanes_z;
   P.lanes_shift = g.lanes_shift;
   P.rows = g.rows;
   P.plane = d->plane;
   P.sc = (A)d->courant;
-  P.y_begin = shell ? shell->y0 : 0;
-  P.y_end = shell ? shell->y1 : d->Ny;
-  P.z_begin = shell ? shell->z0 : 0;
-  P.z_end = shell ? shell->z1 : d->Nz;
+  P.y_begin = 0;
+  P.y_end = d->Ny;
+  P.z_begin = 0;
+  P.z_end = d->Nz;
   for (int c = 0; c < 3; ++c) {
     P.F[c] = (T*)(IS_E ? d->E[c] : d->H[c]);
     P.Fo[c] = P.F[c];
@@ -419,11 +394,6 @@ int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, i
     P.inv2[c] = IS_E ? (const A*)d->inv_eps2[c] : nullptr;
     P.absorb[c] = IS_E ? (const A*)d->absorb[c] : nullptr;
     P.absorb2[c] = IS_E ? (const A*)d->absorb2[c] : nullptr;
-    if (shell) {
-      P.F[c] = (T*)shell->Fin[c];
-      P.Fo[c] = (T*)shell->Fout[c];
-      P.G[c] = (const T*)shell->G[c];
-    }
   }
   // a class map is only meaningful with the arrays it refers to
   P.cls = plain ? nullptr : d->tile_class;
@@ -431,7 +401,7 @@ int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, i
   if (P.inv[0] != nullptr && d->tile_class == nullptr) return fail(FDTD_ERR_ARG, "material arrays need a tile_class map");
   P.n_slabs = d->n_slabs;
   for (int s = 0; s < d->n_slabs; ++s) P.slabs[s] = slab_k<T, IS_E, A>(d->slabs[s]);
-  if (!shell && post_is_fused(d)) {
+  if (post_is_fused(d)) {
     P.dyn = graph_step >= 0 ? (const i64*)d->dyn : nullptr;
     for (int n = 0; n < d->n_sources; ++n) {
       const fdtd_source& S = d->sources[n];
@@ -991,49 +961,23 @@ int fdtd_halo_refresh(const fdtd_desc* d, fdtd_halo* h, void* stream) {
 // ---- temporally fused E+H steps (yee_fused_eh.cuh) --------------------------------------------------------
 extern "C++" {
 namespace {
-struct InteriorBox {
-  int x0, x1, y0, y1, z0, z1;
-};
-
-// the largest box free of CPML cells and of the grid faces (where the curls are masked); z aligned to the vector
-bool interior_box(const fdtd_desc* d, int vec, InteriorBox* b) {
-  int lo[3] = {1, 1, 1}, hi[3] = {d->Nx - 1, d->Ny - 1, d->Nz - 1};
-  const bool whole_rows = d->fuse_eh == 3;   // the pipelined kernel handles every slab and face itself: no shell
-  for (int s = 0; s < d->n_slabs; ++s) {
-    const fdtd_slab& S = d->slabs[s];
-    if (!S.fused) return false;
-    if (whole_rows) {
-      if (!d->psi_E2[s] && S.psi_count > 0) return false;
-      continue;
-    }
-    if (S.lo == 0) {
-      if (S.thickness > lo[S.axis]) lo[S.axis] = S.thickness;
-    } else if (S.lo < hi[S.axis]) {
-      hi[S.axis] = S.lo;
-    }
-  }
-  b->x0 = whole_rows ? 0 : lo[0];
-  b->x1 = whole_rows ? d->Nx : hi[0];
-  b->y0 = whole_rows ? 0 : lo[1];
-  b->y1 = whole_rows ? d->Ny : hi[1];
-  b->z0 = whole_rows ? 0 : (lo[2] + vec - 1) / vec * vec;
-  b->z1 = whole_rows ? d->Nz : hi[2] / vec * vec;
+#ifndef FDTD_FUSE_EH_MIN_CELLS
 #ifdef FDTD_EMU
-  // (CPU tests: any non-empty box, so that small grids with partial tiles exercise every branch)
-  return b->x1 - b->x0 >= 2 && b->y1 - b->y0 >= 1 && b->z1 - b->z0 >= vec;
+#define FDTD_FUSE_EH_MIN_CELLS 0
 #else
-  // below these extents the shell dominates and the ordinary half-steps are faster
-  return b->x1 - b->x0 >= 8 && b->y1 - b->y0 >= 8 && b->z1 - b->z0 >= 32 * vec;
+#define FDTD_FUSE_EH_MIN_CELLS 600000000LL   // below, the 7 x 124-cell tiles quantise badly and the two half-steps win
 #endif
-}
+#endif
 
-bool fuse_eh_eligible(const fdtd_desc* d, InteriorBox* box) {
+// fuse_eh = 1: wherever it is legal; fuse_eh = 2: only where it is also faster (large grids)
+bool fuse_eh_eligible(const fdtd_desc* d) {
   if (!d->fuse_eh || d->dtype == FDTD_F32X) return false;
   for (int c = 0; c < 3; ++c)
     if (!d->E2[c] || !d->H2[c] || d->inv_eps[c] || d->inv_mu[c] || d->absorb[c]) return false;
-  if (d->Nx != d->Nx_global || d->n_post != 0) return false;
+  if (d->Nx != d->Nx_global || d->n_post != 0 || d->n_deep != 0) return false;
   const int vec = d->dtype == FDTD_F32 ? 4 : 2;
   if (d->Nz % vec) return false;
+  if (d->fuse_eh == 2 && (int64_t)d->Nx * d->Ny * d->Nz < FDTD_FUSE_EH_MIN_CELLS) return false;
   int nsrc = 0;
   for (int n = 0; n < d->n_sources; ++n) {
     if (d->sources[n].kind != FDTD_SRC_POINTS || d->sources[n].field != 0) return false;
@@ -1042,26 +986,24 @@ bool fuse_eh_eligible(const fdtd_desc* d, InteriorBox* box) {
   if (nsrc > FDTD_FUSED_MAX) return false;
   for (int n = 0; n < d->n_detectors; ++n)
     if (d->detectors[n].kind != FDTD_DET_FIELD) return false;
-  return interior_box(d, vec, box);
+  for (int s = 0; s < d->n_slabs; ++s) {
+    // the kernel applies every CPML correction itself (slabs registered after a periodic boundary are post ops, and
+    // periodic boundaries are excluded above anyway) and needs the second psi_E buffer
+    if (!d->slabs[s].fused || (d->slabs[s].psi_count > 0 && !d->psi_E2[s])) return false;
+  }
+#ifndef FDTD_EMU
+  return d->Nx >= 8 && d->Ny >= 8 && d->Nz >= 32 * vec;
+#else
+  return d->Nx >= 2;     // (CPU tests: small grids with partial tiles exercise every branch)
+#endif
 }
 
-// one full step reading (Ein, Hin) and writing (Eout, Hout)
+// one full step reading (Ein, Hin) and writing (Eout, Hout); parity 0: psi_E -> psi_E2, 1: back
 template <typename T>
-int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, void* const* Eout, void* const* Hin,
-                  void* const* Hout, int64_t q, int64_t slot, void* stream, int parity) {
+int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void* const* Hin, void* const* Hout,
+                  int64_t q, int64_t slot, void* stream, int parity) {
   const int Nx = d->Nx, Ny = d->Ny, Nz = d->Nz;
-  // the shell: six boxes around the interior box
-  const int boxes[6][6] = {{0, B.x0, 0, Ny, 0, Nz},        {B.x1, Nx, 0, Ny, 0, Nz},
-                           {B.x0, B.x1, 0, B.y0, 0, Nz},   {B.x0, B.x1, B.y1, Ny, 0, Nz},
-                           {B.x0, B.x1, B.y0, B.y1, 0, B.z0}, {B.x0, B.x1, B.y0, B.y1, B.z1, Nz}};
   int rc;
-  // 1. E half-step on the shell (CPML, boundary masks): A -> B
-  for (int n = 0; n < 6; ++n) {
-    ShellOpts o{boxes[n][2], boxes[n][3], boxes[n][4], boxes[n][5], Ein, Eout, Hin};
-    rc = launch_halfstep<T, true>(d, boxes[n][0], boxes[n][1], q, slot, stream, -1, nullptr, nullptr, &o);
-    if (rc) return rc;
-  }
-  // 2. sources: shell points here, interior points inside the fused kernel
   fdtd::FusedParams<T> P;
   memset(&P, 0, sizeof(P));
   for (int n = 0; n < d->n_sources; ++n) {
@@ -1070,14 +1012,6 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
     if (w < 0 || w >= S.wave_len)
       return fail(FDTD_ERR_ARG, "source %d: step %lld outside its waveform table", n, (long long)q);
     if (S.n == 0) continue;
-    const bool whole_grid = B.x0 == 0 && B.x1 == Nx && B.y0 == 0 && B.y1 == Ny && B.z0 == 0 && B.z1 == Nz;
-    if (!whole_grid) {
-      FDTD_LAUNCH((fdtd::source_points_outside_kernel<T>), dim3(blocks_for(S.n)), dim3(256), stream, (T*)Eout[S.comp],
-                  (const i64*)S.idx, (const T*)S.profile, S.n, (const T*)S.wave, (i64)w, (i64)d->plane, Nz, B.x0, B.x1,
-                  B.y0, B.y1, B.z0, B.z1);
-      rc = check_launch("shell source");
-      if (rc) return rc;
-    }
     fdtd::SrcK<T>& K = P.src[P.n_src++];
     K.kind = S.kind;
     K.comp = S.comp;
@@ -1088,12 +1022,12 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
     K.wave = (const T*)S.wave;
     K.w = w;
   }
-  // 3. the interior: E and H in one pass
   constexpr int VEC = sizeof(T) == 4 ? 4 : 2;
+  P.Nx = Nx;
   P.Ny = Ny;
   P.Nz = Nz;
   P.plane = d->plane;
-  P.x0 = B.x0; P.x1 = B.x1; P.y0 = B.y0; P.y1 = B.y1; P.z0 = B.z0; P.z1 = B.z1;
+  P.x0 = 0; P.x1 = Nx; P.y0 = 0; P.y1 = Ny; P.z0 = 0; P.z1 = Nz;
   P.x_chunk = d->x_chunk > 0 ? d->x_chunk : 32;
   for (int c = 0; c < 3; ++c) {
     P.Ein[c] = (const T*)Ein[c];
@@ -1103,69 +1037,46 @@ int fused_eh_step(const fdtd_desc* d, const InteriorBox& B, void* const* Ein, vo
     P.ce[c] = rounded_product<T>(d->courant, d->bg_inv_eps[c]);
     P.ch[c] = rounded_product<T>(d->courant, d->bg_inv_mu[c]);
   }
-  const unsigned chunks = (B.x1 - B.x0 + P.x_chunk - 1) / P.x_chunk;
-  if (d->fuse_eh == 3) {
-    // every slab inside the kernel, registration order: psi_E read from one buffer and written to the other
-    // (parity 0: psi_E -> psi_E2)
-    P.Nx = Nx;
-    for (int s = 0; s < d->n_slabs; ++s) {
-      const fdtd_slab& S = d->slabs[s];
-      if (S.psi_count == 0) continue;
-      typename fdtd::FusedParams<T>::Slab& K = P.sl[P.n_sl++];
-      K.axis = S.axis;
-      K.lo = S.lo;
-      K.t = S.thickness;
-      K.lo_al = z_slab_lo(S);
-      K.tp = z_slab_row(S);
-      K.count = S.psi_count;
-      K.psiE_in = (const T*)(parity == 0 ? S.psi_E : d->psi_E2[s]);
-      K.psiE_out = (T*)(parity == 0 ? d->psi_E2[s] : S.psi_E);
-      K.psiH = (T*)S.psi_H;
-      K.bE = (const T*)S.bE;
-      K.cE = (const T*)S.cE;
-      K.bH = (const T*)S.bH;
-      K.cH = (const T*)S.cH;
-    }
-    // the pipelined variant: inputs staged in shared memory by cp.async two planes ahead
-    using Lay = fdtd::FusedPipeLayout<T, VEC>;
-    dim3 grid((B.z1 - B.z0 + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC),
-              (B.y1 - B.y0 + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);
-    dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
-#ifndef FDTD_EMU
-    static bool configured = false;      // (per instantiation: one kernel function each)
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::BYTES);
-      if (e != cudaSuccess) return fail(FDTD_ERR_CUDA, "cudaFuncSetAttribute(smem %zu): %s", Lay::BYTES, cudaGetErrorString(e));
-      // several blocks per SM only fit with the shared-memory carve-out at its maximum
-      cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           (int)cudaSharedmemCarveoutMaxShared);
-      configured = true;
-    }
-#endif
-    FDTD_LAUNCH_SMEM((fdtd::fused_eh_pipe_kernel<T, VEC>), grid, block, Lay::BYTES, stream, P);
-  } else if (d->fuse_eh != 2) {
-    // the shared-memory variant (one barrier per plane): the faster one so far (profiles/r1_fused_rt.log)
-    dim3 grid((B.z1 - B.z0 + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC),
-              (B.y1 - B.y0 + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);
-    dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
-    FDTD_LAUNCH_SYNC((fdtd::fused_eh_kernel<T, VEC>), grid, block, stream, P);
-  } else {
-    // the register-tiled variant: a thread owns R rows of VEC cells, no communication between threads
-    constexpr int R = fdtd::FUSED_RT_R, WARPS = fdtd::FUSED_RT_WARPS;
-    dim3 grid((B.z1 - B.z0 + 32 * VEC - 1) / (32 * VEC), (B.y1 - B.y0 + WARPS * R - 1) / (WARPS * R), chunks);
-    dim3 block(32 * WARPS);
-    FDTD_LAUNCH((fdtd::fused_eh_rt_kernel<T, VEC, R>), grid, block, stream, P);
+  // every slab inside the kernel, registration order: psi_E read from one buffer and written to the other
+  for (int s = 0; s < d->n_slabs; ++s) {
+    const fdtd_slab& S = d->slabs[s];
+    if (S.psi_count == 0) continue;
+    typename fdtd::FusedParams<T>::Slab& K = P.sl[P.n_sl++];
+    K.axis = S.axis;
+    K.lo = S.lo;
+    K.t = S.thickness;
+    K.lo_al = z_slab_lo(S);
+    K.tp = z_slab_row(S);
+    K.count = S.psi_count;
+    K.psiE_in = (const T*)(parity == 0 ? S.psi_E : d->psi_E2[s]);
+    K.psiE_out = (T*)(parity == 0 ? d->psi_E2[s] : S.psi_E);
+    K.psiH = (T*)S.psi_H;
+    K.bE = (const T*)S.bE;
+    K.cE = (const T*)S.cE;
+    K.bH = (const T*)S.bH;
+    K.cH = (const T*)S.cH;
   }
+  using Lay = fdtd::FusedPipeLayout<T, VEC>;
+  const unsigned chunks = (Nx + P.x_chunk - 1) / P.x_chunk;
+  dim3 grid((Nz + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC), (Ny + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);
+  dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
+  if (grid.y > 65535u || grid.z > 65535u) return fail(FDTD_ERR_UNSUPPORTED, "grid too large for one launch");
+#ifndef FDTD_EMU
+  static bool configured = false;      // (per instantiation: one kernel function each)
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::BYTES);
+    if (e != cudaSuccess) return fail(FDTD_ERR_CUDA, "cudaFuncSetAttribute(smem %zu): %s", Lay::BYTES, cudaGetErrorString(e));
+    // two blocks per SM only fit with the shared-memory carve-out at its maximum
+    cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+#endif
+  FDTD_LAUNCH_SMEM((fdtd::fused_eh_pipe_kernel<T, VEC>), grid, block, Lay::BYTES, stream, P);
   rc = check_launch("fused_eh");
   if (rc) return rc;
-  // 4. H half-step on the shell: A -> B, curls from the new E
-  for (int n = 0; n < 6; ++n) {
-    ShellOpts o{boxes[n][2], boxes[n][3], boxes[n][4], boxes[n][5], Hin, Hout, Eout};
-    rc = launch_halfstep<T, false>(d, boxes[n][0], boxes[n][1], q, slot, stream, -1, nullptr, nullptr, &o);
-    if (rc) return rc;
-  }
-  // 5. detectors on the new fields
+  // detectors on the new fields
   for (int n = 0; n < d->n_detectors; ++n) {
     const fdtd_detector& D = d->detectors[n];
     if (D.n == 0) continue;
@@ -1269,8 +1180,7 @@ int graph_for(const fdtd_desc* d, cudaGraphExec_t* out) {
 int fdtd_fuse_eh_active(const fdtd_desc* d) {
   int rc = validate(d);
   if (rc) return rc;
-  InteriorBox box;
-  return fuse_eh_eligible(d, &box) ? 1 : 0;
+  return fuse_eh_eligible(d) ? 1 : 0;
 }
 
 int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void* stream) {
@@ -1282,16 +1192,15 @@ int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void
   int64_t s = 0;
   {
     // pairs of temporally fused steps: A -> B -> A, so the caller's buffers hold the result again
-    InteriorBox box;
-    if (nsteps >= 2 && fuse_eh_eligible(d, &box)) {
+    if (nsteps >= 2 && fuse_eh_eligible(d)) {
       for (; s + 2 <= nsteps; s += 2) {
         rc = d->dtype == FDTD_F32
-                 ? fused_eh_step<float>(d, box, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream, 0)
-                 : fused_eh_step<double>(d, box, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream, 0);
+                 ? fused_eh_step<float>(d, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream, 0)
+                 : fused_eh_step<double>(d, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream, 0);
         if (rc) return rc;
         rc = d->dtype == FDTD_F32
-                 ? fused_eh_step<float>(d, box, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream, 1)
-                 : fused_eh_step<double>(d, box, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream, 1);
+                 ? fused_eh_step<float>(d, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream, 1)
+                 : fused_eh_step<double>(d, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream, 1);
         if (rc) return rc;
       }
     }

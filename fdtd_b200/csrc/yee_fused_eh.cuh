@@ -1,35 +1,24 @@
-// yee_fused_eh.cuh -- single-pass E+H update of the homogeneous interior (temporal fusion).
+// yee_fused_eh.cuh -- single-pass E+H update of a whole homogeneous grid (temporal fusion).
 //
 // The two-half-step algorithm moves 18 words per cell and step (E half-step: read H, read E, write E; H half-step:
 // read E, read H, write H).  Here a block marching along x updates E[i] and, one plane behind, H[i-1] in the same
 // pass, so that every field word is read once and written once per STEP: 12 words.  What makes this legal:
 //   * H[i-1]'s curl needs E_new of the y+1 / z+1 neighbours.  Inside the tile they come through shared memory;
-//     at the tile edge a one-cell halo of E_new is recomputed by extra threads (17x17 threads for a 16x16 core),
-//     or -- where the halo cell lies outside the interior box -- read back from memory, where the shell launches
-//     (the ordinary half-step kernel on the PML / boundary shell) have already put it;
+//     at the tile edge a one-cell halo of E_new is recomputed by one extra row and one extra lane of threads;
 //   * blocks are not synchronised with each other, so nothing may be updated in place: E and H are ping-pong
-//     buffers (all kernels of a fused step read buffer A and write buffer B; an even number of fused steps ends
-//     in the caller's buffers, an odd remainder is run with the ordinary in-place kernels);
-//   * the box is free of CPML cells, material arrays and boundary masks, so a halo cell's E_new needs no state;
-//     E point sources inside the box are applied to every recomputed value (owner and halo alike).
+//     buffers (a fused step reads buffer A and writes buffer B; an even number of fused steps ends in the caller's
+//     buffers, an odd remainder is run with the ordinary in-place kernels), and so is psi_E (halo cells recompute
+//     E_new from the OLD psi_E while the owner writes the new one); psi_H is owner-only and stays in place;
+//   * every CPML slab (registration order) and the masked one-sided differences on the six faces are handled inside
+//     the kernel: one launch per step, no shell; E point sources are applied to every recomputed value.
 // Arithmetic per cell is the same as in halfstep_kernel, operation by operation: results are bit-identical
 // (tests/test_gpu_parity.py::test_temporally_fused_steps_equal_two_half_steps).
 //
-// STATUS (round 1): correct, opt-in (FDTD_B200_FUSE_EH=1), NOT yet faster.  1024^3 f32 on one B200
-// (profiles/r1_fused_eh_launches.csv, 16x16 tile): the fused kernel moves 51.8 GB in 10.8 ms (4.8 TB/s -- the
-// barrier per plane hides latency worse than the barrier-free streaming kernel's 6.1 TB/s), the twelve shell
-// launches add 2.6 ms, 1.7 ms of which in the two 12-cell-wide z strips whose 48-byte rows waste DRAM sectors
-// 4x.  Best tile (4x32 lanes): 12.8 ms per step against 12.7 ms for the two half-steps.  Tried without gain:
-// L2 prefetch, 3 blocks/SM, register prefetch of the next plane across the barrier (spills).  To win it needs
-// the inputs staged by TMA / cp.async in shared memory and the z strips handled inside the fused kernel.
+// History (profiles/README.md): round 1 had three variants -- (1) shared-memory exchange with direct global loads on
+// the CPML-free interior plus twelve shell launches of the ordinary kernel, (2) a register-tiled kernel without any
+// inter-thread communication, (3) this one.  On the B200 at 1024^3 f32 they ran 12.74 / 15.0 / 11.69 ms per step
+// against 12.62 for the two half-steps (round 2, profiles/r2_fused_variants.txt); (1) and (2) were deleted.
 #pragma once
-
-#ifndef FDTD_FUSED_MIN_BLOCKS
-#define FDTD_FUSED_MIN_BLOCKS 4
-#endif
-#ifndef FDTD_FUSED_PREFETCH
-#define FDTD_FUSED_PREFETCH 0   // L2 prefetch of the six input streams this many planes ahead (measured: hurts)
-#endif
 
 namespace fdtd {
 
@@ -46,10 +35,8 @@ struct FusedParams {
   T ce[3], ch[3];  // sc * background eps^-1 / mu^-1, rounded as the reference rounds them
   int n_src;
   SrcK<T> src[FDTD_FUSED_MAX];  // soft point-list sources on E (ascending idx)
-  // fused_eh_pipe_kernel only: the box is the WHOLE grid, so every CPML slab and the masked one-sided differences
-  // at the six faces are handled inside the kernel, in registration order -- one kernel per step, no shell.
-  // psi_E is ping-pong like the fields (halo cells and the last plane of an x-chunk recompute E_new from the OLD
-  // psi while the owner writes the new one); psi_H is owner-only, in place.
+  // the box is the WHOLE grid: every CPML slab and the masked one-sided differences at the six faces are handled
+  // inside the kernel, in registration order.  psi_E is ping-pong like the fields, psi_H in place.
   int Nx;
   int n_sl;
   struct Slab {
@@ -89,482 +76,32 @@ FDTD_DEV void fused_sources_vec(const FusedParams<T>& P, int i, int j, int k0, i
   }
 }
 
-// core tile of a block: measured on B200 at 1024^3 f32 (ms per fused step incl. shell): 16x16 lanes 13.5,
-// 8x16 13.2, 8x32 13.2, 4x32 12.8 -- small barrier domains matter more than the halo redundancy
+// core tile of a block: R rows x L vector lanes, plus one halo row and one halo lane of threads.  7 x 31 + halo =
+// 8 full warps; two blocks per SM.  Measured at 1024^3 f32 (ms per step): 4x32 (165 threads, 3 blocks) 14.3,
+// 4x31 (3 blocks) 12.8, 8x16 (2) 13.1, 15x31 (1) 12.1, 3x31 (4) 11.9, 7x31 (2) 11.7   profiles/r2_fused_variants.txt
 #ifndef FDTD_FUSED_ROWS
-#define FDTD_FUSED_ROWS 4
+#define FDTD_FUSED_ROWS 7
 #endif
 #ifndef FDTD_FUSED_LANES
-#define FDTD_FUSED_LANES 32
+#define FDTD_FUSED_LANES 31
 #endif
 constexpr int FUSED_R = FDTD_FUSED_ROWS;   // core rows per block
 constexpr int FUSED_L = FDTD_FUSED_LANES;  // core vector lanes per block
 
-template <typename T, int VEC>
-__global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_MIN_BLOCKS)
-    fused_eh_kernel(const __grid_constant__ FusedParams<T> P) {
-  constexpr int R = FUSED_R, L = FUSED_L, W = (L + 1) * VEC;
-  __shared__ __align__(16) T sm[2][3][R + 1][W];   // rows are multiples of 16 bytes: vector stores / loads
-
-  const int tid = threadIdx.x;
-  const int r = tid / (L + 1), l = tid % (L + 1);
-  const int j = P.y0 + blockIdx.y * R + r;
-  const int k0 = P.z0 + (blockIdx.x * L + l) * VEC;
-  const bool core = (r < R) && (l < L) && (j < P.y1) && (k0 < P.z1);
-  const bool active = (j <= P.y1) && (k0 <= P.z1);  // own cells + the one-cell halo (always inside the grid)
-  const bool inside = (j < P.y1) && (k0 < P.z1);    // E_new recomputed here; otherwise the shell computed it
-  const int Nz = P.Nz;
-  const i64 plane = P.plane;
-  const i64 p = (i64)j * Nz + k0;
-  const int xa = P.x0 + blockIdx.z * P.x_chunk;
-  const int xb = (xa + P.x_chunk < P.x1) ? xa + P.x_chunk : P.x1;
-
-  // loop-invariant: can a source touch this thread's row / z-range at all?
-  bool src_yz = false;
-  for (int s = 0; s < P.n_src; ++s)
-    src_yz |= (j >= P.src[s].bb[2]) && (j < P.src[s].bb[3]) && (k0 + VEC > P.src[s].bb[4]) && (k0 < P.src[s].bb[5]);
-
-  // carried: H_old[i-1] and E_new[i-1] of the own cells
-  Pack<T, VEC> hp0, hp1, hp2, ep0, ep1, ep2;
-  if (active && inside) {
-    const i64 o = (i64)(xa - 1) * plane + p;
-    hp0 = ldv<T, VEC>(P.Hin[0] + o);
-    hp1 = ldv<T, VEC>(P.Hin[1] + o);
-    hp2 = ldv<T, VEC>(P.Hin[2] + o);
-  }
-
-  for (int i = xa; i <= xb; ++i) {
-    const i64 off = (i64)i * plane + p;
-    Pack<T, VEC> e0, e1, e2, h0, h1, h2;
-#if FDTD_FUSED_PREFETCH > 0
-    if (core && i + FDTD_FUSED_PREFETCH < P.x1) {
-      const i64 pf = off + (i64)FDTD_FUSED_PREFETCH * plane;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Hin[0] + pf));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Hin[1] + pf));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Hin[2] + pf));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Ein[0] + pf));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Ein[1] + pf));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Ein[2] + pf));
-    }
-#endif
-    if (active) {
-      if (inside && i < P.x1) {
-        // ---- E_new[i] = E_old + (sc eps^-1) * curl_H(H_old)      (fdtd/grid.py:54-76, 283)
-        h0 = ldv<T, VEC>(P.Hin[0] + off);
-        h1 = ldv<T, VEC>(P.Hin[1] + off);
-        h2 = ldv<T, VEC>(P.Hin[2] + off);
-        const Pack<T, VEC> y0v = ldv<T, VEC>(P.Hin[0] + off - Nz);
-        const Pack<T, VEC> y2v = ldv<T, VEC>(P.Hin[2] + off - Nz);
-        const T zs0 = P.Hin[0][off - 1];
-        const T zs1 = P.Hin[1][off - 1];
-        e0 = ldv<T, VEC>(P.Ein[0] + off);
-        e1 = ldv<T, VEC>(P.Ein[1] + off);
-        e2 = ldv<T, VEC>(P.Ein[2] + off);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const T zn0 = e == 0 ? zs0 : h0.v[e > 0 ? e - 1 : 0];
-          const T zn1 = e == 0 ? zs1 : h1.v[e > 0 ? e - 1 : 0];
-          const T d_zy = h2.v[e] - y2v.v[e];
-          const T d_xy = h0.v[e] - y0v.v[e];
-          const T d_yz = h1.v[e] - zn1;
-          const T d_xz = h0.v[e] - zn0;
-          const T d_zx = h2.v[e] - hp2.v[e];
-          const T d_yx = h1.v[e] - hp1.v[e];
-          e0.v[e] = e0.v[e] + P.ce[0] * (d_zy - d_yz);
-          e1.v[e] = e1.v[e] + P.ce[1] * (d_xz - d_zx);
-          e2.v[e] = e2.v[e] + P.ce[2] * (d_yx - d_xy);
-        }
-        if (src_yz) {
-          // soft sources, registration order (fdtd/sources.py:93-109, 278-297)
-          for (int s = 0; s < P.n_src; ++s) {
-            const SrcK<T>& S = P.src[s];
-            if (i < S.bb[0] || i >= S.bb[1] || j < S.bb[2] || j >= S.bb[3] || k0 + VEC <= S.bb[4] || k0 >= S.bb[5])
-              continue;
-            const T wv = S.wave[S.w];
-            for (int n = lower_bound_i64(S.idx, S.n, off); n < S.n && S.idx[n] < off + VEC; ++n) {
-              const int de = (int)(S.idx[n] - off);
-              const T v = S.profile[n] * wv;
-#pragma unroll
-              for (int e = 0; e < VEC; ++e) {
-                if (e == de) {
-                  if (S.comp == 0) e0.v[e] = e0.v[e] + v;
-                  else if (S.comp == 1) e1.v[e] = e1.v[e] + v;
-                  else e2.v[e] = e2.v[e] + v;
-                }
-              }
-            }
-          }
-        }
-        if (core && i < xb) {
-          stv<T, VEC>(P.Eout[0] + off, e0);
-          stv<T, VEC>(P.Eout[1] + off, e1);
-          stv<T, VEC>(P.Eout[2] + off, e2);
-        }
-      } else {
-        // a shell cell (outside the box in y / z, or the plane x1): its E_new is already in memory
-        e0 = ldv<T, VEC>(P.Eout[0] + off);
-        e1 = ldv<T, VEC>(P.Eout[1] + off);
-        e2 = ldv<T, VEC>(P.Eout[2] + off);
-      }
-    }
-
-    // ---- H_new[i-1] = H_old - (sc mu^-1) * curl_E(E_new)      (fdtd/grid.py:29-51, 309)
-    if (core && i > xa) {
-      const int b = (i - 1) & 1;
-      Pack<T, VEC> hx = hp0, hy = hp1, hz = hp2;
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const T ex_y = sm[b][0][r + 1][l * VEC + e];
-        const T ez_y = sm[b][2][r + 1][l * VEC + e];
-        const T ex_z = e == VEC - 1 ? sm[b][0][r][(l + 1) * VEC] : ep0.v[e < VEC - 1 ? e + 1 : 0];
-        const T ey_z = e == VEC - 1 ? sm[b][1][r][(l + 1) * VEC] : ep1.v[e < VEC - 1 ? e + 1 : 0];
-        const T d_zy = ez_y - ep2.v[e];
-        const T d_xy = ex_y - ep0.v[e];
-        const T d_yz = ey_z - ep1.v[e];
-        const T d_xz = ex_z - ep0.v[e];
-        const T d_zx = e2.v[e] - ep2.v[e];
-        const T d_yx = e1.v[e] - ep1.v[e];
-        hx.v[e] = hx.v[e] - P.ch[0] * (d_zy - d_yz);
-        hy.v[e] = hy.v[e] - P.ch[1] * (d_xz - d_zx);
-        hz.v[e] = hz.v[e] - P.ch[2] * (d_yx - d_xy);
-      }
-      const i64 om = off - plane;
-      stv<T, VEC>(P.Hout[0] + om, hx);
-      stv<T, VEC>(P.Hout[1] + om, hy);
-      stv<T, VEC>(P.Hout[2] + om, hz);
-    }
-
-    // ---- publish E_new[i] to the block, carry the planes ---------------------------------------------
-    if (active) {
-      const int b = i & 1;
-      // (one 128-bit store per component: scalar stores at a stride of VEC words conflict 4-way on the banks)
-      stv<T, VEC>(&sm[b][0][r][l * VEC], e0);
-      stv<T, VEC>(&sm[b][1][r][l * VEC], e1);
-      stv<T, VEC>(&sm[b][2][r][l * VEC], e2);
-      ep0 = e0;
-      ep1 = e1;
-      ep2 = e2;
-      if (inside && i < P.x1) {
-        hp0 = h0;
-        hp1 = h1;
-        hp2 = h2;
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// ---- register-tiled variant: no shared memory, no barrier, no shuffle ------------------------------------------
-// A thread owns R consecutive y rows of VEC z-cells and marches along x like the shared-memory kernel above, but
-// everything H_new[i-1] needs of E_new comes out of the thread's own registers:
-//   * the y+1 neighbour of row r is row r+1 of the same thread; above the last row one more row ("halo row") of
-//     Ex_new / Ez_new is recomputed (or, at the box edge, read back from the shell's result);
-//   * the z+1 neighbour of the last cell of a vector is recomputed too: Ex_new / Ey_new of the single cell at
-//     k0 + VEC (its inputs are the neighbouring lane's vectors: L1 hits).
-// Threads never communicate, so there is nothing to wait for except memory: the kernel keeps the latency-hiding
-// behaviour of the streaming half-step kernel (independent loads of R+1 rows in flight per thread) at 12 instead
-// of 18 words per cell and step, for (R+1)/R x (VEC+1)/VEC redundant flops, which are free here.
-// Arithmetic per value is the same as in halfstep_kernel, operation by operation.
-// STATUS (round 1, one measurement, profiles/r1_fused_rt.log): bit-identical on the GPU; with R = 4 (226 registers,
-// 8 warps per SM) a 1024^3 f32 step takes 15.0 ms against 12.8 ms for the shared-memory kernel and 12.9 ms for the
-// two half-steps -- the occupancy is too low to hide the latency.  Untried: R = 2 / 3 (151 / 188 registers), fewer
-// warps per block, loads of all rows issued ahead of the arithmetic.  Selected with fuse_eh = 2.
-#ifndef FDTD_FUSED_RT_ROWS
-#define FDTD_FUSED_RT_ROWS 4
-#endif
-#ifndef FDTD_FUSED_RT_WARPS
-#define FDTD_FUSED_RT_WARPS 4
-#endif
-#ifndef FDTD_FUSED_RT_MIN_BLOCKS
-#define FDTD_FUSED_RT_MIN_BLOCKS 2
-#endif
-constexpr int FUSED_RT_R = FDTD_FUSED_RT_ROWS;
-constexpr int FUSED_RT_WARPS = FDTD_FUSED_RT_WARPS;
-
-// inputs of a fused step are never written by it (ping-pong buffers): read-only path, free to be hoisted over stores
-template <typename T, int VEC>
-FDTD_DEV Pack<T, VEC> ldv_ro(const T* p) {
-#ifndef FDTD_EMU
-  if constexpr (sizeof(Pack<T, VEC>) == 16) {
-    const float4 r = __ldg(reinterpret_cast<const float4*>(p));
-    return *reinterpret_cast<const Pack<T, VEC>*>(&r);
-  } else if constexpr (sizeof(Pack<T, VEC>) == 8) {
-    const float2 r = __ldg(reinterpret_cast<const float2*>(p));
-    return *reinterpret_cast<const Pack<T, VEC>*>(&r);
-  }
-#endif
-  return ldv<T, VEC>(p);
-}
-template <typename T>
-FDTD_DEV T ld_ro(const T* p) {
-#ifndef FDTD_EMU
-  return __ldg(p);
-#else
-  return *p;
-#endif
-}
-
-// soft point sources of the box on ONE recomputed E value, registration order (fdtd/sources.py:93-109, 278-297)
-template <typename T>
-FDTD_DEV T fused_sources(const FusedParams<T>& P, int i, int j, int k, i64 lin, int comp, T v) {
-  for (int s = 0; s < P.n_src; ++s) {
-    const SrcK<T>& S = P.src[s];
-    if (S.comp != comp || i < S.bb[0] || i >= S.bb[1] || j < S.bb[2] || j >= S.bb[3] || k < S.bb[4] || k >= S.bb[5])
-      continue;
-    const T wv = S.wave[S.w];
-    for (int n = lower_bound_i64(S.idx, S.n, lin); n < S.n && S.idx[n] == lin; ++n) v = v + S.profile[n] * wv;
-  }
-  return v;
-}
-
-template <typename T, int VEC, int R>
-__global__ void __launch_bounds__(32 * FUSED_RT_WARPS, FDTD_FUSED_RT_MIN_BLOCKS)
-    fused_eh_rt_kernel(const FusedParams<T> P) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int jb = P.y0 + ((int)blockIdx.y * FUSED_RT_WARPS + warp) * R;  // first own row
-  const int k0 = P.z0 + ((int)blockIdx.x * 32 + lane) * VEC;
-  if (jb >= P.y1 || k0 >= P.z1) return;  // threads are independent: no barrier to miss
-  const int kz = k0 + VEC;               // the z+1 neighbour cell of the vector (<= z1 < Nz)
-  const bool kz_in = kz < P.z1;          // inside the box: recomputed here; at z1 the shell has computed it
-  const int Nz = P.Nz;
-  const i64 plane = P.plane;
-  const i64 pb = (i64)jb * Nz + k0;
-  const int xa = P.x0 + blockIdx.z * P.x_chunk;
-  const int xb = (xa + P.x_chunk < P.x1) ? xa + P.x_chunk : P.x1;
-
-  bool src_any = false;  // can a source touch this thread's rows / z-range (halo cells included) at all?
-  for (int s = 0; s < P.n_src; ++s)
-    src_any |= (jb + R >= P.src[s].bb[2]) && (jb < P.src[s].bb[3]) && (kz >= P.src[s].bb[4]) && (k0 < P.src[s].bb[5]);
-
-  // ---- carried from plane i-1 ----------------------------------------------------------------------------
-  T hp[R][3][VEC];   // H_old of the own rows
-  T hpy[VEC];        // Hy_old of the halo row (x-difference of its Ez)
-  T hpz[R];          // Hz_old at kz of the own rows (x-difference of the z-halo Ey)
-  T ep[R][3][VEC];   // E_new of the own rows
-  T eh0[VEC], eh2[VEC];  // Ex_new, Ez_new of the halo row
-  T ezx[R], ezy[R];      // Ex_new, Ey_new at kz of the own rows
-  {
-    const i64 o = (i64)(xa - 1) * plane + pb;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (jb + r < P.y1) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const Pack<T, VEC> v = ldv_ro<T, VEC>(P.Hin[c] + o + (i64)r * Nz);
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) hp[r][c][e] = v.v[e];
-        }
-        hpz[r] = kz_in ? ld_ro(P.Hin[2] + o + (i64)r * Nz + VEC) : T(0);
-      }
-    }
-    if (jb + R < P.y1) {
-      const Pack<T, VEC> v = ldv_ro<T, VEC>(P.Hin[1] + o + (i64)R * Nz);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) hpy[e] = v.v[e];
-    }
-  }
-
-  for (int i = xa; i <= xb; ++i) {
-    const i64 offb = (i64)i * plane + pb;
-    const bool in_x = i < P.x1;  // plane x1 belongs to the shell: its E_new is already in memory
-    // y-1 neighbours of the first row (H_old, plane i)
-    T hm0[VEC], hm2[VEC], hmz = T(0);
-    if (in_x) {
-      const Pack<T, VEC> a = ldv_ro<T, VEC>(P.Hin[0] + offb - Nz);
-      const Pack<T, VEC> b = ldv_ro<T, VEC>(P.Hin[2] + offb - Nz);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        hm0[e] = a.v[e];
-        hm2[e] = b.v[e];
-      }
-      if (kz_in) hmz = ld_ro(P.Hin[2] + offb - Nz + VEC);
-    }
-#pragma unroll
-    for (int r = 0; r <= R; ++r) {
-      const int j = jb + r;
-      if (j > P.y1) continue;            // beyond the y+1 neighbour of the box's last row: nothing needed
-      const bool own = r < R;            // false: the halo row (Ex, Ez only, no z-halo, no H)
-      const bool compute = in_x && j < P.y1;
-      const i64 off = offb + (i64)r * Nz;
-      T e0[VEC], e1[VEC], e2[VEC], ex = T(0), ey = T(0);
-      T h0[VEC], h1[VEC], h2[VEC], hzz = T(0);
-      if (compute) {
-        // ---- E_new[i] = E_old + (sc eps^-1) * curl_H(H_old)      (fdtd/grid.py:54-76, 283)
-        {
-          const Pack<T, VEC> a = ldv_ro<T, VEC>(P.Hin[0] + off);
-          const Pack<T, VEC> b = ldv_ro<T, VEC>(P.Hin[1] + off);
-          const Pack<T, VEC> c = ldv_ro<T, VEC>(P.Hin[2] + off);
-          const Pack<T, VEC> u = ldv_ro<T, VEC>(P.Ein[0] + off);
-          const Pack<T, VEC> w = ldv_ro<T, VEC>(P.Ein[2] + off);
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            h0[e] = a.v[e]; h1[e] = b.v[e]; h2[e] = c.v[e];
-            e0[e] = u.v[e]; e2[e] = w.v[e];
-          }
-          if (own) {
-            const Pack<T, VEC> v = ldv_ro<T, VEC>(P.Ein[1] + off);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) e1[e] = v.v[e];
-          }
-        }
-        const T zs0 = ld_ro(P.Hin[0] + off - 1);
-        const T zs1 = ld_ro(P.Hin[1] + off - 1);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const T zn0 = e == 0 ? zs0 : h0[e > 0 ? e - 1 : 0];
-          const T zn1 = e == 0 ? zs1 : h1[e > 0 ? e - 1 : 0];
-          const T d_zy = h2[e] - hm2[e];
-          const T d_xy = h0[e] - hm0[e];
-          const T d_yz = h1[e] - zn1;
-          const T d_xz = h0[e] - zn0;
-          const T d_yx = h1[e] - (own ? hp[own ? r : 0][1][e] : hpy[e]);
-          e0[e] = e0[e] + P.ce[0] * (d_zy - d_yz);
-          e2[e] = e2[e] + P.ce[2] * (d_yx - d_xy);
-          if (own) {
-            const T d_zx = h2[e] - hp[own ? r : 0][2][e];
-            e1[e] = e1[e] + P.ce[1] * (d_xz - d_zx);
-          }
-        }
-        if (own) {
-          // the z+1 neighbour cell (j, kz): Ex_new and Ey_new only
-          if (kz_in) {
-            const T hxz = ld_ro(P.Hin[0] + off + VEC);
-            const T hyz = ld_ro(P.Hin[1] + off + VEC);
-            hzz = ld_ro(P.Hin[2] + off + VEC);
-            const T d_zy = hzz - hmz;
-            const T d_yz = hyz - h1[VEC - 1];
-            const T d_xz = hxz - h0[VEC - 1];
-            const T d_zx = hzz - hpz[own ? r : 0];
-            ex = ld_ro(P.Ein[0] + off + VEC) + P.ce[0] * (d_zy - d_yz);
-            ey = ld_ro(P.Ein[1] + off + VEC) + P.ce[1] * (d_xz - d_zx);
-          } else {
-            ex = P.Eout[0][off + VEC];
-            ey = P.Eout[1][off + VEC];
-          }
-        }
-        if (src_any) {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            e0[e] = fused_sources(P, i, j, k0 + e, off + e, 0, e0[e]);
-            if (own) e1[e] = fused_sources(P, i, j, k0 + e, off + e, 1, e1[e]);
-            e2[e] = fused_sources(P, i, j, k0 + e, off + e, 2, e2[e]);
-          }
-          if (own && kz_in) {
-            ex = fused_sources(P, i, j, kz, off + VEC, 0, ex);
-            ey = fused_sources(P, i, j, kz, off + VEC, 1, ey);
-          }
-        }
-        if (own && i < xb) {
-          Pack<T, VEC> a, b, c;
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            a.v[e] = e0[e]; b.v[e] = e1[e]; c.v[e] = e2[e];
-          }
-          stv<T, VEC>(P.Eout[0] + off, a);
-          stv<T, VEC>(P.Eout[1] + off, b);
-          stv<T, VEC>(P.Eout[2] + off, c);
-        }
-      } else {
-        // a shell cell (row y1, or plane x1): its E_new is already in memory
-        const Pack<T, VEC> a = ldv<T, VEC>(P.Eout[0] + off);
-        const Pack<T, VEC> c = ldv<T, VEC>(P.Eout[2] + off);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          e0[e] = a.v[e]; e2[e] = c.v[e];
-        }
-        if (own) {
-          const Pack<T, VEC> b = ldv<T, VEC>(P.Eout[1] + off);
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) e1[e] = b.v[e];
-          ex = P.Eout[0][off + VEC];
-          ey = P.Eout[1][off + VEC];
-        }
-      }
-
-      // ---- H_new[i-1] = H_old - (sc mu^-1) * curl_E(E_new)      (fdtd/grid.py:29-51, 309)
-      if (own && j < P.y1 && i > xa) {
-        Pack<T, VEC> hx, hy, hz;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const int rr = own ? r : 0;                       // (keeps the indices in range when r == R is unrolled)
-          const T ex_y = (rr + 1 < R) ? ep[rr + 1 < R ? rr + 1 : 0][0][e] : eh0[e];
-          const T ez_y = (rr + 1 < R) ? ep[rr + 1 < R ? rr + 1 : 0][2][e] : eh2[e];
-          const T ex_z = e == VEC - 1 ? ezx[rr] : ep[rr][0][e < VEC - 1 ? e + 1 : 0];
-          const T ey_z = e == VEC - 1 ? ezy[rr] : ep[rr][1][e < VEC - 1 ? e + 1 : 0];
-          const T d_zy = ez_y - ep[rr][2][e];
-          const T d_xy = ex_y - ep[rr][0][e];
-          const T d_yz = ey_z - ep[rr][1][e];
-          const T d_xz = ex_z - ep[rr][0][e];
-          const T d_zx = e2[e] - ep[rr][2][e];
-          const T d_yx = e1[e] - ep[rr][1][e];
-          hx.v[e] = hp[rr][0][e] - P.ch[0] * (d_zy - d_yz);
-          hy.v[e] = hp[rr][1][e] - P.ch[1] * (d_xz - d_zx);
-          hz.v[e] = hp[rr][2][e] - P.ch[2] * (d_yx - d_xy);
-        }
-        const i64 om = off - plane;
-        stv<T, VEC>(P.Hout[0] + om, hx);
-        stv<T, VEC>(P.Hout[1] + om, hy);
-        stv<T, VEC>(P.Hout[2] + om, hz);
-      }
-
-      // ---- carry to plane i+1, and down to row r+1 ---------------------------------------------------------
-      if (own) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          ep[own ? r : 0][0][e] = e0[e];
-          ep[own ? r : 0][1][e] = e1[e];
-          ep[own ? r : 0][2][e] = e2[e];
-        }
-        ezx[own ? r : 0] = ex;
-        ezy[own ? r : 0] = ey;
-        if (compute) {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            hp[own ? r : 0][0][e] = h0[e];
-            hp[own ? r : 0][1][e] = h1[e];
-            hp[own ? r : 0][2][e] = h2[e];
-          }
-          hpz[own ? r : 0] = hzz;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          eh0[e] = e0[e];
-          eh2[e] = e2[e];
-        }
-        if (compute) {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) hpy[e] = h1[e];
-        }
-      }
-      if (compute) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          hm0[e] = h0[e];
-          hm2[e] = h2[e];
-        }
-        hmz = hzz;
-      }
-    }
-  }
-}
-
-// ---- pipelined variant: the inputs of each plane are staged in shared memory by cp.async, two planes ahead -----
-// Same thread layout, halo scheme and arithmetic as fused_eh_kernel, but no thread ever waits for a global load it
-// has just issued: every plane's H_old tile (own cells + the y-1 row and the z-1 vector) and E_old tile arrive in
-// one of three shared-memory stages through asynchronous 16-byte copies (LDGSTS, L2 only) issued two iterations
-// before they are consumed, so the one barrier per plane no longer exposes the memory latency of the slowest warp.
-// Each global word is requested once per block (the y-1 / z-1 neighbours come out of the staged tile).
-// STATUS (round 1): bit-identical on the B200, but the first build was 2.8x SLOWER than the two half-steps at 512^3
-// f32 (profiles/r1_fused_pipe_check.log).  Never profiled.  What its SASS showed, and what has been changed since
-// (CPU-verified only, not re-measured): a per-thread copy table and the field vectors lived in local memory (the
-// table is gone: copy addresses derive from the thread's own cell; the slab helper selects its operands at compile
-// time; the source helper is inlined) and the shared-memory carve-out was left to the driver (3 blocks of 69 KB only
-// fit at the maximum carve-out, which is now requested).  64 bytes of spills remain at 96 registers (3 blocks per
-// SM); 132 registers and none at 2 blocks per SM; without any slab / source code the march needs 89 registers and
-// ~300 instructions per thread and plane.  Moving the slab code out of line was tried and dropped: the difference
-// arrays and field vectors it takes by reference are then stored to local memory on EVERY plane (36 STL), not only
-// on the planes that call it.  Opt-in only (fuse_eh = 3).
+// ---- the inputs of each plane are staged in shared memory by cp.async, two planes ahead ------------------------
+// No thread ever waits for a global load it has just issued: every plane's H_old tile (own cells + the y-1 row and
+// the z-1 vector) and E_old tile arrive in one of three shared-memory stages through asynchronous 16-byte copies
+// (LDGSTS, L2 only) issued two iterations before they are consumed, so the one barrier per plane does not expose the
+// memory latency of the slowest warp.  Each global word is requested once per block (the y-1 / z-1 neighbours come
+// out of the staged tile).  Copy addresses derive from the thread's own cell; the slab helper selects its operands at
+// compile time and the source helper is inlined, so the field vectors stay in registers (128 registers, no spill,
+// 104 KB of shared memory per block: two blocks per SM).
+// Measured (ncu, profiles/r2_ncu_summary_before.txt): 11.66 ms per launch at 1024^3 f32, DRAM 57.3 GB (algorithmic
+// 53.6 GB: the halo threads' re-reads) at 4.9 TB/s -- not DRAM-bound: 44 % of the issue slots with 4 warps per
+// scheduler; 14 % of the stall samples sit on the barrier, 13 % on the first use of psi (the only global loads left on
+// the critical path; one waiting thread holds its block at the barrier, and a quarter of all blocks touch a z slab).
+// Tried without gain (profiles/r2_fused_variants.txt): L2 prefetch of the inputs 3-6 planes ahead (+0.4 ms), L1 / L2
+// prefetch of psi (+1.4 ms: the index arithmetic runs in every thread), longer x-chunks (+0.2 / +0.7 ms).
 // Iteration i:  wait for this thread's copies of plane i -> barrier (everyone's copies landed, everyone's
 // E_new[i-1] is published, stage (i-1)%3 is free) -> issue the copies of plane i+2 into stage (i-1)%3 ->
 // E_new[i] from stage i%3 -> H_new[i-1] from the published E_new[i-1] -> publish E_new[i].
@@ -585,14 +122,14 @@ __global__ void __launch_bounds__(32 * FUSED_RT_WARPS, FDTD_FUSED_RT_MIN_BLOCKS)
 #define FDTD_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 #ifndef FDTD_FUSED_PIPE_MIN_BLOCKS
-#define FDTD_FUSED_PIPE_MIN_BLOCKS 3
+#define FDTD_FUSED_PIPE_MIN_BLOCKS 2
 #endif
 #ifndef FDTD_FUSED_PIPE_PSI_PREFETCH
-#define FDTD_FUSED_PIPE_PSI_PREFETCH 2   // CPML psi of the thread's cells is prefetched (L1) this many planes ahead: the psi
+#define FDTD_FUSED_PIPE_PSI_PREFETCH 0   // CPML psi of the thread's cells is prefetched (L1) this many planes ahead: the psi
                                          // loads are the only global loads left on the per-plane critical path, and one
                                          // thread waiting for them holds its whole block at the barrier -- a quarter of all
-                                         // blocks touch a z slab (profiles/r2_pipe_stalls.txt: 13 % of all stall samples on
-                                         // the first use of psi / the b table).  0 = off
+                                         // blocks touch a z slab.  Measured: +1.4 ms per step (the index arithmetic runs in
+                                         // every thread of every block) -- off
 #endif
 #ifndef FDTD_FUSED_PIPE_PSI_LEVEL
 #define FDTD_FUSED_PIPE_PSI_LEVEL 1      // 1: prefetch.global.L1, 2: prefetch.global.L2
@@ -977,19 +514,6 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
       }
     }
     hit_prev = hit_now;
-  }
-}
-
-// shell E sources of a fused step: the points OUTSIDE the interior box (those inside are applied by the fused kernel)
-template <typename T>
-__global__ void source_points_outside_kernel(T* F, const i64* idx, const T* profile, int n, const T* wave, i64 w,
-                                             i64 plane, int Nz, int x0, int x1, int y0, int y1, int z0, int z1) {
-  const T s = wave[w];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    const i64 lin = idx[t];
-    const int x = (int)(lin / plane), y = (int)((lin % plane) / Nz), z = (int)(lin % Nz);
-    if (x >= x0 && x < x1 && y >= y0 && y < y1 && z >= z0 && z < z1) continue;
-    fdtd_atomic_add(F + lin, profile[t] * s);
   }
 }
 

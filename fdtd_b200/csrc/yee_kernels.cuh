@@ -26,6 +26,11 @@
 #ifndef FDTD_MIN_BLOCKS
 #define FDTD_MIN_BLOCKS 3      // resident 256-thread blocks per SM the register budget is sized for
 #endif
+#ifndef FDTD_MAT_MIN_BLOCKS
+#define FDTD_MAT_MIN_BLOCKS 2   // instantiations with material / object code (MAT = true): 122 registers and no spill at two
+                                // blocks per SM instead of 80 with spills at three -- 512^3 absorber + lens +0.6 %, the GRIN
+                                // slab of config 5 +6.3 % (profiles/r2_mat_variants.txt)
+#endif
 #ifndef FDTD_BLOCK_THREADS
 #define FDTD_BLOCK_THREADS 256 // threads per block of the half-step kernels
 #endif
@@ -472,7 +477,7 @@ FDTD_SLAB_FN void slab_pass(const HalfStepParams<T, A>& P, CellState<A, VEC>& C,
 // MAT: the grid has material arrays and a tile-class map; without them (homogeneous grids, e.g. the 1024^3
 // benchmark) all coefficient / object / absorber code is compiled out and costs no registers
 template <typename T, int VEC, bool IS_E, bool HAS_POST, bool HAS_PUSH, bool MAT, typename A = T>
-__global__ void __launch_bounds__(FDTD_BLOCK_THREADS, (sizeof(A) > sizeof(T) ? 2 : FDTD_MIN_BLOCKS)) halfstep_kernel(const FDTD_GRID_CONSTANT HalfStepParams<T, A> P) {
+__global__ void __launch_bounds__(FDTD_BLOCK_THREADS, (sizeof(A) > sizeof(T) ? 2 : (MAT ? FDTD_MAT_MIN_BLOCKS : FDTD_MIN_BLOCKS))) halfstep_kernel(const FDTD_GRID_CONSTANT HalfStepParams<T, A> P) {
   const int tid = threadIdx.x;
   const int lane = tid & (P.lanes_z - 1);
   const int row = tid >> P.lanes_shift;

@@ -23,6 +23,8 @@ RING_BYTES = 64 << 20          # detector ring budget per grid
 WAVE_TABLE_MIN = 1024          # look-ahead of the host waveform tables (steps)
 WAVE_TABLE_MAX = 1 << 16
 GRAPH_MAX_CELLS = 1 << 23      # grids up to this many cells replay CUDA graphs of 32-step chunks in run()
+FUSE_EH_MIN_CELLS = 600_000_000  # from here on the single-pass E+H kernel beats the two half-steps (automatic mode;
+                                 # 768^3: -2 %, 896^3: +4 %, 1024^3: +8 %, profiles/r2_fused_sizes.txt)
 
 
 def _ptr(t):
@@ -288,16 +290,20 @@ class Engine:
         if self._feedback_sources and not self._dets:
             self.ring_capacity = 4096
 
-        # temporally fused E+H steps (12 instead of 18 words per cell and step) need a second pair of field
-        # buffers; opt-in (FDTD_B200_FUSE_EH=1 / grid._fuse_eh): homogeneous, unsharded grids only
-        if (g._fuse_eh and not part.sharded and ie_eff is None and imu is None):
-            if g._E2 is None:
+        # temporally fused E+H steps (12 instead of 18 words per cell and step) need a second pair of field buffers and
+        # a second psi_E per slab: homogeneous, unsharded grids only.  grid._fuse_eh / FDTD_B200_FUSE_EH: 0 never,
+        # 1 wherever legal, 2 (default) where it is also faster -- large grids -- and the buffers fit in free memory
+        want = g._fuse_eh
+        big = part.nx * g.Ny * g.Nz >= FUSE_EH_MIN_CELLS
+        if (want and not part.sharded and not self._hooked and ie_eff is None and imu is None and not post
+                and g._sdtype is g._dtype and (want == 1 or big)):
+            if g._E2 is None and (want == 1 or self._room_for(2 * g._E.numel() * g._E.element_size())):
                 g._E2, g._H2 = torch.zeros_like(g._E), torch.zeros_like(g._H)
-            for c in range(3):
-                d.E2[c] = g._E2[c, 1].data_ptr()
-                d.H2[c] = g._H2[c, 1].data_ptr()
-            d.fuse_eh = int(g._fuse_eh) if int(g._fuse_eh) in (2, 3) else 1
-            if d.fuse_eh == 3:
+            if g._E2 is not None:
+                for c in range(3):
+                    d.E2[c] = g._E2[c, 1].data_ptr()
+                    d.H2[c] = g._H2[c, 1].data_ptr()
+                d.fuse_eh = 1 if want == 1 else 2
                 for idx, b in enumerate(slabs):          # psi_E ping-pong (include/fdtd_b200.h, psi_E2)
                     if getattr(b, "_psi_E2", None) is None:
                         b._psi_E2 = torch.zeros_like(b._psi_E)
@@ -317,6 +323,14 @@ class Engine:
             self._setup_halo()
             self._wrap = WrapExchange(part, g._E, g._H) if x_wrap else None
         g._baked_counts = g._registration_count
+
+    def _room_for(self, nbytes):
+        """is there free device memory for `nbytes` more, with a margin? (the fused E+H path is optional)"""
+        dev = self.grid._E.device
+        if dev.type != "cuda":
+            return True
+        free, _ = torch.cuda.mem_get_info(dev)
+        return free > nbytes + (4 << 30)
 
     def _setup_halo(self):
         """x-sharded grids: direct peer-to-peer ghost-plane stores (default on CUDA), or NCCL / gloo send-recv

@@ -109,9 +109,8 @@ class Grid:
         # None: automatic (launch-bound small grids), True / False: force.  FDTD_B200_GRAPHS / FDTD_B200_FUSE = 0|1
         self._use_graphs = _env_flag("FDTD_B200_GRAPHS")
         self._fuse_post = _env_flag("FDTD_B200_FUSE")
-        # temporally fused E+H steps in run() (opt-in): 1 = shared-memory kernel, 2 = register-tiled kernel,
-        # 3 = shared-memory kernel with cp.async-staged inputs
-        self._fuse_eh = int(os.environ.get("FDTD_B200_FUSE_EH") or 0)
+        # temporally fused E+H steps in run(): 0 never, 1 wherever legal, 2 (default) where also faster (engine.py)
+        self._fuse_eh = int(os.environ.get("FDTD_B200_FUSE_EH", "2") or 0)
         self._E2 = self._H2 = None
 
     # ----------------------------------------------------------------------------- materials

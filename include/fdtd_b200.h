@@ -204,20 +204,20 @@ typedef struct fdtd_desc {
   int32_t x_chunk;     /* planes marched per thread block; 0 = library default */
   int32_t use_graphs;  /* 1: fdtd_run may replay CUDA graphs of step chunks (launch-bound small grids) */
   int64_t* dyn;        /* device int64[2] scratch owned by the caller, needed when use_graphs = 1 */
-  int32_t fuse_eh;     /* != 0: fdtd_run may run pairs of temporally fused E+H steps (12 instead of 18 words per cell
-                          and step) on homogeneous unsharded grids; needs E2 / H2.  1 = shared-memory kernel (E_new exchanged through
-                          shared memory, one barrier per plane), 2 = register-tiled kernel (no communication between
-                          threads), 3 = the shared-memory kernel with its inputs staged by cp.async two planes
-                          ahead */
+  int32_t fuse_eh;     /* != 0: fdtd_run may run pairs of temporally fused E+H steps -- one kernel per step that moves 12
+                          instead of 18 words per cell -- on homogeneous unsharded grids without periodic boundaries,
+                          with point sources on E only; needs E2 / H2 / psi_E2.  1: wherever that is legal,
+                          2: only where it is also faster than the two half-steps (grids of 6e8 cells and more) */
   int32_t pad2_;
   void* E2[3];         /* second field buffers of the ping-pong pair, same layout as E / H (ghost planes included), */
   void* H2[3];         /* or NULL; after fdtd_run the results are always in E / H */
   int32_t fuse_post;   /* sources/detectors folded into the half-step kernel: 1 always (when legal), 0 never,
                           -1 automatic (local slabs up to 2^23 cells, where a step is launch-bound) */
   int32_t pad3_;
-  void* psi_E2[FDTD_MAX_SLABS];  /* fuse_eh = 3: a second psi_E buffer [2][psi_count] for every slab.  That kernel
-                          updates the whole grid, CPML cells and faces included, in its single pass; cells whose E_new is recomputed by a neighbouring thread need the OLD psi_E, so psi_E
-                          alternates between the two buffers like the fields (results always end in psi_E) */
+  void* psi_E2[FDTD_MAX_SLABS];  /* fuse_eh: a second psi_E buffer [2][psi_count] for every slab.  The fused kernel updates the
+                          whole grid, CPML cells and faces included, in its single pass; cells whose E_new is recomputed
+                          by a neighbouring thread need the OLD psi_E, so psi_E alternates between the two buffers like
+                          the fields (results always end in psi_E) */
   int32_t n_deep;      /* objects beyond the second one on a cell */
   int32_t h_wrap_ghost;/* x-sharded grids: 1 = the caller keeps the LOW ghost plane of Hy on the first slab equal to the last
                           slab's last plane, so that a CurrentDetector cell on global plane x = 0 finds H[x-1] = H[-1]
@@ -285,7 +285,7 @@ int fdtd_update_H(const fdtd_desc* d, int64_t q, int64_t slot, void* stream);
 int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void* stream);
 
 /* 1 when fdtd_run will execute pairs of temporally fused E+H steps for this descriptor (fuse_eh set, second
- * buffers given, homogeneous unsharded grid, point sources on E only, a large enough CPML-free interior) */
+ * buffers given, homogeneous unsharded grid, no periodic boundary, point sources on E only) */
 int fdtd_fuse_eh_active(const fdtd_desc* d);
 
 /* --- direct peer-to-peer halo exchange (x-sharded grids, one process per GPU) -------------------------

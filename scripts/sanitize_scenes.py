@@ -38,7 +38,7 @@ def main():
             g[key] = fd.PML()
         g[20, 18, 70] = fd.PointSource(period=15)
         g[2:38, 18, 60] = fd.LineDetector()
-        g._fuse_eh = 3
+        g._fuse_eh = 1
         g.run(10, progress_bar=False)
         torch.cuda.synchronize()
         assert g._engine.lib.fdtd_fuse_eh_active(g._engine.desc) == 1

@@ -52,6 +52,9 @@ VARIANTS = {
     "pipe_r3l31_mb4_pf4": ["-DFDTD_FUSED_ROWS=3", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4", "-DFDTD_FUSED_PIPE_PREFETCH=4"],
     "fz_r7l31_mb2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_MIN_BLOCKS=2"],
     "fz_r7l31_mb3": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_MIN_BLOCKS=3"],
+    "mat_mb2": ["-DFDTD_MAT_MIN_BLOCKS=2"],
+    "mat_mb2_noinl": ["-DFDTD_MAT_MIN_BLOCKS=2", "-DFDTD_SPECIAL_NOINLINE=1"],
+    "mat_noinl": ["-DFDTD_SPECIAL_NOINLINE=1"],
     "pfcap": ["-DFDTD_PREFETCH_CAP=1"],
     "pfcap_pf2": ["-DFDTD_PREFETCH_CAP=1", "-DFDTD_PREFETCH_PLANES=2"],
     "nopf": ["-DFDTD_PREFETCH_PLANES=0"],
