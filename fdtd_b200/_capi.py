@@ -71,6 +71,7 @@ class Halo(C.Structure):
     """mirror of fdtd_halo: one rank's peer pointers, flags and push counts of the peer-to-peer halo exchange"""
     _fields_ = [("has_left", C.c_int32), ("has_right", C.c_int32),
                 ("left_ghost_y", _vp), ("left_ghost_z", _vp), ("right_ghost_y", _vp), ("right_ghost_z", _vp),
+                ("left_ghost_y2", _vp), ("left_ghost_z2", _vp), ("right_ghost_y2", _vp), ("right_ghost_z2", _vp),
                 ("left_flag", _vp), ("right_flag", _vp), ("flags", _vp), ("error", _vp),
                 ("count", C.c_int64 * 2), ("push_fused", C.c_int32 * 2), ("side_stream", _vp),
                 ("timeout_ns", C.c_int64)]
@@ -102,6 +103,7 @@ EXPORTS = {
     "fdtd_halo_wait": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp]),
     "fdtd_sharded_halfstep": (C.c_int, [C.POINTER(Desc), C.POINTER(Halo), C.c_int32, C.c_int64, C.c_int64, _vp]),
     "fdtd_run_sharded": (C.c_int, [C.POINTER(Desc), C.POINTER(Halo), C.c_int64, C.c_int64, C.c_int64, _vp]),
+    "fdtd_fuse_eh_sharded_active": (C.c_int, [C.POINTER(Desc), C.POINTER(Halo)]),
     "fdtd_halo_refresh": (C.c_int, [C.POINTER(Desc), C.POINTER(Halo), _vp]),
     "fdtd_sizeof_halo": (C.c_int64, []),
     "fdtd_post_phases": (C.c_int, [C.POINTER(Desc), C.c_int32, C.c_uint32, C.c_int64, C.c_int64, _vp]),

@@ -305,11 +305,19 @@ fdtd::SlabK<T, A> slab_k(const fdtd_slab& S) {
   return k;
 }
 
+// explicit in / out / curl-source buffers of a launch (the last H plane of a temporally fused step on an x-sharded
+// slab: H from one buffer of the ping-pong pair into the other, curls from the new E); no folded sources / detectors
+struct Buffers {
+  void* const* Fin;
+  void* const* Fout;
+  void* const* G;
+};
+
 // graph_step >= 0: the launch is being captured as step `graph_step` of a replayable chunk; waveform
 // index and ring slot are then graph_step + the bases in d->dyn
 template <typename T, bool IS_E, typename A = T>
 int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
-                        int64_t graph_step, void* push_y, void* push_z, bool plain);
+                        int64_t graph_step, void* push_y, void* push_z, bool plain, const Buffers* buf = nullptr);
 
 #ifndef FDTD_PLAIN_RUN_MIN
 #ifdef FDTD_EMU
@@ -361,7 +369,7 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
 // plain: every tile of these planes is homogeneous -> no class map, no material arrays
 template <typename T, bool IS_E, typename A>
 int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
-                        int64_t graph_step, void* push_y, void* push_z, bool plain) {
+                        int64_t graph_step, void* push_y, void* push_z, bool plain, const Buffers* buf) {
   Geometry g = geometry(d->dtype, d->Ny, d->Nz);
   fdtd::HalfStepParams<T, A> P;
   memset(&P, 0, sizeof(P));
@@ -394,6 +402,11 @@ int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, i
     P.inv2[c] = IS_E ? (const A*)d->inv_eps2[c] : nullptr;
     P.absorb[c] = IS_E ? (const A*)d->absorb[c] : nullptr;
     P.absorb2[c] = IS_E ? (const A*)d->absorb2[c] : nullptr;
+    if (buf) {
+      P.F[c] = (T*)buf->Fin[c];
+      P.Fo[c] = (T*)buf->Fout[c];
+      P.G[c] = (const T*)buf->G[c];
+    }
   }
   // a class map is only meaningful with the arrays it refers to
   P.cls = plain ? nullptr : d->tile_class;
@@ -401,7 +414,7 @@ int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, i
   if (P.inv[0] != nullptr && d->tile_class == nullptr) return fail(FDTD_ERR_ARG, "material arrays need a tile_class map");
   P.n_slabs = d->n_slabs;
   for (int s = 0; s < d->n_slabs; ++s) P.slabs[s] = slab_k<T, IS_E, A>(d->slabs[s]);
-  if (post_is_fused(d)) {
+  if (!buf && post_is_fused(d)) {
     P.dyn = graph_step >= 0 ? (const i64*)d->dyn : nullptr;
     for (int n = 0; n < d->n_sources; ++n) {
       const fdtd_source& S = d->sources[n];
@@ -804,6 +817,169 @@ int fdtd_ipc_import(const void* handle64, int64_t offset, void** dev_ptr) {
 }
 #endif
 
+// ---- temporally fused E+H steps (yee_fused_eh.cuh) --------------------------------------------------------
+extern "C++" {
+namespace {
+#ifndef FDTD_FUSE_EH_MIN_CELLS
+#ifdef FDTD_EMU
+#define FDTD_FUSE_EH_MIN_CELLS 0
+#else
+#define FDTD_FUSE_EH_MIN_CELLS 600000000LL   // below, the 7 x 124-cell tiles quantise badly and the two half-steps win
+#endif
+#endif
+
+// fuse_eh = 1: wherever it is legal; fuse_eh = 2: only where it is also faster (large grids: what counts is the
+// tile quantisation of the y-z plane, so an x-slab of a large grid qualifies like the grid itself)
+bool fuse_eh_eligible(const fdtd_desc* d, bool sharded = false) {
+  if (!d->fuse_eh || d->dtype == FDTD_F32X) return false;
+  for (int c = 0; c < 3; ++c)
+    if (!d->E2[c] || !d->H2[c] || d->inv_eps[c] || d->inv_mu[c] || d->absorb[c]) return false;
+  if ((d->Nx != d->Nx_global) != sharded || d->n_post != 0 || d->n_deep != 0 || d->x_wrap) return false;
+  const int vec = d->dtype == FDTD_F32 ? 4 : 2;
+  if (d->Nz % vec) return false;
+  if (d->fuse_eh == 2 && (int64_t)d->Nx_global * d->Ny * d->Nz < FDTD_FUSE_EH_MIN_CELLS) return false;
+  if (sharded && d->Nx < 4) return false;
+  int nsrc = 0;
+  for (int n = 0; n < d->n_sources; ++n) {
+    if (d->sources[n].kind != FDTD_SRC_POINTS || d->sources[n].field != 0) return false;
+    ++nsrc;
+  }
+  if (nsrc > FDTD_FUSED_MAX) return false;
+  for (int n = 0; n < d->n_detectors; ++n)
+    if (d->detectors[n].kind != FDTD_DET_FIELD) return false;
+  for (int s = 0; s < d->n_slabs; ++s) {
+    // the kernel applies every CPML correction itself (slabs registered after a periodic boundary are post ops, and
+    // periodic boundaries are excluded above anyway) and needs the second psi_E buffer
+    if (!d->slabs[s].fused || (d->slabs[s].psi_count > 0 && !d->psi_E2[s])) return false;
+  }
+#ifndef FDTD_EMU
+  return d->Nx >= 8 && d->Ny >= 8 && d->Nz >= 32 * vec;
+#else
+  return d->Nx >= 2;     // (CPU tests: small grids with partial tiles exercise every branch)
+#endif
+}
+
+// what an x-sharded slab adds to a fused step
+struct FusedShard {
+  void* push_y;        // the left neighbour's ghost planes (in ITS output buffer) for E_new[plane 0], or null
+  void* push_z;
+  int skip_last_h;     // the H update of the last local plane is a separate launch (it waits for the right neighbour)
+};
+
+template <typename T>
+int fused_detectors(const fdtd_desc* d, void* const* Eout, void* const* Hout, int64_t slot, void* stream) {
+  for (int n = 0; n < d->n_detectors; ++n) {
+    const fdtd_detector& D = d->detectors[n];
+    if (D.n == 0) continue;
+    if (slot < 0 || slot >= D.capacity) return fail(FDTD_ERR_ARG, "detector %d: ring slot outside capacity", n);
+    FDTD_LAUNCH((fdtd::detector_kernel<T>), dim3(blocks_for((i64)D.n * 3)), dim3(256), stream, (const T*)Eout[0],
+                (const T*)Eout[1], (const T*)Eout[2], (const i64*)D.idx, (const int*)D.pos, D.n, (T*)D.ring_E,
+                (i64)slot);
+    int rc = check_launch("detector");
+    if (rc) return rc;
+    FDTD_LAUNCH((fdtd::detector_kernel<T>), dim3(blocks_for((i64)D.n * 3)), dim3(256), stream, (const T*)Hout[0],
+                (const T*)Hout[1], (const T*)Hout[2], (const i64*)D.idx, (const int*)D.pos, D.n, (T*)D.ring_H,
+                (i64)slot);
+    rc = check_launch("detector");
+    if (rc) return rc;
+  }
+  return FDTD_OK;
+}
+
+// one full step reading (Ein, Hin) and writing (Eout, Hout); parity 0: psi_E -> psi_E2, 1: back
+template <typename T>
+int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void* const* Hin, void* const* Hout,
+                  int64_t q, int64_t slot, void* stream, int parity, const FusedShard* shard = nullptr) {
+  const int Nx = d->Nx, Ny = d->Ny, Nz = d->Nz;
+  int rc;
+  fdtd::FusedParams<T> P;
+  memset(&P, 0, sizeof(P));
+  for (int n = 0; n < d->n_sources; ++n) {
+    const fdtd_source& S = d->sources[n];
+    int64_t w = q - S.wave_q0;
+    if (w < 0 || w >= S.wave_len)
+      return fail(FDTD_ERR_ARG, "source %d: step %lld outside its waveform table", n, (long long)q);
+    if (S.n == 0) continue;
+    fdtd::SrcK<T>& K = P.src[P.n_src++];
+    K.kind = S.kind;
+    K.comp = S.comp;
+    K.n = S.n;
+    for (int k = 0; k < 6; ++k) K.bb[k] = S.bbox[k];
+    K.idx = (const i64*)S.idx;
+    K.profile = (const T*)S.profile;
+    K.wave = (const T*)S.wave;
+    K.w = w;
+  }
+  constexpr int VEC = sizeof(T) == 4 ? 4 : 2;
+  P.Nx = Nx;
+  P.Ny = Ny;
+  P.Nz = Nz;
+  P.plane = d->plane;
+  P.x_offset = d->x_offset;
+  P.Nx_global = d->Nx_global;
+  if (shard) {
+    P.push_y = (T*)shard->push_y;
+    P.push_z = (T*)shard->push_z;
+    P.skip_last_h = shard->skip_last_h;
+  }
+  P.x0 = 0; P.x1 = Nx; P.y0 = 0; P.y1 = Ny; P.z0 = 0; P.z1 = Nz;
+  P.x_chunk = d->x_chunk > 0 ? d->x_chunk : 32;
+  for (int c = 0; c < 3; ++c) {
+    P.Ein[c] = (const T*)Ein[c];
+    P.Eout[c] = (T*)Eout[c];
+    P.Hin[c] = (const T*)Hin[c];
+    P.Hout[c] = (T*)Hout[c];
+    P.ce[c] = rounded_product<T>(d->courant, d->bg_inv_eps[c]);
+    P.ch[c] = rounded_product<T>(d->courant, d->bg_inv_mu[c]);
+  }
+  // every slab inside the kernel, registration order: psi_E read from one buffer and written to the other
+  for (int s = 0; s < d->n_slabs; ++s) {
+    const fdtd_slab& S = d->slabs[s];
+    if (S.psi_count == 0) continue;
+    typename fdtd::FusedParams<T>::Slab& K = P.sl[P.n_sl++];
+    K.axis = S.axis;
+    K.lo = S.axis == 0 ? S.lo - d->x_offset : S.lo;
+    K.xs = S.x0;
+    K.xe = S.x1;
+    K.t = S.thickness;
+    K.lo_al = z_slab_lo(S);
+    K.tp = z_slab_row(S);
+    K.count = S.psi_count;
+    K.psiE_in = (const T*)(parity == 0 ? S.psi_E : d->psi_E2[s]);
+    K.psiE_out = (T*)(parity == 0 ? d->psi_E2[s] : S.psi_E);
+    K.psiH = (T*)S.psi_H;
+    K.bE = (const T*)S.bE;
+    K.cE = (const T*)S.cE;
+    K.bH = (const T*)S.bH;
+    K.cH = (const T*)S.cH;
+  }
+  using Lay = fdtd::FusedPipeLayout<T, VEC>;
+  const unsigned chunks = (Nx + P.x_chunk - 1) / P.x_chunk;
+  dim3 grid((Nz + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC), (Ny + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);
+  dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
+  if (grid.y > 65535u || grid.z > 65535u) return fail(FDTD_ERR_UNSUPPORTED, "grid too large for one launch");
+#ifndef FDTD_EMU
+  static bool configured = false;      // (per instantiation: one kernel function each)
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::BYTES);
+    if (e != cudaSuccess) return fail(FDTD_ERR_CUDA, "cudaFuncSetAttribute(smem %zu): %s", Lay::BYTES, cudaGetErrorString(e));
+    // two blocks per SM only fit with the shared-memory carve-out at its maximum
+    cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+#endif
+  FDTD_LAUNCH_SMEM((fdtd::fused_eh_pipe_kernel<T, VEC>), grid, block, Lay::BYTES, stream, P);
+  rc = check_launch("fused_eh");
+  if (rc) return rc;
+  // detectors on the new fields (a sharded step samples after its last H plane)
+  if (!shard) return fused_detectors<T>(d, Eout, Hout, slot, stream);
+  return FDTD_OK;
+}
+}  // namespace
+}  // extern "C++"
+
 // ---- a whole half-step / run of an x-sharded slab on the C side (no host work between the steps) -----------
 #ifdef FDTD_EMU
 int fdtd_sharded_halfstep(const fdtd_desc*, fdtd_halo*, int32_t, int64_t, int64_t, void*) {
@@ -812,6 +988,7 @@ int fdtd_sharded_halfstep(const fdtd_desc*, fdtd_halo*, int32_t, int64_t, int64_
 int fdtd_run_sharded(const fdtd_desc*, fdtd_halo*, int64_t, int64_t, int64_t, void*) {
   return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA");
 }
+int fdtd_fuse_eh_sharded_active(const fdtd_desc*, const fdtd_halo*) { return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA"); }
 int fdtd_halo_refresh(const fdtd_desc*, fdtd_halo*, void*) { return fail(FDTD_ERR_UNSUPPORTED, "peer-to-peer halo needs CUDA"); }
 #else
 extern "C++" {
@@ -904,6 +1081,72 @@ int sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int field, int64_t q, int
 }  // namespace
 }  // extern "C++"
 
+extern "C++" {
+namespace {
+bool fuse_eh_sharded(const fdtd_desc* d, const fdtd_halo* h) {
+  if (!fuse_eh_eligible(d, true)) return false;
+  if (h->has_left && (!h->left_ghost_y2 || !h->left_ghost_z2)) return false;
+  if (h->has_right && (!h->right_ghost_y2 || !h->right_ghost_z2)) return false;
+  return true;
+}
+
+// One temporally fused step of an x-sharded slab, reading buffer pair (Ein, Hin) and writing (Eout, Hout).
+//   1. wait for the left neighbour's last H plane of the PREVIOUS step (the ghost of Hin);
+//   2. the fused kernel: E_new everywhere -- plane 0 also stored into the left neighbour's ghost of ITS Eout -- and
+//      H_new on all planes but the last one; then the flag that publishes plane 0;
+//   3. wait for the right neighbour's E_new[0] in the ghost of Eout, then the H update of the last plane with the
+//      ordinary half-step kernel (Hin -> Hout, curls from Eout), stored into the right neighbour's ghost of ITS Hout
+//      as well, and the flag that publishes it;
+//   4. detectors.
+// Flags and counts are the ones of the two-half-step protocol (one E push and one H push per step), so fused and
+// ordinary steps can follow each other.
+template <typename T>
+int fused_sharded_step(const fdtd_desc* d, fdtd_halo* h, int parity, int64_t q, int64_t slot, void* stream) {
+  void* const* Ein = parity == 0 ? d->E : d->E2;
+  void* const* Eout = parity == 0 ? d->E2 : d->E;
+  void* const* Hin = parity == 0 ? d->H : d->H2;
+  void* const* Hout = parity == 0 ? d->H2 : d->H;
+  int rc;
+  if (h->has_left) {
+    FDTD_LAUNCH((fdtd::halo_wait_kernel), dim3(1), dim3(32), stream, (const i64*)h->flags + 1, (i64)h->count[1],
+                (int*)h->error, (i64)h->timeout_ns);
+    if ((rc = check_launch("halo_wait")) != 0) return rc;
+  }
+  FusedShard sh;
+  sh.push_y = h->has_left ? (parity == 0 ? h->left_ghost_y2 : h->left_ghost_y) : nullptr;
+  sh.push_z = h->has_left ? (parity == 0 ? h->left_ghost_z2 : h->left_ghost_z) : nullptr;
+  sh.skip_last_h = h->has_right;
+  if ((rc = fused_eh_step<T>(d, Ein, Eout, Hin, Hout, q, slot, stream, parity, &sh)) != 0) return rc;
+  if (h->has_left) {
+    FDTD_LAUNCH((fdtd::halo_signal_kernel), dim3(1), dim3(32), stream, (i64*)h->left_flag, (i64)(h->count[0] + 1));
+    if ((rc = check_launch("halo_signal")) != 0) return rc;
+  }
+  h->count[0] += 1;
+  if (h->has_right) {
+    FDTD_LAUNCH((fdtd::halo_wait_kernel), dim3(1), dim3(32), stream, (const i64*)h->flags, (i64)h->count[0],
+                (int*)h->error, (i64)h->timeout_ns);
+    if ((rc = check_launch("halo_wait")) != 0) return rc;
+    Buffers buf{Hin, Hout, Eout};
+    rc = launch_halfstep_run<T, false, T>(d, d->Nx - 1, d->Nx, q, slot, stream, -1,
+                                          parity == 0 ? h->right_ghost_y2 : h->right_ghost_y,
+                                          parity == 0 ? h->right_ghost_z2 : h->right_ghost_z, true, &buf);
+    if (rc) return rc;
+    FDTD_LAUNCH((fdtd::halo_signal_kernel), dim3(1), dim3(32), stream, (i64*)h->right_flag, (i64)(h->count[1] + 1));
+    if ((rc = check_launch("halo_signal")) != 0) return rc;
+  }
+  h->count[1] += 1;
+  return fused_detectors<T>(d, Eout, Hout, slot, stream);
+}
+}  // namespace
+}  // extern "C++"
+
+int fdtd_fuse_eh_sharded_active(const fdtd_desc* d, const fdtd_halo* h) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if ((rc = check_halo(d, h)) != 0) return rc;
+  return fuse_eh_sharded(d, h) ? 1 : 0;
+}
+
 int fdtd_sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int32_t field, int64_t q, int64_t slot, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
@@ -921,7 +1164,20 @@ int fdtd_run_sharded(const fdtd_desc* d, fdtd_halo* h, int64_t q0, int64_t nstep
   if (nsteps < 0) return fail(FDTD_ERR_ARG, "nsteps < 0");
   if (d->x_wrap) return fail(FDTD_ERR_UNSUPPORTED, "periodic x boundary across slabs: drive the parts yourself");
   if ((rc = g_join.ensure()) != 0) return rc;
-  for (int64_t s = 0; s < nsteps; ++s) {
+  int64_t s = 0;
+  if (nsteps >= 2 && fuse_eh_sharded(d, h)) {
+    // pairs of temporally fused steps, A -> B -> A: the caller's buffers hold the result again.  Everything that is
+    // still running on the side stream (the boundary plane of an earlier two-half-step step) comes first.
+    if ((rc = stream_after((cudaStream_t)stream, (cudaStream_t)h->side_stream, g_join.to_main)) != 0) return rc;
+    for (; s + 2 <= nsteps; s += 2) {
+      for (int parity = 0; parity < 2; ++parity) {
+        rc = d->dtype == FDTD_F32 ? fused_sharded_step<float>(d, h, parity, q0 + s + parity, slot0 + s + parity, stream)
+                                  : fused_sharded_step<double>(d, h, parity, q0 + s + parity, slot0 + s + parity, stream);
+        if (rc) return rc;
+      }
+    }
+  }
+  for (; s < nsteps; ++s) {
     for (int field = 0; field < 2; ++field) {
       rc = (d->dtype == FDTD_F32 ? sharded_halfstep<float, float>(d, h, field, q0 + s, slot0 + s, stream) : d->dtype == FDTD_F64 ? sharded_halfstep<double, double>(d, h, field, q0 + s, slot0 + s, stream) : sharded_halfstep<float, double>(d, h, field, q0 + s, slot0 + s, stream));
       if (rc) return rc;
@@ -957,145 +1213,6 @@ int fdtd_halo_refresh(const fdtd_desc* d, fdtd_halo* h, void* stream) {
   return FDTD_OK;
 }
 #endif
-
-// ---- temporally fused E+H steps (yee_fused_eh.cuh) --------------------------------------------------------
-extern "C++" {
-namespace {
-#ifndef FDTD_FUSE_EH_MIN_CELLS
-#ifdef FDTD_EMU
-#define FDTD_FUSE_EH_MIN_CELLS 0
-#else
-#define FDTD_FUSE_EH_MIN_CELLS 600000000LL   // below, the 7 x 124-cell tiles quantise badly and the two half-steps win
-#endif
-#endif
-
-// fuse_eh = 1: wherever it is legal; fuse_eh = 2: only where it is also faster (large grids)
-bool fuse_eh_eligible(const fdtd_desc* d) {
-  if (!d->fuse_eh || d->dtype == FDTD_F32X) return false;
-  for (int c = 0; c < 3; ++c)
-    if (!d->E2[c] || !d->H2[c] || d->inv_eps[c] || d->inv_mu[c] || d->absorb[c]) return false;
-  if (d->Nx != d->Nx_global || d->n_post != 0 || d->n_deep != 0) return false;
-  const int vec = d->dtype == FDTD_F32 ? 4 : 2;
-  if (d->Nz % vec) return false;
-  if (d->fuse_eh == 2 && (int64_t)d->Nx * d->Ny * d->Nz < FDTD_FUSE_EH_MIN_CELLS) return false;
-  int nsrc = 0;
-  for (int n = 0; n < d->n_sources; ++n) {
-    if (d->sources[n].kind != FDTD_SRC_POINTS || d->sources[n].field != 0) return false;
-    ++nsrc;
-  }
-  if (nsrc > FDTD_FUSED_MAX) return false;
-  for (int n = 0; n < d->n_detectors; ++n)
-    if (d->detectors[n].kind != FDTD_DET_FIELD) return false;
-  for (int s = 0; s < d->n_slabs; ++s) {
-    // the kernel applies every CPML correction itself (slabs registered after a periodic boundary are post ops, and
-    // periodic boundaries are excluded above anyway) and needs the second psi_E buffer
-    if (!d->slabs[s].fused || (d->slabs[s].psi_count > 0 && !d->psi_E2[s])) return false;
-  }
-#ifndef FDTD_EMU
-  return d->Nx >= 8 && d->Ny >= 8 && d->Nz >= 32 * vec;
-#else
-  return d->Nx >= 2;     // (CPU tests: small grids with partial tiles exercise every branch)
-#endif
-}
-
-// one full step reading (Ein, Hin) and writing (Eout, Hout); parity 0: psi_E -> psi_E2, 1: back
-template <typename T>
-int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void* const* Hin, void* const* Hout,
-                  int64_t q, int64_t slot, void* stream, int parity) {
-  const int Nx = d->Nx, Ny = d->Ny, Nz = d->Nz;
-  int rc;
-  fdtd::FusedParams<T> P;
-  memset(&P, 0, sizeof(P));
-  for (int n = 0; n < d->n_sources; ++n) {
-    const fdtd_source& S = d->sources[n];
-    int64_t w = q - S.wave_q0;
-    if (w < 0 || w >= S.wave_len)
-      return fail(FDTD_ERR_ARG, "source %d: step %lld outside its waveform table", n, (long long)q);
-    if (S.n == 0) continue;
-    fdtd::SrcK<T>& K = P.src[P.n_src++];
-    K.kind = S.kind;
-    K.comp = S.comp;
-    K.n = S.n;
-    for (int k = 0; k < 6; ++k) K.bb[k] = S.bbox[k];
-    K.idx = (const i64*)S.idx;
-    K.profile = (const T*)S.profile;
-    K.wave = (const T*)S.wave;
-    K.w = w;
-  }
-  constexpr int VEC = sizeof(T) == 4 ? 4 : 2;
-  P.Nx = Nx;
-  P.Ny = Ny;
-  P.Nz = Nz;
-  P.plane = d->plane;
-  P.x0 = 0; P.x1 = Nx; P.y0 = 0; P.y1 = Ny; P.z0 = 0; P.z1 = Nz;
-  P.x_chunk = d->x_chunk > 0 ? d->x_chunk : 32;
-  for (int c = 0; c < 3; ++c) {
-    P.Ein[c] = (const T*)Ein[c];
-    P.Eout[c] = (T*)Eout[c];
-    P.Hin[c] = (const T*)Hin[c];
-    P.Hout[c] = (T*)Hout[c];
-    P.ce[c] = rounded_product<T>(d->courant, d->bg_inv_eps[c]);
-    P.ch[c] = rounded_product<T>(d->courant, d->bg_inv_mu[c]);
-  }
-  // every slab inside the kernel, registration order: psi_E read from one buffer and written to the other
-  for (int s = 0; s < d->n_slabs; ++s) {
-    const fdtd_slab& S = d->slabs[s];
-    if (S.psi_count == 0) continue;
-    typename fdtd::FusedParams<T>::Slab& K = P.sl[P.n_sl++];
-    K.axis = S.axis;
-    K.lo = S.lo;
-    K.t = S.thickness;
-    K.lo_al = z_slab_lo(S);
-    K.tp = z_slab_row(S);
-    K.count = S.psi_count;
-    K.psiE_in = (const T*)(parity == 0 ? S.psi_E : d->psi_E2[s]);
-    K.psiE_out = (T*)(parity == 0 ? d->psi_E2[s] : S.psi_E);
-    K.psiH = (T*)S.psi_H;
-    K.bE = (const T*)S.bE;
-    K.cE = (const T*)S.cE;
-    K.bH = (const T*)S.bH;
-    K.cH = (const T*)S.cH;
-  }
-  using Lay = fdtd::FusedPipeLayout<T, VEC>;
-  const unsigned chunks = (Nx + P.x_chunk - 1) / P.x_chunk;
-  dim3 grid((Nz + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC), (Ny + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);
-  dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
-  if (grid.y > 65535u || grid.z > 65535u) return fail(FDTD_ERR_UNSUPPORTED, "grid too large for one launch");
-#ifndef FDTD_EMU
-  static bool configured = false;      // (per instantiation: one kernel function each)
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::BYTES);
-    if (e != cudaSuccess) return fail(FDTD_ERR_CUDA, "cudaFuncSetAttribute(smem %zu): %s", Lay::BYTES, cudaGetErrorString(e));
-    // two blocks per SM only fit with the shared-memory carve-out at its maximum
-    cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         (int)cudaSharedmemCarveoutMaxShared);
-    configured = true;
-  }
-#endif
-  FDTD_LAUNCH_SMEM((fdtd::fused_eh_pipe_kernel<T, VEC>), grid, block, Lay::BYTES, stream, P);
-  rc = check_launch("fused_eh");
-  if (rc) return rc;
-  // detectors on the new fields
-  for (int n = 0; n < d->n_detectors; ++n) {
-    const fdtd_detector& D = d->detectors[n];
-    if (D.n == 0) continue;
-    if (slot < 0 || slot >= D.capacity) return fail(FDTD_ERR_ARG, "detector %d: ring slot outside capacity", n);
-    FDTD_LAUNCH((fdtd::detector_kernel<T>), dim3(blocks_for((i64)D.n * 3)), dim3(256), stream, (const T*)Eout[0],
-                (const T*)Eout[1], (const T*)Eout[2], (const i64*)D.idx, (const int*)D.pos, D.n, (T*)D.ring_E,
-                (i64)slot);
-    rc = check_launch("detector");
-    if (rc) return rc;
-    FDTD_LAUNCH((fdtd::detector_kernel<T>), dim3(blocks_for((i64)D.n * 3)), dim3(256), stream, (const T*)Hout[0],
-                (const T*)Hout[1], (const T*)Hout[2], (const i64*)D.idx, (const int*)D.pos, D.n, (T*)D.ring_H,
-                (i64)slot);
-    rc = check_launch("detector");
-    if (rc) return rc;
-  }
-  return FDTD_OK;
-}
-}  // namespace
-}  // extern "C++"
 
 #ifndef FDTD_EMU
 // ---- CUDA-graph replay of step chunks (small, launch-bound grids) ---------------------------------

@@ -37,10 +37,20 @@ struct FusedParams {
   SrcK<T> src[FDTD_FUSED_MAX];  // soft point-list sources on E (ascending idx)
   // the box is the WHOLE grid: every CPML slab and the masked one-sided differences at the six faces are handled
   // inside the kernel, in registration order.  psi_E is ping-pong like the fields, psi_H in place.
-  int Nx;
+  int Nx;          // first x index without a plane of its own in Eout: the local extent, + 1 when a right neighbour's
+                   // first plane lies in the ghost plane behind it
+  // x-sharded slabs: global index of local plane 0 and the global extent (the face masks are global), the peer's ghost
+  // planes the y / z components of E_new[plane 0] are stored into as well (or null), and whether the H update of the
+  // LAST local plane is left to a separate launch (it needs the right neighbour's E_new, which arrives meanwhile)
+  int x_offset, Nx_global;
+  T* push_y;
+  T* push_z;
+  int skip_last_h;
   int n_sl;
   struct Slab {
-    int axis, lo, t, lo_al, tp;   // lo_al / tp: padded psi rows of z slabs (include/fdtd_b200.h)
+    int axis, lo, t, lo_al, tp;   // lo: LOCAL coordinate of the slab's first cell along its axis (x slabs: may be
+                                  // negative on a slab that starts inside it); lo_al / tp: padded psi rows of z slabs
+    int xs, xe;                   // x slabs: local planes [xs, xe) have psi storage
     i64 count;
     const T* psiE_in;
     T* psiE_out;
@@ -239,7 +249,7 @@ FDTD_DEV void fused_stage_issue(const FusedParams<T>& P, T* stage, i64 off, int 
 template <typename T, int VEC>
 FDTD_DEV i64 fused_psi_index(const typename FusedParams<T>::Slab& S, int i, int j, int k0, i64 plane, i64 p, int Ny,
                              int Nz) {
-  if (S.axis == 0) return (i64)(i - S.lo) * plane + p;
+  if (S.axis == 0) return (i64)(i - S.xs) * plane + p;
   if (S.axis == 1) return ((i64)i * S.t + (j - S.lo)) * Nz + k0;
   return ((i64)i * Ny + j) * S.tp + (k0 - S.lo_al);
 }
@@ -304,14 +314,15 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   }
 
   Pack<T, VEC> hp0, hp1, hp2, ep0, ep1, ep2;
-  if (active && inside && xa > 0) {
+  if (active && inside && xa + P.x_offset > 0) {
     const i64 o = (i64)(xa - 1) * plane + p;
     hp0 = ldv<T, VEC>(P.Hin[0] + o);
     hp1 = ldv<T, VEC>(P.Hin[1] + o);
     hp2 = ldv<T, VEC>(P.Hin[2] + o);
   }
 
-  for (int i = xa; i <= xb; ++i) {
+  const int xl = (P.skip_last_h && xb == P.x1) ? xb - 1 : xb;   // (see FusedParams::skip_last_h)
+  for (int i = xa; i <= xl; ++i) {
     FDTD_CP_ASYNC_WAIT_1();
     __syncthreads();
     {
@@ -329,13 +340,13 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
         const typename FusedParams<T>::Slab& S = P.sl[s];
         const bool yz = ((sl_hit >> s) & 1u) != 0;
         if (!yz && S.axis != 0) continue;
-        if (ip < xb && ip < P.x1 && (yz || (ip >= S.lo && ip < S.lo + S.t))) {
+        if (ip < xb && ip < P.x1 && (yz || (ip >= S.xs && ip < S.xe))) {
           const i64 idx = fused_psi_index<T, VEC>(S, ip, j, k0, plane, p, P.Ny, Nz);
           fused_prefetch(S.psiE_in + idx);
           fused_prefetch(S.psiE_in + S.count + idx);
         }
         const int ih = ip - 1;      // (psi_H belongs to the owner of the cell only: the halo threads never touch it)
-        if (core && ih >= xa && ih < xb && (yz || (ih >= S.lo && ih < S.lo + S.t))) {
+        if (core && ih >= xa && ih < xb && (yz || (ih >= S.xs && ih < S.xe))) {
           const i64 idx = fused_psi_index<T, VEC>(S, ih, j, k0, plane, p, P.Ny, Nz);
           fused_prefetch(S.psiH + idx);
           fused_prefetch(S.psiH + S.count + idx);
@@ -362,7 +373,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     unsigned hit_now = sl_hit;   // + the x slabs plane i lies in (the same for the whole block)
     for (unsigned m = xs_bits; m != 0; m &= m - 1) {
       const int s = FDTD_FFS(m) - 1;
-      hit_now |= (i >= P.sl[s].lo && i < P.sl[s].lo + P.sl[s].t) ? (1u << s) : 0u;
+      hit_now |= (i >= P.sl[s].xs && i < P.sl[s].xe) ? (1u << s) : 0u;
     }
     const i64 off = (i64)i * plane + p;
     Pack<T, VEC> e0, e1, e2, h0, h1, h2;
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
           const T zn0 = e == 0 ? zs0 : h0.v[e > 0 ? e - 1 : 0];
           const T zn1 = e == 0 ? zs1 : h1.v[e > 0 ? e - 1 : 0];
           // backward differences are masked on the faces i = 0, j = 0 and k = 0 (fdtd/grid.py:66-74)
-          const bool face_x = i == 0;
+          const bool face_x = i + P.x_offset == 0;
           const bool face_y = j == 0;
           const bool face_z = (e == 0) && (k0 == 0);
           const T d_zy = face_y ? T(0) : h2.v[e] - y2v.v[e];
@@ -416,7 +427,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
           const typename FusedParams<T>::Slab& S = P.sl[s];
           const bool store = core && i < xb;
           if (S.axis == 0) {
-            fused_slab_cells<T, VEC, true, 0>(S, S.psiE_in, S.psiE_out, store, (i64)(i - S.lo) * plane + p, i - S.lo,
+            fused_slab_cells<T, VEC, true, 0>(S, S.psiE_in, S.psiE_out, store, (i64)(i - S.xs) * plane + p, i - S.lo,
                                               D, e0, e1, e2, P.ce);
           } else {
             if (S.axis == 1)
@@ -433,6 +444,11 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
           stv<T, VEC>(P.Eout[0] + off, e0);
           stv<T, VEC>(P.Eout[1] + off, e1);
           stv<T, VEC>(P.Eout[2] + off, e2);
+          if (i == 0 && P.push_y != nullptr) {
+            // the slab's boundary plane also goes into the left neighbour's ghost plane, over NVLink
+            stv<T, VEC>(P.push_y + p, e1);
+            stv<T, VEC>(P.push_z + p, e2);
+          }
         }
       } else if (i < P.Nx) {
         // a shell cell (outside the box in y / z, or the plane x1): its E_new is already in memory
@@ -455,7 +471,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
         const T ex_z = e == VEC - 1 ? x[VEC] : ep0.v[e < VEC - 1 ? e + 1 : 0];
         const T ey_z = e == VEC - 1 ? x[XC + VEC] : ep1.v[e < VEC - 1 ? e + 1 : 0];
         // forward differences are masked on the faces i = Nx-1, j = Ny-1 and k = Nz-1 (fdtd/grid.py:41-49)
-        const bool face_x = i == P.Nx;
+        const bool face_x = i + P.x_offset == P.Nx_global;
         const bool face_y = j == P.Ny - 1;
         const bool face_z = (e == VEC - 1) && (k0 + VEC == Nz);
         const T d_zy = face_y ? T(0) : ez_y - ep2.v[e];
@@ -481,7 +497,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
         if (!((hit_prev >> s) & 1u)) continue;
         const typename FusedParams<T>::Slab& S = P.sl[s];
         if (S.axis == 0) {
-          fused_slab_cells<T, VEC, false, 0>(S, S.psiH, S.psiH, true, (i64)(ih - S.lo) * plane + p, ih - S.lo, D, hx,
+          fused_slab_cells<T, VEC, false, 0>(S, S.psiH, S.psiH, true, (i64)(ih - S.xs) * plane + p, ih - S.lo, D, hx,
                                              hy, hz, P.ch);
         } else {
           if (S.axis == 1)

@@ -294,20 +294,34 @@ class Engine:
         # a second psi_E per slab: homogeneous, unsharded grids only.  grid._fuse_eh / FDTD_B200_FUSE_EH: 0 never,
         # 1 wherever legal, 2 (default) where it is also faster -- large grids -- and the buffers fit in free memory
         want = g._fuse_eh
-        big = part.nx * g.Ny * g.Nz >= FUSE_EH_MIN_CELLS
-        if (want and not part.sharded and not self._hooked and ie_eff is None and imu is None and not post
-                and g._sdtype is g._dtype and (want == 1 or big)):
-            if g._E2 is None and (want == 1 or self._room_for(2 * g._E.numel() * g._E.element_size())):
+        big = g.Nx * g.Ny * g.Nz >= FUSE_EH_MIN_CELLS
+        ok = bool(want and not self._hooked and ie_eff is None and imu is None and not post and not x_wrap
+                  and g._sdtype is g._dtype and (want == 1 or big)
+                  and all(d.sources[k].kind == _capi.SRC_POINTS and d.sources[k].field == 0 for k in range(d.n_sources))
+                  and all(det._kind == _capi.DET_FIELD for det in self._dets) and d.n_sources <= _capi.FUSED_MAX)
+        if part.sharded:
+            # x-slabs: peer-to-peer halo only (the boundary planes go into the neighbours' second buffers), and every
+            # rank must decide alike -- free memory included
+            import os
+            ok = ok and g._E.is_cuda and os.environ.get("FDTD_B200_HALO", "p2p") == "p2p" and self._p2p is not False
+        if ok and g._E2 is None:
+            ok = want == 1 or self._room_for(2 * g._E.numel() * g._E.element_size())
+        if part.sharded and g._E.is_cuda:
+            import torch.distributed as dist
+            flag = torch.tensor([int(ok)], device=g._E.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+        if ok:
+            if g._E2 is None:
                 g._E2, g._H2 = torch.zeros_like(g._E), torch.zeros_like(g._H)
-            if g._E2 is not None:
-                for c in range(3):
-                    d.E2[c] = g._E2[c, 1].data_ptr()
-                    d.H2[c] = g._H2[c, 1].data_ptr()
-                d.fuse_eh = 1 if want == 1 else 2
-                for idx, b in enumerate(slabs):          # psi_E ping-pong (include/fdtd_b200.h, psi_E2)
-                    if getattr(b, "_psi_E2", None) is None:
-                        b._psi_E2 = torch.zeros_like(b._psi_E)
-                    d.psi_E2[idx] = _ptr(b._psi_E2)
+            for c in range(3):
+                d.E2[c] = g._E2[c, 1].data_ptr()
+                d.H2[c] = g._H2[c, 1].data_ptr()
+            d.fuse_eh = 1 if want == 1 else 2
+            for idx, b in enumerate(slabs):          # psi_E ping-pong (include/fdtd_b200.h, psi_E2)
+                if getattr(b, "_psi_E2", None) is None:
+                    b._psi_E2 = torch.zeros_like(b._psi_E)
+                d.psi_E2[idx] = _ptr(b._psi_E2)
 
         # CUDA-graph replay of step chunks pays off where a step is launch-bound (small grids)
         self._dyn = torch.zeros(2, dtype=torch.int64, device=g._E.device)
@@ -347,7 +361,8 @@ class Engine:
             want, self._p2p = "nccl", False
         if self._p2p is None and g._E.is_cuda and want == "p2p":
             try:
-                self._p2p = P2PHalo(g._part, g._E, g._H, self.lib)
+                self._p2p = P2PHalo(g._part, g._E, g._H, self.lib, g._E2 if d.fuse_eh else None,
+                                    g._H2 if d.fuse_eh else None)
             except Exception as exc:                          # IPC refused (e.g. no peer access): NCCL path
                 import warnings
                 warnings.warn(f"fdtd_b200: peer-to-peer halo unavailable ({exc}); using NCCL send/recv")

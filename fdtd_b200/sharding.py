@@ -186,10 +186,11 @@ class P2PHalo:
     dependency chain of the flags is the back-pressure).  A wait that exceeds FDTD_B200_HALO_TIMEOUT_S (default
     120 s) raises the error word and traps, so a dead neighbour can never turn into a silently wrong result."""
 
-    def __init__(self, part, E, H, lib):
+    def __init__(self, part, E, H, lib, E2=None, H2=None):
         import ctypes as C
         from . import _capi
         self.part, self.E, self.H, self.lib = part, E, H, lib
+        self.fused_buffers = E2 is not None and H2 is not None     # second field buffers of temporally fused steps
         self.cuda = True
         dev = E.device
         self.stream = torch.cuda.Stream(device=dev)
@@ -217,6 +218,8 @@ class P2PHalo:
         # waiting, and either ALL ranks use peer-to-peer ghosts or none does
         try:
             mine = {"E": export(E), "H": export(H), "flags": export(self.flags), "nx": part.nx}
+            if self.fused_buffers:
+                mine.update(E2=export(E2), H2=export(H2))
         except Exception as exc:
             mine = {"error": str(exc)}
         everyone = [None] * part.world
@@ -237,12 +240,20 @@ class P2PHalo:
                     h.left_ghost_y = base + ((1 * (nxl + 2) + nxl + 1) * plane) * w
                     h.left_ghost_z = base + ((2 * (nxl + 2) + nxl + 1) * plane) * w
                     h.left_flag = open_(rec["flags"])
+                    if self.fused_buffers and "E2" in rec:
+                        base = open_(rec["E2"])
+                        h.left_ghost_y2 = base + ((1 * (nxl + 2) + nxl + 1) * plane) * w
+                        h.left_ghost_z2 = base + ((2 * (nxl + 2) + nxl + 1) * plane) * w
                 if h.has_right:                                     # H last plane -> right neighbour's low ghost
                     rec = everyone[part.rank + 1]
                     base, nxl = open_(rec["H"]), rec["nx"]
                     h.right_ghost_y = base + (1 * (nxl + 2) * plane) * w
                     h.right_ghost_z = base + (2 * (nxl + 2) * plane) * w
                     h.right_flag = open_(rec["flags"]) + 8
+                    if self.fused_buffers and "H2" in rec:
+                        base = open_(rec["H2"])
+                        h.right_ghost_y2 = base + (1 * (nxl + 2) * plane) * w
+                        h.right_ghost_z2 = base + (2 * (nxl + 2) * plane) * w
             except Exception as exc:
                 failure = str(exc)
         ok = torch.tensor([0 if failure else 1], device=dev)

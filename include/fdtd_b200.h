@@ -321,6 +321,10 @@ typedef struct fdtd_halo {
   void* left_ghost_z;            /*   ... of Ez: where this slab's E plane 0 goes after every E half-step */
   void* right_ghost_y;           /* RIGHT neighbour's LOW ghost plane of Hy */
   void* right_ghost_z;           /*   ... of Hz: where this slab's last H plane goes after every H half-step */
+  void* left_ghost_y2;           /* the same four ghost planes in the neighbours' SECOND field buffers (fdtd_desc E2 / H2): */
+  void* left_ghost_z2;           /*   a temporally fused step writes the other buffer of the ping-pong pair, and its    */
+  void* right_ghost_y2;          /*   boundary planes go into the neighbour's buffer of the same parity.  NULL: no      */
+  void* right_ghost_z2;          /*   fused steps on this slab                                                          */
   int64_t* left_flag;            /* left neighbour's flag word [0]: number of E pushes it has received */
   int64_t* right_flag;           /* right neighbour's flag word [1]: number of H pushes it has received */
   const int64_t* flags;          /* this rank's device int64[2], written by the neighbours */
@@ -343,6 +347,11 @@ int fdtd_sharded_halfstep(const fdtd_desc* d, fdtd_halo* h, int32_t field, int64
 /* Grid.run on an x-sharded slab: nsteps x { E half-step, H half-step } as above, no host work in between --
  * the ranks only meet through the flag words */
 int fdtd_run_sharded(const fdtd_desc* d, fdtd_halo* h, int64_t q0, int64_t nsteps, int64_t slot0, void* stream);
+/* 1 when fdtd_run_sharded will execute pairs of temporally fused E+H steps on this slab (d->fuse_eh, second buffers
+ * and their peer ghosts given, homogeneous grid, no periodic boundary, point sources on E only): per step one fused
+ * kernel that also stores E_new[plane 0] into the left neighbour's ghost, then -- once the right neighbour's E_new has
+ * arrived -- the H update of the last plane, stored into the right neighbour's ghost as well */
+int fdtd_fuse_eh_sharded_active(const fdtd_desc* d, const fdtd_halo* h);
 /* push both boundary planes and wait for the neighbours' (collective: every rank calls it; after the user wrote
  * E / H, and once after set-up) */
 int fdtd_halo_refresh(const fdtd_desc* d, fdtd_halo* h, void* stream);

@@ -39,6 +39,8 @@ def main():
         engine.RING_BYTES = int(os.environ["FDTD_TEST_RING_BYTES"])
     try:
         g = build(fd)
+        if os.environ.get("FDTD_TEST_FUSE_EH"):
+            g._fuse_eh = int(os.environ["FDTD_TEST_FUSE_EH"])
         if os.environ.get("FDTD_TEST_TRACK"):
             scenes.track_all(g, steps)
         g.run(0, progress_bar=False)           # bake: sharding restrictions surface here, on every rank alike
@@ -64,6 +66,9 @@ def main():
         res.update(slice_x=energy_slice(g, x=ix), slice_y=energy_slice(g, y=iy), slice_z=energy_slice(g, z=iz))
     if rank == 0:
         np.savez(out, **res)
+    if os.environ.get("FDTD_TEST_FUSE_EH") == "1":
+        import ctypes
+        assert g._engine.lib.fdtd_fuse_eh_sharded_active(ctypes.byref(g._engine.desc), ctypes.byref(g._engine._p2p.h)) == 1
     if backend != "gloo":
         if os.environ.get("FDTD_B200_HALO", "p2p") == "p2p":
             assert g._engine._p2p, "peer-to-peer halo was requested but not set up"

@@ -161,6 +161,26 @@ def current_x0(fd, n=(18, 12, 10), t=3):
     return g
 
 
+def fusedslab(fd, n=(40, 30, 136), t=5):
+    """a homogeneous grid (non-vacuum background) with six PMLs, sources in a slab corner, on a face and next to the
+    middle x-planes (the cuts of a 2- or 4-rank partition), detectors across the cuts: what the temporally fused
+    step of an x-sharded slab has to get right."""
+    g = fd.Grid(shape=n, grid_spacing=77.5e-9, permittivity=1.3, permeability=1.1)
+    g[0:t, :, :] = fd.PML()
+    g[-t:, :, :] = fd.PML()
+    g[:, 0:t, :] = fd.PML()
+    g[:, -t:, :] = fd.PML()
+    g[:, :, 0:t + 1] = fd.PML()
+    g[:, :, -t:] = fd.PML()
+    g[n[0] // 2, n[1] // 2, n[2] // 2] = fd.PointSource(period=17, name="at_the_cut")
+    g[n[0] // 2 - 1, n[1] // 2 + 2, n[2] // 3] = fd.PointSource(period=11, amplitude=0.4, name="left_of_the_cut")
+    g[1, 2, 3] = fd.PointSource(period=13, amplitude=0.3, name="corner")
+    g[n[0] // 4, n[1] // 2, 0] = fd.PointSource(period=9, amplitude=0.5, name="on_z_face")
+    g[2:n[0] - 2, n[1] // 2 + 1, n[2] // 2 + 2] = fd.LineDetector(name="across")
+    g[n[0] // 2 - 1:n[0] // 2, 3:5, n[2] - 3:n[2] - 2] = fd.BlockDetector(name="at_cut")
+    return g
+
+
 def c4small(fd, n=(32, 32, 32), t=6):
     """configs[3] shape (the bench workload) reduced: six PMLs, centre PointSource, LineDetector."""
     g = fd.Grid(shape=n, grid_spacing=77.5e-9)
