@@ -366,8 +366,33 @@ def sharded_parity(fd, wl, world, rank, steps=24):
         del s
     del g
     torch.cuda.synchronize()
-    return {"sharded_equals_single": bool(ok), "scene": f"{wl.name} structure on {list(got['E'].shape[:3])}, {steps} steps "
-            f"(run + step), {world} ranks, halo {halo}", "arrays": len(got), "worst_rel_l2": worst}
+    out = {"sharded_equals_single": bool(ok), "scene": f"{wl.name} structure on {list(got['E'].shape[:3])}, {steps} steps "
+           f"(run + step), {world} ranks, halo {halo}", "arrays": len(got), "worst_rel_l2": worst}
+    if wl.name == "c4":
+        # the temporally fused steps the full-size slabs run (pairs of single-pass E+H kernels, boundary planes into
+        # the neighbours' second buffers) against the unsharded two-half-step path
+        import ctypes
+        shape = (max(32, 8 * world), 40, 136)
+        g = build_c4(fd, shape, pml=5)
+        g._fuse_eh = 1
+        g.run(steps + 1, progress_bar=False)
+        eng = g._engine
+        active = bool(eng._p2p) and eng.lib.fdtd_fuse_eh_sharded_active(ctypes.byref(eng.desc), ctypes.byref(eng._p2p.h)) == 1
+        got = scenes.dump(g)
+        same = True
+        if rank == 0:
+            s = build_c4(fd, shape, pml=5, shard=False)
+            s._fuse_eh = 0
+            s.run(steps + 1, progress_bar=False)
+            want = scenes.dump(s)
+            same = all(np.array_equal(got[k], want[k]) for k in want) and float(np.abs(want["E"]).max()) > 0
+            del s
+        del g
+        torch.cuda.synchronize()
+        out["fused_steps"] = {"active": bool(active), "sharded_fused_equals_single_two_pass": bool(same),
+                              "scene": f"c4 structure on {list(shape)}, {steps + 1} steps"}
+        out["sharded_equals_single"] = bool(out["sharded_equals_single"] and same)
+    return out
 
 
 def main():

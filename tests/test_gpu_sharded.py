@@ -32,7 +32,7 @@ def test_sharded_equals_single(tmp_path, scene, dtype, halo):
         assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
 
 
-@pytest.mark.parametrize("scene,dtype,steps", [("c4small", "float32", 31), ("pml3d", "float64", 26),
+@pytest.mark.parametrize("scene,dtype,steps", [("fusedslab", "float32", 31), ("fusedslab", "float64", 26),
                                                ("fusedslab", "float32", 24)])
 def test_temporally_fused_steps_on_slabs(tmp_path, scene, dtype, steps):
     """x-sharded grids with grid._fuse_eh = 1: every rank runs pairs of single-pass E+H steps (the fused kernel stores
