@@ -23,6 +23,7 @@ RING_BYTES = 64 << 20          # detector ring budget per grid
 WAVE_TABLE_MIN = 1024          # look-ahead of the host waveform tables (steps)
 WAVE_TABLE_MAX = 1 << 16
 GRAPH_MAX_CELLS = 1 << 23      # grids up to this many cells replay CUDA graphs of 32-step chunks in run()
+FUSE_EH_MIN_SLAB = 192           # x-planes per rank from which fused steps also win on x-sharded grids
 FUSE_EH_MIN_CELLS = 600_000_000  # from here on the single-pass E+H kernel beats the two half-steps (automatic mode;
                                  # 768^3: -2 %, 896^3: +4 %, 1024^3: +8 %, profiles/r2_fused_sizes.txt)
 
@@ -301,9 +302,12 @@ class Engine:
                   and all(det._kind == _capi.DET_FIELD for det in self._dets) and d.n_sources <= _capi.FUSED_MAX)
         if part.sharded:
             # x-slabs: peer-to-peer halo only (the boundary planes go into the neighbours' second buffers), and every
-            # rank must decide alike -- free memory included
+            # rank must decide alike -- free memory included.  Thin slabs keep the two half-steps: a fused step ends in
+            # a serial tail (flag, last H plane, flag) that the bulk of a two-pass step hides, and few x-chunks fill
+            # the GPU badly (1024^3 on 8 B200, 128 planes each: 1.62 ms fused against 1.58; on 4: 3.04 against 3.16)
             import os
-            ok = ok and g._E.is_cuda and os.environ.get("FDTD_B200_HALO", "p2p") == "p2p" and self._p2p is not False
+            ok = (ok and g._E.is_cuda and os.environ.get("FDTD_B200_HALO", "p2p") == "p2p" and self._p2p is not False
+                  and (want == 1 or g.Nx // part.world >= FUSE_EH_MIN_SLAB))
         if ok and g._E2 is None:
             ok = want == 1 or self._room_for(2 * g._E.numel() * g._E.element_size())
         if part.sharded and g._E.is_cuda:
@@ -317,7 +321,7 @@ class Engine:
             for c in range(3):
                 d.E2[c] = g._E2[c, 1].data_ptr()
                 d.H2[c] = g._H2[c, 1].data_ptr()
-            d.fuse_eh = 1 if want == 1 else 2
+            d.fuse_eh = 1 if (want == 1 or part.sharded) else 2      # (sharded: decided here, collectively)
             for idx, b in enumerate(slabs):          # psi_E ping-pong (include/fdtd_b200.h, psi_E2)
                 if getattr(b, "_psi_E2", None) is None:
                     b._psi_E2 = torch.zeros_like(b._psi_E)
@@ -499,15 +503,16 @@ class Engine:
         return v != self._mat_versions
 
     # ------------------------------------------------------------------------------ per-run state
-    def _ensure_wave(self, q0, n):
-        """host-tabulated per-step source scalars covering steps [q0, q0+n)."""
+    def _ensure_wave(self, q0, n, lookahead=WAVE_TABLE_MIN):
+        """host-tabulated per-step source scalars covering steps [q0, q0+n); `lookahead`: how far beyond to tabulate
+        (step()-driven loops ask for one step at a time; run() knows its chunk)."""
         if not self._src_entries:
             return
         if self._wave is not None:
             a, ln = self._wave
             if a <= q0 and q0 + n <= a + ln:
                 return
-        ln = max(n, WAVE_TABLE_MIN)
+        ln = max(n, lookahead)
         g, d = self.grid, self.desc
         tables = {}
         for idx, src in self._src_entries:
@@ -660,7 +665,7 @@ class Engine:
             room = self.ring_capacity - g._ring_fill["E"] if rings else nsteps
             n = min(nsteps - done, room, WAVE_TABLE_MAX)
             q = q0 + done
-            self._ensure_wave(q, n)
+            self._ensure_wave(q, n, lookahead=min(WAVE_TABLE_MIN, -(-n // 32) * 32))
             if self._hooked:
                 # user plug-ins read grid.time_steps_passed like the reference's sources do: keep it current per step
                 for s in range(n):
