@@ -121,20 +121,21 @@ Geometry geometry(int dtype, int Ny, int Nz) {
 // r1_tune4_slabs.txt on B200): every chunk re-reads two carried planes (~0.32/chunk of a launch) and the
 // last, partially filled wave of blocks runs the memory system below capacity (~0.8/waves, 444 resident
 // blocks).  Pick the power of two in [4, 32] that minimises their sum.
-int default_x_chunk(const Geometry& g, int nx, int Ny, int Nz) {
+int default_x_chunk(const Geometry& g, int nx, int Ny, int Nz, int blocks_per_sm = 3) {
   const double tiles = (double)((Ny + g.tile_y - 1) / g.tile_y) * ((Nz + g.tile_z - 1) / g.tile_z);
+  const double resident = 148.0 * blocks_per_sm;
   int best = 4;
   double best_cost = 1e30;
   // grids too small to fill the GPU even with 4-plane chunks are latency bound: the march is serial, so the
   // shortest chunk (most blocks) wins
   // (161x97x1 quick-start grid: 15.2 / 20.3 / 27.1 / 45.5 us per step with 1 / 2 / 4 / 8 planes per block)
-  if (((nx + 3) / 4) * tiles <= 2 * 148.0 * 3) {
+  if (((nx + 3) / 4) * tiles <= 2 * resident) {
     for (int chunk = 1; chunk < 4; chunk *= 2)
-      if (((nx + chunk - 1) / chunk) * tiles <= 4 * 148.0 * 3) return chunk;
+      if (((nx + chunk - 1) / chunk) * tiles <= 4 * resident) return chunk;
     return 4;
   }
   for (int chunk = 4; chunk <= 32; chunk *= 2) {
-    const double waves = ((nx + chunk - 1) / chunk) * tiles / (148.0 * 3);
+    const double waves = ((nx + chunk - 1) / chunk) * tiles / resident;
     const double cost = 0.32 / chunk + 0.8 / waves;
     if (cost < best_cost) {
       best_cost = cost;
@@ -319,6 +320,29 @@ template <typename T, bool IS_E, typename A = T>
 int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64_t slot, void* stream,
                         int64_t graph_step, void* push_y, void* push_z, bool plain, const Buffers* buf = nullptr);
 
+#ifndef FDTD_EMU
+// The runs of one half-step touch disjoint x-planes of the updated field and only read the other one: they are
+// independent, so they go to a few side streams (forked from / joined into the caller's stream with events) and fill
+// the GPU together instead of each ending in its own partial wave of blocks.
+struct RunStreams {
+  static const int N = 3;
+  cudaStream_t side[N] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[N] = {nullptr, nullptr, nullptr};
+  bool ready = false;
+  bool ensure() {
+    if (ready) return true;
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
+    for (int n = 0; n < N; ++n)
+      if (cudaStreamCreateWithFlags(&side[n], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&join[n], cudaEventDisableTiming) != cudaSuccess)
+        return false;
+    ready = true;
+    return true;
+  }
+};
+thread_local RunStreams g_runs;
+#endif
+
 #ifndef FDTD_PLAIN_RUN_MIN
 #ifdef FDTD_EMU
 #define FDTD_PLAIN_RUN_MIN 2   // (CPU tests: small scenes must take the split path too)
@@ -342,6 +366,11 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
   auto is_plain = [&](int x) { return (d->plane_class[x] & bits) == 0; };
   const int push_plane = IS_E ? 0 : d->Nx - 1;
   int i = x_begin;
+  int n_run = 0;
+#ifndef FDTD_EMU
+  unsigned used = 0;
+  const bool concurrent = g_runs.ensure() && cudaEventRecord(g_runs.fork, (cudaStream_t)stream) == cudaSuccess;
+#endif
   while (i < x_end) {
     // the next run: planes of one kind; a short plain run is absorbed by the material run around it
     bool plain = is_plain(i);
@@ -358,11 +387,31 @@ int launch_halfstep(const fdtd_desc* d, int x_begin, int x_end, int64_t q, int64
       }
     }
     const bool has = push_y && push_plane >= i && push_plane < j;
-    int rc = launch_halfstep_run<T, IS_E, A>(d, i, j, q, slot, stream, graph_step, has ? push_y : nullptr,
+    void* run_stream = stream;
+#ifndef FDTD_EMU
+    // the first run stays on the caller's stream, the others rotate over the side streams
+    if (concurrent && n_run > 0) {
+      const int k = (n_run - 1) % RunStreams::N;
+      if (!(used & (1u << k)) && cudaStreamWaitEvent(g_runs.side[k], g_runs.fork, 0) != cudaSuccess)
+        return fail(FDTD_ERR_CUDA, "cudaStreamWaitEvent failed");
+      used |= 1u << k;
+      run_stream = g_runs.side[k];
+    }
+#endif
+    int rc = launch_halfstep_run<T, IS_E, A>(d, i, j, q, slot, run_stream, graph_step, has ? push_y : nullptr,
                                              has ? push_z : nullptr, plain);
     if (rc) return rc;
+    ++n_run;
     i = j;
   }
+#ifndef FDTD_EMU
+  for (int k = 0; k < RunStreams::N; ++k) {
+    if (!(used & (1u << k))) continue;
+    if (cudaEventRecord(g_runs.join[k], g_runs.side[k]) != cudaSuccess ||
+        cudaStreamWaitEvent((cudaStream_t)stream, g_runs.join[k], 0) != cudaSuccess)
+      return fail(FDTD_ERR_CUDA, "joining the run streams failed");
+  }
+#endif
   return FDTD_OK;
 }
 
@@ -381,7 +430,8 @@ int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, i
   P.x_begin = x_begin;
   P.x_end = x_end;
   P.x_chunk = d->x_chunk > 0 ? d->x_chunk
-                             : default_x_chunk(g, x_end - x_begin, d->Ny, d->Nz);
+                             : default_x_chunk(g, x_end - x_begin, d->Ny, d->Nz,
+                                               (sizeof(A) > sizeof(T) || (!plain && d->tile_class)) ? 2 : 3);
   P.lanes_z = g.lanes_z;
   P.lanes_shift = g.lanes_shift;
   P.rows = g.rows;

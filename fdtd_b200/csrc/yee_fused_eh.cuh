@@ -332,24 +332,31 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
       FDTD_CP_ASYNC_COMMIT();
     }
 #if FDTD_FUSED_PIPE_PSI_PREFETCH > 0
-    if (inside && active && (sl_hit | xs_bits) != 0) {
-      // psi_E of plane i + PP and psi_H of plane i + PP - 1 (the H update lags one plane) of the slabs this thread's
-      // cells lie in
+    {
+      // psi_E of plane i + PP and psi_H of plane i + PP - 1 (the H update lags one plane), only in threads whose cells
+      // lie in a slab there: the interior pays the two x-slab range tests and nothing else
       const int ip = i + FDTD_FUSED_PIPE_PSI_PREFETCH;
-      for (int s = 0; s < P.n_sl; ++s) {
-        const typename FusedParams<T>::Slab& S = P.sl[s];
-        const bool yz = ((sl_hit >> s) & 1u) != 0;
-        if (!yz && S.axis != 0) continue;
-        if (ip < xb && ip < P.x1 && (yz || (ip >= S.xs && ip < S.xe))) {
-          const i64 idx = fused_psi_index<T, VEC>(S, ip, j, k0, plane, p, P.Ny, Nz);
-          fused_prefetch(S.psiE_in + idx);
-          fused_prefetch(S.psiE_in + S.count + idx);
-        }
-        const int ih = ip - 1;      // (psi_H belongs to the owner of the cell only: the halo threads never touch it)
-        if (core && ih >= xa && ih < xb && (yz || (ih >= S.xs && ih < S.xe))) {
-          const i64 idx = fused_psi_index<T, VEC>(S, ih, j, k0, plane, p, P.Ny, Nz);
-          fused_prefetch(S.psiH + idx);
-          fused_prefetch(S.psiH + S.count + idx);
+      unsigned hpf = sl_hit;
+      for (unsigned m = xs_bits; m != 0; m &= m - 1) {
+        const int s = FDTD_FFS(m) - 1;
+        hpf |= (ip >= P.sl[s].xs && ip <= P.sl[s].xe) ? (1u << s) : 0u;
+      }
+      if (inside && active && hpf != 0) {
+        for (int s = 0; s < P.n_sl; ++s) {
+          if (!((hpf >> s) & 1u)) continue;
+          const typename FusedParams<T>::Slab& S = P.sl[s];
+          const bool yz = S.axis != 0;
+          if (ip < xb && ip < P.x1 && (yz || (ip >= S.xs && ip < S.xe))) {
+            const i64 idx = fused_psi_index<T, VEC>(S, ip, j, k0, plane, p, P.Ny, Nz);
+            fused_prefetch(S.psiE_in + idx);
+            fused_prefetch(S.psiE_in + S.count + idx);
+          }
+          const int ih = ip - 1;      // (psi_H belongs to the owner of the cell only: the halo threads never touch it)
+          if (core && ih >= xa && ih < xb && (yz || (ih >= S.xs && ih < S.xe))) {
+            const i64 idx = fused_psi_index<T, VEC>(S, ih, j, k0, plane, p, P.Ny, Nz);
+            fused_prefetch(S.psiH + idx);
+            fused_prefetch(S.psiH + S.count + idx);
+          }
         }
       }
     }

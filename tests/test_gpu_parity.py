@@ -436,3 +436,35 @@ def test_fused_steps_are_the_default_on_large_homogeneous_grids():
     assert float(outs[0][0].abs().max()) > 0
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_energy_slice_and_visualize_on_the_device(monkeypatch):
+    """SURVEY 8f rank 3 on the real device: `energy_slice` squares and sums ONE plane of the SoA storage on the GPU
+    (the reference materialises E^2 + H^2 of the whole grid, fdtd/visualization.py:96-104) and `Grid.visualize`
+    draws it (matplotlib is a recording stand-in: this image has none)."""
+    import sys
+    import types
+    from test_visualization import _Recorder
+    from fdtd_b200.visualization import energy_slice
+    fd = cuda("float32")
+    g = scenes.objects3d(fd)
+    g.run(25, progress_bar=False)
+    E, H = g.E.double().cpu().numpy(), g.H.double().cpu().numpy()
+    energy = (E.astype(np.float32) ** 2 + H.astype(np.float32) ** 2)
+    for kw, want in (({"x": 7}, energy[7].sum(-1)), ({"y": 9}, energy[:, 9].sum(-1).T), ({"z": -3}, energy[:, :, -3].sum(-1))):
+        got = energy_slice(g, **kw)
+        assert got.shape == want.shape and got.dtype == np.float32
+        assert scenes.rel_l2(got, want) <= 1e-6, kw                  # (the sum over three components may associate differently)
+    assert energy_slice(g, z=4).max() > 0
+    log = []
+    plt, ptc, colors = (_Recorder(n, log) for n in ("matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors"))
+    root = types.ModuleType("matplotlib")
+    root.pyplot, root.patches, root.colors = plt, ptc, colors
+    for name, mod in (("matplotlib", root), ("matplotlib.pyplot", plt), ("matplotlib.patches", ptc),
+                      ("matplotlib.colors", colors)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    fig = g.visualize(z=6)
+    calls = [c[0] for c in log]
+    assert fig is not None and "imshow" in calls
+    shown = next(c for c in log if c[0] == "imshow")[1][0]
+    assert shown.shape == (g.Nx, g.Ny) and float(shown.max()) > 0

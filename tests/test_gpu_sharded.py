@@ -55,3 +55,18 @@ def test_temporally_fused_steps_on_slabs(tmp_path, scene, dtype, steps):
     assert float(np.abs(want["E"]).max()) > 0
     for k in want:
         assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
+
+
+def test_energy_slices_gather_one_plane(tmp_path):
+    """`energy_slice` on an x-sharded grid on real GPUs: the x-plane comes from its owner, y / z planes are gathered
+    slab by slab -- equal to the energy of the gathered fields."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = min(4, torch.cuda.device_count())
+    out = str(tmp_path / "sharded.npz")
+    launch(world, "nccl", "float64", "objects3d", 20, out, FDTD_TEST_SLICES="7,9,4")
+    got = dict(np.load(out))
+    energy = (got["E"] ** 2 + got["H"] ** 2).sum(-1)
+    assert np.array_equal(got["slice_x"], energy[7])
+    assert np.array_equal(got["slice_y"], energy[:, 9, :].T)
+    assert np.array_equal(got["slice_z"], energy[:, :, 4])
