@@ -26,13 +26,14 @@
 #define FDTD_LAUNCH_SYNC(kern, grid, block, stream, ...) \
   emu::launch_coop(grid, block, [&]() { kern(__VA_ARGS__); })
 #define FDTD_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) \
-  emu::launch_coop(grid, block, [&]() { kern(__VA_ARGS__); })
+  (emu::t_tma.clear(), emu::launch_coop(grid, block, [&]() { kern(__VA_ARGS__); }))
 template <typename T>
 inline void fdtd_atomic_add(T* p, T v) { *p = *p + v; }
 #include <cmath>
 template <typename T>
 inline bool fdtd_signbit(T v) { return std::signbit(v); }
 #else
+#include <cuda.h>            // CUtensorMap and its enums only: the encoder is resolved at run time (no libcuda link)
 #include <cuda_runtime.h>
 #define FDTD_DEV __device__ __forceinline__
 #define FDTD_LAUNCH(kern, grid, block, stream, ...) \
@@ -870,12 +871,15 @@ int fdtd_ipc_import(const void* handle64, int64_t offset, void** dev_ptr) {
 // ---- temporally fused E+H steps (yee_fused_eh.cuh) --------------------------------------------------------
 extern "C++" {
 namespace {
-#ifndef FDTD_FUSE_EH_MIN_CELLS
+// automatic mode (fuse_eh = 2): the fused kernel wins where its 7 x 31-vector tiles quantise the y-z plane well and
+// the march is long enough -- measured on the B200 (profiles/r2_fused_sizes_tma.txt): float32 640^3 -3 %, 768^3 +6 %,
+// 1024^3 +17 %; float64 512^3 +11 %; slabs of 1024^2 planes: 64 planes -5 %, 128 +3 %, 192 +9 %
 #ifdef FDTD_EMU
-#define FDTD_FUSE_EH_MIN_CELLS 0
+#define FDTD_FUSE_EH_MIN_PLANE_BYTES 0
+#define FDTD_FUSE_EH_MIN_PLANES 2
 #else
-#define FDTD_FUSE_EH_MIN_CELLS 600000000LL   // below, the 7 x 124-cell tiles quantise badly and the two half-steps win
-#endif
+#define FDTD_FUSE_EH_MIN_PLANE_BYTES (2LL << 20)
+#define FDTD_FUSE_EH_MIN_PLANES 96
 #endif
 
 // fuse_eh = 1: wherever it is legal; fuse_eh = 2: only where it is also faster (large grids: what counts is the
@@ -887,7 +891,9 @@ bool fuse_eh_eligible(const fdtd_desc* d, bool sharded = false) {
   if ((d->Nx != d->Nx_global) != sharded || d->n_post != 0 || d->n_deep != 0 || d->x_wrap) return false;
   const int vec = d->dtype == FDTD_F32 ? 4 : 2;
   if (d->Nz % vec) return false;
-  if (d->fuse_eh == 2 && (int64_t)d->Nx_global * d->Ny * d->Nz < FDTD_FUSE_EH_MIN_CELLS) return false;
+  if (d->fuse_eh == 2 && ((int64_t)d->Ny * d->Nz * (d->dtype == FDTD_F32 ? 4 : 8) < FDTD_FUSE_EH_MIN_PLANE_BYTES ||
+                          d->Nx < FDTD_FUSE_EH_MIN_PLANES))
+    return false;
   if (sharded && d->Nx < 4) return false;
   int nsrc = 0;
   for (int n = 0; n < d->n_sources; ++n) {
@@ -906,6 +912,70 @@ bool fuse_eh_eligible(const fdtd_desc* d, bool sharded = false) {
   return d->Nx >= 8 && d->Ny >= 8 && d->Nz >= 32 * vec;
 #else
   return d->Nx >= 2;     // (CPU tests: small grids with partial tiles exercise every branch)
+#endif
+}
+
+#ifndef FDTD_FUSED_TMA
+#define FDTD_FUSED_TMA 1     // the fused kernel's inputs are staged by TMA (0: per-thread cp.async copies)
+#endif
+
+// tensor maps of the three components of one field buffer for the fused kernel's staging: a 3-D tensor
+// [Nx + 2][Ny][Nz] per component (the ghost x-planes belong to it), box = (bz x by x 1 plane)
+template <typename T>
+int fused_tma_maps(const fdtd_desc* d, void* const* F, int bz, int by, fdtd::TmaMap<T>* out) {
+#ifdef FDTD_EMU
+  for (int c = 0; c < 3; ++c) {
+    out[c].base = (const T*)F[c] - d->plane;
+    out[c].n0 = d->Nz;
+    out[c].n1 = d->Ny;
+    out[c].n2 = d->Nx + 2;
+  }
+  return FDTD_OK;
+#else
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return fail(FDTD_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = (encode_fn)fn;
+  }
+  // a handful of buffers (two per field): keep the encoded maps
+  struct Entry {
+    void* base;
+    int Nx, Ny, Nz, bz, by;
+    CUtensorMap m;
+  };
+  static thread_local Entry cache[16];
+  static thread_local int next = 0;
+  for (int c = 0; c < 3; ++c) {
+    void* base = (void*)((T*)F[c] - d->plane);
+    const Entry* hit = nullptr;
+    for (const Entry& e : cache)
+      if (e.base == base && e.Nx == d->Nx && e.Ny == d->Ny && e.Nz == d->Nz && e.bz == bz && e.by == by) hit = &e;
+    if (!hit) {
+      Entry& e = cache[next];
+      next = (next + 1) % 16;
+      const cuuint64_t dims[3] = {(cuuint64_t)d->Nz, (cuuint64_t)d->Ny, (cuuint64_t)d->Nx + 2};
+      const cuuint64_t strides[2] = {(cuuint64_t)d->Nz * sizeof(T), (cuuint64_t)d->plane * sizeof(T)};
+      const cuuint32_t box[3] = {(cuuint32_t)bz, (cuuint32_t)by, 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&e.m, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base,
+                          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        e.base = nullptr;
+        return fail(FDTD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+      }
+      e.base = base; e.Nx = d->Nx; e.Ny = d->Ny; e.Nz = d->Nz; e.bz = bz; e.by = by;
+      hit = &e;
+    }
+    out[c].m = hit->m;
+  }
+  return FDTD_OK;
 #endif
 }
 
@@ -1008,19 +1078,27 @@ int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void*
   dim3 grid((Nz + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC), (Ny + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);
   dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
   if (grid.y > 65535u || grid.z > 65535u) return fail(FDTD_ERR_UNSUPPORTED, "grid too large for one launch");
+  constexpr bool TMA = FDTD_FUSED_TMA != 0;
+  fdtd::FusedTmaMaps<T> M;
+  memset(&M, 0, sizeof(M));
+  if (TMA) {
+    // (a TMA row is a multiple of 16 bytes: Nz % VEC == 0, checked by the eligibility test)
+    if ((rc = fused_tma_maps<T>(d, Hin, Lay::HV * VEC, Lay::R + 2, M.h)) != 0) return rc;
+    if ((rc = fused_tma_maps<T>(d, Ein, Lay::EV * VEC, Lay::R + 1, M.e)) != 0) return rc;
+  }
 #ifndef FDTD_EMU
   static bool configured = false;      // (per instantiation: one kernel function each)
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>,
+    cudaError_t e = cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC, TMA>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::BYTES);
     if (e != cudaSuccess) return fail(FDTD_ERR_CUDA, "cudaFuncSetAttribute(smem %zu): %s", Lay::BYTES, cudaGetErrorString(e));
     // two blocks per SM only fit with the shared-memory carve-out at its maximum
-    cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          (int)cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
 #endif
-  FDTD_LAUNCH_SMEM((fdtd::fused_eh_pipe_kernel<T, VEC>), grid, block, Lay::BYTES, stream, P);
+  FDTD_LAUNCH_SMEM((fdtd::fused_eh_pipe_kernel<T, VEC, TMA>), grid, block, Lay::BYTES, stream, P, M);
   rc = check_launch("fused_eh");
   if (rc) return rc;
   // detectors on the new fields (a sharded step samples after its last H plane)

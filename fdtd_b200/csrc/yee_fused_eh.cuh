@@ -120,7 +120,7 @@ constexpr int FUSED_L = FDTD_FUSED_LANES;  // core vector lanes per block
 #define FDTD_CP_ASYNC16(dst, src) emu::cp_async16((dst), (src))
 #define FDTD_CP_ASYNC_COMMIT() emu::cp_async_commit()
 #define FDTD_CP_ASYNC_WAIT_1() emu::cp_async_wait(1)
-#define FDTD_DYN_SMEM(name) alignas(16) static unsigned char name[128 << 10]
+#define FDTD_DYN_SMEM(name) alignas(128) static unsigned char name[256 << 10]
 #else
 #define FDTD_FFS(x) __ffs((int)(x))
 #define FDTD_CP_ASYNC16(dst, src)                                                                      \
@@ -129,11 +129,56 @@ constexpr int FUSED_L = FDTD_FUSED_LANES;  // core vector lanes per block
                : "memory")
 #define FDTD_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
 #define FDTD_CP_ASYNC_WAIT_1() asm volatile("cp.async.wait_group 1;" ::: "memory")
-#define FDTD_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define FDTD_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #endif
 #ifndef FDTD_FUSED_PIPE_MIN_BLOCKS
 #define FDTD_FUSED_PIPE_MIN_BLOCKS 2
 #endif
+
+// ---- staging by TMA: one elected thread issues six bulk tensor copies per plane (the H_old and E_old tiles of the
+// three components, 3-D boxes with hardware zero fill outside the grid), completion is counted on one mbarrier per
+// stage that every thread of the block waits on.  No per-thread copy instructions, address arithmetic or predicates.
+#ifdef FDTD_EMU
+template <typename T>
+struct TmaMap {           // (CPU interpreter) the tensor a map describes: [n2][n1][n0] elements at base
+  const T* base;
+  int n0, n1, n2;
+};
+#define FDTD_MBAR_INIT(bar) emu::mbar_init(bar)
+#define FDTD_MBAR_EXPECT(bar, bytes) ((void)(bytes))
+#define FDTD_MBAR_WAIT(bar, parity) emu::mbar_wait(bar)
+#define FDTD_TMA_LOAD_3D(dst, map, c0, c1, c2, b0, b1, bar) \
+  emu::tma_load_3d((dst), (map)->base, sizeof(*(map)->base), (map)->n0, (map)->n1, (map)->n2, (c0), (c1), (c2), (b0), (b1), (bar))
+#else
+template <typename T>
+struct TmaMap {
+  CUtensorMap m;
+};
+FDTD_DEV unsigned fused_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+#define FDTD_MBAR_INIT(bar) \
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fdtd::fused_smem_addr(bar)) : "memory")
+#define FDTD_MBAR_EXPECT(bar, bytes)                                                                      \
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fdtd::fused_smem_addr(bar)), \
+               "r"((unsigned)(bytes))                                                                      \
+               : "memory")
+#define FDTD_MBAR_WAIT(bar, parity)                                                                        \
+  asm volatile(                                                                                            \
+      "{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\n" \
+      "bra LAB_WAIT;\nDONE:\n}" ::"r"(fdtd::fused_smem_addr(bar)),                                          \
+      "r"((unsigned)(parity))                                                                              \
+      : "memory")
+#define FDTD_TMA_LOAD_3D(dst, map, c0, c1, c2, b0, b1, bar)                                                       \
+  asm volatile(                                                                                                   \
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"( \
+          fdtd::fused_smem_addr(dst)),                                                                            \
+      "l"((unsigned long long)(map)), "r"((int)(c0)), "r"((int)(c1)), "r"((int)(c2)), "r"(fdtd::fused_smem_addr(bar)) \
+      : "memory")
+#endif
+
+template <typename T>
+struct FusedTmaMaps {
+  TmaMap<T> h[3], e[3];   // the three components of the input H and E (ghost x-planes included: plane i is x = i + 1)
+};
 #ifndef FDTD_FUSED_PIPE_PSI_PREFETCH
 #define FDTD_FUSED_PIPE_PSI_PREFETCH 0   // CPML psi of the thread's cells is prefetched (L1) this many planes ahead: the psi
                                          // loads are the only global loads left on the per-plane critical path, and one
@@ -154,12 +199,17 @@ template <typename T, int VEC>
 struct FusedPipeLayout {
   static constexpr int R = FUSED_R, L = FUSED_L;
   static constexpr int HV = L + 2, EV = L + 1;                 // vectors per staged row
-  static constexpr int H_WORDS = 3 * (R + 2) * HV * VEC;       // H_old tile: rows j0-1 .. j0+R, vectors -1 .. L
-  static constexpr int E_WORDS = 3 * (R + 1) * EV * VEC;       // E_old tile: rows j0 .. j0+R, vectors 0 .. L
+  static constexpr int PADW = 128 / (int)sizeof(T);            // a TMA destination is 128-byte aligned
+  static constexpr int HC = ((R + 2) * HV * VEC + PADW - 1) / PADW * PADW;   // words per staged H component
+  static constexpr int EC = ((R + 1) * EV * VEC + PADW - 1) / PADW * PADW;   // words per staged E component
+  static constexpr int H_WORDS = 3 * HC;                       // H_old tile: rows j0-1 .. j0+R, vectors -1 .. L
+  static constexpr int E_WORDS = 3 * EC;                       // E_old tile: rows j0 .. j0+R, vectors 0 .. L
   static constexpr int STAGE_WORDS = H_WORDS + E_WORDS;
   static constexpr int X_WORDS = 3 * (R + 1) * EV * VEC;       // one published E_new tile
+  static constexpr unsigned TMA_BYTES = 3u * ((R + 2) * HV + (R + 1) * EV) * VEC * (unsigned)sizeof(T);  // per plane
   static constexpr int STAGES = 3;
-  static constexpr size_t BYTES = sizeof(T) * (size_t)(STAGES * STAGE_WORDS + 2 * X_WORDS);
+  static constexpr size_t BAR_OFFSET = sizeof(T) * (size_t)(STAGES * STAGE_WORDS + 2 * X_WORDS);   // the mbarriers
+  static constexpr size_t BYTES = BAR_OFFSET + 8 * STAGES;
 };
 
 // CPML update of one slab (axis AX) for the VEC cells of a thread, psi read from `psi_in` and (if `store`) written
@@ -225,8 +275,7 @@ template <typename T, int VEC>
 FDTD_DEV void fused_stage_issue(const FusedParams<T>& P, T* stage, i64 off, int r, int l, bool inside, bool row_m1,
                                 bool vec_m1) {
   using Lay = FusedPipeLayout<T, VEC>;
-  constexpr int R = Lay::R, HV = Lay::HV, EV = Lay::EV;
-  constexpr int HC = (R + 2) * HV * VEC, EC = (R + 1) * EV * VEC;
+  constexpr int HV = Lay::HV, EV = Lay::EV, HC = Lay::HC, EC = Lay::EC;
   if (!inside) return;
   T* h = stage + ((r + 1) * HV + (l + 1)) * VEC;
   T* e = stage + Lay::H_WORDS + (r * EV + l) * VEC;
@@ -266,15 +315,28 @@ FDTD_DEV void fused_prefetch(const void* a) {
 #endif
 }
 
+// one plane of the block's tile into a stage, by TMA (thread 0 only)
 template <typename T, int VEC>
+FDTD_DEV void fused_stage_tma(const FusedTmaMaps<T>& M, T* stage, unsigned long long* bar, int kz0, int j0, int ip) {
+  using Lay = FusedPipeLayout<T, VEC>;
+  FDTD_MBAR_EXPECT(bar, Lay::TMA_BYTES);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    FDTD_TMA_LOAD_3D(stage + c * Lay::HC, &M.h[c], kz0 - VEC, j0 - 1, ip + 1, Lay::HV * VEC, Lay::R + 2, bar);
+    FDTD_TMA_LOAD_3D(stage + Lay::H_WORDS + c * Lay::EC, &M.e[c], kz0, j0, ip + 1, Lay::EV * VEC, Lay::R + 1, bar);
+  }
+}
+
+template <typename T, int VEC, bool TMA>
 __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE_MIN_BLOCKS)
-    fused_eh_pipe_kernel(const __grid_constant__ FusedParams<T> P) {
+    fused_eh_pipe_kernel(const __grid_constant__ FusedParams<T> P, const __grid_constant__ FusedTmaMaps<T> M) {
   using Lay = FusedPipeLayout<T, VEC>;
   constexpr int R = Lay::R, L = Lay::L, HV = Lay::HV, EV = Lay::EV;
   static_assert(sizeof(T) * VEC == 16, "the staged copies are 16 bytes wide");
   FDTD_DYN_SMEM(smem_raw);
   T* const stages = reinterpret_cast<T*>(smem_raw);
   T* const xch = stages + Lay::STAGES * Lay::STAGE_WORDS;
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + Lay::BAR_OFFSET);
 
   const int tid = threadIdx.x;
   const int r = tid / (L + 1), l = tid % (L + 1);
@@ -305,12 +367,26 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   unsigned hit_prev = 0;   // slabs (x slabs included) the cells of plane i-1 lie in: what the H update of i-1 needs
 
   const bool row_m1 = (r == 0) && (j >= 1), vec_m1 = (l == 0) && (k0 >= VEC);   // who copies the y-1 row / z-1 vector
+  if (TMA) {
+    if (tid == 0) {
+      for (int s = 0; s < Lay::STAGES; ++s) FDTD_MBAR_INIT(bars + s);
+    }
+#ifndef FDTD_EMU
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    __syncthreads();
+  }
   // two planes in flight before the first one is consumed (one commit group per plane, empty ones included)
   for (int s = 0; s < 2; ++s) {
     const int ip = xa + s;
-    if (ip <= xb && ip < P.x1)
+    if (TMA) {
+      if (tid == 0 && ip <= xb && ip < P.x1)
+        fused_stage_tma<T, VEC>(M, stages + (ip % 3) * Lay::STAGE_WORDS, bars + (ip % 3), kz0, j0, ip);
+    } else {
+      if (ip <= xb && ip < P.x1)
         fused_stage_issue<T, VEC>(P, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane + p, r, l, inside, row_m1, vec_m1);
-    FDTD_CP_ASYNC_COMMIT();
+      FDTD_CP_ASYNC_COMMIT();
+    }
   }
 
   Pack<T, VEC> hp0, hp1, hp2, ep0, ep1, ep2;
@@ -323,13 +399,23 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
 
   const int xl = (P.skip_last_h && xb == P.x1) ? xb - 1 : xb;   // (see FusedParams::skip_last_h)
   for (int i = xa; i <= xl; ++i) {
-    FDTD_CP_ASYNC_WAIT_1();
+    if (TMA) {
+      // the k-th use of a stage's barrier completes phase k: plane i is use (i - xa) / 3 of stage i % 3
+      if (i < P.x1) FDTD_MBAR_WAIT(bars + (i % 3), ((i - xa) / 3) & 1);
+    } else {
+      FDTD_CP_ASYNC_WAIT_1();
+    }
     __syncthreads();
     {
       const int ip = i + 2;
-      if (ip <= xb && ip < P.x1)
-        fused_stage_issue<T, VEC>(P, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane + p, r, l, inside, row_m1, vec_m1);
-      FDTD_CP_ASYNC_COMMIT();
+      if (TMA) {
+        if (tid == 0 && ip <= xb && ip < P.x1)
+          fused_stage_tma<T, VEC>(M, stages + (ip % 3) * Lay::STAGE_WORDS, bars + (ip % 3), kz0, j0, ip);
+      } else {
+        if (ip <= xb && ip < P.x1)
+          fused_stage_issue<T, VEC>(P, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane + p, r, l, inside, row_m1, vec_m1);
+        FDTD_CP_ASYNC_COMMIT();
+      }
     }
 #if FDTD_FUSED_PIPE_PSI_PREFETCH > 0
     {
@@ -388,7 +474,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
       if (inside && i < P.x1) {
         // ---- E_new[i] = E_old + (sc eps^-1) * curl_H(H_old)      (fdtd/grid.py:54-76, 283)
         const T* hrow = sH + ((r + 1) * HV + (l + 1)) * VEC;            // own vector of component 0
-        constexpr int HC = (R + 2) * HV * VEC;                          // words per staged H component
+        constexpr int HC = Lay::HC;                                     // words per staged H component
         h0 = ldv<T, VEC>(hrow);
         h1 = ldv<T, VEC>(hrow + HC);
         h2 = ldv<T, VEC>(hrow + 2 * HC);
@@ -397,7 +483,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
         const T zs0 = hrow[-1];
         const T zs1 = hrow[HC - 1];
         const T* erow = sE + (r * EV + l) * VEC;
-        constexpr int EC = (R + 1) * EV * VEC;
+        constexpr int EC = Lay::EC;
         e0 = ldv<T, VEC>(erow);
         e1 = ldv<T, VEC>(erow + EC);
         e2 = ldv<T, VEC>(erow + 2 * EC);

@@ -23,9 +23,12 @@ RING_BYTES = 64 << 20          # detector ring budget per grid
 WAVE_TABLE_MIN = 1024          # look-ahead of the host waveform tables (steps)
 WAVE_TABLE_MAX = 1 << 16
 GRAPH_MAX_CELLS = 1 << 23      # grids up to this many cells replay CUDA graphs of 32-step chunks in run()
-FUSE_EH_MIN_SLAB = 192           # x-planes per rank from which fused steps also win on x-sharded grids
-FUSE_EH_MIN_CELLS = 600_000_000  # from here on the single-pass E+H kernel beats the two half-steps (automatic mode;
-                                 # 768^3: -2 %, 896^3: +4 %, 1024^3: +8 %, profiles/r2_fused_sizes.txt)
+# automatic mode of the single-pass E+H kernel (grid._fuse_eh = 2): where it beats the two half-steps on the B200
+# (profiles/r2_fused_sizes_tma.txt: float32 640^3 -3 %, 768^3 +6 %, 1024^3 +17 %; float64 512^3 +11 %; slabs of 1024^2
+# planes: 64 planes -5 %, 128 +3 %, 192 +9 %)
+FUSE_EH_MIN_PLANE_BYTES = 2 << 20     # y-z plane of one component
+FUSE_EH_MIN_PLANES = 96               # x-planes (unsharded)
+FUSE_EH_MIN_SLAB = 112                # x-planes per rank (x-sharded: a fused step ends in a short serial tail)
 
 
 def _ptr(t):
@@ -295,7 +298,8 @@ class Engine:
         # a second psi_E per slab: homogeneous, unsharded grids only.  grid._fuse_eh / FDTD_B200_FUSE_EH: 0 never,
         # 1 wherever legal, 2 (default) where it is also faster -- large grids -- and the buffers fit in free memory
         want = g._fuse_eh
-        big = g.Nx * g.Ny * g.Nz >= FUSE_EH_MIN_CELLS
+        big = (g.Ny * g.Nz * g._E.element_size() >= FUSE_EH_MIN_PLANE_BYTES
+               and (g.Nx // part.world >= FUSE_EH_MIN_SLAB if part.sharded else g.Nx >= FUSE_EH_MIN_PLANES))
         ok = bool(want and not self._hooked and ie_eff is None and imu is None and not post and not x_wrap
                   and g._sdtype is g._dtype and (want == 1 or big)
                   and all(d.sources[k].kind == _capi.SRC_POINTS and d.sources[k].field == 0 for k in range(d.n_sources))
@@ -303,11 +307,9 @@ class Engine:
         if part.sharded:
             # x-slabs: peer-to-peer halo only (the boundary planes go into the neighbours' second buffers), and every
             # rank must decide alike -- free memory included.  Thin slabs keep the two half-steps: a fused step ends in
-            # a serial tail (flag, last H plane, flag) that the bulk of a two-pass step hides, and few x-chunks fill
-            # the GPU badly (1024^3 on 8 B200, 128 planes each: 1.62 ms fused against 1.58; on 4: 3.04 against 3.16)
+            # a serial tail (flag, last H plane, flag) that the bulk of a two-pass step hides (FUSE_EH_MIN_SLAB)
             import os
-            ok = (ok and g._E.is_cuda and os.environ.get("FDTD_B200_HALO", "p2p") == "p2p" and self._p2p is not False
-                  and (want == 1 or g.Nx // part.world >= FUSE_EH_MIN_SLAB))
+            ok = ok and g._E.is_cuda and os.environ.get("FDTD_B200_HALO", "p2p") == "p2p" and self._p2p is not False
         if ok and g._E2 is None:
             ok = want == 1 or self._room_for(2 * g._E.numel() * g._E.element_size())
         if part.sharded and g._E.is_cuda:

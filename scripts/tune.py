@@ -42,6 +42,9 @@ VARIANTS = {
     "pipe_r7l31_mb2_pf3": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=3"],
     "pipe_r7l31_mb2_pf4": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=4"],
     "pipe_r7l31_mb2_pf6": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=6"],
+    "pipe_cpasync": ["-DFDTD_FUSED_TMA=0"],
+    "pipe_tma_r15l31_mb1": ["-DFDTD_FUSED_ROWS=15", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=1"],
+    "pipe_tma_r3l31_mb4": ["-DFDTD_FUSED_ROWS=3", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4"],
     "pipe_psi1": ["-DFDTD_FUSED_PIPE_PSI_PREFETCH=1"],
     "pipe_psi2": ["-DFDTD_FUSED_PIPE_PSI_PREFETCH=2"],
     "pipe_psi2_L2": ["-DFDTD_FUSED_PIPE_PSI_PREFETCH=2", "-DFDTD_FUSED_PIPE_PSI_LEVEL=2"],

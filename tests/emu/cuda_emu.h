@@ -96,6 +96,41 @@ inline void cp_async_wait(size_t pending) {   // cp.async.wait_group N: at most 
   }
 }
 
+// ---- TMA + mbarrier emulation (the fused E+H kernel's staging): a bulk tensor copy is DEFERRED to the first wait on
+// its barrier -- the latest moment the hardware may complete it -- and fills what lies outside the tensor with zeros
+struct TmaCopy {
+  void* dst;
+  const char* base;
+  size_t esize;
+  long n0, n1, n2;
+  long c0, c1, c2;
+  int b0, b1;
+  const void* bar;
+};
+inline thread_local std::vector<TmaCopy> t_tma;
+inline void mbar_init(const void* bar) {
+  for (size_t k = 0; k < t_tma.size();)
+    if (t_tma[k].bar == bar) t_tma.erase(t_tma.begin() + k); else ++k;
+}
+inline void tma_load_3d(void* dst, const void* base, size_t esize, long n0, long n1, long n2, long c0, long c1, long c2,
+                        int b0, int b1, const void* bar) {
+  t_tma.push_back({dst, (const char*)base, esize, n0, n1, n2, c0, c1, c2, b0, b1, bar});
+}
+inline void mbar_wait(const void* bar) {
+  for (size_t k = 0; k < t_tma.size();) {
+    const TmaCopy& c = t_tma[k];
+    if (c.bar != bar) { ++k; continue; }
+    char* out = (char*)c.dst;
+    for (int y = 0; y < c.b1; ++y)
+      for (int z = 0; z < c.b0; ++z, out += c.esize) {
+        const long gz = c.c0 + z, gy = c.c1 + y, gx = c.c2;
+        if (gz < 0 || gz >= c.n0 || gy < 0 || gy >= c.n1 || gx < 0 || gx >= c.n2) memset(out, 0, c.esize);
+        else memcpy(out, c.base + ((gx * c.n1 + gy) * c.n0 + gz) * c.esize, c.esize);
+      }
+    t_tma.erase(t_tma.begin() + k);
+  }
+}
+
 template <typename F>
 inline void launch_coop(dim3 grid, dim3 block, F&& body) {
   t_gridDim = grid;

@@ -419,10 +419,11 @@ def test_running_dft_equals_fft_of_the_record(dtype, monkeypatch):
 
 
 def test_fused_steps_are_the_default_on_large_homogeneous_grids():
-    """automatic mode (grid._fuse_eh = 2, the default): grids of 6e8 cells and more run pairs of single-pass steps
-    when the second buffers fit; the result equals the two-half-step path bit for bit at that size (float32)."""
+    """automatic mode (grid._fuse_eh = 2, the default): grids with y-z planes of 2 MiB per component and more run pairs
+    of single-pass steps when the second buffers fit; the result equals the two-half-step path bit for bit at that
+    size (float32)."""
     fd = cuda("float32")
-    n = 848                              # 6.1e8 cells: 29 GiB of fields + second buffers
+    n = 768                              # 4.5e8 cells: 21 GiB of fields + second buffers
     if torch.cuda.mem_get_info()[0] < 60 << 30:
         pytest.skip("not enough free device memory")
     outs = []
