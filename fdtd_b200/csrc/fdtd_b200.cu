@@ -87,7 +87,7 @@ int pow2_ceil(int v) {
 }
 
 #ifndef FDTD_FUSE_MAX_CELLS
-#define FDTD_FUSE_MAX_CELLS (1LL << 23)
+#define FDTD_FUSE_MAX_CELLS (1LL << 25)
 #endif
 #ifndef FDTD_MAX_LANES_Z
 #define FDTD_MAX_LANES_Z 32   // threads of a block along z (x VEC cells each); the rest of the 256 go to y rows
@@ -515,11 +515,15 @@ int launch_halfstep_run(const fdtd_desc* d, int x_begin, int x_end, int64_t q, i
     P.push_y = (T*)push_y;
     P.push_z = (T*)push_z;
   }
-  // folded sources/detectors only occur on small slabs: they share the general (MAT) instantiation
-  const bool mat = P.cls != nullptr || has_post;
+  // folded sources / detectors: their own material-free instantiation on homogeneous unsharded grids (mid-size
+  // grids, where the fold and the graph replay it enables save the launches between the half-steps); otherwise
+  // they share the general (MAT) one
+  const bool mat = P.cls != nullptr || (has_post && has_push);
 #define FDTD_LAUNCH_HALFSTEP(V)                                                                         \
   if (has_post && has_push) {                                                                           \
     FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, true, true, A>), grid, block, stream, P);     \
+  } else if (has_post && !mat) {                                                                        \
+    FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, false, false, A>), grid, block, stream, P);   \
   } else if (has_post) {                                                                                \
     FDTD_LAUNCH((fdtd::halfstep_kernel<T, V, IS_E, true, false, true, A>), grid, block, stream, P);    \
   } else if (has_push && mat) {                                                                         \

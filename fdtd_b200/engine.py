@@ -22,7 +22,7 @@ from .sharding import HaloExchange, P2PHalo, WrapExchange
 RING_BYTES = 64 << 20          # detector ring budget per grid
 WAVE_TABLE_MIN = 1024          # look-ahead of the host waveform tables (steps)
 WAVE_TABLE_MAX = 1 << 16
-GRAPH_MAX_CELLS = 1 << 23      # grids up to this many cells replay CUDA graphs of 32-step chunks in run()
+GRAPH_MAX_CELLS = 1 << 25      # grids up to this many cells replay CUDA graphs of 32-step chunks in run()
 # automatic mode of the single-pass E+H kernel (grid._fuse_eh = 2): where it beats the two half-steps on the B200
 # (profiles/r2_fused_sizes_tma.txt: float32 640^3 -3 %, 768^3 +6 %, 1024^3 +17 %; float64 512^3 +11 %; slabs of 1024^2
 # planes: 64 planes -5 %, 128 +3 %, 192 +9 %)

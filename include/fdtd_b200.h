@@ -213,7 +213,7 @@ typedef struct fdtd_desc {
   void* E2[3];         /* second field buffers of the ping-pong pair, same layout as E / H (ghost planes included), */
   void* H2[3];         /* or NULL; after fdtd_run the results are always in E / H */
   int32_t fuse_post;   /* sources/detectors folded into the half-step kernel: 1 always (when legal), 0 never,
-                          -1 automatic (local slabs up to 2^23 cells, where a step is launch-bound) */
+                          -1 automatic (local slabs up to 2^25 cells, where the launches between the half-steps still show) */
   int32_t pad3_;
   void* psi_E2[FDTD_MAX_SLABS];  /* fuse_eh: a second psi_E buffer [2][psi_count] for every slab.  The fused kernel updates the
                           whole grid, CPML cells and faces included, in its single pass; cells whose E_new is recomputed
