@@ -18,15 +18,31 @@ def main():
     backend, dtype, scene, steps, out = sys.argv[1:6]
     steps = int(steps)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    import scenes
     if backend == "gloo":
         dist.init_process_group("gloo", rank=rank, world_size=world)
-        from emu.harness import use_emu
-        fd = use_emu(dtype)
     else:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         dist.init_process_group("nccl", rank=rank, world_size=world,
                                 device_id=torch.device("cuda", torch.cuda.current_device()))
+    if "@" in scene:
+        # several "scene@dtype" items in one job (saves the start-up of the ranks): out -> out.<n>.npz
+        for n, item in enumerate(scene.split(",")):
+            name, dt = item.split("@")
+            run_one(backend, dt, name, steps, f"{out}.{n}.npz", rank, world)
+    else:
+        run_one(backend, dtype, scene, steps, out, rank, world)
+    if backend != "gloo":
+        torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_one(backend, dtype, scene, steps, out, rank, world):
+    import scenes
+    if backend == "gloo":
+        from emu.harness import use_emu
+        fd = use_emu(dtype)
+    else:
         import fdtd_b200 as fd
         fd.set_backend("cuda." + dtype)
     if scene.startswith("fuzz:"):
@@ -48,7 +64,6 @@ def main():
         if rank == 0:
             np.savez(out, skipped=np.array(str(exc)))
         dist.barrier()
-        dist.destroy_process_group()
         return
     assert g._part.world == world and g._part.sharded
     if os.environ.get("FDTD_TEST_EXPECT_LATE"):      # a CurrentDetector on a slab's first plane: exchange-then-sample path
@@ -73,8 +88,8 @@ def main():
         if os.environ.get("FDTD_B200_HALO", "p2p") == "p2p":
             assert g._engine._p2p, "peer-to-peer halo was requested but not set up"
         torch.cuda.synchronize()
+    del g
     dist.barrier()
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -37,23 +37,36 @@ def launch(world, backend, dtype, scene, steps, out, **extra_env):
         assert p.returncode == 0, o[-3000:]
 
 
-@pytest.mark.parametrize("world,scene,dtype", [(2, "pml3d", "float64"), (2, "objects3d", "float64"),
-                                               (3, "periodic3d", "float64"), (2, "c4small", "float32"),
-                                               (3, "slab2d_xz", "float64"), (2, "overlaps3d", "float64"),
-                                               (3, "overlaps3d", "float32"), (2, "ring3d", "float64"),
-                                               (3, "ring3d", "float32"), (4, "ring3d", "float64"),
-                                               (2, "feed50", "float64"), (3, "feed50", "float32"),
-                                               (2, "objects3d", "float32x"), (3, "periodic3d", "float32x"),
-                                               (2, "stacked3d", "float64"), (3, "stacked3d", "float32")])
-def test_sharded_equals_single(tmp_path, world, scene, dtype):
-    steps = 24
-    out = str(tmp_path / "sharded.npz")
-    launch(world, "gloo", dtype, scene, steps, out)
-    got = dict(np.load(out))
+CASES = [(2, "pml3d", "float64"), (2, "objects3d", "float64"), (3, "periodic3d", "float64"), (2, "c4small", "float32"),
+         (3, "slab2d_xz", "float64"), (2, "overlaps3d", "float64"), (3, "overlaps3d", "float32"), (2, "ring3d", "float64"),
+         (3, "ring3d", "float32"), (4, "ring3d", "float64"), (2, "feed50", "float64"), (3, "feed50", "float32"),
+         (2, "objects3d", "float32x"), (3, "periodic3d", "float32x"), (2, "stacked3d", "float64"),
+         (3, "stacked3d", "float32")]
+STEPS = 24
+
+
+@pytest.fixture(scope="module")
+def sharded_runs(tmp_path_factory):
+    """every case of one world size in ONE job of that many ranks (the ranks' start-up dominates a single case)"""
+    cache = {}
+
+    def get(world):
+        if world not in cache:
+            items = [(s, d) for w, s, d in CASES if w == world]
+            out = str(tmp_path_factory.mktemp(f"world{world}") / "sharded")
+            launch(world, "gloo", "-", ",".join(f"{s}@{d}" for s, d in items), STEPS, out)
+            cache[world] = {item: dict(np.load(f"{out}.{n}.npz")) for n, item in enumerate(items)}
+        return cache[world]
+    return get
+
+
+@pytest.mark.parametrize("world,scene,dtype", CASES)
+def test_sharded_equals_single(sharded_runs, world, scene, dtype):
+    got = sharded_runs(world)[(scene, dtype)]
     fd = use_emu(dtype)
     g = scenes.SCENES[scene][0](fd)
     assert not g._part.sharded
-    g.run(steps, progress_bar=False)
+    g.run(STEPS, progress_bar=False)
     want = scenes.dump(g)
     assert set(got) == set(want)
     for k in want:
