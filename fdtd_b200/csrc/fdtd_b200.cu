@@ -1047,6 +1047,7 @@ int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void*
     P.skip_last_h = shard->skip_last_h;
   }
   P.x0 = 0; P.x1 = Nx; P.y0 = 0; P.y1 = Ny; P.z0 = 0; P.z1 = Nz;
+  P.psi_stage = 1;
   // planes marched per block: ~48 (1024^3 f32: 10.97 / 10.77 / 10.68 / 10.84 ms per step at 16 / 32 / 48 / 64,
   // profiles/r2_fused_tma.txt), in chunks of equal length
   if (d->x_chunk > 0) {
@@ -1083,6 +1084,8 @@ int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void*
     K.cE = (const T*)S.cE;
     K.bH = (const T*)S.bH;
     K.cH = (const T*)S.cH;
+    // (bulk copies of psi rows: 16-byte aligned sources; rows and array halves are multiples of four words)
+    if (S.axis == 2 && !(aligned(K.psiE_in, 16) && aligned(K.psiH, 16))) P.psi_stage = 0;
   }
   using Lay = fdtd::FusedPipeLayout<T, VEC>;
   const unsigned chunks = (Nx + P.x_chunk - 1) / P.x_chunk;

@@ -46,6 +46,7 @@ struct FusedParams {
   T* push_y;
   T* push_z;
   int skip_last_h;
+  int psi_stage;   // the psi arrays of every z slab are 16-byte aligned: a block may stage them with bulk copies
   int n_sl;
   struct Slab {
     int axis, lo, t, lo_al, tp;   // lo: LOCAL coordinate of the slab's first cell along its axis (x slabs: may be
@@ -149,6 +150,8 @@ struct TmaMap {           // (CPU interpreter) the tensor a map describes: [n2][
 #define FDTD_MBAR_WAIT(bar, parity) emu::mbar_wait(bar)
 #define FDTD_TMA_LOAD_3D(dst, map, c0, c1, c2, b0, b1, bar) \
   emu::tma_load_3d((dst), (map)->base, sizeof(*(map)->base), (map)->n0, (map)->n1, (map)->n2, (c0), (c1), (c2), (b0), (b1), (bar))
+#define FDTD_BULK_LOAD(dst, src, bytes, bar) emu::bulk_load((dst), (src), (bytes), (bar))
+#define FDTD_SHFL_DOWN1(v) emu::shfl_down1(v)
 #else
 template <typename T>
 struct TmaMap {
@@ -173,6 +176,13 @@ FDTD_DEV unsigned fused_smem_addr(const void* p) { return (unsigned)__cvta_gener
           fdtd::fused_smem_addr(dst)),                                                                            \
       "l"((unsigned long long)(map)), "r"((int)(c0)), "r"((int)(c1)), "r"((int)(c2)), "r"(fdtd::fused_smem_addr(bar)) \
       : "memory")
+// a contiguous run of global memory (16-byte aligned, a multiple of 16 bytes) into shared memory, counted on `bar`
+#define FDTD_BULK_LOAD(dst, src, bytes, bar)                                                                     \
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(  \
+                   fdtd::fused_smem_addr(dst)),                                                                  \
+               "l"(src), "r"((unsigned)(bytes)), "r"(fdtd::fused_smem_addr(bar))                                 \
+               : "memory")
+#define FDTD_SHFL_DOWN1(v) __shfl_down_sync(0xffffffffu, (v), 1)
 #endif
 
 template <typename T>
@@ -195,17 +205,37 @@ struct FusedTmaMaps {
                                      // of what saturates HBM; prefetches cost neither registers nor shared memory
 #endif
 
+#ifndef FDTD_FUSED_SHFL
+#define FDTD_FUSED_SHFL 1        // a tile row is one warp (31 core lanes + the halo lane): the z+1 neighbour's E_new comes from
+                                 // the next lane by shuffle, only the two components differenced along y (Ex, Ez) are published
+                                 // through shared memory
+#endif
+#ifndef FDTD_FUSED_PSI_STAGE
+#define FDTD_FUSED_PSI_STAGE 1   // psi of the z slab a block touches (two of every nine blocks at 1024^3) is staged with the
+                                 // plane's field tiles: the rows of a tile are ONE contiguous run of a z slab's psi array, so
+                                 // four 1-D bulk copies per plane take the only global loads off the per-plane critical path
+#endif
+
 template <typename T, int VEC>
 struct FusedPipeLayout {
   static constexpr int R = FUSED_R, L = FUSED_L;
+  static constexpr bool SHFL = (FDTD_FUSED_SHFL != 0) && (L + 1 == 32);
   static constexpr int HV = L + 2, EV = L + 1;                 // vectors per staged row
   static constexpr int PADW = 128 / (int)sizeof(T);            // a TMA destination is 128-byte aligned
   static constexpr int HC = ((R + 2) * HV * VEC + PADW - 1) / PADW * PADW;   // words per staged H component
   static constexpr int EC = ((R + 1) * EV * VEC + PADW - 1) / PADW * PADW;   // words per staged E component
   static constexpr int H_WORDS = 3 * HC;                       // H_old tile: rows j0-1 .. j0+R, vectors -1 .. L
   static constexpr int E_WORDS = 3 * EC;                       // E_old tile: rows j0 .. j0+R, vectors 0 .. L
-  static constexpr int STAGE_WORDS = H_WORDS + E_WORDS;
-  static constexpr int X_WORDS = 3 * (R + 1) * EV * VEC;       // one published E_new tile
+  static constexpr int FIELD_WORDS = H_WORDS + E_WORDS;
+  // staged psi of one z slab: psi_E[0], psi_E[1] (rows j0 .. j0+R of plane i), psi_H[0], psi_H[1] (rows j0 .. j0+R-1 of
+  // plane i-1), each (rows x tp) words as they lie in memory, tp <= PSI_TP
+  static constexpr int PSI_TP = 16;
+  static constexpr int PSI_ARR = (R + 1) * PSI_TP;
+  static constexpr int PSI_WORDS = FDTD_FUSED_PSI_STAGE ? 4 * PSI_ARR : 0;
+  static constexpr int STAGE_WORDS = FIELD_WORDS + PSI_WORDS;
+  static constexpr int XC = (R + 1) * EV * VEC;                // words per published component
+  static constexpr int X_COMPS = SHFL ? 2 : 3;                 // published components of E_new (SHFL: Ex, Ez)
+  static constexpr int X_WORDS = X_COMPS * XC;                 // one published E_new tile
   static constexpr unsigned TMA_BYTES = 3u * ((R + 2) * HV + (R + 1) * EV) * VEC * (unsigned)sizeof(T);  // per plane
   static constexpr int STAGES = 3;
   static constexpr size_t BAR_OFFSET = sizeof(T) * (size_t)(STAGES * STAGE_WORDS + 2 * X_WORDS);   // the mbarriers
@@ -222,11 +252,9 @@ struct FusedDiffs {
 };
 
 template <typename T, int VEC, bool IS_E, int AX>
-FDTD_DEV void fused_slab_cells(const typename FusedParams<T>::Slab& S, const T* psi_in, T* psi_out, bool store,
-                               i64 idx, int l0, const FusedDiffs<T, VEC>& D, Pack<T, VEC>& f0, Pack<T, VEC>& f1,
-                               Pack<T, VEC>& f2, const T (&coef)[3]) {
-  Pack<T, VEC> a = ldv<T, VEC>(psi_in + idx);
-  Pack<T, VEC> b = ldv<T, VEC>(psi_in + S.count + idx);
+FDTD_DEV void fused_slab_cells(const typename FusedParams<T>::Slab& S, Pack<T, VEC>& a, Pack<T, VEC>& b, int l0,
+                               const FusedDiffs<T, VEC>& D, Pack<T, VEC>& f0, Pack<T, VEC>& f1, Pack<T, VEC>& f2,
+                               const T (&coef)[3]) {
   const T* bt = IS_E ? S.bE : S.bH;
   const T* ct = IS_E ? S.cE : S.cH;
   constexpr int U = (AX + 1) % 3, W = (AX + 2) % 3;
@@ -260,6 +288,25 @@ FDTD_DEV void fused_slab_cells(const typename FusedParams<T>::Slab& S, const T* 
       }
     }
   }
+}
+
+// One slab's CPML update of a thread's VEC cells: psi comes from global memory at `idx`, or -- the z slab a block
+// stages -- from the shared-memory copy at `sp`; the new psi goes to global memory (`store`: owner threads only).
+template <typename T, int VEC, bool IS_E>
+FDTD_DEV void fused_slab_update(const typename FusedParams<T>::Slab& S, const T* psi_in, T* psi_out, bool store,
+                                const T* sp, int sp_pitch, i64 idx, int l0, const FusedDiffs<T, VEC>& D,
+                                Pack<T, VEC>& f0, Pack<T, VEC>& f1, Pack<T, VEC>& f2, const T (&coef)[3]) {
+  Pack<T, VEC> a, b;
+  if (sp != nullptr) {
+    a = ldv<T, VEC>(sp);
+    b = ldv<T, VEC>(sp + sp_pitch);
+  } else {
+    a = ldv<T, VEC>(psi_in + idx);
+    b = ldv<T, VEC>(psi_in + S.count + idx);
+  }
+  if (S.axis == 0) fused_slab_cells<T, VEC, IS_E, 0>(S, a, b, l0, D, f0, f1, f2, coef);
+  else if (S.axis == 1) fused_slab_cells<T, VEC, IS_E, 1>(S, a, b, l0, D, f0, f1, f2, coef);
+  else fused_slab_cells<T, VEC, IS_E, 2>(S, a, b, l0, D, f0, f1, f2, coef);
   if (store) {
     stv<T, VEC>(psi_out + idx, a);
     stv<T, VEC>(psi_out + S.count + idx, b);
@@ -315,15 +362,37 @@ FDTD_DEV void fused_prefetch(const void* a) {
 #endif
 }
 
-// one plane of the block's tile into a stage, by TMA (thread 0 only)
+// one plane of the block's tile into a stage, by TMA (thread 0 only); zs >= 0: also the psi rows of z slab zs --
+// psi_E of plane ip (rows j0 .. j0+R) and psi_H of plane ip-1 (rows j0 .. j0+R-1; with_h), contiguous in memory
 template <typename T, int VEC>
-FDTD_DEV void fused_stage_tma(const FusedTmaMaps<T>& M, T* stage, unsigned long long* bar, int kz0, int j0, int ip) {
+FDTD_DEV void fused_stage_tma(const FusedParams<T>& P, const FusedTmaMaps<T>& M, T* stage, unsigned long long* bar,
+                              int kz0, int j0, int ip, int zs, bool with_h) {
   using Lay = FusedPipeLayout<T, VEC>;
-  FDTD_MBAR_EXPECT(bar, Lay::TMA_BYTES);
+  unsigned bytes = Lay::TMA_BYTES, be = 0, bh = 0;
+  if (FDTD_FUSED_PSI_STAGE && zs >= 0) {
+    const int rows_e = P.Ny - j0 < Lay::R + 1 ? P.Ny - j0 : Lay::R + 1;
+    const int rows_h = P.Ny - j0 < Lay::R ? P.Ny - j0 : Lay::R;
+    be = (unsigned)(rows_e * P.sl[zs].tp) * (unsigned)sizeof(T);
+    bh = with_h ? (unsigned)(rows_h * P.sl[zs].tp) * (unsigned)sizeof(T) : 0u;
+    bytes += 2 * (be + bh);
+  }
+  FDTD_MBAR_EXPECT(bar, bytes);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     FDTD_TMA_LOAD_3D(stage + c * Lay::HC, &M.h[c], kz0 - VEC, j0 - 1, ip + 1, Lay::HV * VEC, Lay::R + 2, bar);
     FDTD_TMA_LOAD_3D(stage + Lay::H_WORDS + c * Lay::EC, &M.e[c], kz0, j0, ip + 1, Lay::EV * VEC, Lay::R + 1, bar);
+  }
+  if (FDTD_FUSED_PSI_STAGE && zs >= 0) {
+    const typename FusedParams<T>::Slab& S = P.sl[zs];
+    T* pt = stage + Lay::FIELD_WORDS;
+    const T* se = S.psiE_in + ((i64)ip * P.Ny + j0) * S.tp;
+    FDTD_BULK_LOAD(pt, se, be, bar);
+    FDTD_BULK_LOAD(pt + Lay::PSI_ARR, se + S.count, be, bar);
+    if (with_h) {
+      const T* sh = S.psiH + ((i64)(ip - 1) * P.Ny + j0) * S.tp;
+      FDTD_BULK_LOAD(pt + 2 * Lay::PSI_ARR, sh, bh, bar);
+      FDTD_BULK_LOAD(pt + 3 * Lay::PSI_ARR, sh + S.count, bh, bar);
+    }
   }
 }
 
@@ -365,6 +434,15 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     xs_bits |= P.sl[s].axis == 0 ? (1u << s) : 0u;
   }
   unsigned hit_prev = 0;   // slabs (x slabs included) the cells of plane i-1 lie in: what the H update of i-1 needs
+  // the z slab whose psi this block stages in shared memory (block-uniform): the first one a lane of the tile lies in
+  int zs = -1;
+  if (TMA && FDTD_FUSED_PSI_STAGE && P.psi_stage) {
+    for (int s = P.n_sl - 1; s >= 0; --s)
+      if (P.sl[s].axis == 2 && P.sl[s].tp <= Lay::PSI_TP && kz0 + (L + 1) * VEC > P.sl[s].lo &&
+          kz0 < P.sl[s].lo + P.sl[s].t)
+        zs = s;
+  }
+  const int zs_off = zs >= 0 ? r * P.sl[zs].tp + (k0 - P.sl[zs].lo_al) : 0;   // this thread's cells in a staged psi array
 
   const bool row_m1 = (r == 0) && (j >= 1), vec_m1 = (l == 0) && (k0 >= VEC);   // who copies the y-1 row / z-1 vector
   if (TMA) {
@@ -381,7 +459,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     const int ip = xa + s;
     if (TMA) {
       if (tid == 0 && ip <= xb && ip < P.x1)
-        fused_stage_tma<T, VEC>(M, stages + (ip % 3) * Lay::STAGE_WORDS, bars + (ip % 3), kz0, j0, ip);
+        fused_stage_tma<T, VEC>(P, M, stages + (ip % 3) * Lay::STAGE_WORDS, bars + (ip % 3), kz0, j0, ip, zs, ip > xa);
     } else {
       if (ip <= xb && ip < P.x1)
         fused_stage_issue<T, VEC>(P, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane + p, r, l, inside, row_m1, vec_m1);
@@ -389,7 +467,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     }
   }
 
-  Pack<T, VEC> hp0, hp1, hp2, ep0, ep1, ep2;
+  Pack<T, VEC> hp0, hp1, hp2, ep0 = {}, ep1 = {}, ep2;
   if (active && inside && xa + P.x_offset > 0) {
     const i64 o = (i64)(xa - 1) * plane + p;
     hp0 = ldv<T, VEC>(P.Hin[0] + o);
@@ -410,7 +488,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
       const int ip = i + 2;
       if (TMA) {
         if (tid == 0 && ip <= xb && ip < P.x1)
-          fused_stage_tma<T, VEC>(M, stages + (ip % 3) * Lay::STAGE_WORDS, bars + (ip % 3), kz0, j0, ip);
+          fused_stage_tma<T, VEC>(P, M, stages + (ip % 3) * Lay::STAGE_WORDS, bars + (ip % 3), kz0, j0, ip, zs, ip > xa);
       } else {
         if (ip <= xb && ip < P.x1)
           fused_stage_issue<T, VEC>(P, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane + p, r, l, inside, row_m1, vec_m1);
@@ -519,18 +597,12 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
           if (!((hit_now >> s) & 1u)) continue;
           const typename FusedParams<T>::Slab& S = P.sl[s];
           const bool store = core && i < xb;
-          if (S.axis == 0) {
-            fused_slab_cells<T, VEC, true, 0>(S, S.psiE_in, S.psiE_out, store, (i64)(i - S.xs) * plane + p, i - S.lo,
-                                              D, e0, e1, e2, P.ce);
-          } else {
-            if (S.axis == 1)
-              fused_slab_cells<T, VEC, true, 1>(S, S.psiE_in, S.psiE_out, store, ((i64)i * S.t + (j - S.lo)) * Nz + k0,
-                                                j - S.lo, D, e0, e1, e2, P.ce);
-            else
-              fused_slab_cells<T, VEC, true, 2>(S, S.psiE_in, S.psiE_out, store,
-                                                ((i64)i * P.Ny + j) * S.tp + (k0 - S.lo_al), k0 - S.lo, D, e0, e1, e2,
-                                                P.ce);
-          }
+          const T* sp = (FDTD_FUSED_PSI_STAGE && s == zs) ? sH + Lay::FIELD_WORDS + zs_off : nullptr;
+          const i64 idx = S.axis == 0 ? (i64)(i - S.xs) * plane + p
+                                      : (S.axis == 1 ? ((i64)i * S.t + (j - S.lo)) * Nz + k0
+                                                     : ((i64)i * P.Ny + j) * S.tp + (k0 - S.lo_al));
+          const int l0 = S.axis == 0 ? i - S.lo : (S.axis == 1 ? j - S.lo : k0 - S.lo);
+          fused_slab_update<T, VEC, true>(S, S.psiE_in, S.psiE_out, store, sp, Lay::PSI_ARR, idx, l0, D, e0, e1, e2, P.ce);
         }
         if (src_yz) fused_sources_vec<T, VEC>(P, i, j, k0, off, e0, e1, e2);
         if (core && i < xb) {
@@ -552,17 +624,27 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     }
 
     // ---- H_new[i-1] = H_old - (sc mu^-1) * curl_E(E_new)      (fdtd/grid.py:29-51, 309)
-    constexpr int XC = (R + 1) * EV * VEC;                              // words per published component
+    constexpr int XC = Lay::XC;                                         // words per published component
+    constexpr int XZ = (Lay::X_COMPS - 1) * XC;                         // where the published Ez starts
+    T nx0 = T(0), ny0 = T(0);   // Ex, Ey of the z+1 neighbour cell of this thread's last cell (E_new[i-1])
+    if (Lay::SHFL) {
+      nx0 = FDTD_SHFL_DOWN1(ep0.v[0]);
+      ny0 = FDTD_SHFL_DOWN1(ep1.v[0]);
+    }
     if (core && i > xa) {
       const T* x = xch + ((i - 1) & 1) * Lay::X_WORDS + (r * EV + l) * VEC;
+      if (!Lay::SHFL) {
+        nx0 = x[VEC];
+        ny0 = x[XC + VEC];
+      }
       Pack<T, VEC> hx = hp0, hy = hp1, hz = hp2;
       FusedDiffs<T, VEC> D;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const T ex_y = x[EV * VEC + e];
-        const T ez_y = x[2 * XC + EV * VEC + e];
-        const T ex_z = e == VEC - 1 ? x[VEC] : ep0.v[e < VEC - 1 ? e + 1 : 0];
-        const T ey_z = e == VEC - 1 ? x[XC + VEC] : ep1.v[e < VEC - 1 ? e + 1 : 0];
+        const T ez_y = x[XZ + EV * VEC + e];
+        const T ex_z = e == VEC - 1 ? nx0 : ep0.v[e < VEC - 1 ? e + 1 : 0];
+        const T ey_z = e == VEC - 1 ? ny0 : ep1.v[e < VEC - 1 ? e + 1 : 0];
         // forward differences are masked on the faces i = Nx-1, j = Ny-1 and k = Nz-1 (fdtd/grid.py:41-49)
         const bool face_x = i + P.x_offset == P.Nx_global;
         const bool face_y = j == P.Ny - 1;
@@ -589,17 +671,13 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
       for (int s = 0; hit_prev != 0 && s < P.n_sl; ++s) {
         if (!((hit_prev >> s) & 1u)) continue;
         const typename FusedParams<T>::Slab& S = P.sl[s];
-        if (S.axis == 0) {
-          fused_slab_cells<T, VEC, false, 0>(S, S.psiH, S.psiH, true, (i64)(ih - S.xs) * plane + p, ih - S.lo, D, hx,
-                                             hy, hz, P.ch);
-        } else {
-          if (S.axis == 1)
-            fused_slab_cells<T, VEC, false, 1>(S, S.psiH, S.psiH, true, ((i64)ih * S.t + (j - S.lo)) * Nz + k0,
-                                               j - S.lo, D, hx, hy, hz, P.ch);
-          else
-            fused_slab_cells<T, VEC, false, 2>(S, S.psiH, S.psiH, true, ((i64)ih * P.Ny + j) * S.tp + (k0 - S.lo_al),
-                                               k0 - S.lo, D, hx, hy, hz, P.ch);
-        }
+        // (the stage of plane i carries psi_H of plane i-1; the last iteration of the last chunk has no stage)
+        const T* sp = (FDTD_FUSED_PSI_STAGE && s == zs && i < P.x1) ? sH + Lay::FIELD_WORDS + 2 * Lay::PSI_ARR + zs_off : nullptr;
+        const i64 idx = S.axis == 0 ? (i64)(ih - S.xs) * plane + p
+                                    : (S.axis == 1 ? ((i64)ih * S.t + (j - S.lo)) * Nz + k0
+                                                   : ((i64)ih * P.Ny + j) * S.tp + (k0 - S.lo_al));
+        const int l0 = S.axis == 0 ? ih - S.lo : (S.axis == 1 ? j - S.lo : k0 - S.lo);
+        fused_slab_update<T, VEC, false>(S, S.psiH, S.psiH, true, sp, Lay::PSI_ARR, idx, l0, D, hx, hy, hz, P.ch);
       }
       const i64 om = off - plane;
       stv<T, VEC>(P.Hout[0] + om, hx);
@@ -611,8 +689,8 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     if (active) {
       T* x = xch + (i & 1) * Lay::X_WORDS + (r * EV + l) * VEC;
       stv<T, VEC>(x, e0);
-      stv<T, VEC>(x + XC, e1);
-      stv<T, VEC>(x + 2 * XC, e2);
+      if (!Lay::SHFL) stv<T, VEC>(x + XC, e1);
+      stv<T, VEC>(x + XZ, e2);
       ep0 = e0;
       ep1 = e1;
       ep2 = e2;

@@ -43,6 +43,11 @@ VARIANTS = {
     "pipe_r7l31_mb2_pf4": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=4"],
     "pipe_r7l31_mb2_pf6": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=6"],
     "pipe_cpasync": ["-DFDTD_FUSED_TMA=0"],
+    # session 13: z+1 neighbour by shuffle, psi of the block's z slab staged by bulk copies
+    "pipe_v2_noshfl": ["-DFDTD_FUSED_SHFL=0"],
+    "pipe_v2_nopsi": ["-DFDTD_FUSED_PSI_STAGE=0"],
+    "pipe_v2_old": ["-DFDTD_FUSED_SHFL=0", "-DFDTD_FUSED_PSI_STAGE=0"],
+    "pipe_v2_r8": ["-DFDTD_FUSED_ROWS=8"],
     "pipe_tma_r15l31_mb1": ["-DFDTD_FUSED_ROWS=15", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=1"],
     "pipe_tma_r3l31_mb4": ["-DFDTD_FUSED_ROWS=3", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4"],
     "pipe_psi1": ["-DFDTD_FUSED_PIPE_PSI_PREFETCH=1"],

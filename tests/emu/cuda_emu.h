@@ -116,10 +116,19 @@ inline void tma_load_3d(void* dst, const void* base, size_t esize, long n0, long
                         int b0, int b1, const void* bar) {
   t_tma.push_back({dst, (const char*)base, esize, n0, n1, n2, c0, c1, c2, b0, b1, bar});
 }
+// cp.async.bulk (1-D): `bytes` contiguous bytes, deferred like the tensor copies (n0 < 0 marks it, c0 = bytes)
+inline void bulk_load(void* dst, const void* src, size_t bytes, const void* bar) {
+  t_tma.push_back({dst, (const char*)src, 1, -1, 0, 0, (long)bytes, 0, 0, 0, 0, bar});
+}
 inline void mbar_wait(const void* bar) {
   for (size_t k = 0; k < t_tma.size();) {
     const TmaCopy& c = t_tma[k];
     if (c.bar != bar) { ++k; continue; }
+    if (c.n0 < 0) {
+      memcpy(c.dst, c.base, (size_t)c.c0);
+      t_tma.erase(t_tma.begin() + k);
+      continue;
+    }
     char* out = (char*)c.dst;
     for (int y = 0; y < c.b1; ++y)
       for (int z = 0; z < c.b0; ++z, out += c.esize) {
@@ -129,6 +138,19 @@ inline void mbar_wait(const void* bar) {
       }
     t_tma.erase(t_tma.begin() + k);
   }
+}
+
+// __shfl_down_sync(full mask, v, 1) of a one-dimensional block whose rows are warps: every thread of the block deposits
+// its value, all run up to this point, each reads its upper neighbour's (the last lane of a warp gets its own back)
+inline thread_local double t_shfl[1024];
+template <typename V>
+inline V shfl_down1(V v) {
+  const unsigned t = t_cur->tid.x;
+  t_shfl[t] = (double)v;
+  sync_threads();
+  const V r = ((t & 31u) != 31u && t + 1 < t_blockDim.x) ? (V)t_shfl[t + 1] : v;
+  sync_threads();
+  return r;
 }
 
 template <typename F>

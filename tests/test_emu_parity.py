@@ -322,7 +322,8 @@ def test_running_dft_of_a_current_detector():
 
 @pytest.mark.parametrize("dtype,n,t,zp", [("float32", (20, 23, 40), 3, "lo"), ("float64", (14, 21, 22), 3, "both"),
                                           ("float32", (13, 9, 16), 2, "none"), ("float32", (12, 40, 144), 2, "both"),
-                                          ("float64", (12, 11, 136), 2, "hi"), ("float32", (16, 19, 24), 3, "zfirst")])
+                                          ("float64", (12, 11, 136), 2, "hi"), ("float32", (16, 19, 24), 3, "zfirst"),
+                                          ("float32", (10, 9, 132), 2, "halo"), ("float64", (10, 9, 48), 2, "thick")])
 def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t, zp):
     """run() with the single-pass E+H kernel (one launch per step over the whole grid: ping-pong field and psi_E
     buffers, inputs staged by asynchronous copies, E_new exchanged through shared memory -- its block runs as
@@ -346,6 +347,11 @@ def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t, zp):
             g[:, :, 0:t + 1] = fd.PML()
         if zp in ("hi", "both"):
             g[:, :, -(t + 2):] = fd.PML()
+        if zp == "halo":            # the slab starts exactly at the halo lane of the first z tile (31 lanes x 4 cells)
+            g[:, :, -8:] = fd.PML()
+        if zp == "thick":           # psi rows too long for the staged copy: those blocks load psi from global memory
+            g[:, :, 0:19] = fd.PML()
+            g[:, :, -18:] = fd.PML()
         g[n[0] // 2, n[1] // 2, n[2] // 2] = fd.PointSource(period=17, name="centre")
         g[2, n[1] // 2, 3] = fd.PointSource(period=11, amplitude=0.4, name="in_pml")
         g[n[0] // 2, n[1] // 2 - 1, 0] = fd.PointSource(period=13, amplitude=0.3, name="on_z_face")
