@@ -876,14 +876,17 @@ int fdtd_ipc_import(const void* handle64, int64_t offset, void** dev_ptr) {
 extern "C++" {
 namespace {
 // automatic mode (fuse_eh = 2): the fused kernel wins where its 7 x 31-vector tiles quantise the y-z plane well and
-// the march is long enough -- measured on the B200 (profiles/r2_fused_sizes_tma.txt): float32 640^3 -3 %, 768^3 +6 %,
-// 1024^3 +17 %; float64 512^3 +11 %; slabs of 1024^2 planes: 64 planes -5 %, 128 +3 %, 192 +9 %
+// the march is long enough -- measured on the B200 (profiles/r2_s14/fused_sizes.log): float32 512^3 -5 % (4.13 z tiles),
+// 576^3 +12 %, 640^3 +7 %, 768^3 +13 %, 1024^3 +25 %; float64 256^3 -18 %, 384^3 +6 %, 512^3 +19 %; slabs of 1024^2
+// planes: 64 planes +2 %, 96 +3 %, 128 +10 %, 256 +17 %
 #ifdef FDTD_EMU
 #define FDTD_FUSE_EH_MIN_PLANE_BYTES 0
 #define FDTD_FUSE_EH_MIN_PLANES 2
+#define FDTD_FUSE_EH_MIN_Z_FILL 0.0
 #else
-#define FDTD_FUSE_EH_MIN_PLANE_BYTES (2LL << 20)
-#define FDTD_FUSE_EH_MIN_PLANES 96
+#define FDTD_FUSE_EH_MIN_PLANE_BYTES (1100LL << 10)
+#define FDTD_FUSE_EH_MIN_PLANES 64
+#define FDTD_FUSE_EH_MIN_Z_FILL 0.85     // Nz / (z tiles x tile length): the last z tile of a row is mostly empty below
 #endif
 
 // fuse_eh = 1: wherever it is legal; fuse_eh = 2: only where it is also faster (large grids: what counts is the
@@ -895,8 +898,10 @@ bool fuse_eh_eligible(const fdtd_desc* d, bool sharded = false) {
   if ((d->Nx != d->Nx_global) != sharded || d->n_post != 0 || d->n_deep != 0 || d->x_wrap) return false;
   const int vec = d->dtype == FDTD_F32 ? 4 : 2;
   if (d->Nz % vec) return false;
+  const int tile_z = fdtd::FUSED_L * vec;
   if (d->fuse_eh == 2 && ((int64_t)d->Ny * d->Nz * (d->dtype == FDTD_F32 ? 4 : 8) < FDTD_FUSE_EH_MIN_PLANE_BYTES ||
-                          d->Nx < FDTD_FUSE_EH_MIN_PLANES))
+                          d->Nx < FDTD_FUSE_EH_MIN_PLANES ||
+                          (double)d->Nz < FDTD_FUSE_EH_MIN_Z_FILL * (double)((d->Nz + tile_z - 1) / tile_z * tile_z)))
     return false;
   if (sharded && d->Nx < 4) return false;
   int nsrc = 0;
@@ -911,6 +916,7 @@ bool fuse_eh_eligible(const fdtd_desc* d, bool sharded = false) {
     // the kernel applies every CPML correction itself (slabs registered after a periodic boundary are post ops, and
     // periodic boundaries are excluded above anyway) and needs the second psi_E buffer
     if (!d->slabs[s].fused || (d->slabs[s].psi_count > 0 && !d->psi_E2[s])) return false;
+    if (d->slabs[s].thickness > FDTD_FUSED_TAB_T) return false;   // (its coefficient tables live in shared memory)
   }
 #ifndef FDTD_EMU
   return d->Nx >= 8 && d->Ny >= 8 && d->Nz >= 32 * vec;
@@ -922,6 +928,20 @@ bool fuse_eh_eligible(const fdtd_desc* d, bool sharded = false) {
 #ifndef FDTD_FUSED_TMA
 #define FDTD_FUSED_TMA 1     // the fused kernel's inputs are staged by TMA (0: per-thread cp.async copies)
 #endif
+
+int sm_count() {
+#ifdef FDTD_EMU
+  return 148;
+#else
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+#endif
+}
 
 // tensor maps of the three components of one field buffer for the fused kernel's staging: a 3-D tensor
 // [Nx + 2][Ny][Nz] per component (the ghost x-planes belong to it), box = (bz x by x 1 plane)
@@ -967,9 +987,15 @@ int fused_tma_maps(const fdtd_desc* d, void* const* F, int bz, int by, fdtd::Tma
       const cuuint64_t strides[2] = {(cuuint64_t)d->Nz * sizeof(T), (cuuint64_t)d->plane * sizeof(T)};
       const cuuint32_t box[3] = {(cuuint32_t)bz, (cuuint32_t)by, 1};
       const cuuint32_t estr[3] = {1, 1, 1};
+      // (development knob: FDTD_B200_TMA_L2PROMO = 0 none / 1 64 B / 2 128 B / 3 256 B)
+      static const int promo = [] { const char* v = getenv("FDTD_B200_TMA_L2PROMO"); return v ? atoi(v) : 2; }();
+      const CUtensorMapL2promotion l2 = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                        : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                        : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                     : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
       CUresult r = encode(&e.m, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base,
-                          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
         e.base = nullptr;
         return fail(FDTD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -1050,11 +1076,23 @@ int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void*
   P.psi_stage = 1;
   // planes marched per block: ~48 (1024^3 f32: 10.97 / 10.77 / 10.68 / 10.84 ms per step at 16 / 32 / 48 / 64,
   // profiles/r2_fused_tma.txt), in chunks of equal length
+  // On thin slabs what counts is how the blocks fill the GPU: the number of chunks that minimises
+  // (waves of blocks) x (chunk length + start-up), two resident blocks per SM (128 planes on one of eight GPUs: four
+  // chunks of 32 = 17.9 waves instead of three of 43 = 13.4).
   if (d->x_chunk > 0) {
     P.x_chunk = d->x_chunk;
   } else {
-    const int n_chunks = (Nx + 47) / 48;
-    P.x_chunk = (Nx + n_chunks - 1) / n_chunks;
+    const int64_t tiles = (int64_t)((Nz + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC)) * ((Ny + fdtd::FUSED_R - 1) / fdtd::FUSED_R);
+    const int64_t slots = 2 * (int64_t)sm_count();
+    int best_c = (Nx + 47) / 48;
+    int64_t best_cost = -1;
+    for (int c = (Nx + 51) / 52; c <= (Nx + 27) / 28; ++c) {
+      if (c < 1) continue;
+      const int len = (Nx + c - 1) / c;
+      const int64_t cost = ((tiles * c + slots - 1) / slots) * (len + 2);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
+    }
+    P.x_chunk = (Nx + best_c - 1) / best_c;
   }
   for (int c = 0; c < 3; ++c) {
     P.Ein[c] = (const T*)Ein[c];

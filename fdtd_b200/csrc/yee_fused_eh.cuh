@@ -216,6 +216,10 @@ struct FusedTmaMaps {
                                  // four 1-D bulk copies per plane take the only global loads off the per-plane critical path
 #endif
 
+#ifndef FDTD_FUSED_TAB_T
+#define FDTD_FUSED_TAB_T 32      // thickest CPML slab the fused kernel takes (cells); thicker ones: two half-steps
+#endif
+
 template <typename T, int VEC>
 struct FusedPipeLayout {
   static constexpr int R = FUSED_R, L = FUSED_L;
@@ -238,7 +242,12 @@ struct FusedPipeLayout {
   static constexpr int X_WORDS = X_COMPS * XC;                 // one published E_new tile
   static constexpr unsigned TMA_BYTES = 3u * ((R + 2) * HV + (R + 1) * EV) * VEC * (unsigned)sizeof(T);  // per plane
   static constexpr int STAGES = 3;
-  static constexpr size_t BAR_OFFSET = sizeof(T) * (size_t)(STAGES * STAGE_WORDS + 2 * X_WORDS);   // the mbarriers
+  // the CPML coefficient tables (b_E, c_E, b_H, c_H of every slab, TAB_T entries each) live in shared memory: their
+  // loads sat on the long scoreboard in every slab cell (profiles/r2_s13/stalls_fused_v2.txt)
+  static constexpr int TAB_T = FDTD_FUSED_TAB_T;
+  static constexpr int TAB_WORDS = 6 * 4 * TAB_T;
+  static constexpr size_t TAB_OFFSET = sizeof(T) * (size_t)(STAGES * STAGE_WORDS + 2 * X_WORDS);
+  static constexpr size_t BAR_OFFSET = TAB_OFFSET + sizeof(T) * (size_t)TAB_WORDS;   // the mbarriers
   static constexpr size_t BYTES = BAR_OFFSET + 8 * STAGES;
 };
 
@@ -254,9 +263,7 @@ struct FusedDiffs {
 template <typename T, int VEC, bool IS_E, int AX>
 FDTD_DEV void fused_slab_cells(const typename FusedParams<T>::Slab& S, Pack<T, VEC>& a, Pack<T, VEC>& b, int l0,
                                const FusedDiffs<T, VEC>& D, Pack<T, VEC>& f0, Pack<T, VEC>& f1, Pack<T, VEC>& f2,
-                               const T (&coef)[3]) {
-  const T* bt = IS_E ? S.bE : S.bH;
-  const T* ct = IS_E ? S.cE : S.cH;
+                               const T (&coef)[3], const T* bt, const T* ct) {
   constexpr int U = (AX + 1) % 3, W = (AX + 2) % 3;
   Pack<T, VEC>& fu = U == 0 ? f0 : (U == 1 ? f1 : f2);
   Pack<T, VEC>& fw = W == 0 ? f0 : (W == 1 ? f1 : f2);
@@ -295,7 +302,10 @@ FDTD_DEV void fused_slab_cells(const typename FusedParams<T>::Slab& S, Pack<T, V
 template <typename T, int VEC, bool IS_E>
 FDTD_DEV void fused_slab_update(const typename FusedParams<T>::Slab& S, const T* psi_in, T* psi_out, bool store,
                                 const T* sp, int sp_pitch, i64 idx, int l0, const FusedDiffs<T, VEC>& D,
-                                Pack<T, VEC>& f0, Pack<T, VEC>& f1, Pack<T, VEC>& f2, const T (&coef)[3]) {
+                                Pack<T, VEC>& f0, Pack<T, VEC>& f1, Pack<T, VEC>& f2, const T (&coef)[3],
+                                const T* tab) {
+  const T* bt = tab + (IS_E ? 0 : 2) * FDTD_FUSED_TAB_T;   // (shared memory: b_E, c_E, b_H, c_H of this slab)
+  const T* ct = bt + FDTD_FUSED_TAB_T;
   Pack<T, VEC> a, b;
   if (sp != nullptr) {
     a = ldv<T, VEC>(sp);
@@ -304,9 +314,9 @@ FDTD_DEV void fused_slab_update(const typename FusedParams<T>::Slab& S, const T*
     a = ldv<T, VEC>(psi_in + idx);
     b = ldv<T, VEC>(psi_in + S.count + idx);
   }
-  if (S.axis == 0) fused_slab_cells<T, VEC, IS_E, 0>(S, a, b, l0, D, f0, f1, f2, coef);
-  else if (S.axis == 1) fused_slab_cells<T, VEC, IS_E, 1>(S, a, b, l0, D, f0, f1, f2, coef);
-  else fused_slab_cells<T, VEC, IS_E, 2>(S, a, b, l0, D, f0, f1, f2, coef);
+  if (S.axis == 0) fused_slab_cells<T, VEC, IS_E, 0>(S, a, b, l0, D, f0, f1, f2, coef, bt, ct);
+  else if (S.axis == 1) fused_slab_cells<T, VEC, IS_E, 1>(S, a, b, l0, D, f0, f1, f2, coef, bt, ct);
+  else fused_slab_cells<T, VEC, IS_E, 2>(S, a, b, l0, D, f0, f1, f2, coef, bt, ct);
   if (store) {
     stv<T, VEC>(psi_out + idx, a);
     stv<T, VEC>(psi_out + S.count + idx, b);
@@ -405,6 +415,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   FDTD_DYN_SMEM(smem_raw);
   T* const stages = reinterpret_cast<T*>(smem_raw);
   T* const xch = stages + Lay::STAGES * Lay::STAGE_WORDS;
+  T* const tabs = reinterpret_cast<T*>(smem_raw + Lay::TAB_OFFSET);
   unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + Lay::BAR_OFFSET);
 
   const int tid = threadIdx.x;
@@ -431,7 +442,8 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     const bool hit = P.sl[s].axis == 1 ? (j >= P.sl[s].lo && j < P.sl[s].lo + P.sl[s].t)
                                        : (k0 - P.sl[s].lo + VEC > 0) && (k0 - P.sl[s].lo < P.sl[s].t);
     sl_hit |= (hit && P.sl[s].axis != 0) ? (1u << s) : 0u;
-    xs_bits |= P.sl[s].axis == 0 ? (1u << s) : 0u;
+    // (x slabs that do not reach into this block's planes [xa, xb] are never looked at again)
+    xs_bits |= (P.sl[s].axis == 0 && P.sl[s].xe > xa && P.sl[s].xs <= xb) ? (1u << s) : 0u;
   }
   unsigned hit_prev = 0;   // slabs (x slabs included) the cells of plane i-1 lie in: what the H update of i-1 needs
   // the z slab whose psi this block stages in shared memory (block-uniform): the first one a lane of the tile lies in
@@ -452,8 +464,14 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
 #ifndef FDTD_EMU
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
-    __syncthreads();
   }
+  // the coefficient tables of every slab (thickness <= TAB_T: the host's eligibility test)
+  for (int n = tid; n < P.n_sl * 4 * Lay::TAB_T; n += (R + 1) * (L + 1)) {
+    const int s = n / (4 * Lay::TAB_T), w = (n / Lay::TAB_T) & 3, ll = n % Lay::TAB_T;
+    const T* src = w == 0 ? P.sl[s].bE : (w == 1 ? P.sl[s].cE : (w == 2 ? P.sl[s].bH : P.sl[s].cH));
+    tabs[n] = ll < P.sl[s].t ? src[ll] : T(0);
+  }
+  __syncthreads();
   // two planes in flight before the first one is consumed (one commit group per plane, empty ones included)
   for (int s = 0; s < 2; ++s) {
     const int ip = xa + s;
@@ -483,6 +501,10 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     } else {
       FDTD_CP_ASYNC_WAIT_1();
     }
+    // (tried: the barrier split into an mbarrier arrival after the publish below and a wait between the next E and H
+    // updates, so that warps may drift by one E update: 10.15 instead of 10.00 ms per step, profiles/r2_s14/; an L2
+    // prefetch of the tiles 3 / 4 / 6 planes ahead by cp.async.bulk.prefetch.tensor: 10.80 / 11.19 / 12.27 ms against
+    // 9.98, profiles/r2_s15/ -- the kernel waits for DRAM at 5.7 TB/s, more requests in flight only queue longer)
     __syncthreads();
     {
       const int ip = i + 2;
@@ -602,7 +624,8 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
                                       : (S.axis == 1 ? ((i64)i * S.t + (j - S.lo)) * Nz + k0
                                                      : ((i64)i * P.Ny + j) * S.tp + (k0 - S.lo_al));
           const int l0 = S.axis == 0 ? i - S.lo : (S.axis == 1 ? j - S.lo : k0 - S.lo);
-          fused_slab_update<T, VEC, true>(S, S.psiE_in, S.psiE_out, store, sp, Lay::PSI_ARR, idx, l0, D, e0, e1, e2, P.ce);
+          fused_slab_update<T, VEC, true>(S, S.psiE_in, S.psiE_out, store, sp, Lay::PSI_ARR, idx, l0, D, e0, e1, e2, P.ce,
+                                          tabs + s * 4 * Lay::TAB_T);
         }
         if (src_yz) fused_sources_vec<T, VEC>(P, i, j, k0, off, e0, e1, e2);
         if (core && i < xb) {
@@ -677,7 +700,8 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
                                     : (S.axis == 1 ? ((i64)ih * S.t + (j - S.lo)) * Nz + k0
                                                    : ((i64)ih * P.Ny + j) * S.tp + (k0 - S.lo_al));
         const int l0 = S.axis == 0 ? ih - S.lo : (S.axis == 1 ? j - S.lo : k0 - S.lo);
-        fused_slab_update<T, VEC, false>(S, S.psiH, S.psiH, true, sp, Lay::PSI_ARR, idx, l0, D, hx, hy, hz, P.ch);
+        fused_slab_update<T, VEC, false>(S, S.psiH, S.psiH, true, sp, Lay::PSI_ARR, idx, l0, D, hx, hy, hz, P.ch,
+                                           tabs + s * 4 * Lay::TAB_T);
       }
       const i64 om = off - plane;
       stv<T, VEC>(P.Hout[0] + om, hx);

@@ -24,10 +24,12 @@ WAVE_TABLE_MIN = 1024          # look-ahead of the host waveform tables (steps)
 WAVE_TABLE_MAX = 1 << 16
 GRAPH_MAX_CELLS = 1 << 25      # grids up to this many cells replay CUDA graphs of 32-step chunks in run()
 # automatic mode of the single-pass E+H kernel (grid._fuse_eh = 2): where it beats the two half-steps on the B200
-# (profiles/r2_fused_sizes_tma.txt: float32 640^3 -3 %, 768^3 +6 %, 1024^3 +17 %; float64 512^3 +11 %; slabs of 1024^2
-# planes: 64 planes -5 %, 128 +3 %, 192 +9 %)
-FUSE_EH_MIN_PLANE_BYTES = 2 << 20     # y-z plane of one component
-FUSE_EH_MIN_PLANES = 96               # x-planes (unsharded)
+# (profiles/r2_s14/fused_sizes.log: float32 512^3 -5 %, 576^3 +12 %, 640^3 +7 %, 768^3 +13 %, 1024^3 +25 %; float64
+# 384^3 +6 %, 512^3 +19 %; slabs of 1024^2 planes: 64 planes +2 %, 128 +10 %, 256 +17 %) -- the same test as
+# fuse_eh_eligible() in csrc/fdtd_b200.cu
+FUSE_EH_MIN_PLANE_BYTES = 1100 << 10  # y-z plane of one component
+FUSE_EH_MIN_PLANES = 64               # x-planes (unsharded)
+FUSE_EH_MIN_Z_FILL = 0.85             # Nz / (z tiles of 31 vectors x their length)
 FUSE_EH_MIN_SLAB = 112                # x-planes per rank (x-sharded: a fused step ends in a short serial tail)
 
 
@@ -298,7 +300,9 @@ class Engine:
         # a second psi_E per slab: homogeneous, unsharded grids only.  grid._fuse_eh / FDTD_B200_FUSE_EH: 0 never,
         # 1 wherever legal, 2 (default) where it is also faster -- large grids -- and the buffers fit in free memory
         want = g._fuse_eh
+        tile_z = 31 * (16 // g._E.element_size())
         big = (g.Ny * g.Nz * g._E.element_size() >= FUSE_EH_MIN_PLANE_BYTES
+               and g.Nz >= FUSE_EH_MIN_Z_FILL * (-(-g.Nz // tile_z) * tile_z)
                and (g.Nx // part.world >= FUSE_EH_MIN_SLAB if part.sharded else g.Nx >= FUSE_EH_MIN_PLANES))
         ok = bool(want and not self._hooked and ie_eff is None and imu is None and not post and not x_wrap
                   and g._sdtype is g._dtype and (want == 1 or big)

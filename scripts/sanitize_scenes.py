@@ -16,8 +16,8 @@ import scenes  # noqa: E402
 
 
 def main():
-    fused = "fused" in sys.argv[1:]
-    for dtype in ("float64", "float32", "float32x"):
+    fused = "fused" in sys.argv[1:] or "only-fused" in sys.argv[1:]
+    for dtype in () if "only-fused" in sys.argv[1:] else ("float64", "float32", "float32x"):
         fd.set_backend("cuda." + dtype)
         for name in ("pml3d", "objects3d", "periodic3d", "stacked3d", "feed50", "quickstart2d"):
             g = scenes.SCENES[name][0](fd)

@@ -64,6 +64,7 @@ struct Fiber {
   std::vector<char> stack;
   bool done = false;
   dim3 tid;
+  unsigned long shfl_gen = 0;
   // cp.async emulation: copies are DEFERRED to the wait that covers their group (the latest moment the hardware
   // may complete them), so a kernel that reads a staged value before waiting for it reads stale data here too
   std::vector<AsyncCopy> open;
@@ -74,14 +75,39 @@ inline thread_local Fiber* t_cur = nullptr;
 inline thread_local void (*t_entry)(void*) = nullptr;
 inline thread_local void* t_entry_arg = nullptr;
 
+inline void fiber_exit();
 inline void fiber_main() {
   t_entry(t_entry_arg);
   t_cur->done = true;
+  fiber_exit();
   swapcontext(&t_cur->ctx, &t_sched);
 }
 
-// __syncthreads(): every live thread of the block runs up to its next barrier before any continues
-inline void sync_threads() { swapcontext(&t_cur->ctx, &t_sched); }
+
+// hand control to the next fiber of the block (every spin loop below does)
+inline void yield() { swapcontext(&t_cur->ctx, &t_sched); }
+// __syncthreads(): a counting barrier over the live threads of the block (fibers are not in lockstep: the shuffle
+// emulation below lets the lanes of a warp rendezvous on their own)
+inline thread_local unsigned t_bar_arrived = 0, t_bar_live = 0;
+inline thread_local unsigned long t_bar_gen = 0;
+inline void sync_threads() {
+  const unsigned long gen = t_bar_gen;
+  if (++t_bar_arrived >= t_bar_live) {
+    t_bar_arrived = 0;
+    ++t_bar_gen;
+    return;
+  }
+  while (t_bar_gen == gen) yield();
+}
+
+// a thread that has exited no longer counts in the block barrier
+inline void fiber_exit() {
+  --t_bar_live;
+  if (t_bar_live > 0 && t_bar_arrived >= t_bar_live) {
+    t_bar_arrived = 0;
+    ++t_bar_gen;
+  }
+}
 
 inline void cp_async16(void* dst, const void* src) { t_cur->open.push_back({dst, src}); }
 inline void cp_async_commit() {
@@ -114,10 +140,14 @@ inline void mbar_init(const void* bar) {
 }
 inline void tma_load_3d(void* dst, const void* base, size_t esize, long n0, long n1, long n2, long c0, long c1, long c2,
                         int b0, int b1, const void* bar) {
+  // from the moment a copy is issued its destination may change at any time: poison it (NaN bit patterns), so that a
+  // thread still reading the stage's previous contents -- a missing "stage is free" rendezvous -- shows in the results
+  memset(dst, 0xff, (size_t)b0 * b1 * esize);
   t_tma.push_back({dst, (const char*)base, esize, n0, n1, n2, c0, c1, c2, b0, b1, bar});
 }
 // cp.async.bulk (1-D): `bytes` contiguous bytes, deferred like the tensor copies (n0 < 0 marks it, c0 = bytes)
 inline void bulk_load(void* dst, const void* src, size_t bytes, const void* bar) {
+  memset(dst, 0xff, bytes);
   t_tma.push_back({dst, (const char*)src, 1, -1, 0, 0, (long)bytes, 0, 0, 0, 0, bar});
 }
 inline void mbar_wait(const void* bar) {
@@ -140,17 +170,20 @@ inline void mbar_wait(const void* bar) {
   }
 }
 
-// __shfl_down_sync(full mask, v, 1) of a one-dimensional block whose rows are warps: every thread of the block deposits
-// its value, all run up to this point, each reads its upper neighbour's (the last lane of a warp gets its own back)
-inline thread_local double t_shfl[1024];
+// __shfl_down_sync(full mask, v, 1) of a one-dimensional block whose rows are warps: the lanes of a warp rendezvous
+// (warps are NOT in lockstep with each other once the block barrier is split), deposit their values in the slot of
+// this shuffle's generation and read their upper neighbour's (the last lane of a warp gets its own back)
+inline thread_local double t_shfl[2][1024];
+inline thread_local unsigned long t_shfl_arrived[32];   // per warp: deposits so far
 template <typename V>
 inline V shfl_down1(V v) {
-  const unsigned t = t_cur->tid.x;
-  t_shfl[t] = (double)v;
-  sync_threads();
-  const V r = ((t & 31u) != 31u && t + 1 < t_blockDim.x) ? (V)t_shfl[t + 1] : v;
-  sync_threads();
-  return r;
+  const unsigned t = t_cur->tid.x, w = t >> 5;
+  const unsigned lanes = t_blockDim.x - (w << 5) < 32u ? t_blockDim.x - (w << 5) : 32u;
+  const unsigned long gen = t_cur->shfl_gen++;
+  t_shfl[gen & 1][t] = (double)v;
+  ++t_shfl_arrived[w];
+  while (t_shfl_arrived[w] < (gen + 1) * lanes) yield();   // (a lane cannot be a whole generation ahead)
+  return ((t & 31u) != 31u && t + 1 < t_blockDim.x) ? (V)t_shfl[gen & 1][t + 1] : v;
 }
 
 template <typename F>
@@ -169,11 +202,16 @@ inline void launch_coop(dim3 grid, dim3 block, F&& body) {
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
         unsigned t = 0;
+        for (unsigned long& a : t_shfl_arrived) a = 0;
+        t_bar_arrived = 0;
+        t_bar_live = n;
+        t_bar_gen = 0;
         for (unsigned tz = 0; tz < block.z; ++tz)
           for (unsigned ty = 0; ty < block.y; ++ty)
             for (unsigned tx = 0; tx < block.x; ++tx, ++t) {
               Fiber& f = fibers[t];
               f.done = false;
+              f.shfl_gen = 0;
               f.open.clear();
               f.groups.clear();
               f.tid = dim3(tx, ty, tz);
