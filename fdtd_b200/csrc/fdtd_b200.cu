@@ -9,6 +9,7 @@
 // product library never contains that path.
 #include <stdarg.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -1014,6 +1015,9 @@ struct FusedShard {
   void* push_y;        // the left neighbour's ghost planes (in ITS output buffer) for E_new[plane 0], or null
   void* push_z;
   int skip_last_h;     // the H update of the last local plane is a separate launch (it waits for the right neighbour)
+  int part;            // 0: every x-chunk; 1: only the first and the last one (the planes the neighbours wait for);
+                       // 2: only the ones in between
+  int* n_chunks;       // out (may be null): how many x-chunks the slab is cut into
 };
 
 template <typename T>
@@ -1126,8 +1130,21 @@ int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void*
     if (S.axis == 2 && !(aligned(K.psiE_in, 16) && aligned(K.psiH, 16))) P.psi_stage = 0;
   }
   using Lay = fdtd::FusedPipeLayout<T, VEC>;
-  const unsigned chunks = (Nx + P.x_chunk - 1) / P.x_chunk;
-  dim3 grid((Nz + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC), (Ny + fdtd::FUSED_R - 1) / fdtd::FUSED_R, chunks);
+  const int chunks = (Nx + P.x_chunk - 1) / P.x_chunk;
+  int launch_chunks = chunks;
+  P.chunk0 = 0;
+  P.chunk_step = 1;
+  if (shard && shard->n_chunks) *shard->n_chunks = chunks;
+  if (shard && shard->part == 1) {
+    P.chunk_step = chunks > 1 ? chunks - 1 : 1;
+    launch_chunks = chunks > 1 ? 2 : 1;
+  } else if (shard && shard->part == 2) {
+    P.chunk0 = 1;
+    launch_chunks = chunks - 2;
+    if (launch_chunks <= 0) return FDTD_OK;
+  }
+  dim3 grid((Nz + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC), (Ny + fdtd::FUSED_R - 1) / fdtd::FUSED_R,
+            (unsigned)launch_chunks);
   dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
   if (grid.y > 65535u || grid.z > 65535u) return fail(FDTD_ERR_UNSUPPORTED, "grid too large for one launch");
   constexpr bool TMA = FDTD_FUSED_TMA != 0;
@@ -1156,6 +1173,21 @@ int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void*
   // detectors on the new fields (a sharded step samples after its last H plane)
   if (!shard) return fused_detectors<T>(d, Eout, Hout, slot, stream);
   return FDTD_OK;
+}
+
+// an unsharded fused step; FDTD_B200_FUSE_SPLIT_TEST=1 (tests): as two launches, the first and last x-chunk and then
+// the ones in between -- the chunk subsets an x-sharded slab runs on two streams
+template <typename T>
+int fused_eh_step_unsharded(const fdtd_desc* d, void* const* Ein, void* const* Eout, void* const* Hin, void* const* Hout,
+                            int64_t q, int64_t slot, void* stream, int parity) {
+  const char* v = getenv("FDTD_B200_FUSE_SPLIT_TEST");
+  if (!v || atoi(v) == 0) return fused_eh_step<T>(d, Ein, Eout, Hin, Hout, q, slot, stream, parity);
+  FusedShard sh{nullptr, nullptr, 0, 1, nullptr};
+  int rc = fused_eh_step<T>(d, Ein, Eout, Hin, Hout, q, slot, stream, parity, &sh);
+  if (rc) return rc;
+  sh.part = 2;
+  if ((rc = fused_eh_step<T>(d, Ein, Eout, Hin, Hout, q, slot, stream, parity, &sh)) != 0) return rc;
+  return fused_detectors<T>(d, Eout, Hout, slot, stream);
 }
 }  // namespace
 }  // extern "C++"
@@ -1286,35 +1318,56 @@ int fused_sharded_step(const fdtd_desc* d, fdtd_halo* h, int parity, int64_t q, 
   void* const* Eout = parity == 0 ? d->E2 : d->E;
   void* const* Hin = parity == 0 ? d->H : d->H2;
   void* const* Hout = parity == 0 ? d->H2 : d->H;
+  cudaStream_t main = (cudaStream_t)stream, side = (cudaStream_t)h->side_stream;
   int rc;
-  if (h->has_left) {
-    FDTD_LAUNCH((fdtd::halo_wait_kernel), dim3(1), dim3(32), stream, (const i64*)h->flags + 1, (i64)h->count[1],
-                (int*)h->error, (i64)h->timeout_ns);
-    if ((rc = check_launch("halo_wait")) != 0) return rc;
-  }
+  // The x-chunks the neighbours wait for -- the first one (E_new[plane 0] goes left) and the last one (its E_new feeds
+  // the H update of the last plane, which goes right) -- run on the (high-priority) side stream together with the
+  // flags and the last H plane; the chunks in between run on the caller's stream meanwhile and hide that serial chain.
+  // FDTD_B200_FUSE_SPLIT=0: everything in one launch on the caller's stream.
+  static const bool want_split = [] { const char* v = getenv("FDTD_B200_FUSE_SPLIT"); return !v || atoi(v) != 0; }();
+  int n_chunks = 0;
   FusedShard sh;
   sh.push_y = h->has_left ? (parity == 0 ? h->left_ghost_y2 : h->left_ghost_y) : nullptr;
   sh.push_z = h->has_left ? (parity == 0 ? h->left_ghost_z2 : h->left_ghost_z) : nullptr;
   sh.skip_last_h = h->has_right;
-  if ((rc = fused_eh_step<T>(d, Ein, Eout, Hin, Hout, q, slot, stream, parity, &sh)) != 0) return rc;
+  sh.n_chunks = &n_chunks;
+  sh.part = want_split ? 1 : 0;
+  cudaStream_t edge = want_split ? side : main;
+  if (want_split) {
+    // both streams have seen everything of the previous step
+    if ((rc = stream_after(side, main, g_join.to_side)) != 0) return rc;
+    if ((rc = stream_after(main, side, g_join.to_main)) != 0) return rc;
+  }
   if (h->has_left) {
-    FDTD_LAUNCH((fdtd::halo_signal_kernel), dim3(1), dim3(32), stream, (i64*)h->left_flag, (i64)(h->count[0] + 1));
+    FDTD_LAUNCH((fdtd::halo_wait_kernel), dim3(1), dim3(32), edge, (const i64*)h->flags + 1, (i64)h->count[1],
+                (int*)h->error, (i64)h->timeout_ns);
+    if ((rc = check_launch("halo_wait")) != 0) return rc;
+  }
+  if ((rc = fused_eh_step<T>(d, Ein, Eout, Hin, Hout, q, slot, edge, parity, &sh)) != 0) return rc;
+  if (want_split) {
+    sh.part = 2;
+    sh.n_chunks = nullptr;
+    if ((rc = fused_eh_step<T>(d, Ein, Eout, Hin, Hout, q, slot, main, parity, &sh)) != 0) return rc;
+  }
+  if (h->has_left) {
+    FDTD_LAUNCH((fdtd::halo_signal_kernel), dim3(1), dim3(32), edge, (i64*)h->left_flag, (i64)(h->count[0] + 1));
     if ((rc = check_launch("halo_signal")) != 0) return rc;
   }
   h->count[0] += 1;
   if (h->has_right) {
-    FDTD_LAUNCH((fdtd::halo_wait_kernel), dim3(1), dim3(32), stream, (const i64*)h->flags, (i64)h->count[0],
+    FDTD_LAUNCH((fdtd::halo_wait_kernel), dim3(1), dim3(32), edge, (const i64*)h->flags, (i64)h->count[0],
                 (int*)h->error, (i64)h->timeout_ns);
     if ((rc = check_launch("halo_wait")) != 0) return rc;
     Buffers buf{Hin, Hout, Eout};
-    rc = launch_halfstep_run<T, false, T>(d, d->Nx - 1, d->Nx, q, slot, stream, -1,
+    rc = launch_halfstep_run<T, false, T>(d, d->Nx - 1, d->Nx, q, slot, edge, -1,
                                           parity == 0 ? h->right_ghost_y2 : h->right_ghost_y,
                                           parity == 0 ? h->right_ghost_z2 : h->right_ghost_z, true, &buf);
     if (rc) return rc;
-    FDTD_LAUNCH((fdtd::halo_signal_kernel), dim3(1), dim3(32), stream, (i64*)h->right_flag, (i64)(h->count[1] + 1));
+    FDTD_LAUNCH((fdtd::halo_signal_kernel), dim3(1), dim3(32), edge, (i64*)h->right_flag, (i64)(h->count[1] + 1));
     if ((rc = check_launch("halo_signal")) != 0) return rc;
   }
   h->count[1] += 1;
+  if (want_split && (rc = stream_after(main, side, g_join.to_main)) != 0) return rc;
   return fused_detectors<T>(d, Eout, Hout, slot, stream);
 }
 }  // namespace
@@ -1492,12 +1545,12 @@ int fdtd_run(const fdtd_desc* d, int64_t q0, int64_t nsteps, int64_t slot0, void
     if (nsteps >= 2 && fuse_eh_eligible(d)) {
       for (; s + 2 <= nsteps; s += 2) {
         rc = d->dtype == FDTD_F32
-                 ? fused_eh_step<float>(d, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream, 0)
-                 : fused_eh_step<double>(d, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream, 0);
+                 ? fused_eh_step_unsharded<float>(d, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream, 0)
+                 : fused_eh_step_unsharded<double>(d, d->E, d->E2, d->H, d->H2, q0 + s, slot0 + s, stream, 0);
         if (rc) return rc;
         rc = d->dtype == FDTD_F32
-                 ? fused_eh_step<float>(d, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream, 1)
-                 : fused_eh_step<double>(d, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream, 1);
+                 ? fused_eh_step_unsharded<float>(d, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream, 1)
+                 : fused_eh_step_unsharded<double>(d, d->E2, d->E, d->H2, d->H, q0 + s + 1, slot0 + s + 1, stream, 1);
         if (rc) return rc;
       }
     }

@@ -28,6 +28,7 @@ struct FusedParams {
   i64 plane;
   int x0, x1, y0, y1, z0, z1;  // interior box (cells); z0, z1 multiples of the vector width
   int x_chunk;
+  int chunk0, chunk_step;      // block z handles x-chunk chunk0 + z * chunk_step (a launch may cover a subset of the chunks)
   const T* Ein[3];
   T* Eout[3];
   const T* Hin[3];
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   const bool inside = (j < P.y1) && (k0 < P.z1);
   const i64 plane = P.plane;
   const i64 p = (i64)j * Nz + k0;
-  const int xa = P.x0 + blockIdx.z * P.x_chunk;
+  const int xa = P.x0 + (P.chunk0 + (int)blockIdx.z * P.chunk_step) * P.x_chunk;
   const int xb = (xa + P.x_chunk < P.x1) ? xa + P.x_chunk : P.x1;
 
   bool src_yz = false;

@@ -30,7 +30,7 @@ GRAPH_MAX_CELLS = 1 << 25      # grids up to this many cells replay CUDA graphs 
 FUSE_EH_MIN_PLANE_BYTES = 1100 << 10  # y-z plane of one component
 FUSE_EH_MIN_PLANES = 64               # x-planes (unsharded)
 FUSE_EH_MIN_Z_FILL = 0.85             # Nz / (z tiles of 31 vectors x their length)
-FUSE_EH_MIN_SLAB = 112                # x-planes per rank (x-sharded: a fused step ends in a short serial tail)
+FUSE_EH_MIN_SLAB = 96                 # x-planes per rank (x-sharded; 128 planes per rank: 1.41 against 1.64 ms per step, profiles/r2_n2c/)
 
 
 def _ptr(t):

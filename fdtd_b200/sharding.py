@@ -193,7 +193,9 @@ class P2PHalo:
         self.fused_buffers = E2 is not None and H2 is not None     # second field buffers of temporally fused steps
         self.cuda = True
         dev = E.device
-        self.stream = torch.cuda.Stream(device=dev)
+        # high priority: the boundary-plane launches and flags are dispatched ahead of the bulk's pending blocks, so the
+        # neighbour gets its ghost plane while the bulk is still running
+        self.stream = torch.cuda.Stream(device=dev, priority=-1)
         self.flags = torch.zeros(2, dtype=torch.int64, device=dev)     # [0]: E pushes received, [1]: H pushes
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         torch.cuda.synchronize(dev)

@@ -57,6 +57,8 @@ def run_one(backend, dtype, scene, steps, out, rank, world):
         g = build(fd)
         if os.environ.get("FDTD_TEST_FUSE_EH"):
             g._fuse_eh = int(os.environ["FDTD_TEST_FUSE_EH"])
+        if os.environ.get("FDTD_TEST_X_CHUNK"):      # short x-chunks: a slab of a small scene is cut into several
+            g._x_chunk = int(os.environ["FDTD_TEST_X_CHUNK"])
         if os.environ.get("FDTD_TEST_TRACK"):
             scenes.track_all(g, steps)
         g.run(0, progress_bar=False)           # bake: sharding restrictions surface here, on every rank alike

@@ -324,7 +324,7 @@ def test_running_dft_of_a_current_detector():
                                           ("float32", (13, 9, 16), 2, "none"), ("float32", (12, 40, 144), 2, "both"),
                                           ("float64", (12, 11, 136), 2, "hi"), ("float32", (16, 19, 24), 3, "zfirst"),
                                           ("float32", (10, 9, 132), 2, "halo"), ("float64", (10, 9, 48), 2, "thick")])
-def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t, zp):
+def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t, zp, monkeypatch):
     """run() with the single-pass E+H kernel (one launch per step over the whole grid: ping-pong field and psi_E
     buffers, inputs staged by asynchronous copies, E_new exchanged through shared memory -- its block runs as
     cooperative fibers here and every copy is deferred to the wait that covers it) reproduces the two-half-step path
@@ -363,7 +363,10 @@ def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t, zp):
         return g
 
     outs = []
-    for fuse, chunk in ((0, 0), (1, 0), (1, 4), (1, 1)):
+    # (split: the step as two launches -- first and last x-chunk, then the ones in between -- as an x-sharded slab
+    # runs them on two streams)
+    for fuse, chunk, split in ((0, 0, "0"), (1, 0, "0"), (1, 4, "0"), (1, 1, "0"), (1, 4, "1"), (1, 3, "1")):
+        monkeypatch.setenv("FDTD_B200_FUSE_SPLIT_TEST", split)
         g = build()
         g._fuse_eh = fuse
         g._x_chunk = chunk
@@ -372,6 +375,7 @@ def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t, zp):
         g.run(4, progress_bar=False)
         assert bool(g._engine.lib.fdtd_fuse_eh_active(g._engine.desc)) == bool(fuse)
         outs.append(scenes.dump(g))
+    monkeypatch.delenv("FDTD_B200_FUSE_SPLIT_TEST")
     assert float(np.abs(outs[0]["E"]).max()) > 0
     for other in outs[1:]:
         compare(other, outs[0], 0.0, bitwise=True)

@@ -32,9 +32,9 @@ def test_sharded_equals_single(tmp_path, scene, dtype, halo):
         assert np.array_equal(got[k], want[k]), f"{k}: rel-L2 {scenes.rel_l2(got[k], want[k]):.3e}"
 
 
-@pytest.mark.parametrize("scene,dtype,steps", [("fusedslab", "float32", 31), ("fusedslab", "float64", 26),
-                                               ("fusedslab", "float32", 24)])
-def test_temporally_fused_steps_on_slabs(tmp_path, scene, dtype, steps):
+@pytest.mark.parametrize("scene,dtype,steps,chunk", [("fusedslab", "float32", 31, 0), ("fusedslab", "float64", 26, 3),
+                                                     ("fusedslab", "float32", 24, 2), ("fusedslab", "float32", 27, 4)])
+def test_temporally_fused_steps_on_slabs(tmp_path, scene, dtype, steps, chunk):
     """x-sharded grids with grid._fuse_eh = 1: every rank runs pairs of single-pass E+H steps (the fused kernel stores
     E_new[plane 0] into the left neighbour's second buffer, the last H plane follows once the right neighbour's E_new
     has arrived), an odd remainder and step()-driven steps run as two half-steps.  Bit-identical to the single-GPU
@@ -43,7 +43,9 @@ def test_temporally_fused_steps_on_slabs(tmp_path, scene, dtype, steps):
         pytest.skip("needs 2 GPUs")
     world = min(4, torch.cuda.device_count())
     out = str(tmp_path / "sharded.npz")
-    launch(world, "nccl", dtype, scene, steps, out, FDTD_TEST_FUSE_EH="1")
+    # chunk > 0: the slab is cut into several x-chunks -- the first and the last one run on the side stream with the
+    # flags and the last H plane, the ones in between on the main stream
+    launch(world, "nccl", dtype, scene, steps, out, FDTD_TEST_FUSE_EH="1", FDTD_TEST_X_CHUNK=str(chunk))
     got = dict(np.load(out))
     import fdtd_b200 as fd
     fd.set_backend("cuda." + dtype)
