@@ -55,16 +55,35 @@ def six_pml(fd, g, t=PML_CELLS):
     g[:, :, -t:] = fd.PML()
 
 
-def pml_plane_cost(nx, pml=PML_CELLS, lo=True, hi=True):
-    """planes inside an x-PML move 13 instead of 9 words per cell and half-step: give their ranks fewer planes"""
-    return [13.0 / 9.0 if ((lo and i < pml) or (hi and i >= nx - pml)) else 1.0 for i in range(nx)]
+# what a plane inside an x-PML costs relative to an ordinary one, measured on the B200 (profiles/r2_s16, r2_s17): the two
+# half-steps 1.56 (13 instead of 9 words per cell and half-step), the single-pass E+H kernel more (20 instead of 12 words
+# per cell and step, and psi arrives by plain loads instead of staged copies)
+XPML_PLANE_COST, XPML_PLANE_COST_FUSED = 1.56, 1.93
+
+
+def pml_plane_cost(nx, pml=PML_CELLS, lo=True, hi=True, weight=XPML_PLANE_COST):
+    """planes inside an x-PML cost more than ordinary ones: give their ranks fewer planes"""
+    return [weight if ((lo and i < pml) or (hi and i >= nx - pml)) else 1.0 for i in range(nx)]
+
+
+def fused_steps_expected(fd, shape, itemsize=4):
+    """will the ranks of an x-sharded homogeneous grid run the single-pass E+H kernel? (fdtd_b200/engine.py's test)"""
+    import torch.distributed as dist
+    from fdtd_b200 import engine
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    nx, ny, nz = shape
+    tile_z = 31 * (16 // itemsize)
+    return (os.environ.get("FDTD_B200_FUSE_EH", "2") != "0" and ny * nz * itemsize >= engine.FUSE_EH_MIN_PLANE_BYTES
+            and nz >= engine.FUSE_EH_MIN_Z_FILL * (-(-nz // tile_z) * tile_z)
+            and nx // world >= (engine.FUSE_EH_MIN_SLAB if world > 1 else engine.FUSE_EH_MIN_PLANES))
 
 
 def build_c4(fd, n, pml=PML_CELLS, balance=False, **kw):
     """configs[3]: six PMLs, centre PointSource, LineDetector along z through the centre."""
     nx, ny, nz = (n, n, n) if isinstance(n, int) else n
     if balance:
-        kw["x_plane_cost"] = pml_plane_cost(nx, pml)
+        fused = fused_steps_expected(fd, (nx, ny, nz))
+        kw["x_plane_cost"] = pml_plane_cost(nx, pml, weight=XPML_PLANE_COST_FUSED if fused else XPML_PLANE_COST)
     g = fd.Grid(shape=(nx, ny, nz), grid_spacing=GRID_SPACING, **kw)
     six_pml(fd, g, pml)
     g[nx // 2, ny // 2, nz // 2] = fd.PointSource(period=20, name="src")

@@ -190,6 +190,9 @@ template <typename T>
 struct FusedTmaMaps {
   TmaMap<T> h[3], e[3];   // the three components of the input H and E (ghost x-planes included: plane i is x = i + 1)
 };
+#ifndef FDTD_FUSED_EARLY_XPSI
+#define FDTD_FUSED_EARLY_XPSI 1          // psi of x-slab planes is loaded at the top of the iteration (see the kernel)
+#endif
 #ifndef FDTD_FUSED_PIPE_PSI_PREFETCH
 #define FDTD_FUSED_PIPE_PSI_PREFETCH 0   // CPML psi of the thread's cells is prefetched (L1) this many planes ahead: the psi
                                          // loads are the only global loads left on the per-plane critical path, and one
@@ -304,11 +307,14 @@ template <typename T, int VEC, bool IS_E>
 FDTD_DEV void fused_slab_update(const typename FusedParams<T>::Slab& S, const T* psi_in, T* psi_out, bool store,
                                 const T* sp, int sp_pitch, i64 idx, int l0, const FusedDiffs<T, VEC>& D,
                                 Pack<T, VEC>& f0, Pack<T, VEC>& f1, Pack<T, VEC>& f2, const T (&coef)[3],
-                                const T* tab) {
+                                const T* tab, bool early, const Pack<T, VEC>& ea, const Pack<T, VEC>& eb) {
   const T* bt = tab + (IS_E ? 0 : 2) * FDTD_FUSED_TAB_T;   // (shared memory: b_E, c_E, b_H, c_H of this slab)
   const T* ct = bt + FDTD_FUSED_TAB_T;
   Pack<T, VEC> a, b;
-  if (sp != nullptr) {
+  if (early) {             // loaded at the top of the iteration (x slabs)
+    a = ea;
+    b = eb;
+  } else if (sp != nullptr) {
     a = ldv<T, VEC>(sp);
     b = ldv<T, VEC>(sp + sp_pitch);
   } else {
@@ -495,7 +501,32 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   }
 
   const int xl = (P.skip_last_h && xb == P.x1) ? xb - 1 : xb;   // (see FusedParams::skip_last_h)
+  int sx_prev = -1;        // the x slab whose psi_H of plane i-1 is loaded early (see below)
   for (int i = xa; i <= xl; ++i) {
+    unsigned hit_now = sl_hit;   // + the x slabs plane i lies in (the same for the whole block)
+    int sx = -1;                 // the first of them
+    for (unsigned m = xs_bits; m != 0; m &= m - 1) {
+      const int s = FDTD_FFS(m) - 1;
+      const bool in = i >= P.sl[s].xs && i < P.sl[s].xe;
+      hit_now |= in ? (1u << s) : 0u;
+      if (in && sx < 0) sx = s;
+    }
+    // Inside an x slab EVERY thread needs psi, and its loads were the only global loads on the per-plane critical path
+    // (an x-PML plane cost 2.3 ordinary planes, profiles/r2_s16/): they are issued here, ahead of the wait for the
+    // staged plane, the barrier and the curls -- psi_E of plane i and psi_H of plane i-1.
+    Pack<T, VEC> xea = {}, xeb = {}, xha = {}, xhb = {};
+    const bool early_e = FDTD_FUSED_EARLY_XPSI && sx >= 0 && active && inside && i < P.x1;
+    const bool early_h = FDTD_FUSED_EARLY_XPSI && sx_prev >= 0 && core && i > xa;
+    if (early_e) {
+      const i64 idx = (i64)(i - P.sl[sx].xs) * plane + p;
+      xea = ldv<T, VEC>(P.sl[sx].psiE_in + idx);
+      xeb = ldv<T, VEC>(P.sl[sx].psiE_in + P.sl[sx].count + idx);
+    }
+    if (early_h) {
+      const i64 idx = (i64)(i - 1 - P.sl[sx_prev].xs) * plane + p;
+      xha = ldv<T, VEC>(P.sl[sx_prev].psiH + idx);
+      xhb = ldv<T, VEC>(P.sl[sx_prev].psiH + P.sl[sx_prev].count + idx);
+    }
     if (TMA) {
       // the k-th use of a stage's barrier completes phase k: plane i is use (i - xa) / 3 of stage i % 3
       if (i < P.x1) FDTD_MBAR_WAIT(bars + (i % 3), ((i - xa) / 3) & 1);
@@ -564,11 +595,6 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
 #endif
     const T* sH = stages + (i % 3) * Lay::STAGE_WORDS;
     const T* sE = sH + Lay::H_WORDS;
-    unsigned hit_now = sl_hit;   // + the x slabs plane i lies in (the same for the whole block)
-    for (unsigned m = xs_bits; m != 0; m &= m - 1) {
-      const int s = FDTD_FFS(m) - 1;
-      hit_now |= (i >= P.sl[s].xs && i < P.sl[s].xe) ? (1u << s) : 0u;
-    }
     const i64 off = (i64)i * plane + p;
     Pack<T, VEC> e0, e1, e2, h0, h1, h2;
     if (active) {
@@ -626,7 +652,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
                                                      : ((i64)i * P.Ny + j) * S.tp + (k0 - S.lo_al));
           const int l0 = S.axis == 0 ? i - S.lo : (S.axis == 1 ? j - S.lo : k0 - S.lo);
           fused_slab_update<T, VEC, true>(S, S.psiE_in, S.psiE_out, store, sp, Lay::PSI_ARR, idx, l0, D, e0, e1, e2, P.ce,
-                                          tabs + s * 4 * Lay::TAB_T);
+                                          tabs + s * 4 * Lay::TAB_T, early_e && s == sx, xea, xeb);
         }
         if (src_yz) fused_sources_vec<T, VEC>(P, i, j, k0, off, e0, e1, e2);
         if (core && i < xb) {
@@ -702,7 +728,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
                                                    : ((i64)ih * P.Ny + j) * S.tp + (k0 - S.lo_al));
         const int l0 = S.axis == 0 ? ih - S.lo : (S.axis == 1 ? j - S.lo : k0 - S.lo);
         fused_slab_update<T, VEC, false>(S, S.psiH, S.psiH, true, sp, Lay::PSI_ARR, idx, l0, D, hx, hy, hz, P.ch,
-                                           tabs + s * 4 * Lay::TAB_T);
+                                           tabs + s * 4 * Lay::TAB_T, early_h && s == sx_prev, xha, xhb);
       }
       const i64 om = off - plane;
       stv<T, VEC>(P.Hout[0] + om, hx);
@@ -726,6 +752,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
       }
     }
     hit_prev = hit_now;
+    sx_prev = sx;
   }
 }
 

@@ -48,6 +48,8 @@ VARIANTS = {
     "pipe_v2_nopsi": ["-DFDTD_FUSED_PSI_STAGE=0"],
     "pipe_v2_old": ["-DFDTD_FUSED_SHFL=0", "-DFDTD_FUSED_PSI_STAGE=0"],
     "pipe_v2_r8": ["-DFDTD_FUSED_ROWS=8"],
+    # session 17: psi of x-slab planes loaded at the top of the iteration
+    "pipe_v5_noearly": ["-DFDTD_FUSED_EARLY_XPSI=0"],
     "pipe_tma_r15l31_mb1": ["-DFDTD_FUSED_ROWS=15", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=1"],
     "pipe_tma_r3l31_mb4": ["-DFDTD_FUSED_ROWS=3", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4"],
     "pipe_psi1": ["-DFDTD_FUSED_PIPE_PSI_PREFETCH=1"],
