@@ -926,10 +926,6 @@ bool fuse_eh_eligible(const fdtd_desc* d, bool sharded = false) {
 #endif
 }
 
-#ifndef FDTD_FUSED_TMA
-#define FDTD_FUSED_TMA 1     // the fused kernel's inputs are staged by TMA (0: per-thread cp.async copies)
-#endif
-
 int sm_count() {
 #ifdef FDTD_EMU
   return 148;
@@ -1147,27 +1143,24 @@ int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void*
             (unsigned)launch_chunks);
   dim3 block((fdtd::FUSED_R + 1) * (fdtd::FUSED_L + 1));
   if (grid.y > 65535u || grid.z > 65535u) return fail(FDTD_ERR_UNSUPPORTED, "grid too large for one launch");
-  constexpr bool TMA = FDTD_FUSED_TMA != 0;
   fdtd::FusedTmaMaps<T> M;
   memset(&M, 0, sizeof(M));
-  if (TMA) {
-    // (a TMA row is a multiple of 16 bytes: Nz % VEC == 0, checked by the eligibility test)
-    if ((rc = fused_tma_maps<T>(d, Hin, Lay::HV * VEC, Lay::R + 2, M.h)) != 0) return rc;
-    if ((rc = fused_tma_maps<T>(d, Ein, Lay::EV * VEC, Lay::R + 1, M.e)) != 0) return rc;
-  }
+  // (a TMA row is a multiple of 16 bytes: Nz % VEC == 0, checked by the eligibility test)
+  if ((rc = fused_tma_maps<T>(d, Hin, Lay::HV * VEC, Lay::R + 2, M.h)) != 0) return rc;
+  if ((rc = fused_tma_maps<T>(d, Ein, Lay::EV * VEC, Lay::R + 1, M.e)) != 0) return rc;
 #ifndef FDTD_EMU
   static bool configured = false;      // (per instantiation: one kernel function each)
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC, TMA>,
+    cudaError_t e = cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::BYTES);
     if (e != cudaSuccess) return fail(FDTD_ERR_CUDA, "cudaFuncSetAttribute(smem %zu): %s", Lay::BYTES, cudaGetErrorString(e));
     // two blocks per SM only fit with the shared-memory carve-out at its maximum
-    cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(fdtd::fused_eh_pipe_kernel<T, VEC>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          (int)cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
 #endif
-  FDTD_LAUNCH_SMEM((fdtd::fused_eh_pipe_kernel<T, VEC, TMA>), grid, block, Lay::BYTES, stream, P, M);
+  FDTD_LAUNCH_SMEM((fdtd::fused_eh_pipe_kernel<T, VEC>), grid, block, Lay::BYTES, stream, P, M);
   rc = check_launch("fused_eh");
   if (rc) return rc;
   // detectors on the new fields (a sharded step samples after its last H plane)

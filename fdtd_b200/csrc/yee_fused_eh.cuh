@@ -14,10 +14,13 @@
 // Arithmetic per cell is the same as in halfstep_kernel, operation by operation: results are bit-identical
 // (tests/test_gpu_parity.py::test_temporally_fused_steps_equal_two_half_steps).
 //
-// History (profiles/README.md): round 1 had three variants -- (1) shared-memory exchange with direct global loads on
-// the CPML-free interior plus twelve shell launches of the ordinary kernel, (2) a register-tiled kernel without any
-// inter-thread communication, (3) this one.  On the B200 at 1024^3 f32 they ran 12.74 / 15.0 / 11.69 ms per step
-// against 12.62 for the two half-steps (round 2, profiles/r2_fused_variants.txt); (1) and (2) were deleted.
+// History (profiles/README.md): round 1 had three variants -- (1) shared-memory exchange with direct
+// global loads on the CPML-free interior plus twelve shell launches of the ordinary kernel, (2) a register-tiled kernel
+// without any inter-thread communication, (3) this one with per-thread cp.async staging.  On the B200 at 1024^3 f32
+// they ran 12.74 / 15.0 / 11.69 ms per step against 12.62 for the two half-steps; (1) and (2) were deleted.  Since then:
+// TMA staging (10.77), psi of the block's z slab staged by bulk copies + z+1 neighbour by shuffle (10.20), CPML tables in
+// shared memory (9.98); the cp.async staging, a split mbarrier barrier and several prefetch schemes were measured and
+// removed.  The kernel is DRAM-bound at 5.7 TB/s (profiles/r2_s15/).
 #pragma once
 
 namespace fdtd {
@@ -100,37 +103,19 @@ FDTD_DEV void fused_sources_vec(const FusedParams<T>& P, int i, int j, int k0, i
 constexpr int FUSED_R = FDTD_FUSED_ROWS;   // core rows per block
 constexpr int FUSED_L = FDTD_FUSED_LANES;  // core vector lanes per block
 
-// ---- the inputs of each plane are staged in shared memory by cp.async, two planes ahead ------------------------
+// ---- the inputs of each plane are staged in shared memory two planes ahead -----------------------------------------
 // No thread ever waits for a global load it has just issued: every plane's H_old tile (own cells + the y-1 row and
-// the z-1 vector) and E_old tile arrive in one of three shared-memory stages through asynchronous 16-byte copies
-// (LDGSTS, L2 only) issued two iterations before they are consumed, so the one barrier per plane does not expose the
-// memory latency of the slowest warp.  Each global word is requested once per block (the y-1 / z-1 neighbours come
-// out of the staged tile).  Copy addresses derive from the thread's own cell; the slab helper selects its operands at
-// compile time and the source helper is inlined, so the field vectors stay in registers (128 registers, no spill,
-// 104 KB of shared memory per block: two blocks per SM).
-// Measured (ncu, profiles/r2_ncu_summary_before.txt): 11.66 ms per launch at 1024^3 f32, DRAM 57.3 GB (algorithmic
-// 53.6 GB: the halo threads' re-reads) at 4.9 TB/s -- not DRAM-bound: 44 % of the issue slots with 4 warps per
-// scheduler; 14 % of the stall samples sit on the barrier, 13 % on the first use of psi (the only global loads left on
-// the critical path; one waiting thread holds its block at the barrier, and a quarter of all blocks touch a z slab).
-// Tried without gain (profiles/r2_fused_variants.txt): L2 prefetch of the inputs 3-6 planes ahead (+0.4 ms), L1 / L2
-// prefetch of psi (+1.4 ms: the index arithmetic runs in every thread), longer x-chunks (+0.2 / +0.7 ms).
-// Iteration i:  wait for this thread's copies of plane i -> barrier (everyone's copies landed, everyone's
-// E_new[i-1] is published, stage (i-1)%3 is free) -> issue the copies of plane i+2 into stage (i-1)%3 ->
-// E_new[i] from stage i%3 -> H_new[i-1] from the published E_new[i-1] -> publish E_new[i].
+// the z-1 vector) and E_old tile arrive in one of three shared-memory stages through bulk copies issued two
+// iterations before they are consumed.  Each global word is requested once per block (the y-1 / z-1 neighbours come
+// out of the staged tile).
+// Iteration i:  wait for the stage of plane i -> barrier (everyone's E_new[i-1] is published, stage (i-1)%3 is free)
+// -> issue the copies of plane i+2 into stage (i-1)%3 -> E_new[i] from stage i%3 -> H_new[i-1] from the published
+// E_new[i-1] -> publish E_new[i].
 #ifdef FDTD_EMU
 #define FDTD_FFS(x) __builtin_ffs((int)(x))
-#define FDTD_CP_ASYNC16(dst, src) emu::cp_async16((dst), (src))
-#define FDTD_CP_ASYNC_COMMIT() emu::cp_async_commit()
-#define FDTD_CP_ASYNC_WAIT_1() emu::cp_async_wait(1)
 #define FDTD_DYN_SMEM(name) alignas(128) static unsigned char name[256 << 10]
 #else
 #define FDTD_FFS(x) __ffs((int)(x))
-#define FDTD_CP_ASYNC16(dst, src)                                                                      \
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), \
-               "l"(src)                                                                                \
-               : "memory")
-#define FDTD_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
-#define FDTD_CP_ASYNC_WAIT_1() asm volatile("cp.async.wait_group 1;" ::: "memory")
 #define FDTD_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #endif
 #ifndef FDTD_FUSED_PIPE_MIN_BLOCKS
@@ -192,21 +177,6 @@ struct FusedTmaMaps {
 };
 #ifndef FDTD_FUSED_EARLY_XPSI
 #define FDTD_FUSED_EARLY_XPSI 1          // psi of x-slab planes is loaded at the top of the iteration (see the kernel)
-#endif
-#ifndef FDTD_FUSED_PIPE_PSI_PREFETCH
-#define FDTD_FUSED_PIPE_PSI_PREFETCH 0   // CPML psi of the thread's cells is prefetched (L1) this many planes ahead: the psi
-                                         // loads are the only global loads left on the per-plane critical path, and one
-                                         // thread waiting for them holds its whole block at the barrier -- a quarter of all
-                                         // blocks touch a z slab.  Measured: +1.4 ms per step (the index arithmetic runs in
-                                         // every thread of every block) -- off
-#endif
-#ifndef FDTD_FUSED_PIPE_PSI_LEVEL
-#define FDTD_FUSED_PIPE_PSI_LEVEL 1      // 1: prefetch.global.L1, 2: prefetch.global.L2
-#endif
-#ifndef FDTD_FUSED_PIPE_PREFETCH
-#define FDTD_FUSED_PIPE_PREFETCH 0   // L2 prefetch of the six input streams this many planes ahead of the march (0 = off):
-                                     // the two planes the cp.async stages hold in flight are ~100 KB per SM, about half
-                                     // of what saturates HBM; prefetches cost neither registers nor shared memory
 #endif
 
 #ifndef FDTD_FUSED_SHFL
@@ -330,55 +300,6 @@ FDTD_DEV void fused_slab_update(const typename FusedParams<T>::Slab& S, const T*
   }
 }
 
-// The asynchronous 16-byte copies of one plane of the block's tile into a stage.  Every thread whose cells lie in
-// the box copies the six input vectors of its own cells (they land where its neighbours will look for their y-1 /
-// z-1 values too); the threads of the first row add the y-1 row (Hx, Hz: the only components differenced along y)
-// and those of the first lane the z-1 vector (Hx, Hy).  Addresses derive from the thread's own cell offset: no
-// per-thread copy table, no registers held across the march.
-template <typename T, int VEC>
-FDTD_DEV void fused_stage_issue(const FusedParams<T>& P, T* stage, i64 off, int r, int l, bool inside, bool row_m1,
-                                bool vec_m1) {
-  using Lay = FusedPipeLayout<T, VEC>;
-  constexpr int HV = Lay::HV, EV = Lay::EV, HC = Lay::HC, EC = Lay::EC;
-  if (!inside) return;
-  T* h = stage + ((r + 1) * HV + (l + 1)) * VEC;
-  T* e = stage + Lay::H_WORDS + (r * EV + l) * VEC;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    FDTD_CP_ASYNC16(h + c * HC, P.Hin[c] + off);
-    FDTD_CP_ASYNC16(e + c * EC, P.Ein[c] + off);
-  }
-  if (row_m1) {
-    FDTD_CP_ASYNC16(h - HV * VEC, P.Hin[0] + off - P.Nz);
-    FDTD_CP_ASYNC16(h + 2 * HC - HV * VEC, P.Hin[2] + off - P.Nz);
-  }
-  if (vec_m1) {
-    FDTD_CP_ASYNC16(h - VEC, P.Hin[0] + off - VEC);
-    FDTD_CP_ASYNC16(h + HC - VEC, P.Hin[1] + off - VEC);
-  }
-}
-
-// psi index of the VEC cells of a thread at plane i in slab S (the layouts of include/fdtd_b200.h, fdtd_slab)
-template <typename T, int VEC>
-FDTD_DEV i64 fused_psi_index(const typename FusedParams<T>::Slab& S, int i, int j, int k0, i64 plane, i64 p, int Ny,
-                             int Nz) {
-  if (S.axis == 0) return (i64)(i - S.xs) * plane + p;
-  if (S.axis == 1) return ((i64)i * S.t + (j - S.lo)) * Nz + k0;
-  return ((i64)i * Ny + j) * S.tp + (k0 - S.lo_al);
-}
-
-FDTD_DEV void fused_prefetch(const void* a) {
-#if !defined(FDTD_EMU)
-#if FDTD_FUSED_PIPE_PSI_LEVEL == 1
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-#else
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-#endif
-#else
-  (void)a;
-#endif
-}
-
 // one plane of the block's tile into a stage, by TMA (thread 0 only); zs >= 0: also the psi rows of z slab zs --
 // psi_E of plane ip (rows j0 .. j0+R) and psi_H of plane ip-1 (rows j0 .. j0+R-1; with_h), contiguous in memory
 template <typename T, int VEC>
@@ -413,7 +334,7 @@ FDTD_DEV void fused_stage_tma(const FusedParams<T>& P, const FusedTmaMaps<T>& M,
   }
 }
 
-template <typename T, int VEC, bool TMA>
+template <typename T, int VEC>
 __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE_MIN_BLOCKS)
     fused_eh_pipe_kernel(const __grid_constant__ FusedParams<T> P, const __grid_constant__ FusedTmaMaps<T> M) {
   using Lay = FusedPipeLayout<T, VEC>;
@@ -455,7 +376,7 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   unsigned hit_prev = 0;   // slabs (x slabs included) the cells of plane i-1 lie in: what the H update of i-1 needs
   // the z slab whose psi this block stages in shared memory (block-uniform): the first one a lane of the tile lies in
   int zs = -1;
-  if (TMA && FDTD_FUSED_PSI_STAGE && P.psi_stage) {
+  if (FDTD_FUSED_PSI_STAGE && P.psi_stage) {
     for (int s = P.n_sl - 1; s >= 0; --s)
       if (P.sl[s].axis == 2 && P.sl[s].tp <= Lay::PSI_TP && kz0 + (L + 1) * VEC > P.sl[s].lo &&
           kz0 < P.sl[s].lo + P.sl[s].t)
@@ -463,15 +384,12 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   }
   const int zs_off = zs >= 0 ? r * P.sl[zs].tp + (k0 - P.sl[zs].lo_al) : 0;   // this thread's cells in a staged psi array
 
-  const bool row_m1 = (r == 0) && (j >= 1), vec_m1 = (l == 0) && (k0 >= VEC);   // who copies the y-1 row / z-1 vector
-  if (TMA) {
-    if (tid == 0) {
-      for (int s = 0; s < Lay::STAGES; ++s) FDTD_MBAR_INIT(bars + s);
-    }
-#ifndef FDTD_EMU
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#endif
+  if (tid == 0) {
+    for (int s = 0; s < Lay::STAGES; ++s) FDTD_MBAR_INIT(bars + s);
   }
+#ifndef FDTD_EMU
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
   // the coefficient tables of every slab (thickness <= TAB_T: the host's eligibility test)
   for (int n = tid; n < P.n_sl * 4 * Lay::TAB_T; n += (R + 1) * (L + 1)) {
     const int s = n / (4 * Lay::TAB_T), w = (n / Lay::TAB_T) & 3, ll = n % Lay::TAB_T;
@@ -479,17 +397,11 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     tabs[n] = ll < P.sl[s].t ? src[ll] : T(0);
   }
   __syncthreads();
-  // two planes in flight before the first one is consumed (one commit group per plane, empty ones included)
+  // two planes in flight before the first one is consumed
   for (int s = 0; s < 2; ++s) {
     const int ip = xa + s;
-    if (TMA) {
-      if (tid == 0 && ip <= xb && ip < P.x1)
-        fused_stage_tma<T, VEC>(P, M, stages + (ip % 3) * Lay::STAGE_WORDS, bars + (ip % 3), kz0, j0, ip, zs, ip > xa);
-    } else {
-      if (ip <= xb && ip < P.x1)
-        fused_stage_issue<T, VEC>(P, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane + p, r, l, inside, row_m1, vec_m1);
-      FDTD_CP_ASYNC_COMMIT();
-    }
+    if (tid == 0 && ip <= xb && ip < P.x1)
+      fused_stage_tma<T, VEC>(P, M, stages + (ip % 3) * Lay::STAGE_WORDS, bars + (ip % 3), kz0, j0, ip, zs, ip > xa);
   }
 
   Pack<T, VEC> hp0, hp1, hp2, ep0 = {}, ep1 = {}, ep2;
@@ -527,12 +439,8 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
       xha = ldv<T, VEC>(P.sl[sx_prev].psiH + idx);
       xhb = ldv<T, VEC>(P.sl[sx_prev].psiH + P.sl[sx_prev].count + idx);
     }
-    if (TMA) {
-      // the k-th use of a stage's barrier completes phase k: plane i is use (i - xa) / 3 of stage i % 3
-      if (i < P.x1) FDTD_MBAR_WAIT(bars + (i % 3), ((i - xa) / 3) & 1);
-    } else {
-      FDTD_CP_ASYNC_WAIT_1();
-    }
+    // the k-th use of a stage's barrier completes phase k: plane i is use (i - xa) / 3 of stage i % 3
+    if (i < P.x1) FDTD_MBAR_WAIT(bars + (i % 3), ((i - xa) / 3) & 1);
     // (tried: the barrier split into an mbarrier arrival after the publish below and a wait between the next E and H
     // updates, so that warps may drift by one E update: 10.15 instead of 10.00 ms per step, profiles/r2_s14/; an L2
     // prefetch of the tiles 3 / 4 / 6 planes ahead by cp.async.bulk.prefetch.tensor: 10.80 / 11.19 / 12.27 ms against
@@ -540,59 +448,9 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     __syncthreads();
     {
       const int ip = i + 2;
-      if (TMA) {
-        if (tid == 0 && ip <= xb && ip < P.x1)
-          fused_stage_tma<T, VEC>(P, M, stages + (ip % 3) * Lay::STAGE_WORDS, bars + (ip % 3), kz0, j0, ip, zs, ip > xa);
-      } else {
-        if (ip <= xb && ip < P.x1)
-          fused_stage_issue<T, VEC>(P, stages + (ip % 3) * Lay::STAGE_WORDS, (i64)ip * plane + p, r, l, inside, row_m1, vec_m1);
-        FDTD_CP_ASYNC_COMMIT();
-      }
+      if (tid == 0 && ip <= xb && ip < P.x1)
+        fused_stage_tma<T, VEC>(P, M, stages + (ip % 3) * Lay::STAGE_WORDS, bars + (ip % 3), kz0, j0, ip, zs, ip > xa);
     }
-#if FDTD_FUSED_PIPE_PSI_PREFETCH > 0
-    {
-      // psi_E of plane i + PP and psi_H of plane i + PP - 1 (the H update lags one plane), only in threads whose cells
-      // lie in a slab there: the interior pays the two x-slab range tests and nothing else
-      const int ip = i + FDTD_FUSED_PIPE_PSI_PREFETCH;
-      unsigned hpf = sl_hit;
-      for (unsigned m = xs_bits; m != 0; m &= m - 1) {
-        const int s = FDTD_FFS(m) - 1;
-        hpf |= (ip >= P.sl[s].xs && ip <= P.sl[s].xe) ? (1u << s) : 0u;
-      }
-      if (inside && active && hpf != 0) {
-        for (int s = 0; s < P.n_sl; ++s) {
-          if (!((hpf >> s) & 1u)) continue;
-          const typename FusedParams<T>::Slab& S = P.sl[s];
-          const bool yz = S.axis != 0;
-          if (ip < xb && ip < P.x1 && (yz || (ip >= S.xs && ip < S.xe))) {
-            const i64 idx = fused_psi_index<T, VEC>(S, ip, j, k0, plane, p, P.Ny, Nz);
-            fused_prefetch(S.psiE_in + idx);
-            fused_prefetch(S.psiE_in + S.count + idx);
-          }
-          const int ih = ip - 1;      // (psi_H belongs to the owner of the cell only: the halo threads never touch it)
-          if (core && ih >= xa && ih < xb && (yz || (ih >= S.xs && ih < S.xe))) {
-            const i64 idx = fused_psi_index<T, VEC>(S, ih, j, k0, plane, p, P.Ny, Nz);
-            fused_prefetch(S.psiH + idx);
-            fused_prefetch(S.psiH + S.count + idx);
-          }
-        }
-      }
-    }
-#endif
-#if FDTD_FUSED_PIPE_PREFETCH > 0 && !defined(FDTD_EMU)
-    {
-      // one prefetch per 128-byte line of the tile row (every eighth lane, and the last one: rows start unaligned)
-      const int ip = i + FDTD_FUSED_PIPE_PREFETCH;
-      if (inside && ip <= xb && ip < P.x1 && ((l & 7) == 0 || l == L)) {
-        const i64 po = (i64)ip * plane + p;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Hin[c] + po));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Ein[c] + po));
-        }
-      }
-    }
-#endif
     const T* sH = stages + (i % 3) * Lay::STAGE_WORDS;
     const T* sE = sH + Lay::H_WORDS;
     const i64 off = (i64)i * plane + p;

@@ -20,13 +20,6 @@ VARIANTS = {
     "default": [],
     # register-tiled fused E+H kernel (yee_fused_eh.cuh, FDTD_B200_FUSE_EH=2): rows per thread / warps per block /
     # blocks per SM -- time with scripts/gpu_fused_rt.sh
-    "rt_r2_w4_mb3": ["-DFDTD_FUSED_RT_ROWS=2", "-DFDTD_FUSED_RT_WARPS=4", "-DFDTD_FUSED_RT_MIN_BLOCKS=3"],
-    "rt_r2_w2_mb6": ["-DFDTD_FUSED_RT_ROWS=2", "-DFDTD_FUSED_RT_WARPS=2", "-DFDTD_FUSED_RT_MIN_BLOCKS=6"],
-    "rt_r2_w8_mb1": ["-DFDTD_FUSED_RT_ROWS=2", "-DFDTD_FUSED_RT_WARPS=8", "-DFDTD_FUSED_RT_MIN_BLOCKS=1"],
-    "rt_r3_w4_mb2": ["-DFDTD_FUSED_RT_ROWS=3", "-DFDTD_FUSED_RT_WARPS=4", "-DFDTD_FUSED_RT_MIN_BLOCKS=2"],
-    "rt_r4_w4_mb2": ["-DFDTD_FUSED_RT_ROWS=4", "-DFDTD_FUSED_RT_WARPS=4", "-DFDTD_FUSED_RT_MIN_BLOCKS=2"],
-    "rt_r4_w2_mb4": ["-DFDTD_FUSED_RT_ROWS=4", "-DFDTD_FUSED_RT_WARPS=2", "-DFDTD_FUSED_RT_MIN_BLOCKS=4"],
-    "rt_r1_w4_mb4": ["-DFDTD_FUSED_RT_ROWS=1", "-DFDTD_FUSED_RT_WARPS=4", "-DFDTD_FUSED_RT_MIN_BLOCKS=4"],
     # cp.async-pipelined fused kernel (FDTD_B200_FUSE_EH=3): tile and blocks per SM (shared memory: 3 stages + 2 tiles)
     "pipe_r4l32_mb3": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=3"],
     "pipe_r4l32_mb2": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
@@ -38,11 +31,6 @@ VARIANTS = {
     "pipe_r4l31_mb3": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=3"],
     "pipe_r4l31_mb2": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
     "pipe_r7l31_mb2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2"],
-    "fz_r4l31_mb4": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_MIN_BLOCKS=4"],
-    "pipe_r7l31_mb2_pf3": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=3"],
-    "pipe_r7l31_mb2_pf4": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=4"],
-    "pipe_r7l31_mb2_pf6": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PREFETCH=6"],
-    "pipe_cpasync": ["-DFDTD_FUSED_TMA=0"],
     # session 13: z+1 neighbour by shuffle, psi of the block's z slab staged by bulk copies
     "pipe_v2_noshfl": ["-DFDTD_FUSED_SHFL=0"],
     "pipe_v2_nopsi": ["-DFDTD_FUSED_PSI_STAGE=0"],
@@ -52,19 +40,8 @@ VARIANTS = {
     "pipe_v5_noearly": ["-DFDTD_FUSED_EARLY_XPSI=0"],
     "pipe_tma_r15l31_mb1": ["-DFDTD_FUSED_ROWS=15", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=1"],
     "pipe_tma_r3l31_mb4": ["-DFDTD_FUSED_ROWS=3", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4"],
-    "pipe_psi1": ["-DFDTD_FUSED_PIPE_PSI_PREFETCH=1"],
-    "pipe_psi2": ["-DFDTD_FUSED_PIPE_PSI_PREFETCH=2"],
-    "pipe_psi2_L2": ["-DFDTD_FUSED_PIPE_PSI_PREFETCH=2", "-DFDTD_FUSED_PIPE_PSI_LEVEL=2"],
-    "pipe_r7l31_mb2_psi0": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PSI_PREFETCH=0"],
-    "pipe_r7l31_mb2_psi2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PSI_PREFETCH=2"],
-    "pipe_r7l31_mb2_psi3": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PSI_PREFETCH=3"],
-    "pipe_r7l31_mb2_psi2L2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=2", "-DFDTD_FUSED_PIPE_PSI_PREFETCH=2", "-DFDTD_FUSED_PIPE_PSI_LEVEL=2"],
     "pipe_r15l31_mb1": ["-DFDTD_FUSED_ROWS=15", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=1"],
-    "pipe_r15l31_mb1_pf4": ["-DFDTD_FUSED_ROWS=15", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=1", "-DFDTD_FUSED_PIPE_PREFETCH=4"],
     "pipe_r3l31_mb4": ["-DFDTD_FUSED_ROWS=3", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4"],
-    "pipe_r3l31_mb4_pf4": ["-DFDTD_FUSED_ROWS=3", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_PIPE_MIN_BLOCKS=4", "-DFDTD_FUSED_PIPE_PREFETCH=4"],
-    "fz_r7l31_mb2": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_MIN_BLOCKS=2"],
-    "fz_r7l31_mb3": ["-DFDTD_FUSED_ROWS=7", "-DFDTD_FUSED_LANES=31", "-DFDTD_FUSED_MIN_BLOCKS=3"],
     "mat_mb2": ["-DFDTD_MAT_MIN_BLOCKS=2"],
     "mat_mb2_noinl": ["-DFDTD_MAT_MIN_BLOCKS=2", "-DFDTD_SPECIAL_NOINLINE=1"],
     "mat_noinl": ["-DFDTD_SPECIAL_NOINLINE=1"],
@@ -73,21 +50,6 @@ VARIANTS = {
     "nopf": ["-DFDTD_PREFETCH_PLANES=0"],
     "post_inline": ["-DFDTD_POST_INLINE=1"],
     "hdown": ["-DFDTD_H_DOWNWARD=1"],
-    "fz_pf0": ["-DFDTD_FUSED_PREFETCH=0"],
-    "fzp_r16_mb2": [],
-    "fzp_r16_mb1": ["-DFDTD_FUSED_MIN_BLOCKS=1"],
-    "fzp_r4l32_mb3": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=3"],
-    "fzp_r4l32_mb4": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=4"],
-    "fzp_r8l16_mb3": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_MIN_BLOCKS=3"],
-    "fzp_r2l32_mb5": ["-DFDTD_FUSED_ROWS=2", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=5"],
-    "fznp_r4l32_mb4": ["-DFDTD_FUSED_PIPELINE=0", "-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=4"],
-    "fz_r8": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_MIN_BLOCKS=4"],
-    "fz_r8_l32": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=2"],
-    "fz_r4_l32": ["-DFDTD_FUSED_ROWS=4", "-DFDTD_FUSED_LANES=32", "-DFDTD_FUSED_MIN_BLOCKS=4"],
-    "fz_r8_mb3": ["-DFDTD_FUSED_ROWS=8", "-DFDTD_FUSED_MIN_BLOCKS=3"],
-    "fz_pf2": ["-DFDTD_FUSED_PREFETCH=2"],
-    "fz_mb3": ["-DFDTD_FUSED_MIN_BLOCKS=3"],
-    "fz_mb3_pf2": ["-DFDTD_FUSED_MIN_BLOCKS=3", "-DFDTD_FUSED_PREFETCH=2"],
     "special_noinline": ["-DFDTD_SPECIAL_NOINLINE=1"],
     "lanes16": ["-DFDTD_MAX_LANES_Z=16"],
     "lanes8": ["-DFDTD_MAX_LANES_Z=8"],

@@ -55,20 +55,12 @@ inline void launch(dim3 grid, dim3 block, F&& body) {
 
 namespace emu {
 // ---- cooperative launch: one fiber per thread of a block, for kernels with barriers ---------------------
-struct AsyncCopy {
-  void* dst;
-  const void* src;
-};
 struct Fiber {
   ucontext_t ctx;
   std::vector<char> stack;
   bool done = false;
   dim3 tid;
   unsigned long shfl_gen = 0;
-  // cp.async emulation: copies are DEFERRED to the wait that covers their group (the latest moment the hardware
-  // may complete them), so a kernel that reads a staged value before waiting for it reads stale data here too
-  std::vector<AsyncCopy> open;
-  std::vector<std::vector<AsyncCopy>> groups;
 };
 inline thread_local ucontext_t t_sched;
 inline thread_local Fiber* t_cur = nullptr;
@@ -106,19 +98,6 @@ inline void fiber_exit() {
   if (t_bar_live > 0 && t_bar_arrived >= t_bar_live) {
     t_bar_arrived = 0;
     ++t_bar_gen;
-  }
-}
-
-inline void cp_async16(void* dst, const void* src) { t_cur->open.push_back({dst, src}); }
-inline void cp_async_commit() {
-  t_cur->groups.push_back(std::move(t_cur->open));
-  t_cur->open.clear();
-}
-inline void cp_async_wait(size_t pending) {   // cp.async.wait_group N: at most N most recent groups stay pending
-  std::vector<std::vector<AsyncCopy>>& g = t_cur->groups;
-  while (g.size() > pending) {
-    for (const AsyncCopy& c : g.front()) memcpy(c.dst, c.src, 16);
-    g.erase(g.begin());
   }
 }
 
@@ -212,8 +191,6 @@ inline void launch_coop(dim3 grid, dim3 block, F&& body) {
               Fiber& f = fibers[t];
               f.done = false;
               f.shfl_gen = 0;
-              f.open.clear();
-              f.groups.clear();
               f.tid = dim3(tx, ty, tz);
               getcontext(&f.ctx);
               f.ctx.uc_stack.ss_sp = f.stack.data();

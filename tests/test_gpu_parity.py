@@ -343,7 +343,7 @@ def test_random_scene_on_gpu(seed, dtype):
                                        ("float32", (33, 41, 148), 3)])
 def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
     """run() with the single-pass E+H kernel (grid._fuse_eh = 1: one launch per step over the whole grid, ping-pong
-    field and psi_E buffers, cp.async-staged inputs, shared-memory exchange of E_new) must reproduce the two-half-
+    field and psi_E buffers, TMA-staged inputs, shared-memory / shuffle exchange of E_new) must reproduce the two-half-
     step path bit for bit, for even and odd step counts, sources in the interior and in the slabs, detectors
     everywhere."""
     fd = cuda(dtype)
