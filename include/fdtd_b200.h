@@ -207,8 +207,9 @@ typedef struct fdtd_desc {
   int32_t fuse_eh;     /* != 0: fdtd_run may run pairs of temporally fused E+H steps -- one kernel per step that moves 12
                           instead of 18 words per cell -- on homogeneous unsharded grids without periodic boundaries,
                           with point sources on E only; needs E2 / H2 / psi_E2.  1: wherever that is legal,
-                          2: only where it is also faster than the two half-steps (y-z planes of 2 MiB per component and more, 96
-                          x-planes and more) */
+                          2: only where it is also faster than the two half-steps (y-z planes of 1.07 MiB per component and
+                          more whose z extent fills the kernel's 31-vector tiles to 85 %, 64 x-planes and more; CPML slabs of
+                          up to 32 cells in either mode) */
   int32_t pad2_;
   void* E2[3];         /* second field buffers of the ping-pong pair, same layout as E / H (ghost planes included), */
   void* H2[3];         /* or NULL; after fdtd_run the results are always in E / H */

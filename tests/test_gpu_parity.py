@@ -139,6 +139,15 @@ def test_pokes_and_rebake_on_gpu():
 # ---- full-size properties (BASELINE.json configs 1-3 sizes) -------------------------------------
 
 def _c4(fd, n, amplitude=1.0, with_source=True):
+    if not isinstance(n, int):
+        nx, ny, nz = n
+        g = fd.Grid(shape=(nx, ny, nz), grid_spacing=77.5e-9)
+        for key in ((slice(0, 10),), (slice(-10, None),), (slice(None), slice(0, 10)), (slice(None), slice(-10, None)),
+                    (slice(None), slice(None), slice(0, 10)), (slice(None), slice(None), slice(-10, None))):
+            g[key] = fd.PML()
+        g[nx // 2, ny // 2, nz // 2] = fd.PointSource(period=20, amplitude=amplitude)
+        g[nx // 2 + 4, ny // 2, 12:nz - 12] = fd.LineDetector()
+        return g
     g = fd.Grid(shape=(n, n, n), grid_spacing=77.5e-9)
     g[0:10, :, :] = fd.PML()
     g[-10:, :, :] = fd.PML()
@@ -419,8 +428,7 @@ def test_running_dft_equals_fft_of_the_record(dtype, monkeypatch):
 
 
 def test_fused_steps_are_the_default_on_large_homogeneous_grids():
-    """automatic mode (grid._fuse_eh = 2, the default): grids with y-z planes of 2 MiB per component and more run pairs
-    of single-pass steps when the second buffers fit; the result equals the two-half-step path bit for bit at that
+    """automatic mode (grid._fuse_eh = 2, the default): large grids run pairs of single-pass steps when the second buffers fit; the result equals the two-half-step path bit for bit at that
     size (float32)."""
     fd = cuda("float32")
     n = 768                              # 4.5e8 cells: 21 GiB of fields + second buffers
@@ -437,6 +445,30 @@ def test_fused_steps_are_the_default_on_large_homogeneous_grids():
     assert float(outs[0][0].abs().max()) > 0
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert np.array_equal(outs[0][2], outs[1][2])
+
+
+@pytest.mark.parametrize("dtype,shape,fused", [("float32", (64, 1024, 1024), True), ("float32", (64, 576, 576), True),
+                                               ("float32", (64, 512, 512), False),       # plane below 1.07 MiB
+                                               ("float32", (64, 1024, 520), False),      # 4.19 z tiles: fill 0.84
+                                               ("float32", (48, 1024, 1024), False),     # march too short
+                                               ("float64", (64, 384, 384), True), ("float64", (64, 256, 256), False)])
+def test_automatic_mode_of_the_fused_steps_by_grid_shape(dtype, shape, fused):
+    """grid._fuse_eh = 2 (the default): the host layer (which allocates the second buffers) and the library (which
+    launches) apply the same test -- plane size, z-tile fill, march length (profiles/r2_s14/fused_sizes.log) -- and the
+    fused steps give the two half-steps' result bit for bit wherever they are chosen."""
+    fd = cuda(dtype)
+    outs = []
+    for fuse in (2, 0):
+        g = _c4(fd, shape)
+        g._fuse_eh = fuse
+        g.run(7, progress_bar=False)
+        active = g._engine.lib.fdtd_fuse_eh_active(g._engine.desc) == 1
+        assert active == (fused and fuse == 2)
+        assert (g._E2 is not None) == active          # no second buffers where they are not used
+        outs.append((g.E.clone(), g.H.clone()))
+        del g
+    assert float(outs[0][0].abs().max()) > 0
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
 def test_energy_slice_and_visualize_on_the_device(monkeypatch):
