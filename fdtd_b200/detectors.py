@@ -65,6 +65,7 @@ class _Detector:
             self._rank_positions = [np.nonzero((gx >= part.bounds(r)[0]) & (gx < part.bounds(r)[1]))[0]
                                     for r in range(part.world)]
         # points of the rank that holds most of them: what every rank sizes the ring capacity with
+        self._rank_pos_dev = None
         self._n_ring = max(len(p) for p in self._rank_positions) if part.sharded else self._n_local
 
     def _ensure_ring(self, capacity):
@@ -149,29 +150,48 @@ class _Detector:
         return self.spectrum("H")
 
     def _drain(self, nE, nH):
-        """copy the filled part of the rings to the host (one batch) and assemble global samples."""
+        """copy the filled part of the rings to the host (one batch) and assemble global samples.
+
+        x-sharded grids: ONE all_gather carries the rows of both fields (padded to the rank that holds most points),
+        the global samples are assembled on the device and only they cross to the host -- not the padding of every
+        rank."""
         part = self.grid._part
-        for f, ring, n in (("E", self._ring_E, nE), ("H", self._ring_H, nH)):
-            if n == 0 or f not in self._chunks:
-                continue
+        todo = [(f, ring, n) for f, ring, n in (("E", self._ring_E, nE), ("H", self._ring_H, nH))
+                if n and f in self._chunks]
+        for f, ring, n in todo:
             if self._dft_freqs is not None:
                 self._accumulate(f, ring, n)
             self._n_seen[f] += n
-            if not self._keep_trace:
-                continue
-            if part.sharded:
-                n_max = max(1, max(len(p) for p in self._rank_positions))
-                send = ring.new_zeros((n, n_max, self._width))
-                send[:, :self._n_local] = ring[:n, :self._n_local]
-                recv = [torch.empty_like(send) for _ in range(part.world)]
-                dist.all_gather(recv, send)
-                recv = torch.stack(recv).to("cpu").numpy()
-                full = np.zeros((n, self._n_points, self._width), dtype=recv.dtype)
-                for r, pos in enumerate(self._rank_positions):
-                    full[:, pos] = recv[r, :, :len(pos)]
-            else:
-                full = ring[:n, :self._n_local].to("cpu", copy=True).numpy()
-            tail = (self._width,) if self._width > 1 else ()
+        if not self._keep_trace or not todo:
+            return
+        tail = (self._width,) if self._width > 1 else ()
+        if part.sharded:
+            n_max = max(1, max(len(p) for p in self._rank_positions))
+            rows = sum(n for _, _, n in todo)
+            ring0 = todo[0][1]
+            send = ring0.new_zeros((rows, n_max, self._width))
+            at = 0
+            for _, ring, n in todo:
+                send[at:at + n, :self._n_local] = ring[:n, :self._n_local]
+                at += n
+            recv = [torch.empty_like(send) for _ in range(part.world)]
+            dist.all_gather(recv, send)
+            if getattr(self, "_rank_pos_dev", None) is None:
+                self._rank_pos_dev = [torch.as_tensor(np.asarray(pos, dtype=np.int64), device=send.device)
+                                      for pos in self._rank_positions]
+            full = send.new_zeros((rows, self._n_points, self._width))
+            for r, pos in enumerate(self._rank_pos_dev):
+                if pos.numel():
+                    full[:, pos] = recv[r][:, :pos.numel()]
+            full = full.to("cpu").numpy()
+            at = 0
+            for f, _, n in todo:
+                self._chunks[f].append(full[at:at + n].reshape((n,) + self._sample_shape + tail))
+                self._lists[f] = None
+                at += n
+            return
+        for f, ring, n in todo:
+            full = ring[:n, :self._n_local].to("cpu", copy=True).numpy()
             self._chunks[f].append(full.reshape((n,) + self._sample_shape + tail))
             self._lists[f] = None
 
