@@ -926,20 +926,6 @@ bool fuse_eh_eligible(const fdtd_desc* d, bool sharded = false) {
 #endif
 }
 
-int sm_count() {
-#ifdef FDTD_EMU
-  return 148;
-#else
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
-#endif
-}
-
 // tensor maps of the three components of one field buffer for the fused kernel's staging: a 3-D tensor
 // [Nx + 2][Ny][Nz] per component (the ghost x-planes belong to it), box = (bz x by x 1 plane)
 template <typename T>
@@ -1074,25 +1060,43 @@ int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void*
   }
   P.x0 = 0; P.x1 = Nx; P.y0 = 0; P.y1 = Ny; P.z0 = 0; P.z1 = Nz;
   P.psi_stage = 1;
-  // planes marched per block: ~48 (1024^3 f32: 10.97 / 10.77 / 10.68 / 10.84 ms per step at 16 / 32 / 48 / 64,
-  // profiles/r2_fused_tma.txt), in chunks of equal length
-  // On thin slabs what counts is how the blocks fill the GPU: the number of chunks that minimises
-  // (waves of blocks) x (chunk length + start-up), two resident blocks per SM (128 planes on one of eight GPUs: four
-  // chunks of 32 = 17.9 waves instead of three of 43 = 13.4).
-  if (d->x_chunk > 0) {
-    P.x_chunk = d->x_chunk;
-  } else {
-    const int64_t tiles = (int64_t)((Nz + fdtd::FUSED_L * VEC - 1) / (fdtd::FUSED_L * VEC)) * ((Ny + fdtd::FUSED_R - 1) / fdtd::FUSED_R);
-    const int64_t slots = 2 * (int64_t)sm_count();
-    int best_c = (Nx + 47) / 48;
-    int64_t best_cost = -1;
-    for (int c = (Nx + 51) / 52; c <= (Nx + 27) / 28; ++c) {
-      if (c < 1) continue;
-      const int len = (Nx + c - 1) / c;
-      const int64_t cost = ((tiles * c + slots - 1) / slots) * (len + 2);
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
+  // The march along x is cut into chunks of ~40 planes (1024^3 f32: 9.99 / 9.95 / 9.90 / 9.92 / 9.90 / 10.01 ms per step
+  // at 24 / 32 / 36 / 40 / 44 / 49 planes, profiles/r2_s19/): every chunk costs a pipeline fill and one extra E plane,
+  // and the blocks that run last finish with the GPU half empty -- so ONE chunk is only about half as long as the
+  // others and its blocks are launched last (128 planes: 37+37+37+17 runs 3 % faster than 4 x 32).  On an x-sharded slab
+  // the first and the last chunk run first (fused_sharded_step): the short chunk is the second to last there, the end
+  // of what the caller's stream runs.  grid._x_chunk / desc.x_chunk > 0: chunks of exactly that length.
+  const bool split = shard && shard->part != 0;
+  int n_chunks = 0;
+  {
+    const int cap = FDTD_FUSED_MAX_CHUNKS;
+    int len, c, short_at = -1, short_len = 0;
+    if (d->x_chunk > 0) {
+      len = d->x_chunk;
+      if ((Nx + len - 1) / len > cap) len = (Nx + cap - 1) / cap;
+      c = (Nx + len - 1) / len;
+    } else {
+#ifdef FDTD_EMU
+      const double target = 5.0;                     // (CPU tests: small grids get several chunks, too)
+#else
+      const double target = 40.0;
+#endif
+      c = (int)((double)Nx / target + 0.999);        // chunks of ~40 planes, one of them half as long
+      if (c > cap) c = cap;
+      if (c < 1) c = 1;
+      len = c > 1 ? (int)((double)Nx / (c - 0.5) + 0.999) : Nx;
+      while (c > 1 && (c - 1) * len >= Nx) --len;    // (the short chunk must not be empty)
+      short_len = Nx - (c - 1) * len;
+      short_at = (split && c >= 3) ? c - 2 : c - 1;
     }
-    P.x_chunk = (Nx + best_c - 1) / best_c;
+    int x = 0;
+    for (int k = 0; k < c; ++k) {
+      P.xstart[k] = x;
+      x += (k == short_at) ? short_len : len;
+      if (x > Nx) x = Nx;
+    }
+    P.xstart[c] = Nx;
+    n_chunks = c;
   }
   for (int c = 0; c < 3; ++c) {
     P.Ein[c] = (const T*)Ein[c];
@@ -1126,7 +1130,7 @@ int fused_eh_step(const fdtd_desc* d, void* const* Ein, void* const* Eout, void*
     if (S.axis == 2 && !(aligned(K.psiE_in, 16) && aligned(K.psiH, 16))) P.psi_stage = 0;
   }
   using Lay = fdtd::FusedPipeLayout<T, VEC>;
-  const int chunks = (Nx + P.x_chunk - 1) / P.x_chunk;
+  const int chunks = n_chunks;
   int launch_chunks = chunks;
   P.chunk0 = 0;
   P.chunk_step = 1;

@@ -25,13 +25,19 @@
 
 namespace fdtd {
 
+#ifndef FDTD_FUSED_MAX_CHUNKS
+#define FDTD_FUSED_MAX_CHUNKS 64     // x-chunks per launch (kernel parameter space)
+#endif
+
 template <typename T>
 struct FusedParams {
   int Ny, Nz;
   i64 plane;
   int x0, x1, y0, y1, z0, z1;  // interior box (cells); z0, z1 multiples of the vector width
-  int x_chunk;
-  int chunk0, chunk_step;      // block z handles x-chunk chunk0 + z * chunk_step (a launch may cover a subset of the chunks)
+  // the march along x is cut into chunks [xstart[k], xstart[k+1]); block z handles chunk chunk0 + z * chunk_step (a launch
+  // may cover a subset of the chunks)
+  int chunk0, chunk_step;
+  int xstart[FDTD_FUSED_MAX_CHUNKS + 1];
   const T* Ein[3];
   T* Eout[3];
   const T* Hin[3];
@@ -357,8 +363,8 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
   const bool inside = (j < P.y1) && (k0 < P.z1);
   const i64 plane = P.plane;
   const i64 p = (i64)j * Nz + k0;
-  const int xa = P.x0 + (P.chunk0 + (int)blockIdx.z * P.chunk_step) * P.x_chunk;
-  const int xb = (xa + P.x_chunk < P.x1) ? xa + P.x_chunk : P.x1;
+  const int xa = P.xstart[P.chunk0 + (int)blockIdx.z * P.chunk_step];
+  const int xb = P.xstart[P.chunk0 + (int)blockIdx.z * P.chunk_step + 1];
 
   bool src_yz = false;
   for (int s = 0; s < P.n_src; ++s)
@@ -444,7 +450,9 @@ __global__ void __launch_bounds__((FUSED_R + 1) * (FUSED_L + 1), FDTD_FUSED_PIPE
     // (tried: the barrier split into an mbarrier arrival after the publish below and a wait between the next E and H
     // updates, so that warps may drift by one E update: 10.15 instead of 10.00 ms per step, profiles/r2_s14/; an L2
     // prefetch of the tiles 3 / 4 / 6 planes ahead by cp.async.bulk.prefetch.tensor: 10.80 / 11.19 / 12.27 ms against
-    // 9.98, profiles/r2_s15/ -- the kernel waits for DRAM at 5.7 TB/s, more requests in flight only queue longer)
+    // 9.98, profiles/r2_s15/ -- the kernel waits for DRAM at 5.7 TB/s, more requests in flight only queue longer;
+    // evict-first stores (st.global.cs) of E_new / H_new / psi: 10.09 against 10.00, DRAM reads 29.77 instead of 29.97 GB,
+    // profiles/r2_s18/)
     __syncthreads();
     {
       const int ip = i + 2;

@@ -365,7 +365,7 @@ def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t, zp, monkeypatc
     outs = []
     # (split: the step as two launches -- first and last x-chunk, then the ones in between -- as an x-sharded slab
     # runs them on two streams)
-    variants = [(0, 0, "0"), (1, 0, "0"), (1, 4, "0"), (1, 3, "1")]
+    variants = [(0, 0, "0"), (1, 0, "0"), (1, 4, "0"), (1, 3, "1"), (1, 0, "1")]     # (chunk 0: the library's choice)
     if zp in ("lo", "hi"):
         variants += [(1, 1, "0"), (1, 4, "1")]
     for fuse, chunk, split in variants:
