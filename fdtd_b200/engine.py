@@ -30,6 +30,7 @@ GRAPH_MAX_CELLS = 1 << 25      # grids up to this many cells replay CUDA graphs 
 FUSE_EH_MIN_PLANE_BYTES = 1100 << 10  # y-z plane of one component
 FUSE_EH_MIN_PLANES = 64               # x-planes (unsharded)
 FUSE_EH_MIN_Z_FILL = 0.85             # Nz / (z tiles of 31 vectors x their length)
+FUSE_EH_MAX_PML = 32                  # cells per CPML slab (the fused kernel keeps the tables in shared memory)
 FUSE_EH_MIN_SLAB = 96                 # x-planes per rank (x-sharded; 128 planes per rank: 1.41 against 1.64 ms per step, profiles/r2_n2c/)
 
 
@@ -306,6 +307,7 @@ class Engine:
                and (g.Nx // part.world >= FUSE_EH_MIN_SLAB if part.sharded else g.Nx >= FUSE_EH_MIN_PLANES))
         ok = bool(want and not self._hooked and ie_eff is None and imu is None and not post and not x_wrap
                   and g._sdtype is g._dtype and (want == 1 or big)
+                  and all(b.thickness <= FUSE_EH_MAX_PML for b in slabs)
                   and all(d.sources[k].kind == _capi.SRC_POINTS and d.sources[k].field == 0 for k in range(d.n_sources))
                   and all(det._kind == _capi.DET_FIELD for det in self._dets) and d.n_sources <= _capi.FUSED_MAX)
         if part.sharded:

@@ -399,7 +399,7 @@ def test_fused_steps_refuse_slabs_thicker_than_their_table_space():
         return g
 
     a, b = build(1), build(0)
-    assert a._engine.lib.fdtd_fuse_eh_active(a._engine.desc) == 0
+    assert a._engine.lib.fdtd_fuse_eh_active(a._engine.desc) == 0 and a._E2 is None      # (no second buffers either)
     compare(scenes.dump(a), scenes.dump(b), 0.0, bitwise=True)
     c = fd.Grid(shape=(70, 9, 8), grid_spacing=77.5e-9)
     c[0:32, :, :] = fd.PML()
