@@ -118,3 +118,49 @@ def random_scene(seed):
 
     steps = int(rs.randint(12, 30))
     return build, steps
+
+
+def random_fused_scene(seed, large=False):
+    """Seeded random scenes the single-pass E+H kernel is eligible for: homogeneous background (scalar materials),
+    any subset of the six PML faces with their own thicknesses in random registration order, point / line sources on
+    E anywhere (interior, slabs, faces), line / block detectors; z extents around the kernel's tile length (31 vectors
+    of 4 float32 / 2 float64 cells), so that slabs start at, before and after tile and halo-lane boundaries.
+    `large`: extents the library accepts for the kernel on a real GPU (at least 8 x 8 x 32 vectors).
+    Returns (build, steps, x_chunk, split): the chunking and whether the step runs as the two launches of a slab."""
+    r0 = np.random.RandomState(1000 + seed)
+    steps = int(r0.randint(5, 12))
+    x_chunk = int(r0.choice([0, 0, 1, 2, 3, 5, 7]))
+    split = bool(r0.randint(0, 2))
+
+    def build(fd):
+        r = np.random.RandomState(seed)
+        nz = int(r.choice([int(r.randint(8, 40)), 62, 64, 66, 124, 126, 128, 132, int(r.randint(120, 150))]))
+        nz -= nz % 4                                        # (the fused kernel wants whole vectors along z)
+        n = (int(r.randint(4, 24)), int(r.randint(3, 20)), max(8, nz))
+        if large:
+            n = (int(r.randint(8, 60)), int(r.randint(8, 40)), int(r.choice([128, 132, 136, 160, 244, 248, 252, 256, 300])))
+        g = fd.Grid(shape=n, grid_spacing=float(60e-9 * (1 + r.rand())), permittivity=float(1 + r.rand()),
+                    permeability=float(1 + 0.3 * r.rand()))
+        faces = [(a, side) for a in range(3) for side in (0, 1) if r.rand() < 0.7]
+        r.shuffle(faces)
+        for a, side in faces:
+            t = int(r.randint(1, max(2, min(n[a] // 2 - 1, 18 if a == 2 else 6))))
+            if t >= n[a] // 2:
+                continue
+            key = [slice(None)] * 3
+            key[a] = slice(0, t) if side == 0 else slice(-t, None)
+            g[tuple(key)] = fd.PML()
+        for k in range(int(r.randint(1, 5))):
+            p = [int(r.randint(0, n[a])) for a in range(3)]
+            g[p[0], p[1], p[2]] = fd.PointSource(period=int(r.randint(5, 30)), amplitude=float(0.2 + r.rand()),
+                                                 name=f"p{k}")
+        if n[0] > 6 and r.rand() < 0.6:
+            y, z = int(r.randint(0, n[1])), int(r.randint(0, n[2]))
+            g[1:n[0] - 1, y, z] = fd.LineSource(period=int(r.randint(7, 25)), name="line")
+        y, z = int(r.randint(0, n[1])), int(r.randint(0, n[2]))
+        g[0:n[0], y, z] = fd.LineDetector(name="across")
+        x, y = int(r.randint(0, n[0] - 1)), int(r.randint(0, n[1] - 2))      # (BlockDetector ranges include `stop`)
+        g[x:x + 1, y:y + 1, n[2] - 3:n[2] - 2] = fd.BlockDetector(name="block")
+        return g
+
+    return build, steps, x_chunk, split

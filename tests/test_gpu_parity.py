@@ -348,6 +348,32 @@ def test_random_scene_on_gpu(seed, dtype):
     compare(got, want, TOL[dtype], bitwise=True)
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("seed", range(300, 312))
+def test_random_fused_scene_on_gpu(seed, dtype, monkeypatch):
+    """the single-pass E+H kernel against the two half-steps on random eligible scenes (tests/fuzz_scenes.py: any
+    subset of PML faces and thicknesses in any order, sources and detectors anywhere, z extents around the tile length,
+    random x-chunking, the step as one launch or as the two launches of a slab): bit-identical on the device."""
+    from fuzz_scenes import random_fused_scene
+    build, steps, x_chunk, split = random_fused_scene(seed, large=True)
+    fd = cuda(dtype)
+    outs = []
+    for fuse in (1, 0):
+        monkeypatch.setenv("FDTD_B200_FUSE_SPLIT_TEST", "1" if (fuse and split) else "0")
+        g = build(fd)
+        g._fuse_eh = fuse
+        g._x_chunk = x_chunk
+        g.run(steps, progress_bar=False)
+        g.step()
+        g.run(2, progress_bar=False)
+        assert bool(g._engine.lib.fdtd_fuse_eh_active(g._engine.desc)) == bool(fuse), "the scene must be eligible"
+        outs.append(scenes.dump(g))
+    monkeypatch.delenv("FDTD_B200_FUSE_SPLIT_TEST")
+    assert float(np.abs(outs[1]["E"]).max()) > 0
+    for k in outs[1]:
+        assert np.array_equal(outs[0][k], outs[1][k]), f"seed {seed} {k}: rel-L2 {scenes.rel_l2(outs[0][k], outs[1][k]):.3e}"
+
+
 @pytest.mark.parametrize("dtype,n,t", [("float32", (72, 64, 192), 6), ("float64", (40, 52, 100), 5),
                                        ("float32", (33, 41, 148), 3)])
 def test_temporally_fused_steps_equal_two_half_steps(dtype, n, t):
